@@ -1,0 +1,257 @@
+/*
+ * rwgpu.h -- C ABI of the B200-native streaming HashAgg / HashJoin / hash-shuffle path.
+ *
+ * The reference (risingwavelabs/risingwave) has NO extern "C" surface on this path: the
+ * operators are Rust types behind `trait Execute` (src/stream/src/executor/mod.rs:240-253)
+ * built by `ExecutorBuilder::new_boxed_executor` (src/stream/src/from_proto/mod.rs:131-140).
+ * This header is therefore what a thin Rust shim (`GpuHashAggExecutor` / `GpuHashJoinExecutor`,
+ * see INTEGRATION.md) binds with `extern "C"`; every entry point cites the reference
+ * function whose work it replaces.
+ *
+ * Conventions
+ *  - every function returns an int32 status (RW_OK == 0); `rwgpu_last_error()` gives a
+ *    thread-local message.  No exceptions / longjmp cross the boundary.
+ *  - a handle is single-owner (one actor == one tokio task polls it; actor.rs:272); different
+ *    handles may be used concurrently from different threads.
+ *  - input chunks are BORROWED for the duration of the call; output objects are LIBRARY-OWNED
+ *    until `rwgpu_out_release`.
+ *  - all layouts are little-endian; bitmaps are uint64 words, LSB first
+ *    (bit i = words[i/64] >> (i%64) & 1, src/common/src/bitmap.rs:363-369); a NULL bitmap
+ *    pointer means "all ones" (Bitmap.bits == None, bitmap.rs:220-224).
+ */
+#ifndef RWGPU_H_
+#define RWGPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- status codes */
+#define RW_OK 0
+#define RW_ERR_INVALID 1       /* bad argument / malformed descriptor                          */
+#define RW_ERR_UNSUPPORTED 2   /* plan shape not offloadable: shim falls back to CPU executor */
+#define RW_ERR_OOM 3
+#define RW_ERR_NUMERIC_OUT_OF_RANGE 4 /* ExprError::NumericOutOfRange (general.rs:32-40)       */
+#define RW_ERR_INCONSISTENT 5  /* strict-consistency violation (src/stream/src/lib.rs:58-127)  */
+#define RW_ERR_CUDA 6
+#define RW_ERR_NO_DEVICE 7
+
+/* ---------------------------------------------------------------- Op (stream_chunk.rs:84-91, to_i16) */
+#define RW_OP_INSERT 1
+#define RW_OP_DELETE 2
+#define RW_OP_UPDATE_INSERT 3
+#define RW_OP_UPDATE_DELETE 4
+
+/* ---------------------------------------------------------------- column types (fixed width only;
+ * varlen keys are `KeySerialized` in the reference and stay on the CPU executor) */
+#define RW_T_BOOL 1        /* 1 byte / row (BoolArray bit-unpacked by the shim)         */
+#define RW_T_INT16 2
+#define RW_T_INT32 3
+#define RW_T_INT64 4
+#define RW_T_FLOAT32 5
+#define RW_T_FLOAT64 6
+#define RW_T_DATE 7        /* int32 days                                               */
+#define RW_T_TIME 8        /* int64 microseconds                                       */
+#define RW_T_TIMESTAMP 9   /* int64 microseconds since epoch                           */
+#define RW_T_TIMESTAMPTZ 10/* int64 microseconds                                       */
+#define RW_T_SERIAL 11     /* int64 row id                                             */
+#define RW_T_DECIMAL 12    /* 16 bytes: little-endian two's-complement i128 mantissa,
+                              scale fixed per column by agreement          */
+
+/* width in bytes of one value of `type`, 0 if unknown */
+int32_t rwgpu_type_width(int32_t type);
+
+/* ---------------------------------------------------------------- StreamChunk view
+ * mirrors StreamChunk{ops, DataChunk{columns, visibility}} (stream_chunk.rs:106-110,
+ * data_chunk.rs:65-68) and PrimitiveArray{bitmap,data} (primitive_array.rs:137-140). */
+typedef struct rw_column {
+  int32_t type;              /* RW_T_*                                                  */
+  int32_t reserved;
+  const void* data;          /* n_rows * width bytes; NULL slots hold any value         */
+  const uint64_t* validity;  /* 1 = non-NULL; NULL pointer = no NULLs                   */
+} rw_column;
+
+typedef struct rw_chunk {
+  int64_t n_rows;            /* capacity(): rows incl. invisible ones                   */
+  int32_t n_cols;
+  int32_t reserved;
+  const uint8_t* ops;        /* RW_OP_* per row                                         */
+  const uint64_t* visibility;/* NULL = all visible                                      */
+  const rw_column* columns;
+} rw_chunk;
+
+/* ---------------------------------------------------------------- output object */
+typedef struct rwgpu_out rwgpu_out;
+/* number of StreamChunks produced by the call that returned `out` (0 is legal). */
+int32_t rwgpu_out_num_chunks(const rwgpu_out* out);
+/* total rows (capacity) over all chunks. */
+int64_t rwgpu_out_num_rows(const rwgpu_out* out);
+/* fill `view` with host pointers valid until rwgpu_out_release(out). */
+int32_t rwgpu_out_chunk(const rwgpu_out* out, int32_t idx, rw_chunk* view);
+void rwgpu_out_release(rwgpu_out* out);
+
+/* ================================================================ HashAgg ===================
+ * replaces HashAggExecutor (src/stream/src/executor/aggregate/hash_agg.rs):
+ *   rwgpu_agg_push   <-> apply_chunk            hash_agg.rs:332-409
+ *   rwgpu_agg_flush  <-> flush_data at barrier  hash_agg.rs:412-514, 651-676
+ * Only value-state calls are offloaded (agg_state.rs:49-56): count, sum, and min/max on
+ * append-only input.  Others => RW_ERR_UNSUPPORTED.                           */
+#define RW_AGG_COUNT 1     /* count(*) when arg_col < 0, else count(col)   general.rs:155-162 */
+#define RW_AGG_SUM 2       /* general.rs:28-41                                                 */
+#define RW_AGG_MIN 3       /* general.rs:91-108 (append-only)                                  */
+#define RW_AGG_MAX 4       /* general.rs:110-125 (append-only)                                 */
+#define RW_AGG_SUM0 5      /* sum0(int8)->int8, init 0     general.rs:28                      */
+
+typedef struct rw_agg_call {
+  int32_t kind;       /* RW_AGG_*                                                        */
+  int32_t arg_col;    /* input column index, -1 for count(*)                             */
+  int32_t ret_type;   /* RW_T_*: sum(int2|int4)->INT64, sum(int8)->DECIMAL (scale 0) or the
+                         internal sum(int8)->INT64 form; sum(float)->same float; count->INT64;
+                         min/max -> arg type                                             */
+  int32_t reserved;
+} rw_agg_call;
+
+typedef struct rw_agg_desc {
+  int32_t n_input_cols;
+  const int32_t* input_types;       /* RW_T_* per input column                            */
+  int32_t n_group_keys;
+  const int32_t* group_key_indices; /* hash_agg.rs:338                                    */
+  int32_t n_calls;
+  const rw_agg_call* calls;
+  int32_t row_count_index;          /* index into calls of the count(*) used by
+                                       OnlyOutputIfHasInput (agg_group.rs:131-166)        */
+  int32_t is_append_only;           /* input has no Delete/UpdateDelete                   */
+  int32_t chunk_size;               /* output chunk rows (config/mod.rs:213-215)          */
+  int32_t strict_consistency;       /* 1: negative row count => RW_ERR_INCONSISTENT
+                                       (agg_group.rs:55-79); 0: clamp to 0               */
+  uint64_t group_capacity_hint;     /* expected distinct groups (table grows on demand)   */
+} rw_agg_desc;
+
+typedef struct rwgpu_agg rwgpu_agg;
+
+int32_t rwgpu_agg_create(const rw_agg_desc* desc, rwgpu_agg** out_handle);
+void rwgpu_agg_destroy(rwgpu_agg* h);
+/* HOST chunk: staged into pinned memory, copied H2D and applied asynchronously on the handle's
+ * stream; rows are coalesced across calls into one device batch until flush. */
+int32_t rwgpu_agg_push(rwgpu_agg* h, const rw_chunk* chunk);
+/* DEVICE chunk: every pointer inside `chunk` (ops, visibility, column data/validity) is a device
+ * pointer; the rw_chunk/rw_column structs themselves are host memory.  The kernel is enqueued on
+ * `cuda_stream` (a cudaStream_t; NULL = the handle's own stream) and the call does not sync.  */
+int32_t rwgpu_agg_push_device(rwgpu_agg* h, const rw_chunk* chunk, void* cuda_stream);
+/* barrier: emit one +, - or U-/U+ pair per changed group, outputs copied to host. */
+int32_t rwgpu_agg_flush(rwgpu_agg* h, uint64_t epoch, rwgpu_out** out);
+/* barrier with the delta left in HBM: `view` receives DEVICE pointers to one un-cut chunk
+ * (valid until the next flush on this handle); *n_rows is read back (one 8-byte D2H).       */
+int32_t rwgpu_agg_flush_device(rwgpu_agg* h, uint64_t epoch, rw_chunk* view, void* cuda_stream);
+/* number of groups currently held / table capacity (diagnostics, join_cached_entry_count-like) */
+int32_t rwgpu_agg_stats(rwgpu_agg* h, uint64_t* n_groups, uint64_t* capacity, uint64_t* kernel_launches);
+
+/* ================================================================ HashJoin ==================
+ * replaces HashJoinExecutor (src/stream/src/executor/hash_join.rs):
+ *   rwgpu_join_push    <-> eq_join_oneside::<SIDE>   hash_join.rs:925-1062 (+1072-1357)
+ *   rwgpu_join_barrier <-> flush_data / commit       hash_join.rs:754-766                     */
+#define RW_JOIN_INNER 0
+#define RW_JOIN_LEFT_OUTER 1
+#define RW_JOIN_RIGHT_OUTER 2
+#define RW_JOIN_FULL_OUTER 3
+#define RW_JOIN_LEFT_SEMI 4
+#define RW_JOIN_LEFT_ANTI 5
+#define RW_JOIN_RIGHT_SEMI 6
+#define RW_JOIN_RIGHT_ANTI 7
+
+#define RW_SIDE_LEFT 0
+#define RW_SIDE_RIGHT 1
+
+/* restricted non-equi condition: `concat_row[lhs] <cmp> concat_row[rhs]` over the
+ * (left cols || right cols) row, both integer-typed; anything richer stays on the CPU
+ * executor (hash_join.rs:1362-1384 evaluates a general expression).                           */
+#define RW_CMP_NONE 0
+#define RW_CMP_LT 1
+#define RW_CMP_LE 2
+#define RW_CMP_GT 3
+#define RW_CMP_GE 4
+#define RW_CMP_EQ 5
+#define RW_CMP_NE 6
+typedef struct rw_join_cond {
+  int32_t cmp;   /* RW_CMP_*                                       */
+  int32_t lhs;   /* index into left||right concatenated columns    */
+  int32_t rhs;
+  int32_t reserved;
+} rw_join_cond;
+
+typedef struct rw_join_side_desc {
+  int32_t n_cols;
+  const int32_t* types;             /* RW_T_* per input column                               */
+  const int32_t* key_indices;       /* JoinParams.join_key_indices (hash_join.rs:75-89)      */
+  int32_t n_pk;
+  const int32_t* pk_indices;        /* JoinParams.deduped_pk_indices                         */
+  int32_t n_stream_key;
+  const int32_t* stream_key;        /* input.stream_key(): decides pk_contained_in_jk
+                                       (hash_join.rs:377-381)                               */
+  uint64_t row_capacity_hint;
+} rw_join_side_desc;
+
+typedef struct rw_join_desc {
+  int32_t join_type;                /* RW_JOIN_*  (join/mod.rs:43-52)                        */
+  int32_t n_keys;
+  rw_join_side_desc left, right;
+  const uint8_t* null_safe;         /* n_keys flags, IS NOT DISTINCT FROM (stream_plan.proto:639) */
+  int32_t n_output;
+  const int32_t* output_indices;    /* projection of the natural output (hash_join.rs:337-359) */
+  rw_join_cond cond;                /* cmp == RW_CMP_NONE => no condition                    */
+  int32_t is_append_only;           /* enables append_only_optimize when pk ⊆ jk both sides  */
+  int32_t chunk_size;               /* output chunk rows, clamped to >= 2 (join/builder.rs:44-47) */
+  int32_t strict_consistency;
+  int32_t reserved;
+} rw_join_desc;
+
+typedef struct rwgpu_join rwgpu_join;
+
+int32_t rwgpu_join_create(const rw_join_desc* desc, rwgpu_join** out_handle);
+void rwgpu_join_destroy(rwgpu_join* h);
+/* HOST chunk from `side`; `out` receives 0..k output chunks (host buffers). */
+int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* chunk, rwgpu_out** out);
+/* DEVICE chunk; output left in HBM as one un-cut chunk `view` (device pointers, valid until the
+ * next push on this handle).  *view.n_rows is read back (one 8-byte D2H).                    */
+int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* chunk, rw_chunk* view,
+                               void* cuda_stream);
+int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t epoch);
+int32_t rwgpu_join_stats(rwgpu_join* h, uint64_t* left_rows, uint64_t* right_rows,
+                         uint64_t* kernel_launches);
+
+/* ================================================================ hash shuffle ==============
+ * replaces VirtualNode::compute_chunk (src/common/src/hash/consistent_hash/vnode.rs:151-182)
+ * and the routing half of HashDataDispatcher::dispatch_data (src/stream/src/executor/
+ * dispatch.rs:961-1053).  vnode = crc32(IEEE, bytes of key datums) % vnode_count.             */
+/* HOST: vnode per row (invisible rows still get a value, as in the reference).               */
+int32_t rwgpu_vnode_compute(const rw_chunk* chunk, const int32_t* key_indices, int32_t n_keys,
+                            int32_t vnode_count, uint16_t* out_vnodes);
+/* HOST: the op rewrite of dispatch.rs:1001-1019 (U-/U+ whose dist key changed -> -/+).       */
+int32_t rwgpu_dispatch_rewrite_ops(const rw_chunk* chunk, const int32_t* key_indices, int32_t n_keys,
+                                   uint8_t* out_ops);
+/* DEVICE: partition the visible rows of a device chunk by destination
+ *   dest = vnode_to_dest[vnode]   (vnode_to_dest: DEVICE array of vnode_count int32)
+ * into per-destination contiguous regions of caller-provided DEVICE output columns
+ * (same types as input; capacity n_rows each), ops included; counts[n_dest] / offsets[n_dest]
+ * are DEVICE int64 arrays.  This is the send-side of the NCCL all-to-all-v that replaces the
+ * Dispatch/Exchange pair for the hash-shuffle path.                                          */
+int32_t rwgpu_shuffle_partition_device(const rw_chunk* chunk, const int32_t* key_indices,
+                                       int32_t n_keys, int32_t vnode_count,
+                                       const int32_t* vnode_to_dest, int32_t n_dest,
+                                       uint8_t* out_ops, void* const* out_cols,
+                                       uint8_t* const* out_valid_bytes, /* 1 byte/row, may be NULL */
+                                       int64_t* counts, int64_t* offsets, void* cuda_stream);
+
+/* ================================================================ misc */
+const char* rwgpu_last_error(void);
+/* 0 if a CUDA device is usable, else RW_ERR_NO_DEVICE (and every create() fails loudly). */
+int32_t rwgpu_device_check(void);
+/* "rwgpu <version> sm_100a" */
+const char* rwgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RWGPU_H_ */

@@ -1,0 +1,434 @@
+"""Host-side mirror of the reference's executor interface for the HashAgg / HashJoin path.
+
+Reference surface being mirrored (Rust, cannot be compiled here):
+  * `trait Execute { fn execute(self: Box<Self>) -> BoxedMessageStream }`  src/stream/src/executor/mod.rs:240-253
+  * `Message = Chunk | Barrier | Watermark`                                 mod.rs:1283-1299
+  * `HashAggExecutor`   src/stream/src/executor/aggregate/hash_agg.rs (execute_inner :561-706)
+  * `HashJoinExecutor`  src/stream/src/executor/hash_join.rs (into_stream :582-751)
+  * `barrier_align`     src/stream/src/executor/barrier_align.rs:44-165
+  * test harness `MockSource` / `MessageSender` / `StreamExecutorTestExt`
+    src/stream/src/executor/test_utils/{mock_source.rs:16-137, mod.rs:61-124}
+
+This file is the *driver* used by tests / bench; the production drop-in is the Rust shim shown in
+INTEGRATION.md which forwards to the same C ABI (include/rwgpu.h).  All compute happens behind the
+`Backend` (a ctypes view of a shared library exporting the rwgpu ABI); the product constructs
+`Backend.cuda()`, which loads librwgpu.so and fails loudly if it is absent.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from collections import deque
+from dataclasses import dataclass, field
+from typing import Deque, Iterator, List, Optional, Sequence, Tuple
+
+from . import abi
+from .stream_chunk import StreamChunk
+
+
+# =============================================================================== Backend
+class Backend:
+    """ctypes binding of one implementation of the rwgpu C ABI (symbol prefix selects it)."""
+
+    def __init__(self, lib: C.CDLL, prefix: str = "rwgpu_"):
+        self.lib = lib
+        self.prefix = prefix
+        f = self._fn
+        f("out_num_chunks", C.c_int32, [C.c_void_p])
+        f("out_num_rows", C.c_int64, [C.c_void_p])
+        f("out_chunk", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(abi.RwChunk)])
+        f("out_release", None, [C.c_void_p])
+        f("agg_create", C.c_int32, [C.POINTER(abi.RwAggDesc), C.POINTER(C.c_void_p)])
+        f("agg_destroy", None, [C.c_void_p])
+        f("agg_push", C.c_int32, [C.c_void_p, C.POINTER(abi.RwChunk)])
+        f("agg_flush", C.c_int32, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)])
+        f("join_create", C.c_int32, [C.POINTER(abi.RwJoinDesc), C.POINTER(C.c_void_p)])
+        f("join_destroy", None, [C.c_void_p])
+        f("join_push", C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(abi.RwChunk), C.POINTER(C.c_void_p)])
+        f("join_barrier", C.c_int32, [C.c_void_p, C.c_uint64])
+        f("vnode_compute", C.c_int32, [C.POINTER(abi.RwChunk), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                       C.POINTER(C.c_uint16)])
+        f("dispatch_rewrite_ops", C.c_int32, [C.POINTER(abi.RwChunk), C.POINTER(C.c_int32), C.c_int32,
+                                              C.POINTER(C.c_uint8)])
+        f("last_error", C.c_char_p, [])
+
+    @staticmethod
+    def cuda() -> "Backend":
+        return Backend(abi.load_library(), "rwgpu_")
+
+    def _fn(self, name, restype, argtypes):
+        fn = getattr(self.lib, self.prefix + name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+        setattr(self, "_" + name, fn)
+
+    def check(self, rc: int):
+        if rc != abi.RW_OK:
+            msg = self._last_error()
+            raise abi.RwError(rc, msg.decode() if msg else "")
+
+    def take_out(self, out_ptr) -> List[StreamChunk]:
+        chunks = []
+        try:
+            for i in range(self._out_num_chunks(out_ptr)):
+                view = abi.RwChunk()
+                self.check(self._out_chunk(out_ptr, i, C.byref(view)))
+                chunks.append(StreamChunk.from_abi(view))
+        finally:
+            self._out_release(out_ptr)
+        return chunks
+
+    # ---- shuffle helpers (host)
+    def vnode_compute(self, chunk: StreamChunk, keys: Sequence[int], vnode_count: int = 256):
+        import numpy as np
+        ch, keep = chunk.to_abi()
+        k = (C.c_int32 * len(keys))(*keys)
+        out = np.zeros(chunk.capacity(), dtype=np.uint16)
+        self.check(self._vnode_compute(C.byref(ch), k, len(keys), vnode_count,
+                                       out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return out
+
+    def dispatch_rewrite_ops(self, chunk: StreamChunk, keys: Sequence[int]):
+        import numpy as np
+        ch, keep = chunk.to_abi()
+        k = (C.c_int32 * len(keys))(*keys)
+        out = np.zeros(chunk.capacity(), dtype=np.uint8)
+        self.check(self._dispatch_rewrite_ops(C.byref(ch), k, len(keys), out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+
+# =============================================================================== Message
+@dataclass
+class Barrier:
+    epoch: int
+    stop: bool = False
+
+
+@dataclass
+class Watermark:
+    col_idx: int
+    data_type: int
+    val: int
+
+
+@dataclass
+class Message:
+    """Message::{Chunk, Barrier, Watermark}  (mod.rs:1283-1299)"""
+    chunk: Optional[StreamChunk] = None
+    barrier: Optional[Barrier] = None
+    watermark: Optional[Watermark] = None
+
+
+PENDING = object()  # Poll::Pending
+
+
+class MessageSender:
+    """MessageSender (test_utils/mock_source.rs:39-108)."""
+
+    def __init__(self, q: Deque[Message]):
+        self._q = q
+
+    def push_chunk(self, chunk: StreamChunk):
+        self._q.append(Message(chunk=chunk))
+
+    def push_barrier(self, epoch: int, stop: bool = False):
+        self._q.append(Message(barrier=Barrier(epoch, stop)))
+
+    def push_watermark(self, col_idx: int, data_type: int, val: int):
+        self._q.append(Message(watermark=Watermark(col_idx, data_type, val)))
+
+
+class MockSource:
+    """MockSource::channel() (test_utils/mock_source.rs:110-137): an input executor fed by hand."""
+
+    def __init__(self, q: Deque[Message], schema: Sequence[int] = (), stream_key: Sequence[int] = ()):
+        self._q = q
+        self.schema = list(schema)
+        self.stream_key = list(stream_key)
+
+    @staticmethod
+    def channel() -> Tuple[MessageSender, "MockSource"]:
+        q: Deque[Message] = deque()
+        return MessageSender(q), MockSource(q)
+
+    def into_executor(self, schema: Sequence[int], stream_key: Sequence[int]) -> "MockSource":
+        self.schema = list(schema)
+        self.stream_key = list(stream_key)
+        return self
+
+    def poll(self):
+        return self._q.popleft() if self._q else PENDING
+
+
+class MessageStream:
+    """BoxedMessageStream + StreamExecutorTestExt (test_utils/mod.rs:61-124)."""
+
+    def __init__(self, gen: Iterator):
+        self._gen = gen
+
+    def poll_next(self):
+        return next(self._gen)
+
+    def next_unwrap_pending(self):
+        m = self.poll_next()
+        assert m is PENDING, f"expected pending, got {m}"
+
+    def next_unwrap_ready(self) -> Message:
+        m = self.poll_next()
+        assert m is not PENDING, "expected ready, got pending"
+        return m
+
+    def next_unwrap_ready_chunk(self) -> StreamChunk:
+        m = self.next_unwrap_ready()
+        assert m.chunk is not None, f"expected chunk, got {m}"
+        return m.chunk
+
+    def next_unwrap_ready_barrier(self) -> Barrier:
+        m = self.next_unwrap_ready()
+        assert m.barrier is not None, f"expected barrier, got {m}"
+        return m.barrier
+
+    def next_unwrap_ready_watermark(self) -> Watermark:
+        m = self.next_unwrap_ready()
+        assert m.watermark is not None, f"expected watermark, got {m}"
+        return m.watermark
+
+    def drain_until_pending(self) -> List[Message]:
+        """check_until_pending (tests/integration_tests/snapshot.rs:180-217)."""
+        out = []
+        while True:
+            m = self.poll_next()
+            if m is PENDING:
+                return out
+            out.append(m)
+
+
+# =============================================================================== AggCall
+_PG_TYPES = {"int2": abi.T_INT16, "int4": abi.T_INT32, "int8": abi.T_INT64, "float4": abi.T_FLOAT32,
+             "float8": abi.T_FLOAT64, "decimal": abi.T_DECIMAL, "boolean": abi.T_BOOL, "date": abi.T_DATE,
+             "timestamp": abi.T_TIMESTAMP, "timestamptz": abi.T_TIMESTAMPTZ, "serial": abi.T_SERIAL}
+_AGG_KINDS = {"count": abi.AGG_COUNT, "sum": abi.AGG_SUM, "min": abi.AGG_MIN, "max": abi.AGG_MAX,
+              "sum0": abi.AGG_SUM0}
+
+
+@dataclass
+class AggCall:
+    kind: int
+    arg_col: int
+    ret_type: int
+    arg_type: int = 0
+
+    @staticmethod
+    def from_pretty(s: str) -> "AggCall":
+        """`(sum:int8 $1:int8)` / `(count:int8)`  -- AggCall::from_pretty (src/expr/core/src/aggregate/def.rs)."""
+        m = re.fullmatch(r"\(\s*(\w+):(\w+)(?:\s+\$(\d+):(\w+))?\s*\)", s.strip())
+        if not m:
+            raise ValueError(f"bad agg call {s!r}")
+        kind, ret, idx, at = m.groups()
+        return AggCall(_AGG_KINDS[kind], -1 if idx is None else int(idx), _PG_TYPES[ret],
+                       0 if at is None else _PG_TYPES[at])
+
+
+# =============================================================================== HashAgg
+class HashAggExecutor:
+    """Mirror of HashAggExecutor<K,S> (aggregate/hash_agg.rs); arguments follow
+    `new_boxed_hash_agg_executor` (test_utils/agg_executor.rs:224-300)."""
+
+    def __init__(self, backend: Backend, input: MockSource, is_append_only: bool, agg_calls: Sequence[AggCall],
+                 row_count_index: int, group_key_indices: Sequence[int], chunk_size: int = 1024,
+                 strict_consistency: bool = True, group_capacity_hint: int = 0):
+        self.backend = backend
+        self.input = input
+        n_in = len(input.schema)
+        self._types = (C.c_int32 * n_in)(*input.schema)
+        self._keys = (C.c_int32 * max(1, len(group_key_indices)))(*group_key_indices)
+        self._calls = (abi.RwAggCall * max(1, len(agg_calls)))()
+        for i, c in enumerate(agg_calls):
+            self._calls[i].kind = c.kind
+            self._calls[i].arg_col = c.arg_col
+            self._calls[i].ret_type = c.ret_type
+        d = abi.RwAggDesc()
+        d.n_input_cols = n_in
+        d.input_types = self._types
+        d.n_group_keys = len(group_key_indices)
+        d.group_key_indices = self._keys
+        d.n_calls = len(agg_calls)
+        d.calls = self._calls
+        d.row_count_index = row_count_index
+        d.is_append_only = int(is_append_only)
+        d.chunk_size = chunk_size
+        d.strict_consistency = int(strict_consistency)
+        d.group_capacity_hint = group_capacity_hint
+        self._desc = d
+        h = C.c_void_p()
+        backend.check(backend._agg_create(C.byref(d), C.byref(h)))
+        self._h = h
+        self.schema = [input.schema[k] for k in group_key_indices] + [c.ret_type for c in agg_calls]
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self.backend._agg_destroy(h)
+            self._h = None
+
+    # direct operator calls (what the Rust shim would issue)
+    def apply_chunk(self, chunk: StreamChunk):
+        ch, keep = chunk.to_abi()
+        self.backend.check(self.backend._agg_push(self._h, C.byref(ch)))
+
+    def flush_data(self, epoch: int) -> List[StreamChunk]:
+        out = C.c_void_p()
+        self.backend.check(self.backend._agg_flush(self._h, epoch, C.byref(out)))
+        return self.backend.take_out(out)
+
+    def execute(self) -> MessageStream:
+        return MessageStream(self._run())
+
+    def _run(self):
+        # execute_inner (hash_agg.rs:561-706): first barrier initialises; chunks apply; a barrier
+        # flushes deltas, then is forwarded.
+        first = True
+        while True:
+            m = self.input.poll()
+            if m is PENDING:
+                yield PENDING
+                continue
+            if m.chunk is not None:
+                self.apply_chunk(m.chunk)
+            elif m.barrier is not None:
+                if first:
+                    first = False
+                    yield m
+                    continue
+                for ch in self.flush_data(m.barrier.epoch):
+                    yield Message(chunk=ch)
+                yield m
+            else:
+                yield m  # watermarks on group keys pass through (hash_agg.rs:628-637, simplified)
+
+
+# =============================================================================== HashJoin
+@dataclass
+class JoinParams:
+    """JoinParams (hash_join.rs:75-89)."""
+    join_key_indices: List[int]
+    deduped_pk_indices: List[int]
+
+
+_CMP = {"less_than": abi.CMP_LT, "less_than_or_equal": abi.CMP_LE, "greater_than": abi.CMP_GT,
+        "greater_than_or_equal": abi.CMP_GE, "equal": abi.CMP_EQ, "not_equal": abi.CMP_NE}
+
+
+def parse_cond(text: Optional[str]) -> Tuple[int, int, int]:
+    """`(less_than:boolean $1:int8 $3:int8)` -> (cmp, lhs, rhs) (build_from_pretty subset)."""
+    if text is None:
+        return (abi.CMP_NONE, 0, 0)
+    m = re.fullmatch(r"\(\s*(\w+):boolean\s+\$(\d+):\w+\s+\$(\d+):\w+\s*\)", text.strip())
+    if not m:
+        raise ValueError(f"unsupported join condition {text!r}")
+    return (_CMP[m.group(1)], int(m.group(2)), int(m.group(3)))
+
+
+class HashJoinExecutor:
+    """Mirror of HashJoinExecutor<K,S,T,E>::new (hash_join.rs:255-301)."""
+
+    def __init__(self, backend: Backend, join_type: int, input_l: MockSource, input_r: MockSource,
+                 params_l: JoinParams, params_r: JoinParams, null_safe: Sequence[bool],
+                 output_indices: Optional[Sequence[int]] = None, cond: Optional[str] = None,
+                 is_append_only: bool = False, chunk_size: int = 1024, strict_consistency: bool = True,
+                 capacity_hint: int = 0):
+        self.backend = backend
+        self.input_l, self.input_r = input_l, input_r
+        self._keep = []
+        d = abi.RwJoinDesc()
+        d.join_type = join_type
+        d.n_keys = len(params_l.join_key_indices)
+        for side, inp, p in ((d.left, input_l, params_l), (d.right, input_r, params_r)):
+            types = (C.c_int32 * max(1, len(inp.schema)))(*inp.schema)
+            keys = (C.c_int32 * max(1, len(p.join_key_indices)))(*p.join_key_indices)
+            pk = (C.c_int32 * max(1, len(p.deduped_pk_indices)))(*p.deduped_pk_indices)
+            sk = (C.c_int32 * max(1, len(inp.stream_key)))(*inp.stream_key)
+            self._keep += [types, keys, pk, sk]
+            side.n_cols = len(inp.schema)
+            side.types = types
+            side.key_indices = keys
+            side.n_pk = len(p.deduped_pk_indices)
+            side.pk_indices = pk
+            side.n_stream_key = len(inp.stream_key)
+            side.stream_key = sk
+            side.row_capacity_hint = capacity_hint
+        ns = (C.c_uint8 * max(1, len(null_safe)))(*[int(b) for b in null_safe])
+        d.null_safe = ns
+        if join_type in (abi.JOIN_LEFT_SEMI, abi.JOIN_LEFT_ANTI):
+            nat = list(input_l.schema)
+        elif join_type in (abi.JOIN_RIGHT_SEMI, abi.JOIN_RIGHT_ANTI):
+            nat = list(input_r.schema)
+        else:
+            nat = list(input_l.schema) + list(input_r.schema)
+        if output_indices is None:
+            output_indices = list(range(len(nat)))
+        oi = (C.c_int32 * max(1, len(output_indices)))(*output_indices)
+        d.n_output = len(output_indices)
+        d.output_indices = oi
+        cmp_, lhs, rhs = parse_cond(cond)
+        d.cond.cmp, d.cond.lhs, d.cond.rhs = cmp_, lhs, rhs
+        d.is_append_only = int(is_append_only)
+        d.chunk_size = chunk_size
+        d.strict_consistency = int(strict_consistency)
+        self._keep += [ns, oi]
+        self._desc = d
+        h = C.c_void_p()
+        backend.check(backend._join_create(C.byref(d), C.byref(h)))
+        self._h = h
+        self.schema = [nat[i] for i in output_indices]
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self.backend._join_destroy(h)
+            self._h = None
+
+    # direct operator calls (what the Rust shim would issue)
+    def eq_join_oneside(self, side: int, chunk: StreamChunk) -> List[StreamChunk]:
+        ch, keep = chunk.to_abi()
+        out = C.c_void_p()
+        self.backend.check(self.backend._join_push(self._h, side, C.byref(ch), C.byref(out)))
+        return self.backend.take_out(out)
+
+    def flush_data(self, epoch: int):
+        self.backend.check(self.backend._join_barrier(self._h, epoch))
+
+    def execute(self) -> MessageStream:
+        return MessageStream(self._run())
+
+    def _run(self):
+        # into_stream (hash_join.rs:582-751) over barrier_align (barrier_align.rs:44-165).  The
+        # reference picks the polled side at random (:67); we prefer left, which is one of its
+        # legal interleavings.  A side that delivered its barrier is blocked until the other does.
+        blocked = [None, None]
+        inputs = (self.input_l, self.input_r)
+        while True:
+            progressed = False
+            for s in (abi.SIDE_LEFT, abi.SIDE_RIGHT):
+                if blocked[s] is not None:
+                    continue
+                m = inputs[s].poll()
+                if m is PENDING:
+                    continue
+                progressed = True
+                if m.chunk is not None:
+                    for ch in self.eq_join_oneside(s, m.chunk):
+                        yield Message(chunk=ch)
+                elif m.barrier is not None:
+                    blocked[s] = m.barrier
+                    if blocked[0] is not None and blocked[1] is not None:
+                        assert blocked[0].epoch == blocked[1].epoch, "barrier epoch mismatch"
+                        b = blocked[0]
+                        blocked = [None, None]
+                        self.flush_data(b.epoch)
+                        yield Message(barrier=b)
+                else:
+                    pass  # watermark state cleaning stays on the CPU executor (hash_join.rs:791-891)
+                break
+            if not progressed:
+                yield PENDING

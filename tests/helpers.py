@@ -1,0 +1,129 @@
+"""Shared test helpers: run the reference's golden test scripts through an executor Backend."""
+import json
+import os
+
+import numpy as np
+
+from risingwave_b200 import abi
+from risingwave_b200.executor import (AggCall, HashAggExecutor, HashJoinExecutor, JoinParams, MockSource, PENDING)
+from risingwave_b200.stream_chunk import StreamChunk, PRETTY_TYPES, net_multiset, emitted_multiset
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+JOIN_TYPES = {"Inner": abi.JOIN_INNER, "LeftOuter": abi.JOIN_LEFT_OUTER, "RightOuter": abi.JOIN_RIGHT_OUTER,
+              "FullOuter": abi.JOIN_FULL_OUTER, "LeftSemi": abi.JOIN_LEFT_SEMI, "LeftAnti": abi.JOIN_LEFT_ANTI,
+              "RightSemi": abi.JOIN_RIGHT_SEMI, "RightAnti": abi.JOIN_RIGHT_ANTI}
+
+
+def load_golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def schema_types(s):
+    return [PRETTY_TYPES[ch] for ch in s]
+
+
+def make_join(backend, cfg, chunk_size=1024):
+    types = schema_types(cfg["schema"])
+    tx_l, src_l = MockSource.channel()
+    tx_r, src_r = MockSource.channel()
+    src_l = src_l.into_executor(types, cfg["stream_key"])
+    src_r = src_r.into_executor(types, cfg["stream_key"])
+    ex = HashJoinExecutor(backend, JOIN_TYPES[cfg["join_type"]], src_l, src_r,
+                          JoinParams(cfg["join_keys"], cfg["deduped_pk"]),
+                          JoinParams(cfg["join_keys"], cfg["deduped_pk"]),
+                          cfg["null_safe"], None, cfg.get("cond"), cfg["append_only"], chunk_size)
+    return tx_l, tx_r, ex
+
+
+def run_join_kat(backend, kat, exact=True):
+    """Replays one hash_join.rs test.  exact=True: StreamChunk equality incl. visibility (what the
+    reference asserts).  exact=False: per-step net applied multiset (order-insensitive parity)."""
+    tx_l, tx_r, ex = make_join(backend, kat["config"])
+    stream = ex.execute()
+    tx = {"l": tx_l, "r": tx_r}
+    for i, st in enumerate(kat["steps"]):
+        op = st["op"]
+        if op == "push_chunk":
+            tx[st["side"]].push_chunk(StreamChunk.from_pretty(st["chunk"]))
+        elif op == "push_barrier":
+            tx[st["side"]].push_barrier(st["epoch"])
+        elif op == "expect_pending":
+            if exact:
+                stream.next_unwrap_pending()
+            else:  # a chunk whose rows are all invisible / net-zero is also acceptable
+                m = stream.poll_next()
+                if m is not PENDING:
+                    assert m.chunk is not None and not net_multiset([m.chunk]), f"step {i}: expected pending, got {m}"
+                    stream.next_unwrap_pending()
+        elif op == "expect_barrier":
+            stream.next_unwrap_ready_barrier()
+        elif op == "expect_chunk":
+            want = StreamChunk.from_pretty(st["chunk"])
+            got = stream.next_unwrap_ready_chunk()
+            if exact:
+                if st.get("compact_vis"):
+                    got = StreamChunk.from_rows(got.types(), list(got.rows()))
+                assert got == want, f"{kat['name']} step {i}:\n got\n{got}\n want\n{want}"
+            else:
+                assert net_multiset([got]) == net_multiset([want]), \
+                    f"{kat['name']} step {i}:\n got\n{got}\n want\n{want}"
+        else:
+            raise AssertionError(op)
+
+
+def make_agg(backend, cfg, chunk_size=1024):
+    tx, src = MockSource.channel()
+    src = src.into_executor(schema_types(cfg["schema"]), [])
+    calls = [AggCall.from_pretty(c) for c in cfg["agg_calls"]]
+    ex = HashAggExecutor(backend, src, cfg["append_only"], calls, cfg["row_count_index"], cfg["group_keys"], chunk_size)
+    return tx, ex
+
+
+REF_OP_ORDER = {abi.OP_INSERT: 0, abi.OP_DELETE: 1, abi.OP_UPDATE_DELETE: 2, abi.OP_UPDATE_INSERT: 3}
+OPTOK = {"+": abi.OP_INSERT, "-": abi.OP_DELETE, "U-": abi.OP_UPDATE_DELETE, "U+": abi.OP_UPDATE_INSERT}
+
+
+def sorted_rows(chunk):
+    """Op derive(Ord) order Insert < Delete < UpdateDelete < UpdateInsert, then row (snapshot.rs sort_chunk)."""
+    return sorted(((REF_OP_ORDER[op], tuple((v is None, 0 if v is None else v) for v in row)) for op, row in chunk.rows()))
+
+
+def run_agg_kat(backend, kat):
+    tx, ex = make_agg(backend, kat["config"])
+    stream = ex.execute()
+    for st in kat["steps"]:
+        if st["op"] == "push_chunk":
+            tx.push_chunk(StreamChunk.from_pretty(st["chunk"]))
+        else:
+            tx.push_barrier(st["epoch"])
+    msgs = stream.drain_until_pending()
+    exp = kat["expected"]
+    assert len(msgs) == len(exp), (msgs, exp)
+    for m, e in zip(msgs, exp):
+        if "barrier" in e:
+            assert m.barrier is not None and m.barrier.epoch == e["barrier"]
+        else:
+            want = sorted((REF_OP_ORDER[OPTOK[r[0]]], tuple((False, int(x)) for x in r[1:])) for r in e["chunk_rows"])
+            assert sorted_rows(m.chunk) == want, f"{kat['name']}: got\n{m.chunk}\nwant {e['chunk_rows']}"
+
+
+def rand_chunk(rng, n, types, key_cols=(), key_range=16, null_frac=0.0, ops=None, vis_frac=1.0):
+    """random StreamChunk of n rows; key columns drawn from a small range to force collisions."""
+    from risingwave_b200.stream_chunk import Column, NP_DTYPE
+    cols = []
+    for k, t in enumerate(types):
+        if t in (abi.T_FLOAT32, abi.T_FLOAT64):
+            data = rng.integers(-1000, 1000, n).astype(NP_DTYPE[t]) / 4
+        else:
+            hi = key_range if k in key_cols else 1000
+            data = rng.integers(0, hi, n).astype(NP_DTYPE[t])
+        valid = None
+        if null_frac > 0:
+            valid = rng.random(n) >= null_frac
+        cols.append(Column(t, data, valid))
+    if ops is None:
+        ops = np.full(n, abi.OP_INSERT, np.uint8)
+    vis = None if vis_frac >= 1.0 else rng.random(n) < vis_frac
+    return StreamChunk(ops, cols, vis)
