@@ -1,0 +1,1079 @@
+// agg.cu -- streaming HashAgg on sm_100a: fused group-by hash + atomic partial aggregate, and the
+// barrier-time delta (change inference + compaction) kernel.
+//
+// Replaces (reference, Rust):
+//   HashAggExecutor::apply_chunk   src/stream/src/executor/aggregate/hash_agg.rs:332-409
+//   AggGroup::apply_chunk          aggregate/agg_group.rs:379-402  (+ generated `update`, expr/macro gen.rs:838-912)
+//   HashAggExecutor::flush_data    hash_agg.rs:412-514
+//   AggGroup::get_outputs / build_outputs_change / OnlyOutputIfHasInput  agg_group.rs:431-468,545-606,131-166
+//
+// HBM layout (open-addressed, linear probing, power-of-two capacity `cap`, load <= 1/2):
+//   hot  [cap+2][HW] u64 : key word(s) | one state word per agg call     (cfg2: 8+3*8 = 32 B = 1 sector)
+//   cold [cap+2][CW] u64 : flags | prev output per call | sum carry (hi) words | prev hi words
+//   dirty[(cap+2+31)/32] u32 : one bit per slot touched since the last barrier
+// Slots cap / cap+1 are side slots for the NULL key and for the key equal to the EMPTY sentinel
+// (single-column-key mode).  Multi-column keys store a tag word (hash bits | null mask | occupied)
+// followed by the key words; the tag is claimed with CAS under a lock bit.
+#include <algorithm>
+#include <memory>
+
+#include "common.cuh"
+
+namespace rw {
+
+#define AGG_EMPTY 0x8000000000000000ull
+#define AGG_ERR_OVERFLOW 1u
+#define AGG_ERR_NEG_COUNT 2u
+#define AGG_ERR_RETRACT_APPEND_ONLY 4u
+#define AGG_ERR_OUT_CAPACITY 8u
+
+struct AggStatus {
+  unsigned long long out_rows;
+  unsigned long long n_groups;
+  unsigned int err;
+  unsigned int pad;
+};
+
+struct AggPlanDev {
+  int n_keys;
+  int key_col[RW_MAX_KEYS];
+  int key_type[RW_MAX_KEYS];
+  int n_calls;
+  int kind[RW_MAX_CALLS];
+  int arg_col[RW_MAX_CALLS];
+  int arg_type[RW_MAX_CALLS];
+  int ret_type[RW_MAX_CALLS];
+  int hi_off[RW_MAX_CALLS];      // cold word of the sum carry (hi) word, -1 if none
+  int prevhi_off[RW_MAX_CALLS];  // cold word of prev output hi (decimal ret), -1 if none
+  int KW, HW, CW;
+  int single_key;
+  int row_count_call;
+  int strict;
+};
+
+struct AggTable {
+  uint64_t* hot;
+  uint64_t* cold;
+  uint32_t* dirty;
+  AggStatus* status;
+  uint64_t cap;  // power of two
+};
+
+struct AggOutDev {
+  uint8_t* ops;
+  void* col[RW_MAX_KEYS + RW_MAX_CALLS];
+  uint8_t* valid[RW_MAX_KEYS + RW_MAX_CALLS];  // 1 byte / row
+  unsigned int* has_null;                       // per column flag
+  int64_t capacity;
+};
+
+// cold word 0: bits 0..15 state-non-NULL flag per call, bits 16..31 prev-output NULL mask, bit 32 has_prev
+#define COLD_HAS_PREV (1ull << 32)
+
+__device__ __forceinline__ uint64_t state_init(int kind, int arg_type) {
+  if (kind == RW_AGG_MIN) return (uint64_t)INT64_MAX;
+  if (kind == RW_AGG_MAX) return (uint64_t)INT64_MIN;
+  return 0ull;  // count / sum / sum0 (double 0.0 has bit pattern 0 too)
+}
+
+// ------------------------------------------------------------------ table init
+__global__ void agg_init_kernel(AggTable t, AggPlanDev p, uint64_t from_slot) {
+  uint64_t total = t.cap + 2;
+  for (uint64_t s = from_slot + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < total;
+       s += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t* h = t.hot + s * p.HW;
+    h[0] = p.single_key ? AGG_EMPTY : 0ull;
+    for (int k = 1; k < p.KW; k++) h[k] = 0;
+    for (int c = 0; c < p.n_calls; c++) h[p.KW + c] = state_init(p.kind[c], p.arg_type[c]);
+    uint64_t* cw = t.cold + s * p.CW;
+    for (int k = 0; k < p.CW; k++) cw[k] = 0;
+  }
+}
+
+// ------------------------------------------------------------------ slot lookup
+__device__ __forceinline__ uint64_t find_or_insert_single(const AggTable& t, int HW, uint64_t key, bool* created) {
+  uint64_t mask = t.cap - 1;
+  uint64_t idx = mix64(key) & mask;
+  while (true) {
+    unsigned long long* p = (unsigned long long*)(t.hot + idx * HW);
+    unsigned long long cur = *p;
+    if (cur == key) return idx;
+    if (cur == AGG_EMPTY) {
+      unsigned long long old = atomicCAS(p, (unsigned long long)AGG_EMPTY, (unsigned long long)key);
+      if (old == AGG_EMPTY) { *created = true; return idx; }
+      if (old == key) return idx;
+    }
+    idx = (idx + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ uint64_t find_or_insert_multi(const AggTable& t, const AggPlanDev& p, const uint64_t* kw,
+                                                          uint32_t nullmask, bool* created) {
+  uint64_t h = 0x9e3779b97f4a7c15ull ^ nullmask;
+  for (int k = 0; k < p.n_keys; k++) h = mix64(h ^ kw[k]) + 0x9e3779b97f4a7c15ull;
+  uint64_t tag = (h & ~0xFFFFull) | ((uint64_t)nullmask << 8) | 1ull;
+  uint64_t mask = t.cap - 1;
+  uint64_t idx = (h >> 17) & mask;
+  while (true) {
+    unsigned long long* ptr = (unsigned long long*)(t.hot + idx * p.HW);
+    unsigned long long cur = *(volatile unsigned long long*)ptr;
+    if (cur == 0ull) {
+      unsigned long long old = atomicCAS(ptr, 0ull, (unsigned long long)(tag | 2ull));
+      if (old == 0ull) {
+        for (int k = 0; k < p.n_keys; k++) __stcg((unsigned long long*)ptr + 1 + k, (unsigned long long)kw[k]);
+        __threadfence();
+        atomicExch(ptr, (unsigned long long)tag);
+        *created = true;
+        return idx;
+      }
+      cur = old;
+    }
+    if ((cur & ~2ull) == tag) {
+      while (cur & 2ull) cur = *(volatile unsigned long long*)ptr;  // writer publishes within a few cycles
+      bool eq = true;
+      for (int k = 0; k < p.n_keys; k++) eq = eq && (__ldcg((const unsigned long long*)ptr + 1 + k) == kw[k]);
+      if (eq) return idx;
+    }
+    idx = (idx + 1) & mask;
+  }
+}
+
+// ------------------------------------------------------------------ apply one row to the group's states
+__device__ __forceinline__ void agg_apply_row(const AggTable& t, const AggPlanDev& p, const DevChunk& ch, int64_t r,
+                                               uint8_t op, uint64_t slot, int per_row_flags) {
+  uint64_t* hot = t.hot + slot * p.HW + p.KW;
+  uint64_t* cold = t.cold + slot * p.CW;
+  const bool retract = (op == RW_OP_DELETE || op == RW_OP_UPDATE_DELETE);
+  uint32_t setflags = 0;
+#pragma unroll 1
+  for (int c = 0; c < p.n_calls; c++) {
+    const int kind = p.kind[c];
+    const int ac = p.arg_col[c];
+    if (ac >= 0 && col_is_null(ch.cols[ac], r)) continue;  // (state, None) => state   gen.rs:894-896
+    unsigned long long* sp = (unsigned long long*)(hot + c);
+    if (kind == RW_AGG_COUNT) {
+      atomicAdd(sp, retract ? ~0ull : 1ull);
+      continue;
+    }
+    setflags |= 1u << c;
+    const int at = p.arg_type[c];
+    const bool isf = (at == RW_T_FLOAT32 || at == RW_T_FLOAT64);
+    if (kind == RW_AGG_SUM || kind == RW_AGG_SUM0) {
+      if (isf) {
+        double x = load_f64(ch.cols[ac], r);
+        atomicAdd((double*)sp, retract ? -x : x);
+      } else {
+        int64_t x = load_i64(ch.cols[ac], r);
+        unsigned long long add = retract ? (0ull - (unsigned long long)x) : (unsigned long long)x;
+        if (ch.cols[ac].width == 8) {
+          // exact 128-bit accumulation: lo word here, carries into the cold hi word
+          bool neg = retract ? (x > 0) : (x < 0);
+          unsigned long long old = atomicAdd(sp, add);
+          unsigned long long nw = old + add;
+          long long hd = (neg ? -1ll : 0ll) + ((nw < old) ? 1ll : 0ll);
+          if (hd != 0) atomicAdd((unsigned long long*)(cold + p.hi_off[c]), (unsigned long long)hd);
+        } else {
+          atomicAdd(sp, add);  // |x| < 2^31: cannot leave int64 below 2^32 rows per group
+        }
+      }
+    } else {  // MIN / MAX (append-only value state, general.rs:91-125)
+      if (op != RW_OP_INSERT) { atomicOr(&t.status->err, AGG_ERR_RETRACT_APPEND_ONLY); continue; }
+      long long v = isf ? (long long)f64_sortable(load_f64(ch.cols[ac], r)) : (long long)load_i64(ch.cols[ac], r);
+      if (kind == RW_AGG_MIN) atomicMin((long long*)sp, v); else atomicMax((long long*)sp, v);
+    }
+  }
+  if (per_row_flags && setflags) {
+    unsigned long long f = __ldcg((const unsigned long long*)cold);
+    if ((f & setflags) != setflags) atomicOr((unsigned long long*)cold, (unsigned long long)setflags);
+  }
+}
+
+// ------------------------------------------------------------------ generic apply kernel (one thread per row)
+__global__ void __launch_bounds__(256) agg_apply_kernel(AggTable t, AggPlanDev p, DevChunk ch, int per_row_flags) {
+  unsigned int created_local = 0;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
+    uint8_t op = ch.ops[r];
+    if (!row_visible(ch, r, op)) continue;
+    uint64_t slot;
+    bool created = false;
+    if (p.single_key) {
+      const ColRef& kc = ch.cols[p.key_col[0]];
+      if (col_is_null(kc, r)) slot = t.cap;  // NULL is a legal group value (key_v2.rs:216-220)
+      else {
+        uint64_t key = load_key_word(kc, r);
+        if (key == AGG_EMPTY) slot = t.cap + 1;
+        else slot = find_or_insert_single(t, p.HW, key, &created);
+      }
+    } else {
+      uint64_t kw[RW_MAX_KEYS];
+      uint32_t nm = 0;
+      for (int k = 0; k < p.n_keys; k++) {
+        const ColRef& kc = ch.cols[p.key_col[k]];
+        if (col_is_null(kc, r)) { nm |= 1u << k; kw[k] = 0; }
+        else kw[k] = load_key_word(kc, r);
+      }
+      slot = find_or_insert_multi(t, p, kw, nm, &created);
+    }
+    if (created) created_local++;
+    uint32_t bit = 1u << (slot & 31);
+    uint32_t* dw = t.dirty + (slot >> 5);
+    if (!(__ldcg(dw) & bit)) atomicOr(dw, bit);
+    agg_apply_row(t, p, ch, r, op, slot, per_row_flags);
+  }
+  // warp-aggregated group counter
+  for (int o = 16; o > 0; o >>= 1) created_local += __shfl_xor_sync(0xffffffffu, created_local, o);
+  if (lane_id() == 0 && created_local) atomicAdd(&t.status->n_groups, (unsigned long long)created_local);
+}
+
+// ------------------------------------------------------------------ fast path: 1 x 8-byte key, no NULLs anywhere,
+// calls = {count(*), sum(int8)->int8, max/min(int8)} in any order (BASELINE cfg2 / Nexmark q4 shape).
+// Two rows per thread with 128-bit loads of the key / argument columns.
+template <int NCALLS>
+__global__ void __launch_bounds__(256) agg_apply_fast_kernel(AggTable t, AggPlanDev p, DevChunk ch) {
+  unsigned int created_local = 0;
+  const int64_t npair = (ch.n + 1) >> 1;
+  const longlong2* keyv = (const longlong2*)ch.cols[p.key_col[0]].data;
+  const unsigned short* opv = (const unsigned short*)ch.ops;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npair; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r0 = i * 2;
+    const bool two = (r0 + 1 < ch.n);
+    long long k[2];
+    uint8_t op[2];
+    long long a[NCALLS][2];
+    if (two) {
+      longlong2 kv = __ldg(keyv + i);
+      k[0] = kv.x; k[1] = kv.y;
+      unsigned short o2 = __ldg(opv + i);
+      op[0] = (uint8_t)(o2 & 0xff); op[1] = (uint8_t)(o2 >> 8);
+#pragma unroll
+      for (int c = 0; c < NCALLS; c++) {
+        if (p.arg_col[c] >= 0) {
+          longlong2 av = __ldg((const longlong2*)ch.cols[p.arg_col[c]].data + i);
+          a[c][0] = av.x; a[c][1] = av.y;
+        }
+      }
+    } else {
+      k[0] = ((const long long*)ch.cols[p.key_col[0]].data)[r0]; k[1] = 0;
+      op[0] = ch.ops[r0]; op[1] = 0;
+#pragma unroll
+      for (int c = 0; c < NCALLS; c++)
+        if (p.arg_col[c] >= 0) { a[c][0] = ((const long long*)ch.cols[p.arg_col[c]].data)[r0]; a[c][1] = 0; }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      if (op[j] == 0) continue;
+      bool created = false;
+      uint64_t slot = ((uint64_t)k[j] == AGG_EMPTY) ? t.cap + 1 : find_or_insert_single(t, p.HW, (uint64_t)k[j], &created);
+      if (created) created_local++;
+      uint32_t bit = 1u << (slot & 31);
+      uint32_t* dw = t.dirty + (slot >> 5);
+      if (!(__ldcg(dw) & bit)) atomicOr(dw, bit);
+      unsigned long long* sp = (unsigned long long*)(t.hot + slot * p.HW + 1);
+      const bool retract = (op[j] == RW_OP_DELETE || op[j] == RW_OP_UPDATE_DELETE);
+#pragma unroll
+      for (int c = 0; c < NCALLS; c++) {
+        const int kind = p.kind[c];
+        if (kind == RW_AGG_COUNT) {
+          atomicAdd(sp + c, retract ? ~0ull : 1ull);
+        } else if (kind == RW_AGG_SUM || kind == RW_AGG_SUM0) {
+          long long x = a[c][j];
+          unsigned long long add = retract ? (0ull - (unsigned long long)x) : (unsigned long long)x;
+          bool neg = retract ? (x > 0) : (x < 0);
+          unsigned long long old = atomicAdd(sp + c, add);
+          unsigned long long nw = old + add;
+          long long hd = (neg ? -1ll : 0ll) + ((nw < old) ? 1ll : 0ll);
+          if (hd != 0) atomicAdd((unsigned long long*)(t.cold + slot * p.CW + p.hi_off[c]), (unsigned long long)hd);
+        } else {
+          if (op[j] != RW_OP_INSERT) { atomicOr(&t.status->err, AGG_ERR_RETRACT_APPEND_ONLY); continue; }
+          if (kind == RW_AGG_MIN) atomicMin((long long*)(sp + c), a[c][j]); else atomicMax((long long*)(sp + c), a[c][j]);
+        }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) created_local += __shfl_xor_sync(0xffffffffu, created_local, o);
+  if (lane_id() == 0 && created_local) atomicAdd(&t.status->n_groups, (unsigned long long)created_local);
+}
+
+// ------------------------------------------------------------------ mark "state non-NULL" for all dirty groups
+// (used when every push of the epoch had NULL-free argument columns: then every visible row
+// contributed a non-NULL value to every call, so the per-row flag update can be elided)
+__global__ void agg_set_flags_kernel(AggTable t, AggPlanDev p, uint32_t mask) {
+  uint64_t nwords = (t.cap + 2 + 31) >> 5;
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t bits = t.dirty[w];
+    while (bits) {
+      int b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      uint64_t slot = (w << 5) + b;
+      t.cold[slot * p.CW] |= (uint64_t)mask;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ flush: change inference + compaction
+struct OutVal {
+  uint64_t lo, hi;
+  bool null;
+};
+
+__global__ void __launch_bounds__(256) agg_flush_kernel(AggTable t, AggPlanDev p, AggOutDev o, uint32_t epoch_flag_mask) {
+  const uint64_t nwords = (t.cap + 2 + 31) >> 5;
+  const uint64_t warps_total = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = lane_id();
+  for (uint64_t w = warp0; w < nwords; w += warps_total) {
+    uint32_t bits = t.dirty[w];
+    if (bits == 0) continue;  // warp-uniform
+    const uint64_t slot = (w << 5) + lane;
+    const bool active = (bits >> lane) & 1;
+    int nrows = 0;
+    uint8_t op0 = 0, op1 = 0;
+    OutVal prev[RW_MAX_CALLS], curr[RW_MAX_CALLS];
+    uint64_t keyw[RW_MAX_KEYS];
+    uint32_t key_nm = 0;
+    if (active) {
+      uint64_t* hot = t.hot + slot * p.HW;
+      uint64_t* cold = t.cold + slot * p.CW;
+      uint64_t flags = cold[0] | (uint64_t)epoch_flag_mask;
+      // group key
+      if (p.single_key) {
+        if (slot == t.cap) { key_nm = 1; keyw[0] = 0; }
+        else keyw[0] = (slot == t.cap + 1) ? AGG_EMPTY : hot[0];
+      } else {
+        key_nm = (uint32_t)((hot[0] >> 8) & 0xff);
+        for (int k = 0; k < p.n_keys; k++) keyw[k] = hot[1 + k];
+      }
+      // row_count_of (agg_group.rs:55-79)
+      long long rc = (long long)hot[p.KW + p.row_count_call];
+      if (rc < 0) {
+        if (p.strict) atomicOr(&t.status->err, AGG_ERR_NEG_COUNT);
+        rc = 0;
+      }
+      if (rc == 0) {  // reset value states (agg_group.rs:438-446)
+        for (int c = 0; c < p.n_calls; c++) {
+          hot[p.KW + c] = state_init(p.kind[c], p.arg_type[c]);
+          if (p.hi_off[c] >= 0) cold[p.hi_off[c]] = 0;
+        }
+        flags &= ~0xFFFFull;
+      }
+      const bool has_prev = (flags & COLD_HAS_PREV) != 0;
+      const uint32_t prev_nm = (uint32_t)((flags >> 16) & 0xFFFF);
+      long long prev_rc = 0;
+      uint32_t curr_nm = 0;
+      bool same = true;
+      for (int c = 0; c < p.n_calls; c++) {
+        const int kind = p.kind[c];
+        const int at = p.arg_type[c];
+        const bool isf = (at == RW_T_FLOAT32 || at == RW_T_FLOAT64);
+        uint64_t s = hot[p.KW + c];
+        OutVal v;
+        v.hi = 0;
+        v.null = false;
+        if (kind == RW_AGG_COUNT) {
+          v.lo = (rc == 0 && c == p.row_count_call) ? 0 : s;
+        } else if (kind == RW_AGG_SUM0 && !((flags >> c) & 1)) {
+          v.lo = 0;  // init_state = 0
+        } else if (!((flags >> c) & 1)) {
+          v.null = true; v.lo = 0;
+        } else if (kind == RW_AGG_SUM || kind == RW_AGG_SUM0) {
+          if (isf) {
+            v.lo = s;
+            if (p.ret_type[c] == RW_T_FLOAT32) {  // sum(float4) -> float4
+              float f = (float)__longlong_as_double((long long)s);
+              v.lo = (uint64_t)__double_as_longlong((double)f);
+            }
+          } else {
+            long long hi = (p.hi_off[c] >= 0) ? (long long)cold[p.hi_off[c]] : (((long long)s) >> 63);
+            v.lo = s;
+            v.hi = (uint64_t)hi;
+            if (p.ret_type[c] == RW_T_DECIMAL) {
+              // rust_decimal: 96-bit mantissa
+              bool ok = (hi >= 0) ? (hi < (1ll << 32)) : (hi > -(1ll << 32) || (hi == -(1ll << 32) && s != 0));
+              if (!ok) atomicOr(&t.status->err, AGG_ERR_OVERFLOW);
+            } else {
+              if (hi != (((long long)s) >> 63)) atomicOr(&t.status->err, AGG_ERR_OVERFLOW);
+            }
+          }
+        } else {  // min / max
+          v.lo = isf ? (uint64_t)__double_as_longlong(f64_unsortable((int64_t)s)) : s;
+          if (isf && p.ret_type[c] == RW_T_FLOAT32) { /* value is an exact f32 already */ }
+        }
+        if (v.null) curr_nm |= 1u << c;
+        curr[c] = v;
+        OutVal pv;
+        pv.lo = cold[1 + c];
+        pv.hi = (p.prevhi_off[c] >= 0) ? cold[p.prevhi_off[c]] : 0;
+        pv.null = (prev_nm >> c) & 1;
+        prev[c] = pv;
+        if (has_prev) {
+          bool eq = (pv.null == v.null) && (v.null || (pv.lo == v.lo && (p.prevhi_off[c] < 0 || pv.hi == v.hi)));
+          if (!eq && !v.null && !pv.null && (p.ret_type[c] == RW_T_FLOAT32 || p.ret_type[c] == RW_T_FLOAT64)) {
+            // OrderedFloat equality: NaN == NaN, -0 == +0
+            double a = __longlong_as_double((long long)pv.lo), b = __longlong_as_double((long long)v.lo);
+            eq = (a != a && b != b) || (a == b);
+          }
+          same = same && eq;
+        }
+      }
+      if (has_prev) {
+        prev_rc = (long long)cold[1 + p.row_count_call];
+        if (prev_rc < 0) prev_rc = 0;
+      }
+      // OnlyOutputIfHasInput::infer_change_type (agg_group.rs:131-166)
+      bool store_prev = false, clear_prev = false;
+      if (prev_rc == 0 && rc == 0) { nrows = 0; }
+      else if (prev_rc == 0) { nrows = 1; op0 = RW_OP_INSERT; store_prev = true; }
+      else if (rc == 0) { nrows = 1; op0 = RW_OP_DELETE; clear_prev = true; }
+      else if (!same) { nrows = 2; op0 = RW_OP_UPDATE_DELETE; op1 = RW_OP_UPDATE_INSERT; store_prev = true; }
+      uint64_t nf = flags;
+      if (store_prev) {
+        for (int c = 0; c < p.n_calls; c++) {
+          cold[1 + c] = curr[c].lo;
+          if (p.prevhi_off[c] >= 0) cold[p.prevhi_off[c]] = curr[c].hi;
+        }
+        nf = (nf & ~(0xFFFFull << 16)) | ((uint64_t)curr_nm << 16) | COLD_HAS_PREV;
+      } else if (clear_prev) {
+        nf &= ~(COLD_HAS_PREV | (0xFFFFull << 16));
+      }
+      cold[0] = nf;
+    }
+    // warp-scan compaction of the emitted rows
+    int incl = nrows;
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && total) base = atomicAdd(&t.status->out_rows, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (nrows) {
+      int64_t row = (int64_t)base + (incl - nrows);
+      if (row + nrows > o.capacity) {
+        atomicOr(&t.status->err, AGG_ERR_OUT_CAPACITY);
+      } else {
+        for (int j = 0; j < nrows; j++) {
+          const uint8_t op = j == 0 ? op0 : op1;
+          const OutVal* vals = (op == RW_OP_DELETE || op == RW_OP_UPDATE_DELETE) ? prev : curr;
+          const int64_t rr = row + j;
+          o.ops[rr] = op;
+          for (int k = 0; k < p.n_keys; k++) {
+            bool nul = (key_nm >> k) & 1;
+            o.valid[k][rr] = nul ? 0 : 1;
+            if (nul) o.has_null[k] = 1;
+            store_word(o.col[k], type_width_dev(p.key_type[k]), p.key_type[k], rr, keyw[k]);
+          }
+          for (int c = 0; c < p.n_calls; c++) {
+            const int oc = p.n_keys + c;
+            o.valid[oc][rr] = vals[c].null ? 0 : 1;
+            if (vals[c].null) o.has_null[oc] = 1;
+            if (p.ret_type[c] == RW_T_DECIMAL) {
+              ((uint64_t*)o.col[oc])[rr * 2] = vals[c].lo;
+              ((uint64_t*)o.col[oc])[rr * 2 + 1] = vals[c].hi;
+            } else {
+              store_word(o.col[oc], type_width_dev(p.ret_type[c]), p.ret_type[c], rr, vals[c].lo);
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) t.dirty[w] = 0;
+  }
+}
+
+// ------------------------------------------------------------------ rehash (growth) kernel
+__global__ void agg_rehash_kernel(AggTable o, AggTable n, AggPlanDev p) {
+  const uint64_t total = o.cap + 2;
+  unsigned int kept = 0;
+  for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < total; s += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t* oh = o.hot + s * p.HW;
+    const uint64_t* oc = o.cold + s * p.CW;
+    const bool dirty = (o.dirty[s >> 5] >> (s & 31)) & 1;
+    uint64_t dst;
+    if (s >= o.cap) {
+      dst = n.cap + (s - o.cap);
+    } else {
+      uint64_t w0 = oh[0];
+      if (p.single_key ? (w0 == AGG_EMPTY) : (w0 == 0)) continue;
+      // drop groups that hold no rows, emitted nothing and are not dirty (the reference evicts them
+      // from its LRU and deletes their intermediate-state row, agg_group.rs:473-538)
+      long long rc = (long long)oh[p.KW + p.row_count_call];
+      if (rc == 0 && !(oc[0] & COLD_HAS_PREV) && !dirty) continue;
+      kept++;
+      uint64_t mask = n.cap - 1;
+      if (p.single_key) {
+        uint64_t idx = mix64(w0) & mask;
+        while (true) {
+          unsigned long long* ptr = (unsigned long long*)(n.hot + idx * p.HW);
+          if (atomicCAS(ptr, (unsigned long long)AGG_EMPTY, (unsigned long long)w0) == AGG_EMPTY) break;
+          idx = (idx + 1) & mask;
+        }
+        dst = idx;
+      } else {
+        uint32_t nm = (uint32_t)((w0 >> 8) & 0xff);
+        uint64_t h = 0x9e3779b97f4a7c15ull ^ nm;
+        for (int k = 0; k < p.n_keys; k++) h = mix64(h ^ oh[1 + k]) + 0x9e3779b97f4a7c15ull;
+        uint64_t idx = (h >> 17) & mask;
+        while (true) {
+          unsigned long long* ptr = (unsigned long long*)(n.hot + idx * p.HW);
+          if (atomicCAS(ptr, 0ull, (unsigned long long)w0) == 0ull) break;
+          idx = (idx + 1) & mask;
+        }
+        dst = idx;
+      }
+    }
+    uint64_t* nh = n.hot + dst * p.HW;
+    uint64_t* nc = n.cold + dst * p.CW;
+    for (int k = (s >= o.cap ? 0 : 1); k < p.HW; k++) nh[k] = oh[k];
+    for (int k = 0; k < p.CW; k++) nc[k] = oc[k];
+    if (dirty) atomicOr(n.dirty + (dst >> 5), 1u << (dst & 31));
+  }
+  for (int d = 16; d > 0; d >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, d);
+  if (lane_id() == 0 && kept) atomicAdd(&n.status->n_groups, (unsigned long long)kept);
+}
+
+__global__ void pack_bytes_to_bits_kernel(const uint8_t* bytes, uint64_t* words, int64_t n) {
+  int64_t nw = (n + 63) >> 6;
+  for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nw; w += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t v = 0;
+    int64_t base = w << 6;
+    int lim = (int)((n - base) < 64 ? (n - base) : 64);
+    for (int b = 0; b < lim; b++) v |= (uint64_t)(bytes[base + b] != 0) << b;
+    words[w] = v;
+  }
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace rw
+
+// =============================================================================== host handle
+using namespace rw;
+
+struct AggStage {
+  PinnedBuf host;
+  DevBuf dev;
+  cudaEvent_t done = nullptr;
+  bool in_flight = false;
+  int64_t rows = 0;
+  bool has_valid[RW_MAX_COLS];
+};
+
+struct rwgpu_agg {
+  AggPlanDev plan;
+  std::vector<int> in_types, out_types, used_cols;
+  int chunk_size = 1024;
+  cudaStream_t stream = nullptr;
+  DevBuf hot, cold, dirty, status;
+  uint64_t cap = 0;
+  uint64_t groups_upper = 0;
+  uint64_t epoch_rows = 0;
+  bool per_row_mode = false, nullfree_push_seen = false;
+  uint32_t all_flag_mask = 0;
+  uint64_t launches = 0;
+  bool fast_eligible = false;
+  // staging (host pushes)
+  AggStage stage[2];
+  int cur = 0;
+  int64_t stage_cap = 1 << 18;
+  size_t off_ops = 0, stage_bytes = 0;
+  size_t off_data[RW_MAX_COLS], off_valid[RW_MAX_COLS];
+  // output buffers (device)
+  DevBuf out_ops, out_hasnull, out_col[RW_MAX_KEYS + RW_MAX_CALLS], out_valid[RW_MAX_KEYS + RW_MAX_CALLS],
+      out_bits[RW_MAX_KEYS + RW_MAX_CALLS];
+  int64_t out_cap = 0;
+  PinnedBuf status_host;
+  std::vector<rw_column> dev_view_cols;
+
+  AggTable table() const {
+    AggTable t;
+    t.hot = hot.as<uint64_t>();
+    t.cold = cold.as<uint64_t>();
+    t.dirty = dirty.as<uint32_t>();
+    t.status = status.as<AggStatus>();
+    t.cap = cap;
+    return t;
+  }
+  ~rwgpu_agg() {
+    for (auto& s : stage) if (s.done) cudaEventDestroy(s.done);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+static int grid_for(int64_t n_threads, int block) {
+  int64_t g = (n_threads + block - 1) / block;
+  int64_t maxg = 148 * 8;
+  return (int)std::max<int64_t>(1, std::min(g, maxg));
+}
+
+static int agg_alloc_table(rwgpu_agg* h, uint64_t cap, DevBuf& hot, DevBuf& cold, DevBuf& dirty) {
+  size_t slots = cap + 2;
+  RW_CUDA(hot.reserve(slots * h->plan.HW * 8));
+  RW_CUDA(cold.reserve(slots * h->plan.CW * 8));
+  RW_CUDA(dirty.reserve(((slots + 31) / 32) * 4));
+  return RW_OK;
+}
+
+static int agg_init_table(rwgpu_agg* h, AggTable t) {
+  RW_CUDA(cudaMemsetAsync(t.dirty, 0, ((t.cap + 2 + 31) / 32) * 4, h->stream));
+  agg_init_kernel<<<grid_for((int64_t)t.cap + 2, 256), 256, 0, h->stream>>>(t, h->plan, 0);
+  RW_CUDA(cudaGetLastError());
+  h->launches++;
+  return RW_OK;
+}
+
+// make room for `incoming` more rows (each may open a new group); grows + rehashes when needed
+static int agg_ensure_capacity(rwgpu_agg* h, uint64_t incoming) {
+  if ((h->groups_upper + incoming) * 2 <= h->cap) return RW_OK;
+  // the bound is pessimistic: read the real group count
+  AggStatus* sh = h->status_host.as<AggStatus>();
+  RW_CUDA(cudaMemcpyAsync(sh, h->status.p, sizeof(AggStatus), cudaMemcpyDeviceToHost, h->stream));
+  RW_CUDA(cudaStreamSynchronize(h->stream));
+  h->groups_upper = sh->n_groups;
+  if ((h->groups_upper + incoming) * 2 <= h->cap) return RW_OK;
+  uint64_t need = (h->groups_upper + incoming) * 4;
+  uint64_t ncap = h->cap;
+  while (ncap < need) ncap <<= 1;
+  DevBuf nh, nc, nd;
+  int rc = agg_alloc_table(h, ncap, nh, nc, nd);
+  if (rc != RW_OK) return rc;
+  AggTable ot = h->table();
+  AggTable nt = ot;
+  nt.hot = nh.as<uint64_t>(); nt.cold = nc.as<uint64_t>(); nt.dirty = nd.as<uint32_t>(); nt.cap = ncap;
+  rc = agg_init_table(h, nt);
+  if (rc != RW_OK) return rc;
+  RW_CUDA(cudaMemsetAsync(&h->status.as<AggStatus>()->n_groups, 0, sizeof(unsigned long long), h->stream));
+  agg_rehash_kernel<<<grid_for((int64_t)ot.cap + 2, 256), 256, 0, h->stream>>>(ot, nt, h->plan);
+  RW_CUDA(cudaGetLastError());
+  h->launches++;
+  RW_CUDA(cudaStreamSynchronize(h->stream));  // old buffers are freed below
+  h->hot = std::move(nh);
+  h->cold = std::move(nc);
+  h->dirty = std::move(nd);
+  h->cap = ncap;
+  RW_CUDA(cudaMemcpy(sh, h->status.p, sizeof(AggStatus), cudaMemcpyDeviceToHost));
+  h->groups_upper = sh->n_groups;
+  return RW_OK;
+}
+
+static bool chunk_fast_ok(const rwgpu_agg* h, const DevChunk& ch) {
+  if (!h->fast_eligible || ch.vis_bits != nullptr) return false;
+  if (((uintptr_t)ch.ops & 1) != 0) return false;
+  for (int c : h->used_cols) {
+    const ColRef& r = ch.cols[c];
+    if (r.valid_bits || r.valid_bytes) return false;
+    if (((uintptr_t)r.data & 15) != 0) return false;
+  }
+  return true;
+}
+
+// enqueue the apply kernel for a device-resident chunk
+static int agg_apply_dev(rwgpu_agg* h, const DevChunk& ch, cudaStream_t st) {
+  if (ch.n <= 0) return RW_OK;
+  int rc = agg_ensure_capacity(h, (uint64_t)ch.n);
+  if (rc != RW_OK) return rc;
+  bool has_nulls = false;
+  for (int c : h->used_cols) if (ch.cols[c].valid_bits || ch.cols[c].valid_bytes) has_nulls = true;
+  if (has_nulls) {
+    if (!h->per_row_mode && h->nullfree_push_seen) {
+      agg_set_flags_kernel<<<grid_for((int64_t)((h->cap + 2 + 31) >> 5), 256), 256, 0, st>>>(h->table(), h->plan, h->all_flag_mask);
+      RW_CUDA(cudaGetLastError());
+      h->launches++;
+    }
+    h->per_row_mode = true;
+  } else if (!h->per_row_mode) {
+    h->nullfree_push_seen = true;
+  }
+  AggTable t = h->table();
+  if (!h->per_row_mode && chunk_fast_ok(h, ch)) {
+    int g = grid_for((ch.n + 1) / 2, 256);
+    switch (h->plan.n_calls) {
+      case 1: agg_apply_fast_kernel<1><<<g, 256, 0, st>>>(t, h->plan, ch); break;
+      case 2: agg_apply_fast_kernel<2><<<g, 256, 0, st>>>(t, h->plan, ch); break;
+      case 3: agg_apply_fast_kernel<3><<<g, 256, 0, st>>>(t, h->plan, ch); break;
+      default: agg_apply_fast_kernel<4><<<g, 256, 0, st>>>(t, h->plan, ch); break;
+    }
+  } else {
+    agg_apply_kernel<<<grid_for(ch.n, 256), 256, 0, st>>>(t, h->plan, ch, h->per_row_mode ? 1 : 0);
+  }
+  RW_CUDA(cudaGetLastError());
+  h->launches++;
+  h->groups_upper += (uint64_t)ch.n;
+  h->epoch_rows += (uint64_t)ch.n;
+  return RW_OK;
+}
+
+static int agg_launch_stage(rwgpu_agg* h) {
+  AggStage& s = h->stage[h->cur];
+  if (s.rows == 0) return RW_OK;
+  uint8_t* hp = s.host.as<uint8_t>();
+  uint8_t* dp = s.dev.as<uint8_t>();
+  RW_CUDA(cudaMemcpyAsync(dp + h->off_ops, hp + h->off_ops, (size_t)s.rows, cudaMemcpyHostToDevice, h->stream));
+  DevChunk ch;
+  memset(&ch, 0, sizeof(ch));
+  ch.n = s.rows;
+  ch.ops = dp + h->off_ops;
+  ch.vis_bits = nullptr;
+  ch.n_cols = (int)h->in_types.size();
+  for (size_t k = 0; k < h->in_types.size(); k++) {
+    ch.cols[k].type = h->in_types[k];
+    ch.cols[k].width = type_width(h->in_types[k]);
+  }
+  for (int c : h->used_cols) {
+    int w = type_width(h->in_types[c]);
+    RW_CUDA(cudaMemcpyAsync(dp + h->off_data[c], hp + h->off_data[c], (size_t)s.rows * w, cudaMemcpyHostToDevice, h->stream));
+    ch.cols[c].data = dp + h->off_data[c];
+    if (s.has_valid[c]) {
+      RW_CUDA(cudaMemcpyAsync(dp + h->off_valid[c], hp + h->off_valid[c], (size_t)s.rows, cudaMemcpyHostToDevice, h->stream));
+      ch.cols[c].valid_bytes = dp + h->off_valid[c];
+    }
+  }
+  int rc = agg_apply_dev(h, ch, h->stream);
+  if (rc != RW_OK) return rc;
+  RW_CUDA(cudaEventRecord(s.done, h->stream));
+  s.in_flight = true;
+  s.rows = 0;
+  h->cur ^= 1;
+  AggStage& nx = h->stage[h->cur];
+  if (nx.in_flight) {
+    RW_CUDA(cudaEventSynchronize(nx.done));
+    nx.in_flight = false;
+  }
+  nx.rows = 0;
+  memset(nx.has_valid, 0, sizeof(nx.has_valid));
+  return RW_OK;
+}
+
+static int agg_ensure_out(rwgpu_agg* h, int64_t rows) {
+  if (rows <= h->out_cap) return RW_OK;
+  int64_t cap = std::max<int64_t>(rows, 4096);
+  RW_CUDA(h->out_ops.reserve((size_t)cap));
+  for (size_t k = 0; k < h->out_types.size(); k++) {
+    RW_CUDA(h->out_col[k].reserve((size_t)cap * type_width(h->out_types[k])));
+    RW_CUDA(h->out_valid[k].reserve((size_t)cap));
+    RW_CUDA(h->out_bits[k].reserve((size_t)((cap + 63) / 64) * 8));
+  }
+  h->out_cap = cap;
+  return RW_OK;
+}
+
+static const char* agg_err_msg(unsigned int e) {
+  if (e & AGG_ERR_OVERFLOW) return "Numeric out of range";
+  if (e & AGG_ERR_NEG_COUNT) return "row count should be non-negative";
+  if (e & AGG_ERR_RETRACT_APPEND_ONLY) return "attempt to retract on append-only min/max";
+  if (e & AGG_ERR_OUT_CAPACITY) return "internal: output capacity";
+  return "unknown";
+}
+static int agg_err_code(unsigned int e) {
+  if (e & AGG_ERR_OVERFLOW) return RW_ERR_NUMERIC_OUT_OF_RANGE;
+  if (e & (AGG_ERR_NEG_COUNT | AGG_ERR_RETRACT_APPEND_ONLY)) return RW_ERR_INCONSISTENT;
+  return RW_ERR_CUDA;
+}
+
+// run the flush kernel; on return *n_rows rows sit in the device output buffers
+static int agg_flush_dev(rwgpu_agg* h, cudaStream_t st, int64_t* n_rows, unsigned int* has_null_host) {
+  int rc = agg_launch_stage(h);
+  if (rc != RW_OK) return rc;
+  int64_t bound = (int64_t)std::min<uint64_t>(h->epoch_rows, h->groups_upper + 2) * 2 + 2;
+  rc = agg_ensure_out(h, bound);
+  if (rc != RW_OK) return rc;
+  AggStatus* ds = h->status.as<AggStatus>();
+  RW_CUDA(cudaMemsetAsync(&ds->out_rows, 0, sizeof(unsigned long long), st));
+  RW_CUDA(cudaMemsetAsync(h->out_hasnull.p, 0, sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS), st));
+  AggOutDev o;
+  o.ops = h->out_ops.as<uint8_t>();
+  for (size_t k = 0; k < h->out_types.size(); k++) { o.col[k] = h->out_col[k].p; o.valid[k] = h->out_valid[k].as<uint8_t>(); }
+  o.has_null = h->out_hasnull.as<unsigned int>();
+  o.capacity = h->out_cap;
+  uint32_t mask = h->per_row_mode ? 0u : h->all_flag_mask;
+  if (h->epoch_rows > 0) {
+    int64_t nwords = (int64_t)((h->cap + 2 + 31) >> 5);
+    agg_flush_kernel<<<grid_for(nwords * 32, 256), 256, 0, st>>>(h->table(), h->plan, o, mask);
+    RW_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+  uint8_t* sh = h->status_host.as<uint8_t>();
+  RW_CUDA(cudaMemcpyAsync(sh, h->status.p, sizeof(AggStatus), cudaMemcpyDeviceToHost, st));
+  RW_CUDA(cudaMemcpyAsync(sh + 64, h->out_hasnull.p, sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS), cudaMemcpyDeviceToHost, st));
+  RW_CUDA(cudaStreamSynchronize(st));
+  AggStatus* s = (AggStatus*)sh;
+  h->groups_upper = s->n_groups;
+  h->epoch_rows = 0;
+  h->per_row_mode = false;
+  h->nullfree_push_seen = false;
+  if (s->err) {
+    unsigned int e = s->err;
+    cudaMemsetAsync(&ds->err, 0, sizeof(unsigned int), st);
+    return fail(agg_err_code(e), agg_err_msg(e));
+  }
+  *n_rows = (int64_t)s->out_rows;
+  memcpy(has_null_host, sh + 64, sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS));
+  return RW_OK;
+}
+
+extern "C" {
+
+int32_t rwgpu_agg_create(const rw_agg_desc* d, rwgpu_agg** out) {
+  if (!d || !out) return fail(RW_ERR_INVALID, "null descriptor");
+  int rc = rwgpu_device_check();
+  if (rc != RW_OK) return rc;
+  if (d->n_group_keys < 1 || d->n_group_keys > RW_MAX_KEYS) return fail(RW_ERR_UNSUPPORTED, "1..4 group key columns supported");
+  if (d->n_calls < 1 || d->n_calls > RW_MAX_CALLS) return fail(RW_ERR_UNSUPPORTED, "1..16 agg calls supported");
+  if (d->n_input_cols > RW_MAX_COLS) return fail(RW_ERR_UNSUPPORTED, "too many input columns");
+  if (d->row_count_index < 0 || d->row_count_index >= d->n_calls) return fail(RW_ERR_INVALID, "row_count_index");
+  auto h = new rwgpu_agg();
+  std::unique_ptr<rwgpu_agg> guard(h);
+  AggPlanDev& p = h->plan;
+  memset(&p, 0, sizeof(p));
+  h->in_types.assign(d->input_types, d->input_types + d->n_input_cols);
+  for (int t : h->in_types) if (!type_supported(t)) return fail(RW_ERR_UNSUPPORTED, "unsupported input type");
+  p.n_keys = d->n_group_keys;
+  std::vector<bool> used(d->n_input_cols, false);
+  for (int k = 0; k < p.n_keys; k++) {
+    int c = d->group_key_indices[k];
+    if (c < 0 || c >= d->n_input_cols) return fail(RW_ERR_INVALID, "group key index");
+    if (h->in_types[c] == RW_T_DECIMAL) return fail(RW_ERR_UNSUPPORTED, "decimal group key");
+    p.key_col[k] = c;
+    p.key_type[k] = h->in_types[c];
+    used[c] = true;
+    h->out_types.push_back(h->in_types[c]);
+  }
+  p.single_key = (p.n_keys == 1);
+  p.KW = p.single_key ? 1 : 1 + p.n_keys;
+  p.n_calls = d->n_calls;
+  int cw = 1 + p.n_calls;
+  bool fast = p.single_key && type_width(p.key_type[0]) == 8 && !type_is_float(p.key_type[0]) && p.n_calls <= 4;
+  for (int c = 0; c < p.n_calls; c++) {
+    const rw_agg_call& call = d->calls[c];
+    p.kind[c] = call.kind;
+    p.arg_col[c] = call.arg_col;
+    p.ret_type[c] = call.ret_type;
+    p.hi_off[c] = -1;
+    p.prevhi_off[c] = -1;
+    int at = 0;
+    if (call.arg_col >= 0) {
+      if (call.arg_col >= d->n_input_cols) return fail(RW_ERR_INVALID, "agg arg index");
+      at = h->in_types[call.arg_col];
+      used[call.arg_col] = true;
+    }
+    p.arg_type[c] = at;
+    switch (call.kind) {
+      case RW_AGG_COUNT:
+        if (call.ret_type != RW_T_INT64) return fail(RW_ERR_INVALID, "count returns int8");
+        if (call.arg_col >= 0) fast = false;
+        break;
+      case RW_AGG_SUM:
+      case RW_AGG_SUM0:
+        if (call.arg_col < 0) return fail(RW_ERR_INVALID, "sum needs an argument");
+        if (at == RW_T_DECIMAL || at == RW_T_BOOL) return fail(RW_ERR_UNSUPPORTED, "sum over this type stays on the CPU executor");
+        if (type_is_float(at)) {
+          if (call.ret_type != at) return fail(RW_ERR_INVALID, "sum(float) returns the same float type");
+          fast = false;
+        } else {
+          if (call.ret_type != RW_T_INT64 && call.ret_type != RW_T_DECIMAL) return fail(RW_ERR_INVALID, "sum(int) returns int8 or decimal");
+          if (type_width(at) == 8) p.hi_off[c] = cw++;
+          if (call.ret_type == RW_T_DECIMAL) { p.prevhi_off[c] = cw++; fast = false; }
+          if (type_width(at) != 8) fast = false;
+        }
+        h->all_flag_mask |= 1u << c;
+        break;
+      case RW_AGG_MIN:
+      case RW_AGG_MAX:
+        // retractable min/max is a MaterializedInput state (agg_state.rs:49-56): CPU executor
+        if (!d->is_append_only) return fail(RW_ERR_UNSUPPORTED, "retractable min/max uses MaterializedInput state");
+        if (call.arg_col < 0 || at == RW_T_DECIMAL) return fail(RW_ERR_UNSUPPORTED, "min/max over this type");
+        if (call.ret_type != at) return fail(RW_ERR_INVALID, "min/max returns the argument type");
+        if (type_width(at) != 8 || type_is_float(at)) fast = false;
+        h->all_flag_mask |= 1u << c;
+        break;
+      default:
+        return fail(RW_ERR_UNSUPPORTED, "agg kind not offloaded");
+    }
+    h->out_types.push_back(call.ret_type);
+  }
+  if (d->calls[d->row_count_index].kind != RW_AGG_COUNT || d->calls[d->row_count_index].arg_col >= 0)
+    return fail(RW_ERR_INVALID, "row_count_index must name a count(*) call");
+  p.HW = p.KW + p.n_calls;
+  p.CW = cw;
+  p.row_count_call = d->row_count_index;
+  p.strict = d->strict_consistency;
+  h->fast_eligible = fast;
+  h->chunk_size = d->chunk_size > 0 ? d->chunk_size : 1024;
+  for (int c = 0; c < d->n_input_cols; c++) if (used[c]) h->used_cols.push_back(c);
+
+  RW_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  uint64_t want = std::max<uint64_t>(d->group_capacity_hint * 2, 1024);
+  uint64_t cap = 1024;
+  while (cap < want) cap <<= 1;
+  h->cap = cap;
+  rc = agg_alloc_table(h, cap, h->hot, h->cold, h->dirty);
+  if (rc != RW_OK) return rc;
+  RW_CUDA(h->status.reserve(sizeof(AggStatus)));
+  RW_CUDA(cudaMemsetAsync(h->status.p, 0, sizeof(AggStatus), h->stream));
+  RW_CUDA(h->out_hasnull.reserve(sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS)));
+  RW_CUDA(h->status_host.reserve(256));
+  rc = agg_init_table(h, h->table());
+  if (rc != RW_OK) return rc;
+  // staging layout: [ops | per used column: data, valid bytes], 256-byte aligned regions
+  size_t off = 0;
+  h->off_ops = off; off = align_up(off + (size_t)h->stage_cap, 256);
+  for (int c : h->used_cols) {
+    h->off_data[c] = off; off = align_up(off + (size_t)h->stage_cap * type_width(h->in_types[c]), 256);
+    h->off_valid[c] = off; off = align_up(off + (size_t)h->stage_cap, 256);
+  }
+  h->stage_bytes = off;
+  RW_CUDA(cudaStreamSynchronize(h->stream));
+  *out = guard.release();
+  return RW_OK;
+}
+
+void rwgpu_agg_destroy(rwgpu_agg* h) {
+  if (!h) return;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  delete h;
+}
+
+static int agg_stage_init(rwgpu_agg* h) {
+  for (auto& s : h->stage) {
+    if (s.host.p) continue;
+    RW_CUDA(s.host.reserve(h->stage_bytes));
+    RW_CUDA(s.dev.reserve(h->stage_bytes));
+    RW_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    s.rows = 0;
+    s.in_flight = false;
+    memset(s.has_valid, 0, sizeof(s.has_valid));
+  }
+  return RW_OK;
+}
+
+int32_t rwgpu_agg_push(rwgpu_agg* h, const rw_chunk* c) {
+  if (!h || !c) return fail(RW_ERR_INVALID, "null");
+  if (c->n_cols != (int)h->in_types.size()) return fail(RW_ERR_INVALID, "chunk schema mismatch");
+  for (int k = 0; k < c->n_cols; k++)
+    if (c->columns[k].type != h->in_types[k]) return fail(RW_ERR_INVALID, "chunk column type mismatch");
+  int rc = agg_stage_init(h);
+  if (rc != RW_OK) return rc;
+  int64_t done = 0;
+  while (done < c->n_rows) {
+    AggStage& s = h->stage[h->cur];
+    int64_t m = std::min<int64_t>(c->n_rows - done, h->stage_cap - s.rows);
+    uint8_t* hp = s.host.as<uint8_t>();
+    uint8_t* ops = hp + h->off_ops + s.rows;
+    if (c->visibility == nullptr) {
+      memcpy(ops, c->ops + done, (size_t)m);
+    } else {
+      for (int64_t i = 0; i < m; i++) {
+        int64_t r = done + i;
+        ops[i] = ((c->visibility[r >> 6] >> (r & 63)) & 1) ? c->ops[r] : 0;
+      }
+    }
+    for (int col : h->used_cols) {
+      int w = type_width(h->in_types[col]);
+      memcpy(hp + h->off_data[col] + (size_t)s.rows * w, (const uint8_t*)c->columns[col].data + (size_t)done * w, (size_t)m * w);
+      const uint64_t* vb = c->columns[col].validity;
+      uint8_t* vdst = hp + h->off_valid[col];
+      if (vb) {
+        if (!s.has_valid[col]) { memset(vdst, 1, (size_t)s.rows); s.has_valid[col] = true; }
+        for (int64_t i = 0; i < m; i++) {
+          int64_t r = done + i;
+          vdst[s.rows + i] = (uint8_t)((vb[r >> 6] >> (r & 63)) & 1);
+        }
+      } else if (s.has_valid[col]) {
+        memset(vdst + s.rows, 1, (size_t)m);
+      }
+    }
+    s.rows += m;
+    done += m;
+    if (s.rows == h->stage_cap) {
+      rc = agg_launch_stage(h);
+      if (rc != RW_OK) return rc;
+    }
+  }
+  return RW_OK;
+}
+
+int32_t rwgpu_agg_push_device(rwgpu_agg* h, const rw_chunk* c, void* cuda_stream) {
+  if (!h || !c) return fail(RW_ERR_INVALID, "null");
+  if (c->n_cols != (int)h->in_types.size()) return fail(RW_ERR_INVALID, "chunk schema mismatch");
+  DevChunk ch;
+  int rc = devchunk_from_abi(c, &ch);
+  if (rc != RW_OK) return rc;
+  rc = agg_launch_stage(h);  // keep host-staged rows ordered before this chunk
+  if (rc != RW_OK) return rc;
+  return agg_apply_dev(h, ch, cuda_stream ? (cudaStream_t)cuda_stream : h->stream);
+}
+
+int32_t rwgpu_agg_flush(rwgpu_agg* h, uint64_t /*epoch*/, rwgpu_out** out) {
+  if (!h || !out) return fail(RW_ERR_INVALID, "null");
+  int64_t n = 0;
+  unsigned int has_null[RW_MAX_KEYS + RW_MAX_CALLS];
+  int rc = agg_flush_dev(h, h->stream, &n, has_null);
+  if (rc != RW_OK) return rc;
+  auto o = new rwgpu_out();
+  o->n_rows = n;
+  o->chunk_size = h->chunk_size;
+  o->types = h->out_types;
+  o->ops.resize((size_t)n);
+  o->data.resize(h->out_types.size());
+  o->valid_bytes.resize(h->out_types.size());
+  if (n > 0) {
+    cudaMemcpyAsync(o->ops.data(), h->out_ops.p, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+    for (size_t k = 0; k < h->out_types.size(); k++) {
+      size_t w = type_width(h->out_types[k]);
+      o->data[k].resize((size_t)n * w);
+      cudaMemcpyAsync(o->data[k].data(), h->out_col[k].p, (size_t)n * w, cudaMemcpyDeviceToHost, h->stream);
+      if (has_null[k]) {
+        o->valid_bytes[k].resize((size_t)n);
+        cudaMemcpyAsync(o->valid_bytes[k].data(), h->out_valid[k].p, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+      }
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { delete o; return fail(RW_ERR_CUDA, cudaGetErrorString(e)); }
+  }
+  o->finalize();
+  *out = o;
+  return RW_OK;
+}
+
+int32_t rwgpu_agg_flush_device(rwgpu_agg* h, uint64_t /*epoch*/, rw_chunk* view, void* cuda_stream) {
+  if (!h || !view) return fail(RW_ERR_INVALID, "null");
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  int64_t n = 0;
+  unsigned int has_null[RW_MAX_KEYS + RW_MAX_CALLS];
+  int rc = agg_flush_dev(h, st, &n, has_null);
+  if (rc != RW_OK) return rc;
+  h->dev_view_cols.resize(h->out_types.size());
+  for (size_t k = 0; k < h->out_types.size(); k++) {
+    rw_column& c = h->dev_view_cols[k];
+    c.type = h->out_types[k];
+    c.reserved = 0;
+    c.data = h->out_col[k].p;
+    c.validity = nullptr;
+    if (has_null[k] && n > 0) {
+      pack_bytes_to_bits_kernel<<<grid_for((n + 63) / 64, 256), 256, 0, st>>>(h->out_valid[k].as<uint8_t>(), h->out_bits[k].as<uint64_t>(), n);
+      RW_CUDA(cudaGetLastError());
+      h->launches++;
+      c.validity = h->out_bits[k].as<uint64_t>();
+    }
+  }
+  view->n_rows = n;
+  view->n_cols = (int32_t)h->out_types.size();
+  view->reserved = 0;
+  view->ops = h->out_ops.as<uint8_t>();
+  view->visibility = nullptr;
+  view->columns = h->dev_view_cols.data();
+  return RW_OK;
+}
+
+int32_t rwgpu_agg_stats(rwgpu_agg* h, uint64_t* n_groups, uint64_t* capacity, uint64_t* launches) {
+  if (!h) return fail(RW_ERR_INVALID, "null");
+  AggStatus s;
+  RW_CUDA(cudaStreamSynchronize(h->stream));
+  RW_CUDA(cudaMemcpy(&s, h->status.p, sizeof(s), cudaMemcpyDeviceToHost));
+  if (n_groups) *n_groups = s.n_groups;
+  if (capacity) *capacity = h->cap;
+  if (launches) *launches = h->launches;
+  return RW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+// common.cuh -- shared host/device helpers for librwgpu (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rwgpu.h"
+
+namespace rw {
+
+// ------------------------------------------------------------------ errors
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+const char* last_error_cstr();
+
+#define RW_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::rw::fail(RW_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+int type_width(int t);
+bool type_is_float(int t);
+bool type_supported(int t);
+
+// ------------------------------------------------------------------ device buffer (RAII)
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  // grow-only allocation; contents are NOT preserved
+  cudaError_t reserve(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n; else p = nullptr;
+    return e;
+  }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  PinnedBuf() {}
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  ~PinnedBuf() { release(); }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+  cudaError_t reserve(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMallocHost(&p, n);
+    if (e == cudaSuccess) bytes = n; else p = nullptr;
+    return e;
+  }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+// ------------------------------------------------------------------ device-side chunk view
+#define RW_MAX_COLS 24
+#define RW_MAX_KEYS 4
+#define RW_MAX_CALLS 16
+
+struct ColRef {
+  const void* data;
+  const uint64_t* valid_bits;  // LSB-first bitmap, or nullptr
+  const uint8_t* valid_bytes;  // 1 byte / row, or nullptr
+  int32_t type;
+  int32_t width;
+};
+
+struct DevChunk {
+  int64_t n;
+  const uint8_t* ops;          // RW_OP_*; 0 = invisible (host staging folds visibility in)
+  const uint64_t* vis_bits;    // or nullptr
+  int32_t n_cols;
+  int32_t pad;
+  ColRef cols[RW_MAX_COLS];
+};
+
+// host: build a DevChunk from an rw_chunk whose pointers are DEVICE pointers
+int devchunk_from_abi(const rw_chunk* c, DevChunk* out);
+
+// ------------------------------------------------------------------ output object (host side)
+struct OutColHost {
+  int type = 0;
+  std::vector<uint8_t> data;
+  std::vector<uint64_t> valid;  // packed per chunk on demand
+  bool has_null = false;
+};
+
+}  // namespace rw
+
+// C-ABI output object: one super-chunk in host memory + lazily cut chunk views
+struct rwgpu_out {
+  int64_t n_rows = 0;
+  int chunk_size = 1024;
+  std::vector<int> types;
+  std::vector<uint8_t> ops;
+  std::vector<uint8_t> vis_bytes;          // empty = all visible
+  std::vector<std::vector<uint8_t>> data;  // per column, native width
+  std::vector<std::vector<uint8_t>> valid_bytes;  // per column, empty = no NULLs
+  // chunk cutting (StreamChunkBuilder rule: a U- is never the last row of a chunk)
+  std::vector<int64_t> cut;  // chunk i = rows [cut[i], cut[i+1])
+  // per-chunk packed bitmaps, built by finalize()
+  std::vector<std::vector<uint64_t>> chunk_vis;
+  std::vector<std::vector<std::vector<uint64_t>>> chunk_valid;
+  std::vector<std::vector<rw_column>> chunk_cols;
+  void finalize();
+};
+
+#ifdef __CUDACC__
+namespace rw {
+
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ bool bit_get(const uint64_t* w, int64_t i) {
+  return w == nullptr || ((w[i >> 6] >> (i & 63)) & 1ull);
+}
+
+__device__ __forceinline__ bool row_visible(const DevChunk& c, int64_t r, uint8_t op) {
+  return op != 0 && (c.vis_bits == nullptr || ((c.vis_bits[r >> 6] >> (r & 63)) & 1ull));
+}
+
+__device__ __forceinline__ bool col_is_null(const ColRef& c, int64_t r) {
+  if (c.valid_bits != nullptr && !((c.valid_bits[r >> 6] >> (r & 63)) & 1ull)) return true;
+  if (c.valid_bytes != nullptr && c.valid_bytes[r] == 0) return true;
+  return false;
+}
+
+// finalizer of murmur3 / splitmix64: the table hash (values never observable)
+__device__ __host__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+// sortable encoding of a double (total order, NaN canonical & largest, -0 == +0):
+// mirrors Ord on OrderedFloat (src/common/src/types/ordered_float.rs)
+__device__ __host__ __forceinline__ int64_t f64_sortable(double f) {
+  if (f != f) return INT64_MAX;
+  if (f == 0.0) f = 0.0;
+  int64_t b;
+#ifdef __CUDA_ARCH__
+  b = __double_as_longlong(f);
+#else
+  memcpy(&b, &f, 8);
+#endif
+  return b < 0 ? (b ^ 0x7fffffffffffffffLL) : b;
+}
+__device__ __host__ __forceinline__ double f64_unsortable(int64_t s) {
+  int64_t b = s < 0 ? (s ^ 0x7fffffffffffffffLL) : s;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double(b);
+#else
+  double f; memcpy(&f, &b, 8); return f;
+#endif
+}
+
+// load column value r as a 64-bit word: ints sign-extended, floats as normalised double bits
+// (HashKeySer: F32/F64 `normalized()`, -0 -> +0, canonical NaN; src/common/src/hash/key.rs:400-631)
+__device__ __forceinline__ int64_t load_i64(const ColRef& c, int64_t r) {
+  switch (c.width) {
+    case 1: return (int64_t)((const uint8_t*)c.data)[r];
+    case 2: return (int64_t)((const int16_t*)c.data)[r];
+    case 4: return (int64_t)((const int32_t*)c.data)[r];
+    default: return ((const int64_t*)c.data)[r];
+  }
+}
+__device__ __forceinline__ double load_f64(const ColRef& c, int64_t r) {
+  return c.type == RW_T_FLOAT32 ? (double)((const float*)c.data)[r] : ((const double*)c.data)[r];
+}
+__device__ __forceinline__ uint64_t load_key_word(const ColRef& c, int64_t r) {
+  if (c.type == RW_T_FLOAT32 || c.type == RW_T_FLOAT64) {
+    double f = load_f64(c, r);
+    if (f != f) return 0x7ff8000000000000ull;
+    if (f == 0.0) f = 0.0;
+    return (uint64_t)__double_as_longlong(f);
+  }
+  return (uint64_t)load_i64(c, r);
+}
+
+// store a 64-bit word into an output column of native width
+__device__ __forceinline__ void store_word(void* data, int width, int type, int64_t r, uint64_t w) {
+  switch (width) {
+    case 1: ((uint8_t*)data)[r] = (uint8_t)w; break;
+    case 2: ((int16_t*)data)[r] = (int16_t)w; break;
+    case 4:
+      if (type == RW_T_FLOAT32) ((float*)data)[r] = (float)__longlong_as_double((long long)w);
+      else ((int32_t*)data)[r] = (int32_t)w;
+      break;
+    default: ((uint64_t*)data)[r] = w; break;
+  }
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ int type_width_dev(int t) {
+  switch (t) {
+    case RW_T_BOOL: return 1;
+    case RW_T_INT16: return 2;
+    case RW_T_INT32: case RW_T_FLOAT32: case RW_T_DATE: return 4;
+    case RW_T_DECIMAL: return 16;
+    default: return 8;
+  }
+}
+
+// bytes (1 = set) -> LSB-first bitmap words; thread per output word
+__global__ void pack_bytes_to_bits_kernel(const uint8_t* bytes, uint64_t* words, int64_t n);
+
+}  // namespace rw
+#endif

@@ -1,0 +1,402 @@
+// shuffle.cu -- the hash-shuffle (vnode) path on sm_100a.
+//
+// Replaces (reference, Rust):
+//   VirtualNode::compute_chunk              src/common/src/hash/consistent_hash/vnode.rs:151-182
+//   Crc32FastBuilder / to_vnode             src/common/src/util/hash_util.rs:24-33, vnode.rs:45-50
+//   HashDataDispatcher::dispatch_data       src/stream/src/executor/dispatch.rs:961-1053
+// The reference builds one visibility bitmap per downstream actor over shared column buffers;
+// here rows are STABLY partitioned by destination GPU into contiguous regions (the send buffers
+// of an NCCL all-to-all-v), preserving per-key row order.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace rw {
+
+__device__ __forceinline__ uint32_t crc_table_entry(uint32_t i) {
+  uint32_t c = i;
+#pragma unroll
+  for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : (c >> 1);
+  return c;
+}
+
+__device__ __forceinline__ uint32_t crc_feed(const uint32_t* tab, uint32_t c, uint64_t v, int nbytes) {
+  for (int b = 0; b < nbytes; b++) {
+    c = tab[(c ^ (uint32_t)(v & 0xff)) & 0xff] ^ (c >> 8);
+    v >>= 8;
+  }
+  return c;
+}
+
+// raw_double_bits (src/common/src/types/ordered_float.rs:852-870), via Float::integer_decode
+__device__ __forceinline__ uint64_t raw_double_bits_f64(double f) {
+  if (f != f) return 0x7ff8000000000000ull;
+  uint64_t bits = (uint64_t)__double_as_longlong(f);
+  int sign_pos = (bits >> 63) == 0;
+  int e = (int)((bits >> 52) & 0x7ff);
+  uint64_t man = e == 0 ? (bits & 0xfffffffffffffull) << 1 : (bits & 0xfffffffffffffull) | 0x10000000000000ull;
+  short exp = (short)(e - (1023 + 52));
+  if (man == 0) return 0;
+  uint64_t eu = (uint64_t)(unsigned short)exp;
+  return (man & 0x000fffffffffffffull) | ((eu << 52) & 0x7ff0000000000000ull) | ((uint64_t)sign_pos << 63);
+}
+__device__ __forceinline__ uint64_t raw_double_bits_f32(float f) {
+  if (f != f) return 0x7ff8000000000000ull;
+  uint32_t bits = __float_as_uint(f);
+  int sign_pos = (bits >> 31) == 0;
+  int e = (int)((bits >> 23) & 0xff);
+  uint32_t man32 = e == 0 ? (bits & 0x7fffff) << 1 : (bits & 0x7fffff) | 0x800000;
+  short exp = (short)(e - (127 + 23));
+  uint64_t man = man32;
+  if (man == 0) return 0;
+  uint64_t eu = (uint64_t)(unsigned short)exp;
+  return (man & 0x000fffffffffffffull) | ((eu << 52) & 0x7ff0000000000000ull) | ((uint64_t)sign_pos << 63);
+}
+
+// bytes of one datum as fed to the hasher (Array::hash_at, src/common/src/array/mod.rs:280-288;
+// NULL_VAL_FOR_HASH :97).  Date/Time/Timestamp/Decimal hash through chrono / rust_decimal impls
+// that are not in the reference tree: the ABI value's LE bytes are used (self-consistent on both
+// join sides; "vnode parity unpinned" for those types).
+__device__ __forceinline__ uint32_t crc_feed_datum(const uint32_t* tab, uint32_t c, const ColRef& col, int64_t r) {
+  if (col_is_null(col, r)) return crc_feed(tab, c, 0xfffffff0ull, 4);
+  if (col.type == RW_T_FLOAT64) return crc_feed(tab, c, raw_double_bits_f64(((const double*)col.data)[r]), 8);
+  if (col.type == RW_T_FLOAT32) return crc_feed(tab, c, raw_double_bits_f32(((const float*)col.data)[r]), 8);
+  if (col.width == 16) {
+    const uint64_t* p = (const uint64_t*)col.data + r * 2;
+    c = crc_feed(tab, c, p[0], 8);
+    return crc_feed(tab, c, p[1], 8);
+  }
+  return crc_feed(tab, c, (uint64_t)load_i64(col, r), col.width);
+}
+
+struct VnodePlan {
+  int n_keys;
+  int key_col[RW_MAX_KEYS * 2];
+  int vnode_count;
+  int serial_fast;  // single Serial key: vnode taken from the row id (vnode.rs:156-176)
+};
+
+// compute_vnode_from_row_id (src/common/src/util/row_id.rs:135-173)
+__device__ __forceinline__ uint32_t vnode_from_row_id(int64_t id, int vnode_count) {
+  uint32_t vnode_bit = 10;
+  if (vnode_count > 1024) { vnode_bit = 0; while ((1u << vnode_bit) < (uint32_t)vnode_count) vnode_bit++; }
+  uint32_t seq_bit = 22 - vnode_bit;
+  uint64_t part = ((uint64_t)id >> seq_bit) & ((1ull << vnode_bit) - 1);
+  return (uint32_t)(part % (uint64_t)vnode_count);
+}
+
+__device__ __forceinline__ uint32_t row_vnode(const uint32_t* tab, const VnodePlan& p, const DevChunk& ch, int64_t r,
+                                               bool visible) {
+  if (p.serial_fast) {
+    const ColRef& c = ch.cols[p.key_col[0]];
+    if (!col_is_null(c, r)) return vnode_from_row_id(((const int64_t*)c.data)[r], p.vnode_count);
+    uint32_t crc = 0xFFFFFFFFu;  // hash the entire row
+    for (int k = 0; k < ch.n_cols; k++) crc = crc_feed_datum(tab, crc, ch.cols[k], r);
+    return (crc ^ 0xFFFFFFFFu) % (uint32_t)p.vnode_count;
+  }
+  uint32_t crc = 0xFFFFFFFFu;
+  if (visible)  // get_hash_values hashes visible rows only (data_chunk.rs:338-355)
+    for (int k = 0; k < p.n_keys; k++) crc = crc_feed_datum(tab, crc, ch.cols[p.key_col[k]], r);
+  return (crc ^ 0xFFFFFFFFu) % (uint32_t)p.vnode_count;
+}
+
+__global__ void __launch_bounds__(256) vnode_kernel(DevChunk ch, VnodePlan p, uint16_t* out) {
+  __shared__ uint32_t tab[256];
+  tab[threadIdx.x] = crc_table_entry(threadIdx.x);
+  __syncthreads();
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
+    bool vis = bit_get(ch.vis_bits, r) && (ch.ops == nullptr || ch.ops[r] != 0);
+    out[r] = (uint16_t)row_vnode(tab, p, ch, r, vis);
+  }
+}
+
+// the op rewrite of dispatch.rs:1001-1019: a visible U+ looks back to the previous visible row (its U-)
+__global__ void dispatch_rewrite_kernel(DevChunk ch, VnodePlan p, uint8_t* out_ops, unsigned int* err) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
+    uint8_t op = ch.ops[r];
+    if (op != RW_OP_UPDATE_INSERT || !row_visible(ch, r, op)) {
+      if (op != RW_OP_UPDATE_DELETE || !row_visible(ch, r, op)) out_ops[r] = op;
+      continue;
+    }
+    int64_t j = r - 1;
+    while (j >= 0 && !row_visible(ch, j, ch.ops[j])) j--;
+    if (j < 0 || ch.ops[j] != RW_OP_UPDATE_DELETE) { atomicOr(err, 1u); out_ops[r] = op; continue; }
+    bool changed = false;
+    for (int k = 0; k < p.n_keys; k++) {
+      const ColRef& c = ch.cols[p.key_col[k]];
+      bool n1 = col_is_null(c, j), n2 = col_is_null(c, r);
+      if (n1 != n2) changed = true;
+      else if (!n1) {
+        if (c.width == 16) {
+          const uint64_t* a = (const uint64_t*)c.data;
+          if (a[j * 2] != a[r * 2] || a[j * 2 + 1] != a[r * 2 + 1]) changed = true;
+        } else if (load_key_word(c, j) != load_key_word(c, r)) changed = true;
+      }
+    }
+    out_ops[j] = changed ? RW_OP_DELETE : RW_OP_UPDATE_DELETE;
+    out_ops[r] = changed ? RW_OP_INSERT : RW_OP_UPDATE_INSERT;
+  }
+}
+// a visible U- with no following visible U+ keeps its op (and is an error in the reference)
+__global__ void dispatch_rewrite_fix_kernel(DevChunk ch, uint8_t* out_ops, unsigned int* err) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
+    uint8_t op = ch.ops[r];
+    if (op != RW_OP_UPDATE_DELETE || !row_visible(ch, r, op)) continue;
+    int64_t j = r + 1;
+    while (j < ch.n && !row_visible(ch, j, ch.ops[j])) j++;
+    if (j >= ch.n || ch.ops[j] != RW_OP_UPDATE_INSERT) { atomicOr(err, 2u); out_ops[r] = op; }
+  }
+}
+
+// ------------------------------------------------------------------ stable partition by destination
+#define PART_BLOCK 256
+#define PART_ROWS_PER_BLOCK 2048
+#define PART_MAX_DEST 64
+
+// pass 1: dest per row (255 = dropped: invisible) + per-block histogram
+__global__ void __launch_bounds__(PART_BLOCK) part_hist_kernel(DevChunk ch, VnodePlan p, const int32_t* vnode_to_dest,
+                                                                int n_dest, uint8_t* dest, uint32_t* block_hist) {
+  __shared__ uint32_t tab[256];
+  __shared__ uint32_t hist[PART_MAX_DEST];
+  tab[threadIdx.x] = crc_table_entry(threadIdx.x);
+  if (threadIdx.x < PART_MAX_DEST) hist[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t base = (int64_t)blockIdx.x * PART_ROWS_PER_BLOCK;
+  for (int i = threadIdx.x; i < PART_ROWS_PER_BLOCK; i += PART_BLOCK) {
+    int64_t r = base + i;
+    if (r >= ch.n) break;
+    uint8_t op = ch.ops[r];
+    uint8_t d = 255;
+    if (row_visible(ch, r, op)) {
+      uint32_t v = row_vnode(tab, p, ch, r, true);
+      d = (uint8_t)vnode_to_dest[v];
+      atomicAdd(&hist[d], 1u);
+    }
+    dest[r] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x < n_dest) block_hist[(size_t)blockIdx.x * n_dest + threadIdx.x] = hist[threadIdx.x];
+}
+
+// pass 2: one block; per destination exclusive scan over blocks -> block offsets; totals + region starts
+__global__ void part_scan_kernel(uint32_t* block_hist, int n_blocks, int n_dest, int64_t* counts, int64_t* offsets) {
+  __shared__ int64_t totals[PART_MAX_DEST];
+  int d = threadIdx.x;
+  if (d < n_dest) {
+    uint32_t run = 0;
+    for (int b = 0; b < n_blocks; b++) {
+      uint32_t v = block_hist[(size_t)b * n_dest + d];
+      block_hist[(size_t)b * n_dest + d] = run;
+      run += v;
+    }
+    totals[d] = run;
+    counts[d] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t acc = 0;
+    for (int k = 0; k < n_dest; k++) { offsets[k] = acc; acc += totals[k]; }
+  }
+}
+
+struct PartOut {
+  uint8_t* ops;
+  void* col[RW_MAX_COLS];
+  uint8_t* valid[RW_MAX_COLS];
+};
+
+// pass 3: stable scatter.  Rows of a block are ranked per destination in row order with warp ballots.
+__global__ void __launch_bounds__(PART_BLOCK) part_scatter_kernel(DevChunk ch, const uint8_t* dest, const uint32_t* block_off,
+                                                                   int n_dest, const int64_t* offsets, PartOut o) {
+  __shared__ uint32_t run[PART_MAX_DEST];        // running count per destination within the block
+  __shared__ uint32_t warp_cnt[PART_BLOCK / 32][PART_MAX_DEST];
+  if (threadIdx.x < PART_MAX_DEST) run[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = lane_id(), wid = threadIdx.x >> 5;
+  int64_t base = (int64_t)blockIdx.x * PART_ROWS_PER_BLOCK;
+  for (int it = 0; it < PART_ROWS_PER_BLOCK / PART_BLOCK; it++) {
+    int64_t r = base + it * PART_BLOCK + threadIdx.x;
+    uint8_t d = (r < ch.n) ? dest[r] : 255;
+    // rank within warp among lanes with the same destination
+    unsigned peers = __match_any_sync(0xffffffffu, (unsigned)d);
+    unsigned rank_in_warp = __popc(peers & ((1u << lane) - 1));
+    bool leader = (rank_in_warp == 0);
+    for (int k = lane; k < n_dest; k += 32) warp_cnt[wid][k] = 0;
+    __syncwarp();
+    if (leader && d != 255) warp_cnt[wid][d] = __popc(peers);
+    __syncthreads();
+    uint32_t pos = 0;
+    if (d != 255) {
+      uint32_t before = 0;
+      for (int w = 0; w < wid; w++) before += warp_cnt[w][d];
+      pos = run[d] + before + rank_in_warp;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_dest) {
+      uint32_t tot = 0;
+      for (int w = 0; w < PART_BLOCK / 32; w++) tot += warp_cnt[w][threadIdx.x];
+      run[threadIdx.x] += tot;
+    }
+    if (d != 255) {
+      int64_t dst = offsets[d] + block_off[(size_t)blockIdx.x * n_dest + d] + pos;
+      o.ops[dst] = ch.ops[r];
+      for (int k = 0; k < ch.n_cols; k++) {
+        const ColRef& c = ch.cols[k];
+        if (o.col[k] == nullptr) continue;
+        switch (c.width) {
+          case 1: ((uint8_t*)o.col[k])[dst] = ((const uint8_t*)c.data)[r]; break;
+          case 2: ((uint16_t*)o.col[k])[dst] = ((const uint16_t*)c.data)[r]; break;
+          case 4: ((uint32_t*)o.col[k])[dst] = ((const uint32_t*)c.data)[r]; break;
+          case 8: ((uint64_t*)o.col[k])[dst] = ((const uint64_t*)c.data)[r]; break;
+          default: ((ulonglong2*)o.col[k])[dst] = ((const ulonglong2*)c.data)[r]; break;
+        }
+        if (o.valid[k]) o.valid[k][dst] = col_is_null(c, r) ? 0 : 1;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int make_vnode_plan(const rw_chunk* c, const int32_t* keys, int n_keys, int vnode_count, VnodePlan* p) {
+  if (n_keys < 1 || n_keys > RW_MAX_KEYS * 2) return fail(RW_ERR_UNSUPPORTED, "1..8 distribution key columns");
+  if (vnode_count < 1 || vnode_count > 32768) return fail(RW_ERR_INVALID, "vnode_count (vnode.rs:79 MAX_COUNT = 2^15)");
+  p->n_keys = n_keys;
+  for (int k = 0; k < n_keys; k++) {
+    if (keys[k] < 0 || keys[k] >= c->n_cols) return fail(RW_ERR_INVALID, "key index");
+    p->key_col[k] = keys[k];
+  }
+  p->vnode_count = vnode_count;
+  p->serial_fast = (n_keys == 1 && c->columns[keys[0]].type == RW_T_SERIAL) ? 1 : 0;
+  return RW_OK;
+}
+
+static int grid_rows(int64_t n, int block) {
+  int64_t g = (n + block - 1) / block;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(g, 148 * 8));
+}
+
+// upload a HOST rw_chunk into one temporary device allocation
+static int upload_chunk(const rw_chunk* c, DevBuf& buf, DevChunk* out, cudaStream_t st) {
+  if (c->n_cols > RW_MAX_COLS) return fail(RW_ERR_UNSUPPORTED, "too many columns");
+  int64_t n = c->n_rows;
+  size_t nw = (size_t)((n + 63) / 64) * 8;
+  size_t total = 256 + (size_t)n + nw;
+  for (int k = 0; k < c->n_cols; k++) {
+    int w = type_width(c->columns[k].type);
+    if (!w) return fail(RW_ERR_UNSUPPORTED, "column type");
+    total += 256 + (size_t)n * w + 256 + nw;
+  }
+  RW_CUDA(buf.reserve(total + 1024));
+  uint8_t* d = buf.as<uint8_t>();
+  size_t off = 0;
+  auto put = [&](const void* src, size_t bytes) -> const void* {
+    if (!src) return nullptr;
+    size_t o = (off + 255) / 256 * 256;
+    cudaMemcpyAsync(d + o, src, bytes, cudaMemcpyHostToDevice, st);
+    off = o + bytes;
+    return d + o;
+  };
+  memset(out, 0, sizeof(*out));
+  out->n = n;
+  out->n_cols = c->n_cols;
+  out->ops = (const uint8_t*)put(c->ops, (size_t)n);
+  out->vis_bits = (const uint64_t*)put(c->visibility, nw);
+  for (int k = 0; k < c->n_cols; k++) {
+    int w = type_width(c->columns[k].type);
+    out->cols[k].type = c->columns[k].type;
+    out->cols[k].width = w;
+    out->cols[k].data = put(c->columns[k].data, (size_t)n * w);
+    out->cols[k].valid_bits = (const uint64_t*)put(c->columns[k].validity, nw);
+  }
+  RW_CUDA(cudaGetLastError());
+  return RW_OK;
+}
+
+}  // namespace rw
+
+using namespace rw;
+
+extern "C" {
+
+int32_t rwgpu_vnode_compute(const rw_chunk* c, const int32_t* keys, int32_t n_keys, int32_t vnode_count, uint16_t* out) {
+  if (!c || !keys || !out) return fail(RW_ERR_INVALID, "null");
+  int rc = rwgpu_device_check();
+  if (rc != RW_OK) return rc;
+  VnodePlan p;
+  rc = make_vnode_plan(c, keys, n_keys, vnode_count, &p);
+  if (rc != RW_OK) return rc;
+  if (c->n_rows == 0) return RW_OK;
+  DevBuf buf, dout;
+  DevChunk ch;
+  rc = upload_chunk(c, buf, &ch, 0);
+  if (rc != RW_OK) return rc;
+  RW_CUDA(dout.reserve((size_t)c->n_rows * 2));
+  vnode_kernel<<<grid_rows(c->n_rows, 256), 256>>>(ch, p, dout.as<uint16_t>());
+  RW_CUDA(cudaGetLastError());
+  RW_CUDA(cudaMemcpy(out, dout.p, (size_t)c->n_rows * 2, cudaMemcpyDeviceToHost));
+  return RW_OK;
+}
+
+int32_t rwgpu_dispatch_rewrite_ops(const rw_chunk* c, const int32_t* keys, int32_t n_keys, uint8_t* out_ops) {
+  if (!c || !keys || !out_ops) return fail(RW_ERR_INVALID, "null");
+  int rc = rwgpu_device_check();
+  if (rc != RW_OK) return rc;
+  VnodePlan p;
+  rc = make_vnode_plan(c, keys, n_keys, 256, &p);
+  if (rc != RW_OK) return rc;
+  if (c->n_rows == 0) return RW_OK;
+  DevBuf buf, dout;
+  DevChunk ch;
+  rc = upload_chunk(c, buf, &ch, 0);
+  if (rc != RW_OK) return rc;
+  RW_CUDA(dout.reserve((size_t)c->n_rows + 16));
+  unsigned int* err = (unsigned int*)(dout.as<uint8_t>() + ((size_t)c->n_rows + 7) / 8 * 8);
+  RW_CUDA(cudaMemset(dout.p, 0, (size_t)c->n_rows + 16));
+  dispatch_rewrite_kernel<<<grid_rows(c->n_rows, 256), 256>>>(ch, p, dout.as<uint8_t>(), err);
+  dispatch_rewrite_fix_kernel<<<grid_rows(c->n_rows, 256), 256>>>(ch, dout.as<uint8_t>(), err);
+  RW_CUDA(cudaGetLastError());
+  RW_CUDA(cudaMemcpy(out_ops, dout.p, (size_t)c->n_rows, cudaMemcpyDeviceToHost));
+  unsigned int e = 0;
+  RW_CUDA(cudaMemcpy(&e, err, 4, cudaMemcpyDeviceToHost));
+  if (e & 1u) return fail(RW_ERR_INCONSISTENT, "missing U- before U+");
+  if (e & 2u) return fail(RW_ERR_INCONSISTENT, "missing U+ after U-");
+  return RW_OK;
+}
+
+int32_t rwgpu_shuffle_partition_device(const rw_chunk* c, const int32_t* keys, int32_t n_keys, int32_t vnode_count,
+                                       const int32_t* vnode_to_dest, int32_t n_dest, uint8_t* out_ops,
+                                       void* const* out_cols, uint8_t* const* out_valid_bytes, int64_t* counts,
+                                       int64_t* offsets, void* cuda_stream) {
+  if (!c || !keys || !vnode_to_dest || !out_ops || !out_cols || !counts || !offsets) return fail(RW_ERR_INVALID, "null");
+  if (n_dest < 1 || n_dest > PART_MAX_DEST) return fail(RW_ERR_UNSUPPORTED, "1..64 destinations");
+  VnodePlan p;
+  int rc = make_vnode_plan(c, keys, n_keys, vnode_count, &p);
+  if (rc != RW_OK) return rc;
+  DevChunk ch;
+  rc = devchunk_from_abi(c, &ch);
+  if (rc != RW_OK) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int n_blocks = (int)std::max<int64_t>(1, (c->n_rows + PART_ROWS_PER_BLOCK - 1) / PART_ROWS_PER_BLOCK);
+  // scratch: dest bytes + block histograms (stream-ordered allocation)
+  uint8_t* scratch = nullptr;
+  size_t dest_bytes = ((size_t)c->n_rows + 255) / 256 * 256;
+  size_t hist_bytes = (size_t)n_blocks * n_dest * 4;
+  RW_CUDA(cudaMallocAsync((void**)&scratch, dest_bytes + hist_bytes + 256, st));
+  uint8_t* dest = scratch;
+  uint32_t* hist = (uint32_t*)(scratch + dest_bytes);
+  part_hist_kernel<<<n_blocks, PART_BLOCK, 0, st>>>(ch, p, vnode_to_dest, n_dest, dest, hist);
+  part_scan_kernel<<<1, PART_MAX_DEST, 0, st>>>(hist, n_blocks, n_dest, counts, offsets);
+  PartOut o;
+  memset(&o, 0, sizeof(o));
+  o.ops = out_ops;
+  for (int k = 0; k < c->n_cols; k++) {
+    o.col[k] = out_cols[k];
+    o.valid[k] = out_valid_bytes ? out_valid_bytes[k] : nullptr;
+  }
+  part_scatter_kernel<<<n_blocks, PART_BLOCK, 0, st>>>(ch, dest, hist, n_dest, offsets, o);
+  RW_CUDA(cudaGetLastError());
+  RW_CUDA(cudaFreeAsync(scratch, st));
+  return RW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+"""CPU: the C-ABI library loads and exports every symbol include/rwgpu.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+from risingwave_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "rwgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rwgpu_\w+)\s*\(", src)))
+
+
+def test_header_and_python_symbol_lists_agree():
+    assert _header_symbols() == sorted(abi.ABI_SYMBOLS)
+
+
+def test_library_exports_every_symbol():
+    lib = abi.load_library()  # raises if librwgpu.so is not built -- there is no fallback
+    for sym in _header_symbols():
+        assert hasattr(lib, sym), sym
+
+
+def test_type_width_and_version():
+    lib = abi.load_library()
+    lib.rwgpu_type_width.restype = ctypes.c_int32
+    for t, w in abi.TYPE_WIDTH.items():
+        assert lib.rwgpu_type_width(t) == w
+    lib.rwgpu_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.rwgpu_version()
+
+
+def test_struct_sizes_match_header():
+    # x86-64 SysV layout of the structs in include/rwgpu.h
+    assert ctypes.sizeof(abi.RwColumn) == 24
+    assert ctypes.sizeof(abi.RwChunk) == 40
+    assert ctypes.sizeof(abi.RwAggCall) == 16
+    assert ctypes.sizeof(abi.RwAggDesc) == 72
+    assert ctypes.sizeof(abi.RwJoinSideDesc) == 64
+    assert ctypes.sizeof(abi.RwJoinDesc) == 192
+
+
+def test_product_does_not_reference_oracle():
+    """The product path must never import / link the oracle (it is test infrastructure)."""
+    pkg = os.path.join(ROOT, "risingwave_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in txt and "rwo_" not in txt and "oracle/" not in txt, f
