@@ -1,0 +1,224 @@
+"""GPU: HashJoin CUDA path (through the C ABI) vs the reference's golden vectors and the CPU oracle."""
+import numpy as np
+import pytest
+
+from risingwave_b200 import abi
+from risingwave_b200.executor import HashJoinExecutor, JoinParams, MockSource
+from risingwave_b200.stream_chunk import Column, StreamChunk, net_multiset, emitted_multiset
+
+from helpers import JOIN_TYPES, load_golden, run_join_kat
+
+pytestmark = pytest.mark.gpu
+
+JOIN_KATS = [k for k in load_golden("hash_join_kats.json") if "skipped" not in k]
+
+
+@pytest.mark.parametrize("kat", JOIN_KATS, ids=[k["name"] for k in JOIN_KATS])
+def test_hash_join_golden(cuda, kat):
+    """Every non-watermark test of hash_join.rs; order-insensitive (net applied multiset per step):
+    the reference's own output order is not deterministic."""
+    run_join_kat(cuda, kat, exact=False)
+
+
+def make_pair(cuda, oracle, jt, types, keys, pk, stream_key, null_safe, cond=None, append_only=False, chunk_size=1024):
+    exs = []
+    for be in (cuda, oracle):
+        _, sl = MockSource.channel()
+        _, sr = MockSource.channel()
+        exs.append(HashJoinExecutor(be, jt, sl.into_executor(types, stream_key), sr.into_executor(types, stream_key),
+                                    JoinParams(keys, pk), JoinParams(keys, pk), null_safe, None, cond, append_only, chunk_size))
+    return exs
+
+
+class StreamGen:
+    """Consistent two-sided change stream: deletes / updates always name a live row (unique pk per side)."""
+
+    def __init__(self, seed, n_keys_cols=1, key_range=12, null_frac=0.0):
+        self.rng = np.random.default_rng(seed)
+        self.live = [[], []]
+        self.next_pk = [0, 0]
+        self.kc = n_keys_cols
+        self.key_range = key_range
+        self.null_frac = null_frac
+
+    def new_row(self, side):
+        r = self.rng
+        keys = tuple(None if r.random() < self.null_frac else int(r.integers(0, self.key_range)) for _ in range(self.kc))
+        pk = self.next_pk[side]
+        self.next_pk[side] += 1
+        payload = None if r.random() < self.null_frac else int(r.integers(0, 50))
+        return keys + (pk, payload)
+
+    def chunk(self, side, n, p_delete=0.25, p_update=0.15, types=None, vis_frac=1.0):
+        rows = []
+        r = self.rng
+        live = self.live[side]
+        while len(rows) < n:
+            x = r.random()
+            if live and x < p_delete:
+                rows.append((abi.OP_DELETE, live.pop(int(r.integers(len(live)))), True))
+            elif live and x < p_delete + p_update and len(rows) + 2 <= n:
+                old = live.pop(int(r.integers(len(live))))
+                new = old[:-1] + (int(r.integers(0, 50)),)  # same key & pk, new payload
+                if r.random() < 0.3:  # key-changing update
+                    new = tuple(int(r.integers(0, self.key_range)) for _ in range(self.kc)) + new[self.kc:]
+                rows.append((abi.OP_UPDATE_DELETE, old, True))
+                rows.append((abi.OP_UPDATE_INSERT, new, True))
+                live.append(new)
+            else:
+                row = self.new_row(side)
+                vis = r.random() < vis_frac
+                rows.append((abi.OP_INSERT, row, vis))
+                if vis:
+                    live.append(row)
+        ch = StreamChunk.from_rows(types, [(op, row) for op, row, _ in rows])
+        vis = np.array([v for _, _, v in rows], dtype=bool)
+        if not vis.all():
+            ch.vis = vis
+        return ch
+
+
+def drive(exs, pushes):
+    """pushes: list of (side, chunk). Compares the net applied multiset of every push."""
+    total = 0
+    for i, (side, ch) in enumerate(pushes):
+        outs = [ex.eq_join_oneside(side, ch) for ex in exs]
+        g, o = net_multiset(outs[0]), net_multiset(outs[1])
+        assert g == o, f"push {i} side {side}: net output differs\n gpu-only {g - o}\n oracle-only {o - g}\ninput\n{ch}"
+        for oc in outs[0]:
+            assert oc.capacity() <= max(exs[0]._desc.chunk_size, 2) + 1
+        total += sum(abs(v) for v in g.values())
+    return total
+
+
+ALL_TYPES = list(JOIN_TYPES.items())
+
+
+@pytest.mark.parametrize("name,jt", ALL_TYPES, ids=[n for n, _ in ALL_TYPES])
+def test_random_stream_all_join_types(cuda, oracle, name, jt):
+    types = [abi.T_INT64, abi.T_INT64, abi.T_INT64]
+    exs = make_pair(cuda, oracle, jt, types, [0], [1], [1], [False])
+    gen = StreamGen(seed=10 + jt)
+    pushes = []
+    for i in range(24):
+        side = int(gen.rng.integers(2))
+        pushes.append((side, gen.chunk(side, int(gen.rng.integers(1, 200)), types=types)))
+    assert drive(exs, pushes) > 0
+
+
+@pytest.mark.parametrize("name,jt", ALL_TYPES, ids=[n for n, _ in ALL_TYPES])
+def test_random_stream_nulls_and_null_safe(cuda, oracle, name, jt):
+    types = [abi.T_INT64, abi.T_INT32, abi.T_INT64, abi.T_INT64]
+    exs = make_pair(cuda, oracle, jt, types, [0, 1], [2], [2], [True, False])
+    gen = StreamGen(seed=40 + jt, n_keys_cols=2, key_range=4, null_frac=0.2)
+    pushes = []
+    for i in range(16):
+        side = int(gen.rng.integers(2))
+        pushes.append((side, gen.chunk(side, int(gen.rng.integers(1, 150)), types=types, vis_frac=0.9)))
+    drive(exs, pushes)
+
+
+@pytest.mark.parametrize("name", ["Inner", "LeftOuter", "FullOuter", "RightSemi", "LeftAnti"])
+def test_random_stream_with_condition(cuda, oracle, name):
+    types = [abi.T_INT64, abi.T_INT64, abi.T_INT64]
+    exs = make_pair(cuda, oracle, JOIN_TYPES[name], types, [0], [1], [1], [False], cond="(less_than:boolean $2:int8 $5:int8)")
+    gen = StreamGen(seed=77)
+    pushes = []
+    for i in range(16):
+        side = int(gen.rng.integers(2))
+        pushes.append((side, gen.chunk(side, int(gen.rng.integers(1, 150)), types=types)))
+    drive(exs, pushes)
+
+
+def test_same_pk_insert_delete_in_one_chunk(cuda, oracle):
+    """`+ 3 8` then `- 3 8` in one chunk (hash_join.rs:1819-1823), U-/U+ with equal pk, and a
+    delete-then-reinsert of the same pk: the sequential own-side rule."""
+    types = [abi.T_INT64, abi.T_INT64]
+    exs = make_pair(cuda, oracle, abi.JOIN_INNER, types, [0], [1], [1], [False])
+    L, R = 0, 1
+    pushes = [
+        (L, StreamChunk.from_pretty(" I I\n + 3 8\n - 3 8\n + 3 9\n + 4 1")),
+        (R, StreamChunk.from_pretty(" I I\n + 3 100\n + 4 101")),
+        (L, StreamChunk.from_pretty(" I I\n - 3 9\n + 3 9\n - 3 9\n + 3 9\n U- 4 1\n U+ 4 1")),
+        (R, StreamChunk.from_pretty(" I I\n + 3 102\n - 3 100")),
+        (L, StreamChunk.from_pretty(" I I\n - 3 9\n - 4 1")),
+        (R, StreamChunk.from_pretty(" I I\n + 3 103\n + 4 104")),
+    ]
+    drive(exs, pushes)
+
+
+def test_strict_missing_delete(cuda):
+    types = [abi.T_INT64, abi.T_INT64]
+    for jt in (abi.JOIN_INNER, abi.JOIN_LEFT_OUTER):
+        _, sl = MockSource.channel()
+        _, sr = MockSource.channel()
+        ex = HashJoinExecutor(cuda, jt, sl.into_executor(types, [1]), sr.into_executor(types, [1]),
+                              JoinParams([0], [1]), JoinParams([0], [1]), [False])
+        with pytest.raises(abi.RwError) as e:
+            ex.eq_join_oneside(0, StreamChunk.from_pretty(" I I\n - 1 1"))
+        assert e.value.code == abi.RW_ERR_INCONSISTENT
+
+
+def test_high_amplification_and_chunk_cut(cuda, oracle):
+    """one key with 3000 build rows: a probe row emits 3000 rows cut into <= chunk_size chunks."""
+    types = [abi.T_INT64, abi.T_INT64]
+    exs = make_pair(cuda, oracle, abi.JOIN_INNER, types, [0], [1], [1], [False], chunk_size=256)
+    n = 3000
+    build = StreamChunk(np.full(n, abi.OP_INSERT, np.uint8), [Column(abi.T_INT64, np.full(n, 7, np.int64)), Column(abi.T_INT64, np.arange(n, dtype=np.int64))])
+    probe = StreamChunk.from_pretty(" I I\n + 7 1\n + 8 2\n + 7 3")
+    tot = drive(exs, [(1, build), (0, probe), (0, StreamChunk.from_pretty(" I I\n - 7 1"))])
+    assert tot == 2 * n + n
+
+
+def test_empty_and_ragged(cuda, oracle):
+    types = [abi.T_INT64, abi.T_INT64]
+    exs = make_pair(cuda, oracle, abi.JOIN_FULL_OUTER, types, [0], [1], [1], [False])
+    gen = StreamGen(seed=5)
+    pushes = [(0, StreamChunk.from_pretty(" I I")), (1, StreamChunk.from_pretty(" I I\n + 1 1 D"))]
+    for n in (1, 63, 64, 65, 1025):
+        pushes.append((n % 2, gen.chunk(n % 2, n, types=[abi.T_INT64] * 3).slice(0, n)))
+    exs = make_pair(cuda, oracle, abi.JOIN_FULL_OUTER, [abi.T_INT64] * 3, [0], [1], [1], [False])
+    drive(exs, [p for p in pushes if len(p[1].columns) == 3])
+
+
+def test_large_inner_join_properties(cuda):
+    """BASELINE cfg3 shape at reduced build size: 1M auctions (unique id) then 2M bids probing them.
+    Size-independent properties: every bid matches exactly one auction (|out| == |bids|), the output
+    preserves (bid payload, auction payload) pairing, and deleting all bids emits the exact inverse."""
+    rng = np.random.default_rng(3)
+    nb, npz = 1 << 20, 1 << 21
+    ids = rng.permutation(nb).astype(np.int64)
+    seller = rng.integers(0, 1000, nb).astype(np.int64)
+    types = [abi.T_INT64, abi.T_INT64]
+    _, sl = MockSource.channel()
+    _, sr = MockSource.channel()
+    ex = HashJoinExecutor(cuda, abi.JOIN_INNER, sl.into_executor(types, [1]), sr.into_executor(types, [0]),
+                          JoinParams([0], [1]), JoinParams([0], []), [False], capacity_hint=nb)
+    out = ex.eq_join_oneside(1, StreamChunk(np.full(nb, abi.OP_INSERT, np.uint8), [Column(abi.T_INT64, ids), Column(abi.T_INT64, seller)]))
+    assert out == []
+    auction = rng.integers(0, nb, npz).astype(np.int64)
+    bidpk = np.arange(npz, dtype=np.int64)
+    seller_of = np.zeros(nb, np.int64)
+    seller_of[ids] = seller
+    tot = 0
+    chk = 0
+    B = 1 << 18
+    for i in range(0, npz, B):
+        sl_ = slice(i, i + B)
+        o = ex.eq_join_oneside(0, StreamChunk(np.full(B, abi.OP_INSERT, np.uint8), [Column(abi.T_INT64, auction[sl_]), Column(abi.T_INT64, bidpk[sl_])]))
+        for c in o:
+            assert (c.ops == abi.OP_INSERT).all() and c.vis is None
+            a, b, rid, rs = (c.columns[k].data for k in range(4))
+            assert np.array_equal(a, rid) and np.array_equal(rs, seller_of[a]) and np.array_equal(auction[b], a)
+            tot += len(a)
+            chk += int(b.sum())
+    assert tot == npz and chk == int(bidpk.sum())
+    # retract the first 2^18 bids: exact inverse
+    o = ex.eq_join_oneside(0, StreamChunk(np.full(B, abi.OP_DELETE, np.uint8), [Column(abi.T_INT64, auction[:B]), Column(abi.T_INT64, bidpk[:B])]))
+    assert sum(c.capacity() for c in o) == B and all((c.ops == abi.OP_DELETE).all() for c in o)
+    # an auction update (U-/U+) now sees only the remaining bids
+    cnt = np.bincount(auction[B:], minlength=nb)
+    k = int(np.argmax(cnt))
+    upd = StreamChunk.from_pretty(f" I I\n U- {k} {seller_of[k]}\n U+ {k} 5555")
+    o = ex.eq_join_oneside(1, upd)
+    assert sum(c.capacity() for c in o) == 2 * int(cnt[k])
