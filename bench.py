@@ -1,0 +1,495 @@
+#!/usr/bin/env python3
+"""bench.py -- Nexmark-shaped streaming HashJoin (headline) and HashAgg (secondary) throughput.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload join|agg]
+
+Workload (BASELINE.json configs[2], "Nexmark q7/q8 streaming HashJoin (bid x auction) 1xB200, 10M build
+rows in HBM"):  the auction side (10 000 000 rows: id, seller, category, expires)
+is loaded into the right-side join state, then every STEP pushes one batch of 2^20 bid rows
+(auction, date_time, bidder, price; 1024 StreamChunks of 1024 rows coalesced into one device batch)
+through the inner-join operator: each bid probes the auction state (1 match), the joined 8-column
+rows are emitted, and the bid is inserted into the left-side state.  metric = input rows / s.
+N > 1 (configs[3]): every rank generates its own bid / auction shard, partitions it by the
+reference's CRC32 vnode on the GPU, exchanges rows with NCCL all-to-all-v and joins its vnode
+range (weak scaling: 10M build rows and 2^20 bid rows per step PER GPU).
+
+`value`   : inputs already resident in HBM, `rwgpu_join_push_device` (CUDA-event timed).
+`e2e`     : the same steps through the host-buffer C-ABI call `rwgpu_join_push` (host numpy chunks in,
+            host output chunks out; H2D / D2H inside the timed region).
+`secondary`: BASELINE configs[1] (q4-shaped HashAgg: count(*), sum, max GROUP BY auction, 2^18-row epochs).
+`--impl reference`: the CPU restatement of the reference algorithm (oracle/fastcpu.cc, one
+single-threaded actor per host core, inputs pre-partitioned by vnode) on a bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BUILD = 10_000_000
+BATCH = 1 << 20
+CHUNK = 1024
+SEED = 0x20210410
+AGG_EPOCH_ROWS = 1 << 18
+AGG_KEYS = 1 << 20
+AGG_SEED = 0x20210401
+
+# algorithmic bytes per input row; see DESIGN.md "Roofline arithmetic"
+JOIN_BYTES_PER_ROW_STEP = 194.125    # probe + emit + own-side insert, m = 1
+JOIN_BYTES_PER_ROW_PROBE = 146.125   # dominant kernel only: W_u + 1.125 + S + m*(W_m + W_out + 1)
+AGG_BYTES_PER_ROW_FLOOR = 73.125     # W_in + 1.125 + K + 2A
+
+
+# ------------------------------------------------------------------------------------------ data
+def splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def gen_auctions(n, seed, id_base=0):
+    """auction rows in a pseudo-random arrival order: (id, seller, category, expires)."""
+    with np.errstate(over="ignore"):
+        i = np.arange(n, dtype=np.uint64)
+        order = np.argsort(splitmix64(i ^ np.uint64(seed)), kind="stable")
+        ids = (order.astype(np.int64) + id_base)
+        seller = (splitmix64(i ^ np.uint64(seed + 1)) % np.uint64(1_000_000)).astype(np.int64)
+        category = (np.uint64(10) + splitmix64(i ^ np.uint64(seed + 2)) % np.uint64(5)).astype(np.int64)
+        expires = (splitmix64(i ^ np.uint64(seed + 3)) % np.uint64(1 << 40)).astype(np.int64)
+    return [ids, seller, category, expires]
+
+
+def gen_bids(n, start, seed, n_auction, id_base=0):
+    """bid rows (auction, date_time [unique, the stream key], bidder, price)."""
+    with np.errstate(over="ignore"):
+        i = np.arange(start, start + n, dtype=np.uint64)
+        auction = (splitmix64(i ^ np.uint64(seed + 10)) % np.uint64(n_auction)).astype(np.int64) + id_base
+        date_time = i.astype(np.int64) + 1_600_000_000_000_000
+        bidder = (splitmix64(i ^ np.uint64(seed + 11)) % np.uint64(1_000_000)).astype(np.int64)
+        price = (splitmix64(i ^ np.uint64(seed + 12)) % np.uint64(1 << 24)).astype(np.int64)
+    return [auction, date_time, bidder, price]
+
+
+def gen_agg_rows(n, start, seed):
+    with np.errstate(over="ignore"):
+        i = np.arange(start, start + n, dtype=np.uint64)
+        key = (splitmix64(i ^ np.uint64(seed)) % np.uint64(AGG_KEYS)).astype(np.int64)
+        price = (splitmix64(i ^ np.uint64(seed + 7)) % np.uint64(1 << 24)).astype(np.int64)
+    return [key, price]
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+class FastCpu:
+    def __init__(self):
+        p = os.path.join(ROOT, "oracle", "_build", "libfastcpu.so")
+        if not os.path.exists(p):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+        f = C.CDLL(p)
+        f.rwf_join_new.restype = C.c_void_p
+        f.rwf_join_free.argtypes = [C.c_void_p]
+        f.rwf_join_reserve.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        f.rwf_join_push.restype = C.c_int64
+        f.rwf_join_push.argtypes = [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 5
+        f.rwf_agg_new.restype = C.c_void_p
+        f.rwf_agg_new.argtypes = [C.c_int]
+        f.rwf_agg_free.argtypes = [C.c_void_p]
+        f.rwf_agg_reserve.argtypes = [C.c_void_p, C.c_uint64]
+        f.rwf_agg_push.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        f.rwf_agg_flush.restype = C.c_int64
+        f.rwf_agg_flush.argtypes = [C.c_void_p]
+        self.f = f
+
+
+def vnode_of_int64(keys):
+    """crc32(8 LE bytes) % 256 per key (vnode.rs:45-50) -- numpy table-driven, used to pre-partition
+    the CPU arm's input the way HashDataDispatcher would deliver it."""
+    tab = np.zeros(256, dtype=np.uint32)
+    for i in range(256):
+        c = i
+        for _ in range(8):
+            c = (0xEDB88320 ^ (c >> 1)) if (c & 1) else (c >> 1)
+        tab[i] = c
+    crc = np.full(len(keys), 0xFFFFFFFF, dtype=np.uint32)
+    u = keys.astype(np.uint64)
+    for b in range(8):
+        byte = ((u >> np.uint64(8 * b)) & np.uint64(0xFF)).astype(np.uint32)
+        crc = tab[(crc ^ byte) & 0xFF] ^ (crc >> 8)
+    return ((crc ^ 0xFFFFFFFF) % 256).astype(np.int32)
+
+
+def cpu_join_run(n_build, batches, n_actors, warmup, steps, chunk=CHUNK):
+    """P single-threaded actors (one per vnode range), each fed 1024-row chunks of its partition.
+    Returns rows/s over the timed steps (wall clock, all actors in parallel)."""
+    fc = FastCpu().f
+    actors = [fc.rwf_join_new() for _ in range(n_actors)]
+    auct = gen_auctions(n_build, SEED)
+    a_part = vnode_of_int64(auct[0]) * n_actors // 256
+    ones = np.full(max(n_build, BATCH), 1, np.uint8)
+
+    def feed(actor, side, cols):
+        n = len(cols[0])
+        for i in range(0, n, chunk):
+            m = min(chunk, n - i)
+            fc.rwf_join_push(actor, side, m, ones.ctypes.data, *[c[i:].ctypes.data for c in cols])
+
+    def build(a):
+        sel = np.nonzero(a_part == a)[0]
+        cols = [np.ascontiguousarray(c[sel]) for c in auct]
+        fc.rwf_join_reserve(actors[a], 1, len(sel))
+        fc.rwf_join_reserve(actors[a], 0, len(sel))
+        feed(actors[a], 1, cols)
+
+    ths = [threading.Thread(target=build, args=(a,)) for a in range(n_actors)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    parts = []
+    for cols in batches:
+        p = vnode_of_int64(cols[0]) * n_actors // 256
+        parts.append([[np.ascontiguousarray(c[p == a]) for c in cols] for a in range(n_actors)])
+    out_rows = [0]
+
+    def run_step(s):
+        def work(a):
+            feed(actors[a], 0, parts[s][a])
+        ths = [threading.Thread(target=work, args=(a,)) for a in range(n_actors)]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+
+    for s in range(warmup):
+        run_step(s)
+    t0 = time.perf_counter()
+    for s in range(warmup, warmup + steps):
+        run_step(s)
+    dt = time.perf_counter() - t0
+    rows = sum(len(batches[s][0]) for s in range(warmup, warmup + steps))
+    for a in actors:
+        fc.rwf_join_free(a)
+    return rows / dt, dt
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from risingwave_b200 import abi, device
+    from risingwave_b200.executor import AggCall, Backend, HashAggExecutor, HashJoinExecutor, JoinParams, MockSource
+    from risingwave_b200.stream_chunk import Column, StreamChunk
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    be = Backend.cuda()
+    K, W = args.steps, args.warmup
+    T4 = [abi.T_INT64] * 4
+    stream = torch.cuda.Stream()
+
+    def new_join(hint_l, hint_r):
+        _, sl = MockSource.channel()
+        _, sr = MockSource.channel()
+        # left = bid (key col 0, stream key date_time), right = auction (key col 0 = id = stream key)
+        return HashJoinExecutor(be, abi.JOIN_INNER, sl.into_executor(T4, [1]), sr.into_executor(T4, [0]),
+                                JoinParams([0], [1]), JoinParams([0], []), [False],
+                                capacity_hint=int(1.15 * max(N_BUILD, (K + W) * BATCH)))
+
+    def to_dev(cols):
+        return [torch.from_numpy(c).cuda() for c in cols]
+
+    def dchunk(cols_dev):
+        n = cols_dev[0].numel()
+        return device.DeviceChunk(torch.ones(n, dtype=torch.uint8, device="cuda"), cols_dev, T4)
+
+    id_base = rank * N_BUILD
+    auct = gen_auctions(N_BUILD, SEED + rank * 1000, id_base)
+    # bids of rank r reference auctions of ALL ranks (so the shuffle really moves rows)
+    n_auction_total = N_BUILD * world
+    batches_host = [gen_bids(BATCH, (rank * (K + W) + s) * BATCH, SEED, n_auction_total) for s in range(K + W)]
+
+    if world > 1:
+        from risingwave_b200 import exchange
+        ex_plan = exchange.ShufflePlan(world, rank, key_indices=[0], types=T4)
+
+    def shuffled(cols_dev):
+        if world == 1:
+            return dchunk(cols_dev)
+        ops, cols = ex_plan.exchange(dchunk(cols_dev), stream)
+        return device.DeviceChunk(ops, cols, T4)
+
+    with torch.cuda.stream(stream):
+        # ---------------- build side (untimed; reported separately)
+        join = new_join(0, 0)
+        auct_dev = to_dev(auct)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(0, N_BUILD, BATCH):
+            device.join_push_device(join, abi.SIDE_RIGHT, shuffled([c[i:i + BATCH] for c in auct_dev]), stream)
+        torch.cuda.synchronize()
+        build_s = time.perf_counter() - t0
+        batches_dev = [to_dev(b) for b in batches_host]
+        torch.cuda.synchronize()
+
+        def step(s):
+            return device.join_push_device(join, abi.SIDE_LEFT, shuffled(batches_dev[s]), stream)
+
+        for s in range(W):
+            step(s)
+        device.profile(join, "join", True)
+        l0 = device.launches(join, "join")
+        sampler = ClockSampler(local_rank)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out_rows = 0
+        for s in range(W, W + K):
+            out_rows += step(s).n_rows
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        kern_ms, kern_n = device.profile(join, "join", False)
+        launches = device.launches(join, "join") - l0
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            orow = torch.tensor([out_rows], device="cuda", dtype=torch.int64)
+            dist.all_reduce(orow)
+            out_rows = int(orow.item())
+        rows_total = K * BATCH * world
+        value = rows_total / (ms / 1e3)
+
+        # ---------------- e2e: host buffers through rwgpu_join_push (rank-local; N=1 only)
+        e2e = None
+        secondary = None
+        if world == 1:
+            del join
+            torch.cuda.empty_cache()
+            join2 = new_join(0, 0)
+            for i in range(0, N_BUILD, BATCH):
+                device.join_push_device(join2, abi.SIDE_RIGHT, dchunk([c[i:i + BATCH] for c in auct_dev]), stream)
+            torch.cuda.synchronize()
+            FFI_ROWS = 1 << 18  # 256 coalesced 1024-row chunks per C-ABI call
+            ones = np.ones(FFI_ROWS, np.uint8)
+
+            def host_step(s):
+                tot, d2h = 0, 0
+                for i in range(0, BATCH, FFI_ROWS):
+                    ch = StreamChunk(ones, [Column(abi.T_INT64, c[i:i + FFI_ROWS]) for c in batches_host[s]])
+                    outs = join2.eq_join_oneside(abi.SIDE_LEFT, ch)
+                    for o in outs:
+                        tot += o.capacity()
+                d2h = tot * (8 * 8 + 1)
+                return tot, d2h
+
+            for s in range(W):
+                host_step(s)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            d2h = 0
+            for s in range(W, W + K):
+                tot, b = host_step(s)
+                d2h += b
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            e2e = {"value": K * BATCH / dt, "unit": "rows/s", "h2d_bytes_per_step": BATCH * (4 * 8 + 1),
+                   "d2h_bytes_per_step": d2h // K, "ffi_batch_rows": FFI_ROWS, "ms_per_step": dt / K * 1e3,
+                   "note": "includes the python-side copy of output chunks into numpy (StreamChunk.from_abi)"}
+            del join2
+            torch.cuda.empty_cache()
+
+            # ---------------- secondary: q4-shaped HashAgg (configs[1])
+            _, src = MockSource.channel()
+            agg = HashAggExecutor(be, src.into_executor([abi.T_INT64] * 2, []), True,
+                                  [AggCall.from_pretty(c) for c in ("(count:int8)", "(sum:int8 $1:int8)", "(max:int8 $1:int8)")],
+                                  0, [0], group_capacity_hint=AGG_KEYS)
+            n_ep_w, n_ep = 4, 60
+            ep_dev = []
+            for e in range(n_ep_w + n_ep):
+                k, p = gen_agg_rows(AGG_EPOCH_ROWS, e * AGG_EPOCH_ROWS, AGG_SEED)
+                ep_dev.append(device.DeviceChunk(torch.ones(AGG_EPOCH_ROWS, dtype=torch.uint8, device="cuda"),
+                                                 [torch.from_numpy(k).cuda(), torch.from_numpy(p).cuda()], [abi.T_INT64] * 2))
+            torch.cuda.synchronize()
+            for e in range(n_ep_w):
+                device.agg_push_device(agg, ep_dev[e], stream)
+                device.agg_flush_device(agg, e + 1, stream)
+            device.profile(agg, "agg", True)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            delta_rows = 0
+            for e in range(n_ep_w, n_ep_w + n_ep):
+                device.agg_push_device(agg, ep_dev[e], stream)
+                delta_rows += device.agg_flush_device(agg, e + 1, stream).n_rows
+            a1.record(stream)
+            torch.cuda.synchronize()
+            ams = a0.elapsed_time(a1)
+            akern_ms, akern_n = device.profile(agg, "agg", False)
+            d = delta_rows / 2 / (n_ep * AGG_EPOCH_ROWS)  # dirty groups per input row (U-/U+ pairs dominate)
+            peak, which = measured_peak_hbm()
+            agg_bytes_row = AGG_BYTES_PER_ROW_FLOOR
+            secondary = {"workload": "nexmark_q4_hashagg_cfg2: count(*),sum,max GROUP BY auction; 2^20 keys uniform; "
+                                     "2^18-row epochs (256 chunks x 1024)",
+                         "metric": "rows/s", "value": n_ep * AGG_EPOCH_ROWS / (ams / 1e3), "epochs": n_ep,
+                         "delta_rows_per_input_row": delta_rows / (n_ep * AGG_EPOCH_ROWS),
+                         "roofline": {"bound": "hbm", "kernel": "agg_apply_fast_kernel<3>",
+                                      "achieved": agg_bytes_row * AGG_EPOCH_ROWS * akern_n / (akern_ms / 1e3) / 1e9 if akern_ms else None,
+                                      "peak": peak, "unit": "GB/s",
+                                      "frac": (agg_bytes_row * AGG_EPOCH_ROWS * akern_n / (akern_ms / 1e3) / 1e9 / peak) if akern_ms else None,
+                                      "traffic": None, "peak_source": which,
+                                      "algorithmic_bytes_per_row": agg_bytes_row, "kernel_ms_avg": akern_ms / max(akern_n, 1)}}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, which = measured_peak_hbm()
+    probe_gbs = JOIN_BYTES_PER_ROW_PROBE * BATCH * kern_n / (kern_ms / 1e3) / 1e9 if kern_ms else None
+    line = {
+        "metric": "Nexmark q7/q8-shaped streaming HashJoin input rows/s", "value": value, "unit": "rows/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "nexmark_q7q8_hashjoin_cfg3" if world == 1 else "nexmark_q8_shuffled_hashjoin_cfg4",
+                   "build_rows_per_gpu": N_BUILD, "probe_rows_per_step_per_gpu": BATCH, "chunk_rows": CHUNK,
+                   "chunks_coalesced_per_launch": BATCH // CHUNK, "join": "inner bid.auction = auction.id, Key64, 4+4 int64 cols, 8 out cols",
+                   "l2": "inputs_larger_than_l2 (fresh 32 MiB batch per step; 1.3 GB state)",
+                   "exchange": None if world == 1 else "crc32 vnode partition kernel + NCCL all_to_all_single per column"},
+        "build_rows_per_s": N_BUILD * world / build_s,
+        "out_rows": out_rows,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "join_inner_probe_emit_kernel", "achieved": probe_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": probe_gbs / peak if probe_gbs else None, "traffic": None, "peak_source": which,
+                     "algorithmic_bytes_per_row": JOIN_BYTES_PER_ROW_PROBE, "kernel_ms_avg": kern_ms / max(kern_n, 1),
+                     "kernel_share_of_step": kern_ms / ms if ms else None,
+                     "whole_step_GBps": JOIN_BYTES_PER_ROW_STEP * BATCH * K * world / (ms / 1e3) / 1e9},
+        "e2e": e2e,
+        "secondary": secondary,
+    }
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        nb = 4
+        sample = [gen_bids(1 << 18, s << 18, SEED, N_BUILD) for s in range(nb)]
+        v, dt = cpu_join_run(N_BUILD, sample, 1, 1, nb - 1, CHUNK)
+        line["cpu_baseline"] = {"value": v, "unit": "rows/s", "cores": 1, "kind": "port",
+                                "sample": f"oracle/fastcpu.cc single actor, 10M-row build (untimed) then {nb - 1} x 2^18 bid rows "
+                                          f"in 1024-row chunks ({dt:.1f} s); host has {cores} cores"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """CPU arm: restatement of the reference algorithm on all host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    P = max(1, min(cores, 64))
+    K, W = args.steps, args.warmup
+    step_rows = 1 << 19  # bounded sample of the 2^20-row step
+    n_steps = min(K, 8)
+    batches = [gen_bids(step_rows, s * step_rows, SEED, N_BUILD) for s in range(W + n_steps)]
+    v, dt = cpu_join_run(N_BUILD, batches, P, W, n_steps, CHUNK)
+    line = {"impl": "reference", "metric": "Nexmark q7/q8-shaped streaming HashJoin input rows/s", "value": v, "unit": "rows/s",
+            "n_gpus": world, "steps": n_steps, "warmup": W, "ms_per_step": dt / n_steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "nexmark_q7q8_hashjoin_cfg3", "build_rows_per_gpu": N_BUILD,
+                       "probe_rows_per_step_per_gpu": BATCH, "chunk_rows": CHUNK},
+            "cpu_baseline": {"value": v, "unit": "rows/s", "cores": P, "kind": "port",
+                             "sample": f"oracle/fastcpu.cc: {P} single-threaded actors (vnode-partitioned input), 10M-row build untimed, "
+                                       f"{n_steps} steps of 2^19 bid rows in 1024-row chunks; the Rust reference cannot be built here"},
+            "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

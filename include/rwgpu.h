@@ -147,6 +147,11 @@ int32_t rwgpu_agg_flush(rwgpu_agg* h, uint64_t epoch, rwgpu_out** out);
 int32_t rwgpu_agg_flush_device(rwgpu_agg* h, uint64_t epoch, rw_chunk* view, void* cuda_stream);
 /* number of groups currently held / table capacity (diagnostics, join_cached_entry_count-like) */
 int32_t rwgpu_agg_stats(rwgpu_agg* h, uint64_t* n_groups, uint64_t* capacity, uint64_t* kernel_launches);
+/* device-time accounting of the dominant kernel (the fused group-by + aggregate apply kernel):
+ * enable != 0 starts bracketing every launch with CUDA events on the launching stream; the call
+ * returns the accumulated milliseconds / launch count since the previous call and resets them
+ * (feeds the `join_match_duration_ns`-style metrics, streaming_stats.rs:94-100, and bench.py).  */
+int32_t rwgpu_agg_profile(rwgpu_agg* h, int32_t enable, double* kernel_ms, uint64_t* kernel_launches);
 
 /* ================================================================ HashJoin ==================
  * replaces HashJoinExecutor (src/stream/src/executor/hash_join.rs):
@@ -220,6 +225,8 @@ int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* chun
 int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t epoch);
 int32_t rwgpu_join_stats(rwgpu_join* h, uint64_t* left_rows, uint64_t* right_rows,
                          uint64_t* kernel_launches);
+/* same as rwgpu_agg_profile for the join's dominant kernel (probe + emit). */
+int32_t rwgpu_join_profile(rwgpu_join* h, int32_t enable, double* kernel_ms, uint64_t* kernel_launches);
 
 /* ================================================================ hash shuffle ==============
  * replaces VirtualNode::compute_chunk (src/common/src/hash/consistent_hash/vnode.rs:151-182)

@@ -571,6 +571,7 @@ struct rwgpu_agg {
   bool per_row_mode = false, nullfree_push_seen = false;
   uint32_t all_flag_mask = 0;
   uint64_t launches = 0;
+  KernelProf prof;
   bool fast_eligible = false;
   // staging (host pushes)
   AggStage stage[2];
@@ -685,6 +686,7 @@ static int agg_apply_dev(rwgpu_agg* h, const DevChunk& ch, cudaStream_t st) {
     h->nullfree_push_seen = true;
   }
   AggTable t = h->table();
+  h->prof.begin(st);
   if (!h->per_row_mode && chunk_fast_ok(h, ch)) {
     int g = grid_for((ch.n + 1) / 2, 256);
     switch (h->plan.n_calls) {
@@ -696,6 +698,7 @@ static int agg_apply_dev(rwgpu_agg* h, const DevChunk& ch, cudaStream_t st) {
   } else {
     agg_apply_kernel<<<grid_for(ch.n, 256), 256, 0, st>>>(t, h->plan, ch, h->per_row_mode ? 1 : 0);
   }
+  h->prof.end(st);
   RW_CUDA(cudaGetLastError());
   h->launches++;
   h->groups_upper += (uint64_t)ch.n;
@@ -1062,6 +1065,18 @@ int32_t rwgpu_agg_flush_device(rwgpu_agg* h, uint64_t /*epoch*/, rw_chunk* view,
   view->ops = h->out_ops.as<uint8_t>();
   view->visibility = nullptr;
   view->columns = h->dev_view_cols.data();
+  return RW_OK;
+}
+
+int32_t rwgpu_agg_profile(rwgpu_agg* h, int32_t enable, double* ms, uint64_t* launches) {
+  if (!h) return fail(RW_ERR_INVALID, "null");
+  RW_CUDA(cudaDeviceSynchronize());
+  h->prof.collect();
+  if (ms) *ms = h->prof.ms;
+  if (launches) *launches = h->prof.n;
+  h->prof.ms = 0;
+  h->prof.n = 0;
+  h->prof.on = enable != 0;
   return RW_OK;
 }
 

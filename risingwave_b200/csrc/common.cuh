@@ -70,6 +70,34 @@ struct PinnedBuf {
   template <class T> T* as() const { return (T*)p; }
 };
 
+// ------------------------------------------------------------------ CUDA-event bracket of one kernel family
+struct KernelProf {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;  // pairs
+  size_t used = 0;
+  double ms = 0;
+  uint64_t n = 0;
+  ~KernelProf() { for (auto e : ev) cudaEventDestroy(e); }
+  void begin(cudaStream_t st) {
+    if (!on) return;
+    if (used + 2 > ev.size()) { cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ev.push_back(a); ev.push_back(b); }
+    cudaEventRecord(ev[used], st);
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(ev[used + 1], st);
+    used += 2;
+  }
+  // caller has synchronised the stream(s)
+  void collect() {
+    for (size_t i = 0; i + 1 < used; i += 2) {
+      float t = 0;
+      if (cudaEventElapsedTime(&t, ev[i], ev[i + 1]) == cudaSuccess) { ms += t; n++; }
+    }
+    used = 0;
+  }
+};
+
 // ------------------------------------------------------------------ device-side chunk view
 #define RW_MAX_COLS 24
 #define RW_MAX_KEYS 4

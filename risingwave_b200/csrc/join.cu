@@ -749,6 +749,7 @@ struct rwgpu_join {
   int chunk_size = 1024;
   bool fast_inner = false;
   uint64_t launches = 0;
+  KernelProf prof;
   // scratch
   DevBuf sk, sk_alt, packed, offs, mslot, gtable, cub_tmp, row_of, row_rev, row_bound;
   int64_t scratch_rows = 0;
@@ -943,8 +944,10 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     rc = join_ensure_out(h, std::max<int64_t>(2 * n, 4096));
     if (rc != RW_OK) return rc;
     while (true) {
+      h->prof.begin(st);
       join_inner_probe_emit_kernel<<<jgrid(n, JF_BLOCK), JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, 1 - S), out_dev(h), ds,
                                                                              h->row_of.as<uint32_t>());
+      h->prof.end(st);
       RW_CUDA(cudaGetLastError());
       h->launches++;
       rc = join_read_status(h, st, &hs);
@@ -1001,8 +1004,10 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     const int64_t reserved = (int64_t)hs.out_rows;
     rc = join_ensure_out(h, reserved);
     if (rc != RW_OK) return rc;
+    h->prof.begin(st);
     join_serial_kernel<<<jgrid(n, 128), 128, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), sc, db.Current(), out_dev(h), ds,
                                                         (uint32_t)own.n_rows);
+    h->prof.end(st);
     RW_CUDA(cudaGetLastError());
     h->launches++;
     rc = join_read_status(h, st, &hs);
@@ -1261,6 +1266,18 @@ int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t /*epoch*/) {
   if (!h) return fail(RW_ERR_INVALID, "null");
   // state lives in HBM (StateStore stubbed to memory, north_star): a barrier is an ordering point
   RW_CUDA(cudaStreamSynchronize(h->stream));
+  return RW_OK;
+}
+
+int32_t rwgpu_join_profile(rwgpu_join* h, int32_t enable, double* ms, uint64_t* launches) {
+  if (!h) return fail(RW_ERR_INVALID, "null");
+  RW_CUDA(cudaDeviceSynchronize());
+  h->prof.collect();
+  if (ms) *ms = h->prof.ms;
+  if (launches) *launches = h->prof.n;
+  h->prof.ms = 0;
+  h->prof.n = 0;
+  h->prof.on = enable != 0;
   return RW_OK;
 }
 

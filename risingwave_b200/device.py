@@ -1,0 +1,180 @@
+"""Device-resident driver API: torch CUDA tensors in, device views out, through the C ABI's
+`*_device` entry points (no torch types cross the ABI: raw device pointers and a cudaStream_t).
+
+Used by bench.py (kernel-only throughput with inputs already in HBM) and by the multi-GPU
+hash-shuffle path (exchange.py).  PyTorch is plumbing here: allocation, streams, torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import abi
+
+TORCH_DTYPE = {abi.T_BOOL: torch.uint8, abi.T_INT16: torch.int16, abi.T_INT32: torch.int32, abi.T_INT64: torch.int64,
+               abi.T_FLOAT32: torch.float32, abi.T_FLOAT64: torch.float64, abi.T_DATE: torch.int32,
+               abi.T_TIME: torch.int64, abi.T_TIMESTAMP: torch.int64, abi.T_TIMESTAMPTZ: torch.int64,
+               abi.T_SERIAL: torch.int64}
+
+
+class DeviceChunk:
+    """A StreamChunk whose buffers are CUDA tensors (ops uint8[n]; columns in native width;
+    optional validity / visibility as packed uint64 words held in int64 tensors)."""
+
+    def __init__(self, ops: torch.Tensor, cols: Sequence[torch.Tensor], types: Sequence[int],
+                 validity: Optional[Sequence[Optional[torch.Tensor]]] = None, visibility: Optional[torch.Tensor] = None):
+        assert ops.dtype == torch.uint8 and ops.is_cuda and ops.is_contiguous()
+        self.ops, self.cols, self.types = ops, list(cols), list(types)
+        self.validity = list(validity) if validity is not None else [None] * len(cols)
+        self.visibility = visibility
+        for c, t in zip(self.cols, self.types):
+            assert c.is_cuda and c.is_contiguous() and c.dtype == TORCH_DTYPE[t] and c.numel() == ops.numel()
+
+    def n_rows(self) -> int:
+        return self.ops.numel()
+
+    def to_abi(self):
+        cols = (abi.RwColumn * max(1, len(self.cols)))()
+        for k, (c, t) in enumerate(zip(self.cols, self.types)):
+            cols[k].type = t
+            cols[k].data = c.data_ptr() if c.numel() else None
+            cols[k].validity = self.validity[k].data_ptr() if self.validity[k] is not None else None
+        ch = abi.RwChunk()
+        ch.n_rows = self.ops.numel()
+        ch.n_cols = len(self.cols)
+        ch.ops = self.ops.data_ptr() if self.ops.numel() else None
+        ch.visibility = self.visibility.data_ptr() if self.visibility is not None else None
+        ch.columns = cols
+        return ch, cols
+
+
+class DeviceView:
+    """Device pointers returned by a `*_device` call (valid until the next call on that handle)."""
+
+    def __init__(self, view: abi.RwChunk):
+        self.n_rows = int(view.n_rows)
+        self.n_cols = int(view.n_cols)
+        self.ops_ptr = view.ops
+        self.vis_ptr = view.visibility
+        self.col_ptrs = [view.columns[k].data for k in range(self.n_cols)]
+        self.col_types = [int(view.columns[k].type) for k in range(self.n_cols)]
+        self.valid_ptrs = [view.columns[k].validity for k in range(self.n_cols)]
+
+    def column(self, k: int) -> torch.Tensor:
+        """copy column k out of the library-owned buffer into a fresh tensor (D2D)."""
+        t = self.col_types[k]
+        out = torch.empty(self.n_rows, dtype=TORCH_DTYPE[t], device="cuda")
+        if self.n_rows:
+            cudart().cudaMemcpy(C.c_void_p(out.data_ptr()), C.c_void_p(self.col_ptrs[k]),
+                                C.c_size_t(self.n_rows * abi.TYPE_WIDTH[t]), 3)
+        return out
+
+    def ops(self) -> torch.Tensor:
+        out = torch.empty(self.n_rows, dtype=torch.uint8, device="cuda")
+        if self.n_rows:
+            cudart().cudaMemcpy(C.c_void_p(out.data_ptr()), C.c_void_p(self.ops_ptr), C.c_size_t(self.n_rows), 3)
+        return out
+
+
+_cudart = None
+
+
+def cudart():
+    global _cudart
+    if _cudart is None:
+        import glob
+        import os
+        cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart*.so*")) + \
+            glob.glob("/usr/local/cuda/lib64/libcudart.so*")
+        _cudart = C.CDLL(cands[0])
+    return _cudart
+
+
+def _lib():
+    lib = abi.load_library()
+    if not getattr(lib, "_dev_sigs", False):
+        lib.rwgpu_agg_push_device.restype = C.c_int32
+        lib.rwgpu_agg_push_device.argtypes = [C.c_void_p, C.POINTER(abi.RwChunk), C.c_void_p]
+        lib.rwgpu_agg_flush_device.restype = C.c_int32
+        lib.rwgpu_agg_flush_device.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(abi.RwChunk), C.c_void_p]
+        lib.rwgpu_join_push_device.restype = C.c_int32
+        lib.rwgpu_join_push_device.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.RwChunk), C.POINTER(abi.RwChunk), C.c_void_p]
+        for name in ("rwgpu_agg_profile", "rwgpu_join_profile"):
+            fn = getattr(lib, name)
+            fn.restype = C.c_int32
+            fn.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        lib.rwgpu_agg_stats.restype = C.c_int32
+        lib.rwgpu_agg_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3
+        lib.rwgpu_join_stats.restype = C.c_int32
+        lib.rwgpu_join_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3
+        lib.rwgpu_shuffle_partition_device.restype = C.c_int32
+        lib.rwgpu_shuffle_partition_device.argtypes = [C.POINTER(abi.RwChunk), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                                       C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p),
+                                                       C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.rwgpu_last_error.restype = C.c_char_p
+        lib._dev_sigs = True
+    return lib
+
+
+def _check(rc):
+    if rc != abi.RW_OK:
+        raise abi.RwError(rc, (_lib().rwgpu_last_error() or b"").decode())
+
+
+def _stream_ptr(stream: Optional[torch.cuda.Stream]):
+    return C.c_void_p(stream.cuda_stream) if stream is not None else None
+
+
+def agg_push_device(executor, chunk: DeviceChunk, stream: Optional[torch.cuda.Stream] = None):
+    ch, keep = chunk.to_abi()
+    _check(_lib().rwgpu_agg_push_device(executor._h, C.byref(ch), _stream_ptr(stream)))
+
+
+def agg_flush_device(executor, epoch: int, stream: Optional[torch.cuda.Stream] = None) -> DeviceView:
+    view = abi.RwChunk()
+    _check(_lib().rwgpu_agg_flush_device(executor._h, epoch, C.byref(view), _stream_ptr(stream)))
+    return DeviceView(view)
+
+
+def join_push_device(executor, side: int, chunk: DeviceChunk, stream: Optional[torch.cuda.Stream] = None) -> DeviceView:
+    ch, keep = chunk.to_abi()
+    view = abi.RwChunk()
+    _check(_lib().rwgpu_join_push_device(executor._h, side, C.byref(ch), C.byref(view), _stream_ptr(stream)))
+    return DeviceView(view)
+
+
+def profile(executor, kind: str, enable: bool):
+    """-> (dominant-kernel milliseconds, launches) accumulated since the previous call."""
+    ms, n = C.c_double(), C.c_uint64()
+    fn = _lib().rwgpu_agg_profile if kind == "agg" else _lib().rwgpu_join_profile
+    _check(fn(executor._h, int(enable), C.byref(ms), C.byref(n)))
+    return ms.value, n.value
+
+
+def launches(executor, kind: str) -> int:
+    a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    fn = _lib().rwgpu_agg_stats if kind == "agg" else _lib().rwgpu_join_stats
+    _check(fn(executor._h, C.byref(a), C.byref(b), C.byref(c)))
+    return c.value
+
+
+def shuffle_partition(chunk: DeviceChunk, key_indices: Sequence[int], vnode_to_dest: torch.Tensor, n_dest: int,
+                      vnode_count: int = 256, stream: Optional[torch.cuda.Stream] = None):
+    """Stable partition of the visible rows by destination = vnode_to_dest[crc32(key) % vnode_count].
+    Returns (ops, cols, counts[n_dest], offsets[n_dest]) as CUDA tensors; rows of destination d are
+    [offsets[d], offsets[d]+counts[d])."""
+    n = chunk.n_rows()
+    out_ops = torch.empty(n, dtype=torch.uint8, device="cuda")
+    out_cols = [torch.empty_like(c) for c in chunk.cols]
+    counts = torch.zeros(n_dest, dtype=torch.int64, device="cuda")
+    offsets = torch.zeros(n_dest, dtype=torch.int64, device="cuda")
+    ch, keep = chunk.to_abi()
+    keys = (C.c_int32 * len(key_indices))(*key_indices)
+    colp = (C.c_void_p * len(out_cols))(*[c.data_ptr() for c in out_cols])
+    _check(_lib().rwgpu_shuffle_partition_device(C.byref(ch), keys, len(key_indices), vnode_count,
+                                                 C.c_void_p(vnode_to_dest.data_ptr()), n_dest, C.c_void_p(out_ops.data_ptr()),
+                                                 colp, None, C.c_void_p(counts.data_ptr()), C.c_void_p(offsets.data_ptr()),
+                                                 _stream_ptr(stream)))
+    return out_ops, out_cols, counts, offsets
