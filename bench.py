@@ -183,48 +183,41 @@ def vnode_of_int64(keys):
 
 
 def cpu_join_run(n_build, batches, n_actors, warmup, steps, chunk=CHUNK):
-    """P single-threaded actors (one per vnode range), each fed 1024-row chunks of its partition.
-    Returns rows/s over the timed steps (wall clock, all actors in parallel)."""
+    """P single-threaded actors (one OS thread each, vnode-partitioned input), each fed 1024-row chunks
+    of its partition.  Returns rows/s over the timed steps (wall clock, all actors in parallel)."""
     fc = FastCpu().f
+    fc.rwf_join_push_parallel.restype = C.c_int64
+    fc.rwf_join_push_parallel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p] + [C.c_void_p] * 5 + [C.c_int]
     actors = [fc.rwf_join_new() for _ in range(n_actors)]
-    auct = gen_auctions(n_build, SEED)
-    a_part = vnode_of_int64(auct[0]) * n_actors // 256
-    ones = np.full(max(n_build, BATCH), 1, np.uint8)
+    act_arr = (C.c_void_p * n_actors)(*actors)
 
-    def feed(actor, side, cols):
-        n = len(cols[0])
-        for i in range(0, n, chunk):
-            m = min(chunk, n - i)
-            fc.rwf_join_push(actor, side, m, ones.ctypes.data, *[c[i:].ctypes.data for c in cols])
-
-    def build(a):
-        sel = np.nonzero(a_part == a)[0]
-        cols = [np.ascontiguousarray(c[sel]) for c in auct]
-        fc.rwf_join_reserve(actors[a], 1, len(sel))
-        fc.rwf_join_reserve(actors[a], 0, len(sel))
-        feed(actors[a], 1, cols)
-
-    ths = [threading.Thread(target=build, args=(a,)) for a in range(n_actors)]
-    [t.start() for t in ths]
-    [t.join() for t in ths]
-    parts = []
-    for cols in batches:
+    def parts_of(cols):
+        """-> ctypes argument pack for rwf_join_push_parallel (keeps the numpy arrays alive)."""
         p = vnode_of_int64(cols[0]) * n_actors // 256
-        parts.append([[np.ascontiguousarray(c[p == a]) for c in cols] for a in range(n_actors)])
-    out_rows = [0]
+        order = np.argsort(p, kind="stable")
+        cnt = np.bincount(p, minlength=n_actors).astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+        sc = [np.ascontiguousarray(c[order]) for c in cols]
+        ops = np.ones(len(order), np.uint8)
+        ptr = lambda arr, w: (C.c_void_p * n_actors)(*[arr.ctypes.data + int(o) * w for o in off])  # noqa: E731
+        return (cnt, ptr(ops, 1), [ptr(c, 8) for c in sc], (ops, sc))
 
-    def run_step(s):
-        def work(a):
-            feed(actors[a], 0, parts[s][a])
-        ths = [threading.Thread(target=work, args=(a,)) for a in range(n_actors)]
-        [t.start() for t in ths]
-        [t.join() for t in ths]
+    def push(side, pack):
+        cnt, ops_p, col_p, _ = pack
+        return fc.rwf_join_push_parallel(act_arr, n_actors, side, cnt.ctypes.data, ops_p, *col_p, chunk)
 
+    auct = gen_auctions(n_build, SEED)
+    ap = parts_of(auct)
+    for a in range(n_actors):
+        fc.rwf_join_reserve(actors[a], 1, int(ap[0][a]))
+        fc.rwf_join_reserve(actors[a], 0, int(ap[0][a]))
+    push(1, ap)
+    packs = [parts_of(b) for b in batches]
     for s in range(warmup):
-        run_step(s)
+        push(0, packs[s])
     t0 = time.perf_counter()
     for s in range(warmup, warmup + steps):
-        run_step(s)
+        push(0, packs[s])
     dt = time.perf_counter() - t0
     rows = sum(len(batches[s][0]) for s in range(warmup, warmup + steps))
     for a in actors:
@@ -334,7 +327,7 @@ def run_ours(args):
         # ---------------- e2e: host buffers through rwgpu_join_push (rank-local; N=1 only)
         e2e = None
         secondary = None
-        if world == 1:
+        if world == 1 and not args.only_value:
             del join
             torch.cuda.empty_cache()
             join2 = new_join(0, 0)
@@ -344,15 +337,26 @@ def run_ours(args):
             FFI_ROWS = 1 << 18  # 256 coalesced 1024-row chunks per C-ABI call
             ones = np.ones(FFI_ROWS, np.uint8)
 
-            def host_step(s):
-                tot, d2h = 0, 0
+            lib = be.lib
+            chunks_host = []
+            for s in range(W + K):
                 for i in range(0, BATCH, FFI_ROWS):
                     ch = StreamChunk(ones, [Column(abi.T_INT64, c[i:i + FFI_ROWS]) for c in batches_host[s]])
-                    outs = join2.eq_join_oneside(abi.SIDE_LEFT, ch)
-                    for o in outs:
-                        tot += o.capacity()
-                d2h = tot * (8 * 8 + 1)
-                return tot, d2h
+                    chunks_host.append(ch.to_abi())  # (rw_chunk with HOST pointers, keepalive)
+            per_step = BATCH // FFI_ROWS
+
+            def host_step(s):
+                """the call a Rust shim makes: rwgpu_join_push(host chunk) -> out; walk the chunk views; release"""
+                tot = 0
+                view = abi.RwChunk()
+                for j in range(per_step):
+                    out = C.c_void_p()
+                    be.check(be._join_push(join2._h, abi.SIDE_LEFT, C.byref(chunks_host[s * per_step + j][0]), C.byref(out)))
+                    for i in range(be._out_num_chunks(out)):
+                        be._out_chunk(out, i, C.byref(view))
+                        tot += view.n_rows
+                    be._out_release(out)
+                return tot, tot * (8 * 8 + 1)
 
             for s in range(W):
                 host_step(s)
@@ -366,7 +370,7 @@ def run_ours(args):
             dt = time.perf_counter() - t0
             e2e = {"value": K * BATCH / dt, "unit": "rows/s", "h2d_bytes_per_step": BATCH * (4 * 8 + 1),
                    "d2h_bytes_per_step": d2h // K, "ffi_batch_rows": FFI_ROWS, "ms_per_step": dt / K * 1e3,
-                   "note": "includes the python-side copy of output chunks into numpy (StreamChunk.from_abi)"}
+                   "note": "host numpy buffers -> rwgpu_join_push -> host output chunk views (C ABI called through ctypes)"}
             del join2
             torch.cuda.empty_cache()
 
@@ -439,11 +443,11 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        nb = 4
-        sample = [gen_bids(1 << 18, s << 18, SEED, N_BUILD) for s in range(nb)]
+        nb = 5
+        sample = [gen_bids(1 << 20, s << 20, SEED, N_BUILD) for s in range(nb)]
         v, dt = cpu_join_run(N_BUILD, sample, 1, 1, nb - 1, CHUNK)
         line["cpu_baseline"] = {"value": v, "unit": "rows/s", "cores": 1, "kind": "port",
-                                "sample": f"oracle/fastcpu.cc single actor, 10M-row build (untimed) then {nb - 1} x 2^18 bid rows "
+                                "sample": f"oracle/fastcpu.cc single actor, 10M-row build (untimed) then {nb - 1} x 2^20 bid rows "
                                           f"in 1024-row chunks ({dt:.1f} s); host has {cores} cores"}
     print(json.dumps(line))
     if world > 1:
@@ -459,8 +463,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     P = max(1, min(cores, 64))
     K, W = args.steps, args.warmup
-    step_rows = 1 << 19  # bounded sample of the 2^20-row step
-    n_steps = min(K, 8)
+    step_rows = BATCH
+    n_steps = min(K, 20)
     batches = [gen_bids(step_rows, s * step_rows, SEED, N_BUILD) for s in range(W + n_steps)]
     v, dt = cpu_join_run(N_BUILD, batches, P, W, n_steps, CHUNK)
     line = {"impl": "reference", "metric": "Nexmark q7/q8-shaped streaming HashJoin input rows/s", "value": v, "unit": "rows/s",
@@ -470,7 +474,7 @@ def run_reference(args):
                        "probe_rows_per_step_per_gpu": BATCH, "chunk_rows": CHUNK},
             "cpu_baseline": {"value": v, "unit": "rows/s", "cores": P, "kind": "port",
                              "sample": f"oracle/fastcpu.cc: {P} single-threaded actors (vnode-partitioned input), 10M-row build untimed, "
-                                       f"{n_steps} steps of 2^19 bid rows in 1024-row chunks; the Rust reference cannot be built here"},
+                                       f"{n_steps} steps of 2^20 bid rows in 1024-row chunks; the Rust reference cannot be built here"},
             "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -483,6 +487,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--only-value", action="store_true", help="device-resident leg only (for ncu runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

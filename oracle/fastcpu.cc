@@ -264,3 +264,26 @@ extern "C" void rwf_agg_reserve(rwf_agg* h, uint64_t n) {
   while (cap < n * 2) cap <<= 1;
   if (cap > h->slots.size()) h->resize(cap);
 }
+
+// P actors in parallel, one OS thread each (the reference runs one tokio task per actor on a worker
+// pool, actor.rs:209-232): actor a consumes its n[a] rows in `chunk`-row StreamChunks.
+#include <thread>
+extern "C" int64_t rwf_join_push_parallel(rwf_join** actors, int P, int side, const int64_t* n, const uint8_t* const* ops,
+                                          const int64_t* const* c0, const int64_t* const* c1, const int64_t* const* c2,
+                                          const int64_t* const* c3, int chunk) {
+  std::vector<std::thread> th;
+  std::vector<int64_t> outs(P, 0);
+  for (int a = 0; a < P; a++) {
+    th.emplace_back([&, a]() {
+      int64_t tot = 0;
+      for (int64_t i = 0; i < n[a]; i += chunk) {
+        int64_t m = n[a] - i < chunk ? n[a] - i : chunk;
+        tot += rwf_join_push(actors[a], side, m, ops[a] + i, c0[a] + i, c1[a] + i, c2[a] + i, c3[a] + i);
+      }
+      outs[a] = tot;
+    });
+  }
+  int64_t tot = 0;
+  for (int a = 0; a < P; a++) { th[a].join(); tot += outs[a]; }
+  return tot;
+}
