@@ -335,13 +335,15 @@ def run_ours(args):
                 device.join_push_device(join2, abi.SIDE_RIGHT, dchunk([c[i:i + BATCH] for c in auct_dev]), stream)
             torch.cuda.synchronize()
             FFI_ROWS = 1 << 18  # 256 coalesced 1024-row chunks per C-ABI call
-            ones = np.ones(FFI_ROWS, np.uint8)
+            ones_pinned = torch.ones(FFI_ROWS, dtype=torch.uint8).pin_memory().numpy()
 
             lib = be.lib
             chunks_host = []
             for s in range(W + K):
                 for i in range(0, BATCH, FFI_ROWS):
-                    ch = StreamChunk(ones, [Column(abi.T_INT64, c[i:i + FFI_ROWS]) for c in batches_host[s]])
+                    # the shim's StreamChunk arrays live in pinned host memory (cudaHostAlloc'd arena)
+                    cols = [torch.from_numpy(c[i:i + FFI_ROWS].copy()).pin_memory().numpy() for c in batches_host[s]]
+                    ch = StreamChunk(ones_pinned, [Column(abi.T_INT64, c) for c in cols])
                     chunks_host.append(ch.to_abi())  # (rw_chunk with HOST pointers, keepalive)
             per_step = BATCH // FFI_ROWS
 
@@ -378,7 +380,7 @@ def run_ours(args):
             _, src = MockSource.channel()
             agg = HashAggExecutor(be, src.into_executor([abi.T_INT64] * 2, []), True,
                                   [AggCall.from_pretty(c) for c in ("(count:int8)", "(sum:int8 $1:int8)", "(max:int8 $1:int8)")],
-                                  0, [0], group_capacity_hint=AGG_KEYS)
+                                  0, [0], group_capacity_hint=2 * AGG_KEYS)
             n_ep_w, n_ep = 4, 60
             ep_dev = []
             for e in range(n_ep_w + n_ep):
@@ -461,7 +463,7 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
-    P = max(1, min(cores, 64))
+    P = max(1, min(cores, 256))
     K, W = args.steps, args.warmup
     step_rows = BATCH
     n_steps = min(K, 20)

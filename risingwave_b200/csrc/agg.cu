@@ -584,6 +584,7 @@ struct rwgpu_agg {
       out_bits[RW_MAX_KEYS + RW_MAX_CALLS];
   int64_t out_cap = 0;
   PinnedBuf status_host;
+  std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
   std::vector<rw_column> dev_view_cols;
 
   AggTable table() const {
@@ -1013,22 +1014,16 @@ int32_t rwgpu_agg_flush(rwgpu_agg* h, uint64_t /*epoch*/, rwgpu_out** out) {
   int rc = agg_flush_dev(h, h->stream, &n, has_null);
   if (rc != RW_OK) return rc;
   auto o = new rwgpu_out();
-  o->n_rows = n;
   o->chunk_size = h->chunk_size;
-  o->types = h->out_types;
-  o->ops.resize((size_t)n);
-  o->data.resize(h->out_types.size());
-  o->valid_bytes.resize(h->out_types.size());
+  unsigned long long nullm = 0;
+  for (size_t k = 0; k < h->out_types.size(); k++) if (has_null[k]) nullm |= 1ull << k;
+  if (!o->layout(n, h->out_types, nullm, false, h->pool)) { delete o; return fail(RW_ERR_OOM, "pinned output block"); }
   if (n > 0) {
-    cudaMemcpyAsync(o->ops.data(), h->out_ops.p, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(o->ops, h->out_ops.p, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
     for (size_t k = 0; k < h->out_types.size(); k++) {
       size_t w = type_width(h->out_types[k]);
-      o->data[k].resize((size_t)n * w);
-      cudaMemcpyAsync(o->data[k].data(), h->out_col[k].p, (size_t)n * w, cudaMemcpyDeviceToHost, h->stream);
-      if (has_null[k]) {
-        o->valid_bytes[k].resize((size_t)n);
-        cudaMemcpyAsync(o->valid_bytes[k].data(), h->out_valid[k].p, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
-      }
+      cudaMemcpyAsync(o->data[k], h->out_col[k].p, (size_t)n * w, cudaMemcpyDeviceToHost, h->stream);
+      if (o->valid_bytes[k]) cudaMemcpyAsync(o->valid_bytes[k], h->out_valid[k].p, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
     }
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) { delete o; return fail(RW_ERR_CUDA, cudaGetErrorString(e)); }

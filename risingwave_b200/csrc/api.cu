@@ -43,6 +43,32 @@ int devchunk_from_abi(const rw_chunk* c, DevChunk* out) {
 
 }  // namespace rw
 
+bool rwgpu_out::layout(int64_t rows, const std::vector<int>& col_types, unsigned long long null_mask, bool with_vis,
+                       const std::shared_ptr<PinnedPool>& pl) {
+  n_rows = rows;
+  types = col_types;
+  pool = pl;
+  data.assign(types.size(), nullptr);
+  valid_bytes.assign(types.size(), nullptr);
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  size_t total = up((size_t)rows) * (1 + (with_vis ? 1 : 0));
+  for (size_t k = 0; k < types.size(); k++) {
+    total += up((size_t)rows * rw::type_width(types[k]));
+    if ((null_mask >> k) & 1) total += up((size_t)rows);
+  }
+  if (rows == 0) return true;
+  block = pl ? pl->get(total) : PinnedBlock();
+  if (!block.p) return false;
+  size_t off = 0;
+  ops = block.p + off; off += up((size_t)rows);
+  if (with_vis) { vis_bytes = block.p + off; off += up((size_t)rows); }
+  for (size_t k = 0; k < types.size(); k++) {
+    data[k] = block.p + off; off += up((size_t)rows * rw::type_width(types[k]));
+    if ((null_mask >> k) & 1) { valid_bytes[k] = block.p + off; off += up((size_t)rows); }
+  }
+  return true;
+}
+
 // Cut the super-chunk into StreamChunks of <= chunk_size rows; a U- is never the last row of a
 // chunk (StreamChunkBuilder::append_iter_inner, src/common/src/array/stream_chunk_builder.rs:189-219),
 // and build per-chunk LSB-first bitmaps.
@@ -64,7 +90,7 @@ void rwgpu_out::finalize() {
   for (size_t i = 0; i < nch; i++) {
     int64_t lo = cut[i], n = cut[i + 1] - cut[i];
     size_t nw = (size_t)((n + 63) / 64);
-    if (!vis_bytes.empty()) {
+    if (vis_bytes) {
       bool all = true;
       std::vector<uint64_t> w(nw ? nw : 1, 0);
       for (int64_t r = 0; r < n; r++) {
@@ -79,9 +105,9 @@ void rwgpu_out::finalize() {
       rw_column& c = chunk_cols[i][k];
       c.type = types[k];
       c.reserved = 0;
-      c.data = data[k].data() + (size_t)lo * wd;
+      c.data = data[k] + (size_t)lo * wd;
       c.validity = nullptr;
-      if (!valid_bytes[k].empty()) {
+      if (valid_bytes[k]) {
         bool all = true;
         std::vector<uint64_t> w(nw ? nw : 1, 0);
         for (int64_t r = 0; r < n; r++) {
@@ -120,7 +146,7 @@ int32_t rwgpu_out_chunk(const rwgpu_out* o, int32_t idx, rw_chunk* view) {
   view->n_rows = o->cut[idx + 1] - lo;
   view->n_cols = (int32_t)o->types.size();
   view->reserved = 0;
-  view->ops = o->ops.data() + lo;
+  view->ops = o->ops + lo;
   view->visibility = o->chunk_vis[idx].empty() ? nullptr : o->chunk_vis[idx].data();
   view->columns = o->chunk_cols[idx].data();
   return RW_OK;

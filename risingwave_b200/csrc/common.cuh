@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -133,22 +135,66 @@ struct OutColHost {
 
 }  // namespace rw
 
-// C-ABI output object: one super-chunk in host memory + lazily cut chunk views
+// pool of pinned host blocks backing the output objects (D2H at full PCIe rate, no page faults);
+// shared between a handle and the outputs it produced so either may die first
+struct PinnedBlock {
+  uint8_t* p = nullptr;
+  size_t bytes = 0;
+};
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<PinnedBlock> free_blocks;
+  ~PinnedPool() { for (auto& b : free_blocks) cudaFreeHost(b.p); }
+  PinnedBlock get(size_t bytes) {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      for (size_t i = 0; i < free_blocks.size(); i++)
+        if (free_blocks[i].bytes >= bytes) {
+          PinnedBlock b = free_blocks[i];
+          free_blocks.erase(free_blocks.begin() + i);
+          return b;
+        }
+      if (!free_blocks.empty()) {  // drop a too-small block rather than hoarding
+        cudaFreeHost(free_blocks.back().p);
+        free_blocks.pop_back();
+      }
+    }
+    PinnedBlock b;
+    size_t want = bytes + bytes / 4 + 4096;
+    if (cudaMallocHost((void**)&b.p, want) != cudaSuccess) { b.p = nullptr; b.bytes = 0; cudaGetLastError(); return b; }
+    b.bytes = want;
+    return b;
+  }
+  void put(PinnedBlock b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> g(mu);
+    if (free_blocks.size() >= 4) { cudaFreeHost(b.p); return; }
+    free_blocks.push_back(b);
+  }
+};
+
+// C-ABI output object: one super-chunk in pinned host memory + chunk views cut from it
 struct rwgpu_out {
   int64_t n_rows = 0;
   int chunk_size = 1024;
   std::vector<int> types;
-  std::vector<uint8_t> ops;
-  std::vector<uint8_t> vis_bytes;          // empty = all visible
-  std::vector<std::vector<uint8_t>> data;  // per column, native width
-  std::vector<std::vector<uint8_t>> valid_bytes;  // per column, empty = no NULLs
+  uint8_t* ops = nullptr;
+  uint8_t* vis_bytes = nullptr;            // nullptr = all visible
+  std::vector<uint8_t*> data;              // per column, native width
+  std::vector<uint8_t*> valid_bytes;       // per column, nullptr = no NULLs
+  PinnedBlock block;
+  std::shared_ptr<PinnedPool> pool;
   // chunk cutting (StreamChunkBuilder rule: a U- is never the last row of a chunk)
   std::vector<int64_t> cut;  // chunk i = rows [cut[i], cut[i+1])
   // per-chunk packed bitmaps, built by finalize()
   std::vector<std::vector<uint64_t>> chunk_vis;
   std::vector<std::vector<std::vector<uint64_t>>> chunk_valid;
   std::vector<std::vector<rw_column>> chunk_cols;
+  // carve ops / column / valid / vis regions for `rows` rows out of a pool block; false on OOM
+  bool layout(int64_t rows, const std::vector<int>& col_types, unsigned long long null_mask, bool with_vis,
+              const std::shared_ptr<PinnedPool>& pl);
   void finalize();
+  ~rwgpu_out() { if (pool) pool->put(block); else if (block.p) cudaFreeHost(block.p); }
 };
 
 #ifdef __CUDACC__

@@ -8,13 +8,17 @@
 //   join-type predicates                   src/stream/src/executor/join/mod.rs:103-169
 //
 // HBM layout per side:
-//   row store  : columnar, append-only; col[c][row] in native width, optional valid byte / row,
-//                link[row] = next row of the same key | DEAD bit, degree[row] (u32) when needed
-//   hash index : open addressing, linear probing, power-of-two capacity, load <= 1/2;
-//                slot = key word(s) | (count << 32 | head)       (Key64: 16 B)
+//   record store : array of fixed-stride records, append-only, row id = index.
+//                  record = { u32 link (next row of the same key | DEAD bit), u32 null mask (bit c =
+//                  column c is NULL), u32 seq (arrival order), u32 degree } + the row's columns
+//                  packed at naturally aligned offsets; stride is a multiple of 16 B
+//                  (Nexmark bid / auction: 16 + 4*8 = 48 B = three 128-bit loads, 2 DRAM sectors).
+//   hash index   : open addressing, linear probing, power-of-two capacity, load <= 1/2;
+//                  slot = key word(s) | (live count << 32 | head row)   (Key64: 16 B, one 128-bit load)
 // Two execution paths:
-//   * inner fast path (no degrees): row-parallel probe; matches are emitted with block-scan
-//     compaction; own-side inserts / deletes are applied by separate row-parallel kernels.
+//   * inner fast path (no degrees): ONE fused kernel per batch -- probe the other side, emit the
+//     matches with tile-scan compaction, append the row to the own side; a second kernel applies
+//     own-side deletes (it exits immediately when the batch has none).
 //   * generic path (all 8 join types, degrees, append-only optimisation, mixed +/- on one key):
 //     the batch is grouped by join key (scratch hash table + radix sort) and ONE thread walks each
 //     key's rows in input order -- state of different keys is disjoint, so this is exactly the
@@ -33,6 +37,7 @@ namespace rw {
 #define J_NIL 0x7fffffffu
 #define J_DEAD 0x80000000u
 #define J_MAX_OUT (2 * RW_MAX_COLS)
+#define J_HDR 16
 
 #define JERR_DOUBLE_DELETE 1u
 #define JERR_OUT_CAPACITY 2u
@@ -46,6 +51,8 @@ struct JoinPlanDev {
   int n_cols[2];
   int col_type[2][RW_MAX_COLS];
   int col_width[2][RW_MAX_COLS];
+  int col_off[2][RW_MAX_COLS];  // byte offset of the column inside a record
+  int stride[2];
   int n_pk[2];
   int pk_col[2][RW_MAX_COLS];
   int n_out;
@@ -62,29 +69,28 @@ struct JoinPlanDev {
 };
 
 struct JoinSideDev {
-  void* col[RW_MAX_COLS];
-  uint8_t* valid[RW_MAX_COLS];  // nullptr until the column has seen a NULL
-  uint32_t* link;
-  uint32_t* degree;  // nullptr if the side keeps no degrees
+  uint8_t* recs;
   uint64_t* slots;
   uint64_t cap;
+  int stride;
+  int pad;
 };
 
 struct JoinStatus {
-  unsigned long long out_rows;    // rows reserved in the output
-  unsigned long long n_store;     // store candidates of this push
-  unsigned long long n_keys[2];   // distinct keys ever claimed per side
-  unsigned long long live_rows[2];
+  unsigned long long out_rows;   // rows reserved in the output
+  unsigned long long n_store;    // rows appended to the own side by this push
+  unsigned long long n_del;      // visible delete rows seen by this push
+  unsigned long long null_mask;  // bit k: output column k received a NULL; bit 63: invisible rows exist
+  unsigned long long n_keys[2];  // distinct keys ever claimed per side
   unsigned int err;
   unsigned int pad;
 };
 
 struct JoinOutDev {
   uint8_t* ops;
-  uint8_t* vis;
+  uint8_t* vis;                 // written by the generic path only
   void* col[J_MAX_OUT];
-  uint8_t* valid[J_MAX_OUT];
-  unsigned int* has_null;  // [J_MAX_OUT] + [J_MAX_OUT] = any invisible flag
+  uint8_t* valid[J_MAX_OUT];    // kept at 1; only NULLs are written (0)
   int64_t capacity;
 };
 
@@ -96,6 +102,34 @@ __device__ __host__ __forceinline__ bool jt_only_forward_matched_side(int T, int
 __device__ __host__ __forceinline__ bool jt_is_semi(int T) { return T == RW_JOIN_LEFT_SEMI || T == RW_JOIN_RIGHT_SEMI; }
 __device__ __host__ __forceinline__ bool jt_is_anti(int T) { return T == RW_JOIN_LEFT_ANTI || T == RW_JOIN_RIGHT_ANTI; }
 __device__ __host__ __forceinline__ bool jt_forward_if_not_matched(int T, int S) { return (jt_is_anti(T) && jt_forward_exactly_once(T, S)) || jt_is_outer_side(T, S); }
+
+// ------------------------------------------------------------------ records
+struct RecHdr {
+  uint32_t link, nullmask, seq, degree;
+};
+__device__ __forceinline__ uint8_t* rec_ptr(const JoinSideDev& s, uint32_t row) { return s.recs + (uint64_t)row * s.stride; }
+__device__ __forceinline__ RecHdr* rec_hdr(const JoinSideDev& s, uint32_t row) { return (RecHdr*)rec_ptr(s, row); }
+
+__device__ __forceinline__ uint64_t rec_key_word(const uint8_t* rec, int off, int width, int type) {
+  ColRef cr;
+  cr.data = rec + off;
+  cr.valid_bits = nullptr;
+  cr.valid_bytes = nullptr;
+  cr.type = type;
+  cr.width = width;
+  return load_key_word(cr, 0);
+}
+
+// copy one datum of `width` bytes
+__device__ __forceinline__ void copy_bytes(void* dst, const void* src, int width) {
+  switch (width) {
+    case 1: *(uint8_t*)dst = *(const uint8_t*)src; break;
+    case 2: *(uint16_t*)dst = *(const uint16_t*)src; break;
+    case 4: *(uint32_t*)dst = *(const uint32_t*)src; break;
+    case 8: *(uint64_t*)dst = *(const uint64_t*)src; break;
+    default: *(ulonglong2*)dst = *(const ulonglong2*)src; break;
+  }
+}
 
 // ------------------------------------------------------------------ key helpers
 __device__ __forceinline__ bool chunk_key(const JoinPlanDev* p, int S, const DevChunk& ch, int64_t r, uint64_t* kw,
@@ -122,17 +156,28 @@ __device__ __forceinline__ uint64_t key_hash(const JoinPlanDev* p, const uint64_
   return h;
 }
 
-// find the slot of a key (read-only). returns -1 if absent.
-__device__ __forceinline__ int64_t js_find(const JoinSideDev& s, const JoinPlanDev* p, const uint64_t* kw, uint32_t nm) {
+// head / count live in the last word of a slot: low 32 = head row (J_NIL = none), high 32 = live count
+__device__ __forceinline__ uint32_t* slot_head(const JoinSideDev& s, const JoinPlanDev* p, int64_t slot) {
+  return (uint32_t*)(s.slots + (uint64_t)slot * p->SW + p->KW);
+}
+__device__ __forceinline__ uint32_t* slot_count(const JoinSideDev& s, const JoinPlanDev* p, int64_t slot) {
+  return slot_head(s, p, slot) + 1;
+}
+
+// find the slot of a key (read-only). returns -1 if absent; *hc = (count << 32 | head) of the slot.
+__device__ __forceinline__ int64_t js_find(const JoinSideDev& s, const JoinPlanDev* p, const uint64_t* kw, uint32_t nm,
+                                           uint64_t* hc) {
   const uint64_t mask = s.cap - 1;
   if (p->single_key) {
-    if (nm) return (int64_t)s.cap;                 // NULL key side slot (null-safe equality)
-    if (kw[0] == J_EMPTY) return (int64_t)s.cap + 1;
+    int64_t side = -1;
+    if (nm) side = (int64_t)s.cap;                         // NULL key side slot (null-safe equality)
+    else if (kw[0] == J_EMPTY) side = (int64_t)s.cap + 1;
+    if (side >= 0) { *hc = __ldcg((const unsigned long long*)(s.slots + side * 2 + 1)); return side; }
     uint64_t idx = mix64(kw[0]) & mask;
     while (true) {
-      uint64_t cur = __ldcg((const unsigned long long*)(s.slots + idx * 2));
-      if (cur == kw[0]) return (int64_t)idx;
-      if (cur == J_EMPTY) return -1;
+      const ulonglong2 sl = __ldcg((const ulonglong2*)(s.slots + idx * 2));  // key + head/count in one 128-bit load
+      if (sl.x == kw[0]) { *hc = sl.y; return (int64_t)idx; }
+      if (sl.x == J_EMPTY) return -1;
       idx = (idx + 1) & mask;
     }
   }
@@ -147,7 +192,7 @@ __device__ __forceinline__ int64_t js_find(const JoinSideDev& s, const JoinPlanD
       while (cur & 2ull) cur = *(volatile const unsigned long long*)ptr;
       bool eq = true;
       for (int k = 0; k < p->n_keys; k++) eq = eq && (__ldcg(ptr + 1 + k) == kw[k]);
-      if (eq) return (int64_t)idx;
+      if (eq) { *hc = __ldcg(ptr + p->KW); return (int64_t)idx; }
     }
     idx = (idx + 1) & mask;
   }
@@ -199,14 +244,6 @@ __device__ __forceinline__ int64_t js_find_or_insert(const JoinSideDev& s, const
   }
 }
 
-// head / count live in the last word of a slot: low 32 = head row (J_NIL = none), high 32 = live count
-__device__ __forceinline__ uint32_t* slot_head(const JoinSideDev& s, const JoinPlanDev* p, int64_t slot) {
-  return (uint32_t*)(s.slots + (uint64_t)slot * p->SW + p->KW);
-}
-__device__ __forceinline__ uint32_t* slot_count(const JoinSideDev& s, const JoinPlanDev* p, int64_t slot) {
-  return slot_head(s, p, slot) + 1;
-}
-
 __global__ void join_init_slots_kernel(uint64_t* slots, uint64_t cap, int SW, int KW, int single_key) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap + 2; i += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t* s = slots + i * SW;
@@ -216,34 +253,13 @@ __global__ void join_init_slots_kernel(uint64_t* slots, uint64_t cap, int SW, in
   }
 }
 
-// ------------------------------------------------------------------ row store access
-__device__ __forceinline__ bool store_is_null(const JoinSideDev& s, int c, uint32_t row) {
-  return s.valid[c] != nullptr && s.valid[c][row] == 0;
-}
-__device__ __forceinline__ uint64_t store_word(const JoinSideDev& s, const JoinPlanDev* p, int S, int c, uint32_t row) {
-  ColRef cr;
-  cr.data = s.col[c];
-  cr.type = p->col_type[S][c];
-  cr.width = p->col_width[S][c];
-  return load_key_word(cr, row);
-}
-
-// copy one datum between columns of equal width
-__device__ __forceinline__ void copy_datum(void* dst, int64_t di, const void* src, int64_t si, int width) {
-  switch (width) {
-    case 1: ((uint8_t*)dst)[di] = ((const uint8_t*)src)[si]; break;
-    case 2: ((uint16_t*)dst)[di] = ((const uint16_t*)src)[si]; break;
-    case 4: ((uint32_t*)dst)[di] = ((const uint32_t*)src)[si]; break;
-    case 8: ((uint64_t*)dst)[di] = ((const uint64_t*)src)[si]; break;
-    default: ((ulonglong2*)dst)[di] = ((const ulonglong2*)src)[si]; break;
-  }
-}
-
+// ------------------------------------------------------------------ emission
 // JoinStreamChunkBuilder::{append_row, append_row_update, append_row_matched}  builder.rs:84-148
-__device__ __forceinline__ void emit_row(const JoinOutDev& o, const JoinPlanDev* p, int64_t orow, uint8_t op, int S,
-                                         const DevChunk& ch, int64_t ur, const JoinSideDev& ms, int64_t mr) {
+// (ur < 0: update side NULL-padded; mrec == nullptr: matched side NULL-padded)
+__device__ __forceinline__ void emit_row(const JoinOutDev& o, const JoinPlanDev* p, JoinStatus* st, int64_t orow, uint8_t op,
+                                         int S, const DevChunk& ch, int64_t ur, const uint8_t* mrec) {
   o.ops[orow] = op;
-  o.vis[orow] = 1;
+  unsigned long long nullbits = 0;
   const int n_u = p->n_map[S], n_m = p->n_map[1 - S];
   for (int i = 0; i < n_u; i++) {
     const int ic = p->map_in[S][i], oc = p->map_out[S][i];
@@ -251,26 +267,27 @@ __device__ __forceinline__ void emit_row(const JoinOutDev& o, const JoinPlanDev*
     if (ur >= 0) {
       const ColRef& c = ch.cols[ic];
       nul = col_is_null(c, ur);
-      if (!nul) copy_datum(o.col[oc], orow, c.data, ur, c.width);
+      if (!nul) copy_bytes((uint8_t*)o.col[oc] + orow * c.width, (const uint8_t*)c.data + ur * c.width, c.width);
     }
-    o.valid[oc][orow] = nul ? 0 : 1;
-    if (nul) o.has_null[oc] = 1;
+    if (nul) { o.valid[oc][orow] = 0; nullbits |= 1ull << oc; }
   }
+  const uint32_t mnm = mrec ? ((const RecHdr*)mrec)->nullmask : 0xffffffffu;
   for (int i = 0; i < n_m; i++) {
     const int ic = p->map_in[1 - S][i], oc = p->map_out[1 - S][i];
-    bool nul = true;
-    if (mr >= 0) {
-      nul = store_is_null(ms, ic, (uint32_t)mr);
-      if (!nul) copy_datum(o.col[oc], orow, ms.col[ic], mr, p->col_width[1 - S][ic]);
+    const bool nul = (mnm >> ic) & 1;
+    if (!nul) {
+      const int w = p->col_width[1 - S][ic];
+      copy_bytes((uint8_t*)o.col[oc] + orow * w, mrec + p->col_off[1 - S][ic], w);
+    } else {
+      o.valid[oc][orow] = 0;
+      nullbits |= 1ull << oc;
     }
-    o.valid[oc][orow] = nul ? 0 : 1;
-    if (nul) o.has_null[oc] = 1;
   }
+  if (nullbits) atomicOr(&st->null_mask, nullbits);
 }
 
 // check_join_condition (hash_join.rs:1362-1384) restricted to one integer comparison
-__device__ __forceinline__ bool cond_ok(const JoinPlanDev* p, int S, const DevChunk& ch, int64_t ur, const JoinSideDev& ms,
-                                        uint32_t mr) {
+__device__ __forceinline__ bool cond_ok(const JoinPlanDev* p, int S, const DevChunk& ch, int64_t ur, const uint8_t* mrec) {
   if (p->cond_cmp == RW_CMP_NONE) return true;
   const int nl = p->n_cols[0];
   int64_t v[2];
@@ -283,8 +300,8 @@ __device__ __forceinline__ bool cond_ok(const JoinPlanDev* p, int S, const DevCh
       if (col_is_null(ch.cols[local], ur)) return false;
       v[t] = load_i64(ch.cols[local], ur);
     } else {
-      if (store_is_null(ms, local, mr)) return false;
-      v[t] = (int64_t)store_word(ms, p, 1 - S, local, mr);
+      if ((((const RecHdr*)mrec)->nullmask >> local) & 1) return false;
+      v[t] = (int64_t)rec_key_word(mrec, p->col_off[side][local], p->col_width[side][local], p->col_type[side][local]);
     }
   }
   switch (p->cond_cmp) {
@@ -297,35 +314,43 @@ __device__ __forceinline__ bool cond_ok(const JoinPlanDev* p, int S, const DevCh
   }
 }
 
-// does stored row `row` of side S carry the same pk as chunk row r ?  (pk = deduped_pk_indices;
-// the join key is equal by construction: join/hash_join.rs:710-713)
-__device__ __forceinline__ bool pk_equal(const JoinPlanDev* p, int S, const JoinSideDev& s, uint32_t row, const DevChunk& ch,
-                                         int64_t r) {
+// does the stored record carry the same pk as chunk row r ?  (pk = deduped_pk_indices; the join key
+// is equal by construction: join/hash_join.rs:710-713)
+__device__ __forceinline__ bool pk_equal(const JoinPlanDev* p, int S, const uint8_t* rec, const DevChunk& ch, int64_t r) {
+  const uint32_t nmask = ((const RecHdr*)rec)->nullmask;
   for (int i = 0; i < p->n_pk[S]; i++) {
     const int c = p->pk_col[S][i];
-    const bool n1 = store_is_null(s, c, row), n2 = col_is_null(ch.cols[c], r);
+    const bool n1 = (nmask >> c) & 1, n2 = col_is_null(ch.cols[c], r);
     if (n1 != n2) return false;
     if (n1) continue;
-    if (p->col_width[S][c] == 16) {
-      const uint64_t* a = (const uint64_t*)s.col[c] + (uint64_t)row * 2;
+    const int w = p->col_width[S][c];
+    if (w == 16) {
+      const uint64_t* a = (const uint64_t*)(rec + p->col_off[S][c]);
       const uint64_t* b = (const uint64_t*)ch.cols[c].data + r * 2;
       if (a[0] != b[0] || a[1] != b[1]) return false;
-    } else if (store_word(s, p, S, c, row) != load_key_word(ch.cols[c], r)) {
+    } else if (rec_key_word(rec, p->col_off[S][c], w, p->col_type[S][c]) != load_key_word(ch.cols[c], r)) {
       return false;
     }
   }
   return true;
 }
 
-// write chunk row r into the store at `row`
-__device__ __forceinline__ void store_write_row(const JoinPlanDev* p, int S, const JoinSideDev& s, uint32_t row,
-                                                const DevChunk& ch, int64_t r) {
+// write chunk row r into the record `row`
+__device__ __forceinline__ void rec_write(const JoinPlanDev* p, int S, const JoinSideDev& s, uint32_t row, const DevChunk& ch,
+                                          int64_t r, uint32_t link, uint32_t seq, uint32_t degree) {
+  uint8_t* rec = rec_ptr(s, row);
+  uint32_t nm = 0;
   for (int c = 0; c < p->n_cols[S]; c++) {
     const ColRef& cr = ch.cols[c];
-    const bool nul = col_is_null(cr, r);
-    if (s.valid[c]) s.valid[c][row] = nul ? 0 : 1;
-    if (!nul) copy_datum(s.col[c], row, cr.data, r, cr.width);
+    if (col_is_null(cr, r)) nm |= 1u << c;
+    else copy_bytes(rec + p->col_off[S][c], (const uint8_t*)cr.data + r * cr.width, cr.width);
   }
+  uint4 h;
+  h.x = link;
+  h.y = nm;
+  h.z = seq;
+  h.w = degree;
+  *(uint4*)rec = h;
 }
 
 // =============================================================================== generic path
@@ -362,8 +387,9 @@ __global__ void __launch_bounds__(256) join_prepare_kernel(const JoinPlanDev* __
       gid = 0x80000000u | (uint32_t)r;  // singleton group
       bound = jt_forward_if_not_matched(T, S) ? 1 : 0;
     } else {
-      ms = js_find(other, p, kw, nm);
-      const uint64_t m = ms >= 0 ? (uint64_t)*slot_count(other, p, ms) : 0;
+      uint64_t hc = 0;
+      ms = js_find(other, p, kw, nm, &hc);
+      const uint64_t m = ms >= 0 ? (hc >> 32) : 0;
       uint64_t per_match;
       if (T == RW_JOIN_INNER) per_match = 1;
       else if (jt_is_semi(T) || jt_is_anti(T)) per_match = jt_forward_exactly_once(T, S) ? 0 : 1;
@@ -416,20 +442,20 @@ __global__ void fill_i32_kernel(int32_t* p, uint64_t n, int32_t v) {
 __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch,
                                                            JoinSideDev own, JoinSideDev other, JoinScratch sc,
                                                            const uint64_t* __restrict__ sorted, JoinOutDev o,
-                                                           JoinStatus* st, uint32_t store_base) {
+                                                           JoinStatus* st, uint32_t store_base, uint32_t seq_base) {
   const int T = p->T;
   const bool fwd_once = jt_forward_exactly_once(T, S);
   const bool fwd_unmatched = jt_forward_if_not_matched(T, S);
   const bool fwd_matched = jt_is_semi(T) && fwd_once;
   const bool only_matched = jt_only_forward_matched_side(T, S);
   const bool side_null = jt_outer_side_null(T, S);
-  const bool other_deg = other.degree != nullptr;
+  const bool other_deg = p->need_degree[1 - S] != 0;
+  const bool own_deg = p->need_degree[S] != 0;
   unsigned int new_keys = 0;
-  long long live_own = 0, live_other = 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ch.n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t sk = sorted[i];
     const uint32_t gid = (uint32_t)(sk >> 32);
-    if (gid == 0xFFFFFFFFu) continue;                          // invisible rows
+    if (gid == 0xFFFFFFFFu) continue;                               // invisible rows
     if (i > 0 && (uint32_t)(sorted[i - 1] >> 32) == gid) continue;  // not a group start
     int64_t own_slot = -2;  // lazily resolved
     for (int64_t j = i; j < ch.n && (uint32_t)(sorted[j] >> 32) == gid; j++) {
@@ -445,7 +471,7 @@ __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __r
       const bool room = obase + bound <= o.capacity;
       if (!room) atomicOr(&st->err, JERR_OUT_CAPACITY);
       if (gid & 0x80000000u) {  // CacheResult::NeverMatch (hash_join.rs:1126-1135): forwarded, never stored
-        if (fwd_unmatched && room) emit_row(o, p, obase + w++, jop, S, ch, r, other, -1);
+        if (fwd_unmatched && room) emit_row(o, p, st, obase + w++, jop, S, ch, r, nullptr);
         continue;
       }
       const int64_t ms = sc.match_slot[r];
@@ -454,27 +480,29 @@ __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __r
       if (ms >= 0) {
         uint32_t m = *slot_head(other, p, ms) & 0x7fffffffu;
         while (m != J_NIL) {
-          const uint32_t lk = other.link[m];
+          uint8_t* mrec = rec_ptr(other, m);
+          RecHdr* mh = (RecHdr*)mrec;
+          const uint32_t lk = mh->link;
           if (!(lk & J_DEAD)) {
-            if (cond_ok(p, S, ch, r, other, m)) {
+            if (cond_ok(p, S, ch, r, mrec)) {
               degree++;
-              uint32_t md = other_deg ? other.degree[m] : 0;
+              uint32_t md = other_deg ? mh->degree : 0;
               if (ins && !fwd_once && room) {  // with_match_on_insert (builder.rs:184-231): m.degree BEFORE the increment
-                if (jt_is_anti(T)) { if (md == 0 && only_matched) emit_row(o, p, obase + w++, RW_OP_DELETE, S, ch, -1, other, m); }
-                else if (jt_is_semi(T)) { if (md == 0 && only_matched) emit_row(o, p, obase + w++, RW_OP_INSERT, S, ch, -1, other, m); }
+                if (jt_is_anti(T)) { if (md == 0 && only_matched) emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, -1, mrec); }
+                else if (jt_is_semi(T)) { if (md == 0 && only_matched) emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, -1, mrec); }
                 else if (md == 0 && side_null) {
-                  emit_row(o, p, obase + w++, RW_OP_DELETE, S, ch, -1, other, m);
-                  emit_row(o, p, obase + w++, RW_OP_INSERT, S, ch, r, other, m);
-                } else emit_row(o, p, obase + w++, RW_OP_INSERT, S, ch, r, other, m);
+                  emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, -1, mrec);
+                  emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, r, mrec);
+                } else emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, r, mrec);
               }
-              if (other_deg) { md = ins ? md + 1 : md - 1; other.degree[m] = md; }  // update_degree (join/hash_join.rs:355-380)
+              if (other_deg) { md = ins ? md + 1 : md - 1; mh->degree = md; }  // update_degree (join/hash_join.rs:355-380)
               if (!ins && !fwd_once && room) {  // with_match_on_delete (builder.rs:233-284): m.degree AFTER the decrement
-                if (jt_is_anti(T)) { if (md == 0 && only_matched) emit_row(o, p, obase + w++, RW_OP_INSERT, S, ch, -1, other, m); }
-                else if (jt_is_semi(T)) { if (md == 0 && only_matched) emit_row(o, p, obase + w++, RW_OP_DELETE, S, ch, -1, other, m); }
+                if (jt_is_anti(T)) { if (md == 0 && only_matched) emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, -1, mrec); }
+                else if (jt_is_semi(T)) { if (md == 0 && only_matched) emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, -1, mrec); }
                 else if (md == 0 && side_null) {
-                  emit_row(o, p, obase + w++, RW_OP_DELETE, S, ch, r, other, m);
-                  emit_row(o, p, obase + w++, RW_OP_INSERT, S, ch, -1, other, m);
-                } else emit_row(o, p, obase + w++, RW_OP_DELETE, S, ch, r, other, m);
+                  emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, r, mrec);
+                  emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, -1, mrec);
+                } else emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, r, mrec);
               }
             }
             if (p->append_only_optimize) {  // hash_join.rs:1339-1345 (regardless of the condition)
@@ -487,208 +515,245 @@ __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __r
       }
       // forward rows depending on join types (hash_join.rs:1198-1210)
       if (room) {
-        if (degree == 0) { if (fwd_unmatched) emit_row(o, p, obase + w++, jop, S, ch, r, other, -1); }
-        else if (fwd_matched) emit_row(o, p, obase + w++, jop, S, ch, r, other, -1);
+        if (degree == 0) { if (fwd_unmatched) emit_row(o, p, st, obase + w++, jop, S, ch, r, nullptr); }
+        else if (fwd_matched) emit_row(o, p, st, obase + w++, jop, S, ch, r, nullptr);
+        if (w < bound) atomicOr(&st->null_mask, 1ull << 63);
         for (; w < bound; w++) {  // unused reserved rows become invisible holes
           o.ops[obase + w] = RW_OP_INSERT;
           o.vis[obase + w] = 0;
-          o.has_null[J_MAX_OUT] = 1;
-          for (int k = 0; k < p->n_out; k++) o.valid[k][obase + w] = 0;
         }
       }
       // append-only optimisation (hash_join.rs:1222-1228): drop the matched row, do not store u
       if (p->append_only_optimize && ao_row >= 0) {
-        other.link[ao_row] |= J_DEAD;
+        rec_hdr(other, (uint32_t)ao_row)->link |= J_DEAD;
         *slot_count(other, p, ms) -= 1;
-        live_other--;
         continue;
       }
       // own-side state (hash_join.rs:1230-1242; JoinHashMap::insert / delete join/hash_join.rs:591-681)
       if (own_slot == -2) {
         uint64_t kw[RW_MAX_KEYS];
         uint32_t nm;
+        uint64_t hc;
         chunk_key(p, S, ch, r, kw, &nm);
         bool created = false;
-        own_slot = ins ? js_find_or_insert(own, p, kw, nm, &created) : js_find(own, p, kw, nm);
+        own_slot = ins ? js_find_or_insert(own, p, kw, nm, &created) : js_find(own, p, kw, nm, &hc);
         if (created) new_keys++;
-        if (own_slot < 0 && ins) own_slot = -2;
       }
       if (ins) {
-        store_write_row(p, S, own, store_row, ch, r);
-        if (own.degree) own.degree[store_row] = degree;
         uint32_t* hd = slot_head(own, p, own_slot);
-        own.link[store_row] = *hd & 0x7fffffffu;
+        rec_write(p, S, own, store_row, ch, r, *hd & 0x7fffffffu, seq_base + (uint32_t)r, own_deg ? degree : 0);
         *hd = store_row;
         *slot_count(own, p, own_slot) += 1;
-        live_own++;
       } else {
         bool found = false;
         if (own_slot >= 0) {
           uint32_t m = *slot_head(own, p, own_slot) & 0x7fffffffu;
           while (m != J_NIL) {
-            const uint32_t lk = own.link[m];
-            if (!(lk & J_DEAD) && pk_equal(p, S, own, m, ch, r)) {
-              own.link[m] = lk | J_DEAD;
+            uint8_t* mrec = rec_ptr(own, m);
+            const uint32_t lk = ((RecHdr*)mrec)->link;
+            if (!(lk & J_DEAD) && pk_equal(p, S, mrec, ch, r)) {
+              ((RecHdr*)mrec)->link = lk | J_DEAD;
               *slot_count(own, p, own_slot) -= 1;
-              live_own--;
               found = true;
               break;
             }
             m = lk & 0x7fffffffu;
           }
         } else {
-          own_slot = -2;  // key may be created by a later insert of this group
+          own_slot = -2;  // the key may be created by a later insert of this group
         }
         if (!found && p->strict) atomicOr(&st->err, JERR_DOUBLE_DELETE);
       }
     }
   }
   if (new_keys) atomicAdd(&st->n_keys[S], (unsigned long long)new_keys);
-  if (live_own) atomicAdd(&st->live_rows[S], (unsigned long long)live_own);
-  if (live_other) atomicAdd(&st->live_rows[1 - S], (unsigned long long)live_other);
 }
 
 // =============================================================================== inner fast path
-// F1: probe + emit, fused.  Each thread walks the matched chain once, buffering up to 4 matches in
-// registers; blocks reserve output ranges with one atomicAdd after a block-wide scan (warp shuffles).
-// The kernel does not mutate operator state, so it is simply re-run with a larger output buffer
-// if the reservation overflowed.
+// One fused kernel per batch.  A tile is JF_BLOCK * JF_R consecutive rows, thread t owning rows
+// t, t + JF_BLOCK, ... (coalesced column loads; JF_R independent slot probes and record gathers in
+// flight per thread).  Phase 1 probes the other side's index (128-bit slot loads).  Phase 2 is a
+// tile-wide scan (warp shuffles + one shared-memory pass) of the match counts and of the own-side
+// store flags; one atomicAdd per tile reserves the output range / the record ids.  Phase 3 walks
+// the matched chains and emits (warp-coalesced column stores).  Phase 4 appends the rows to the own
+// side (record write, slot claim, head exchange).  With `PROBE_ONLY` phases 1-3 run alone: the
+// host uses it to redo the emission after an output-capacity overflow (phases 1-3 never touch
+// operator state, and phase 4 only touches the OWN side, so the redo is exact).
 #define JF_BLOCK 256
-__global__ void __launch_bounds__(JF_BLOCK) join_inner_probe_emit_kernel(const JoinPlanDev* __restrict__ p, int S,
-                                                                          DevChunk ch, JoinSideDev other, JoinOutDev o,
-                                                                          JoinStatus* st, uint32_t* store_flag /* [n] */) {
-  __shared__ unsigned long long warp_tot[JF_BLOCK / 32];
-  __shared__ unsigned long long block_base;
+#define JF_R 4
+template <bool PROBE_ONLY>
+__global__ void __launch_bounds__(JF_BLOCK) join_inner_fused_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch,
+                                                                     JoinSideDev own, JoinSideDev other, JoinOutDev o,
+                                                                     JoinStatus* st, uint32_t store_base, uint32_t seq_base) {
+  __shared__ unsigned long long s_cnt[JF_R][JF_BLOCK / 32];
+  __shared__ unsigned int s_sto[JF_R][JF_BLOCK / 32];
+  __shared__ unsigned long long s_out_base;
+  __shared__ unsigned int s_store_base;
   const int lane = lane_id(), wid = threadIdx.x >> 5;
-  const int64_t n_iter = (ch.n + (int64_t)gridDim.x * JF_BLOCK - 1) / ((int64_t)gridDim.x * JF_BLOCK);
-  for (int64_t it = 0; it < n_iter; it++) {
-    const int64_t r = (it * gridDim.x + blockIdx.x) * (int64_t)JF_BLOCK + threadIdx.x;
-    uint32_t cnt = 0, first[4], head = J_NIL;
-    uint8_t op = 0;
-    if (r < ch.n) {
-      op = ch.ops[r];
-      uint32_t sf = 0;
-      if (row_visible(ch, r, op)) {
-        uint64_t kw[RW_MAX_KEYS];
-        uint32_t nm;
-        if (!chunk_key(p, S, ch, r, kw, &nm)) {
-          sf = (op == RW_OP_INSERT || op == RW_OP_UPDATE_INSERT) ? 1u : 0u;
-          const int64_t ms = js_find(other, p, kw, nm);
-          if (ms >= 0) {
-            head = *slot_head(other, p, ms) & 0x7fffffffu;
-            uint32_t m = head;
-            while (m != J_NIL) {
-              const uint32_t lk = __ldcg(other.link + m);
-              if (!(lk & J_DEAD) && cond_ok(p, S, ch, r, other, m)) {
-                if (cnt < 4) first[cnt] = m;
-                cnt++;
-              }
-              m = lk & 0x7fffffffu;
+  const int64_t tile_rows = (int64_t)JF_BLOCK * JF_R;
+  const int64_t n_tiles = (ch.n + tile_rows - 1) / tile_rows;
+  unsigned int new_keys = 0, n_del = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t base = tile * tile_rows;
+    uint32_t head[JF_R], cnt[JF_R];
+    uint8_t op[JF_R];
+    bool store[JF_R];
+    // ---- phase 1: probe
+#pragma unroll
+    for (int k = 0; k < JF_R; k++) {
+      const int64_t r = base + (int64_t)k * JF_BLOCK + threadIdx.x;
+      head[k] = J_NIL; cnt[k] = 0; op[k] = 0; store[k] = false;
+      if (r < ch.n) {
+        op[k] = ch.ops[r];
+        if (row_visible(ch, r, op[k])) {
+          uint64_t kw[RW_MAX_KEYS];
+          uint32_t nm;
+          const bool ins = (op[k] == RW_OP_INSERT || op[k] == RW_OP_UPDATE_INSERT);
+          if (!chunk_key(p, S, ch, r, kw, &nm)) {
+            store[k] = ins;
+            if (!ins) n_del++;
+            uint64_t hc;
+            if (js_find(other, p, kw, nm, &hc) >= 0) {
+              head[k] = (uint32_t)hc & 0x7fffffffu;
+              cnt[k] = (uint32_t)(hc >> 32);
             }
           }
+        } else {
+          op[k] = 0;
         }
       }
-      store_flag[r] = sf;
     }
-    // block-wide exclusive scan of cnt
-    unsigned long long incl = cnt;
-    for (int d = 1; d < 32; d <<= 1) {
-      unsigned long long v = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += v;
+    if (p->cond_cmp != RW_CMP_NONE) {  // a non-equi condition filters matches: count by walking
+#pragma unroll
+      for (int k = 0; k < JF_R; k++) {
+        if (cnt[k] == 0) continue;
+        const int64_t r = base + (int64_t)k * JF_BLOCK + threadIdx.x;
+        uint32_t m = head[k], c = 0;
+        while (m != J_NIL) {
+          const uint8_t* mrec = rec_ptr(other, m);
+          const uint32_t lk = ((const RecHdr*)mrec)->link;
+          if (!(lk & J_DEAD) && cond_ok(p, S, ch, r, mrec)) c++;
+          m = lk & 0x7fffffffu;
+        }
+        cnt[k] = c;
+      }
     }
-    if (lane == 31) warp_tot[wid] = incl;
+    // ---- phase 2: tile scan (row order = k-major), one reservation per tile
+    unsigned long long incl[JF_R];
+    unsigned int sincl[JF_R];
+#pragma unroll
+    for (int k = 0; k < JF_R; k++) {
+      unsigned long long v = cnt[k];
+      unsigned int sv = store[k] ? 1u : 0u;
+      for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, v, d);
+        unsigned int ts = __shfl_up_sync(0xffffffffu, sv, d);
+        if (lane >= d) { v += t; sv += ts; }
+      }
+      incl[k] = v;
+      sincl[k] = sv;
+      if (lane == 31) { s_cnt[k][wid] = v; s_sto[k][wid] = sv; }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long run = 0;
-      for (int w = 0; w < JF_BLOCK / 32; w++) { unsigned long long t = warp_tot[w]; warp_tot[w] = run; run += t; }
-      block_base = run ? atomicAdd(&st->out_rows, run) : 0ull;
+      unsigned int srun = 0;
+      for (int k = 0; k < JF_R; k++)
+        for (int w = 0; w < JF_BLOCK / 32; w++) {
+          unsigned long long t = s_cnt[k][w]; s_cnt[k][w] = run; run += t;
+          unsigned int ts = s_sto[k][w]; s_sto[k][w] = srun; srun += ts;
+        }
+      s_out_base = run ? atomicAdd(&st->out_rows, run) : 0ull;
+      s_store_base = (!PROBE_ONLY && srun) ? (unsigned int)atomicAdd(&st->n_store, (unsigned long long)srun) : 0u;
     }
     __syncthreads();
-    if (cnt) {
-      int64_t pos = (int64_t)(block_base + warp_tot[wid] + incl - cnt);
-      if (pos + cnt > o.capacity) {
-        atomicOr(&st->err, JERR_OUT_CAPACITY);
-      } else {
-        const uint8_t oop = (op == RW_OP_INSERT || op == RW_OP_UPDATE_INSERT) ? RW_OP_INSERT : RW_OP_DELETE;
-        if (cnt <= 4) {
-          for (uint32_t k = 0; k < cnt; k++) emit_row(o, p, pos + k, oop, S, ch, r, other, first[k]);
-        } else {
-          uint32_t m = head;
-          while (m != J_NIL) {
-            const uint32_t lk = __ldcg(other.link + m);
-            if (!(lk & J_DEAD) && cond_ok(p, S, ch, r, other, m)) emit_row(o, p, pos++, oop, S, ch, r, other, m);
-            m = lk & 0x7fffffffu;
-          }
-        }
+    // ---- phase 3: emit
+#pragma unroll
+    for (int k = 0; k < JF_R; k++) {
+      if (cnt[k] == 0) continue;
+      const int64_t r = base + (int64_t)k * JF_BLOCK + threadIdx.x;
+      int64_t pos = (int64_t)(s_out_base + s_cnt[k][wid] + incl[k] - cnt[k]);
+      if (pos + cnt[k] > o.capacity) { atomicOr(&st->err, JERR_OUT_CAPACITY); continue; }
+      const uint8_t oop = (op[k] == RW_OP_INSERT || op[k] == RW_OP_UPDATE_INSERT) ? RW_OP_INSERT : RW_OP_DELETE;
+      uint32_t m = head[k];
+      uint32_t left = cnt[k];
+      while (m != J_NIL && left) {
+        const uint8_t* mrec = rec_ptr(other, m);
+        const uint32_t lk = ((const RecHdr*)mrec)->link;
+        if (!(lk & J_DEAD) && cond_ok(p, S, ch, r, mrec)) { emit_row(o, p, st, pos++, oop, S, ch, r, mrec); left--; }
+        m = lk & 0x7fffffffu;
+      }
+    }
+    // ---- phase 4: append to the own side
+    if (!PROBE_ONLY) {
+#pragma unroll
+      for (int k = 0; k < JF_R; k++) {
+        if (!store[k]) continue;
+        const int64_t r = base + (int64_t)k * JF_BLOCK + threadIdx.x;
+        const uint32_t row = store_base + s_store_base + s_sto[k][wid] + sincl[k] - 1;
+        uint64_t kw[RW_MAX_KEYS];
+        uint32_t nm;
+        chunk_key(p, S, ch, r, kw, &nm);
+        bool created = false;
+        const int64_t slot = js_find_or_insert(own, p, kw, nm, &created);
+        if (created) new_keys++;
+        const uint32_t old = atomicExch(slot_head(own, p, slot), row);
+        rec_write(p, S, own, row, ch, r, old & 0x7fffffffu, seq_base + (uint32_t)r, 0);
+        atomicAdd(slot_count(own, p, slot), 1u);
       }
     }
     __syncthreads();
   }
-}
-
-// F2: own-side inserts (row-parallel).  Store row ids are store_base + (number of stored rows before r)
-// -- an exclusive scan of the store flags -- so ids increase with the chunk position.
-__global__ void __launch_bounds__(256) join_inner_insert_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch,
-                                                                 JoinSideDev own, JoinStatus* st, uint32_t store_base,
-                                                                 const uint32_t* __restrict__ store_flag,
-                                                                 const uint32_t* __restrict__ store_rank) {
-  unsigned int new_keys = 0;
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
-    if (r == ch.n - 1) st->n_store = (unsigned long long)store_rank[r] + store_flag[r];
-    if (!store_flag[r]) continue;
-    uint64_t kw[RW_MAX_KEYS];
-    uint32_t nm = 0;
-    chunk_key(p, S, ch, r, kw, &nm);
-    const uint32_t row = store_base + store_rank[r];
-    store_write_row(p, S, own, row, ch, r);
-    bool created = false;
-    const int64_t slot = js_find_or_insert(own, p, kw, nm, &created);
-    if (created) new_keys++;
-    const uint32_t old = atomicExch(slot_head(own, p, slot), row);
-    own.link[row] = old & 0x7fffffffu;
-    atomicAdd(slot_count(own, p, slot), 1u);
+  if (!PROBE_ONLY) {
+    for (int d = 16; d > 0; d >>= 1) {
+      new_keys += __shfl_xor_sync(0xffffffffu, new_keys, d);
+      n_del += __shfl_xor_sync(0xffffffffu, n_del, d);
+    }
+    if (lane == 0 && new_keys) atomicAdd(&st->n_keys[S], (unsigned long long)new_keys);
+    if (lane == 0 && n_del) atomicAdd(&st->n_del, (unsigned long long)n_del);
   }
-  for (int d = 16; d > 0; d >>= 1) new_keys += __shfl_xor_sync(0xffffffffu, new_keys, d);
-  if (lane_id() == 0 && new_keys) atomicAdd(&st->n_keys[S], (unsigned long long)new_keys);
 }
 
-// F3: own-side deletes (row-parallel, after F2).  Sequential rule: the delete at chunk position r
-// removes the live row with equal pk that was inserted most recently BEFORE position r, i.e. the
-// largest store row id below store_base + rank(r).
+// own-side deletes of the fast path (after the fused kernel; exits at once when the batch has none).
+// Sequential rule: the delete at chunk position r removes the live record with equal pk that
+// arrived most recently BEFORE r (largest seq below seq_base + r, wrap-aware).
 __global__ void __launch_bounds__(256) join_inner_delete_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch,
-                                                                 JoinSideDev own, JoinStatus* st, uint32_t store_base,
-                                                                 const uint32_t* __restrict__ store_rank /* [n] */) {
-  long long removed = 0;
+                                                                 JoinSideDev own, JoinStatus* st, uint32_t seq_base) {
+  if (*(volatile unsigned long long*)&st->n_del == 0ull) return;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
     const uint8_t op = ch.ops[r];
     if (!row_visible(ch, r, op) || !(op == RW_OP_DELETE || op == RW_OP_UPDATE_DELETE)) continue;
     uint64_t kw[RW_MAX_KEYS];
     uint32_t nm;
     if (chunk_key(p, S, ch, r, kw, &nm)) continue;  // never-match rows were never stored
-    const int64_t slot = js_find(own, p, kw, nm);
+    uint64_t hc;
+    const int64_t slot = js_find(own, p, kw, nm, &hc);
     bool found = false;
     if (slot >= 0) {
-      const uint32_t bound = store_base + store_rank[r];
+      const uint32_t my_seq = seq_base + (uint32_t)r;
       while (!found) {
-        uint32_t best = J_NIL;
+        uint32_t best = J_NIL, best_age = 0xffffffffu;
         uint32_t m = *slot_head(own, p, slot) & 0x7fffffffu;
         while (m != J_NIL) {
-          const uint32_t lk = __ldcg(own.link + m);
-          if (!(lk & J_DEAD) && m < bound && (best == J_NIL || m > best) && pk_equal(p, S, own, m, ch, r)) best = m;
+          const uint8_t* mrec = rec_ptr(own, m);
+          const uint32_t lk = __ldcg(&((const RecHdr*)mrec)->link);
+          const uint32_t age = my_seq - ((const RecHdr*)mrec)->seq;  // in (0, 2^31) for records that arrived before r
+          if (!(lk & J_DEAD) && age != 0 && age < 0x80000000u && age < best_age && pk_equal(p, S, mrec, ch, r)) {
+            best = m;
+            best_age = age;
+          }
           m = lk & 0x7fffffffu;
         }
         if (best == J_NIL) break;
-        const uint32_t old = atomicOr(own.link + best, J_DEAD);
+        const uint32_t old = atomicOr(&rec_hdr(own, best)->link, J_DEAD);
         if (!(old & J_DEAD)) {
           atomicSub(slot_count(own, p, slot), 1u);
-          removed++;
           found = true;
         }
       }
     }
     if (!found && p->strict) atomicOr(&st->err, JERR_DOUBLE_DELETE);
   }
-  if (removed) atomicAdd(&st->live_rows[S], (unsigned long long)(-removed));
 }
 
 // ------------------------------------------------------------------ growth helpers
@@ -730,11 +795,10 @@ using namespace rw;
 struct JoinSideHost {
   int n_cols = 0;
   std::vector<int> types;
-  DevBuf col[RW_MAX_COLS], valid[RW_MAX_COLS], link, degree, slots;
-  bool has_valid[RW_MAX_COLS];
-  bool need_degree = false;
-  uint64_t row_cap = 0;   // rows allocated in the store
-  uint64_t n_rows = 0;    // rows handed out (incl. dead / cancelled)
+  DevBuf recs, slots;
+  int stride = 0;
+  uint64_t row_cap = 0;   // records allocated
+  uint64_t n_rows = 0;    // records handed out (incl. dead ones)
   uint64_t slot_cap = 0;
   uint64_t keys_upper = 0;
 };
@@ -749,18 +813,21 @@ struct rwgpu_join {
   int chunk_size = 1024;
   bool fast_inner = false;
   uint64_t launches = 0;
+  uint64_t seq = 0;
   KernelProf prof;
-  // scratch
-  DevBuf sk, sk_alt, packed, offs, mslot, gtable, cub_tmp, row_of, row_rev, row_bound;
+  // scratch (generic path)
+  DevBuf sk, sk_alt, packed, offs, mslot, gtable, cub_tmp;
   int64_t scratch_rows = 0;
   uint64_t gcap = 0;
   size_t cub_bytes = 0;
   // output (device)
-  DevBuf out_ops, out_vis, out_hasnull, out_col[J_MAX_OUT], out_valid[J_MAX_OUT], out_bits[J_MAX_OUT], out_visbits;
+  DevBuf out_ops, out_vis, out_col[J_MAX_OUT], out_valid[J_MAX_OUT], out_bits[J_MAX_OUT], out_visbits;
   int64_t out_cap = 0;
-  // host upload staging
+  unsigned long long valid_dirty = 0;  // columns whose valid bytes hold zeros from the previous push
+  // host staging
   DevBuf up;
   PinnedBuf up_host;
+  std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
   std::vector<rw_column> dev_view_cols;
   ~rwgpu_join() { if (stream) cudaStreamDestroy(stream); }
 };
@@ -773,15 +840,11 @@ static int jgrid(int64_t n, int block) {
 static JoinSideDev side_dev(const rwgpu_join* h, int S) {
   const JoinSideHost& s = h->side[S];
   JoinSideDev d;
-  memset(&d, 0, sizeof(d));
-  for (int c = 0; c < s.n_cols; c++) {
-    d.col[c] = s.col[c].p;
-    d.valid[c] = s.has_valid[c] ? s.valid[c].as<uint8_t>() : nullptr;
-  }
-  d.link = s.link.as<uint32_t>();
-  d.degree = s.need_degree ? s.degree.as<uint32_t>() : nullptr;
+  d.recs = s.recs.as<uint8_t>();
   d.slots = s.slots.as<uint64_t>();
   d.cap = s.slot_cap;
+  d.stride = s.stride;
+  d.pad = 0;
   return d;
 }
 
@@ -793,40 +856,19 @@ static int join_alloc_slots(rwgpu_join* h, DevBuf& buf, uint64_t cap) {
   return RW_OK;
 }
 
-// grow the row store of side S to hold at least `rows` rows (contents preserved)
+// grow the record store of side S to hold at least `rows` records (contents preserved)
 static int join_grow_store(rwgpu_join* h, int S, uint64_t rows) {
   JoinSideHost& s = h->side[S];
   if (rows <= s.row_cap) return RW_OK;
   if (rows >= 0x7ffffff0ull) return fail(RW_ERR_OOM, "join side exceeds 2^31 rows");
   uint64_t ncap = std::max<uint64_t>(s.row_cap * 2, std::max<uint64_t>(rows, 1 << 16));
   ncap = std::min<uint64_t>(ncap, 0x7ffffff0ull);
-  auto grow = [&](DevBuf& b, size_t elt) -> int {
-    DevBuf nb;
-    RW_CUDA(nb.reserve(ncap * elt));
-    if (s.n_rows) RW_CUDA(cudaMemcpyAsync(nb.p, b.p, s.n_rows * elt, cudaMemcpyDeviceToDevice, h->stream));
-    RW_CUDA(cudaStreamSynchronize(h->stream));
-    b = std::move(nb);
-    return RW_OK;
-  };
-  for (int c = 0; c < s.n_cols; c++) {
-    int rc = grow(s.col[c], (size_t)type_width(s.types[c]));
-    if (rc != RW_OK) return rc;
-    if (s.has_valid[c]) { rc = grow(s.valid[c], 1); if (rc != RW_OK) return rc; }
-  }
-  int rc = grow(s.link, 4);
-  if (rc != RW_OK) return rc;
-  if (s.need_degree) { rc = grow(s.degree, 4); if (rc != RW_OK) return rc; }
+  DevBuf nb;
+  RW_CUDA(nb.reserve(ncap * (size_t)s.stride));
+  if (s.n_rows) RW_CUDA(cudaMemcpyAsync(nb.p, s.recs.p, s.n_rows * (size_t)s.stride, cudaMemcpyDeviceToDevice, h->stream));
+  RW_CUDA(cudaStreamSynchronize(h->stream));
+  s.recs = std::move(nb);
   s.row_cap = ncap;
-  return RW_OK;
-}
-
-// a column of side S is about to receive NULLs for the first time: materialise its valid bytes
-static int join_enable_valid(rwgpu_join* h, int S, int c) {
-  JoinSideHost& s = h->side[S];
-  if (s.has_valid[c]) return RW_OK;
-  RW_CUDA(s.valid[c].reserve(std::max<uint64_t>(s.row_cap, 1)));
-  RW_CUDA(cudaMemsetAsync(s.valid[c].p, 1, std::max<uint64_t>(s.row_cap, 1), h->stream));
-  s.has_valid[c] = true;
   return RW_OK;
 }
 
@@ -856,37 +898,44 @@ static int join_ensure_scratch(rwgpu_join* h, int64_t n) {
     RW_CUDA(h->packed.reserve((size_t)cap * 8));
     RW_CUDA(h->offs.reserve((size_t)cap * 8));
     RW_CUDA(h->mslot.reserve((size_t)cap * 8));
-    RW_CUDA(h->row_of.reserve((size_t)cap * 4));
-    RW_CUDA(h->row_rev.reserve((size_t)cap * 4));
-    RW_CUDA(h->row_bound.reserve((size_t)cap * 4));
     uint64_t g = 1024;
     while (g < (uint64_t)cap * 2) g <<= 1;
     RW_CUDA(h->gtable.reserve(g * 4));
     h->gcap = g;
-    size_t b1 = 0, b2 = 0, b3 = 0;
+    size_t b1 = 0, b2 = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, b1, (uint64_t*)nullptr, (uint64_t*)nullptr, (int)cap);
     cub::DoubleBuffer<uint64_t> db((uint64_t*)nullptr, (uint64_t*)nullptr);
     cub::DeviceRadixSort::SortKeys(nullptr, b2, db, (int)cap);
-    cub::DeviceScan::ExclusiveSum(nullptr, b3, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)cap);
-    h->cub_bytes = std::max(b1, std::max(b2, b3)) + 256;
+    h->cub_bytes = std::max(b1, b2) + 256;
     RW_CUDA(h->cub_tmp.reserve(h->cub_bytes));
     h->scratch_rows = cap;
   }
   return RW_OK;
 }
 
-static int join_ensure_out(rwgpu_join* h, int64_t rows) {
+static int join_ensure_out(rwgpu_join* h, int64_t rows, cudaStream_t st) {
   if (rows <= h->out_cap) return RW_OK;
   int64_t cap = std::max<int64_t>(rows + rows / 4, 4096);
+  RW_CUDA(cudaStreamSynchronize(st));
   RW_CUDA(h->out_ops.reserve((size_t)cap));
   RW_CUDA(h->out_vis.reserve((size_t)cap));
   RW_CUDA(h->out_visbits.reserve((size_t)((cap + 63) / 64) * 8));
   for (size_t k = 0; k < h->out_types.size(); k++) {
     RW_CUDA(h->out_col[k].reserve((size_t)cap * type_width(h->out_types[k])));
     RW_CUDA(h->out_valid[k].reserve((size_t)cap));
+    RW_CUDA(cudaMemsetAsync(h->out_valid[k].p, 1, (size_t)cap, st));  // invariant: valid bytes are 1 between pushes
     RW_CUDA(h->out_bits[k].reserve((size_t)((cap + 63) / 64) * 8));
   }
+  h->valid_dirty = 0;
   h->out_cap = cap;
+  return RW_OK;
+}
+
+// restore the "valid bytes are all 1" invariant for the columns the previous push wrote NULLs to
+static int join_clean_valid(rwgpu_join* h, cudaStream_t st) {
+  for (size_t k = 0; k < h->out_types.size(); k++)
+    if ((h->valid_dirty >> k) & 1) RW_CUDA(cudaMemsetAsync(h->out_valid[k].p, 1, (size_t)h->out_cap, st));
+  h->valid_dirty = 0;
   return RW_OK;
 }
 
@@ -896,7 +945,6 @@ static JoinOutDev out_dev(rwgpu_join* h) {
   o.ops = h->out_ops.as<uint8_t>();
   o.vis = h->out_vis.as<uint8_t>();
   for (size_t k = 0; k < h->out_types.size(); k++) { o.col[k] = h->out_col[k].p; o.valid[k] = h->out_valid[k].as<uint8_t>(); }
-  o.has_null = h->out_hasnull.as<unsigned int>();
   o.capacity = h->out_cap;
   return o;
 }
@@ -917,66 +965,67 @@ static int join_check_err(rwgpu_join* h, const JoinStatus& s, cudaStream_t st) {
   return fail(RW_ERR_CUDA, "internal: join output capacity");
 }
 
-// one push of a device-resident chunk; on return the output sits in the device output buffers
+// one push of a device-resident chunk; on return the output sits in the device output buffers.
+// *null_mask: bit k = output column k holds NULLs, bit 63 = some rows are invisible.
 static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t st, int64_t* out_rows,
-                         unsigned int* has_null_host) {
+                         unsigned long long* null_mask) {
   *out_rows = 0;
-  memset(has_null_host, 0, sizeof(unsigned int) * (J_MAX_OUT + 1));
+  *null_mask = 0;
   const int64_t n = ch.n;
   if (n <= 0) return RW_OK;
   if (n >= (1ll << 31)) return fail(RW_ERR_INVALID, "chunk too large");
   JoinSideHost& own = h->side[S];
-  // NULL-carrying input columns need valid bytes in the store
-  for (int c = 0; c < own.n_cols; c++)
-    if (ch.cols[c].valid_bits || ch.cols[c].valid_bytes) { int rc = join_enable_valid(h, S, c); if (rc != RW_OK) return rc; }
-  int rc = join_ensure_scratch(h, n);
-  if (rc != RW_OK) return rc;
-  rc = join_grow_store(h, S, own.n_rows + (uint64_t)n);
+  int rc = join_grow_store(h, S, own.n_rows + (uint64_t)n);
   if (rc != RW_OK) return rc;
   rc = join_grow_slots(h, S, own.keys_upper + (uint64_t)n);
   if (rc != RW_OK) return rc;
+  rc = join_clean_valid(h, st);
+  if (rc != RW_OK) return rc;
   JoinStatus* ds = h->status.as<JoinStatus>();
   const JoinPlanDev* pd = h->plan_dev.as<JoinPlanDev>();
-  RW_CUDA(cudaMemsetAsync(ds, 0, 16, st));  // out_rows, n_store
-  RW_CUDA(cudaMemsetAsync(h->out_hasnull.p, 0, sizeof(unsigned int) * (J_MAX_OUT + 1), st));
+  RW_CUDA(cudaMemsetAsync(ds, 0, 32, st));  // out_rows, n_store, n_del, null_mask
+  const uint32_t seq_base = (uint32_t)h->seq;
+  h->seq += (uint64_t)n;
   JoinStatus hs;
   if (h->fast_inner) {
-    rc = join_ensure_out(h, std::max<int64_t>(2 * n, 4096));
+    rc = join_ensure_out(h, std::max<int64_t>(2 * n, 4096), st);
     if (rc != RW_OK) return rc;
-    while (true) {
-      h->prof.begin(st);
-      join_inner_probe_emit_kernel<<<jgrid(n, JF_BLOCK), JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, 1 - S), out_dev(h), ds,
-                                                                             h->row_of.as<uint32_t>());
-      h->prof.end(st);
+    const int64_t tiles = (n + JF_BLOCK * JF_R - 1) / (JF_BLOCK * JF_R);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, 148 * 8));
+    h->prof.begin(st);
+    join_inner_fused_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
+                                                                (uint32_t)own.n_rows, seq_base);
+    h->prof.end(st);
+    join_inner_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, side_dev(h, S), ds, seq_base);
+    RW_CUDA(cudaGetLastError());
+    h->launches += 2;
+    rc = join_read_status(h, st, &hs);
+    if (rc != RW_OK) return rc;
+    const uint64_t stored = hs.n_store, keys = hs.n_keys[S];
+    unsigned int err = hs.err;
+    while (hs.err & JERR_OUT_CAPACITY) {
+      // the reservation overflowed: redo the (state-free) probe + emit with room for every row
+      const int64_t need = (int64_t)hs.out_rows;
+      RW_CUDA(cudaMemsetAsync(ds, 0, 32, st));
+      RW_CUDA(cudaMemsetAsync(&ds->err, 0, 4, st));
+      rc = join_ensure_out(h, need, st);
+      if (rc != RW_OK) return rc;
+      join_inner_fused_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds, 0, seq_base);
       RW_CUDA(cudaGetLastError());
       h->launches++;
       rc = join_read_status(h, st, &hs);
       if (rc != RW_OK) return rc;
-      if (!(hs.err & JERR_OUT_CAPACITY)) break;
-      // overflow: the probe kernel is read-only, re-run it with room for every reserved row
-      RW_CUDA(cudaMemsetAsync(ds, 0, 16, st));
-      RW_CUDA(cudaMemsetAsync(&ds->err, 0, 4, st));
-      RW_CUDA(cudaMemsetAsync(h->out_hasnull.p, 0, sizeof(unsigned int) * (J_MAX_OUT + 1), st));
-      rc = join_ensure_out(h, (int64_t)hs.out_rows);
-      if (rc != RW_OK) return rc;
+      err = (err & ~JERR_OUT_CAPACITY) | hs.err;
     }
-    const int64_t produced = (int64_t)hs.out_rows;
-    JoinSideDev od = side_dev(h, S);
-    size_t tb = h->cub_bytes;
-    cub::DeviceScan::ExclusiveSum(h->cub_tmp.p, tb, h->row_of.as<uint32_t>(), h->row_rev.as<uint32_t>(), (int)n, st);
-    join_inner_insert_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, od, ds, (uint32_t)own.n_rows, h->row_of.as<uint32_t>(),
-                                                            h->row_rev.as<uint32_t>());
-    join_inner_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, od, ds, (uint32_t)own.n_rows, h->row_rev.as<uint32_t>());
-    RW_CUDA(cudaGetLastError());
-    h->launches += 3;
-    rc = join_read_status(h, st, &hs);
-    if (rc != RW_OK) return rc;
-    own.n_rows += hs.n_store;
-    own.keys_upper = hs.n_keys[S];
+    own.n_rows += stored;
+    own.keys_upper = keys;
+    hs.err = err;
     rc = join_check_err(h, hs, st);
     if (rc != RW_OK) return rc;
-    *out_rows = produced;
+    *out_rows = (int64_t)hs.out_rows;
   } else {
+    rc = join_ensure_scratch(h, n);
+    if (rc != RW_OK) return rc;
     JoinScratch sc;
     sc.sortkey = h->sk.as<uint64_t>();
     sc.sortkey_alt = h->sk_alt.as<uint64_t>();
@@ -984,7 +1033,6 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     sc.offs = h->offs.as<uint64_t>();
     sc.match_slot = h->mslot.as<int64_t>();
     sc.gtable = h->gtable.as<int32_t>();
-    sc.gcap = h->gcap;
     uint64_t g = 1024;
     while (g < (uint64_t)n * 2) g <<= 1;
     sc.gcap = g;
@@ -1002,11 +1050,12 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     rc = join_read_status(h, st, &hs);
     if (rc != RW_OK) return rc;
     const int64_t reserved = (int64_t)hs.out_rows;
-    rc = join_ensure_out(h, reserved);
+    rc = join_ensure_out(h, reserved, st);
     if (rc != RW_OK) return rc;
+    if (reserved > 0) RW_CUDA(cudaMemsetAsync(h->out_vis.p, 1, (size_t)reserved, st));
     h->prof.begin(st);
     join_serial_kernel<<<jgrid(n, 128), 128, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), sc, db.Current(), out_dev(h), ds,
-                                                        (uint32_t)own.n_rows);
+                                                        (uint32_t)own.n_rows, seq_base);
     h->prof.end(st);
     RW_CUDA(cudaGetLastError());
     h->launches++;
@@ -1018,9 +1067,8 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     if (rc != RW_OK) return rc;
     *out_rows = reserved;
   }
-  RW_CUDA(cudaMemcpyAsync(h->status_host.as<uint8_t>() + 128, h->out_hasnull.p, sizeof(unsigned int) * (J_MAX_OUT + 1), cudaMemcpyDeviceToHost, st));
-  RW_CUDA(cudaStreamSynchronize(st));
-  memcpy(has_null_host, h->status_host.as<uint8_t>() + 128, sizeof(unsigned int) * (J_MAX_OUT + 1));
+  *null_mask = hs.null_mask;
+  h->valid_dirty = hs.null_mask & ((1ull << 63) - 1);
   return RW_OK;
 }
 
@@ -1045,14 +1093,19 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
     JoinSideHost& hs = h->side[s];
     hs.n_cols = sd[s]->n_cols;
     hs.types.assign(sd[s]->types, sd[s]->types + sd[s]->n_cols);
-    memset(hs.has_valid, 0, sizeof(hs.has_valid));
     p.n_cols[s] = sd[s]->n_cols;
+    int off = J_HDR;
     for (int c = 0; c < sd[s]->n_cols; c++) {
       int w = type_width(sd[s]->types[c]);
       if (!w) return fail(RW_ERR_UNSUPPORTED, "unsupported column type");
       p.col_type[s][c] = sd[s]->types[c];
       p.col_width[s][c] = w;
+      off = (off + w - 1) / w * w;  // natural alignment
+      p.col_off[s][c] = off;
+      off += w;
     }
+    p.stride[s] = (off + 15) / 16 * 16;
+    hs.stride = p.stride[s];
     for (int k = 0; k < d->n_keys; k++) {
       int c = sd[s]->key_indices[k];
       if (c < 0 || c >= sd[s]->n_cols) return fail(RW_ERR_INVALID, "join key index");
@@ -1083,14 +1136,13 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
   const bool need_r = (T == RW_JOIN_FULL_OUTER || T == RW_JOIN_RIGHT_OUTER || T == RW_JOIN_RIGHT_ANTI || T == RW_JOIN_RIGHT_SEMI);
   p.need_degree[0] = need_l && !pk_in_jk[1];  // :397
   p.need_degree[1] = need_r && !pk_in_jk[0];  // :398
-  h->side[0].need_degree = p.need_degree[0];
-  h->side[1].need_degree = p.need_degree[1];
   // output schema (:337-359) and i2o mappings (builder.rs:63-80)
   int left_len = d->left.n_cols, right_len = d->right.n_cols;
   std::vector<int> nat;
   if (T == RW_JOIN_LEFT_SEMI || T == RW_JOIN_LEFT_ANTI) { nat.assign(d->left.types, d->left.types + left_len); right_len = 0; }
   else if (T == RW_JOIN_RIGHT_SEMI || T == RW_JOIN_RIGHT_ANTI) { nat.assign(d->right.types, d->right.types + right_len); left_len = 0; }
   else { nat.assign(d->left.types, d->left.types + left_len); nat.insert(nat.end(), d->right.types, d->right.types + right_len); }
+  (void)right_len;
   if (d->n_output < 0 || d->n_output > J_MAX_OUT) return fail(RW_ERR_UNSUPPORTED, "too many output columns");
   p.n_out = d->n_output;
   for (int oi = 0; oi < d->n_output; oi++) {
@@ -1130,7 +1182,6 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
   RW_CUDA(h->status.reserve(sizeof(JoinStatus)));
   RW_CUDA(cudaMemsetAsync(h->status.p, 0, sizeof(JoinStatus), h->stream));
   RW_CUDA(h->status_host.reserve(1024));
-  RW_CUDA(h->out_hasnull.reserve(sizeof(unsigned int) * (J_MAX_OUT + 1)));
   for (int s = 0; s < 2; s++) {
     uint64_t hint = sd[s]->row_capacity_hint;
     uint64_t cap = 1024;
@@ -1161,8 +1212,8 @@ int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* c, r
   if (rc != RW_OK) return rc;
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
   int64_t n = 0;
-  unsigned int has_null[J_MAX_OUT + 1];
-  rc = join_push_dev(h, side, ch, st, &n, has_null);
+  unsigned long long nullm = 0;
+  rc = join_push_dev(h, side, ch, st, &n, &nullm);
   if (rc != RW_OK) return rc;
   h->dev_view_cols.resize(h->out_types.size());
   for (size_t k = 0; k < h->out_types.size(); k++) {
@@ -1171,7 +1222,7 @@ int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* c, r
     col.reserved = 0;
     col.data = h->out_col[k].p;
     col.validity = nullptr;
-    if (has_null[k] && n > 0) {
+    if (((nullm >> k) & 1) && n > 0) {
       pack_bytes_to_bits_kernel<<<jgrid((n + 63) / 64, 256), 256, 0, st>>>(h->out_valid[k].as<uint8_t>(), h->out_bits[k].as<uint64_t>(), n);
       RW_CUDA(cudaGetLastError());
       col.validity = h->out_bits[k].as<uint64_t>();
@@ -1182,7 +1233,7 @@ int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* c, r
   view->reserved = 0;
   view->ops = h->out_ops.as<uint8_t>();
   view->visibility = nullptr;
-  if (has_null[J_MAX_OUT] && n > 0) {
+  if ((nullm >> 63) && n > 0) {
     pack_bytes_to_bits_kernel<<<jgrid((n + 63) / 64, 256), 256, 0, st>>>(h->out_vis.as<uint8_t>(), h->out_visbits.as<uint64_t>(), n);
     RW_CUDA(cudaGetLastError());
     view->visibility = h->out_visbits.as<uint64_t>();
@@ -1197,9 +1248,11 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
   if (c->n_cols != h->side[side].n_cols) return fail(RW_ERR_INVALID, "chunk schema mismatch");
   for (int k = 0; k < c->n_cols; k++)
     if (c->columns[k].type != h->side[side].types[k]) return fail(RW_ERR_INVALID, "chunk column type mismatch");
-  // stage the chunk through pinned memory, one H2D copy
+  // small buffers are packed through one pinned staging block; large column buffers are copied
+  // straight from the caller's memory
   const int64_t n = c->n_rows;
   const size_t nw = (size_t)((n + 63) / 64) * 8;
+  const size_t DIRECT = 1 << 20;
   size_t total = 256 + (size_t)n + 256 + nw;
   for (int k = 0; k < c->n_cols; k++) total += 512 + (size_t)n * type_width(c->columns[k].type) + nw;
   RW_CUDA(h->up.reserve(total));
@@ -1210,7 +1263,8 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
   auto put = [&](const void* src, size_t bytes) -> const void* {
     if (!src) return nullptr;
     size_t o = align_up_j(off, 256);
-    memcpy(hp + o, src, bytes);
+    if (bytes >= DIRECT) cudaMemcpyAsync(dp + o, src, bytes, cudaMemcpyHostToDevice, h->stream);
+    else { memcpy(hp + o, src, bytes); cudaMemcpyAsync(dp + o, hp + o, bytes, cudaMemcpyHostToDevice, h->stream); }
     off = o + bytes;
     return dp + o;
   };
@@ -1227,35 +1281,29 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
     ch.cols[k].data = put(c->columns[k].data, (size_t)n * w);
     ch.cols[k].valid_bits = (const uint64_t*)put(c->columns[k].validity, nw);
   }
-  if (off) RW_CUDA(cudaMemcpyAsync(dp, hp, off, cudaMemcpyHostToDevice, h->stream));
+  RW_CUDA(cudaGetLastError());
   int64_t rows = 0;
-  unsigned int has_null[J_MAX_OUT + 1];
-  int rc = join_push_dev(h, side, ch, h->stream, &rows, has_null);
+  unsigned long long nullm = 0;
+  int rc = join_push_dev(h, side, ch, h->stream, &rows, &nullm);
   if (rc != RW_OK) return rc;
   auto o = new rwgpu_out();
-  o->n_rows = rows;
   o->chunk_size = h->chunk_size;
-  o->types = h->out_types;
-  o->ops.resize((size_t)rows);
-  o->data.resize(h->out_types.size());
-  o->valid_bytes.resize(h->out_types.size());
+  if (!o->layout(rows, h->out_types, nullm & ((1ull << 63) - 1), (nullm >> 63) != 0, h->pool)) {
+    delete o;
+    return fail(RW_ERR_OOM, "pinned output block");
+  }
   if (rows > 0) {
-    cudaMemcpyAsync(o->ops.data(), h->out_ops.p, (size_t)rows, cudaMemcpyDeviceToHost, h->stream);
-    if (has_null[J_MAX_OUT]) {
-      o->vis_bytes.resize((size_t)rows);
-      cudaMemcpyAsync(o->vis_bytes.data(), h->out_vis.p, (size_t)rows, cudaMemcpyDeviceToHost, h->stream);
-    }
+    cudaMemcpyAsync(o->ops, h->out_ops.p, (size_t)rows, cudaMemcpyDeviceToHost, h->stream);
+    if (o->vis_bytes) cudaMemcpyAsync(o->vis_bytes, h->out_vis.p, (size_t)rows, cudaMemcpyDeviceToHost, h->stream);
     for (size_t k = 0; k < h->out_types.size(); k++) {
       size_t w = type_width(h->out_types[k]);
-      o->data[k].resize((size_t)rows * w);
-      cudaMemcpyAsync(o->data[k].data(), h->out_col[k].p, (size_t)rows * w, cudaMemcpyDeviceToHost, h->stream);
-      if (has_null[k]) {
-        o->valid_bytes[k].resize((size_t)rows);
-        cudaMemcpyAsync(o->valid_bytes[k].data(), h->out_valid[k].p, (size_t)rows, cudaMemcpyDeviceToHost, h->stream);
-      }
+      cudaMemcpyAsync(o->data[k], h->out_col[k].p, (size_t)rows * w, cudaMemcpyDeviceToHost, h->stream);
+      if (o->valid_bytes[k]) cudaMemcpyAsync(o->valid_bytes[k], h->out_valid[k].p, (size_t)rows, cudaMemcpyDeviceToHost, h->stream);
     }
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) { delete o; return fail(RW_ERR_CUDA, cudaGetErrorString(e)); }
+  } else {
+    RW_CUDA(cudaStreamSynchronize(h->stream));  // the staging block is reused by the next call
   }
   o->finalize();
   *out = o;
@@ -1283,9 +1331,7 @@ int32_t rwgpu_join_profile(rwgpu_join* h, int32_t enable, double* ms, uint64_t* 
 
 int32_t rwgpu_join_stats(rwgpu_join* h, uint64_t* left_rows, uint64_t* right_rows, uint64_t* launches) {
   if (!h) return fail(RW_ERR_INVALID, "null");
-  JoinStatus s;
   RW_CUDA(cudaStreamSynchronize(h->stream));
-  RW_CUDA(cudaMemcpy(&s, h->status.p, sizeof(s), cudaMemcpyDeviceToHost));
   if (left_rows) *left_rows = h->side[0].n_rows;
   if (right_rows) *right_rows = h->side[1].n_rows;
   if (launches) *launches = h->launches;
