@@ -241,10 +241,12 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     be = Backend.cuda()
     K, W = args.steps, args.warmup
+    legs = set(args.legs.split(","))
     T4 = [abi.T_INT64] * 4
     stream = torch.cuda.Stream()
+    peak, which = measured_peak_hbm()
 
-    def new_join(hint_l, hint_r):
+    def new_join():
         _, sl = MockSource.channel()
         _, sr = MockSource.channel()
         # left = bid (key col 0, stream key date_time), right = auction (key col 0 = id = stream key)
@@ -262,8 +264,7 @@ def run_ours(args):
     id_base = rank * N_BUILD
     auct = gen_auctions(N_BUILD, SEED + rank * 1000, id_base)
     # bids of rank r reference auctions of ALL ranks (so the shuffle really moves rows)
-    n_auction_total = N_BUILD * world
-    batches_host = [gen_bids(BATCH, (rank * (K + W) + s) * BATCH, SEED, n_auction_total) for s in range(K + W)]
+    batches_host = [gen_bids(BATCH, (rank * (K + W) + s) * BATCH, SEED, N_BUILD * world) for s in range(K + W)]
 
     if world > 1:
         from risingwave_b200 import exchange
@@ -275,69 +276,86 @@ def run_ours(args):
         ops, cols = ex_plan.exchange(dchunk(cols_dev), stream)
         return device.DeviceChunk(ops, cols, T4)
 
+    line = {}
     with torch.cuda.stream(stream):
-        # ---------------- build side (untimed; reported separately)
-        join = new_join(0, 0)
         auct_dev = to_dev(auct)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(0, N_BUILD, BATCH):
-            device.join_push_device(join, abi.SIDE_RIGHT, shuffled([c[i:i + BATCH] for c in auct_dev]), stream)
-        torch.cuda.synchronize()
-        build_s = time.perf_counter() - t0
-        batches_dev = [to_dev(b) for b in batches_host]
-        torch.cuda.synchronize()
 
-        def step(s):
-            return device.join_push_device(join, abi.SIDE_LEFT, shuffled(batches_dev[s]), stream)
-
-        for s in range(W):
-            step(s)
-        device.profile(join, "join", True)
-        l0 = device.launches(join, "join")
-        sampler = ClockSampler(local_rank)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        if rank == 0:
-            sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        out_rows = 0
-        for s in range(W, W + K):
-            out_rows += step(s).n_rows
-        e1.record(stream)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if rank == 0 else None
-        kern_ms, kern_n = device.profile(join, "join", False)
-        launches = device.launches(join, "join") - l0
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            orow = torch.tensor([out_rows], device="cuda", dtype=torch.int64)
-            dist.all_reduce(orow)
-            out_rows = int(orow.item())
-        rows_total = K * BATCH * world
-        value = rows_total / (ms / 1e3)
-
-        # ---------------- e2e: host buffers through rwgpu_join_push (rank-local; N=1 only)
-        e2e = None
-        secondary = None
-        if world == 1 and not args.only_value:
-            del join
-            torch.cuda.empty_cache()
-            join2 = new_join(0, 0)
-            for i in range(0, N_BUILD, BATCH):
-                device.join_push_device(join2, abi.SIDE_RIGHT, dchunk([c[i:i + BATCH] for c in auct_dev]), stream)
+        def build(join, shuffle=True):
             torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(0, N_BUILD, BATCH):
+                part = [c[i:i + BATCH] for c in auct_dev]
+                device.join_push_device(join, abi.SIDE_RIGHT, shuffled(part) if shuffle else dchunk(part), stream)
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0
+
+        # ================================================================ leg: value (device-resident)
+        if "value" in legs:
+            join = new_join()
+            build_s = build(join)
+            batches_dev = [to_dev(b) for b in batches_host]
+            torch.cuda.synchronize()
+
+            def step(s):
+                return device.join_push_device(join, abi.SIDE_LEFT, shuffled(batches_dev[s]), stream)
+
+            for s in range(W):
+                step(s)
+            device.profile(join, "join", True)
+            l0 = device.launches(join, "join")
+            sampler = ClockSampler(local_rank)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            if rank == 0:
+                sampler.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            out_rows = 0
+            for s in range(W, W + K):
+                out_rows += step(s).n_rows
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ms = e0.elapsed_time(e1)
+            clocks = sampler.stop() if rank == 0 else None
+            kern_ms, kern_n = device.profile(join, "join", False)
+            launches = device.launches(join, "join") - l0
+            if world > 1:
+                t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+                orow = torch.tensor([out_rows], device="cuda", dtype=torch.int64)
+                dist.all_reduce(orow)
+                out_rows = int(orow.item())
+            rows_total = K * BATCH * world
+            fused_gbs = JOIN_BYTES_PER_ROW_STEP * BATCH * kern_n / (kern_ms / 1e3) / 1e9 if kern_ms else None
+            line.update({
+                "metric": "Nexmark q7/q8-shaped streaming HashJoin input rows/s", "value": rows_total / (ms / 1e3), "unit": "rows/s",
+                "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                "config": {"workload": "nexmark_q7q8_hashjoin_cfg3" if world == 1 else "nexmark_q8_shuffled_hashjoin_cfg4",
+                           "build_rows_per_gpu": N_BUILD, "probe_rows_per_step_per_gpu": BATCH, "chunk_rows": CHUNK,
+                           "chunks_coalesced_per_launch": BATCH // CHUNK,
+                           "join": "inner bid.auction = auction.id, Key64, 4+4 int64 cols, 8 out cols",
+                           "l2": "inputs_larger_than_l2 (fresh 32 MiB batch per step; >1.3 GB of join state)",
+                           "exchange": None if world == 1 else "crc32 vnode partition kernel + NCCL all_to_all_single per column"},
+                "build_rows_per_s": N_BUILD * world / build_s, "out_rows": out_rows, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": {"bound": "hbm", "kernel": "join_inner_fused_kernel<false> (probe + emit + own-side append)",
+                             "achieved": fused_gbs, "peak": peak, "unit": "GB/s", "frac": fused_gbs / peak if fused_gbs else None,
+                             "traffic": None, "peak_source": which, "algorithmic_bytes_per_row": JOIN_BYTES_PER_ROW_STEP,
+                             "rows_per_launch": BATCH, "kernel_ms_avg": kern_ms / max(kern_n, 1),
+                             "kernel_share_of_step": kern_ms / ms if ms else None}})
+            del join, batches_dev
+            torch.cuda.empty_cache()
+
+        # ================================================================ leg: e2e (host buffers, C ABI)
+        if "e2e" in legs and world == 1:
+            join2 = new_join()
+            build(join2, shuffle=False)
             FFI_ROWS = 1 << 18  # 256 coalesced 1024-row chunks per C-ABI call
             ones_pinned = torch.ones(FFI_ROWS, dtype=torch.uint8).pin_memory().numpy()
-
-            lib = be.lib
             chunks_host = []
             for s in range(W + K):
                 for i in range(0, BATCH, FFI_ROWS):
@@ -348,7 +366,7 @@ def run_ours(args):
             per_step = BATCH // FFI_ROWS
 
             def host_step(s):
-                """the call a Rust shim makes: rwgpu_join_push(host chunk) -> out; walk the chunk views; release"""
+                """the calls a Rust shim makes: rwgpu_join_push(host chunk) -> out; walk the chunk views; release"""
                 tot = 0
                 view = abi.RwChunk()
                 for j in range(per_step):
@@ -358,25 +376,25 @@ def run_ours(args):
                         be._out_chunk(out, i, C.byref(view))
                         tot += view.n_rows
                     be._out_release(out)
-                return tot, tot * (8 * 8 + 1)
+                return tot
 
             for s in range(W):
                 host_step(s)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            d2h = 0
+            tot = 0
             for s in range(W, W + K):
-                tot, b = host_step(s)
-                d2h += b
+                tot += host_step(s)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            e2e = {"value": K * BATCH / dt, "unit": "rows/s", "h2d_bytes_per_step": BATCH * (4 * 8 + 1),
-                   "d2h_bytes_per_step": d2h // K, "ffi_batch_rows": FFI_ROWS, "ms_per_step": dt / K * 1e3,
-                   "note": "host numpy buffers -> rwgpu_join_push -> host output chunk views (C ABI called through ctypes)"}
-            del join2
+            line["e2e"] = {"value": K * BATCH / dt, "unit": "rows/s", "h2d_bytes_per_step": BATCH * (4 * 8 + 1),
+                           "d2h_bytes_per_step": tot * (8 * 8 + 1) // K, "ffi_batch_rows": FFI_ROWS, "ms_per_step": dt / K * 1e3,
+                           "note": "pinned host StreamChunk buffers -> rwgpu_join_push -> pinned host output chunk views (C ABI via ctypes)"}
+            del join2, chunks_host
             torch.cuda.empty_cache()
 
-            # ---------------- secondary: q4-shaped HashAgg (configs[1])
+        # ================================================================ leg: agg (secondary, configs[1])
+        if "agg" in legs and world == 1:
             _, src = MockSource.channel()
             agg = HashAggExecutor(be, src.into_executor([abi.T_INT64] * 2, []), True,
                                   [AggCall.from_pretty(c) for c in ("(count:int8)", "(sum:int8 $1:int8)", "(max:int8 $1:int8)")],
@@ -402,48 +420,20 @@ def run_ours(args):
             torch.cuda.synchronize()
             ams = a0.elapsed_time(a1)
             akern_ms, akern_n = device.profile(agg, "agg", False)
-            d = delta_rows / 2 / (n_ep * AGG_EPOCH_ROWS)  # dirty groups per input row (U-/U+ pairs dominate)
-            peak, which = measured_peak_hbm()
-            agg_bytes_row = AGG_BYTES_PER_ROW_FLOOR
-            secondary = {"workload": "nexmark_q4_hashagg_cfg2: count(*),sum,max GROUP BY auction; 2^20 keys uniform; "
-                                     "2^18-row epochs (256 chunks x 1024)",
-                         "metric": "rows/s", "value": n_ep * AGG_EPOCH_ROWS / (ams / 1e3), "epochs": n_ep,
-                         "delta_rows_per_input_row": delta_rows / (n_ep * AGG_EPOCH_ROWS),
-                         "roofline": {"bound": "hbm", "kernel": "agg_apply_fast_kernel<3>",
-                                      "achieved": agg_bytes_row * AGG_EPOCH_ROWS * akern_n / (akern_ms / 1e3) / 1e9 if akern_ms else None,
-                                      "peak": peak, "unit": "GB/s",
-                                      "frac": (agg_bytes_row * AGG_EPOCH_ROWS * akern_n / (akern_ms / 1e3) / 1e9 / peak) if akern_ms else None,
-                                      "traffic": None, "peak_source": which,
-                                      "algorithmic_bytes_per_row": agg_bytes_row, "kernel_ms_avg": akern_ms / max(akern_n, 1)}}
+            agbs = AGG_BYTES_PER_ROW_FLOOR * AGG_EPOCH_ROWS * akern_n / (akern_ms / 1e3) / 1e9 if akern_ms else None
+            line["secondary"] = {
+                "workload": "nexmark_q4_hashagg_cfg2: count(*),sum,max GROUP BY auction; 2^20 keys uniform; 2^18-row epochs (256 chunks x 1024)",
+                "metric": "rows/s", "value": n_ep * AGG_EPOCH_ROWS / (ams / 1e3), "epochs": n_ep, "ms_per_epoch": ams / n_ep,
+                "delta_rows_per_input_row": delta_rows / (n_ep * AGG_EPOCH_ROWS),
+                "roofline": {"bound": "hbm", "kernel": "agg_apply_fast_kernel<3>", "achieved": agbs, "peak": peak, "unit": "GB/s",
+                             "frac": agbs / peak if agbs else None, "traffic": None, "peak_source": which,
+                             "algorithmic_bytes_per_row": AGG_BYTES_PER_ROW_FLOOR, "kernel_ms_avg": akern_ms / max(akern_n, 1)}}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peak, which = measured_peak_hbm()
-    probe_gbs = JOIN_BYTES_PER_ROW_PROBE * BATCH * kern_n / (kern_ms / 1e3) / 1e9 if kern_ms else None
-    line = {
-        "metric": "Nexmark q7/q8-shaped streaming HashJoin input rows/s", "value": value, "unit": "rows/s",
-        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "nexmark_q7q8_hashjoin_cfg3" if world == 1 else "nexmark_q8_shuffled_hashjoin_cfg4",
-                   "build_rows_per_gpu": N_BUILD, "probe_rows_per_step_per_gpu": BATCH, "chunk_rows": CHUNK,
-                   "chunks_coalesced_per_launch": BATCH // CHUNK, "join": "inner bid.auction = auction.id, Key64, 4+4 int64 cols, 8 out cols",
-                   "l2": "inputs_larger_than_l2 (fresh 32 MiB batch per step; 1.3 GB state)",
-                   "exchange": None if world == 1 else "crc32 vnode partition kernel + NCCL all_to_all_single per column"},
-        "build_rows_per_s": N_BUILD * world / build_s,
-        "out_rows": out_rows,
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "join_inner_probe_emit_kernel", "achieved": probe_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": probe_gbs / peak if probe_gbs else None, "traffic": None, "peak_source": which,
-                     "algorithmic_bytes_per_row": JOIN_BYTES_PER_ROW_PROBE, "kernel_ms_avg": kern_ms / max(kern_n, 1),
-                     "kernel_share_of_step": kern_ms / ms if ms else None,
-                     "whole_step_GBps": JOIN_BYTES_PER_ROW_STEP * BATCH * K * world / (ms / 1e3) / 1e9},
-        "e2e": e2e,
-        "secondary": secondary,
-    }
-    if world == 1 and not args.no_cpu:
+    if "cpu" in legs and world == 1:
         cores = os.cpu_count() or 1
         nb = 5
         sample = [gen_bids(1 << 20, s << 20, SEED, N_BUILD) for s in range(nb)]
@@ -488,8 +478,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--only-value", action="store_true", help="device-resident leg only (for ncu runs)")
+    ap.add_argument("--legs", default="value,e2e,agg,cpu", help="comma list of: value,e2e,agg,cpu (subset for ncu runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
