@@ -1,4 +1,6 @@
 // api.cu -- host-only parts of the C ABI: errors, type table, output object, misc.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rw {
@@ -134,6 +136,19 @@ int32_t rwgpu_device_check(void) {
   if (e != cudaSuccess || n <= 0) {
     cudaGetLastError();
     return rw::fail(RW_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  }
+  // The hot kernels are random 16-48 byte gathers / atomics into multi-GB hash tables: ask L2 to
+  // fetch single 32 B sectors from HBM instead of the default 64 B pairs (halves the DRAM read
+  // traffic of a miss that only needs one sector).  RWGPU_L2_FETCH=64|128 restores / widens it.
+  static thread_local int applied_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (applied_dev != dev) {
+    size_t g = 32;
+    if (const char* v = getenv("RWGPU_L2_FETCH")) g = (size_t)atoi(v);
+    if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
+    cudaGetLastError();
+    applied_dev = dev;
   }
   return RW_OK;
 }
