@@ -31,7 +31,7 @@ struct AggStatus {
   unsigned long long out_rows;
   unsigned long long n_groups;
   unsigned int err;
-  unsigned int pad;
+  unsigned int n_dirty;  // entries of the dirty list
 };
 
 struct AggPlanDev {
@@ -54,10 +54,28 @@ struct AggPlanDev {
 struct AggTable {
   uint64_t* hot;
   uint64_t* cold;
-  uint32_t* dirty;
+  uint32_t* dirty;       // first-touch filter: one bit per slot
+  uint32_t* dirty_list;  // slots touched since the last barrier (each exactly once)
   AggStatus* status;
   uint64_t cap;  // power of two
 };
+
+// mark `slot` dirty; the thread that flips the bit appends the slot to the dirty list
+// (opportunistic warp aggregation: one atomicAdd per group of converged first-touchers)
+__device__ __forceinline__ void mark_dirty(const AggTable& t, uint64_t slot) {
+  const uint32_t bit = 1u << (slot & 31);
+  uint32_t* dw = t.dirty + (slot >> 5);
+  if (__ldcg(dw) & bit) return;
+  const uint32_t old = atomicOr(dw, bit);
+  if (old & bit) return;
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  unsigned int base = 0;
+  if (lane == leader) base = atomicAdd(&t.status->n_dirty, (unsigned int)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  t.dirty_list[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)slot;
+}
 
 struct AggOutDev {
   uint8_t* ops;
@@ -215,9 +233,7 @@ __global__ void __launch_bounds__(256) agg_apply_kernel(AggTable t, AggPlanDev p
       slot = find_or_insert_multi(t, p, kw, nm, &created);
     }
     if (created) created_local++;
-    uint32_t bit = 1u << (slot & 31);
-    uint32_t* dw = t.dirty + (slot >> 5);
-    if (!(__ldcg(dw) & bit)) atomicOr(dw, bit);
+    mark_dirty(t, slot);
     agg_apply_row(t, p, ch, r, op, slot, per_row_flags);
   }
   // warp-aggregated group counter
@@ -265,9 +281,7 @@ __global__ void __launch_bounds__(256) agg_apply_fast_kernel(AggTable t, AggPlan
       bool created = false;
       uint64_t slot = ((uint64_t)k[j] == AGG_EMPTY) ? t.cap + 1 : find_or_insert_single(t, p.HW, (uint64_t)k[j], &created);
       if (created) created_local++;
-      uint32_t bit = 1u << (slot & 31);
-      uint32_t* dw = t.dirty + (slot >> 5);
-      if (!(__ldcg(dw) & bit)) atomicOr(dw, bit);
+      mark_dirty(t, slot);
       unsigned long long* sp = (unsigned long long*)(t.hot + slot * p.HW + 1);
       const bool retract = (op[j] == RW_OP_DELETE || op[j] == RW_OP_UPDATE_DELETE);
 #pragma unroll
@@ -298,16 +312,9 @@ __global__ void __launch_bounds__(256) agg_apply_fast_kernel(AggTable t, AggPlan
 // (used when every push of the epoch had NULL-free argument columns: then every visible row
 // contributed a non-NULL value to every call, so the per-row flag update can be elided)
 __global__ void agg_set_flags_kernel(AggTable t, AggPlanDev p, uint32_t mask) {
-  uint64_t nwords = (t.cap + 2 + 31) >> 5;
-  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < nwords; w += (uint64_t)gridDim.x * blockDim.x) {
-    uint32_t bits = t.dirty[w];
-    while (bits) {
-      int b = __ffs(bits) - 1;
-      bits &= bits - 1;
-      uint64_t slot = (w << 5) + b;
-      t.cold[slot * p.CW] |= (uint64_t)mask;
-    }
-  }
+  const unsigned int n = t.status->n_dirty;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    t.cold[(uint64_t)t.dirty_list[i] * p.CW] |= (uint64_t)mask;
 }
 
 // ------------------------------------------------------------------ flush: change inference + compaction
@@ -316,33 +323,76 @@ struct OutVal {
   bool null;
 };
 
+// current output of call c from its state (value-state get_output; agg_group.rs:431-468)
+__device__ __forceinline__ OutVal call_output(const AggTable& t, const AggPlanDev& p, int c, const uint64_t* hot,
+                                               const uint64_t* cold, uint64_t flags) {
+  const int kind = p.kind[c];
+  const int at = p.arg_type[c];
+  const bool isf = (at == RW_T_FLOAT32 || at == RW_T_FLOAT64);
+  const uint64_t s = hot[p.KW + c];
+  OutVal v;
+  v.hi = 0;
+  v.lo = 0;
+  v.null = false;
+  if (kind == RW_AGG_COUNT) {
+    v.lo = s;
+  } else if (!((flags >> c) & 1)) {
+    v.null = (kind != RW_AGG_SUM0);  // sum0: init_state = 0; others NULL until a non-NULL input
+  } else if (kind == RW_AGG_SUM || kind == RW_AGG_SUM0) {
+    if (isf) {
+      v.lo = s;
+      if (p.ret_type[c] == RW_T_FLOAT32) {  // sum(float4) -> float4
+        float f = (float)__longlong_as_double((long long)s);
+        v.lo = (uint64_t)__double_as_longlong((double)f);
+      }
+    } else {
+      const long long hi = (p.hi_off[c] >= 0) ? (long long)cold[p.hi_off[c]] : (((long long)s) >> 63);
+      v.lo = s;
+      v.hi = (uint64_t)hi;
+      if (p.ret_type[c] == RW_T_DECIMAL) {  // rust_decimal: 96-bit mantissa
+        const bool ok = (hi >= 0) ? (hi < (1ll << 32)) : (hi > -(1ll << 32) || (hi == -(1ll << 32) && s != 0));
+        if (!ok) atomicOr(&t.status->err, AGG_ERR_OVERFLOW);
+      } else if (hi != (((long long)s) >> 63)) {
+        atomicOr(&t.status->err, AGG_ERR_OVERFLOW);
+      }
+    }
+  } else {  // min / max
+    v.lo = isf ? (uint64_t)__double_as_longlong(f64_unsortable((int64_t)s)) : s;
+  }
+  return v;
+}
+
+__device__ __forceinline__ void write_out_val(const AggOutDev& o, const AggPlanDev& p, int c, int64_t rr, const OutVal& v) {
+  const int oc = p.n_keys + c;
+  o.valid[oc][rr] = v.null ? 0 : 1;
+  if (v.null) o.has_null[oc] = 1;
+  if (p.ret_type[c] == RW_T_DECIMAL) {
+    ((uint64_t*)o.col[oc])[rr * 2] = v.lo;
+    ((uint64_t*)o.col[oc])[rr * 2 + 1] = v.hi;
+  } else {
+    store_word(o.col[oc], type_width_dev(p.ret_type[c]), p.ret_type[c], rr, v.lo);
+  }
+}
+
+// one thread per dirty group (the dirty LIST keeps every lane busy however sparse the epoch's
+// touched set is); the 0 / 1 / 2 output rows of a warp are compacted with a shuffle scan and one
+// atomicAdd, so a U-/U+ pair stays adjacent.
 __global__ void __launch_bounds__(256) agg_flush_kernel(AggTable t, AggPlanDev p, AggOutDev o, uint32_t epoch_flag_mask) {
-  const uint64_t nwords = (t.cap + 2 + 31) >> 5;
-  const uint64_t warps_total = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned int n_dirty = t.status->n_dirty;
   const int lane = lane_id();
-  for (uint64_t w = warp0; w < nwords; w += warps_total) {
-    uint32_t bits = t.dirty[w];
-    if (bits == 0) continue;  // warp-uniform
-    const uint64_t slot = (w << 5) + lane;
-    const bool active = (bits >> lane) & 1;
+  const unsigned int n_round = (n_dirty + 31u) & ~31u;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const bool active = i < n_dirty;
     int nrows = 0;
     uint8_t op0 = 0, op1 = 0;
-    OutVal prev[RW_MAX_CALLS], curr[RW_MAX_CALLS];
-    uint64_t keyw[RW_MAX_KEYS];
-    uint32_t key_nm = 0;
+    uint64_t slot = 0;
+    uint64_t flags = 0;
+    bool store_prev = false;
     if (active) {
+      slot = t.dirty_list[i];
       uint64_t* hot = t.hot + slot * p.HW;
       uint64_t* cold = t.cold + slot * p.CW;
-      uint64_t flags = cold[0] | (uint64_t)epoch_flag_mask;
-      // group key
-      if (p.single_key) {
-        if (slot == t.cap) { key_nm = 1; keyw[0] = 0; }
-        else keyw[0] = (slot == t.cap + 1) ? AGG_EMPTY : hot[0];
-      } else {
-        key_nm = (uint32_t)((hot[0] >> 8) & 0xff);
-        for (int k = 0; k < p.n_keys; k++) keyw[k] = hot[1 + k];
-      }
+      flags = cold[0] | (uint64_t)epoch_flag_mask;
       // row_count_of (agg_group.rs:55-79)
       long long rc = (long long)hot[p.KW + p.row_count_call];
       if (rc < 0) {
@@ -359,83 +409,30 @@ __global__ void __launch_bounds__(256) agg_flush_kernel(AggTable t, AggPlanDev p
       const bool has_prev = (flags & COLD_HAS_PREV) != 0;
       const uint32_t prev_nm = (uint32_t)((flags >> 16) & 0xFFFF);
       long long prev_rc = 0;
-      uint32_t curr_nm = 0;
       bool same = true;
-      for (int c = 0; c < p.n_calls; c++) {
-        const int kind = p.kind[c];
-        const int at = p.arg_type[c];
-        const bool isf = (at == RW_T_FLOAT32 || at == RW_T_FLOAT64);
-        uint64_t s = hot[p.KW + c];
-        OutVal v;
-        v.hi = 0;
-        v.null = false;
-        if (kind == RW_AGG_COUNT) {
-          v.lo = (rc == 0 && c == p.row_count_call) ? 0 : s;
-        } else if (kind == RW_AGG_SUM0 && !((flags >> c) & 1)) {
-          v.lo = 0;  // init_state = 0
-        } else if (!((flags >> c) & 1)) {
-          v.null = true; v.lo = 0;
-        } else if (kind == RW_AGG_SUM || kind == RW_AGG_SUM0) {
-          if (isf) {
-            v.lo = s;
-            if (p.ret_type[c] == RW_T_FLOAT32) {  // sum(float4) -> float4
-              float f = (float)__longlong_as_double((long long)s);
-              v.lo = (uint64_t)__double_as_longlong((double)f);
-            }
-          } else {
-            long long hi = (p.hi_off[c] >= 0) ? (long long)cold[p.hi_off[c]] : (((long long)s) >> 63);
-            v.lo = s;
-            v.hi = (uint64_t)hi;
-            if (p.ret_type[c] == RW_T_DECIMAL) {
-              // rust_decimal: 96-bit mantissa
-              bool ok = (hi >= 0) ? (hi < (1ll << 32)) : (hi > -(1ll << 32) || (hi == -(1ll << 32) && s != 0));
-              if (!ok) atomicOr(&t.status->err, AGG_ERR_OVERFLOW);
-            } else {
-              if (hi != (((long long)s) >> 63)) atomicOr(&t.status->err, AGG_ERR_OVERFLOW);
-            }
-          }
-        } else {  // min / max
-          v.lo = isf ? (uint64_t)__double_as_longlong(f64_unsortable((int64_t)s)) : s;
-          if (isf && p.ret_type[c] == RW_T_FLOAT32) { /* value is an exact f32 already */ }
-        }
-        if (v.null) curr_nm |= 1u << c;
-        curr[c] = v;
-        OutVal pv;
-        pv.lo = cold[1 + c];
-        pv.hi = (p.prevhi_off[c] >= 0) ? cold[p.prevhi_off[c]] : 0;
-        pv.null = (prev_nm >> c) & 1;
-        prev[c] = pv;
-        if (has_prev) {
-          bool eq = (pv.null == v.null) && (v.null || (pv.lo == v.lo && (p.prevhi_off[c] < 0 || pv.hi == v.hi)));
-          if (!eq && !v.null && !pv.null && (p.ret_type[c] == RW_T_FLOAT32 || p.ret_type[c] == RW_T_FLOAT64)) {
+      if (has_prev) {
+        prev_rc = (long long)cold[1 + p.row_count_call];
+        if (prev_rc < 0) prev_rc = 0;
+        for (int c = 0; c < p.n_calls; c++) {
+          const OutVal v = call_output(t, p, c, hot, cold, flags);
+          const bool pnull = (prev_nm >> c) & 1;
+          const uint64_t plo = cold[1 + c];
+          bool eq = (pnull == v.null) && (v.null || (plo == v.lo && (p.prevhi_off[c] < 0 || cold[p.prevhi_off[c]] == v.hi)));
+          if (!eq && !v.null && !pnull && (p.ret_type[c] == RW_T_FLOAT32 || p.ret_type[c] == RW_T_FLOAT64)) {
             // OrderedFloat equality: NaN == NaN, -0 == +0
-            double a = __longlong_as_double((long long)pv.lo), b = __longlong_as_double((long long)v.lo);
+            const double a = __longlong_as_double((long long)plo), b = __longlong_as_double((long long)v.lo);
             eq = (a != a && b != b) || (a == b);
           }
           same = same && eq;
         }
-      }
-      if (has_prev) {
-        prev_rc = (long long)cold[1 + p.row_count_call];
-        if (prev_rc < 0) prev_rc = 0;
+      } else {
+        for (int c = 0; c < p.n_calls; c++) (void)call_output(t, p, c, hot, cold, flags);  // overflow checks
       }
       // OnlyOutputIfHasInput::infer_change_type (agg_group.rs:131-166)
-      bool store_prev = false, clear_prev = false;
       if (prev_rc == 0 && rc == 0) { nrows = 0; }
       else if (prev_rc == 0) { nrows = 1; op0 = RW_OP_INSERT; store_prev = true; }
-      else if (rc == 0) { nrows = 1; op0 = RW_OP_DELETE; clear_prev = true; }
+      else if (rc == 0) { nrows = 1; op0 = RW_OP_DELETE; }
       else if (!same) { nrows = 2; op0 = RW_OP_UPDATE_DELETE; op1 = RW_OP_UPDATE_INSERT; store_prev = true; }
-      uint64_t nf = flags;
-      if (store_prev) {
-        for (int c = 0; c < p.n_calls; c++) {
-          cold[1 + c] = curr[c].lo;
-          if (p.prevhi_off[c] >= 0) cold[p.prevhi_off[c]] = curr[c].hi;
-        }
-        nf = (nf & ~(0xFFFFull << 16)) | ((uint64_t)curr_nm << 16) | COLD_HAS_PREV;
-      } else if (clear_prev) {
-        nf &= ~(COLD_HAS_PREV | (0xFFFFull << 16));
-      }
-      cold[0] = nf;
     }
     // warp-scan compaction of the emitted rows
     int incl = nrows;
@@ -443,41 +440,69 @@ __global__ void __launch_bounds__(256) agg_flush_kernel(AggTable t, AggPlanDev p
       int v = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += v;
     }
-    int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
     unsigned long long base = 0;
     if (lane == 0 && total) base = atomicAdd(&t.status->out_rows, (unsigned long long)total);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (nrows) {
-      int64_t row = (int64_t)base + (incl - nrows);
-      if (row + nrows > o.capacity) {
+    if (active) {
+      uint64_t* hot = t.hot + slot * p.HW;
+      uint64_t* cold = t.cold + slot * p.CW;
+      const int64_t row = (int64_t)base + (incl - nrows);
+      if (nrows && row + nrows > o.capacity) {
         atomicOr(&t.status->err, AGG_ERR_OUT_CAPACITY);
-      } else {
+      } else if (nrows) {
+        // group key
+        uint64_t keyw[RW_MAX_KEYS];
+        uint32_t key_nm = 0;
+        if (p.single_key) {
+          if (slot == t.cap) { key_nm = 1; keyw[0] = 0; }
+          else keyw[0] = (slot == t.cap + 1) ? AGG_EMPTY : hot[0];
+        } else {
+          key_nm = (uint32_t)((hot[0] >> 8) & 0xff);
+          for (int k = 0; k < p.n_keys; k++) keyw[k] = hot[1 + k];
+        }
+        const uint32_t prev_nm = (uint32_t)((flags >> 16) & 0xFFFF);
         for (int j = 0; j < nrows; j++) {
           const uint8_t op = j == 0 ? op0 : op1;
-          const OutVal* vals = (op == RW_OP_DELETE || op == RW_OP_UPDATE_DELETE) ? prev : curr;
+          const bool use_prev = (op == RW_OP_DELETE || op == RW_OP_UPDATE_DELETE);
           const int64_t rr = row + j;
           o.ops[rr] = op;
           for (int k = 0; k < p.n_keys; k++) {
-            bool nul = (key_nm >> k) & 1;
+            const bool nul = (key_nm >> k) & 1;
             o.valid[k][rr] = nul ? 0 : 1;
             if (nul) o.has_null[k] = 1;
             store_word(o.col[k], type_width_dev(p.key_type[k]), p.key_type[k], rr, keyw[k]);
           }
           for (int c = 0; c < p.n_calls; c++) {
-            const int oc = p.n_keys + c;
-            o.valid[oc][rr] = vals[c].null ? 0 : 1;
-            if (vals[c].null) o.has_null[oc] = 1;
-            if (p.ret_type[c] == RW_T_DECIMAL) {
-              ((uint64_t*)o.col[oc])[rr * 2] = vals[c].lo;
-              ((uint64_t*)o.col[oc])[rr * 2 + 1] = vals[c].hi;
+            OutVal v;
+            if (use_prev) {
+              v.lo = cold[1 + c];
+              v.hi = (p.prevhi_off[c] >= 0) ? cold[p.prevhi_off[c]] : 0;
+              v.null = (prev_nm >> c) & 1;
             } else {
-              store_word(o.col[oc], type_width_dev(p.ret_type[c]), p.ret_type[c], rr, vals[c].lo);
+              v = call_output(t, p, c, hot, cold, flags);
             }
+            write_out_val(o, p, c, rr, v);
           }
         }
       }
+      // remember what was emitted (prev_outputs, agg_group.rs:575-603)
+      uint64_t nf = flags;
+      if (store_prev) {
+        uint32_t curr_nm = 0;
+        for (int c = 0; c < p.n_calls; c++) {
+          const OutVal v = call_output(t, p, c, hot, cold, flags);
+          cold[1 + c] = v.lo;
+          if (p.prevhi_off[c] >= 0) cold[p.prevhi_off[c]] = v.hi;
+          if (v.null) curr_nm |= 1u << c;
+        }
+        nf = (nf & ~(0xFFFFull << 16)) | ((uint64_t)curr_nm << 16) | COLD_HAS_PREV;
+      } else if (nrows == 1 && op0 == RW_OP_DELETE) {
+        nf &= ~(COLD_HAS_PREV | (0xFFFFull << 16));
+      }
+      cold[0] = nf;
+      t.dirty[slot >> 5] = 0;  // every dirty slot of this word is in the list; racing zero-stores are benign
     }
-    if (lane == 0) t.dirty[w] = 0;
   }
 }
 
@@ -526,7 +551,10 @@ __global__ void agg_rehash_kernel(AggTable o, AggTable n, AggPlanDev p) {
     uint64_t* nc = n.cold + dst * p.CW;
     for (int k = (s >= o.cap ? 0 : 1); k < p.HW; k++) nh[k] = oh[k];
     for (int k = 0; k < p.CW; k++) nc[k] = oc[k];
-    if (dirty) atomicOr(n.dirty + (dst >> 5), 1u << (dst & 31));
+    if (dirty) {
+      atomicOr(n.dirty + (dst >> 5), 1u << (dst & 31));
+      n.dirty_list[atomicAdd(&n.status->n_dirty, 1u)] = (uint32_t)dst;
+    }
   }
   for (int d = 16; d > 0; d >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, d);
   if (lane_id() == 0 && kept) atomicAdd(&n.status->n_groups, (unsigned long long)kept);
@@ -564,7 +592,7 @@ struct rwgpu_agg {
   std::vector<int> in_types, out_types, used_cols;
   int chunk_size = 1024;
   cudaStream_t stream = nullptr;
-  DevBuf hot, cold, dirty, status;
+  DevBuf hot, cold, dirty, dirty_list, status;
   uint64_t cap = 0;
   uint64_t groups_upper = 0;
   uint64_t epoch_rows = 0;
@@ -592,6 +620,7 @@ struct rwgpu_agg {
     t.hot = hot.as<uint64_t>();
     t.cold = cold.as<uint64_t>();
     t.dirty = dirty.as<uint32_t>();
+    t.dirty_list = dirty_list.as<uint32_t>();
     t.status = status.as<AggStatus>();
     t.cap = cap;
     return t;
@@ -608,11 +637,12 @@ static int grid_for(int64_t n_threads, int block) {
   return (int)std::max<int64_t>(1, std::min(g, maxg));
 }
 
-static int agg_alloc_table(rwgpu_agg* h, uint64_t cap, DevBuf& hot, DevBuf& cold, DevBuf& dirty) {
+static int agg_alloc_table(rwgpu_agg* h, uint64_t cap, DevBuf& hot, DevBuf& cold, DevBuf& dirty, DevBuf& dlist) {
   size_t slots = cap + 2;
   RW_CUDA(hot.reserve(slots * h->plan.HW * 8));
   RW_CUDA(cold.reserve(slots * h->plan.CW * 8));
   RW_CUDA(dirty.reserve(((slots + 31) / 32) * 4));
+  RW_CUDA(dlist.reserve(slots * 4));
   return RW_OK;
 }
 
@@ -636,15 +666,16 @@ static int agg_ensure_capacity(rwgpu_agg* h, uint64_t incoming) {
   uint64_t need = (h->groups_upper + incoming) * 4;
   uint64_t ncap = h->cap;
   while (ncap < need) ncap <<= 1;
-  DevBuf nh, nc, nd;
-  int rc = agg_alloc_table(h, ncap, nh, nc, nd);
+  DevBuf nh, nc, nd, nl;
+  int rc = agg_alloc_table(h, ncap, nh, nc, nd, nl);
   if (rc != RW_OK) return rc;
   AggTable ot = h->table();
   AggTable nt = ot;
-  nt.hot = nh.as<uint64_t>(); nt.cold = nc.as<uint64_t>(); nt.dirty = nd.as<uint32_t>(); nt.cap = ncap;
+  nt.hot = nh.as<uint64_t>(); nt.cold = nc.as<uint64_t>(); nt.dirty = nd.as<uint32_t>(); nt.dirty_list = nl.as<uint32_t>(); nt.cap = ncap;
   rc = agg_init_table(h, nt);
   if (rc != RW_OK) return rc;
   RW_CUDA(cudaMemsetAsync(&h->status.as<AggStatus>()->n_groups, 0, sizeof(unsigned long long), h->stream));
+  RW_CUDA(cudaMemsetAsync(&h->status.as<AggStatus>()->n_dirty, 0, sizeof(unsigned int), h->stream));
   agg_rehash_kernel<<<grid_for((int64_t)ot.cap + 2, 256), 256, 0, h->stream>>>(ot, nt, h->plan);
   RW_CUDA(cudaGetLastError());
   h->launches++;
@@ -652,6 +683,7 @@ static int agg_ensure_capacity(rwgpu_agg* h, uint64_t incoming) {
   h->hot = std::move(nh);
   h->cold = std::move(nc);
   h->dirty = std::move(nd);
+  h->dirty_list = std::move(nl);
   h->cap = ncap;
   RW_CUDA(cudaMemcpy(sh, h->status.p, sizeof(AggStatus), cudaMemcpyDeviceToHost));
   h->groups_upper = sh->n_groups;
@@ -678,7 +710,7 @@ static int agg_apply_dev(rwgpu_agg* h, const DevChunk& ch, cudaStream_t st) {
   for (int c : h->used_cols) if (ch.cols[c].valid_bits || ch.cols[c].valid_bytes) has_nulls = true;
   if (has_nulls) {
     if (!h->per_row_mode && h->nullfree_push_seen) {
-      agg_set_flags_kernel<<<grid_for((int64_t)((h->cap + 2 + 31) >> 5), 256), 256, 0, st>>>(h->table(), h->plan, h->all_flag_mask);
+      agg_set_flags_kernel<<<grid_for((int64_t)std::min<uint64_t>(h->epoch_rows + 1, h->cap + 2), 256), 256, 0, st>>>(h->table(), h->plan, h->all_flag_mask);
       RW_CUDA(cudaGetLastError());
       h->launches++;
     }
@@ -791,9 +823,10 @@ static int agg_flush_dev(rwgpu_agg* h, cudaStream_t st, int64_t* n_rows, unsigne
   o.capacity = h->out_cap;
   uint32_t mask = h->per_row_mode ? 0u : h->all_flag_mask;
   if (h->epoch_rows > 0) {
-    int64_t nwords = (int64_t)((h->cap + 2 + 31) >> 5);
-    agg_flush_kernel<<<grid_for(nwords * 32, 256), 256, 0, st>>>(h->table(), h->plan, o, mask);
+    int64_t max_dirty = (int64_t)std::min<uint64_t>(h->epoch_rows, h->cap + 2);
+    agg_flush_kernel<<<grid_for(max_dirty, 256), 256, 0, st>>>(h->table(), h->plan, o, mask);
     RW_CUDA(cudaGetLastError());
+    RW_CUDA(cudaMemsetAsync(&ds->n_dirty, 0, sizeof(unsigned int), st));
     h->launches++;
   }
   uint8_t* sh = h->status_host.as<uint8_t>();
@@ -910,7 +943,7 @@ int32_t rwgpu_agg_create(const rw_agg_desc* d, rwgpu_agg** out) {
   uint64_t cap = 1024;
   while (cap < want) cap <<= 1;
   h->cap = cap;
-  rc = agg_alloc_table(h, cap, h->hot, h->cold, h->dirty);
+  rc = agg_alloc_table(h, cap, h->hot, h->cold, h->dirty, h->dirty_list);
   if (rc != RW_OK) return rc;
   RW_CUDA(h->status.reserve(sizeof(AggStatus)));
   RW_CUDA(cudaMemsetAsync(h->status.p, 0, sizeof(AggStatus), h->stream));

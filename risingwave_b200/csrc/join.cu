@@ -582,11 +582,11 @@ __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __r
 // host uses it to redo the emission after an output-capacity overflow (phases 1-3 never touch
 // operator state, and phase 4 only touches the OWN side, so the redo is exact).
 #define JF_BLOCK 256
-#define JF_R 4
+#define JF_R 1
 template <bool PROBE_ONLY>
-__global__ void __launch_bounds__(JF_BLOCK) join_inner_fused_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch,
-                                                                     JoinSideDev own, JoinSideDev other, JoinOutDev o,
-                                                                     JoinStatus* st, uint32_t store_base, uint32_t seq_base) {
+__global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch,
+                                                                        JoinSideDev own, JoinSideDev other, JoinOutDev o,
+                                                                        JoinStatus* st, uint32_t store_base, uint32_t seq_base) {
   __shared__ unsigned long long s_cnt[JF_R][JF_BLOCK / 32];
   __shared__ unsigned int s_sto[JF_R][JF_BLOCK / 32];
   __shared__ unsigned long long s_out_base;
@@ -600,91 +600,32 @@ __global__ void __launch_bounds__(JF_BLOCK) join_inner_fused_kernel(const JoinPl
     uint32_t head[JF_R], cnt[JF_R];
     uint8_t op[JF_R];
     bool store[JF_R];
-    // ---- phase 1: probe.  Key64: all JF_R first-probe slot loads are issued before any is consumed
-    // (memory-level parallelism); collisions continue in a scalar loop.
-    if (p->single_key) {
-      uint64_t key[JF_R], idx[JF_R];
-      ulonglong2 sl[JF_R];
-      int state[JF_R];  // 0 = no probe, 1 = probe the table, 2 = NULL side slot, 3 = EMPTY-valued side slot
-      const ColRef& kc = ch.cols[p->key_col[S][0]];
-      const uint64_t mask = other.cap - 1;
-#pragma unroll
-      for (int k = 0; k < JF_R; k++) {
-        const int64_t r = base + (int64_t)k * JF_BLOCK + threadIdx.x;
-        head[k] = J_NIL; cnt[k] = 0; op[k] = 0; store[k] = false; state[k] = 0; key[k] = 0; idx[k] = 0;
-        if (r < ch.n) {
-          op[k] = ch.ops[r];
-          if (row_visible(ch, r, op[k])) {
-            const bool ins = (op[k] == RW_OP_INSERT || op[k] == RW_OP_UPDATE_INSERT);
-            const bool nul = col_is_null(kc, r);
-            if (!(nul && !p->null_safe[0])) {  // not a never-match row (hash_join.rs:985-999)
-              store[k] = ins;
-              if (!ins) n_del++;
-              if (nul) state[k] = 2;
-              else {
-                key[k] = load_key_word(kc, r);
-                state[k] = (key[k] == J_EMPTY) ? 3 : 1;
-                const uint64_t hsh = mix64(key[k]);
-                idx[k] = hsh & mask;
-                if (!PROBE_ONLY && ins) prefetch_l2(own.slots + (hsh & (own.cap - 1)) * 2);  // claimed in phase 4
-              }
-            }
-          } else {
-            op[k] = 0;
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < JF_R; k++) {
-        if (state[k] == 1) sl[k] = __ldcg((const ulonglong2*)(other.slots + idx[k] * 2));
-        else if (state[k] >= 2) { sl[k].x = 0; sl[k].y = __ldcg((const unsigned long long*)(other.slots + (other.cap + (state[k] - 2)) * 2 + 1)); }
-      }
-#pragma unroll
-      for (int k = 0; k < JF_R; k++) {
-        if (state[k] == 0) continue;
-        if (state[k] == 1) {
-          while (sl[k].x != key[k] && sl[k].x != J_EMPTY) {
-            idx[k] = (idx[k] + 1) & mask;
-            sl[k] = __ldcg((const ulonglong2*)(other.slots + idx[k] * 2));
-          }
-          if (sl[k].x != key[k]) continue;
-        }
-        head[k] = (uint32_t)sl[k].y & 0x7fffffffu;
-        cnt[k] = (uint32_t)(sl[k].y >> 32);
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < JF_R; k++) {
-        const int64_t r = base + (int64_t)k * JF_BLOCK + threadIdx.x;
-        head[k] = J_NIL; cnt[k] = 0; op[k] = 0; store[k] = false;
-        if (r < ch.n) {
-          op[k] = ch.ops[r];
-          if (row_visible(ch, r, op[k])) {
-            uint64_t kw[RW_MAX_KEYS];
-            uint32_t nm;
-            const bool ins = (op[k] == RW_OP_INSERT || op[k] == RW_OP_UPDATE_INSERT);
-            if (!chunk_key(p, S, ch, r, kw, &nm)) {
-              store[k] = ins;
-              if (!ins) n_del++;
-              uint64_t hc;
-              if (js_find(other, p, kw, nm, &hc) >= 0) {
-                head[k] = (uint32_t)hc & 0x7fffffffu;
-                cnt[k] = (uint32_t)(hc >> 32);
-              }
-            }
-          } else {
-            op[k] = 0;
-          }
-        }
-      }
-    }
-    // pull the first matched record of every row towards the SM now, so the JF_R gathers overlap
+    // ---- phase 1: probe the other side's index
 #pragma unroll
     for (int k = 0; k < JF_R; k++) {
-      if (cnt[k] && head[k] != J_NIL) {
-        const uint8_t* rp = rec_ptr(other, head[k]);
-        prefetch_l2(rp);
-        prefetch_l2(rp + other.stride - 4);
+      const int64_t r = base + (int64_t)k * JF_BLOCK + threadIdx.x;
+      head[k] = J_NIL; cnt[k] = 0; op[k] = 0; store[k] = false;
+      if (r < ch.n) {
+        op[k] = ch.ops[r];
+        if (row_visible(ch, r, op[k])) {
+          uint64_t kw[RW_MAX_KEYS];
+          uint32_t nm;
+          const bool ins = (op[k] == RW_OP_INSERT || op[k] == RW_OP_UPDATE_INSERT);
+          if (!chunk_key(p, S, ch, r, kw, &nm)) {
+            store[k] = ins;
+            if (!ins) n_del++;
+            if (!PROBE_ONLY && ins && p->single_key && !nm)  // the own-side slot is claimed in phase 4: start fetching it
+              prefetch_l2(own.slots + (mix64(kw[0]) & (own.cap - 1)) * 2);
+            uint64_t hc;
+            if (js_find(other, p, kw, nm, &hc) >= 0) {
+              head[k] = (uint32_t)hc & 0x7fffffffu;
+              cnt[k] = (uint32_t)(hc >> 32);
+              if (cnt[k]) prefetch_l2(rec_ptr(other, head[k]));
+            }
+          }
+        } else {
+          op[k] = 0;
+        }
       }
     }
     if (p->cond_cmp != RW_CMP_NONE) {  // a non-equi condition filters matches: count by walking
