@@ -444,7 +444,8 @@ __global__ void fill_i32_kernel(int32_t* p, uint64_t n, int32_t v) {
 __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch,
                                                            JoinSideDev own, JoinSideDev other, JoinScratch sc,
                                                            const uint64_t* __restrict__ sorted, JoinOutDev o,
-                                                           JoinStatus* st, uint32_t store_base, uint32_t seq_base) {
+                                                           JoinStatus* st, uint32_t store_base, uint32_t seq_base,
+                                                           int64_t out_base) {
   const int T = p->T;
   const bool fwd_once = jt_forward_exactly_once(T, S);
   const bool fwd_unmatched = jt_forward_if_not_matched(T, S);
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __r
       const uint8_t jop = ins ? RW_OP_INSERT : RW_OP_DELETE;
       const uint64_t pk = sc.packed[r];
       const int64_t bound = (int64_t)(pk & ((1ull << 40) - 1));
-      const int64_t obase = (int64_t)(sc.offs[r] & ((1ull << 40) - 1));
+      const int64_t obase = out_base + (int64_t)(sc.offs[r] & ((1ull << 40) - 1));
       const uint32_t store_row = store_base + (uint32_t)(sc.offs[r] >> 40);
       int64_t w = 0;  // rows written so far for r
       const bool room = obase + bound <= o.capacity;
@@ -813,7 +814,8 @@ struct rwgpu_join {
   DevBuf plan_dev, status;
   PinnedBuf status_host;
   JoinSideHost side[2];
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[8] = {nullptr}, ev_main[8] = {nullptr};
   std::vector<int> out_types;
   int chunk_size = 1024;
   bool fast_inner = false;
@@ -834,7 +836,13 @@ struct rwgpu_join {
   PinnedBuf up_host;
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
   std::vector<rw_column> dev_view_cols;
-  ~rwgpu_join() { if (stream) cudaStreamDestroy(stream); }
+  ~rwgpu_join() {
+    for (auto e : ev_h2d) if (e) cudaEventDestroy(e);
+    for (auto e : ev_main) if (e) cudaEventDestroy(e);
+    if (s_h2d) cudaStreamDestroy(s_h2d);
+    if (s_d2h) cudaStreamDestroy(s_d2h);
+    if (stream) cudaStreamDestroy(stream);
+  }
 };
 
 static int jgrid(int64_t n, int block) {
@@ -918,20 +926,32 @@ static int join_ensure_scratch(rwgpu_join* h, int64_t n) {
   return RW_OK;
 }
 
-static int join_ensure_out(rwgpu_join* h, int64_t rows, cudaStream_t st) {
+// make room for `rows` output rows; the first `keep` rows already written are preserved
+static int join_ensure_out(rwgpu_join* h, int64_t rows, cudaStream_t st, int64_t keep = 0) {
   if (rows <= h->out_cap) return RW_OK;
   int64_t cap = std::max<int64_t>(rows + rows / 4, 4096);
-  RW_CUDA(cudaStreamSynchronize(st));
-  RW_CUDA(h->out_ops.reserve((size_t)cap));
-  RW_CUDA(h->out_vis.reserve((size_t)cap));
+  RW_CUDA(cudaDeviceSynchronize());
+  auto grow = [&](DevBuf& b, size_t elt, bool fill_one) -> int {
+    DevBuf nb;
+    RW_CUDA(nb.reserve((size_t)cap * elt));
+    if (fill_one) RW_CUDA(cudaMemset(nb.p, 1, (size_t)cap * elt));
+    if (keep > 0 && b.p) RW_CUDA(cudaMemcpy(nb.p, b.p, (size_t)keep * elt, cudaMemcpyDeviceToDevice));
+    b = std::move(nb);
+    return RW_OK;
+  };
+  int rc = grow(h->out_ops, 1, false);
+  if (rc != RW_OK) return rc;
+  rc = grow(h->out_vis, 1, false);
+  if (rc != RW_OK) return rc;
   RW_CUDA(h->out_visbits.reserve((size_t)((cap + 63) / 64) * 8));
   for (size_t k = 0; k < h->out_types.size(); k++) {
-    RW_CUDA(h->out_col[k].reserve((size_t)cap * type_width(h->out_types[k])));
-    RW_CUDA(h->out_valid[k].reserve((size_t)cap));
-    RW_CUDA(cudaMemsetAsync(h->out_valid[k].p, 1, (size_t)cap, st));  // invariant: valid bytes are 1 between pushes
+    rc = grow(h->out_col[k], (size_t)type_width(h->out_types[k]), false);
+    if (rc != RW_OK) return rc;
+    rc = grow(h->out_valid[k], 1, true);  // invariant: valid bytes are 1 between pushes
+    if (rc != RW_OK) return rc;
     RW_CUDA(h->out_bits[k].reserve((size_t)((cap + 63) / 64) * 8));
   }
-  h->valid_dirty = 0;
+  if (keep == 0) h->valid_dirty = 0;
   h->out_cap = cap;
   return RW_OK;
 }
@@ -972,10 +992,11 @@ static int join_check_err(rwgpu_join* h, const JoinStatus& s, cudaStream_t st) {
 
 // one push of a device-resident chunk; on return the output sits in the device output buffers.
 // *null_mask: bit k = output column k holds NULLs, bit 63 = some rows are invisible.
-static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t st, int64_t* out_rows,
+// `out_base` rows of the device output buffers are already occupied by earlier sub-batches of the
+// same API call (the caller zeroed status.out_rows / null_mask before the first one).
+static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t st, int64_t out_base, int64_t* out_rows,
                          unsigned long long* null_mask) {
   *out_rows = 0;
-  *null_mask = 0;
   const int64_t n = ch.n;
   if (n <= 0) return RW_OK;
   if (n >= (1ll << 31)) return fail(RW_ERR_INVALID, "chunk too large");
@@ -984,16 +1005,14 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
   if (rc != RW_OK) return rc;
   rc = join_grow_slots(h, S, own.keys_upper + (uint64_t)n);
   if (rc != RW_OK) return rc;
-  rc = join_clean_valid(h, st);
-  if (rc != RW_OK) return rc;
   JoinStatus* ds = h->status.as<JoinStatus>();
   const JoinPlanDev* pd = h->plan_dev.as<JoinPlanDev>();
-  RW_CUDA(cudaMemsetAsync(ds, 0, 32, st));  // out_rows, n_store, n_del, null_mask
+  RW_CUDA(cudaMemsetAsync(&ds->n_store, 0, 16, st));  // n_store, n_del (out_rows / null_mask accumulate over the call)
   const uint32_t seq_base = (uint32_t)h->seq;
   h->seq += (uint64_t)n;
   JoinStatus hs;
   if (h->fast_inner) {
-    rc = join_ensure_out(h, std::max<int64_t>(2 * n, 4096), st);
+    rc = join_ensure_out(h, out_base + std::max<int64_t>(2 * n, 4096), st, out_base);
     if (rc != RW_OK) return rc;
     const int64_t tiles = (n + JF_BLOCK * JF_R - 1) / (JF_BLOCK * JF_R);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, 148 * 8));
@@ -1011,9 +1030,12 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     while (hs.err & JERR_OUT_CAPACITY) {
       // the reservation overflowed: redo the (state-free) probe + emit with room for every row
       const int64_t need = (int64_t)hs.out_rows;
-      RW_CUDA(cudaMemsetAsync(ds, 0, 32, st));
+      const unsigned long long base_ull = (unsigned long long)out_base;
+      RW_CUDA(cudaMemcpyAsync(&ds->out_rows, &base_ull, 8, cudaMemcpyHostToDevice, st));
+      RW_CUDA(cudaMemsetAsync(&ds->n_store, 0, 16, st));
       RW_CUDA(cudaMemsetAsync(&ds->err, 0, 4, st));
-      rc = join_ensure_out(h, need, st);
+      RW_CUDA(cudaStreamSynchronize(st));
+      rc = join_ensure_out(h, need, st, out_base);
       if (rc != RW_OK) return rc;
       join_inner_fused_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds, 0, seq_base);
       RW_CUDA(cudaGetLastError());
@@ -1027,7 +1049,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     hs.err = err;
     rc = join_check_err(h, hs, st);
     if (rc != RW_OK) return rc;
-    *out_rows = (int64_t)hs.out_rows;
+    *out_rows = (int64_t)hs.out_rows - out_base;
   } else {
     rc = join_ensure_scratch(h, n);
     if (rc != RW_OK) return rc;
@@ -1055,12 +1077,12 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     rc = join_read_status(h, st, &hs);
     if (rc != RW_OK) return rc;
     const int64_t reserved = (int64_t)hs.out_rows;
-    rc = join_ensure_out(h, reserved, st);
+    rc = join_ensure_out(h, out_base + reserved, st, out_base);
     if (rc != RW_OK) return rc;
-    if (reserved > 0) RW_CUDA(cudaMemsetAsync(h->out_vis.p, 1, (size_t)reserved, st));
+    if (reserved > 0) RW_CUDA(cudaMemsetAsync(h->out_vis.as<uint8_t>() + out_base, 1, (size_t)reserved, st));
     h->prof.begin(st);
     join_serial_kernel<<<jgrid(n, 128), 128, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), sc, db.Current(), out_dev(h), ds,
-                                                        (uint32_t)own.n_rows, seq_base);
+                                                        (uint32_t)own.n_rows, seq_base, out_base);
     h->prof.end(st);
     RW_CUDA(cudaGetLastError());
     h->launches++;
@@ -1073,7 +1095,17 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     *out_rows = reserved;
   }
   *null_mask = hs.null_mask;
-  h->valid_dirty = hs.null_mask & ((1ull << 63) - 1);
+  h->valid_dirty |= hs.null_mask & ((1ull << 63) - 1);
+  return RW_OK;
+}
+
+// start of an API call: restore the valid-byte invariant, zero the per-call accumulators
+static int join_begin_call(rwgpu_join* h, cudaStream_t st) {
+  int rc = join_clean_valid(h, st);
+  if (rc != RW_OK) return rc;
+  JoinStatus* ds = h->status.as<JoinStatus>();
+  RW_CUDA(cudaMemsetAsync(&ds->out_rows, 0, 8, st));
+  RW_CUDA(cudaMemsetAsync(&ds->null_mask, 0, 8, st));
   return RW_OK;
 }
 
@@ -1218,7 +1250,9 @@ int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* c, r
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
   int64_t n = 0;
   unsigned long long nullm = 0;
-  rc = join_push_dev(h, side, ch, st, &n, &nullm);
+  rc = join_begin_call(h, st);
+  if (rc != RW_OK) return rc;
+  rc = join_push_dev(h, side, ch, st, 0, &n, &nullm);
   if (rc != RW_OK) return rc;
   h->dev_view_cols.resize(h->out_types.size());
   for (size_t k = 0; k < h->out_types.size(); k++) {
@@ -1247,71 +1281,143 @@ int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* c, r
   return RW_OK;
 }
 
+// HOST chunk.  Large chunks are cut into sub-batches (multiples of 64 rows, so bitmap words split
+// cleanly) that flow through three streams: H2D of sub-batch j+1 overlaps the kernels of j and the
+// D2H of j-1.  Sub-batches are ordinary consecutive pushes, so the operator semantics are unchanged;
+// their outputs land back to back in one device buffer and one pinned host block.
 int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_out** out) {
   if (!h || !c || !out) return fail(RW_ERR_INVALID, "null");
   if (side != 0 && side != 1) return fail(RW_ERR_INVALID, "side");
   if (c->n_cols != h->side[side].n_cols) return fail(RW_ERR_INVALID, "chunk schema mismatch");
   for (int k = 0; k < c->n_cols; k++)
     if (c->columns[k].type != h->side[side].types[k]) return fail(RW_ERR_INVALID, "chunk column type mismatch");
-  // small buffers are packed through one pinned staging block; large column buffers are copied
-  // straight from the caller's memory
   const int64_t n = c->n_rows;
+  if (!h->s_h2d) {
+    RW_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    RW_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) {
+      RW_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+      RW_CUDA(cudaEventCreateWithFlags(&h->ev_main[i], cudaEventDisableTiming));
+    }
+  }
+  const int J = n >= (1 << 17) ? 8 : (n >= (1 << 15) ? 4 : 1);
+  int64_t sub = (n + J - 1) / J;
+  sub = (sub + 63) / 64 * 64;
+  // device staging: [ops | vis words | per column: data, valid words], regions sized for the whole chunk
   const size_t nw = (size_t)((n + 63) / 64) * 8;
-  const size_t DIRECT = 1 << 20;
-  size_t total = 256 + (size_t)n + 256 + nw;
-  for (int k = 0; k < c->n_cols; k++) total += 512 + (size_t)n * type_width(c->columns[k].type) + nw;
-  RW_CUDA(h->up.reserve(total));
-  RW_CUDA(h->up_host.reserve(total));
+  size_t off = 0;
+  auto region = [&](size_t bytes) { size_t o = align_up_j(off, 256); off = o + bytes; return o; };
+  const size_t o_ops = region((size_t)n), o_vis = region(nw);
+  size_t o_data[RW_MAX_COLS], o_valid[RW_MAX_COLS];
+  for (int k = 0; k < c->n_cols; k++) {
+    o_data[k] = region((size_t)n * type_width(c->columns[k].type));
+    o_valid[k] = region(nw);
+  }
+  RW_CUDA(h->up.reserve(off + 256));
+  RW_CUDA(h->up_host.reserve(off + 256));
   uint8_t* hp = h->up_host.as<uint8_t>();
   uint8_t* dp = h->up.as<uint8_t>();
-  size_t off = 0;
-  auto put = [&](const void* src, size_t bytes) -> const void* {
-    if (!src) return nullptr;
-    size_t o = align_up_j(off, 256);
-    if (bytes >= DIRECT) cudaMemcpyAsync(dp + o, src, bytes, cudaMemcpyHostToDevice, h->stream);
-    else { memcpy(hp + o, src, bytes); cudaMemcpyAsync(dp + o, hp + o, bytes, cudaMemcpyHostToDevice, h->stream); }
-    off = o + bytes;
-    return dp + o;
+  // a caller buffer that is already pinned is copied straight from user memory; pageable small
+  // pieces go through the pinned staging block (one memcpy), pageable large ones directly
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
   };
-  DevChunk ch;
-  memset(&ch, 0, sizeof(ch));
-  ch.n = n;
-  ch.n_cols = c->n_cols;
-  ch.ops = (const uint8_t*)put(c->ops, (size_t)n);
-  ch.vis_bits = (const uint64_t*)put(c->visibility, nw);
-  for (int k = 0; k < c->n_cols; k++) {
-    int w = type_width(c->columns[k].type);
-    ch.cols[k].type = c->columns[k].type;
-    ch.cols[k].width = w;
-    ch.cols[k].data = put(c->columns[k].data, (size_t)n * w);
-    ch.cols[k].valid_bits = (const uint64_t*)put(c->columns[k].validity, nw);
+  auto h2d = [&](size_t dst_off, const void* src, size_t bytes, bool pinned) {
+    if (!bytes) return;
+    if (pinned || bytes >= (1u << 20)) cudaMemcpyAsync(dp + dst_off, src, bytes, cudaMemcpyHostToDevice, h->s_h2d);
+    else { memcpy(hp + dst_off, src, bytes); cudaMemcpyAsync(dp + dst_off, hp + dst_off, bytes, cudaMemcpyHostToDevice, h->s_h2d); }
+  };
+  RW_CUDA(cudaStreamSynchronize(h->s_d2h));  // previous call's copies are long done; cheap guard for buffer reuse
+  bool pin_ops = n ? is_pinned(c->ops) : false, pin_col[RW_MAX_COLS];
+  for (int k = 0; k < c->n_cols; k++) pin_col[k] = n ? is_pinned(c->columns[k].data) : false;
+  // enqueue every sub-batch's H2D up front
+  int n_sub = 0;
+  for (int64_t lo = 0; lo < n; lo += sub, n_sub++) {
+    const int64_t m = std::min<int64_t>(sub, n - lo);
+    const size_t wlo = (size_t)(lo / 64) * 8, wn = (size_t)((m + 63) / 64) * 8;
+    h2d(o_ops + (size_t)lo, c->ops + lo, (size_t)m, pin_ops);
+    if (c->visibility) h2d(o_vis + wlo, (const uint8_t*)c->visibility + wlo, wn, false);
+    for (int k = 0; k < c->n_cols; k++) {
+      const int w = type_width(c->columns[k].type);
+      h2d(o_data[k] + (size_t)lo * w, (const uint8_t*)c->columns[k].data + (size_t)lo * w, (size_t)m * w, pin_col[k]);
+      if (c->columns[k].validity) h2d(o_valid[k] + wlo, (const uint8_t*)c->columns[k].validity + wlo, wn, false);
+    }
+    RW_CUDA(cudaEventRecord(h->ev_h2d[n_sub], h->s_h2d));
   }
   RW_CUDA(cudaGetLastError());
-  int64_t rows = 0;
-  unsigned long long nullm = 0;
-  int rc = join_push_dev(h, side, ch, h->stream, &rows, &nullm);
+  int rc = join_begin_call(h, h->stream);
   if (rc != RW_OK) return rc;
   auto o = new rwgpu_out();
+  std::unique_ptr<rwgpu_out> guard(o);
   o->chunk_size = h->chunk_size;
-  if (!o->layout(rows, h->out_types, nullm & ((1ull << 63) - 1), (nullm >> 63) != 0, h->pool)) {
-    delete o;
-    return fail(RW_ERR_OOM, "pinned output block");
-  }
-  if (rows > 0) {
-    cudaMemcpyAsync(o->ops, h->out_ops.p, (size_t)rows, cudaMemcpyDeviceToHost, h->stream);
-    if (o->vis_bytes) cudaMemcpyAsync(o->vis_bytes, h->out_vis.p, (size_t)rows, cudaMemcpyDeviceToHost, h->stream);
-    for (size_t k = 0; k < h->out_types.size(); k++) {
-      size_t w = type_width(h->out_types[k]);
-      cudaMemcpyAsync(o->data[k], h->out_col[k].p, (size_t)rows * w, cudaMemcpyDeviceToHost, h->stream);
-      if (o->valid_bytes[k]) cudaMemcpyAsync(o->valid_bytes[k], h->out_valid[k].p, (size_t)rows, cudaMemcpyDeviceToHost, h->stream);
+  // pinned host block laid out for `host_cap` rows; re-laid (host copy of the prefix) if outputs exceed it
+  int64_t host_cap = std::max<int64_t>(2 * n, 1024);
+  if (!o->layout(host_cap, h->out_types, ~0ull >> 1, true, h->pool)) return fail(RW_ERR_OOM, "pinned output block");
+  int64_t total = 0;
+  unsigned long long nullm = 0;
+  int js = 0;
+  for (int64_t lo = 0; lo < n; lo += sub, js++) {
+    const int64_t m = std::min<int64_t>(sub, n - lo);
+    DevChunk ch;
+    memset(&ch, 0, sizeof(ch));
+    ch.n = m;
+    ch.n_cols = c->n_cols;
+    ch.ops = dp + o_ops + lo;
+    ch.vis_bits = c->visibility ? (const uint64_t*)(dp + o_vis + (size_t)(lo / 64) * 8) : nullptr;
+    for (int k = 0; k < c->n_cols; k++) {
+      const int w = type_width(c->columns[k].type);
+      ch.cols[k].type = c->columns[k].type;
+      ch.cols[k].width = w;
+      ch.cols[k].data = dp + o_data[k] + (size_t)lo * w;
+      ch.cols[k].valid_bits = c->columns[k].validity ? (const uint64_t*)(dp + o_valid[k] + (size_t)(lo / 64) * 8) : nullptr;
     }
-    cudaError_t e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) { delete o; return fail(RW_ERR_CUDA, cudaGetErrorString(e)); }
-  } else {
-    RW_CUDA(cudaStreamSynchronize(h->stream));  // the staging block is reused by the next call
+    RW_CUDA(cudaStreamWaitEvent(h->stream, h->ev_h2d[js], 0));
+    int64_t rows = 0;
+    rc = join_push_dev(h, side, ch, h->stream, total, &rows, &nullm);
+    if (rc != RW_OK) { cudaStreamSynchronize(h->s_d2h); return rc; }
+    if (total + rows > host_cap) {  // rare: amplification above 2x -- grow the host block, keep the copied prefix
+      RW_CUDA(cudaStreamSynchronize(h->s_d2h));
+      auto o2 = new rwgpu_out();
+      o2->chunk_size = h->chunk_size;
+      const int64_t ncap = (total + rows) * 2;
+      if (!o2->layout(ncap, h->out_types, ~0ull >> 1, true, h->pool)) { delete o2; return fail(RW_ERR_OOM, "pinned output block"); }
+      if (total > 0) {
+        memcpy(o2->ops, o->ops, (size_t)total);
+        for (size_t k = 0; k < h->out_types.size(); k++) memcpy(o2->data[k], o->data[k], (size_t)total * type_width(h->out_types[k]));
+      }
+      guard.reset(o2);
+      o = o2;
+      host_cap = ncap;
+    }
+    if (rows > 0) {
+      RW_CUDA(cudaEventRecord(h->ev_main[js], h->stream));
+      RW_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_main[js], 0));
+      cudaMemcpyAsync(o->ops + total, h->out_ops.as<uint8_t>() + total, (size_t)rows, cudaMemcpyDeviceToHost, h->s_d2h);
+      for (size_t k = 0; k < h->out_types.size(); k++) {
+        const size_t w = type_width(h->out_types[k]);
+        cudaMemcpyAsync(o->data[k] + (size_t)total * w, h->out_col[k].as<uint8_t>() + (size_t)total * w, (size_t)rows * w,
+                        cudaMemcpyDeviceToHost, h->s_d2h);
+      }
+    }
+    total += rows;
   }
+  // NULL / visibility bytes only for the columns that need them (known once all sub-batches ran)
+  if (total > 0) {
+    if (nullm >> 63) cudaMemcpyAsync(o->vis_bytes, h->out_vis.p, (size_t)total, cudaMemcpyDeviceToHost, h->s_d2h);
+    for (size_t k = 0; k < h->out_types.size(); k++)
+      if ((nullm >> k) & 1) cudaMemcpyAsync(o->valid_bytes[k], h->out_valid[k].p, (size_t)total, cudaMemcpyDeviceToHost, h->s_d2h);
+  }
+  RW_CUDA(cudaStreamSynchronize(h->stream));
+  RW_CUDA(cudaStreamSynchronize(h->s_d2h));
+  RW_CUDA(cudaStreamSynchronize(h->s_h2d));
+  o->n_rows = total;
+  if (!(nullm >> 63)) o->vis_bytes = nullptr;
+  for (size_t k = 0; k < h->out_types.size(); k++)
+    if (!((nullm >> k) & 1)) o->valid_bytes[k] = nullptr;
   o->finalize();
-  *out = o;
+  *out = guard.release();
   return RW_OK;
 }
 
