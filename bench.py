@@ -354,7 +354,7 @@ def run_ours(args):
         if "e2e" in legs and world == 1:
             join2 = new_join()
             build(join2, shuffle=False)
-            FFI_ROWS = 1 << 18  # 256 coalesced 1024-row chunks per C-ABI call
+            FFI_ROWS = BATCH  # the same 1024 coalesced 1024-row chunks per C-ABI call as the device-resident leg
             ones_pinned = torch.ones(FFI_ROWS, dtype=torch.uint8).pin_memory().numpy()
             chunks_host = []
             for s in range(W + K):

@@ -24,6 +24,9 @@
 //     key's rows in input order -- state of different keys is disjoint, so this is exactly the
 //     reference's sequential semantics with the parallelism taken across keys.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -1292,6 +1295,9 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
   for (int k = 0; k < c->n_cols; k++)
     if (c->columns[k].type != h->side[side].types[k]) return fail(RW_ERR_INVALID, "chunk column type mismatch");
   const int64_t n = c->n_rows;
+  static const bool trace = getenv("RWGPU_TRACE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = now();
   if (!h->s_h2d) {
     RW_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
     RW_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
@@ -1300,7 +1306,8 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
       RW_CUDA(cudaEventCreateWithFlags(&h->ev_main[i], cudaEventDisableTiming));
     }
   }
-  const int J = n >= (1 << 17) ? 8 : (n >= (1 << 15) ? 4 : 1);
+  // each sub-batch costs one status read-back (~40 us): keep them >= 32K rows
+  const int J = n >= (1 << 19) ? 8 : (n >= (1 << 17) ? 4 : (n >= (1 << 16) ? 2 : 1));
   int64_t sub = (n + J - 1) / J;
   sub = (sub + 63) / 64 * 64;
   // device staging: [ops | vis words | per column: data, valid words], regions sized for the whole chunk
@@ -1347,6 +1354,7 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
     RW_CUDA(cudaEventRecord(h->ev_h2d[n_sub], h->s_h2d));
   }
   RW_CUDA(cudaGetLastError());
+  const double t1 = now();
   int rc = join_begin_call(h, h->stream);
   if (rc != RW_OK) return rc;
   auto o = new rwgpu_out();
@@ -1358,6 +1366,7 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
   int64_t total = 0;
   unsigned long long nullm = 0;
   int js = 0;
+  const double t2 = now();
   for (int64_t lo = 0; lo < n; lo += sub, js++) {
     const int64_t m = std::min<int64_t>(sub, n - lo);
     DevChunk ch;
@@ -1409,14 +1418,19 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
     for (size_t k = 0; k < h->out_types.size(); k++)
       if ((nullm >> k) & 1) cudaMemcpyAsync(o->valid_bytes[k], h->out_valid[k].p, (size_t)total, cudaMemcpyDeviceToHost, h->s_d2h);
   }
+  const double t3 = now();
   RW_CUDA(cudaStreamSynchronize(h->stream));
   RW_CUDA(cudaStreamSynchronize(h->s_d2h));
   RW_CUDA(cudaStreamSynchronize(h->s_h2d));
+  const double t4 = now();
   o->n_rows = total;
   if (!(nullm >> 63)) o->vis_bytes = nullptr;
   for (size_t k = 0; k < h->out_types.size(); k++)
     if (!((nullm >> k) & 1)) o->valid_bytes[k] = nullptr;
   o->finalize();
+  if (trace)
+    fprintf(stderr, "[rwgpu_join_push] n=%lld out=%lld J=%d  h2d-enqueue %.3f  layout %.3f  sub-batches %.3f  drain %.3f  finalize %.3f  total %.3f ms\n",
+            (long long)n, (long long)total, n_sub, t1 - t0, t2 - t1, t3 - t2, t4 - t3, now() - t4, now() - t0);
   *out = guard.release();
   return RW_OK;
 }
