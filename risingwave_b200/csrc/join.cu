@@ -8,13 +8,19 @@
 //   join-type predicates                   src/stream/src/executor/join/mod.rs:103-169
 //
 // HBM layout per side:
-//   record store : array of fixed-stride records, append-only, row id = index.
-//                  record = { u32 link (next row of the same key | DEAD bit), u32 null mask (bit c =
-//                  column c is NULL), u32 seq (arrival order), u32 degree } + the row's columns
-//                  packed at naturally aligned offsets; stride is a multiple of 16 B
-//                  (Nexmark bid / auction: 16 + 4*8 = 48 B = three 128-bit loads, 2 DRAM sectors).
-//   hash index   : open addressing, linear probing, power-of-two capacity, load <= 1/2;
-//                  slot = key word(s) | (live count << 32 | head row)   (Key64: 16 B, one 128-bit load)
+//   record       : { u32 link (next row of the same key | DEAD bit), u32 null mask (bit c = column c
+//                  is NULL), u32 seq (arrival order), u32 degree } + the row's columns packed at
+//                  naturally aligned offsets; stride is a multiple of 16 B (Nexmark bid / auction:
+//                  16 + 4*8 = 48 B).
+//   hash index   : open addressing over BUCKETS, linear probing, power-of-two capacity, load <= 1/2;
+//                  bucket = key word(s) | (live count << 32 | overflow head row) | ONE INLINE RECORD.
+//                  Key64 + 48 B record = 64 B: a probe of a key with one row (bid -> auction) is ONE
+//                  64-byte random access that returns key, count and the row; an insert into a
+//                  fresh key is one 64-byte read-modify-write.  (Random 64 B transactions are what
+//                  bounds this workload: measured 42 G random loads/s, 22 G random RMW/s on B200,
+//                  profiles/r1_ubench_atomics.txt.)
+//   overflow store: further rows of a key go to an append-only array of records chained through
+//                  `link` from the bucket's head.
 // Two execution paths:
 //   * inner fast path (no degrees): ONE fused kernel per batch -- probe the other side, emit the
 //     matches with tile-scan compaction, append the row to the own side; a second kernel applies
@@ -41,6 +47,7 @@ namespace rw {
 #define J_DEAD 0x80000000u
 #define J_MAX_OUT (2 * RW_MAX_COLS)
 #define J_HDR 16
+#define IL_EMPTY 0xFFFFFFFFu  // inline record never used (link field)
 
 #define JERR_DOUBLE_DELETE 1u
 #define JERR_OUT_CAPACITY 2u
@@ -56,6 +63,8 @@ struct JoinPlanDev {
   int col_width[2][RW_MAX_COLS];
   int col_off[2][RW_MAX_COLS];  // byte offset of the column inside a record
   int stride[2];
+  int bhdr;        // bytes of a bucket before its inline record: (KW + 1) * 8
+  int bstride[2];  // bucket bytes: bhdr + stride, rounded up to 16
   int n_pk[2];
   int pk_col[2][RW_MAX_COLS];
   int n_out;
@@ -72,11 +81,11 @@ struct JoinPlanDev {
 };
 
 struct JoinSideDev {
-  uint8_t* recs;
-  uint64_t* slots;
+  uint8_t* recs;     // overflow record store
+  uint8_t* buckets;  // hash index with inline records
   uint64_t cap;
   int stride;
-  int pad;
+  int bstride;
 };
 
 struct JoinStatus {
@@ -161,12 +170,35 @@ __device__ __forceinline__ uint64_t key_hash(const JoinPlanDev* p, const uint64_
   return h;
 }
 
-// head / count live in the last word of a slot: low 32 = head row (J_NIL = none), high 32 = live count
-__device__ __forceinline__ uint32_t* slot_head(const JoinSideDev& s, const JoinPlanDev* p, int64_t slot) {
-  return (uint32_t*)(s.slots + (uint64_t)slot * p->SW + p->KW);
+// bucket = [key word(s)] [head/count word: low 32 = overflow head row (J_NIL = none), high 32 = live count] [inline record]
+__device__ __forceinline__ uint8_t* bkt(const JoinSideDev& s, int64_t b) { return s.buckets + (uint64_t)b * s.bstride; }
+__device__ __forceinline__ uint32_t* slot_head(const JoinSideDev& s, const JoinPlanDev* p, int64_t b) {
+  return (uint32_t*)(bkt(s, b) + p->KW * 8);
 }
-__device__ __forceinline__ uint32_t* slot_count(const JoinSideDev& s, const JoinPlanDev* p, int64_t slot) {
-  return slot_head(s, p, slot) + 1;
+__device__ __forceinline__ uint32_t* slot_count(const JoinSideDev& s, const JoinPlanDev* p, int64_t b) {
+  return slot_head(s, p, b) + 1;
+}
+__device__ __forceinline__ uint8_t* bkt_inline(const JoinSideDev& s, const JoinPlanDev* p, int64_t b) { return bkt(s, b) + p->bhdr; }
+
+// visit every live record of bucket b: the inline record first, then the overflow chain.
+// `f(rec)` returns false to stop.
+template <class F>
+__device__ __forceinline__ void for_each_live(const JoinSideDev& s, const JoinPlanDev* p, int64_t b, F f) {
+  // link words are read through L2 (ld.cg): another thread of the same kernel may set DEAD
+  uint8_t* irec = bkt_inline(s, p, b);
+  const uint32_t ilk = __ldcg(&((const RecHdr*)irec)->link);
+  if (ilk != IL_EMPTY && !(ilk & J_DEAD)) {
+    if (!f(irec)) return;
+  }
+  uint32_t m = __ldcg(slot_head(s, p, b)) & 0x7fffffffu;
+  while (m != J_NIL) {
+    uint8_t* rec = rec_ptr(s, m);
+    const uint32_t lk = __ldcg(&((const RecHdr*)rec)->link);
+    if (!(lk & J_DEAD)) {
+      if (!f(rec)) return;
+    }
+    m = lk & 0x7fffffffu;
+  }
 }
 
 // find the slot of a key (read-only). returns -1 if absent; *hc = (count << 32 | head) of the slot.
@@ -177,10 +209,10 @@ __device__ __forceinline__ int64_t js_find(const JoinSideDev& s, const JoinPlanD
     int64_t side = -1;
     if (nm) side = (int64_t)s.cap;                         // NULL key side slot (null-safe equality)
     else if (kw[0] == J_EMPTY) side = (int64_t)s.cap + 1;
-    if (side >= 0) { *hc = __ldcg((const unsigned long long*)(s.slots + side * 2 + 1)); return side; }
+    if (side >= 0) { *hc = __ldcg((const unsigned long long*)(bkt(s, side) + 8)); return side; }
     uint64_t idx = mix64(kw[0]) & mask;
     while (true) {
-      const ulonglong2 sl = __ldcg((const ulonglong2*)(s.slots + idx * 2));  // key + head/count in one 128-bit load
+      const ulonglong2 sl = __ldcg((const ulonglong2*)bkt(s, (int64_t)idx));  // key + head/count in one 128-bit load
       if (sl.x == kw[0]) { *hc = sl.y; return (int64_t)idx; }
       if (sl.x == J_EMPTY) return -1;
       idx = (idx + 1) & mask;
@@ -190,7 +222,7 @@ __device__ __forceinline__ int64_t js_find(const JoinSideDev& s, const JoinPlanD
   uint64_t tag = (h & ~0xFFFFull) | ((uint64_t)nm << 8) | 1ull;
   uint64_t idx = (h >> 17) & mask;
   while (true) {
-    const unsigned long long* ptr = (const unsigned long long*)(s.slots + idx * p->SW);
+    const unsigned long long* ptr = (const unsigned long long*)bkt(s, (int64_t)idx);
     unsigned long long cur = __ldcg(ptr);
     if (cur == 0ull) return -1;
     if ((cur & ~2ull) == tag) {
@@ -211,7 +243,7 @@ __device__ __forceinline__ int64_t js_find_or_insert(const JoinSideDev& s, const
     if (kw[0] == J_EMPTY) return (int64_t)s.cap + 1;
     uint64_t idx = mix64(kw[0]) & mask;
     while (true) {
-      unsigned long long* ptr = (unsigned long long*)(s.slots + idx * 2);
+      unsigned long long* ptr = (unsigned long long*)bkt(s, (int64_t)idx);
       unsigned long long cur = __ldcg(ptr);
       if (cur == kw[0]) return (int64_t)idx;
       if (cur == J_EMPTY) {
@@ -226,7 +258,7 @@ __device__ __forceinline__ int64_t js_find_or_insert(const JoinSideDev& s, const
   uint64_t tag = (h & ~0xFFFFull) | ((uint64_t)nm << 8) | 1ull;
   uint64_t idx = (h >> 17) & mask;
   while (true) {
-    unsigned long long* ptr = (unsigned long long*)(s.slots + idx * p->SW);
+    unsigned long long* ptr = (unsigned long long*)bkt(s, (int64_t)idx);
     unsigned long long cur = __ldcg(ptr);
     if (cur == 0ull) {
       unsigned long long old = atomicCAS(ptr, 0ull, (unsigned long long)(tag | 2ull));
@@ -249,12 +281,13 @@ __device__ __forceinline__ int64_t js_find_or_insert(const JoinSideDev& s, const
   }
 }
 
-__global__ void join_init_slots_kernel(uint64_t* slots, uint64_t cap, int SW, int KW, int single_key) {
+__global__ void join_init_slots_kernel(uint8_t* buckets, uint64_t cap, int bstride, int KW, int single_key) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap + 2; i += (uint64_t)gridDim.x * blockDim.x) {
-    uint64_t* s = slots + i * SW;
+    uint64_t* s = (uint64_t*)(buckets + i * bstride);
     s[0] = single_key ? J_EMPTY : 0ull;
     for (int k = 1; k < KW; k++) s[k] = 0;
-    s[KW] = (uint64_t)J_NIL;  // head = NIL, count = 0
+    s[KW] = (uint64_t)J_NIL;                          // overflow head = NIL, count = 0
+    ((uint32_t*)(s + KW + 1))[0] = IL_EMPTY;           // inline record: never used
   }
 }
 
@@ -341,9 +374,8 @@ __device__ __forceinline__ bool pk_equal(const JoinPlanDev* p, int S, const uint
 }
 
 // write chunk row r into the record `row`
-__device__ __forceinline__ void rec_write(const JoinPlanDev* p, int S, const JoinSideDev& s, uint32_t row, const DevChunk& ch,
-                                          int64_t r, uint32_t link, uint32_t seq, uint32_t degree) {
-  uint8_t* rec = rec_ptr(s, row);
+__device__ __forceinline__ void rec_write(const JoinPlanDev* p, int S, uint8_t* rec, const DevChunk& ch, int64_t r,
+                                          uint32_t link, uint32_t seq, uint32_t degree) {
   uint32_t nm = 0;
   for (int c = 0; c < p->n_cols[S]; c++) {
     const ColRef& cr = ch.cols[c];
@@ -482,42 +514,37 @@ __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __r
       }
       const int64_t ms = sc.match_slot[r];
       uint32_t degree = 0;
-      int64_t ao_row = -1;
+      uint8_t* ao_rec = nullptr;
       if (ms >= 0) {
-        uint32_t m = *slot_head(other, p, ms) & 0x7fffffffu;
-        while (m != J_NIL) {
-          uint8_t* mrec = rec_ptr(other, m);
+        for_each_live(other, p, ms, [&](uint8_t* mrec) -> bool {
           RecHdr* mh = (RecHdr*)mrec;
-          const uint32_t lk = mh->link;
-          if (!(lk & J_DEAD)) {
-            if (cond_ok(p, S, ch, r, mrec)) {
-              degree++;
-              uint32_t md = other_deg ? mh->degree : 0;
-              if (ins && !fwd_once && room) {  // with_match_on_insert (builder.rs:184-231): m.degree BEFORE the increment
-                if (jt_is_anti(T)) { if (md == 0 && only_matched) emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, -1, mrec); }
-                else if (jt_is_semi(T)) { if (md == 0 && only_matched) emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, -1, mrec); }
-                else if (md == 0 && side_null) {
-                  emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, -1, mrec);
-                  emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, r, mrec);
-                } else emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, r, mrec);
-              }
-              if (other_deg) { md = ins ? md + 1 : md - 1; mh->degree = md; }  // update_degree (join/hash_join.rs:355-380)
-              if (!ins && !fwd_once && room) {  // with_match_on_delete (builder.rs:233-284): m.degree AFTER the decrement
-                if (jt_is_anti(T)) { if (md == 0 && only_matched) emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, -1, mrec); }
-                else if (jt_is_semi(T)) { if (md == 0 && only_matched) emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, -1, mrec); }
-                else if (md == 0 && side_null) {
-                  emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, r, mrec);
-                  emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, -1, mrec);
-                } else emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, r, mrec);
-              }
+          if (cond_ok(p, S, ch, r, mrec)) {
+            degree++;
+            uint32_t md = other_deg ? mh->degree : 0;
+            if (ins && !fwd_once && room) {  // with_match_on_insert (builder.rs:184-231): m.degree BEFORE the increment
+              if (jt_is_anti(T)) { if (md == 0 && only_matched) emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, -1, mrec); }
+              else if (jt_is_semi(T)) { if (md == 0 && only_matched) emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, -1, mrec); }
+              else if (md == 0 && side_null) {
+                emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, -1, mrec);
+                emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, r, mrec);
+              } else emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, r, mrec);
             }
-            if (p->append_only_optimize) {  // hash_join.rs:1339-1345 (regardless of the condition)
-              if (ao_row >= 0) atomicOr(&st->err, JERR_APPEND_ONLY_MULTI);
-              ao_row = m;
+            if (other_deg) { md = ins ? md + 1 : md - 1; mh->degree = md; }  // update_degree (join/hash_join.rs:355-380)
+            if (!ins && !fwd_once && room) {  // with_match_on_delete (builder.rs:233-284): m.degree AFTER the decrement
+              if (jt_is_anti(T)) { if (md == 0 && only_matched) emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, -1, mrec); }
+              else if (jt_is_semi(T)) { if (md == 0 && only_matched) emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, -1, mrec); }
+              else if (md == 0 && side_null) {
+                emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, r, mrec);
+                emit_row(o, p, st, obase + w++, RW_OP_INSERT, S, ch, -1, mrec);
+              } else emit_row(o, p, st, obase + w++, RW_OP_DELETE, S, ch, r, mrec);
             }
           }
-          m = lk & 0x7fffffffu;
-        }
+          if (p->append_only_optimize) {  // hash_join.rs:1339-1345 (regardless of the condition)
+            if (ao_rec) atomicOr(&st->err, JERR_APPEND_ONLY_MULTI);
+            ao_rec = mrec;
+          }
+          return true;
+        });
       }
       // forward rows depending on join types (hash_join.rs:1198-1210)
       if (room) {
@@ -530,8 +557,8 @@ __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __r
         }
       }
       // append-only optimisation (hash_join.rs:1222-1228): drop the matched row, do not store u
-      if (p->append_only_optimize && ao_row >= 0) {
-        rec_hdr(other, (uint32_t)ao_row)->link |= J_DEAD;
+      if (p->append_only_optimize && ao_rec) {
+        ((RecHdr*)ao_rec)->link |= J_DEAD;
         *slot_count(other, p, ms) -= 1;
         continue;
       }
@@ -546,25 +573,26 @@ __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __r
         if (created) new_keys++;
       }
       if (ins) {
-        uint32_t* hd = slot_head(own, p, own_slot);
-        rec_write(p, S, own, store_row, ch, r, *hd & 0x7fffffffu, seq_base + (uint32_t)r, own_deg ? degree : 0);
-        *hd = store_row;
+        uint8_t* irec = bkt_inline(own, p, own_slot);
+        const uint32_t ilk = ((RecHdr*)irec)->link;
+        if (ilk == IL_EMPTY || (ilk & J_DEAD)) {  // the bucket's inline record is free: the row lives in the bucket
+          rec_write(p, S, irec, ch, r, 0u, seq_base + (uint32_t)r, own_deg ? degree : 0);
+        } else {
+          uint32_t* hd = slot_head(own, p, own_slot);
+          rec_write(p, S, rec_ptr(own, store_row), ch, r, *hd & 0x7fffffffu, seq_base + (uint32_t)r, own_deg ? degree : 0);
+          *hd = store_row;
+        }
         *slot_count(own, p, own_slot) += 1;
       } else {
         bool found = false;
         if (own_slot >= 0) {
-          uint32_t m = *slot_head(own, p, own_slot) & 0x7fffffffu;
-          while (m != J_NIL) {
-            uint8_t* mrec = rec_ptr(own, m);
-            const uint32_t lk = ((RecHdr*)mrec)->link;
-            if (!(lk & J_DEAD) && pk_equal(p, S, mrec, ch, r)) {
-              ((RecHdr*)mrec)->link = lk | J_DEAD;
-              *slot_count(own, p, own_slot) -= 1;
-              found = true;
-              break;
-            }
-            m = lk & 0x7fffffffu;
-          }
+          for_each_live(own, p, own_slot, [&](uint8_t* mrec) -> bool {
+            if (!pk_equal(p, S, mrec, ch, r)) return true;
+            ((RecHdr*)mrec)->link |= J_DEAD;
+            *slot_count(own, p, own_slot) -= 1;
+            found = true;
+            return false;
+          });
         } else {
           own_slot = -2;  // the key may be created by a later insert of this group
         }
@@ -618,13 +646,15 @@ __global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const Joi
           if (!chunk_key(p, S, ch, r, kw, &nm)) {
             store[k] = ins;
             if (!ins) n_del++;
-            if (!PROBE_ONLY && ins && p->single_key && !nm)  // the own-side slot is claimed in phase 4: start fetching it
-              prefetch_l2(own.slots + (mix64(kw[0]) & (own.cap - 1)) * 2);
+            if (!PROBE_ONLY && ins && p->single_key && !nm)  // the own-side bucket is claimed in phase 4: start fetching it
+              prefetch_l2(bkt(own, (int64_t)(mix64(kw[0]) & (own.cap - 1))));
             uint64_t hc;
-            if (js_find(other, p, kw, nm, &hc) >= 0) {
-              head[k] = (uint32_t)hc & 0x7fffffffu;
+            const int64_t b = js_find(other, p, kw, nm, &hc);
+            if (b >= 0) {
+              head[k] = (uint32_t)b;  // bucket index of the matched key
               cnt[k] = (uint32_t)(hc >> 32);
-              if (cnt[k]) prefetch_l2(rec_ptr(other, head[k]));
+              const uint32_t oh = (uint32_t)hc & 0x7fffffffu;
+              if (cnt[k] > 1 && oh != J_NIL) prefetch_l2(rec_ptr(other, oh));
             }
           }
         } else {
@@ -637,43 +667,32 @@ __global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const Joi
       for (int k = 0; k < JF_R; k++) {
         if (cnt[k] == 0) continue;
         const int64_t r = base + (int64_t)k * JF_BLOCK + threadIdx.x;
-        uint32_t m = head[k], c = 0;
-        while (m != J_NIL) {
-          const uint8_t* mrec = rec_ptr(other, m);
-          const uint32_t lk = ((const RecHdr*)mrec)->link;
-          if (!(lk & J_DEAD) && cond_ok(p, S, ch, r, mrec)) c++;
-          m = lk & 0x7fffffffu;
-        }
+        uint32_t c = 0;
+        for_each_live(other, p, (int64_t)head[k], [&](uint8_t* mrec) -> bool {
+          if (cond_ok(p, S, ch, r, mrec)) c++;
+          return true;
+        });
         cnt[k] = c;
       }
     }
-    // ---- phase 2: tile scan (row order = k-major), one reservation per tile
+    // ---- phase 2: tile scan of the match counts (row order = k-major), one reservation per tile
     unsigned long long incl[JF_R];
-    unsigned int sincl[JF_R];
 #pragma unroll
     for (int k = 0; k < JF_R; k++) {
       unsigned long long v = cnt[k];
-      unsigned int sv = store[k] ? 1u : 0u;
       for (int d = 1; d < 32; d <<= 1) {
         unsigned long long t = __shfl_up_sync(0xffffffffu, v, d);
-        unsigned int ts = __shfl_up_sync(0xffffffffu, sv, d);
-        if (lane >= d) { v += t; sv += ts; }
+        if (lane >= d) v += t;
       }
       incl[k] = v;
-      sincl[k] = sv;
-      if (lane == 31) { s_cnt[k][wid] = v; s_sto[k][wid] = sv; }
+      if (lane == 31) s_cnt[k][wid] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long run = 0;
-      unsigned int srun = 0;
       for (int k = 0; k < JF_R; k++)
-        for (int w = 0; w < JF_BLOCK / 32; w++) {
-          unsigned long long t = s_cnt[k][w]; s_cnt[k][w] = run; run += t;
-          unsigned int ts = s_sto[k][w]; s_sto[k][w] = srun; srun += ts;
-        }
+        for (int w = 0; w < JF_BLOCK / 32; w++) { unsigned long long t = s_cnt[k][w]; s_cnt[k][w] = run; run += t; }
       s_out_base = run ? atomicAdd(&st->out_rows, run) : 0ull;
-      s_store_base = (!PROBE_ONLY && srun) ? (unsigned int)atomicAdd(&st->n_store, (unsigned long long)srun) : 0u;
     }
     __syncthreads();
     // ---- phase 3: emit
@@ -684,31 +703,74 @@ __global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const Joi
       int64_t pos = (int64_t)(s_out_base + s_cnt[k][wid] + incl[k] - cnt[k]);
       if (pos + cnt[k] > o.capacity) { atomicOr(&st->err, JERR_OUT_CAPACITY); continue; }
       const uint8_t oop = (op[k] == RW_OP_INSERT || op[k] == RW_OP_UPDATE_INSERT) ? RW_OP_INSERT : RW_OP_DELETE;
-      uint32_t m = head[k];
       uint32_t left = cnt[k];
-      while (m != J_NIL && left) {
-        const uint8_t* mrec = rec_ptr(other, m);
-        const uint32_t lk = ((const RecHdr*)mrec)->link;
-        if (!(lk & J_DEAD) && cond_ok(p, S, ch, r, mrec)) { emit_row(o, p, st, pos++, oop, S, ch, r, mrec); left--; }
-        m = lk & 0x7fffffffu;
-      }
+      for_each_live(other, p, (int64_t)head[k], [&](uint8_t* mrec) -> bool {
+        if (cond_ok(p, S, ch, r, mrec)) { emit_row(o, p, st, pos++, oop, S, ch, r, mrec); left--; }
+        return left != 0;
+      });
     }
-    // ---- phase 4: append to the own side
+    // ---- phase 4: append to the own side.  4a: claim the bucket and try its inline record (one
+    // 64 B read-modify-write for a key's first row); 4b: rows that lost go to the overflow store,
+    // whose ids are reserved with one atomicAdd per tile.
     if (!PROBE_ONLY) {
+      int64_t own_b[JF_R];
+      bool overflow[JF_R];
 #pragma unroll
       for (int k = 0; k < JF_R; k++) {
+        overflow[k] = false;
+        own_b[k] = -1;
         if (!store[k]) continue;
         const int64_t r = base + (int64_t)k * JF_BLOCK + threadIdx.x;
-        const uint32_t row = store_base + s_store_base + s_sto[k][wid] + sincl[k] - 1;
         uint64_t kw[RW_MAX_KEYS];
         uint32_t nm;
         chunk_key(p, S, ch, r, kw, &nm);
         bool created = false;
-        const int64_t slot = js_find_or_insert(own, p, kw, nm, &created);
+        const int64_t b = js_find_or_insert(own, p, kw, nm, &created);
         if (created) new_keys++;
-        const uint32_t old = atomicExch(slot_head(own, p, slot), row);
-        rec_write(p, S, own, row, ch, r, old & 0x7fffffffu, seq_base + (uint32_t)r, 0);
-        atomicAdd(slot_count(own, p, slot), 1u);
+        own_b[k] = b;
+        uint8_t* irec = bkt_inline(own, p, b);
+        uint32_t* ilink = &((RecHdr*)irec)->link;
+        uint32_t cur = __ldcg(ilink);
+        bool won = false;
+        while (cur == IL_EMPTY || (cur & J_DEAD)) {  // free inline record: claim it (0 = live)
+          const uint32_t old = atomicCAS(ilink, cur, 0u);
+          if (old == cur) { won = true; break; }
+          cur = old;
+        }
+        if (won) {
+          rec_write(p, S, irec, ch, r, 0u, seq_base + (uint32_t)r, 0);
+          atomicAdd(slot_count(own, p, b), 1u);
+        } else {
+          overflow[k] = true;
+        }
+      }
+      unsigned int sincl[JF_R];
+#pragma unroll
+      for (int k = 0; k < JF_R; k++) {
+        unsigned int sv = overflow[k] ? 1u : 0u;
+        for (int d = 1; d < 32; d <<= 1) {
+          unsigned int ts = __shfl_up_sync(0xffffffffu, sv, d);
+          if (lane >= d) sv += ts;
+        }
+        sincl[k] = sv;
+        if (lane == 31) s_sto[k][wid] = sv;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned int srun = 0;
+        for (int k = 0; k < JF_R; k++)
+          for (int w = 0; w < JF_BLOCK / 32; w++) { unsigned int ts = s_sto[k][w]; s_sto[k][w] = srun; srun += ts; }
+        s_store_base = srun ? (unsigned int)atomicAdd(&st->n_store, (unsigned long long)srun) : 0u;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < JF_R; k++) {
+        if (!overflow[k]) continue;
+        const int64_t r = base + (int64_t)k * JF_BLOCK + threadIdx.x;
+        const uint32_t row = store_base + s_store_base + s_sto[k][wid] + sincl[k] - 1;
+        const uint32_t old = atomicExch(slot_head(own, p, own_b[k]), row);
+        rec_write(p, S, rec_ptr(own, row), ch, r, old & 0x7fffffffu, seq_base + (uint32_t)r, 0);
+        atomicAdd(slot_count(own, p, own_b[k]), 1u);
       }
     }
     __syncthreads();
@@ -741,20 +803,18 @@ __global__ void __launch_bounds__(256) join_inner_delete_kernel(const JoinPlanDe
     if (slot >= 0) {
       const uint32_t my_seq = seq_base + (uint32_t)r;
       while (!found) {
-        uint32_t best = J_NIL, best_age = 0xffffffffu;
-        uint32_t m = *slot_head(own, p, slot) & 0x7fffffffu;
-        while (m != J_NIL) {
-          const uint8_t* mrec = rec_ptr(own, m);
-          const uint32_t lk = __ldcg(&((const RecHdr*)mrec)->link);
+        uint8_t* best = nullptr;
+        uint32_t best_age = 0xffffffffu;
+        for_each_live(own, p, slot, [&](uint8_t* mrec) -> bool {
           const uint32_t age = my_seq - ((const RecHdr*)mrec)->seq;  // in (0, 2^31) for records that arrived before r
-          if (!(lk & J_DEAD) && age != 0 && age < 0x80000000u && age < best_age && pk_equal(p, S, mrec, ch, r)) {
-            best = m;
+          if (age != 0 && age < 0x80000000u && age < best_age && pk_equal(p, S, mrec, ch, r)) {
+            best = mrec;
             best_age = age;
           }
-          m = lk & 0x7fffffffu;
-        }
-        if (best == J_NIL) break;
-        const uint32_t old = atomicOr(&rec_hdr(own, best)->link, J_DEAD);
+          return true;
+        });
+        if (!best) break;
+        const uint32_t old = atomicOr(&((RecHdr*)best)->link, J_DEAD);
         if (!(old & J_DEAD)) {
           atomicSub(slot_count(own, p, slot), 1u);
           found = true;
@@ -766,10 +826,10 @@ __global__ void __launch_bounds__(256) join_inner_delete_kernel(const JoinPlanDe
 }
 
 // ------------------------------------------------------------------ growth helpers
-__global__ void join_rehash_kernel(const uint64_t* os, uint64_t ocap, uint64_t* ns, uint64_t ncap, int SW, int KW,
+__global__ void join_rehash_kernel(const uint8_t* ob, uint64_t ocap, uint8_t* nb, uint64_t ncap, int bstride, int KW,
                                    int single_key, int n_keys) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < ocap + 2; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t* s = os + i * SW;
+    const uint64_t* s = (const uint64_t*)(ob + i * bstride);
     uint64_t dst;
     if (i >= ocap) {
       dst = ncap + (i - ocap);
@@ -780,17 +840,18 @@ __global__ void join_rehash_kernel(const uint64_t* os, uint64_t ocap, uint64_t* 
       uint64_t idx;
       if (single_key) {
         idx = mix64(w0) & mask;
-        while (atomicCAS((unsigned long long*)(ns + idx * SW), (unsigned long long)J_EMPTY, (unsigned long long)w0) != J_EMPTY) idx = (idx + 1) & mask;
+        while (atomicCAS((unsigned long long*)(nb + idx * bstride), (unsigned long long)J_EMPTY, (unsigned long long)w0) != J_EMPTY) idx = (idx + 1) & mask;
       } else {
         uint32_t nm = (uint32_t)((w0 >> 8) & 0xff);
         uint64_t h = 0x9e3779b97f4a7c15ull ^ nm;
         for (int k = 0; k < n_keys; k++) h = mix64(h ^ s[1 + k]) + 0x9e3779b97f4a7c15ull;
         idx = (h >> 17) & mask;
-        while (atomicCAS((unsigned long long*)(ns + idx * SW), 0ull, (unsigned long long)w0) != 0ull) idx = (idx + 1) & mask;
+        while (atomicCAS((unsigned long long*)(nb + idx * bstride), 0ull, (unsigned long long)w0) != 0ull) idx = (idx + 1) & mask;
       }
       dst = idx;
     }
-    for (int k = (i >= ocap ? 0 : 1); k < SW; k++) ns[dst * SW + k] = s[k];
+    uint64_t* d = (uint64_t*)(nb + dst * bstride);
+    for (int k = (i >= ocap ? 0 : 1); k < bstride / 8; k++) d[k] = s[k];  // rest of the header + the inline record
   }
 }
 
@@ -804,8 +865,8 @@ using namespace rw;
 struct JoinSideHost {
   int n_cols = 0;
   std::vector<int> types;
-  DevBuf recs, slots;
-  int stride = 0;
+  DevBuf recs, slots;  // slots = bucket array
+  int stride = 0, bstride = 0;
   uint64_t row_cap = 0;   // records allocated
   uint64_t n_rows = 0;    // records handed out (incl. dead ones)
   uint64_t slot_cap = 0;
@@ -857,16 +918,17 @@ static JoinSideDev side_dev(const rwgpu_join* h, int S) {
   const JoinSideHost& s = h->side[S];
   JoinSideDev d;
   d.recs = s.recs.as<uint8_t>();
-  d.slots = s.slots.as<uint64_t>();
+  d.buckets = s.slots.as<uint8_t>();
   d.cap = s.slot_cap;
   d.stride = s.stride;
-  d.pad = 0;
+  d.bstride = s.bstride;
   return d;
 }
 
-static int join_alloc_slots(rwgpu_join* h, DevBuf& buf, uint64_t cap) {
-  RW_CUDA(buf.reserve((cap + 2) * h->plan.SW * 8));
-  join_init_slots_kernel<<<jgrid((int64_t)cap + 2, 256), 256, 0, h->stream>>>(buf.as<uint64_t>(), cap, h->plan.SW, h->plan.KW, h->plan.single_key);
+static int join_alloc_slots(rwgpu_join* h, int S, DevBuf& buf, uint64_t cap) {
+  const int bs = h->side[S].bstride;
+  RW_CUDA(buf.reserve((cap + 2) * (size_t)bs));
+  join_init_slots_kernel<<<jgrid((int64_t)cap + 2, 256), 256, 0, h->stream>>>(buf.as<uint8_t>(), cap, bs, h->plan.KW, h->plan.single_key);
   RW_CUDA(cudaGetLastError());
   h->launches++;
   return RW_OK;
@@ -894,10 +956,10 @@ static int join_grow_slots(rwgpu_join* h, int S, uint64_t need_keys) {
   uint64_t ncap = s.slot_cap;
   while (ncap < need_keys * 4) ncap <<= 1;
   DevBuf nb;
-  int rc = join_alloc_slots(h, nb, ncap);
+  int rc = join_alloc_slots(h, S, nb, ncap);
   if (rc != RW_OK) return rc;
-  join_rehash_kernel<<<jgrid((int64_t)s.slot_cap + 2, 256), 256, 0, h->stream>>>(s.slots.as<uint64_t>(), s.slot_cap, nb.as<uint64_t>(), ncap,
-                                                                                  h->plan.SW, h->plan.KW, h->plan.single_key, h->plan.n_keys);
+  join_rehash_kernel<<<jgrid((int64_t)s.slot_cap + 2, 256), 256, 0, h->stream>>>(s.slots.as<uint8_t>(), s.slot_cap, nb.as<uint8_t>(), ncap,
+                                                                                  s.bstride, h->plan.KW, h->plan.single_key, h->plan.n_keys);
   RW_CUDA(cudaGetLastError());
   h->launches++;
   RW_CUDA(cudaStreamSynchronize(h->stream));
@@ -1212,6 +1274,11 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
   p.single_key = (p.n_keys == 1);
   p.KW = p.single_key ? 1 : 1 + p.n_keys;
   p.SW = p.KW + 1;
+  p.bhdr = (p.KW + 1) * 8;
+  for (int s2 = 0; s2 < 2; s2++) {
+    p.bstride[s2] = (p.bhdr + p.stride[s2] + 15) / 16 * 16;
+    h->side[s2].bstride = p.bstride[s2];
+  }
   p.strict = d->strict_consistency;
   h->chunk_size = std::max(d->chunk_size > 0 ? d->chunk_size : 1024, 2);  // builder.rs:44-47
   h->fast_inner = (T == RW_JOIN_INNER) && !p.append_only_optimize;
@@ -1227,7 +1294,7 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
     uint64_t cap = 1024;
     while (cap < hint * 2) cap <<= 1;
     h->side[s].slot_cap = cap;
-    rc = join_alloc_slots(h, h->side[s].slots, cap);
+    rc = join_alloc_slots(h, s, h->side[s].slots, cap);
     if (rc != RW_OK) return rc;
     rc = join_grow_store(h, s, std::max<uint64_t>(hint, 1024));
     if (rc != RW_OK) return rc;
