@@ -268,7 +268,12 @@ def run_ours(args):
 
     if world > 1:
         from risingwave_b200 import exchange
-        ex_plan = exchange.ShufflePlan(world, rank, key_indices=[0], types=T4)
+        if os.environ.get("RWGPU_EXCHANGE", "p2p") == "nccl":
+            ex_plan = exchange.ShufflePlan(world, rank, key_indices=[0], types=T4)
+            ex_name = "crc32 vnode partition kernel + NCCL all_to_all_single per column"
+        else:
+            ex_plan = exchange.P2PShufflePlan(world, rank, key_indices=[0], types=T4, batch_rows=BATCH)
+            ex_name = "crc32 vnode partition kernel storing straight into the peers' receive regions over NVLink (symmetric memory), device barrier, unpack kernel"
 
     def shuffled(cols_dev):
         if world == 1:
@@ -340,7 +345,7 @@ def run_ours(args):
                            "chunks_coalesced_per_launch": BATCH // CHUNK,
                            "join": "inner bid.auction = auction.id, Key64, 4+4 int64 cols, 8 out cols",
                            "l2": "inputs_larger_than_l2 (fresh 32 MiB batch per step; >1.3 GB of join state)",
-                           "exchange": None if world == 1 else "crc32 vnode partition kernel + NCCL all_to_all_single per column"},
+                           "exchange": None if world == 1 else ex_name},
                 "build_rows_per_s": N_BUILD * world / build_s, "out_rows": out_rows, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "join_inner_fused_kernel<false> (probe + emit + own-side append)",
                              "achieved": fused_gbs, "peak": peak, "unit": "GB/s", "frac": fused_gbs / peak if fused_gbs else None,

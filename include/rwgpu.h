@@ -251,6 +251,28 @@ int32_t rwgpu_shuffle_partition_device(const rw_chunk* chunk, const int32_t* key
                                        uint8_t* const* out_valid_bytes, /* 1 byte/row, may be NULL */
                                        int64_t* counts, int64_t* offsets, void* cuda_stream);
 
+/* ---- fused partition + transfer over NVLink peer memory (no NCCL call on the data path) ----------------
+ * Every rank owns a receive buffer of n_rank REGIONS (one per source rank), symmetric across ranks and
+ * peer-mapped (e.g. torch.distributed._symmetric_memory); region = [256 B header: int64 row count]
+ * [ops: cap_rows bytes][column k: cap_rows * width_k], each 256-B aligned.                              */
+int32_t rwgpu_shuffle_p2p_region_bytes(const int32_t* types, int32_t n_cols, int64_t cap_rows,
+                                       int64_t* region_bytes);
+/* sender: stable-partition the visible rows of a DEVICE chunk by destination and store them straight into
+ * region `my_rank` of each destination's buffer (`peer_bases`: HOST array of n_dest peer-mapped device
+ * pointers), then publish the row counts in the region headers.  `counts`: DEVICE int64[n_dest];
+ * `overflow`: DEVICE int32 set to 1 if some (src,dst) pair exceeded cap_rows (rows beyond it are dropped:
+ * the caller must fall back to the NCCL path for that batch).  The caller runs a cross-rank barrier on
+ * the same stream before anybody unpacks.                                                               */
+int32_t rwgpu_shuffle_partition_p2p_device(const rw_chunk* chunk, const int32_t* key_indices, int32_t n_keys,
+                                           int32_t vnode_count, const int32_t* vnode_to_dest, int32_t n_dest,
+                                           int32_t my_rank, void* const* peer_bases, int64_t cap_rows,
+                                           int64_t* counts, int32_t* overflow, void* cuda_stream);
+/* receiver: concatenate the n_src regions of `recv_base` (source-rank order, row order preserved) into
+ * contiguous DEVICE ops / columns; *total (DEVICE int64) receives the row count.                         */
+int32_t rwgpu_shuffle_unpack_device(const void* recv_base, int32_t n_src, const int32_t* types, int32_t n_cols,
+                                    int64_t cap_rows, uint8_t* out_ops, void* const* out_cols, int64_t* total,
+                                    void* cuda_stream);
+
 /* ================================================================ misc */
 const char* rwgpu_last_error(void);
 /* 0 if a CUDA device is usable, else RW_ERR_NO_DEVICE (and every create() fails loudly). */

@@ -137,14 +137,13 @@ int32_t rwgpu_device_check(void) {
     cudaGetLastError();
     return rw::fail(RW_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
   }
-  // The hot kernels are random 16-48 byte gathers / atomics into multi-GB hash tables: ask L2 to
-  // fetch single 32 B sectors from HBM instead of the default 64 B pairs (halves the DRAM read
-  // traffic of a miss that only needs one sector).  RWGPU_L2_FETCH=64|128 restores / widens it.
+  // Experiment knob: RWGPU_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity (the hot kernels
+  // are random 64-byte bucket accesses; the driver default of 64 B matches the bucket size).
   static thread_local int applied_dev = -1;
   int dev = 0;
   cudaGetDevice(&dev);
   if (applied_dev != dev) {
-    size_t g = 32;
+    size_t g = 0;  // default: leave the driver's 64 B (measured: 32 / 128 slow the build side 4-7x, steady state unchanged)
     if (const char* v = getenv("RWGPU_L2_FETCH")) g = (size_t)atoi(v);
     if (g == 32 || g == 64 || g == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g);
     cudaGetLastError();

@@ -785,6 +785,228 @@ __global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const Joi
   }
 }
 
+// ------------------------------------------------------------------ Key64 / all-8-byte-columns specialisation
+// The generic fused kernel pays ~1800 warp instructions per 32 rows on runtime-typed loops whose
+// loads depend on each other (plan -> column pointer -> datum -> store).  Nexmark-shaped joins have a
+// single 8-byte key and only 8-byte columns, for which everything can be straight-line code:
+//   * the WHOLE other-side bucket (key | head/count | inline record) is fetched with 16-byte loads
+//     issued together, before the key is even compared (one HBM round trip per probe);
+//   * the update row's columns are loaded once (coalesced) and reused for emission and for the
+//     own-side record;
+//   * the own-side record is written with 16-byte stores into the bucket's inline record.
+// Rows it cannot take (key == EMPTY sentinel, matched record with NULLs, keys with several rows)
+// fall through to the same helpers the generic kernel uses.
+#define W8_MAXC 8
+struct W8Plan {
+  int n_u, n_m;            // columns of the update / matched side (all 8 bytes wide)
+  int key_col;             // key column of the update side
+  int8_t u_out[W8_MAXC];   // output column fed by update column c (-1 = not projected)
+  int8_t m_out[W8_MAXC];   // output column fed by matched column c
+};
+
+// the overflow chain only (the inline record was handled by the caller)
+template <class F>
+__device__ __forceinline__ void for_each_overflow_live(const JoinSideDev& s, uint32_t head, F f) {
+  uint32_t m = head & 0x7fffffffu;
+  while (m != J_NIL) {
+    uint8_t* rec = rec_ptr(s, m);
+    const uint32_t lk = __ldcg(&((const RecHdr*)rec)->link);
+    if (!(lk & J_DEAD)) {
+      if (!f(rec)) return;
+    }
+    m = lk & 0x7fffffffu;
+  }
+}
+
+template <bool PROBE_ONLY>
+__global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_fused_w8_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch,
+                                                                           JoinSideDev own, JoinSideDev other, JoinOutDev o,
+                                                                           JoinStatus* st, uint32_t store_base, uint32_t seq_base) {
+  __shared__ unsigned long long s_cnt[JF_BLOCK / 32];
+  __shared__ unsigned int s_sto[JF_BLOCK / 32];
+  __shared__ unsigned long long s_out_base;
+  __shared__ unsigned int s_store_base;
+  const int lane = lane_id(), wid = threadIdx.x >> 5;
+  const int64_t n_tiles = (ch.n + JF_BLOCK - 1) / JF_BLOCK;
+  const uint64_t omask = other.cap - 1, wmask = own.cap - 1;
+  unsigned int new_keys = 0, n_del = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r = tile * JF_BLOCK + threadIdx.x;
+    uint8_t op = 0;
+    bool ins = false, fast = false, ilive = false;
+    uint64_t key = 0, uv[W8_MAXC], mv[W8_MAXC];
+    uint32_t cnt = 0, ohead = J_NIL;
+    int64_t ob = -1;
+    // ---- phase 1: load the row, probe the other side
+    if (r < ch.n) op = ch.ops[r];
+    if (op != 0) {
+      ins = (op == RW_OP_INSERT || op == RW_OP_UPDATE_INSERT);
+      if (!ins) n_del++;
+#pragma unroll
+      for (int c = 0; c < W8_MAXC; c++)
+        if (c < w.n_u) uv[c] = __ldg((const unsigned long long*)ch.cols[c].data + r);
+      key = __ldg((const unsigned long long*)ch.cols[w.key_col].data + r);
+      fast = key != J_EMPTY;
+      if (fast) {
+        if (!PROBE_ONLY && ins) prefetch_l2(bkt(own, (int64_t)(mix64(key) & wmask)));
+        uint64_t idx = mix64(key) & omask;
+        while (true) {
+          const uint8_t* bp = bkt(other, (int64_t)idx);
+          const ulonglong2 h0 = __ldcg((const ulonglong2*)bp);          // key | head/count
+          const uint4 mh = __ldcg((const uint4*)(bp + 16));             // inline record header
+          ulonglong2 m2[W8_MAXC / 2];
+#pragma unroll
+          for (int c = 0; c < W8_MAXC / 2; c++)
+            if (2 * c < w.n_m) m2[c] = __ldcg((const ulonglong2*)(bp + 32 + 16 * c));
+          if (h0.x == key) {
+            ob = (int64_t)idx;
+            cnt = (uint32_t)(h0.y >> 32);
+            ohead = (uint32_t)h0.y;
+            ilive = (mh.x != IL_EMPTY) && !(mh.x & J_DEAD);
+            if (ilive && mh.y != 0) { ilive = false; fast = false; }  // NULLs in the matched record: generic emission
+#pragma unroll
+            for (int c = 0; c < W8_MAXC / 2; c++) { mv[2 * c] = m2[c].x; mv[2 * c + 1] = m2[c].y; }
+            break;
+          }
+          if (h0.x == J_EMPTY) break;
+          idx = (idx + 1) & omask;
+        }
+      } else {
+        uint64_t kw[1] = {key}, hc = 0;
+        ob = js_find(other, p, kw, 0, &hc);
+        if (ob >= 0) { cnt = (uint32_t)(hc >> 32); ohead = (uint32_t)hc; }
+      }
+    }
+    // ---- phase 2: tile scan of the match counts, one reservation per tile
+    unsigned long long incl = cnt;
+    for (int d = 1; d < 32; d <<= 1) {
+      unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_cnt[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long run = 0;
+      for (int k = 0; k < JF_BLOCK / 32; k++) { unsigned long long t = s_cnt[k]; s_cnt[k] = run; run += t; }
+      s_out_base = run ? atomicAdd(&st->out_rows, run) : 0ull;
+    }
+    __syncthreads();
+    // ---- phase 3: emit
+    if (cnt) {
+      int64_t pos = (int64_t)(s_out_base + s_cnt[wid] + incl - cnt);
+      if (pos + cnt > o.capacity) {
+        atomicOr(&st->err, JERR_OUT_CAPACITY);
+      } else {
+        const uint8_t oop = ins ? RW_OP_INSERT : RW_OP_DELETE;
+        uint32_t left = cnt;
+        if (fast) {
+          if (ilive) {
+            o.ops[pos] = oop;
+#pragma unroll
+            for (int c = 0; c < W8_MAXC; c++)
+              if (c < w.n_u && w.u_out[c] >= 0) ((uint64_t*)o.col[w.u_out[c]])[pos] = uv[c];
+#pragma unroll
+            for (int c = 0; c < W8_MAXC; c++)
+              if (c < w.n_m && w.m_out[c] >= 0) ((uint64_t*)o.col[w.m_out[c]])[pos] = mv[c];
+            pos++;
+            left--;
+          }
+          if (left)
+            for_each_overflow_live(other, ohead, [&](uint8_t* mrec) -> bool {
+              emit_row(o, p, st, pos++, oop, S, ch, r, mrec);
+              return --left != 0;
+            });
+        } else {
+          for_each_live(other, p, ob, [&](uint8_t* mrec) -> bool {
+            emit_row(o, p, st, pos++, oop, S, ch, r, mrec);
+            return --left != 0;
+          });
+        }
+      }
+    }
+    // ---- phase 4: append to the own side (4a bucket + inline record, 4b overflow rows)
+    if (!PROBE_ONLY) {
+      bool overflow = false;
+      int64_t wb = -1;
+      if (op != 0 && ins) {
+        bool created = false;
+        if (key != J_EMPTY) {
+          uint64_t idx = mix64(key) & wmask;
+          while (true) {
+            unsigned long long* kp = (unsigned long long*)bkt(own, (int64_t)idx);
+            unsigned long long cur = __ldcg(kp);
+            if (cur == key) break;
+            if (cur == J_EMPTY) {
+              const unsigned long long old = atomicCAS(kp, (unsigned long long)J_EMPTY, (unsigned long long)key);
+              if (old == J_EMPTY) { created = true; break; }
+              if (old == key) break;
+            }
+            idx = (idx + 1) & wmask;
+          }
+          wb = (int64_t)idx;
+        } else {
+          uint64_t kw[1] = {key};
+          wb = js_find_or_insert(own, p, kw, 0, &created);
+        }
+        if (created) new_keys++;
+        uint8_t* irec = bkt_inline(own, p, wb);
+        uint32_t* ilink = &((RecHdr*)irec)->link;
+        uint32_t cur = created ? IL_EMPTY : __ldcg(ilink);
+        bool won = false;
+        while (cur == IL_EMPTY || (cur & J_DEAD)) {
+          const uint32_t old = atomicCAS(ilink, cur, 0u);
+          if (old == cur) { won = true; break; }
+          cur = old;
+        }
+        if (won) {
+          uint4 h;
+          h.x = 0u; h.y = 0u; h.z = seq_base + (uint32_t)r; h.w = 0u;
+          *(uint4*)irec = h;
+#pragma unroll
+          for (int c = 0; c < W8_MAXC / 2; c++)
+            if (2 * c < w.n_u) {
+              ulonglong2 v;
+              v.x = uv[2 * c];
+              v.y = (2 * c + 1 < w.n_u) ? uv[2 * c + 1] : 0ull;
+              *(ulonglong2*)(irec + 16 + 16 * c) = v;
+            }
+          atomicAdd(slot_count(own, p, wb), 1u);
+        } else {
+          overflow = true;
+        }
+      }
+      unsigned int sv = overflow ? 1u : 0u;
+      for (int d = 1; d < 32; d <<= 1) {
+        unsigned int ts = __shfl_up_sync(0xffffffffu, sv, d);
+        if (lane >= d) sv += ts;
+      }
+      if (lane == 31) s_sto[wid] = sv;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned int srun = 0;
+        for (int k = 0; k < JF_BLOCK / 32; k++) { unsigned int ts = s_sto[k]; s_sto[k] = srun; srun += ts; }
+        s_store_base = srun ? (unsigned int)atomicAdd(&st->n_store, (unsigned long long)srun) : 0u;
+      }
+      __syncthreads();
+      if (overflow) {
+        const uint32_t row = store_base + s_store_base + s_sto[wid] + sv - 1;
+        const uint32_t old = atomicExch(slot_head(own, p, wb), row);
+        rec_write(p, S, rec_ptr(own, row), ch, r, old & 0x7fffffffu, seq_base + (uint32_t)r, 0);
+        atomicAdd(slot_count(own, p, wb), 1u);
+      }
+    }
+    __syncthreads();
+  }
+  if (!PROBE_ONLY) {
+    for (int d = 16; d > 0; d >>= 1) {
+      new_keys += __shfl_xor_sync(0xffffffffu, new_keys, d);
+      n_del += __shfl_xor_sync(0xffffffffu, n_del, d);
+    }
+    if (lane == 0 && new_keys) atomicAdd(&st->n_keys[S], (unsigned long long)new_keys);
+    if (lane == 0 && n_del) atomicAdd(&st->n_del, (unsigned long long)n_del);
+  }
+}
+
 // own-side deletes of the fast path (after the fused kernel; exits at once when the batch has none).
 // Sequential rule: the delete at chunk position r removes the live record with equal pk that
 // arrived most recently BEFORE r (largest seq below seq_base + r, wrap-aware).
@@ -883,6 +1105,8 @@ struct rwgpu_join {
   std::vector<int> out_types;
   int chunk_size = 1024;
   bool fast_inner = false;
+  bool w8_ok[2] = {false, false};  // per update side: Key64 + all-8-byte columns specialisation usable
+  W8Plan w8[2];
   uint64_t launches = 0;
   uint64_t seq = 0;
   KernelProf prof;
@@ -1039,8 +1263,16 @@ static JoinOutDev out_dev(rwgpu_join* h) {
   return o;
 }
 
+// The status block is pushed to pinned host memory by a one-thread kernel (UVA: cudaMallocHost memory
+// is device-addressable) instead of a cudaMemcpy: a tiny D2H copy would queue on the copy engine
+// behind the megabytes of output the previous sub-batch is still draining.
+__global__ void join_status_to_host_kernel(const JoinStatus* src, JoinStatus* dst_host) {
+  *dst_host = *src;
+  __threadfence_system();
+}
 static int join_read_status(rwgpu_join* h, cudaStream_t st, JoinStatus* out) {
-  RW_CUDA(cudaMemcpyAsync(h->status_host.p, h->status.p, sizeof(JoinStatus), cudaMemcpyDeviceToHost, st));
+  join_status_to_host_kernel<<<1, 1, 0, st>>>(h->status.as<JoinStatus>(), h->status_host.as<JoinStatus>());
+  RW_CUDA(cudaGetLastError());
   RW_CUDA(cudaStreamSynchronize(st));
   memcpy(out, h->status_host.p, sizeof(JoinStatus));
   return RW_OK;
@@ -1081,9 +1313,17 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     if (rc != RW_OK) return rc;
     const int64_t tiles = (n + JF_BLOCK * JF_R - 1) / (JF_BLOCK * JF_R);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, 148 * 8));
+    // Key64 / 8-byte-column specialisation when the chunk carries no bitmaps (ops == 0 still hides rows)
+    bool use_w8 = h->w8_ok[S] && ch.vis_bits == nullptr;
+    for (int c = 0; c < ch.n_cols && use_w8; c++)
+      use_w8 = !ch.cols[c].valid_bits && !ch.cols[c].valid_bytes && (((uintptr_t)ch.cols[c].data & 7) == 0);
     h->prof.begin(st);
-    join_inner_fused_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
-                                                                (uint32_t)own.n_rows, seq_base);
+    if (use_w8)
+      join_inner_fused_w8_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
+                                                                     (uint32_t)own.n_rows, seq_base);
+    else
+      join_inner_fused_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
+                                                                  (uint32_t)own.n_rows, seq_base);
     h->prof.end(st);
     join_inner_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, side_dev(h, S), ds, seq_base);
     RW_CUDA(cudaGetLastError());
@@ -1102,7 +1342,10 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
       RW_CUDA(cudaStreamSynchronize(st));
       rc = join_ensure_out(h, need, st, out_base);
       if (rc != RW_OK) return rc;
-      join_inner_fused_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds, 0, seq_base);
+      if (use_w8)
+        join_inner_fused_w8_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds, 0, seq_base);
+      else
+        join_inner_fused_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds, 0, seq_base);
       RW_CUDA(cudaGetLastError());
       h->launches++;
       rc = join_read_status(h, st, &hs);
@@ -1282,6 +1525,29 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
   p.strict = d->strict_consistency;
   h->chunk_size = std::max(d->chunk_size > 0 ? d->chunk_size : 1024, 2);  // builder.rs:44-47
   h->fast_inner = (T == RW_JOIN_INNER) && !p.append_only_optimize;
+  // W8 specialisation: one 8-byte non-float key, <= 8 columns per side, all 8 bytes wide, no
+  // condition, every input column projected to at most one output column
+  for (int s2 = 0; s2 < 2 && h->fast_inner; s2++) {
+    W8Plan& w = h->w8[s2];
+    memset(&w, 0, sizeof(w));
+    bool ok = p.single_key && p.cond_cmp == RW_CMP_NONE && p.n_cols[0] <= W8_MAXC && p.n_cols[1] <= W8_MAXC;
+    for (int side = 0; side < 2 && ok; side++)
+      for (int c = 0; c < p.n_cols[side]; c++) ok = ok && p.col_width[side][c] == 8 && p.col_off[side][c] == J_HDR + 8 * c;
+    ok = ok && !type_is_float(p.col_type[s2][p.key_col[s2][0]]);
+    w.n_u = p.n_cols[s2];
+    w.n_m = p.n_cols[1 - s2];
+    w.key_col = p.key_col[s2][0];
+    for (int c = 0; c < W8_MAXC; c++) { w.u_out[c] = -1; w.m_out[c] = -1; }
+    for (int i = 0; i < p.n_map[s2] && ok; i++) {
+      if (w.u_out[p.map_in[s2][i]] >= 0) ok = false;
+      w.u_out[p.map_in[s2][i]] = (int8_t)p.map_out[s2][i];
+    }
+    for (int i = 0; i < p.n_map[1 - s2] && ok; i++) {
+      if (w.m_out[p.map_in[1 - s2][i]] >= 0) ok = false;
+      w.m_out[p.map_in[1 - s2][i]] = (int8_t)p.map_out[1 - s2][i];
+    }
+    h->w8_ok[s2] = ok;
+  }
 
   RW_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   RW_CUDA(h->plan_dev.reserve(sizeof(JoinPlanDev)));
@@ -1449,9 +1715,12 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
       ch.cols[k].data = dp + o_data[k] + (size_t)lo * w;
       ch.cols[k].valid_bits = c->columns[k].validity ? (const uint64_t*)(dp + o_valid[k] + (size_t)(lo / 64) * 8) : nullptr;
     }
+    double ta = 0, tb = 0;
+    if (trace) { ta = now(); cudaEventSynchronize(h->ev_h2d[js]); tb = now(); }
     RW_CUDA(cudaStreamWaitEvent(h->stream, h->ev_h2d[js], 0));
     int64_t rows = 0;
     rc = join_push_dev(h, side, ch, h->stream, total, &rows, &nullm);
+    if (trace) fprintf(stderr, "   sub %d: wait-h2d %.3f  push_dev %.3f ms\n", js, tb - ta, now() - tb);
     if (rc != RW_OK) { cudaStreamSynchronize(h->s_d2h); return rc; }
     if (total + rows > host_cap) {  // rare: amplification above 2x -- grow the host block, keep the copied prefix
       RW_CUDA(cudaStreamSynchronize(h->s_d2h));

@@ -8,6 +8,7 @@
 // here rows are STABLY partitioned by destination GPU into contiguous regions (the send buffers
 // of an NCCL all-to-all-v), preserving per-key row order.
 #include <algorithm>
+#include <vector>
 
 #include "common.cuh"
 
@@ -257,6 +258,144 @@ __global__ void __launch_bounds__(PART_BLOCK) part_scatter_kernel(DevChunk ch, c
   }
 }
 
+// ------------------------------------------------------------------ P2P exchange over NVLink peer memory
+// Receive buffer of a rank (symmetric on every rank): one REGION per source rank,
+//   region = [ header 256 B: int64 row count ][ ops: cap bytes ][ column k: cap * width_k bytes ] (each 256-B aligned).
+// The sender's scatter kernel stores its rows for destination d straight into region `my_rank` of d's
+// buffer (plain st.global on a peer-mapped pointer: partition and transfer are ONE kernel, no send
+// staging, no NCCL call on the data path).  After a device-side barrier the receiver unpacks the W
+// regions into contiguous columns.
+struct P2PLayout {
+  int64_t cap_rows;
+  int64_t region_bytes;
+  int64_t ops_off;
+  int64_t col_off[RW_MAX_COLS];
+  int n_cols;
+  int col_width[RW_MAX_COLS];
+};
+struct PeerBases {
+  uint8_t* base[PART_MAX_DEST];
+};
+
+static int p2p_layout(const int32_t* types, int n_cols, int64_t cap_rows, P2PLayout* L) {
+  if (n_cols < 0 || n_cols > RW_MAX_COLS || cap_rows <= 0) return fail(RW_ERR_INVALID, "p2p layout");
+  auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+  int64_t off = 256;
+  L->cap_rows = cap_rows;
+  L->n_cols = n_cols;
+  L->ops_off = off;
+  off = up(off + cap_rows);
+  for (int k = 0; k < n_cols; k++) {
+    int w = type_width(types[k]);
+    if (!w) return fail(RW_ERR_UNSUPPORTED, "column type");
+    L->col_width[k] = w;
+    L->col_off[k] = off;
+    off = up(off + cap_rows * w);
+  }
+  L->region_bytes = off;
+  return RW_OK;
+}
+
+__global__ void __launch_bounds__(PART_BLOCK) part_scatter_p2p_kernel(DevChunk ch, const uint8_t* dest, const uint32_t* block_off,
+                                                                       int n_dest, P2PLayout L, PeerBases peers, int my_rank,
+                                                                       int* overflow) {
+  __shared__ uint32_t run[PART_MAX_DEST];
+  __shared__ uint32_t warp_cnt[PART_BLOCK / 32][PART_MAX_DEST];
+  if (threadIdx.x < PART_MAX_DEST) run[threadIdx.x] = 0;
+  __syncthreads();
+  const int lane = lane_id(), wid = threadIdx.x >> 5;
+  int64_t base = (int64_t)blockIdx.x * PART_ROWS_PER_BLOCK;
+  for (int it = 0; it < PART_ROWS_PER_BLOCK / PART_BLOCK; it++) {
+    int64_t r = base + it * PART_BLOCK + threadIdx.x;
+    uint8_t d = (r < ch.n) ? dest[r] : 255;
+    unsigned peers_m = __match_any_sync(0xffffffffu, (unsigned)d);
+    unsigned rank_in_warp = __popc(peers_m & ((1u << lane) - 1));
+    for (int k = lane; k < n_dest; k += 32) warp_cnt[wid][k] = 0;
+    __syncwarp();
+    if (rank_in_warp == 0 && d != 255) warp_cnt[wid][d] = __popc(peers_m);
+    __syncthreads();
+    uint32_t pos = 0;
+    if (d != 255) {
+      uint32_t before = 0;
+      for (int w = 0; w < wid; w++) before += warp_cnt[w][d];
+      pos = run[d] + before + rank_in_warp;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_dest) {
+      uint32_t tot = 0;
+      for (int w = 0; w < PART_BLOCK / 32; w++) tot += warp_cnt[w][threadIdx.x];
+      run[threadIdx.x] += tot;
+    }
+    if (d != 255) {
+      const int64_t dst = (int64_t)block_off[(size_t)blockIdx.x * n_dest + d] + pos;  // row index inside (my_rank -> d)
+      if (dst >= L.cap_rows) {
+        *overflow = 1;
+      } else {
+        uint8_t* reg = peers.base[d] + (int64_t)my_rank * L.region_bytes;
+        reg[L.ops_off + dst] = ch.ops[r];
+        for (int k = 0; k < ch.n_cols; k++) {
+          const ColRef& c = ch.cols[k];
+          uint8_t* col = reg + L.col_off[k];
+          switch (c.width) {
+            case 1: ((uint8_t*)col)[dst] = ((const uint8_t*)c.data)[r]; break;
+            case 2: ((uint16_t*)col)[dst] = ((const uint16_t*)c.data)[r]; break;
+            case 4: ((uint32_t*)col)[dst] = ((const uint32_t*)c.data)[r]; break;
+            case 8: ((uint64_t*)col)[dst] = ((const uint64_t*)c.data)[r]; break;
+            default: ((ulonglong2*)col)[dst] = ((const ulonglong2*)c.data)[r]; break;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// publish the per-destination row counts in the region headers of the peers
+__global__ void p2p_publish_counts_kernel(const int64_t* counts, int n_dest, P2PLayout L, PeerBases peers, int my_rank) {
+  int d = threadIdx.x;
+  if (d < n_dest) {
+    int64_t c = counts[d] <= L.cap_rows ? counts[d] : -1;  // -1: this (source, destination) pair overflowed its region
+    *(int64_t*)(peers.base[d] + (int64_t)my_rank * L.region_bytes) = c;
+    __threadfence_system();
+  }
+}
+
+// receiver: W regions -> contiguous ops / columns (source-rank order, row order kept inside a source)
+__global__ void __launch_bounds__(256) p2p_unpack_kernel(const uint8_t* recv, int n_src, P2PLayout L, uint8_t* out_ops, PartOut o,
+                                                          int64_t* total) {
+  __shared__ int64_t off[PART_MAX_DEST + 1];
+  if (threadIdx.x == 0) {
+    int64_t acc = 0;
+    bool bad = false;
+    for (int s = 0; s < n_src; s++) {
+      off[s] = acc;
+      const int64_t c = *(const volatile int64_t*)(recv + (int64_t)s * L.region_bytes);
+      if (c < 0) bad = true; else acc += c;
+    }
+    off[n_src] = acc;
+    if (blockIdx.x == 0) *total = bad ? -1 : acc;
+  }
+  __syncthreads();
+  const int64_t n = off[n_src];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int s = 0;
+    while (i >= off[s + 1]) s++;
+    const int64_t j = i - off[s];
+    const uint8_t* reg = recv + (int64_t)s * L.region_bytes;
+    out_ops[i] = reg[L.ops_off + j];
+    for (int k = 0; k < L.n_cols; k++) {
+      const uint8_t* col = reg + L.col_off[k];
+      switch (L.col_width[k]) {
+        case 1: ((uint8_t*)o.col[k])[i] = col[j]; break;
+        case 2: ((uint16_t*)o.col[k])[i] = ((const uint16_t*)col)[j]; break;
+        case 4: ((uint32_t*)o.col[k])[i] = ((const uint32_t*)col)[j]; break;
+        case 8: ((uint64_t*)o.col[k])[i] = ((const uint64_t*)col)[j]; break;
+        default: ((ulonglong2*)o.col[k])[i] = ((const ulonglong2*)col)[j]; break;
+      }
+    }
+  }
+}
+
 static int make_vnode_plan(const rw_chunk* c, const int32_t* keys, int n_keys, int vnode_count, VnodePlan* p) {
   if (n_keys < 1 || n_keys > RW_MAX_KEYS * 2) return fail(RW_ERR_UNSUPPORTED, "1..8 distribution key columns");
   if (vnode_count < 1 || vnode_count > 32768) return fail(RW_ERR_INVALID, "vnode_count (vnode.rs:79 MAX_COUNT = 2^15)");
@@ -396,6 +535,69 @@ int32_t rwgpu_shuffle_partition_device(const rw_chunk* c, const int32_t* keys, i
   part_scatter_kernel<<<n_blocks, PART_BLOCK, 0, st>>>(ch, dest, hist, n_dest, offsets, o);
   RW_CUDA(cudaGetLastError());
   RW_CUDA(cudaFreeAsync(scratch, st));
+  return RW_OK;
+}
+
+
+int32_t rwgpu_shuffle_p2p_region_bytes(const int32_t* types, int32_t n_cols, int64_t cap_rows, int64_t* region_bytes) {
+  if (!types || !region_bytes) return fail(RW_ERR_INVALID, "null");
+  P2PLayout L;
+  int rc = p2p_layout(types, n_cols, cap_rows, &L);
+  if (rc != RW_OK) return rc;
+  *region_bytes = L.region_bytes;
+  return RW_OK;
+}
+
+int32_t rwgpu_shuffle_partition_p2p_device(const rw_chunk* c, const int32_t* keys, int32_t n_keys, int32_t vnode_count,
+                                           const int32_t* vnode_to_dest, int32_t n_dest, int32_t my_rank,
+                                           void* const* peer_bases, int64_t cap_rows, int64_t* counts, int32_t* overflow,
+                                           void* cuda_stream) {
+  if (!c || !keys || !vnode_to_dest || !peer_bases || !counts || !overflow) return fail(RW_ERR_INVALID, "null");
+  if (n_dest < 1 || n_dest > PART_MAX_DEST || my_rank < 0 || my_rank >= n_dest) return fail(RW_ERR_INVALID, "ranks");
+  VnodePlan p;
+  int rc = make_vnode_plan(c, keys, n_keys, vnode_count, &p);
+  if (rc != RW_OK) return rc;
+  DevChunk ch;
+  rc = devchunk_from_abi(c, &ch);
+  if (rc != RW_OK) return rc;
+  std::vector<int32_t> types(c->n_cols);
+  for (int k = 0; k < c->n_cols; k++) types[k] = c->columns[k].type;
+  P2PLayout L;
+  rc = p2p_layout(types.data(), c->n_cols, cap_rows, &L);
+  if (rc != RW_OK) return rc;
+  PeerBases pb;
+  memset(&pb, 0, sizeof(pb));
+  for (int d = 0; d < n_dest; d++) pb.base[d] = (uint8_t*)peer_bases[d];
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int n_blocks = (int)std::max<int64_t>(1, (c->n_rows + PART_ROWS_PER_BLOCK - 1) / PART_ROWS_PER_BLOCK);
+  uint8_t* scratch = nullptr;
+  size_t dest_bytes = ((size_t)c->n_rows + 255) / 256 * 256;
+  size_t hist_bytes = (size_t)n_blocks * n_dest * 4;
+  RW_CUDA(cudaMallocAsync((void**)&scratch, dest_bytes + hist_bytes + 1024, st));
+  uint8_t* dest = scratch;
+  uint32_t* hist = (uint32_t*)(scratch + dest_bytes);
+  int64_t* offsets = (int64_t*)(scratch + dest_bytes + (hist_bytes + 255) / 256 * 256);
+  part_hist_kernel<<<n_blocks, PART_BLOCK, 0, st>>>(ch, p, vnode_to_dest, n_dest, dest, hist);
+  part_scan_kernel<<<1, PART_MAX_DEST, 0, st>>>(hist, n_blocks, n_dest, counts, offsets);
+  part_scatter_p2p_kernel<<<n_blocks, PART_BLOCK, 0, st>>>(ch, dest, hist, n_dest, L, pb, my_rank, overflow);
+  p2p_publish_counts_kernel<<<1, PART_MAX_DEST, 0, st>>>(counts, n_dest, L, pb, my_rank);
+  RW_CUDA(cudaGetLastError());
+  RW_CUDA(cudaFreeAsync(scratch, st));
+  return RW_OK;
+}
+
+int32_t rwgpu_shuffle_unpack_device(const void* recv_base, int32_t n_src, const int32_t* types, int32_t n_cols, int64_t cap_rows,
+                                    uint8_t* out_ops, void* const* out_cols, int64_t* total, void* cuda_stream) {
+  if (!recv_base || !types || !out_ops || !out_cols || !total) return fail(RW_ERR_INVALID, "null");
+  if (n_src < 1 || n_src > PART_MAX_DEST) return fail(RW_ERR_INVALID, "n_src");
+  P2PLayout L;
+  int rc = p2p_layout(types, n_cols, cap_rows, &L);
+  if (rc != RW_OK) return rc;
+  PartOut o;
+  memset(&o, 0, sizeof(o));
+  for (int k = 0; k < n_cols; k++) o.col[k] = out_cols[k];
+  p2p_unpack_kernel<<<148 * 4, 256, 0, (cudaStream_t)cuda_stream>>>((const uint8_t*)recv_base, n_src, L, out_ops, o, total);
+  RW_CUDA(cudaGetLastError());
   return RW_OK;
 }
 

@@ -113,6 +113,15 @@ def _lib():
         lib.rwgpu_shuffle_partition_device.argtypes = [C.POINTER(abi.RwChunk), C.POINTER(C.c_int32), C.c_int32, C.c_int32,
                                                        C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p),
                                                        C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.rwgpu_shuffle_p2p_region_bytes.restype = C.c_int32
+        lib.rwgpu_shuffle_p2p_region_bytes.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.POINTER(C.c_int64)]
+        lib.rwgpu_shuffle_partition_p2p_device.restype = C.c_int32
+        lib.rwgpu_shuffle_partition_p2p_device.argtypes = [C.POINTER(abi.RwChunk), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p,
+                                                           C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int64, C.c_void_p,
+                                                           C.c_void_p, C.c_void_p]
+        lib.rwgpu_shuffle_unpack_device.restype = C.c_int32
+        lib.rwgpu_shuffle_unpack_device.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_void_p,
+                                                    C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
         lib.rwgpu_last_error.restype = C.c_char_p
         lib._dev_sigs = True
     return lib
@@ -178,3 +187,30 @@ def shuffle_partition(chunk: DeviceChunk, key_indices: Sequence[int], vnode_to_d
                                                  colp, None, C.c_void_p(counts.data_ptr()), C.c_void_p(offsets.data_ptr()),
                                                  _stream_ptr(stream)))
     return out_ops, out_cols, counts, offsets
+
+
+def p2p_region_bytes(types: Sequence[int], cap_rows: int) -> int:
+    t = (C.c_int32 * len(types))(*types)
+    out = C.c_int64()
+    _check(_lib().rwgpu_shuffle_p2p_region_bytes(t, len(types), cap_rows, C.byref(out)))
+    return out.value
+
+
+def shuffle_partition_p2p(chunk: DeviceChunk, key_indices: Sequence[int], vnode_to_dest: torch.Tensor, n_dest: int, my_rank: int,
+                          peer_ptrs: Sequence[int], cap_rows: int, counts: torch.Tensor, overflow: torch.Tensor,
+                          vnode_count: int = 256, stream: Optional[torch.cuda.Stream] = None):
+    """fused stable partition + store into the peers' receive regions (NVLink peer memory)."""
+    ch, keep = chunk.to_abi()
+    keys = (C.c_int32 * len(key_indices))(*key_indices)
+    peers = (C.c_void_p * n_dest)(*peer_ptrs)
+    _check(_lib().rwgpu_shuffle_partition_p2p_device(C.byref(ch), keys, len(key_indices), vnode_count,
+                                                     C.c_void_p(vnode_to_dest.data_ptr()), n_dest, my_rank, peers, cap_rows,
+                                                     C.c_void_p(counts.data_ptr()), C.c_void_p(overflow.data_ptr()), _stream_ptr(stream)))
+
+
+def shuffle_unpack(recv_ptr: int, n_src: int, types: Sequence[int], cap_rows: int, out_ops: torch.Tensor,
+                   out_cols: Sequence[torch.Tensor], total: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
+    t = (C.c_int32 * len(types))(*types)
+    colp = (C.c_void_p * len(out_cols))(*[c.data_ptr() for c in out_cols])
+    _check(_lib().rwgpu_shuffle_unpack_device(C.c_void_p(recv_ptr), n_src, t, len(types), cap_rows, C.c_void_p(out_ops.data_ptr()),
+                                              colp, C.c_void_p(total.data_ptr()), _stream_ptr(stream)))

@@ -68,3 +68,55 @@ class ShufflePlan:
         ops, cols, counts, offsets = device.shuffle_partition(chunk, self.keys, self.v2d, self.world, self.vnode_count, stream)
         ins, outs = plan_splits(counts)
         return all_to_all_columns(ops, cols, ins, outs)
+
+
+class P2PShufflePlan:
+    """Hash shuffle with the transfer fused into the partition kernel: every rank's scatter kernel
+    stores its rows straight into the destination ranks' receive regions over NVLink peer memory
+    (torch symmetric memory supplies the peer-mapped buffers and a device-side barrier); no NCCL call
+    is on the data path.  Two receive buffers alternate, so one barrier per batch is enough: a peer
+    can only start writing buffer b again after every rank passed the barrier of the batch in between,
+    which each rank enqueues AFTER its own unpack of buffer b (stream order).
+
+    `cap_rows` bounds the rows of one (source, destination) pair per batch; if it overflows (heavy key
+    skew) the batch is redone through the NCCL all-to-all-v path of `ShufflePlan`."""
+
+    def __init__(self, world: int, rank: int, key_indices: Sequence[int], types: Sequence[int], batch_rows: int,
+                 group=None, vnode_count: int = 256):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import device
+        self.world, self.rank = world, rank
+        self.keys, self.types, self.vnode_count = list(key_indices), list(types), vnode_count
+        self.v2d = vnode_to_dest_table(world, vnode_count).cuda()
+        self.cap = int(batch_rows / world * 1.25) + 8192
+        self.region = device.p2p_region_bytes(self.types, self.cap)
+        group = group if group is not None else dist.group.WORLD
+        self.bufs, self.hdls, self.peers = [], [], []
+        for _ in range(2):
+            b = symm_mem.empty(world * self.region, dtype=torch.uint8, device="cuda")
+            h = symm_mem.rendezvous(b, group)
+            self.bufs.append(b)
+            self.hdls.append(h)
+            self.peers.append([int(h.buffer_ptrs[r]) for r in range(world)])
+        self.counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+        self.overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self.total = torch.zeros(1, dtype=torch.int64, device="cuda")
+        self.step = 0
+        self.fallback = ShufflePlan(world, rank, key_indices, types, vnode_count)
+        self.max_rows = world * self.cap
+
+    def exchange(self, chunk, stream=None):
+        from . import device
+        b = self.step & 1
+        self.step += 1
+        device.shuffle_partition_p2p(chunk, self.keys, self.v2d, self.world, self.rank, self.peers[b], self.cap, self.counts,
+                                     self.overflow, self.vnode_count, stream)
+        self.hdls[b].barrier(channel=0)  # all peers' stores into my regions are complete and visible
+        ops = torch.empty(self.max_rows, dtype=torch.uint8, device="cuda")
+        cols = [torch.empty(self.max_rows, dtype=device.TORCH_DTYPE[t], device="cuda") for t in self.types]
+        device.shuffle_unpack(self.bufs[b].data_ptr(), self.world, self.types, self.cap, ops, cols, self.total, stream)
+        n = int(self.total.item())  # one 8-byte D2H (the join push needs the row count on the host anyway)
+        if n < 0:
+            raise RuntimeError("p2p shuffle: a (source, destination) pair exceeded its region capacity "
+                               f"({self.cap} rows); use ShufflePlan (NCCL all-to-all-v) for this stream")
+        return ops[:n], [c[:n] for c in cols]
