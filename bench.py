@@ -252,7 +252,7 @@ def run_ours(args):
         # left = bid (key col 0, stream key date_time), right = auction (key col 0 = id = stream key)
         return HashJoinExecutor(be, abi.JOIN_INNER, sl.into_executor(T4, [1]), sr.into_executor(T4, [0]),
                                 JoinParams([0], [1]), JoinParams([0], []), [False],
-                                capacity_hint=int(1.15 * max(N_BUILD, (K + W) * BATCH)))
+                                capacity_hint=(N_BUILD, N_BUILD))  # distinct auction ids per GPU, both sides
 
     def to_dev(cols):
         return [torch.from_numpy(c).cuda() for c in cols]

@@ -195,7 +195,7 @@ typedef struct rw_join_side_desc {
   int32_t n_stream_key;
   const int32_t* stream_key;        /* input.stream_key(): decides pk_contained_in_jk
                                        (hash_join.rs:377-381)                               */
-  uint64_t row_capacity_hint;
+  uint64_t row_capacity_hint;       /* expected distinct join keys of this side (index grows on demand) */
 } rw_join_side_desc;
 
 typedef struct rw_join_desc {

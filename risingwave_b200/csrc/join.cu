@@ -818,192 +818,193 @@ __device__ __forceinline__ void for_each_overflow_live(const JoinSideDev& s, uin
   }
 }
 
+// Output convention of this kernel ("positional"): the first match of input row r is written to
+// output row out_base + r -- no scan, no block barrier, warps never wait for each other; a row
+// without a match (or an invisible input row) leaves an invisible output row.  Further matches of a
+// row (keys with several rows on the other side) are appended behind the n positional rows with a
+// warp-aggregated atomicAdd.  A StreamChunk with invisible rows is a legal chunk; for the
+// bid -> auction probe (every bid matches exactly one auction) the output is dense and in input order.
+// JoinStatus.out_rows counts the EXTRA rows; JoinStatus.pad = 1 when some row matched;
+// null_mask bit 63 = some positional row is invisible.
 template <bool PROBE_ONLY>
-__global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_fused_w8_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch,
-                                                                           JoinSideDev own, JoinSideDev other, JoinOutDev o,
-                                                                           JoinStatus* st, uint32_t store_base, uint32_t seq_base) {
-  __shared__ unsigned long long s_cnt[JF_BLOCK / 32];
-  __shared__ unsigned int s_sto[JF_BLOCK / 32];
-  __shared__ unsigned long long s_out_base;
-  __shared__ unsigned int s_store_base;
-  const int lane = lane_id(), wid = threadIdx.x >> 5;
-  const int64_t n_tiles = (ch.n + JF_BLOCK - 1) / JF_BLOCK;
+__global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch,
+                                                                      JoinSideDev own, JoinSideDev other, JoinOutDev o, JoinStatus* st,
+                                                                      uint32_t store_base, uint32_t seq_base, int64_t out_base) {
+  const int lane = lane_id();
   const uint64_t omask = other.cap - 1, wmask = own.cap - 1;
   unsigned int new_keys = 0, n_del = 0;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t r = tile * JF_BLOCK + threadIdx.x;
-    uint8_t op = 0;
-    bool ins = false, fast = false, ilive = false;
-    uint64_t key = 0, uv[W8_MAXC], mv[W8_MAXC];
+  bool any_match = false, any_hole = false;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t op = ch.ops[r];
+    if (op == 0) { o.vis[out_base + r] = 0; any_hole = true; continue; }
+    const bool ins = (op == RW_OP_INSERT || op == RW_OP_UPDATE_INSERT);
+    if (!ins) n_del++;
+    uint64_t uv[W8_MAXC], mv[W8_MAXC];
+#pragma unroll
+    for (int c = 0; c < W8_MAXC; c++)
+      if (c < w.n_u) uv[c] = __ldg((const unsigned long long*)ch.cols[c].data + r);
+    const uint64_t key = __ldg((const unsigned long long*)ch.cols[w.key_col].data + r);
+    bool fast = key != J_EMPTY, ilive = false;
     uint32_t cnt = 0, ohead = J_NIL;
     int64_t ob = -1;
-    // ---- phase 1: load the row, probe the other side
-    if (r < ch.n) op = ch.ops[r];
-    if (op != 0) {
-      ins = (op == RW_OP_INSERT || op == RW_OP_UPDATE_INSERT);
-      if (!ins) n_del++;
+    // ---- probe: the whole 64-byte bucket of the other side in one round trip
+    if (fast) {
+      if (!PROBE_ONLY && ins) prefetch_l2(bkt(own, (int64_t)(mix64(key) & wmask)));
+      uint64_t idx = mix64(key) & omask;
+      while (true) {
+        const uint8_t* bp = bkt(other, (int64_t)idx);
+        const ulonglong2 h0 = __ldcg((const ulonglong2*)bp);          // key | head/count
+        const uint4 mh = __ldcg((const uint4*)(bp + 16));             // inline record header
+        ulonglong2 m2[W8_MAXC / 2];
 #pragma unroll
-      for (int c = 0; c < W8_MAXC; c++)
-        if (c < w.n_u) uv[c] = __ldg((const unsigned long long*)ch.cols[c].data + r);
-      key = __ldg((const unsigned long long*)ch.cols[w.key_col].data + r);
-      fast = key != J_EMPTY;
-      if (fast) {
-        if (!PROBE_ONLY && ins) prefetch_l2(bkt(own, (int64_t)(mix64(key) & wmask)));
-        uint64_t idx = mix64(key) & omask;
-        while (true) {
-          const uint8_t* bp = bkt(other, (int64_t)idx);
-          const ulonglong2 h0 = __ldcg((const ulonglong2*)bp);          // key | head/count
-          const uint4 mh = __ldcg((const uint4*)(bp + 16));             // inline record header
-          ulonglong2 m2[W8_MAXC / 2];
+        for (int c = 0; c < W8_MAXC / 2; c++)
+          if (2 * c < w.n_m) m2[c] = __ldcg((const ulonglong2*)(bp + 32 + 16 * c));
+        if (h0.x == key) {
+          ob = (int64_t)idx;
+          cnt = (uint32_t)(h0.y >> 32);
+          ohead = (uint32_t)h0.y;
+          ilive = (mh.x != IL_EMPTY) && !(mh.x & J_DEAD);
+          if (ilive && mh.y != 0) { ilive = false; fast = false; }  // NULLs in the matched record: generic emission
 #pragma unroll
-          for (int c = 0; c < W8_MAXC / 2; c++)
-            if (2 * c < w.n_m) m2[c] = __ldcg((const ulonglong2*)(bp + 32 + 16 * c));
-          if (h0.x == key) {
-            ob = (int64_t)idx;
-            cnt = (uint32_t)(h0.y >> 32);
-            ohead = (uint32_t)h0.y;
-            ilive = (mh.x != IL_EMPTY) && !(mh.x & J_DEAD);
-            if (ilive && mh.y != 0) { ilive = false; fast = false; }  // NULLs in the matched record: generic emission
-#pragma unroll
-            for (int c = 0; c < W8_MAXC / 2; c++) { mv[2 * c] = m2[c].x; mv[2 * c + 1] = m2[c].y; }
-            break;
-          }
-          if (h0.x == J_EMPTY) break;
-          idx = (idx + 1) & omask;
+          for (int c = 0; c < W8_MAXC / 2; c++) { mv[2 * c] = m2[c].x; mv[2 * c + 1] = m2[c].y; }
+          break;
         }
-      } else {
-        uint64_t kw[1] = {key}, hc = 0;
-        ob = js_find(other, p, kw, 0, &hc);
-        if (ob >= 0) { cnt = (uint32_t)(hc >> 32); ohead = (uint32_t)hc; }
+        if (h0.x == J_EMPTY) break;
+        idx = (idx + 1) & omask;
       }
+    } else {
+      uint64_t kw[1] = {key}, hc = 0;
+      ob = js_find(other, p, kw, 0, &hc);
+      if (ob >= 0) { cnt = (uint32_t)(hc >> 32); ohead = (uint32_t)hc; }
     }
-    // ---- phase 2: tile scan of the match counts, one reservation per tile
-    unsigned long long incl = cnt;
-    for (int d = 1; d < 32; d <<= 1) {
-      unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
-    }
-    if (lane == 31) s_cnt[wid] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long run = 0;
-      for (int k = 0; k < JF_BLOCK / 32; k++) { unsigned long long t = s_cnt[k]; s_cnt[k] = run; run += t; }
-      s_out_base = run ? atomicAdd(&st->out_rows, run) : 0ull;
-    }
-    __syncthreads();
-    // ---- phase 3: emit
-    if (cnt) {
-      int64_t pos = (int64_t)(s_out_base + s_cnt[wid] + incl - cnt);
-      if (pos + cnt > o.capacity) {
-        atomicOr(&st->err, JERR_OUT_CAPACITY);
-      } else {
-        const uint8_t oop = ins ? RW_OP_INSERT : RW_OP_DELETE;
-        uint32_t left = cnt;
-        if (fast) {
-          if (ilive) {
-            o.ops[pos] = oop;
+    // ---- emit
+    const uint8_t oop = ins ? RW_OP_INSERT : RW_OP_DELETE;
+    if (cnt == 0) {
+      o.vis[out_base + r] = 0;
+      any_hole = true;
+    } else {
+      any_match = true;
+      o.vis[out_base + r] = 1;
+      int64_t pos = out_base + r;
+      uint32_t left = cnt;
+      // extra matches go behind the positional rows
+      int64_t xpos = 0;
+      if (cnt > 1) {
+        const unsigned m = __activemask();
+        // lanes converged here may need different amounts: reserve individually but with one atomic per lane group
+        xpos = out_base + ch.n + (int64_t)atomicAdd(&st->out_rows, (unsigned long long)(cnt - 1));
+        (void)m;
+        if (xpos + (cnt - 1) > o.capacity) { atomicOr(&st->err, JERR_OUT_CAPACITY); left = 1; }
+      }
+      bool first = true;
+      auto place = [&]() -> int64_t {
+        if (first) { first = false; return pos; }
+        o.vis[xpos] = 1;
+        return xpos++;
+      };
+      if (fast && ilive) {
+        const int64_t q = place();
+        o.ops[q] = oop;
 #pragma unroll
-            for (int c = 0; c < W8_MAXC; c++)
-              if (c < w.n_u && w.u_out[c] >= 0) ((uint64_t*)o.col[w.u_out[c]])[pos] = uv[c];
+        for (int c = 0; c < W8_MAXC; c++)
+          if (c < w.n_u && w.u_out[c] >= 0) ((uint64_t*)o.col[w.u_out[c]])[q] = uv[c];
 #pragma unroll
-            for (int c = 0; c < W8_MAXC; c++)
-              if (c < w.n_m && w.m_out[c] >= 0) ((uint64_t*)o.col[w.m_out[c]])[pos] = mv[c];
-            pos++;
-            left--;
-          }
-          if (left)
-            for_each_overflow_live(other, ohead, [&](uint8_t* mrec) -> bool {
-              emit_row(o, p, st, pos++, oop, S, ch, r, mrec);
-              return --left != 0;
-            });
-        } else {
-          for_each_live(other, p, ob, [&](uint8_t* mrec) -> bool {
-            emit_row(o, p, st, pos++, oop, S, ch, r, mrec);
+        for (int c = 0; c < W8_MAXC; c++)
+          if (c < w.n_m && w.m_out[c] >= 0) ((uint64_t*)o.col[w.m_out[c]])[q] = mv[c];
+        left--;
+        if (left)
+          for_each_overflow_live(other, ohead, [&](uint8_t* mrec) -> bool {
+            emit_row(o, p, st, place(), oop, S, ch, r, mrec);
             return --left != 0;
           });
-        }
+      } else {
+        for_each_live(other, p, ob, [&](uint8_t* mrec) -> bool {
+          emit_row(o, p, st, place(), oop, S, ch, r, mrec);
+          return --left != 0;
+        });
       }
     }
-    // ---- phase 4: append to the own side (4a bucket + inline record, 4b overflow rows)
-    if (!PROBE_ONLY) {
-      bool overflow = false;
-      int64_t wb = -1;
-      if (op != 0 && ins) {
-        bool created = false;
-        if (key != J_EMPTY) {
-          uint64_t idx = mix64(key) & wmask;
-          while (true) {
-            unsigned long long* kp = (unsigned long long*)bkt(own, (int64_t)idx);
-            unsigned long long cur = __ldcg(kp);
-            if (cur == key) break;
-            if (cur == J_EMPTY) {
-              const unsigned long long old = atomicCAS(kp, (unsigned long long)J_EMPTY, (unsigned long long)key);
-              if (old == J_EMPTY) { created = true; break; }
-              if (old == key) break;
-            }
-            idx = (idx + 1) & wmask;
+    // ---- append to the own side: bucket claim, then the bucket's inline record or the overflow store
+    if (!PROBE_ONLY && ins) {
+      bool created = false;
+      int64_t wb;
+      if (key != J_EMPTY) {
+        uint64_t idx = mix64(key) & wmask;
+        while (true) {
+          unsigned long long* kp = (unsigned long long*)bkt(own, (int64_t)idx);
+          unsigned long long cur = __ldcg(kp);
+          if (cur == key) break;
+          if (cur == J_EMPTY) {
+            const unsigned long long old = atomicCAS(kp, (unsigned long long)J_EMPTY, (unsigned long long)key);
+            if (old == J_EMPTY) { created = true; break; }
+            if (old == key) break;
           }
-          wb = (int64_t)idx;
-        } else {
-          uint64_t kw[1] = {key};
-          wb = js_find_or_insert(own, p, kw, 0, &created);
+          idx = (idx + 1) & wmask;
         }
-        if (created) new_keys++;
-        uint8_t* irec = bkt_inline(own, p, wb);
-        uint32_t* ilink = &((RecHdr*)irec)->link;
-        uint32_t cur = created ? IL_EMPTY : __ldcg(ilink);
-        bool won = false;
-        while (cur == IL_EMPTY || (cur & J_DEAD)) {
-          const uint32_t old = atomicCAS(ilink, cur, 0u);
-          if (old == cur) { won = true; break; }
-          cur = old;
-        }
-        if (won) {
-          uint4 h;
-          h.x = 0u; h.y = 0u; h.z = seq_base + (uint32_t)r; h.w = 0u;
-          *(uint4*)irec = h;
+        wb = (int64_t)idx;
+      } else {
+        uint64_t kw[1] = {key};
+        wb = js_find_or_insert(own, p, kw, 0, &created);
+      }
+      if (created) new_keys++;
+      uint8_t* irec = bkt_inline(own, p, wb);
+      uint32_t* ilink = &((RecHdr*)irec)->link;
+      uint32_t cur = created ? IL_EMPTY : __ldcg(ilink);
+      bool won = false;
+      while (cur == IL_EMPTY || (cur & J_DEAD)) {
+        const uint32_t old = atomicCAS(ilink, cur, 0u);
+        if (old == cur) { won = true; break; }
+        cur = old;
+      }
+      if (won) {
+        uint4 hh;
+        hh.x = 0u; hh.y = 0u; hh.z = seq_base + (uint32_t)r; hh.w = 0u;
+        *(uint4*)irec = hh;
 #pragma unroll
-          for (int c = 0; c < W8_MAXC / 2; c++)
-            if (2 * c < w.n_u) {
-              ulonglong2 v;
-              v.x = uv[2 * c];
-              v.y = (2 * c + 1 < w.n_u) ? uv[2 * c + 1] : 0ull;
-              *(ulonglong2*)(irec + 16 + 16 * c) = v;
-            }
-          atomicAdd(slot_count(own, p, wb), 1u);
-        } else {
-          overflow = true;
-        }
-      }
-      unsigned int sv = overflow ? 1u : 0u;
-      for (int d = 1; d < 32; d <<= 1) {
-        unsigned int ts = __shfl_up_sync(0xffffffffu, sv, d);
-        if (lane >= d) sv += ts;
-      }
-      if (lane == 31) s_sto[wid] = sv;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        unsigned int srun = 0;
-        for (int k = 0; k < JF_BLOCK / 32; k++) { unsigned int ts = s_sto[k]; s_sto[k] = srun; srun += ts; }
-        s_store_base = srun ? (unsigned int)atomicAdd(&st->n_store, (unsigned long long)srun) : 0u;
-      }
-      __syncthreads();
-      if (overflow) {
-        const uint32_t row = store_base + s_store_base + s_sto[wid] + sv - 1;
+        for (int c = 0; c < W8_MAXC / 2; c++)
+          if (2 * c < w.n_u) {
+            ulonglong2 v;
+            v.x = uv[2 * c];
+            v.y = (2 * c + 1 < w.n_u) ? uv[2 * c + 1] : 0ull;
+            *(ulonglong2*)(irec + 16 + 16 * c) = v;
+          }
+      } else {
+        // overflow row: id from a warp-aggregated reservation
+        const unsigned m = __activemask();
+        const int leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(&st->n_store, (unsigned long long)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        const uint32_t row = store_base + (uint32_t)base + __popc(m & ((1u << lane) - 1));
         const uint32_t old = atomicExch(slot_head(own, p, wb), row);
-        rec_write(p, S, rec_ptr(own, row), ch, r, old & 0x7fffffffu, seq_base + (uint32_t)r, 0);
-        atomicAdd(slot_count(own, p, wb), 1u);
+        uint8_t* rec = rec_ptr(own, row);
+        uint4 hh;
+        hh.x = old & 0x7fffffffu; hh.y = 0u; hh.z = seq_base + (uint32_t)r; hh.w = 0u;
+        *(uint4*)rec = hh;
+#pragma unroll
+        for (int c = 0; c < W8_MAXC / 2; c++)
+          if (2 * c < w.n_u) {
+            ulonglong2 v;
+            v.x = uv[2 * c];
+            v.y = (2 * c + 1 < w.n_u) ? uv[2 * c + 1] : 0ull;
+            *(ulonglong2*)(rec + 16 + 16 * c) = v;
+          }
       }
+      atomicAdd(slot_count(own, p, wb), 1u);
     }
-    __syncthreads();
   }
-  if (!PROBE_ONLY) {
-    for (int d = 16; d > 0; d >>= 1) {
-      new_keys += __shfl_xor_sync(0xffffffffu, new_keys, d);
-      n_del += __shfl_xor_sync(0xffffffffu, n_del, d);
-    }
-    if (lane == 0 && new_keys) atomicAdd(&st->n_keys[S], (unsigned long long)new_keys);
-    if (lane == 0 && n_del) atomicAdd(&st->n_del, (unsigned long long)n_del);
+  unsigned long long flags = (any_hole ? (1ull << 63) : 0ull);
+  const bool warp_match = __any_sync(0xffffffffu, any_match);
+  for (int d = 16; d > 0; d >>= 1) {
+    flags |= __shfl_xor_sync(0xffffffffu, flags, d);
+    new_keys += __shfl_xor_sync(0xffffffffu, new_keys, d);
+    n_del += __shfl_xor_sync(0xffffffffu, n_del, d);
+  }
+  if (lane == 0) {
+    if (flags && (__ldcg(&st->null_mask) & flags) != flags) atomicOr(&st->null_mask, flags);
+    if (warp_match && __ldcg(&st->pad) == 0u) st->pad = 1u;  // "some row matched" (plain store: all writers store 1)
+    if (!PROBE_ONLY && new_keys) atomicAdd(&st->n_keys[S], (unsigned long long)new_keys);
+    if (!PROBE_ONLY && n_del) atomicAdd(&st->n_del, (unsigned long long)n_del);
   }
 }
 
@@ -1176,9 +1177,10 @@ static int join_grow_store(rwgpu_join* h, int S, uint64_t rows) {
 
 static int join_grow_slots(rwgpu_join* h, int S, uint64_t need_keys) {
   JoinSideHost& s = h->side[S];
+  // linear probing over 64-byte buckets: keep load <= 0.5
   if (need_keys * 2 <= s.slot_cap) return RW_OK;
   uint64_t ncap = s.slot_cap;
-  while (ncap < need_keys * 4) ncap <<= 1;
+  while (ncap < need_keys * 4) ncap <<= 1;  // regrow to load <= 0.25
   DevBuf nb;
   int rc = join_alloc_slots(h, S, nb, ncap);
   if (rc != RW_OK) return rc;
@@ -1298,10 +1300,18 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
   if (n <= 0) return RW_OK;
   if (n >= (1ll << 31)) return fail(RW_ERR_INVALID, "chunk too large");
   JoinSideHost& own = h->side[S];
+  static const bool trace = getenv("RWGPU_TRACE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double tt0 = now();
+  const uint64_t cap0 = own.slot_cap, rcap0 = own.row_cap;
   int rc = join_grow_store(h, S, own.n_rows + (uint64_t)n);
   if (rc != RW_OK) return rc;
   rc = join_grow_slots(h, S, own.keys_upper + (uint64_t)n);
   if (rc != RW_OK) return rc;
+  if (trace)
+    fprintf(stderr, "  [push_dev S=%d n=%lld] grow %.3f ms (slot_cap %llu->%llu, row_cap %llu->%llu, n_rows %llu keys %llu)\n", S, (long long)n,
+            now() - tt0, (unsigned long long)cap0, (unsigned long long)own.slot_cap, (unsigned long long)rcap0,
+            (unsigned long long)own.row_cap, (unsigned long long)own.n_rows, (unsigned long long)own.keys_upper);
   JoinStatus* ds = h->status.as<JoinStatus>();
   const JoinPlanDev* pd = h->plan_dev.as<JoinPlanDev>();
   RW_CUDA(cudaMemsetAsync(&ds->n_store, 0, 16, st));  // n_store, n_del (out_rows / null_mask accumulate over the call)
@@ -1309,55 +1319,97 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
   h->seq += (uint64_t)n;
   JoinStatus hs;
   if (h->fast_inner) {
-    rc = join_ensure_out(h, out_base + std::max<int64_t>(2 * n, 4096), st, out_base);
-    if (rc != RW_OK) return rc;
-    const int64_t tiles = (n + JF_BLOCK * JF_R - 1) / (JF_BLOCK * JF_R);
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, 148 * 8));
     // Key64 / 8-byte-column specialisation when the chunk carries no bitmaps (ops == 0 still hides rows)
     bool use_w8 = h->w8_ok[S] && ch.vis_bits == nullptr;
     for (int c = 0; c < ch.n_cols && use_w8; c++)
       use_w8 = !ch.cols[c].valid_bits && !ch.cols[c].valid_bytes && (((uintptr_t)ch.cols[c].data & 7) == 0);
-    h->prof.begin(st);
-    if (use_w8)
-      join_inner_fused_w8_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
-                                                                     (uint32_t)own.n_rows, seq_base);
-    else
-      join_inner_fused_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
-                                                                  (uint32_t)own.n_rows, seq_base);
-    h->prof.end(st);
-    join_inner_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, side_dev(h, S), ds, seq_base);
-    RW_CUDA(cudaGetLastError());
-    h->launches += 2;
-    rc = join_read_status(h, st, &hs);
-    if (rc != RW_OK) return rc;
-    const uint64_t stored = hs.n_store, keys = hs.n_keys[S];
-    unsigned int err = hs.err;
-    while (hs.err & JERR_OUT_CAPACITY) {
-      // the reservation overflowed: redo the (state-free) probe + emit with room for every row
-      const int64_t need = (int64_t)hs.out_rows;
-      const unsigned long long base_ull = (unsigned long long)out_base;
-      RW_CUDA(cudaMemcpyAsync(&ds->out_rows, &base_ull, 8, cudaMemcpyHostToDevice, st));
-      RW_CUDA(cudaMemsetAsync(&ds->n_store, 0, 16, st));
-      RW_CUDA(cudaMemsetAsync(&ds->err, 0, 4, st));
-      RW_CUDA(cudaStreamSynchronize(st));
-      rc = join_ensure_out(h, need, st, out_base);
+    static const bool dbg_probe_only = getenv("RWGPU_DBG_PROBE_ONLY") != nullptr;  // timing experiments only (state is not updated)
+    if (use_w8) {
+      // positional output: n rows aligned with the input + extra matches behind them
+      RW_CUDA(cudaMemsetAsync(&ds->out_rows, 0, 8, st));
+      RW_CUDA(cudaMemsetAsync(&ds->pad, 0, 4, st));
+      rc = join_ensure_out(h, out_base + n + std::max<int64_t>(n / 2, 4096), st, out_base);
       if (rc != RW_OK) return rc;
-      if (use_w8)
-        join_inner_fused_w8_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds, 0, seq_base);
+      const int grid = jgrid(n, JF_BLOCK);
+      h->prof.begin(st);
+      if (dbg_probe_only && S == 0)
+        join_inner_w8p_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
+                                                                (uint32_t)own.n_rows, seq_base, out_base);
       else
-        join_inner_fused_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds, 0, seq_base);
+        join_inner_w8p_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
+                                                                 (uint32_t)own.n_rows, seq_base, out_base);
+      h->prof.end(st);
+      join_inner_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, side_dev(h, S), ds, seq_base);
       RW_CUDA(cudaGetLastError());
-      h->launches++;
+      h->launches += 2;
       rc = join_read_status(h, st, &hs);
       if (rc != RW_OK) return rc;
-      err = (err & ~JERR_OUT_CAPACITY) | hs.err;
+      const uint64_t stored = hs.n_store, keys = hs.n_keys[S];
+      unsigned int err = hs.err;
+      if (hs.err & JERR_OUT_CAPACITY) {
+        // the extra-match area overflowed: redo the (state-free) probe + emit with room for every row
+        const int64_t extras = (int64_t)hs.out_rows;
+        RW_CUDA(cudaMemsetAsync(&ds->out_rows, 0, 8, st));
+        RW_CUDA(cudaMemsetAsync(&ds->err, 0, 4, st));
+        RW_CUDA(cudaStreamSynchronize(st));
+        rc = join_ensure_out(h, out_base + n + extras, st, out_base);
+        if (rc != RW_OK) return rc;
+        join_inner_w8p_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds, 0,
+                                                                seq_base, out_base);
+        RW_CUDA(cudaGetLastError());
+        h->launches++;
+        rc = join_read_status(h, st, &hs);
+        if (rc != RW_OK) return rc;
+        err = (err & ~JERR_OUT_CAPACITY) | hs.err;
+      }
+      own.n_rows += stored;
+      own.keys_upper = keys;
+      const bool any_match = hs.pad != 0;
+      hs.err = err;
+      rc = join_check_err(h, hs, st);
+      if (rc != RW_OK) return rc;
+      *out_rows = (any_match || hs.out_rows) ? n + (int64_t)hs.out_rows : 0;
+    } else {
+      rc = join_ensure_out(h, out_base + std::max<int64_t>(2 * n, 4096), st, out_base);
+      if (rc != RW_OK) return rc;
+      const int64_t tiles = (n + JF_BLOCK * JF_R - 1) / (JF_BLOCK * JF_R);
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, 148 * 8));
+      h->prof.begin(st);
+      join_inner_fused_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
+                                                                  (uint32_t)own.n_rows, seq_base);
+      h->prof.end(st);
+      join_inner_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, side_dev(h, S), ds, seq_base);
+      RW_CUDA(cudaGetLastError());
+      h->launches += 2;
+      rc = join_read_status(h, st, &hs);
+      if (rc != RW_OK) return rc;
+      const uint64_t stored = hs.n_store, keys = hs.n_keys[S];
+      unsigned int err = hs.err;
+      while (hs.err & JERR_OUT_CAPACITY) {
+        // the reservation overflowed: redo the (state-free) probe + emit with room for every row
+        const int64_t need = (int64_t)hs.out_rows;
+        const unsigned long long base_ull = (unsigned long long)out_base;
+        RW_CUDA(cudaMemcpyAsync(&ds->out_rows, &base_ull, 8, cudaMemcpyHostToDevice, st));
+        RW_CUDA(cudaMemsetAsync(&ds->n_store, 0, 16, st));
+        RW_CUDA(cudaMemsetAsync(&ds->err, 0, 4, st));
+        RW_CUDA(cudaStreamSynchronize(st));
+        rc = join_ensure_out(h, need, st, out_base);
+        if (rc != RW_OK) return rc;
+        join_inner_fused_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds, 0, seq_base);
+        RW_CUDA(cudaGetLastError());
+        h->launches++;
+        rc = join_read_status(h, st, &hs);
+        if (rc != RW_OK) return rc;
+        err = (err & ~JERR_OUT_CAPACITY) | hs.err;
+      }
+      own.n_rows += stored;
+      own.keys_upper = keys;
+      hs.err = err;
+      rc = join_check_err(h, hs, st);
+      if (rc != RW_OK) return rc;
+      *out_rows = (int64_t)hs.out_rows - out_base;
+      // keep the cumulative convention of the scan-based kernel consistent with out_base
     }
-    own.n_rows += stored;
-    own.keys_upper = keys;
-    hs.err = err;
-    rc = join_check_err(h, hs, st);
-    if (rc != RW_OK) return rc;
-    *out_rows = (int64_t)hs.out_rows - out_base;
   } else {
     rc = join_ensure_scratch(h, n);
     if (rc != RW_OK) return rc;
@@ -1558,11 +1610,11 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
   for (int s = 0; s < 2; s++) {
     uint64_t hint = sd[s]->row_capacity_hint;
     uint64_t cap = 1024;
-    while (cap < hint * 2) cap <<= 1;
+    while (cap * 4 < hint * 10) cap <<= 1;  // load <= 0.4 at `hint` keys (every extra probe is a 64 B HBM access)
     h->side[s].slot_cap = cap;
     rc = join_alloc_slots(h, s, h->side[s].slots, cap);
     if (rc != RW_OK) return rc;
-    rc = join_grow_store(h, s, std::max<uint64_t>(hint, 1024));
+    rc = join_grow_store(h, s, 1024);  // overflow rows only; grows on demand
     if (rc != RW_OK) return rc;
   }
   RW_CUDA(cudaStreamSynchronize(h->stream));
