@@ -47,7 +47,20 @@ namespace rw {
 #define J_DEAD 0x80000000u
 #define J_MAX_OUT (2 * RW_MAX_COLS)
 #define J_HDR 16
-#define IL_EMPTY 0xFFFFFFFFu  // inline record never used (link field)
+// bucket state word W (64 bit, follows the key word(s)):
+//   bits  0..30  head of the overflow chain (row id, J_NIL = none)
+//   bits 31..32  state of the inline record: 0 = never used, 1 = live, 2 = dead (reusable)
+//   bits 33..63  live row count of the key (inline + overflow)
+// Every own-side mutation of a bucket is ONE compare-and-swap on W (or one 128-bit CAS on key|W
+// when the bucket is claimed): random atomics are the scarce resource (22 G/s on B200).
+#define W_EMPTY 0x7fffffffull
+#define W_COUNT_ONE (1ull << 33)
+#define W_IL_LIVE (1ull << 31)
+#define W_IL_DEAD (2ull << 31)
+#define W_IL_MASK (3ull << 31)
+__device__ __host__ __forceinline__ uint32_t W_head(uint64_t W) { return (uint32_t)(W & 0x7fffffffull); }
+__device__ __host__ __forceinline__ uint32_t W_istate(uint64_t W) { return (uint32_t)((W >> 31) & 3ull); }
+__device__ __host__ __forceinline__ uint32_t W_count(uint64_t W) { return (uint32_t)(W >> 33); }
 
 #define JERR_DOUBLE_DELETE 1u
 #define JERR_OUT_CAPACITY 2u
@@ -170,27 +183,59 @@ __device__ __forceinline__ uint64_t key_hash(const JoinPlanDev* p, const uint64_
   return h;
 }
 
-// bucket = [key word(s)] [head/count word: low 32 = overflow head row (J_NIL = none), high 32 = live count] [inline record]
+// bucket = [key word(s)] [state word W] [inline record]
 __device__ __forceinline__ uint8_t* bkt(const JoinSideDev& s, int64_t b) { return s.buckets + (uint64_t)b * s.bstride; }
-__device__ __forceinline__ uint32_t* slot_head(const JoinSideDev& s, const JoinPlanDev* p, int64_t b) {
-  return (uint32_t*)(bkt(s, b) + p->KW * 8);
-}
-__device__ __forceinline__ uint32_t* slot_count(const JoinSideDev& s, const JoinPlanDev* p, int64_t b) {
-  return slot_head(s, p, b) + 1;
+__device__ __forceinline__ unsigned long long* bkt_W(const JoinSideDev& s, const JoinPlanDev* p, int64_t b) {
+  return (unsigned long long*)(bkt(s, b) + p->KW * 8);
 }
 __device__ __forceinline__ uint8_t* bkt_inline(const JoinSideDev& s, const JoinPlanDev* p, int64_t b) { return bkt(s, b) + p->bhdr; }
+
+// 128-bit compare-and-swap (sm_90+): claims an empty Key64 bucket, key and state word at once
+__device__ __forceinline__ bool cas128(void* addr, ulonglong2 expect, ulonglong2 desired, ulonglong2* found) {
+  unsigned long long o0, o1;
+  asm volatile(
+      "{\n .reg .b128 c, d, o;\n mov.b128 c, {%2, %3};\n mov.b128 d, {%4, %5};\n atom.global.cas.b128 o, [%6], c, d;\n mov.b128 {%0, %1}, o;\n}"
+      : "=l"(o0), "=l"(o1)
+      : "l"(expect.x), "l"(expect.y), "l"(desired.x), "l"(desired.y), "l"(addr)
+      : "memory");
+  found->x = o0;
+  found->y = o1;
+  return o0 == expect.x && o1 == expect.y;
+}
+
+// own-side append of one row to bucket b whose key is already claimed.  Returns true if the row got
+// the bucket's inline record (caller writes it there); otherwise the caller supplies an overflow row
+// id to `w_push_overflow`.  One CAS on W either way.
+__device__ __forceinline__ bool w_claim_inline(unsigned long long* Wp) {
+  unsigned long long cur = __ldcg(Wp);
+  while (W_istate(cur) != 1u) {
+    const unsigned long long nw = ((cur & ~W_IL_MASK) | W_IL_LIVE) + W_COUNT_ONE;
+    const unsigned long long old = atomicCAS(Wp, cur, nw);
+    if (old == cur) return true;
+    cur = old;
+  }
+  return false;
+}
+__device__ __forceinline__ uint32_t w_push_overflow(unsigned long long* Wp, uint32_t row) {
+  unsigned long long cur = __ldcg(Wp);
+  while (true) {
+    const unsigned long long nw = ((cur & ~0x7fffffffull) | (unsigned long long)row) + W_COUNT_ONE;
+    const unsigned long long old = atomicCAS(Wp, cur, nw);
+    if (old == cur) return W_head(cur);
+    cur = old;
+  }
+}
 
 // visit every live record of bucket b: the inline record first, then the overflow chain.
 // `f(rec)` returns false to stop.
 template <class F>
 __device__ __forceinline__ void for_each_live(const JoinSideDev& s, const JoinPlanDev* p, int64_t b, F f) {
-  // link words are read through L2 (ld.cg): another thread of the same kernel may set DEAD
-  uint8_t* irec = bkt_inline(s, p, b);
-  const uint32_t ilk = __ldcg(&((const RecHdr*)irec)->link);
-  if (ilk != IL_EMPTY && !(ilk & J_DEAD)) {
-    if (!f(irec)) return;
+  // state / link words are read through L2 (ld.cg): another thread of the same kernel may change them
+  const unsigned long long W = __ldcg(bkt_W(s, p, b));
+  if (W_istate(W) == 1u) {
+    if (!f(bkt_inline(s, p, b))) return;
   }
-  uint32_t m = __ldcg(slot_head(s, p, b)) & 0x7fffffffu;
+  uint32_t m = W_head(W);
   while (m != J_NIL) {
     uint8_t* rec = rec_ptr(s, m);
     const uint32_t lk = __ldcg(&((const RecHdr*)rec)->link);
@@ -286,8 +331,7 @@ __global__ void join_init_slots_kernel(uint8_t* buckets, uint64_t cap, int bstri
     uint64_t* s = (uint64_t*)(buckets + i * bstride);
     s[0] = single_key ? J_EMPTY : 0ull;
     for (int k = 1; k < KW; k++) s[k] = 0;
-    s[KW] = (uint64_t)J_NIL;                          // overflow head = NIL, count = 0
-    ((uint32_t*)(s + KW + 1))[0] = IL_EMPTY;           // inline record: never used
+    s[KW] = W_EMPTY;                                   // overflow head = NIL, inline never used, count = 0
   }
 }
 
@@ -426,7 +470,7 @@ __global__ void __launch_bounds__(256) join_prepare_kernel(const JoinPlanDev* __
     } else {
       uint64_t hc = 0;
       ms = js_find(other, p, kw, nm, &hc);
-      const uint64_t m = ms >= 0 ? (hc >> 32) : 0;
+      const uint64_t m = ms >= 0 ? W_count(hc) : 0;
       uint64_t per_match;
       if (T == RW_JOIN_INNER) per_match = 1;
       else if (jt_is_semi(T) || jt_is_anti(T)) per_match = jt_forward_exactly_once(T, S) ? 0 : 1;
@@ -558,8 +602,9 @@ __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __r
       }
       // append-only optimisation (hash_join.rs:1222-1228): drop the matched row, do not store u
       if (p->append_only_optimize && ao_rec) {
-        ((RecHdr*)ao_rec)->link |= J_DEAD;
-        *slot_count(other, p, ms) -= 1;
+        unsigned long long* Wo = bkt_W(other, p, ms);
+        if (ao_rec == bkt_inline(other, p, ms)) *Wo = ((*Wo & ~W_IL_MASK) | W_IL_DEAD) - W_COUNT_ONE;
+        else { ((RecHdr*)ao_rec)->link |= J_DEAD; *Wo -= W_COUNT_ONE; }
         continue;
       }
       // own-side state (hash_join.rs:1230-1242; JoinHashMap::insert / delete join/hash_join.rs:591-681)
@@ -573,23 +618,24 @@ __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __r
         if (created) new_keys++;
       }
       if (ins) {
-        uint8_t* irec = bkt_inline(own, p, own_slot);
-        const uint32_t ilk = ((RecHdr*)irec)->link;
-        if (ilk == IL_EMPTY || (ilk & J_DEAD)) {  // the bucket's inline record is free: the row lives in the bucket
-          rec_write(p, S, irec, ch, r, 0u, seq_base + (uint32_t)r, own_deg ? degree : 0);
+        unsigned long long* Wp = bkt_W(own, p, own_slot);
+        const unsigned long long W = *Wp;
+        if (W_istate(W) != 1u) {  // the bucket's inline record is free: the row lives in the bucket
+          rec_write(p, S, bkt_inline(own, p, own_slot), ch, r, 0u, seq_base + (uint32_t)r, own_deg ? degree : 0);
+          *Wp = ((W & ~W_IL_MASK) | W_IL_LIVE) + W_COUNT_ONE;
         } else {
-          uint32_t* hd = slot_head(own, p, own_slot);
-          rec_write(p, S, rec_ptr(own, store_row), ch, r, *hd & 0x7fffffffu, seq_base + (uint32_t)r, own_deg ? degree : 0);
-          *hd = store_row;
+          rec_write(p, S, rec_ptr(own, store_row), ch, r, W_head(W), seq_base + (uint32_t)r, own_deg ? degree : 0);
+          *Wp = ((W & ~0x7fffffffull) | (unsigned long long)store_row) + W_COUNT_ONE;
         }
-        *slot_count(own, p, own_slot) += 1;
       } else {
         bool found = false;
         if (own_slot >= 0) {
+          unsigned long long* Wp = bkt_W(own, p, own_slot);
+          uint8_t* irec = bkt_inline(own, p, own_slot);
           for_each_live(own, p, own_slot, [&](uint8_t* mrec) -> bool {
             if (!pk_equal(p, S, mrec, ch, r)) return true;
-            ((RecHdr*)mrec)->link |= J_DEAD;
-            *slot_count(own, p, own_slot) -= 1;
+            if (mrec == irec) *Wp = ((*Wp & ~W_IL_MASK) | W_IL_DEAD) - W_COUNT_ONE;
+            else { ((RecHdr*)mrec)->link |= J_DEAD; *Wp -= W_COUNT_ONE; }
             found = true;
             return false;
           });
@@ -652,8 +698,8 @@ __global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const Joi
             const int64_t b = js_find(other, p, kw, nm, &hc);
             if (b >= 0) {
               head[k] = (uint32_t)b;  // bucket index of the matched key
-              cnt[k] = (uint32_t)(hc >> 32);
-              const uint32_t oh = (uint32_t)hc & 0x7fffffffu;
+              cnt[k] = W_count(hc);
+              const uint32_t oh = W_head(hc);
               if (cnt[k] > 1 && oh != J_NIL) prefetch_l2(rec_ptr(other, oh));
             }
           }
@@ -728,21 +774,8 @@ __global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const Joi
         const int64_t b = js_find_or_insert(own, p, kw, nm, &created);
         if (created) new_keys++;
         own_b[k] = b;
-        uint8_t* irec = bkt_inline(own, p, b);
-        uint32_t* ilink = &((RecHdr*)irec)->link;
-        uint32_t cur = __ldcg(ilink);
-        bool won = false;
-        while (cur == IL_EMPTY || (cur & J_DEAD)) {  // free inline record: claim it (0 = live)
-          const uint32_t old = atomicCAS(ilink, cur, 0u);
-          if (old == cur) { won = true; break; }
-          cur = old;
-        }
-        if (won) {
-          rec_write(p, S, irec, ch, r, 0u, seq_base + (uint32_t)r, 0);
-          atomicAdd(slot_count(own, p, b), 1u);
-        } else {
-          overflow[k] = true;
-        }
+        if (w_claim_inline(bkt_W(own, p, b))) rec_write(p, S, bkt_inline(own, p, b), ch, r, 0u, seq_base + (uint32_t)r, 0);
+        else overflow[k] = true;
       }
       unsigned int sincl[JF_R];
 #pragma unroll
@@ -768,9 +801,8 @@ __global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const Joi
         if (!overflow[k]) continue;
         const int64_t r = base + (int64_t)k * JF_BLOCK + threadIdx.x;
         const uint32_t row = store_base + s_store_base + s_sto[k][wid] + sincl[k] - 1;
-        const uint32_t old = atomicExch(slot_head(own, p, own_b[k]), row);
-        rec_write(p, S, rec_ptr(own, row), ch, r, old & 0x7fffffffu, seq_base + (uint32_t)r, 0);
-        atomicAdd(slot_count(own, p, own_b[k]), 1u);
+        const uint32_t old = w_push_overflow(bkt_W(own, p, own_b[k]), row);
+        rec_write(p, S, rec_ptr(own, row), ch, r, old, seq_base + (uint32_t)r, 0);
       }
     }
     __syncthreads();
@@ -861,9 +893,9 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinP
           if (2 * c < w.n_m) m2[c] = __ldcg((const ulonglong2*)(bp + 32 + 16 * c));
         if (h0.x == key) {
           ob = (int64_t)idx;
-          cnt = (uint32_t)(h0.y >> 32);
-          ohead = (uint32_t)h0.y;
-          ilive = (mh.x != IL_EMPTY) && !(mh.x & J_DEAD);
+          cnt = W_count(h0.y);
+          ohead = W_head(h0.y);
+          ilive = W_istate(h0.y) == 1u;
           if (ilive && mh.y != 0) { ilive = false; fast = false; }  // NULLs in the matched record: generic emission
 #pragma unroll
           for (int c = 0; c < W8_MAXC / 2; c++) { mv[2 * c] = m2[c].x; mv[2 * c + 1] = m2[c].y; }
@@ -875,7 +907,7 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinP
     } else {
       uint64_t kw[1] = {key}, hc = 0;
       ob = js_find(other, p, kw, 0, &hc);
-      if (ob >= 0) { cnt = (uint32_t)(hc >> 32); ohead = (uint32_t)hc; }
+      if (ob >= 0) { cnt = W_count(hc); ohead = W_head(hc); }
     }
     // ---- emit
     const uint8_t oop = ins ? RW_OP_INSERT : RW_OP_DELETE;
@@ -926,20 +958,24 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinP
     }
     // ---- append to the own side: bucket claim, then the bucket's inline record or the overflow store
     if (!PROBE_ONLY && ins) {
-      bool created = false;
+      // one 128-bit CAS claims an empty bucket together with its inline record; an existing key
+      // costs one 64-bit CAS on its state word
+      bool created = false, inline_won = false;
       int64_t wb;
       if (key != J_EMPTY) {
         uint64_t idx = mix64(key) & wmask;
         while (true) {
-          unsigned long long* kp = (unsigned long long*)bkt(own, (int64_t)idx);
-          unsigned long long cur = __ldcg(kp);
-          if (cur == key) break;
-          if (cur == J_EMPTY) {
-            const unsigned long long old = atomicCAS(kp, (unsigned long long)J_EMPTY, (unsigned long long)key);
-            if (old == J_EMPTY) { created = true; break; }
-            if (old == key) break;
+          ulonglong2* bp = (ulonglong2*)bkt(own, (int64_t)idx);
+          ulonglong2 cur = __ldcg(bp);
+          if (cur.x == J_EMPTY) {
+            ulonglong2 want, found;
+            want.x = key;
+            want.y = (W_EMPTY | W_IL_LIVE) + W_COUNT_ONE;
+            if (cas128(bp, cur, want, &found)) { created = true; inline_won = true; break; }
+            cur = found;
           }
-          idx = (idx + 1) & wmask;
+          if (cur.x == key) break;
+          if (cur.x != J_EMPTY) idx = (idx + 1) & wmask;
         }
         wb = (int64_t)idx;
       } else {
@@ -947,27 +983,12 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinP
         wb = js_find_or_insert(own, p, kw, 0, &created);
       }
       if (created) new_keys++;
-      uint8_t* irec = bkt_inline(own, p, wb);
-      uint32_t* ilink = &((RecHdr*)irec)->link;
-      uint32_t cur = created ? IL_EMPTY : __ldcg(ilink);
-      bool won = false;
-      while (cur == IL_EMPTY || (cur & J_DEAD)) {
-        const uint32_t old = atomicCAS(ilink, cur, 0u);
-        if (old == cur) { won = true; break; }
-        cur = old;
-      }
-      if (won) {
-        uint4 hh;
-        hh.x = 0u; hh.y = 0u; hh.z = seq_base + (uint32_t)r; hh.w = 0u;
-        *(uint4*)irec = hh;
-#pragma unroll
-        for (int c = 0; c < W8_MAXC / 2; c++)
-          if (2 * c < w.n_u) {
-            ulonglong2 v;
-            v.x = uv[2 * c];
-            v.y = (2 * c + 1 < w.n_u) ? uv[2 * c + 1] : 0ull;
-            *(ulonglong2*)(irec + 16 + 16 * c) = v;
-          }
+      unsigned long long* Wp = bkt_W(own, p, wb);
+      if (!inline_won) inline_won = w_claim_inline(Wp);
+      uint8_t* rec;
+      uint32_t link = 0u;
+      if (inline_won) {
+        rec = bkt_inline(own, p, wb);
       } else {
         // overflow row: id from a warp-aggregated reservation
         const unsigned m = __activemask();
@@ -976,21 +997,20 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinP
         if (lane == leader) base = atomicAdd(&st->n_store, (unsigned long long)__popc(m));
         base = __shfl_sync(m, base, leader);
         const uint32_t row = store_base + (uint32_t)base + __popc(m & ((1u << lane) - 1));
-        const uint32_t old = atomicExch(slot_head(own, p, wb), row);
-        uint8_t* rec = rec_ptr(own, row);
-        uint4 hh;
-        hh.x = old & 0x7fffffffu; hh.y = 0u; hh.z = seq_base + (uint32_t)r; hh.w = 0u;
-        *(uint4*)rec = hh;
-#pragma unroll
-        for (int c = 0; c < W8_MAXC / 2; c++)
-          if (2 * c < w.n_u) {
-            ulonglong2 v;
-            v.x = uv[2 * c];
-            v.y = (2 * c + 1 < w.n_u) ? uv[2 * c + 1] : 0ull;
-            *(ulonglong2*)(rec + 16 + 16 * c) = v;
-          }
+        link = w_push_overflow(Wp, row);
+        rec = rec_ptr(own, row);
       }
-      atomicAdd(slot_count(own, p, wb), 1u);
+      uint4 hh;
+      hh.x = link; hh.y = 0u; hh.z = seq_base + (uint32_t)r; hh.w = 0u;
+      *(uint4*)rec = hh;
+#pragma unroll
+      for (int c = 0; c < W8_MAXC / 2; c++)
+        if (2 * c < w.n_u) {
+          ulonglong2 v;
+          v.x = uv[2 * c];
+          v.y = (2 * c + 1 < w.n_u) ? uv[2 * c + 1] : 0ull;
+          *(ulonglong2*)(rec + 16 + 16 * c) = v;
+        }
     }
   }
   unsigned long long flags = (any_hole ? (1ull << 63) : 0ull);
@@ -1037,10 +1057,20 @@ __global__ void __launch_bounds__(256) join_inner_delete_kernel(const JoinPlanDe
           return true;
         });
         if (!best) break;
-        const uint32_t old = atomicOr(&((RecHdr*)best)->link, J_DEAD);
-        if (!(old & J_DEAD)) {
-          atomicSub(slot_count(own, p, slot), 1u);
-          found = true;
+        unsigned long long* Wp = bkt_W(own, p, slot);
+        if (best == bkt_inline(own, p, slot)) {
+          unsigned long long cur = __ldcg(Wp);
+          while (W_istate(cur) == 1u) {  // live -> dead, count - 1, in one CAS
+            const unsigned long long old = atomicCAS(Wp, cur, ((cur & ~W_IL_MASK) | W_IL_DEAD) - W_COUNT_ONE);
+            if (old == cur) { found = true; break; }
+            cur = old;
+          }
+        } else {
+          const uint32_t old = atomicOr(&((RecHdr*)best)->link, J_DEAD);
+          if (!(old & J_DEAD)) {
+            atomicAdd(Wp, 0ull - W_COUNT_ONE);
+            found = true;
+          }
         }
       }
     }
