@@ -506,6 +506,18 @@ __global__ void __launch_bounds__(256) agg_flush_kernel(AggTable t, AggPlanDev p
   }
 }
 
+// status + per-column NULL flags -> pinned host memory (UVA), then reset the per-barrier counters
+__global__ void agg_epilogue_kernel(AggStatus* st, unsigned int* has_null, AggStatus* st_host, unsigned int* has_null_host) {
+  const int t = threadIdx.x;
+  if (t < RW_MAX_KEYS + RW_MAX_CALLS) { has_null_host[t] = has_null[t]; has_null[t] = 0; }
+  if (t == 0) {
+    *st_host = *st;
+    st->out_rows = 0;
+    st->n_dirty = 0;
+  }
+  __threadfence_system();
+}
+
 // ------------------------------------------------------------------ rehash (growth) kernel
 __global__ void agg_rehash_kernel(AggTable o, AggTable n, AggPlanDev p) {
   const uint64_t total = o.cap + 2;
@@ -814,8 +826,6 @@ static int agg_flush_dev(rwgpu_agg* h, cudaStream_t st, int64_t* n_rows, unsigne
   rc = agg_ensure_out(h, bound);
   if (rc != RW_OK) return rc;
   AggStatus* ds = h->status.as<AggStatus>();
-  RW_CUDA(cudaMemsetAsync(&ds->out_rows, 0, sizeof(unsigned long long), st));
-  RW_CUDA(cudaMemsetAsync(h->out_hasnull.p, 0, sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS), st));
   AggOutDev o;
   o.ops = h->out_ops.as<uint8_t>();
   for (size_t k = 0; k < h->out_types.size(); k++) { o.col[k] = h->out_col[k].p; o.valid[k] = h->out_valid[k].as<uint8_t>(); }
@@ -826,12 +836,14 @@ static int agg_flush_dev(rwgpu_agg* h, cudaStream_t st, int64_t* n_rows, unsigne
     int64_t max_dirty = (int64_t)std::min<uint64_t>(h->epoch_rows, h->cap + 2);
     agg_flush_kernel<<<grid_for(max_dirty, 256), 256, 0, st>>>(h->table(), h->plan, o, mask);
     RW_CUDA(cudaGetLastError());
-    RW_CUDA(cudaMemsetAsync(&ds->n_dirty, 0, sizeof(unsigned int), st));
     h->launches++;
   }
+  // epilogue: publish status + NULL flags to pinned host memory (no copy-engine round trip) and
+  // re-arm the per-barrier counters
   uint8_t* sh = h->status_host.as<uint8_t>();
-  RW_CUDA(cudaMemcpyAsync(sh, h->status.p, sizeof(AggStatus), cudaMemcpyDeviceToHost, st));
-  RW_CUDA(cudaMemcpyAsync(sh + 64, h->out_hasnull.p, sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS), cudaMemcpyDeviceToHost, st));
+  agg_epilogue_kernel<<<1, 32, 0, st>>>(ds, o.has_null, (AggStatus*)sh, (unsigned int*)(sh + 64));
+  RW_CUDA(cudaGetLastError());
+  h->launches++;
   RW_CUDA(cudaStreamSynchronize(st));
   AggStatus* s = (AggStatus*)sh;
   h->groups_upper = s->n_groups;
@@ -948,6 +960,7 @@ int32_t rwgpu_agg_create(const rw_agg_desc* d, rwgpu_agg** out) {
   RW_CUDA(h->status.reserve(sizeof(AggStatus)));
   RW_CUDA(cudaMemsetAsync(h->status.p, 0, sizeof(AggStatus), h->stream));
   RW_CUDA(h->out_hasnull.reserve(sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS)));
+  RW_CUDA(cudaMemsetAsync(h->out_hasnull.p, 0, sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS), h->stream));
   RW_CUDA(h->status_host.reserve(256));
   rc = agg_init_table(h, h->table());
   if (rc != RW_OK) return rc;
