@@ -1028,12 +1028,242 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinP
   }
 }
 
+// ------------------------------------------------------------------ quad-cooperative Key64 kernel (<= 4 + 4 columns)
+// tools/ubench_bucket.cu (profiles/r1_ubench_bucket.txt): what a random bucket access costs is the
+// number of memory INSTRUCTIONS that touch the line, not its bytes -- one thread reading a 64-byte
+// bucket with 4 x LDG.128 takes 90 us per 2^20 rows, four lanes reading 16 bytes each in ONE
+// instruction take 25 us (the price of a single 16-byte load); a record written with three 16-byte
+// stores costs 89 us cold but ~17 us once the claiming CAS has pulled the line into L2.
+// So a row is owned by a QUAD of lanes and a warp works on 8 rows:
+//   lane q of the quad loads piece q of the other side's bucket   [key|W] [rec hdr] [col0,col1] [col2,col3]
+//   lanes 0,1 hold the update row's columns (0,1) / (2,3) and write them to the output,
+//   lanes 2,3 hold the matched columns and write those -- two store instructions emit the row;
+//   lane 0 claims the own-side bucket with one speculative 128-bit CAS issued BEFORE the probe
+//   resolves (both random accesses are in flight together); lanes 1..3 then write the record
+//   (header, columns) with one 16-byte store each into the line the CAS just brought in.
+// Rows the quad cannot finish this way (sentinel key, several matches, match not in the inline
+// record, NULLs in the matched record) are finished by lane 0 with the generic helpers.
+// Output convention: positional, exactly as join_inner_w8p_kernel.
+__device__ __forceinline__ uint64_t shfl64m(unsigned mask, uint64_t v, int src) {
+  return (uint64_t)__shfl_sync(mask, (unsigned long long)v, src);
+}
+
+template <bool PROBE_ONLY>
+__global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_q4_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch,
+                                                                     JoinSideDev own, JoinSideDev other, JoinOutDev o, JoinStatus* st,
+                                                                     uint32_t store_base, uint32_t seq_base, int64_t out_base) {
+  const int lane = lane_id(), q = lane & 3, qlead = lane & ~3;
+  const unsigned qmask = 0xFu << qlead;
+  const uint64_t omask = other.cap - 1, wmask = own.cap - 1;
+  unsigned int new_keys = 0, n_del = 0;
+  bool any_match = false, any_hole = false;
+  // column roles of this lane
+  const int ca = 2 * (q & 1), cb = ca + 1;
+  const unsigned long long* pa = ca < w.n_u ? (const unsigned long long*)ch.cols[ca].data : nullptr;
+  const unsigned long long* pb = cb < w.n_u ? (const unsigned long long*)ch.cols[cb].data : nullptr;
+  const unsigned long long* pk = (const unsigned long long*)ch.cols[w.key_col].data;
+  int oc0, oc1;
+  if (q < 2) {
+    oc0 = ca < w.n_u ? w.u_out[ca] : -1;
+    oc1 = cb < w.n_u ? w.u_out[cb] : -1;
+  } else {
+    oc0 = ca < w.n_m ? w.m_out[ca] : -1;
+    oc1 = cb < w.n_m ? w.m_out[cb] : -1;
+  }
+  uint64_t* po0 = oc0 >= 0 ? (uint64_t*)o.col[oc0] : nullptr;
+  uint64_t* po1 = oc1 >= 0 ? (uint64_t*)o.col[oc1] : nullptr;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t groups = (ch.n + 7) >> 3;
+  ulonglong2 cas_empty, cas_want;
+  cas_empty.x = J_EMPTY;
+  cas_empty.y = W_EMPTY;
+  cas_want.y = (W_EMPTY | W_IL_LIVE) + W_COUNT_ONE;
+  for (int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < groups; g += nwarps) {
+    const int64_t r = g * 8 + (lane >> 2);
+    if (r >= ch.n) continue;
+    const uint8_t op = ch.ops[r];
+    const int64_t pos = out_base + r;
+    if (op == 0) {  // invisible input row
+      if (q == 0) o.vis[pos] = 0;
+      any_hole = true;
+      continue;
+    }
+    const bool ins = (op == RW_OP_INSERT || op == RW_OP_UPDATE_INSERT);
+    if (!ins && q == 0) n_del++;
+    const uint64_t key = __ldg(pk + r);
+    const uint64_t va = pa ? __ldg(pa + r) : 0ull, vb = pb ? __ldg(pb + r) : 0ull;
+    const bool keyok = key != J_EMPTY;
+    const uint64_t hsh = mix64(key);
+    // ---- own side: speculative claim, in flight together with the probe
+    ulonglong2 cf;
+    cf.x = 0; cf.y = 0;
+    bool cas_ok = false;
+    uint64_t widx = hsh & wmask;
+    if (!PROBE_ONLY && ins && keyok && q == 0) {
+      cas_want.x = key;
+      cas_ok = cas128(own.buckets + widx * 64, cas_empty, cas_want, &cf);
+    }
+    // ---- probe: each lane one 16-byte piece of the 64-byte bucket
+    bool found = false;
+    uint64_t W = 0, idx = hsh & omask;
+    ulonglong2 piece;
+    piece.x = 0; piece.y = 0;
+    if (keyok) {
+      while (true) {
+        piece = __ldcg((const ulonglong2*)(other.buckets + idx * 64 + 16 * q));
+        const uint64_t k0 = shfl64m(qmask, piece.x, qlead);
+        if (k0 == key) { found = true; W = shfl64m(qmask, piece.y, qlead); break; }
+        if (k0 == J_EMPTY) break;
+        idx = (idx + 1) & omask;
+      }
+    }
+    // ---- emit
+    uint32_t cnt = found ? W_count(W) : 0u;
+    bool quad_emit = false;
+    if (cnt == 1u && W_istate(W) == 1u) {
+      const uint32_t mnull = (uint32_t)(shfl64m(qmask, piece.x, qlead + 1) >> 32);  // rec hdr: link | nullmask
+      quad_emit = mnull == 0u;
+    }
+    if (quad_emit) {
+      any_match = true;
+      if (q == 0) o.ops[pos] = ins ? RW_OP_INSERT : RW_OP_DELETE;
+      if (q == 1) o.vis[pos] = 1;
+      if (po0) po0[pos] = q < 2 ? va : piece.x;
+      if (po1) po1[pos] = q < 2 ? vb : piece.y;
+    } else if (q == 0) {
+      int64_t ob = found ? (int64_t)idx : -1;
+      if (!keyok) {
+        uint64_t kw[1] = {key}, hc = 0;
+        ob = js_find(other, p, kw, 0, &hc);
+        cnt = ob >= 0 ? W_count(hc) : 0u;
+      }
+      if (cnt == 0u) {
+        o.vis[pos] = 0;
+        any_hole = true;
+      } else {
+        any_match = true;
+        o.vis[pos] = 1;
+        const uint8_t oop = ins ? RW_OP_INSERT : RW_OP_DELETE;
+        uint32_t left = cnt;
+        int64_t xpos = 0;
+        if (cnt > 1u) {
+          xpos = out_base + ch.n + (int64_t)atomicAdd(&st->out_rows, (unsigned long long)(cnt - 1));
+          if (xpos + (cnt - 1) > o.capacity) { atomicOr(&st->err, JERR_OUT_CAPACITY); left = 1; }
+        }
+        bool first = true;
+        for_each_live(other, p, ob, [&](uint8_t* mrec) -> bool {
+          int64_t at = pos;
+          if (!first) { o.vis[xpos] = 1; at = xpos++; }
+          first = false;
+          emit_row(o, p, st, at, oop, S, ch, r, mrec);
+          return --left != 0;
+        });
+      }
+    }
+    // ---- append to the own side
+    if (!PROBE_ONLY && ins) {
+      uint64_t recp = 0;
+      uint32_t link = 0u;
+      if (q == 0) {
+        bool created = false, inline_won = false;
+        unsigned long long Wcur = 0ull;
+        unsigned long long* Wp;
+        if (keyok) {
+          while (true) {
+            if (cas_ok) { created = true; inline_won = true; break; }
+            if (cf.x == key) { Wcur = cf.y; break; }
+            widx = (widx + 1) & wmask;  // bucket held by another key
+            cas_ok = cas128(own.buckets + widx * 64, cas_empty, cas_want, &cf);
+          }
+          Wp = (unsigned long long*)(own.buckets + widx * 64 + 8);
+        } else {
+          uint64_t kw[1] = {key};
+          widx = (uint64_t)js_find_or_insert(own, p, kw, 0, &created);
+          Wp = (unsigned long long*)(own.buckets + widx * 64 + 8);
+          Wcur = __ldcg(Wp);
+        }
+        if (created) new_keys++;
+        if (!inline_won) {
+          while (W_istate(Wcur) != 1u) {  // the inline record is free (never used, or its row was deleted)
+            const unsigned long long nw = ((Wcur & ~W_IL_MASK) | W_IL_LIVE) + W_COUNT_ONE;
+            const unsigned long long old = atomicCAS(Wp, Wcur, nw);
+            if (old == Wcur) { inline_won = true; break; }
+            Wcur = old;
+          }
+        }
+        if (inline_won) {
+          recp = (uint64_t)(own.buckets + widx * 64 + 16);
+        } else {
+          // overflow row: id from a warp-aggregated reservation, then one CAS pushes it on the chain
+          const unsigned m = __activemask();
+          const int leader = __ffs(m) - 1;
+          unsigned long long base = 0;
+          if (lane == leader) base = atomicAdd(&st->n_store, (unsigned long long)__popc(m));
+          base = __shfl_sync(m, base, leader);
+          const uint32_t row = store_base + (uint32_t)base + __popc(m & ((1u << lane) - 1));
+          while (true) {
+            const unsigned long long nw = ((Wcur & ~0x7fffffffull) | (unsigned long long)row) + W_COUNT_ONE;
+            const unsigned long long old = atomicCAS(Wp, Wcur, nw);
+            if (old == Wcur) break;
+            Wcur = old;
+          }
+          link = W_head(Wcur);
+          recp = (uint64_t)rec_ptr(own, row);
+        }
+      }
+      recp = shfl64m(qmask, recp, qlead);
+      link = __shfl_sync(qmask, link, qlead);
+      if (q != 0) {
+        ulonglong2 v;
+        if (q == 1) {  // RecHdr {link, nullmask = 0, seq, degree = 0}
+          v.x = (unsigned long long)link;
+          v.y = (unsigned long long)(seq_base + (uint32_t)r);
+        } else {       // lane 2: columns 0,1   lane 3: columns 2,3
+          v.x = va;
+          v.y = vb;
+        }
+        *(ulonglong2*)(recp + 16 * (q - 1)) = v;
+      }
+    }
+  }
+  unsigned long long flags = (any_hole ? (1ull << 63) : 0ull);
+  const bool warp_match = __any_sync(0xffffffffu, any_match);
+  for (int d = 16; d > 0; d >>= 1) {
+    flags |= __shfl_xor_sync(0xffffffffu, flags, d);
+    new_keys += __shfl_xor_sync(0xffffffffu, new_keys, d);
+    n_del += __shfl_xor_sync(0xffffffffu, n_del, d);
+  }
+  if (lane == 0) {
+    if (flags && (__ldcg(&st->null_mask) & flags) != flags) atomicOr(&st->null_mask, flags);
+    if (warp_match && __ldcg(&st->pad) == 0u) st->pad = 1u;
+    if (!PROBE_ONLY && new_keys) atomicAdd(&st->n_keys[S], (unsigned long long)new_keys);
+    if (!PROBE_ONLY && n_del) atomicAdd(&st->n_del, (unsigned long long)n_del);
+  }
+}
+
 // own-side deletes of the fast path (after the fused kernel; exits at once when the batch has none).
 // Sequential rule: the delete at chunk position r removes the live record with equal pk that
 // arrived most recently BEFORE r (largest seq below seq_base + r, wrap-aware).
+// status block -> pinned host memory (UVA), tagged so the host can tell a fresh copy from a stale one;
+// then the per-push counters are zeroed for the next push (reset bit 0: n_store / n_del / null_mask,
+// bit 1: out_rows / pad of the positional kernels).
+__device__ __forceinline__ void join_status_publish(JoinStatus* st, JoinStatus* host, unsigned long long tag, int reset) {
+  const JoinStatus s = *st;
+  *host = s;
+  *(unsigned long long*)(host + 1) = tag;
+  __threadfence_system();
+  if (reset & 1) { st->n_store = 0ull; st->n_del = 0ull; st->null_mask = 0ull; }
+  if (reset & 2) { st->out_rows = 0ull; st->pad = 0u; }
+}
+
 __global__ void __launch_bounds__(256) join_inner_delete_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch,
-                                                                 JoinSideDev own, JoinStatus* st, uint32_t seq_base) {
-  if (*(volatile unsigned long long*)&st->n_del == 0ull) return;
+                                                                 JoinSideDev own, JoinStatus* st, uint32_t seq_base,
+                                                                 JoinStatus* status_host, unsigned long long tag, int reset) {
+  if (*(volatile unsigned long long*)&st->n_del == 0ull) {
+    // nothing to delete (the usual case): this launch doubles as the status read-back
+    if (status_host && blockIdx.x == 0 && threadIdx.x == 0) join_status_publish(st, status_host, tag, reset);
+    return;
+  }
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
     const uint8_t op = ch.ops[r];
     if (!row_visible(ch, r, op) || !(op == RW_OP_DELETE || op == RW_OP_UPDATE_DELETE)) continue;
@@ -1137,9 +1367,13 @@ struct rwgpu_join {
   int chunk_size = 1024;
   bool fast_inner = false;
   bool w8_ok[2] = {false, false};  // per update side: Key64 + all-8-byte columns specialisation usable
+  bool q4_ok = false;              // both sides: 3..4 columns, 64-byte buckets -> quad-cooperative kernel
   W8Plan w8[2];
   uint64_t launches = 0;
   uint64_t seq = 0;
+  unsigned long long status_tag = 0;
+  unsigned long long call_null_mask = 0;  // null_mask accumulated over the sub-batches of one API call
+  bool out_rows_cumulative = false;       // the device out_rows counter was left non-zero by the scan-based kernel
   KernelProf prof;
   // scratch (generic path)
   DevBuf sk, sk_alt, packed, offs, mslot, gtable, cub_tmp;
@@ -1298,15 +1532,25 @@ static JoinOutDev out_dev(rwgpu_join* h) {
 // The status block is pushed to pinned host memory by a one-thread kernel (UVA: cudaMallocHost memory
 // is device-addressable) instead of a cudaMemcpy: a tiny D2H copy would queue on the copy engine
 // behind the megabytes of output the previous sub-batch is still draining.
-__global__ void join_status_to_host_kernel(const JoinStatus* src, JoinStatus* dst_host) {
-  *dst_host = *src;
-  __threadfence_system();
+__global__ void join_status_to_host_kernel(JoinStatus* src, JoinStatus* dst_host, unsigned long long tag, int reset) {
+  join_status_publish(src, dst_host, tag, reset);
 }
-static int join_read_status(rwgpu_join* h, cudaStream_t st, JoinStatus* out) {
-  join_status_to_host_kernel<<<1, 1, 0, st>>>(h->status.as<JoinStatus>(), h->status_host.as<JoinStatus>());
+// `tag` != 0: a kernel already in the stream publishes the status itself unless it had real work
+// (join_inner_delete_kernel); only then is the one-thread kernel needed.
+static int join_read_status(rwgpu_join* h, cudaStream_t st, JoinStatus* out, int reset = 1, unsigned long long tag = 0) {
+  JoinStatus* host = h->status_host.as<JoinStatus>();
+  if (tag) {
+    RW_CUDA(cudaStreamSynchronize(st));
+    if (*(volatile unsigned long long*)(host + 1) == tag) {
+      memcpy(out, host, sizeof(JoinStatus));
+      return RW_OK;
+    }
+  }
+  join_status_to_host_kernel<<<1, 1, 0, st>>>(h->status.as<JoinStatus>(), host, 0ull, reset);
   RW_CUDA(cudaGetLastError());
+  h->launches++;
   RW_CUDA(cudaStreamSynchronize(st));
-  memcpy(out, h->status_host.p, sizeof(JoinStatus));
+  memcpy(out, host, sizeof(JoinStatus));
   return RW_OK;
 }
 
@@ -1344,7 +1588,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
             (unsigned long long)own.row_cap, (unsigned long long)own.n_rows, (unsigned long long)own.keys_upper);
   JoinStatus* ds = h->status.as<JoinStatus>();
   const JoinPlanDev* pd = h->plan_dev.as<JoinPlanDev>();
-  RW_CUDA(cudaMemsetAsync(&ds->n_store, 0, 16, st));  // n_store, n_del (out_rows / null_mask accumulate over the call)
+  // n_store / n_del are zero here: every status read-back resets them (join_status_publish)
   const uint32_t seq_base = (uint32_t)h->seq;
   h->seq += (uint64_t)n;
   JoinStatus hs;
@@ -1356,23 +1600,38 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     static const bool dbg_probe_only = getenv("RWGPU_DBG_PROBE_ONLY") != nullptr;  // timing experiments only (state is not updated)
     if (use_w8) {
       // positional output: n rows aligned with the input + extra matches behind them
-      RW_CUDA(cudaMemsetAsync(&ds->out_rows, 0, 8, st));
-      RW_CUDA(cudaMemsetAsync(&ds->pad, 0, 4, st));
+      // (out_rows / pad: zeroed by join_begin_call and by the previous push's status read-back)
       rc = join_ensure_out(h, out_base + n + std::max<int64_t>(n / 2, 4096), st, out_base);
       if (rc != RW_OK) return rc;
-      const int grid = jgrid(n, JF_BLOCK);
+      // quad-cooperative kernel when both sides fit a 64-byte bucket (<= 4 columns); else one thread per row
+      static const bool no_q4 = getenv("RWGPU_NO_Q4") != nullptr;
+      const bool q4 = h->q4_ok && !no_q4;
+      const int grid = q4 ? (int)std::max<int64_t>(1, std::min<int64_t>((n + 63) / 64, 148 * 6)) : jgrid(n, JF_BLOCK);
+      auto launch = [&](bool probe_only, uint32_t store_base) {
+        if (q4) {
+          if (probe_only)
+            join_inner_q4_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
+                                                                   store_base, seq_base, out_base);
+          else
+            join_inner_q4_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
+                                                                    store_base, seq_base, out_base);
+        } else {
+          if (probe_only)
+            join_inner_w8p_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
+                                                                    store_base, seq_base, out_base);
+          else
+            join_inner_w8p_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
+                                                                     store_base, seq_base, out_base);
+        }
+      };
       h->prof.begin(st);
-      if (dbg_probe_only && S == 0)
-        join_inner_w8p_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
-                                                                (uint32_t)own.n_rows, seq_base, out_base);
-      else
-        join_inner_w8p_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
-                                                                 (uint32_t)own.n_rows, seq_base, out_base);
+      launch(dbg_probe_only && S == 0, (uint32_t)own.n_rows);
       h->prof.end(st);
-      join_inner_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, side_dev(h, S), ds, seq_base);
+      const unsigned long long tag = ++h->status_tag;
+      join_inner_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, side_dev(h, S), ds, seq_base, h->status_host.as<JoinStatus>(), tag, 3);
       RW_CUDA(cudaGetLastError());
       h->launches += 2;
-      rc = join_read_status(h, st, &hs);
+      rc = join_read_status(h, st, &hs, 3, tag);
       if (rc != RW_OK) return rc;
       const uint64_t stored = hs.n_store, keys = hs.n_keys[S];
       unsigned int err = hs.err;
@@ -1384,11 +1643,10 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
         RW_CUDA(cudaStreamSynchronize(st));
         rc = join_ensure_out(h, out_base + n + extras, st, out_base);
         if (rc != RW_OK) return rc;
-        join_inner_w8p_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds, 0,
-                                                                seq_base, out_base);
+        launch(true, 0u);
         RW_CUDA(cudaGetLastError());
         h->launches++;
-        rc = join_read_status(h, st, &hs);
+        rc = join_read_status(h, st, &hs, 3);
         if (rc != RW_OK) return rc;
         err = (err & ~JERR_OUT_CAPACITY) | hs.err;
       }
@@ -1402,13 +1660,14 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     } else {
       rc = join_ensure_out(h, out_base + std::max<int64_t>(2 * n, 4096), st, out_base);
       if (rc != RW_OK) return rc;
+      h->out_rows_cumulative = true;
       const int64_t tiles = (n + JF_BLOCK * JF_R - 1) / (JF_BLOCK * JF_R);
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, 148 * 8));
       h->prof.begin(st);
       join_inner_fused_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
                                                                   (uint32_t)own.n_rows, seq_base);
       h->prof.end(st);
-      join_inner_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, side_dev(h, S), ds, seq_base);
+      join_inner_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, side_dev(h, S), ds, seq_base, nullptr, 0ull, 0);
       RW_CUDA(cudaGetLastError());
       h->launches += 2;
       rc = join_read_status(h, st, &hs);
@@ -1484,7 +1743,8 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     if (rc != RW_OK) return rc;
     *out_rows = reserved;
   }
-  *null_mask = hs.null_mask;
+  h->call_null_mask |= hs.null_mask;  // the device copy restarts from zero after every read-back
+  *null_mask = h->call_null_mask;
   h->valid_dirty |= hs.null_mask & ((1ull << 63) - 1);
   return RW_OK;
 }
@@ -1494,8 +1754,9 @@ static int join_begin_call(rwgpu_join* h, cudaStream_t st) {
   int rc = join_clean_valid(h, st);
   if (rc != RW_OK) return rc;
   JoinStatus* ds = h->status.as<JoinStatus>();
-  RW_CUDA(cudaMemsetAsync(&ds->out_rows, 0, 8, st));
-  RW_CUDA(cudaMemsetAsync(&ds->null_mask, 0, 8, st));
+  if (h->out_rows_cumulative) RW_CUDA(cudaMemsetAsync(&ds->out_rows, 0, 8, st));  // scan-based kernel: cumulative over sub-batches
+  h->out_rows_cumulative = false;
+  h->call_null_mask = 0;
   return RW_OK;
 }
 
@@ -1630,6 +1891,8 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
     }
     h->w8_ok[s2] = ok;
   }
+  h->q4_ok = h->w8_ok[0] && h->w8_ok[1] && p.bhdr == 16 && p.stride[0] == 48 && p.stride[1] == 48 && p.bstride[0] == 64 &&
+             p.bstride[1] == 64 && p.n_cols[0] <= 4 && p.n_cols[1] <= 4;
 
   RW_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   RW_CUDA(h->plan_dev.reserve(sizeof(JoinPlanDev)));
