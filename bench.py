@@ -91,15 +91,57 @@ def gen_agg_rows(n, start, seed):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region.  In-process NVML (what nvidia-smi
+    itself reads) every 2 ms: spawning `nvidia-smi -lms` next to a timed region that lasts a few
+    milliseconds put its start-up (driver attach) inside the measurement and stalled kernel launches
+    for milliseconds.  nvidia-smi is the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index=0):
-        self.path = tempfile.mktemp(suffix=".csv")
-        self.proc = None
         self.idx = gpu_index
+        self.proc = None
+        self.nv = None
+        self.samples = []
+        self.thread = None
+        self.halt = False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.halt:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(sm), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nv is not None:
+            import threading
+            self.halt = False
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
+        self.path = tempfile.mktemp(suffix=".csv")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
@@ -107,6 +149,21 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.nv is not None:
+            self.halt = True
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+            if not self.samples:  # region shorter than one sampling period: take one sample now
+                try:
+                    self.samples.append((float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)), 0))
+                except Exception:
+                    pass
+            sm = [x[0] for x in self.samples]
+            bits = 0
+            for x in self.samples:
+                bits |= x[1]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(name for bit, name in self.REASONS if bits & bit), "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -130,7 +187,7 @@ class ClockSampler:
                     reasons.add(name)
         os.unlink(self.path)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peak_hbm():
@@ -301,14 +358,17 @@ def run_ours(args):
             batches_dev = [to_dev(b) for b in batches_host]
             torch.cuda.synchronize()
 
-            def step(s):
-                return device.join_push_device(join, abi.SIDE_LEFT, shuffled(batches_dev[s]), stream)
+            # N=1: the step's input is the resident batch; N>1: the exchange is part of the step
+            chunks_dev = [dchunk(b) for b in batches_dev] if world == 1 else None
 
+            def step(s):
+                return device.join_push_device(join, abi.SIDE_LEFT, chunks_dev[s] if world == 1 else shuffled(batches_dev[s]), stream)
+
+            sampler = ClockSampler(local_rank)
             for s in range(W):
                 step(s)
             device.profile(join, "join", True)
             l0 = device.launches(join, "join")
-            sampler = ClockSampler(local_rank)
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
@@ -347,12 +407,12 @@ def run_ours(args):
                            "l2": "inputs_larger_than_l2 (fresh 32 MiB batch per step; >1.3 GB of join state)",
                            "exchange": None if world == 1 else ex_name},
                 "build_rows_per_s": N_BUILD * world / build_s, "out_rows": out_rows, "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "join_inner_fused_kernel<false> (probe + emit + own-side append)",
+                "roofline": {"bound": "hbm", "kernel": "join_inner_q4_kernel<false> (probe + emit + own-side append, 4 lanes per row)",
                              "achieved": fused_gbs, "peak": peak, "unit": "GB/s", "frac": fused_gbs / peak if fused_gbs else None,
                              "traffic": None, "peak_source": which, "algorithmic_bytes_per_row": JOIN_BYTES_PER_ROW_STEP,
                              "rows_per_launch": BATCH, "kernel_ms_avg": kern_ms / max(kern_n, 1),
                              "kernel_share_of_step": kern_ms / ms if ms else None}})
-            del join, batches_dev
+            del join, batches_dev, chunks_dev
             torch.cuda.empty_cache()
 
         # ================================================================ leg: e2e (host buffers, C ABI)

@@ -1,9 +1,39 @@
 // api.cu -- host-only parts of the C ABI: errors, type table, output object, misc.
 #include <stdlib.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rw {
+
+// driver entry points of the virtual memory management API, resolved once through the runtime
+static VmmApi load_vmm_api() {
+  VmmApi a;
+  // opt-in: on the B200 boxes measured (profiles/README.md) cuMemCreate+cuMemMap of a few hundred MB took
+  // 8-11 ms, cudaMalloc + device copy + cudaFree of the same store 0.3-0.7 ms
+  if (!getenv("RWGPU_VMM")) return a;
+  auto get = [](const char* name, void** fn) -> bool {
+    cudaDriverEntryPointQueryResult q;
+    *fn = nullptr;
+    return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+  };
+  bool ok = get("cuMemAddressReserve", (void**)&a.AddressReserve);
+  ok = ok && get("cuMemAddressFree", (void**)&a.AddressFree);
+  ok = ok && get("cuMemCreate", (void**)&a.Create);
+  ok = ok && get("cuMemRelease", (void**)&a.Release);
+  ok = ok && get("cuMemMap", (void**)&a.Map);
+  ok = ok && get("cuMemUnmap", (void**)&a.Unmap);
+  ok = ok && get("cuMemSetAccess", (void**)&a.SetAccess);
+  ok = ok && get("cuMemGetAllocationGranularity", (void**)&a.GetGranularity);
+  a.ok = ok;
+  if (!ok) cudaGetLastError();  // clear the sticky-less error state of a failed lookup
+  return a;
+}
+const VmmApi& vmm_api() {
+  static const VmmApi a = load_vmm_api();
+  return a;
+}
 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }

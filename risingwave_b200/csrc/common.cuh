@@ -1,9 +1,11 @@
 // common.cuh -- shared host/device helpers for librwgpu (sm_100a).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
 
+#include <algorithm>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -52,6 +54,133 @@ struct DevBuf {
     return e;
   }
   template <class T> T* as() const { return (T*)p; }
+};
+
+// Device buffer that GROWS IN PLACE: a virtual address range is reserved once (cuMemAddressReserve)
+// and physical memory is mapped behind it chunk by chunk (cuMemCreate / cuMemMap).  Join state
+// keeps growing while the stream runs; growing a cudaMalloc'd store means allocating the doubled
+// store, copying hundreds of MB and freeing the old one in the middle of the data path, growing
+// this one touches no existing byte and keeps every device pointer valid.  The driver entry points
+// are looked up at run time (cudaGetDriverEntryPoint), so the library has no link dependency on
+// libcuda and still loads on a machine without a driver.  If the VMM API is unavailable the buffer
+// degrades to allocate-copy-free.
+struct VmmApi {
+  bool ok = false;
+  CUresult (*AddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*Create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*GetGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+};
+const VmmApi& vmm_api();  // api.cu
+
+struct GrowBuf {
+  CUdeviceptr base = 0;
+  size_t reserved = 0, mapped = 0, gran = 0;
+  int dev = 0;
+  std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;
+  DevBuf plain;          // fallback storage
+  bool use_vmm = false, decided = false;
+  GrowBuf() {}
+  GrowBuf(const GrowBuf&) = delete;
+  GrowBuf& operator=(const GrowBuf&) = delete;
+  ~GrowBuf() { release(); }
+  void* p() const { return use_vmm ? (void*)base : plain.p; }
+  size_t bytes() const { return use_vmm ? mapped : plain.bytes; }
+  template <class T> T* as() const { return (T*)p(); }
+  void release() {
+    if (use_vmm) {
+      const VmmApi& a = vmm_api();
+      size_t off = 0;
+      for (auto& c : chunks) {
+        a.Unmap(base + off, c.second);
+        a.Release(c.first);
+        off += c.second;
+      }
+      chunks.clear();
+      if (base) a.AddressFree(base, reserved);
+      base = 0; reserved = 0; mapped = 0;
+    }
+    plain.release();
+  }
+  // make at least `need` bytes usable; the first `live` bytes keep their contents (always true for
+  // the VMM path; the fallback copies them on `st`).  `va_limit` bounds the address reservation.
+  cudaError_t ensure(size_t need, size_t live, size_t va_limit, cudaStream_t st) {
+    if (need <= bytes()) return cudaSuccess;
+    if (!decided) {
+      decided = true;
+      const VmmApi& a = vmm_api();
+      if (a.ok && cudaGetDevice(&dev) == cudaSuccess) {
+        CUmemAllocationProp prop;
+        memset(&prop, 0, sizeof(prop));
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = dev;
+        size_t g = 0;
+        if (a.GetGranularity(&g, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) == CUDA_SUCCESS && g) {
+          gran = g;
+          size_t want = (std::max(va_limit, need) + gran - 1) / gran * gran;
+          if (a.AddressReserve(&base, want, 0, 0, 0) == CUDA_SUCCESS) {
+            reserved = want;
+            use_vmm = true;
+          }
+        }
+      }
+    }
+    if (use_vmm) {
+      if (need > reserved) return cudaErrorMemoryAllocation;
+      const VmmApi& a = vmm_api();
+      // geometric growth in mapped chunks (amortises the map calls), never below the granularity
+      size_t add = std::max(need - mapped, std::max(mapped / 2, gran));
+      add = std::min((add + gran - 1) / gran * gran, reserved - mapped);
+      CUmemAllocationProp prop;
+      memset(&prop, 0, sizeof(prop));
+      prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+      prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      prop.location.id = dev;
+      CUmemGenericAllocationHandle hnd;
+      CUresult r = a.Create(&hnd, add, &prop, 0);
+      if (r != CUDA_SUCCESS && add > (need - mapped + gran - 1) / gran * gran) {  // retry with the bare minimum
+        add = (need - mapped + gran - 1) / gran * gran;
+        r = a.Create(&hnd, add, &prop, 0);
+      }
+      if (r != CUDA_SUCCESS) return cudaErrorMemoryAllocation;
+      if (a.Map(base + mapped, add, 0, hnd, 0) != CUDA_SUCCESS) { a.Release(hnd); return cudaErrorMemoryAllocation; }
+      CUmemAccessDesc acc;
+      memset(&acc, 0, sizeof(acc));
+      acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      acc.location.id = dev;
+      acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+      if (a.SetAccess(base + mapped, add, &acc, 1) != CUDA_SUCCESS) {
+        a.Unmap(base + mapped, add);
+        a.Release(hnd);
+        return cudaErrorMemoryAllocation;
+      }
+      chunks.emplace_back(hnd, add);
+      mapped += add;
+      return cudaSuccess;
+    }
+    // fallback: allocate, copy the live prefix, free
+    size_t ncap = std::max(need, plain.bytes * 2);
+    DevBuf nb;
+    cudaError_t e = nb.reserve(ncap);
+    if (e != cudaSuccess) {
+      ncap = need;
+      e = nb.reserve(ncap);
+      if (e != cudaSuccess) return e;
+    }
+    if (live && plain.p) {
+      e = cudaMemcpyAsync(nb.p, plain.p, live, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return e;
+      e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return e;
+    }
+    plain = std::move(nb);
+    return cudaSuccess;
+  }
 };
 
 struct PinnedBuf {

@@ -65,6 +65,7 @@ __device__ __host__ __forceinline__ uint32_t W_count(uint64_t W) { return (uint3
 #define JERR_DOUBLE_DELETE 1u
 #define JERR_OUT_CAPACITY 2u
 #define JERR_APPEND_ONLY_MULTI 4u
+#define JERR_STORE_CAPACITY 8u
 
 struct JoinPlanDev {
   int T;
@@ -97,6 +98,8 @@ struct JoinSideDev {
   uint8_t* recs;     // overflow record store
   uint8_t* buckets;  // hash index with inline records
   uint64_t cap;
+  uint2* pools;      // per-warp row-id pools of the overflow store {next, end} (join_inner_q4_kernel)
+  uint64_t rec_cap;  // records the overflow store can hold
   int stride;
   int bstride;
 };
@@ -183,6 +186,11 @@ __device__ __forceinline__ uint64_t key_hash(const JoinPlanDev* p, const uint64_
   return h;
 }
 
+// Key64 tables: the probe sequence of a key starts at an EVEN bucket, i.e. at a 128-byte aligned pair
+// of 64-byte buckets, and continues bucket by bucket.  The quad-cooperative kernel fetches the whole
+// pair with one 32-byte load per lane: the second probe of a collision costs no second trip to HBM.
+__device__ __forceinline__ uint64_t home64(uint64_t key, uint64_t mask) { return mix64(key) & mask & ~1ull; }
+
 // bucket = [key word(s)] [state word W] [inline record]
 __device__ __forceinline__ uint8_t* bkt(const JoinSideDev& s, int64_t b) { return s.buckets + (uint64_t)b * s.bstride; }
 __device__ __forceinline__ unsigned long long* bkt_W(const JoinSideDev& s, const JoinPlanDev* p, int64_t b) {
@@ -255,7 +263,7 @@ __device__ __forceinline__ int64_t js_find(const JoinSideDev& s, const JoinPlanD
     if (nm) side = (int64_t)s.cap;                         // NULL key side slot (null-safe equality)
     else if (kw[0] == J_EMPTY) side = (int64_t)s.cap + 1;
     if (side >= 0) { *hc = __ldcg((const unsigned long long*)(bkt(s, side) + 8)); return side; }
-    uint64_t idx = mix64(kw[0]) & mask;
+    uint64_t idx = home64(kw[0], mask);
     while (true) {
       const ulonglong2 sl = __ldcg((const ulonglong2*)bkt(s, (int64_t)idx));  // key + head/count in one 128-bit load
       if (sl.x == kw[0]) { *hc = sl.y; return (int64_t)idx; }
@@ -286,7 +294,7 @@ __device__ __forceinline__ int64_t js_find_or_insert(const JoinSideDev& s, const
   if (p->single_key) {
     if (nm) return (int64_t)s.cap;
     if (kw[0] == J_EMPTY) return (int64_t)s.cap + 1;
-    uint64_t idx = mix64(kw[0]) & mask;
+    uint64_t idx = home64(kw[0], mask);
     while (true) {
       unsigned long long* ptr = (unsigned long long*)bkt(s, (int64_t)idx);
       unsigned long long cur = __ldcg(ptr);
@@ -693,7 +701,7 @@ __global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const Joi
             store[k] = ins;
             if (!ins) n_del++;
             if (!PROBE_ONLY && ins && p->single_key && !nm)  // the own-side bucket is claimed in phase 4: start fetching it
-              prefetch_l2(bkt(own, (int64_t)(mix64(kw[0]) & (own.cap - 1))));
+              prefetch_l2(bkt(own, (int64_t)home64(kw[0], own.cap - 1)));
             uint64_t hc;
             const int64_t b = js_find(other, p, kw, nm, &hc);
             if (b >= 0) {
@@ -829,6 +837,7 @@ __global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const Joi
 // Rows it cannot take (key == EMPTY sentinel, matched record with NULLs, keys with several rows)
 // fall through to the same helpers the generic kernel uses.
 #define W8_MAXC 8
+#define Q4_MAX_GRID (148 * 8)  // blocks of JF_BLOCK threads; one row-id pool per warp
 struct W8Plan {
   int n_u, n_m;            // columns of the update / matched side (all 8 bytes wide)
   int key_col;             // key column of the update side
@@ -881,8 +890,8 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinP
     int64_t ob = -1;
     // ---- probe: the whole 64-byte bucket of the other side in one round trip
     if (fast) {
-      if (!PROBE_ONLY && ins) prefetch_l2(bkt(own, (int64_t)(mix64(key) & wmask)));
-      uint64_t idx = mix64(key) & omask;
+      if (!PROBE_ONLY && ins) prefetch_l2(bkt(own, (int64_t)home64(key, wmask)));
+      uint64_t idx = home64(key, omask);
       while (true) {
         const uint8_t* bp = bkt(other, (int64_t)idx);
         const ulonglong2 h0 = __ldcg((const ulonglong2*)bp);          // key | head/count
@@ -963,7 +972,7 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinP
       bool created = false, inline_won = false;
       int64_t wb;
       if (key != J_EMPTY) {
-        uint64_t idx = mix64(key) & wmask;
+        uint64_t idx = home64(key, wmask);
         while (true) {
           ulonglong2* bp = (ulonglong2*)bkt(own, (int64_t)idx);
           ulonglong2 cur = __ldcg(bp);
@@ -1044,16 +1053,33 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinP
 // Rows the quad cannot finish this way (sentinel key, several matches, match not in the inline
 // record, NULLs in the matched record) are finished by lane 0 with the generic helpers.
 // Output convention: positional, exactly as join_inner_w8p_kernel.
+struct U256 { uint64_t a, b, c, d; };
+// one 32-byte load (LDG.E.256, sm_100), L2 only
+__device__ __forceinline__ U256 ld256_cg(const void* ptr) {
+  U256 v;
+  asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(ptr));
+  return v;
+}
 __device__ __forceinline__ uint64_t shfl64m(unsigned mask, uint64_t v, int src) {
   return (uint64_t)__shfl_sync(mask, (unsigned long long)v, src);
 }
 
-template <bool PROBE_ONLY>
-__global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_q4_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch,
+template <bool PROBE_ONLY, int MINB>
+__global__ void __launch_bounds__(JF_BLOCK, MINB) join_inner_q4_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch,
                                                                      JoinSideDev own, JoinSideDev other, JoinOutDev o, JoinStatus* st,
-                                                                     uint32_t store_base, uint32_t seq_base, int64_t out_base) {
+                                                                     uint32_t store_base, uint32_t seq_base, int64_t out_base, uint32_t pool_chunk) {
   const int lane = lane_id(), q = lane & 3, qlead = lane & ~3;
-  const unsigned qmask = 0xFu << qlead;
+  // Overflow row ids come from a per-warp pool that persists across launches: one atomicAdd on the
+  // shared counter hands a warp `pool_chunk` ids.  (One atomicAdd per 8 rows on that single address
+  // was measured at +0.3 ms per 2^20 rows -- same-address atomics serialise in one L2 slice.)
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  uint32_t pool_next = 0, pool_end = 0;
+  if (!PROBE_ONLY) {
+    const uint2 pl = own.pools[warp_global];
+    pool_next = pl.x;
+    pool_end = pl.y;
+  }
+  const uint32_t pool_next0 = pool_next, pool_end0 = pool_end;
   const uint64_t omask = other.cap - 1, wmask = own.cap - 1;
   unsigned int new_keys = 0, n_del = 0;
   bool any_match = false, any_hole = false;
@@ -1078,60 +1104,86 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_q4_kernel(const JoinPl
   cas_empty.x = J_EMPTY;
   cas_empty.y = W_EMPTY;
   cas_want.y = (W_EMPTY | W_IL_LIVE) + W_COUNT_ONE;
-  for (int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < groups; g += nwarps) {
+  // All shuffles use the full-warp mask and sit in warp-uniform control flow: a shuffle with a
+  // per-quad mask splits the warp into eight separately issued groups (measured: 2.8x slower).
+  // Software pipeline: the (sequential) column loads of the warp's NEXT group are issued right after
+  // the random accesses of the current one, so they are out of the dependent chain
+  // ops -> key -> bucket / CAS -> chain CAS that bounds this latency-bound kernel.
+  uint8_t n_op = 0;
+  uint64_t n_key = J_EMPTY, n_va = 0ull, n_vb = 0ull;
+  auto fetch = [&](int64_t g2) {
+    const int64_t r2 = g2 * 8 + (lane >> 2);
+    n_op = 0;
+    if (g2 < groups && r2 < ch.n) {
+      n_op = ch.ops[r2];
+      n_key = __ldg(pk + r2);
+      if (pa) n_va = __ldg(pa + r2);
+      if (pb) n_vb = __ldg(pb + r2);
+    }
+  };
+  fetch(warp_global);
+  for (int64_t g = warp_global; g < groups; g += nwarps) {
     const int64_t r = g * 8 + (lane >> 2);
-    if (r >= ch.n) continue;
-    const uint8_t op = ch.ops[r];
+    const bool in = r < ch.n;
+    const uint8_t op = n_op;
+    const uint64_t key = n_key, va = n_va, vb = n_vb;
     const int64_t pos = out_base + r;
-    if (op == 0) {  // invisible input row
+    const bool act = op != 0;
+    if (in && !act) {  // invisible input row
       if (q == 0) o.vis[pos] = 0;
       any_hole = true;
-      continue;
     }
-    const bool ins = (op == RW_OP_INSERT || op == RW_OP_UPDATE_INSERT);
-    if (!ins && q == 0) n_del++;
-    const uint64_t key = __ldg(pk + r);
-    const uint64_t va = pa ? __ldg(pa + r) : 0ull, vb = pb ? __ldg(pb + r) : 0ull;
-    const bool keyok = key != J_EMPTY;
+    const bool ins = act && (op == RW_OP_INSERT || op == RW_OP_UPDATE_INSERT);
+    if (act && !ins && q == 0) n_del++;
+    const bool keyok = act && key != J_EMPTY;
     const uint64_t hsh = mix64(key);
     // ---- own side: speculative claim, in flight together with the probe
+    const bool do_ins = !PROBE_ONLY && ins;
+    // (the result `cf` is only looked at after the probe: comparing it here would make the warp
+    // wait for the atomic before the probe load is even issued)
     ulonglong2 cf;
     cf.x = 0; cf.y = 0;
-    bool cas_ok = false;
-    uint64_t widx = hsh & wmask;
-    if (!PROBE_ONLY && ins && keyok && q == 0) {
+    uint64_t widx = hsh & wmask & ~1ull;
+    if (do_ins && keyok && q == 0) {
       cas_want.x = key;
-      cas_ok = cas128(own.buckets + widx * 64, cas_empty, cas_want, &cf);
+      cas128(own.buckets + widx * 64, cas_empty, cas_want, &cf);
     }
-    // ---- probe: each lane one 16-byte piece of the 64-byte bucket
-    bool found = false;
-    uint64_t W = 0, idx = hsh & omask;
-    ulonglong2 piece;
-    piece.x = 0; piece.y = 0;
-    if (keyok) {
-      while (true) {
-        piece = __ldcg((const ulonglong2*)(other.buckets + idx * 64 + 16 * q));
-        const uint64_t k0 = shfl64m(qmask, piece.x, qlead);
-        if (k0 == key) { found = true; W = shfl64m(qmask, piece.y, qlead); break; }
-        if (k0 == J_EMPTY) break;
-        idx = (idx + 1) & omask;
+    fetch(g + nwarps);
+    // ---- probe: the quad fetches the 128-byte bucket PAIR, one 32-byte load per lane
+    //   lane 0: A.key A.W A.hdr   lane 1: A.cols 0..3   lane 2: B.key B.W B.hdr   lane 3: B.cols 0..3
+    // the warp iterates until its longest probe sequence ends (finished quads idle)
+    bool found = false, need = keyok;
+    uint64_t idx = hsh & omask & ~1ull;
+    int sel = 0;  // 0: matched bucket A, 2: bucket B
+    U256 pv;
+    pv.a = 0; pv.b = 0; pv.c = 0; pv.d = 0;
+    while (__any_sync(0xffffffffu, need)) {
+      if (need) pv = ld256_cg(other.buckets + idx * 64 + 32 * q);
+      const uint64_t kA = shfl64m(0xffffffffu, pv.a, qlead), kB = shfl64m(0xffffffffu, pv.a, qlead + 2);
+      if (need) {
+        if (kA == key) { found = true; sel = 0; need = false; }
+        else if (kB == key) { found = true; sel = 2; need = false; }
+        else if (kA == J_EMPTY || kB == J_EMPTY) need = false;  // an empty bucket ends the probe sequence
+        else idx = (idx + 2) & omask;
       }
     }
+    const int hl = qlead + sel;  // lane holding key | W | record header of the matched bucket
+    const uint64_t W = shfl64m(0xffffffffu, pv.b, hl);
+    const uint32_t mnull = __shfl_sync(0xffffffffu, (uint32_t)(pv.c >> 32), hl);  // rec hdr: link | nullmask
+    // matched columns: lane 2 writes (0,1), lane 3 writes (2,3)
+    const uint64_t m0 = shfl64m(0xffffffffu, pv.a, hl + 1), m1 = shfl64m(0xffffffffu, pv.b, hl + 1);
+    const uint64_t m2 = shfl64m(0xffffffffu, pv.c, hl + 1), m3 = shfl64m(0xffffffffu, pv.d, hl + 1);
+    const uint64_t ma = q == 3 ? m2 : m0, mb = q == 3 ? m3 : m1;
     // ---- emit
     uint32_t cnt = found ? W_count(W) : 0u;
-    bool quad_emit = false;
-    if (cnt == 1u && W_istate(W) == 1u) {
-      const uint32_t mnull = (uint32_t)(shfl64m(qmask, piece.x, qlead + 1) >> 32);  // rec hdr: link | nullmask
-      quad_emit = mnull == 0u;
-    }
-    if (quad_emit) {
+    if (cnt == 1u && W_istate(W) == 1u && mnull == 0u) {
       any_match = true;
       if (q == 0) o.ops[pos] = ins ? RW_OP_INSERT : RW_OP_DELETE;
       if (q == 1) o.vis[pos] = 1;
-      if (po0) po0[pos] = q < 2 ? va : piece.x;
-      if (po1) po1[pos] = q < 2 ? vb : piece.y;
-    } else if (q == 0) {
-      int64_t ob = found ? (int64_t)idx : -1;
+      if (po0) po0[pos] = q < 2 ? va : ma;
+      if (po1) po1[pos] = q < 2 ? vb : mb;
+    } else if (act && q == 0) {
+      int64_t ob = found ? (int64_t)idx + (sel >> 1) : -1;
       if (!keyok) {
         uint64_t kw[1] = {key}, hc = 0;
         ob = js_find(other, p, kw, 0, &hc);
@@ -1161,47 +1213,62 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_q4_kernel(const JoinPl
       }
     }
     // ---- append to the own side
-    if (!PROBE_ONLY && ins) {
-      uint64_t recp = 0;
-      uint32_t link = 0u;
-      if (q == 0) {
-        bool created = false, inline_won = false;
-        unsigned long long Wcur = 0ull;
-        unsigned long long* Wp;
-        if (keyok) {
-          while (true) {
-            if (cas_ok) { created = true; inline_won = true; break; }
-            if (cf.x == key) { Wcur = cf.y; break; }
-            widx = (widx + 1) & wmask;  // bucket held by another key
-            cas_ok = cas128(own.buckets + widx * 64, cas_empty, cas_want, &cf);
-          }
-          Wp = (unsigned long long*)(own.buckets + widx * 64 + 8);
-        } else {
-          uint64_t kw[1] = {key};
-          widx = (uint64_t)js_find_or_insert(own, p, kw, 0, &created);
-          Wp = (unsigned long long*)(own.buckets + widx * 64 + 8);
-          Wcur = __ldcg(Wp);
+    uint64_t recp = 0;
+    uint32_t link = 0u;
+    bool need_ovf = false;
+    unsigned long long Wcur = 0ull;
+    unsigned long long* Wp = nullptr;
+    if (do_ins && q == 0) {
+      bool created = false, inline_won = false;
+      if (keyok) {
+        while (true) {
+          if (cf.x == J_EMPTY && cf.y == W_EMPTY) { created = true; inline_won = true; break; }  // the CAS took the bucket
+          if (cf.x == key) { Wcur = cf.y; break; }
+          widx = (widx + 1) & wmask;  // bucket held by another key
+          cas128(own.buckets + widx * 64, cas_empty, cas_want, &cf);
         }
-        if (created) new_keys++;
-        if (!inline_won) {
-          while (W_istate(Wcur) != 1u) {  // the inline record is free (never used, or its row was deleted)
-            const unsigned long long nw = ((Wcur & ~W_IL_MASK) | W_IL_LIVE) + W_COUNT_ONE;
-            const unsigned long long old = atomicCAS(Wp, Wcur, nw);
-            if (old == Wcur) { inline_won = true; break; }
-            Wcur = old;
-          }
+        Wp = (unsigned long long*)(own.buckets + widx * 64 + 8);
+      } else {
+        uint64_t kw[1] = {key};
+        widx = (uint64_t)js_find_or_insert(own, p, kw, 0, &created);
+        Wp = (unsigned long long*)(own.buckets + widx * 64 + 8);
+        Wcur = __ldcg(Wp);
+      }
+      if (created) new_keys++;
+      if (!inline_won) {
+        while (W_istate(Wcur) != 1u) {  // the inline record is free (never used, or its row was deleted)
+          const unsigned long long nw = ((Wcur & ~W_IL_MASK) | W_IL_LIVE) + W_COUNT_ONE;
+          const unsigned long long old = atomicCAS(Wp, Wcur, nw);
+          if (old == Wcur) { inline_won = true; break; }
+          Wcur = old;
         }
-        if (inline_won) {
-          recp = (uint64_t)(own.buckets + widx * 64 + 16);
+      }
+      if (inline_won) recp = (uint64_t)(own.buckets + widx * 64 + 16);
+      else need_ovf = true;
+    }
+    if (!PROBE_ONLY) {
+      const unsigned bal = __ballot_sync(0xffffffffu, need_ovf);
+      if (bal) {  // warp-uniform: ids for the rows that go to the overflow store
+        const uint32_t k = __popc(bal), left = pool_end - pool_next;
+        uint32_t nb = 0;
+        if (left < k) {  // refill; the remainder of the old chunk is used up first
+          if (lane == 0) {
+            nb = store_base + (uint32_t)atomicAdd(&st->n_store, (unsigned long long)pool_chunk);
+            if ((uint64_t)nb + pool_chunk > own.rec_cap) { atomicOr(&st->err, JERR_STORE_CAPACITY); nb = 0xffffffffu; }
+          }
+          nb = __shfl_sync(0xffffffffu, nb, 0);
+        }
+        const uint32_t i = __popc(bal & ((1u << lane) - 1u));
+        const uint32_t row = i < left ? pool_next + i : nb + (i - left);
+        const bool bad = left < k && nb == 0xffffffffu;
+        if (left < k) {
+          pool_next = bad ? 0u : nb + (k - left);
+          pool_end = bad ? 0u : nb + pool_chunk;
         } else {
-          // overflow row: id from a warp-aggregated reservation, then one CAS pushes it on the chain
-          const unsigned m = __activemask();
-          const int leader = __ffs(m) - 1;
-          unsigned long long base = 0;
-          if (lane == leader) base = atomicAdd(&st->n_store, (unsigned long long)__popc(m));
-          base = __shfl_sync(m, base, leader);
-          const uint32_t row = store_base + (uint32_t)base + __popc(m & ((1u << lane) - 1));
-          while (true) {
+          pool_next += k;
+        }
+        if (need_ovf && !(bad && i >= left)) {
+          while (true) {  // one CAS pushes the row on the key's chain
             const unsigned long long nw = ((Wcur & ~0x7fffffffull) | (unsigned long long)row) + W_COUNT_ONE;
             const unsigned long long old = atomicCAS(Wp, Wcur, nw);
             if (old == Wcur) break;
@@ -1211,9 +1278,9 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_q4_kernel(const JoinPl
           recp = (uint64_t)rec_ptr(own, row);
         }
       }
-      recp = shfl64m(qmask, recp, qlead);
-      link = __shfl_sync(qmask, link, qlead);
-      if (q != 0) {
+      recp = shfl64m(0xffffffffu, recp, qlead);
+      link = __shfl_sync(0xffffffffu, link, qlead);
+      if (do_ins && q != 0 && recp) {
         ulonglong2 v;
         if (q == 1) {  // RecHdr {link, nullmask = 0, seq, degree = 0}
           v.x = (unsigned long long)link;
@@ -1226,6 +1293,7 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_q4_kernel(const JoinPl
       }
     }
   }
+  if (!PROBE_ONLY && lane == 0 && (pool_next != pool_next0 || pool_end != pool_end0)) own.pools[warp_global] = make_uint2(pool_next, pool_end);
   unsigned long long flags = (any_hole ? (1ull << 63) : 0ull);
   const bool warp_match = __any_sync(0xffffffffu, any_match);
   for (int d = 16; d > 0; d >>= 1) {
@@ -1322,7 +1390,7 @@ __global__ void join_rehash_kernel(const uint8_t* ob, uint64_t ocap, uint8_t* nb
       const uint64_t mask = ncap - 1;
       uint64_t idx;
       if (single_key) {
-        idx = mix64(w0) & mask;
+        idx = home64(w0, mask);
         while (atomicCAS((unsigned long long*)(nb + idx * bstride), (unsigned long long)J_EMPTY, (unsigned long long)w0) != J_EMPTY) idx = (idx + 1) & mask;
       } else {
         uint32_t nm = (uint32_t)((w0 >> 8) & 0xff);
@@ -1348,7 +1416,9 @@ using namespace rw;
 struct JoinSideHost {
   int n_cols = 0;
   std::vector<int> types;
-  DevBuf recs, slots;  // slots = bucket array
+  GrowBuf recs;        // overflow record store (grows in place)
+  DevBuf slots;        // bucket array
+  DevBuf pools;        // per-warp row-id pools of join_inner_q4_kernel
   int stride = 0, bstride = 0;
   uint64_t row_cap = 0;   // records allocated
   uint64_t n_rows = 0;    // records handed out (incl. dead ones)
@@ -1407,6 +1477,8 @@ static JoinSideDev side_dev(const rwgpu_join* h, int S) {
   const JoinSideHost& s = h->side[S];
   JoinSideDev d;
   d.recs = s.recs.as<uint8_t>();
+  d.pools = s.pools.as<uint2>();
+  d.rec_cap = s.row_cap;
   d.buckets = s.slots.as<uint8_t>();
   d.cap = s.slot_cap;
   d.stride = s.stride;
@@ -1423,19 +1495,18 @@ static int join_alloc_slots(rwgpu_join* h, int S, DevBuf& buf, uint64_t cap) {
   return RW_OK;
 }
 
-// grow the record store of side S to hold at least `rows` records (contents preserved)
+// grow the record store of side S to hold at least `rows` records (contents preserved, in place)
 static int join_grow_store(rwgpu_join* h, int S, uint64_t rows) {
   JoinSideHost& s = h->side[S];
   if (rows <= s.row_cap) return RW_OK;
   if (rows >= 0x7ffffff0ull) return fail(RW_ERR_OOM, "join side exceeds 2^31 rows");
-  uint64_t ncap = std::max<uint64_t>(s.row_cap * 2, std::max<uint64_t>(rows, 1 << 16));
-  ncap = std::min<uint64_t>(ncap, 0x7ffffff0ull);
-  DevBuf nb;
-  RW_CUDA(nb.reserve(ncap * (size_t)s.stride));
-  if (s.n_rows) RW_CUDA(cudaMemcpyAsync(nb.p, s.recs.p, s.n_rows * (size_t)s.stride, cudaMemcpyDeviceToDevice, h->stream));
-  RW_CUDA(cudaStreamSynchronize(h->stream));
-  s.recs = std::move(nb);
-  s.row_cap = ncap;
+  // address space for the whole row-id range, capped at the device's memory size
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const size_t va_limit = std::min<size_t>((size_t)0x7ffffff0ull * (size_t)s.stride, std::max<size_t>(total_b, (size_t)1 << 30));
+  cudaError_t e = s.recs.ensure((size_t)rows * (size_t)s.stride, (size_t)s.n_rows * (size_t)s.stride, va_limit, h->stream);
+  if (e != cudaSuccess) return fail(RW_ERR_OOM, std::string("join record store: ") + cudaGetErrorString(e));
+  s.row_cap = std::min<uint64_t>(s.recs.bytes() / (size_t)s.stride, 0x7ffffff0ull);
   return RW_OK;
 }
 
@@ -1560,6 +1631,7 @@ static int join_check_err(rwgpu_join* h, const JoinStatus& s, cudaStream_t st) {
   cudaMemsetAsync(&h->status.as<JoinStatus>()->err, 0, sizeof(unsigned int), st);
   if (e & JERR_DOUBLE_DELETE) return fail(RW_ERR_INCONSISTENT, "removing a join state entry but it is not in the cache");
   if (e & JERR_APPEND_ONLY_MULTI) return fail(RW_ERR_INCONSISTENT, "append-only optimisation: more than one matched row");
+  if (e & JERR_STORE_CAPACITY) return fail(RW_ERR_CUDA, "internal: join record store capacity");
   return fail(RW_ERR_CUDA, "internal: join output capacity");
 }
 
@@ -1578,7 +1650,14 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double tt0 = now();
   const uint64_t cap0 = own.slot_cap, rcap0 = own.row_cap;
-  int rc = join_grow_store(h, S, own.n_rows + (uint64_t)n);
+  // quad-cooperative kernel: its warps draw overflow row ids from persistent pools in chunks, so the
+  // id counter can run ahead of the rows really stored by one chunk per warp
+  static const bool no_q4 = getenv("RWGPU_NO_Q4") != nullptr;
+  const bool q4 = h->fast_inner && h->q4_ok && !no_q4;
+  const int q4_grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 63) / 64, Q4_MAX_GRID));
+  uint32_t pool_chunk = 32;
+  while (pool_chunk < 256 && (int64_t)pool_chunk * q4_grid * 8 < 4 * n) pool_chunk <<= 1;
+  int rc = join_grow_store(h, S, own.n_rows + (uint64_t)n + (q4 ? (uint64_t)q4_grid * 8 * pool_chunk : 0));
   if (rc != RW_OK) return rc;
   rc = join_grow_slots(h, S, own.keys_upper + (uint64_t)n);
   if (rc != RW_OK) return rc;
@@ -1604,17 +1683,17 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
       rc = join_ensure_out(h, out_base + n + std::max<int64_t>(n / 2, 4096), st, out_base);
       if (rc != RW_OK) return rc;
       // quad-cooperative kernel when both sides fit a 64-byte bucket (<= 4 columns); else one thread per row
-      static const bool no_q4 = getenv("RWGPU_NO_Q4") != nullptr;
-      const bool q4 = h->q4_ok && !no_q4;
-      const int grid = q4 ? (int)std::max<int64_t>(1, std::min<int64_t>((n + 63) / 64, 148 * 6)) : jgrid(n, JF_BLOCK);
+      const int grid = q4 ? q4_grid : jgrid(n, JF_BLOCK);
       auto launch = [&](bool probe_only, uint32_t store_base) {
         if (q4) {
-          if (probe_only)
-            join_inner_q4_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
-                                                                   store_base, seq_base, out_base);
-          else
-            join_inner_q4_kernel<false><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
-                                                                    store_base, seq_base, out_base);
+          static const int minb = getenv("RWGPU_Q4_MINB") ? atoi(getenv("RWGPU_Q4_MINB")) : 4;  // occupancy experiment
+#define Q4_LAUNCH(PO, MB)                                                                                                              \
+  join_inner_q4_kernel<PO, MB><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds, \
+                                                          store_base, seq_base, out_base, pool_chunk)
+          if (probe_only) Q4_LAUNCH(true, 4);
+          else if (minb == 6) Q4_LAUNCH(false, 6);
+          else Q4_LAUNCH(false, 4);  // measured: 3 blocks/SM 0.262 ms, 4: 0.227, 5: 0.267, 6: 0.300, 8: 0.329 per 2^20 rows
+#undef Q4_LAUNCH
         } else {
           if (probe_only)
             join_inner_w8p_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
@@ -1723,7 +1802,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
     cub::DeviceRadixSort::SortKeys(h->cub_tmp.p, tb, db, (int)n, 0, 64, st);
     RW_CUDA(cudaGetLastError());
     h->launches += 6;
-    rc = join_read_status(h, st, &hs);
+    rc = join_read_status(h, st, &hs, 0);  // n_store (written by join_totals_kernel) must survive until the second read
     if (rc != RW_OK) return rc;
     const int64_t reserved = (int64_t)hs.out_rows;
     rc = join_ensure_out(h, out_base + reserved, st, out_base);
@@ -1908,6 +1987,9 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
     rc = join_alloc_slots(h, s, h->side[s].slots, cap);
     if (rc != RW_OK) return rc;
     rc = join_grow_store(h, s, 1024);  // overflow rows only; grows on demand
+    if (rc != RW_OK) return rc;
+    RW_CUDA(h->side[s].pools.reserve((size_t)Q4_MAX_GRID * (JF_BLOCK / 32) * sizeof(uint2)));
+    RW_CUDA(cudaMemsetAsync(h->side[s].pools.p, 0, h->side[s].pools.bytes, h->stream));
     if (rc != RW_OK) return rc;
   }
   RW_CUDA(cudaStreamSynchronize(h->stream));
