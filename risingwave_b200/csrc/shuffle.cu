@@ -179,19 +179,32 @@ __global__ void __launch_bounds__(PART_BLOCK) part_hist_kernel(DevChunk ch, Vnod
   if (threadIdx.x < n_dest) block_hist[(size_t)blockIdx.x * n_dest + threadIdx.x] = hist[threadIdx.x];
 }
 
-// pass 2: one block; per destination exclusive scan over blocks -> block offsets; totals + region starts
-__global__ void part_scan_kernel(uint32_t* block_hist, int n_blocks, int n_dest, int64_t* counts, int64_t* offsets) {
+// pass 2: one block; per destination exclusive scan over blocks -> block offsets; totals + region starts.
+// One WARP per destination scans the per-block counts 32 at a time (shuffle scan, the chunk loads do
+// not depend on each other); a serial loop over 512 blocks per thread cost ~100 us of a 1M-row batch.
+#define PART_SCAN_THREADS 1024
+__global__ void __launch_bounds__(PART_SCAN_THREADS) part_scan_kernel(uint32_t* block_hist, int n_blocks, int n_dest, int64_t* counts,
+                                                                       int64_t* offsets) {
   __shared__ int64_t totals[PART_MAX_DEST];
-  int d = threadIdx.x;
-  if (d < n_dest) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  for (int d = wid; d < n_dest; d += n_warps) {
     uint32_t run = 0;
-    for (int b = 0; b < n_blocks; b++) {
-      uint32_t v = block_hist[(size_t)b * n_dest + d];
-      block_hist[(size_t)b * n_dest + d] = run;
-      run += v;
+    for (int b0 = 0; b0 < n_blocks; b0 += 32) {
+      const int b = b0 + lane;
+      const uint32_t v = b < n_blocks ? block_hist[(size_t)b * n_dest + d] : 0u;
+      uint32_t inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (b < n_blocks) block_hist[(size_t)b * n_dest + d] = run + inc - v;
+      run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    totals[d] = run;
-    counts[d] = run;
+    if (lane == 0) {
+      totals[d] = run;
+      counts[d] = run;
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -524,7 +537,7 @@ int32_t rwgpu_shuffle_partition_device(const rw_chunk* c, const int32_t* keys, i
   uint8_t* dest = scratch;
   uint32_t* hist = (uint32_t*)(scratch + dest_bytes);
   part_hist_kernel<<<n_blocks, PART_BLOCK, 0, st>>>(ch, p, vnode_to_dest, n_dest, dest, hist);
-  part_scan_kernel<<<1, PART_MAX_DEST, 0, st>>>(hist, n_blocks, n_dest, counts, offsets);
+  part_scan_kernel<<<1, PART_SCAN_THREADS, 0, st>>>(hist, n_blocks, n_dest, counts, offsets);
   PartOut o;
   memset(&o, 0, sizeof(o));
   o.ops = out_ops;
@@ -578,7 +591,7 @@ int32_t rwgpu_shuffle_partition_p2p_device(const rw_chunk* c, const int32_t* key
   uint32_t* hist = (uint32_t*)(scratch + dest_bytes);
   int64_t* offsets = (int64_t*)(scratch + dest_bytes + (hist_bytes + 255) / 256 * 256);
   part_hist_kernel<<<n_blocks, PART_BLOCK, 0, st>>>(ch, p, vnode_to_dest, n_dest, dest, hist);
-  part_scan_kernel<<<1, PART_MAX_DEST, 0, st>>>(hist, n_blocks, n_dest, counts, offsets);
+  part_scan_kernel<<<1, PART_SCAN_THREADS, 0, st>>>(hist, n_blocks, n_dest, counts, offsets);
   part_scatter_p2p_kernel<<<n_blocks, PART_BLOCK, 0, st>>>(ch, dest, hist, n_dest, L, pb, my_rank, overflow);
   p2p_publish_counts_kernel<<<1, PART_MAX_DEST, 0, st>>>(counts, n_dest, L, pb, my_rank);
   RW_CUDA(cudaGetLastError());

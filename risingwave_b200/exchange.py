@@ -69,6 +69,17 @@ class ShufflePlan:
         ins, outs = plan_splits(counts)
         return all_to_all_columns(ops, cols, ins, outs)
 
+    def start(self, chunk, stream=None):
+        """same interface as P2PShufflePlan (the NCCL path needs the split sizes on the host in the
+        middle, so the whole exchange happens here)"""
+        if stream is None:
+            return self.exchange(chunk, stream)
+        with torch.cuda.stream(stream):
+            return self.exchange(chunk, stream)
+
+    def finish(self, token):
+        return token
+
 
 class P2PShufflePlan:
     """Hash shuffle with the transfer fused into the partition kernel: every rank's scatter kernel
@@ -100,23 +111,45 @@ class P2PShufflePlan:
             self.peers.append([int(h.buffer_ptrs[r]) for r in range(world)])
         self.counts = torch.zeros(world, dtype=torch.int64, device="cuda")
         self.overflow = torch.zeros(1, dtype=torch.int32, device="cuda")
-        self.total = torch.zeros(1, dtype=torch.int64, device="cuda")
         self.step = 0
         self.fallback = ShufflePlan(world, rank, key_indices, types, vnode_count)
         self.max_rows = world * self.cap
+        # double-buffered outputs + row-count read-back (pinned), so that the exchange of batch s+1 can
+        # run on its own stream while the consumer still reads the rows of batch s
+        self.out, self.totals, self.totals_host, self.events = [], [], [], []
+        for _ in range(2):
+            self.out.append((torch.empty(self.max_rows, dtype=torch.uint8, device="cuda"),
+                             [torch.empty(self.max_rows, dtype=device.TORCH_DTYPE[t], device="cuda") for t in self.types]))
+            self.totals.append(torch.zeros(1, dtype=torch.int64, device="cuda"))
+            self.totals_host.append(torch.zeros(1, dtype=torch.int64).pin_memory())
+            self.events.append(torch.cuda.Event())
 
-    def exchange(self, chunk, stream=None):
+    def start(self, chunk, stream=None):
+        """enqueue partition + peer stores + barrier + unpack of one batch on `stream`; returns a token"""
         from . import device
         b = self.step & 1
         self.step += 1
-        device.shuffle_partition_p2p(chunk, self.keys, self.v2d, self.world, self.rank, self.peers[b], self.cap, self.counts,
-                                     self.overflow, self.vnode_count, stream)
-        self.hdls[b].barrier(channel=0)  # all peers' stores into my regions are complete and visible
-        ops = torch.empty(self.max_rows, dtype=torch.uint8, device="cuda")
-        cols = [torch.empty(self.max_rows, dtype=device.TORCH_DTYPE[t], device="cuda") for t in self.types]
-        device.shuffle_unpack(self.bufs[b].data_ptr(), self.world, self.types, self.cap, ops, cols, self.total, stream)
-        n = int(self.total.item())  # one 8-byte D2H (the join push needs the row count on the host anyway)
+        stream = stream if stream is not None else torch.cuda.current_stream()
+        with torch.cuda.stream(stream):  # the symmetric-memory barrier runs on the current stream
+            device.shuffle_partition_p2p(chunk, self.keys, self.v2d, self.world, self.rank, self.peers[b], self.cap, self.counts,
+                                         self.overflow, self.vnode_count, stream)
+            self.hdls[b].barrier(channel=0)  # all peers' stores into my regions are complete and visible
+            ops, cols = self.out[b]
+            device.shuffle_unpack(self.bufs[b].data_ptr(), self.world, self.types, self.cap, ops, cols, self.totals[b], stream)
+            self.totals_host[b].copy_(self.totals[b], non_blocking=True)
+            self.events[b].record(stream)
+        return b
+
+    def finish(self, b):
+        """wait for the batch of token `b`; -> (ops, cols) views of the received rows (valid until the
+        second `start` after this one)"""
+        self.events[b].synchronize()
+        n = int(self.totals_host[b][0])  # the consumer needs the row count on the host
         if n < 0:
             raise RuntimeError("p2p shuffle: a (source, destination) pair exceeded its region capacity "
                                f"({self.cap} rows); use ShufflePlan (NCCL all-to-all-v) for this stream")
+        ops, cols = self.out[b]
         return ops[:n], [c[:n] for c in cols]
+
+    def exchange(self, chunk, stream=None):
+        return self.finish(self.start(chunk, stream))
