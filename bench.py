@@ -212,6 +212,14 @@ def pin_to_gpu_numa_node(gpu_index):
         pass
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r1_traffic.json), or None"""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kernel]["bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -475,7 +483,9 @@ def run_ours(args):
                 "build_rows_per_s": N_BUILD * world / build_s, "out_rows": out_rows, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "join_inner_q4_kernel<false> (probe + emit + own-side append, 4 lanes per row)",
                              "achieved": fused_gbs, "peak": peak, "unit": "GB/s", "frac": fused_gbs / peak if fused_gbs else None,
-                             "traffic": None, "peak_source": which, "algorithmic_bytes_per_row": JOIN_BYTES_PER_ROW_STEP,
+                             "traffic": ncu_traffic("join_inner_q4_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                             "algorithmic_bytes_per_launch": JOIN_BYTES_PER_ROW_STEP * BATCH,
+                             "peak_source": which, "algorithmic_bytes_per_row": JOIN_BYTES_PER_ROW_STEP,
                              "rows_per_launch": BATCH, "kernel_ms_avg": kern_ms / max(kern_n, 1),
                              "kernel_share_of_step": kern_ms / ms if ms else None}})
             del join, batches_dev, chunks_dev
@@ -563,7 +573,7 @@ def run_ours(args):
                 "metric": "rows/s", "value": n_ep * AGG_EPOCH_ROWS / (ams / 1e3), "epochs": n_ep, "ms_per_epoch": ams / n_ep,
                 "delta_rows_per_input_row": delta_rows / (n_ep * AGG_EPOCH_ROWS),
                 "roofline": {"bound": "hbm", "kernel": "agg_apply_fast_kernel<3>", "achieved": agbs, "peak": peak, "unit": "GB/s",
-                             "frac": agbs / peak if agbs else None, "traffic": None, "peak_source": which,
+                             "frac": agbs / peak if agbs else None, "traffic": ncu_traffic("agg_apply_fast_kernel"), "peak_source": which,
                              "algorithmic_bytes_per_row": AGG_BYTES_PER_ROW_FLOOR, "kernel_ms_avg": akern_ms / max(akern_n, 1)}}
 
     if rank != 0:
