@@ -447,12 +447,22 @@ def run_ours(args):
             else:
                 # N>1: the exchange of batch s+1 (stream ex_stream) overlaps the join of batch s -- upstream
                 # dispatcher and join executor are separate actors.  Nothing is in flight when e0 is recorded.
+                t_fin = t_sta = t_join = 0.0
                 token = shuffle_start(chunks_dev[W])
                 for s in range(W, W + K):
+                    ta = time.perf_counter()
                     ch = shuffle_finish(token)
+                    tb = time.perf_counter()
                     if s + 1 < W + K:
                         token = shuffle_start(chunks_dev[s + 1])
+                    tc = time.perf_counter()
                     out_rows += device.join_push_device(join, abi.SIDE_LEFT, ch, stream).n_rows
+                    td = time.perf_counter()
+                    t_fin += tb - ta
+                    t_sta += tc - tb
+                    t_join += td - tc
+                host_phases = {"wait_exchange_ms": 1e3 * t_fin / K, "enqueue_next_exchange_ms": 1e3 * t_sta / K,
+                               "join_push_ms": 1e3 * t_join / K}
             e1.record(stream)
             torch.cuda.synchronize()
             if world > 1:
@@ -480,6 +490,7 @@ def run_ours(args):
                            "join": "inner bid.auction = auction.id, Key64, 4+4 int64 cols, 8 out cols",
                            "l2": "inputs_larger_than_l2 (fresh 32 MiB batch per step; >1.3 GB of join state)",
                            "exchange": None if world == 1 else ex_name},
+                "host_phases_per_step": host_phases if (world > 1 and not trace) else None,
                 "build_rows_per_s": N_BUILD * world / build_s, "out_rows": out_rows, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "join_inner_q4_kernel<false> (probe + emit + own-side append, 4 lanes per row)",
                              "achieved": fused_gbs, "peak": peak, "unit": "GB/s", "frac": fused_gbs / peak if fused_gbs else None,

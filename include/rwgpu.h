@@ -273,6 +273,22 @@ int32_t rwgpu_shuffle_unpack_device(const void* recv_base, int32_t n_src, const 
                                     int64_t cap_rows, uint8_t* out_ops, void* const* out_cols, int64_t* total,
                                     void* cuda_stream);
 
+/* one call = one batch of the exchange: partition + peer stores + count publication (as above), a
+ * cross-rank barrier, and the unpack -- five launches on `cuda_stream`, no library call in between.
+ *   peer_flags : HOST array of n_dest peer-mapped device pointers to each rank's flag block
+ *                (1024 bytes, zero-initialised, symmetric: uint64 flag[64] + scratch); the barrier of batch `epoch` (1, 2, ...
+ *                strictly increasing per flag array) stores `epoch` into slot my_rank of every rank's
+ *                array and waits until every slot of its own array holds >= epoch.
+ *   recv_base  : this rank's receive buffer (== peer_bases[my_rank]).
+ *   total_host : PINNED host int64 (device-addressable): receives the row count (-1 = a region
+ *                overflowed) when the unpack kernel has run; the caller waits on the stream / an event. */
+int32_t rwgpu_shuffle_exchange_p2p_device(const rw_chunk* chunk, const int32_t* key_indices, int32_t n_keys,
+                                          int32_t vnode_count, const int32_t* vnode_to_dest, int32_t n_dest,
+                                          int32_t my_rank, void* const* peer_bases, void* const* peer_flags,
+                                          uint64_t epoch, int64_t cap_rows, const void* recv_base,
+                                          uint8_t* out_ops, void* const* out_cols, int64_t* counts,
+                                          int32_t* overflow, int64_t* total_host, void* cuda_stream);
+
 /* ================================================================ misc */
 const char* rwgpu_last_error(void);
 /* 0 if a CUDA device is usable, else RW_ERR_NO_DEVICE (and every create() fails loudly). */

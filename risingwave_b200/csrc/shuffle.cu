@@ -409,6 +409,28 @@ __global__ void __launch_bounds__(256) p2p_unpack_kernel(const uint8_t* recv, in
   }
 }
 
+// cross-rank barrier on peer-mapped flag arrays: thread t signals rank t and waits for rank t's signal.
+// Everything this rank stored into its peers (earlier kernels of the stream) is ordered before the
+// signal (fence + release store at system scope); the peers' data is visible once their signal is seen.
+__global__ void p2p_barrier_kernel(PeerBases flags, int n, int my_rank, unsigned long long epoch) {
+  const int t = threadIdx.x;
+  if (t < n) {
+    __threadfence_system();
+    unsigned long long* remote = (unsigned long long*)flags.base[t] + my_rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
+    const unsigned long long* mine = (const unsigned long long*)flags.base[my_rank] + t;
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    } while (v < epoch);
+  }
+}
+
+__global__ void p2p_total_to_host_kernel(const int64_t* total, int64_t* total_host) {
+  *total_host = *total;
+  __threadfence_system();
+}
+
 static int make_vnode_plan(const rw_chunk* c, const int32_t* keys, int n_keys, int vnode_count, VnodePlan* p) {
   if (n_keys < 1 || n_keys > RW_MAX_KEYS * 2) return fail(RW_ERR_UNSUPPORTED, "1..8 distribution key columns");
   if (vnode_count < 1 || vnode_count > 32768) return fail(RW_ERR_INVALID, "vnode_count (vnode.rs:79 MAX_COUNT = 2^15)");
@@ -596,6 +618,32 @@ int32_t rwgpu_shuffle_partition_p2p_device(const rw_chunk* c, const int32_t* key
   p2p_publish_counts_kernel<<<1, PART_MAX_DEST, 0, st>>>(counts, n_dest, L, pb, my_rank);
   RW_CUDA(cudaGetLastError());
   RW_CUDA(cudaFreeAsync(scratch, st));
+  return RW_OK;
+}
+
+int32_t rwgpu_shuffle_exchange_p2p_device(const rw_chunk* c, const int32_t* keys, int32_t n_keys, int32_t vnode_count,
+                                          const int32_t* vnode_to_dest, int32_t n_dest, int32_t my_rank,
+                                          void* const* peer_bases, void* const* peer_flags, uint64_t epoch, int64_t cap_rows,
+                                          const void* recv_base, uint8_t* out_ops, void* const* out_cols, int64_t* counts,
+                                          int32_t* overflow, int64_t* total_host, void* cuda_stream) {
+  if (!peer_flags || !recv_base || !out_ops || !out_cols || !total_host || !c) return fail(RW_ERR_INVALID, "null");
+  int rc = rwgpu_shuffle_partition_p2p_device(c, keys, n_keys, vnode_count, vnode_to_dest, n_dest, my_rank, peer_bases, cap_rows,
+                                              counts, overflow, cuda_stream);
+  if (rc != RW_OK) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  PeerBases pf;
+  memset(&pf, 0, sizeof(pf));
+  for (int d = 0; d < n_dest; d++) pf.base[d] = (uint8_t*)peer_flags[d];
+  p2p_barrier_kernel<<<1, PART_MAX_DEST, 0, st>>>(pf, n_dest, my_rank, (unsigned long long)epoch);
+  RW_CUDA(cudaGetLastError());
+  std::vector<int32_t> types(c->n_cols);
+  for (int k = 0; k < c->n_cols; k++) types[k] = c->columns[k].type;
+  // the device-side total lives in the (unused) tail of this rank's flag array page: slot n_dest
+  int64_t* total_dev = (int64_t*)((uint8_t*)peer_flags[my_rank] + sizeof(uint64_t) * PART_MAX_DEST);
+  rc = rwgpu_shuffle_unpack_device(recv_base, n_dest, types.data(), c->n_cols, cap_rows, out_ops, out_cols, total_dev, cuda_stream);
+  if (rc != RW_OK) return rc;
+  p2p_total_to_host_kernel<<<1, 1, 0, st>>>(total_dev, total_host);
+  RW_CUDA(cudaGetLastError());
   return RW_OK;
 }
 

@@ -214,3 +214,30 @@ def shuffle_unpack(recv_ptr: int, n_src: int, types: Sequence[int], cap_rows: in
     colp = (C.c_void_p * len(out_cols))(*[c.data_ptr() for c in out_cols])
     _check(_lib().rwgpu_shuffle_unpack_device(C.c_void_p(recv_ptr), n_src, t, len(types), cap_rows, C.c_void_p(out_ops.data_ptr()),
                                               colp, C.c_void_p(total.data_ptr()), _stream_ptr(stream)))
+
+
+class P2PExchangeCall:
+    """Pre-built argument block of rwgpu_shuffle_exchange_p2p_device for one receive-buffer parity: the
+    per-batch call is then a single ctypes call (the step is host-latency sensitive)."""
+
+    def __init__(self, key_indices, vnode_to_dest, n_dest, my_rank, peer_ptrs, flag_ptrs, cap_rows, recv_ptr, out_ops, out_cols,
+                 counts, overflow, total_host, vnode_count=256):
+        self.keys = (C.c_int32 * len(key_indices))(*key_indices)
+        self.n_keys = len(key_indices)
+        self.peers = (C.c_void_p * n_dest)(*peer_ptrs)
+        self.flags = (C.c_void_p * n_dest)(*flag_ptrs)
+        self.colp = (C.c_void_p * len(out_cols))(*[c.data_ptr() for c in out_cols])
+        self.args = (vnode_count, C.c_void_p(vnode_to_dest.data_ptr()), n_dest, my_rank)
+        self.cap_rows, self.recv = cap_rows, C.c_void_p(recv_ptr)
+        self.out_ops = C.c_void_p(out_ops.data_ptr())
+        self.counts, self.overflow = C.c_void_p(counts.data_ptr()), C.c_void_p(overflow.data_ptr())
+        self.total_host = C.c_void_p(total_host.data_ptr())
+        self.keep = (vnode_to_dest, out_ops, out_cols, counts, overflow, total_host)
+
+    def __call__(self, chunk: DeviceChunk, epoch: int, stream):
+        ch, keep = chunk.to_abi()
+        vc, v2d, n_dest, my_rank = self.args
+        _check(_lib().rwgpu_shuffle_exchange_p2p_device(C.byref(ch), self.keys, self.n_keys, vc, v2d, n_dest, my_rank, self.peers,
+                                                        self.flags, C.c_uint64(epoch), C.c_int64(self.cap_rows), self.recv,
+                                                        self.out_ops, self.colp, self.counts, self.overflow, self.total_host,
+                                                        _stream_ptr(stream)))

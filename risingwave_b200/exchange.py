@@ -84,8 +84,9 @@ class ShufflePlan:
 class P2PShufflePlan:
     """Hash shuffle with the transfer fused into the partition kernel: every rank's scatter kernel
     stores its rows straight into the destination ranks' receive regions over NVLink peer memory
-    (torch symmetric memory supplies the peer-mapped buffers and a device-side barrier); no NCCL call
-    is on the data path.  Two receive buffers alternate, so one barrier per batch is enough: a peer
+    (torch symmetric memory supplies the peer-mapped buffers; the cross-rank barrier is the library's
+    own kernel on peer-mapped flags); no NCCL call is on the data path and one batch is ONE library
+    call.  Two receive buffers alternate, so one barrier per batch is enough: a peer
     can only start writing buffer b again after every rank passed the barrier of the batch in between,
     which each rank enqueues AFTER its own unpack of buffer b (stream order).
 
@@ -116,28 +117,33 @@ class P2PShufflePlan:
         self.max_rows = world * self.cap
         # double-buffered outputs + row-count read-back (pinned), so that the exchange of batch s+1 can
         # run on its own stream while the consumer still reads the rows of batch s
-        self.out, self.totals, self.totals_host, self.events = [], [], [], []
-        for _ in range(2):
-            self.out.append((torch.empty(self.max_rows, dtype=torch.uint8, device="cuda"),
-                             [torch.empty(self.max_rows, dtype=device.TORCH_DTYPE[t], device="cuda") for t in self.types]))
-            self.totals.append(torch.zeros(1, dtype=torch.int64, device="cuda"))
+        self.out, self.totals_host, self.events, self.calls = [], [], [], []
+        # flag block of the library's own cross-rank barrier (symmetric, zeroed; epochs only grow)
+        self.flags = symm_mem.empty(1024, dtype=torch.uint8, device="cuda")
+        self.flags.zero_()
+        self.flags_hdl = symm_mem.rendezvous(self.flags, group)
+        flag_ptrs = [int(self.flags_hdl.buffer_ptrs[r]) for r in range(world)]
+        torch.cuda.synchronize()
+        self.flags_hdl.barrier(channel=0)  # every rank's flags are zero before anybody signals
+        torch.cuda.synchronize()
+        for b in range(2):
+            ops = torch.empty(self.max_rows, dtype=torch.uint8, device="cuda")
+            cols = [torch.empty(self.max_rows, dtype=device.TORCH_DTYPE[t], device="cuda") for t in self.types]
+            self.out.append((ops, cols))
             self.totals_host.append(torch.zeros(1, dtype=torch.int64).pin_memory())
             self.events.append(torch.cuda.Event())
+            self.calls.append(device.P2PExchangeCall(self.keys, self.v2d, world, rank, self.peers[b], flag_ptrs, self.cap,
+                                                     self.bufs[b].data_ptr(), ops, cols, self.counts, self.overflow,
+                                                     self.totals_host[b], vnode_count))
 
     def start(self, chunk, stream=None):
-        """enqueue partition + peer stores + barrier + unpack of one batch on `stream`; returns a token"""
-        from . import device
+        """enqueue partition + peer stores + barrier + unpack of one batch on `stream` (one library call, five
+        launches); returns a token"""
         b = self.step & 1
         self.step += 1
         stream = stream if stream is not None else torch.cuda.current_stream()
-        with torch.cuda.stream(stream):  # the symmetric-memory barrier runs on the current stream
-            device.shuffle_partition_p2p(chunk, self.keys, self.v2d, self.world, self.rank, self.peers[b], self.cap, self.counts,
-                                         self.overflow, self.vnode_count, stream)
-            self.hdls[b].barrier(channel=0)  # all peers' stores into my regions are complete and visible
-            ops, cols = self.out[b]
-            device.shuffle_unpack(self.bufs[b].data_ptr(), self.world, self.types, self.cap, ops, cols, self.totals[b], stream)
-            self.totals_host[b].copy_(self.totals[b], non_blocking=True)
-            self.events[b].record(stream)
+        self.calls[b](chunk, self.step, stream)  # epoch = batch number (1, 2, ...)
+        self.events[b].record(stream)
         return b
 
     def finish(self, b):

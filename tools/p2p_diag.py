@@ -55,21 +55,6 @@ def main():
     ms = timed(lambda: plan.exchange(chunk, stream))
     rep.append(f"P2PShufflePlan.exchange (2^20 rows): {ms:.3f} ms")
 
-    # phases
-    def phase_partition():
-        b = plan.step & 1
-        plan.step += 1
-        device.shuffle_partition_p2p(chunk, plan.keys, plan.v2d, world, rank, plan.peers[b], plan.cap, plan.counts, plan.overflow,
-                                     plan.vnode_count, stream)
-    ms = timed(phase_partition)
-    rep.append(f"  partition + scatter to peers only: {ms:.3f} ms")
-    ops = torch.empty(plan.max_rows, dtype=torch.uint8, device="cuda")
-    oc = [torch.empty(plan.max_rows, dtype=torch.int64, device="cuda") for _ in T4]
-    ms = timed(lambda: device.shuffle_unpack(plan.bufs[0].data_ptr(), world, T4, plan.cap, ops, oc, plan.total, stream))
-    rep.append(f"  unpack only: {ms:.3f} ms")
-    ms = timed(lambda: plan.total.item())
-    rep.append(f"  total.item(): {ms * 1e3:.1f} us")
-
     nplan = exchange.ShufflePlan(world, rank, [0], T4)
     ms = timed(lambda: nplan.exchange(chunk, stream))
     rep.append(f"ShufflePlan.exchange (NCCL all-to-all-v): {ms:.3f} ms")
