@@ -369,21 +369,10 @@ def run_ours(args):
             ex_plan = exchange.P2PShufflePlan(world, rank, key_indices=[0], types=T4, batch_rows=BATCH)
             ex_name = "crc32 vnode partition kernel storing straight into the peers' receive regions over NVLink (symmetric memory), device barrier, unpack kernel"
 
-    ex_stream = torch.cuda.Stream(priority=-1) if world > 1 else None  # its small kernels go ahead of the join grid
-
     def shuffled(cols_dev):
         if world == 1:
             return dchunk(cols_dev)
         ops, cols = ex_plan.exchange(dchunk(cols_dev), stream)
-        return device.DeviceChunk(ops, cols, T4)
-
-    def shuffle_start(chunk):
-        """enqueue the exchange of one batch on its own stream (the dispatcher actor runs beside the join actor)"""
-        return ex_plan.start(chunk, ex_stream)
-
-    def shuffle_finish(token):
-        ops, cols = ex_plan.finish(token)
-        torch.cuda.current_stream().wait_stream(ex_stream)
         return device.DeviceChunk(ops, cols, T4)
 
     line = {}
@@ -412,7 +401,32 @@ def run_ours(args):
 
             trace = os.environ.get("BENCH_TRACE") is not None  # per-phase wall clock (adds syncs: never for a reported number)
 
+            counted = world > 1 and isinstance(ex_plan, exchange.P2PShufflePlan) and not trace
+            recv_chunks = [device.DeviceChunk(*ex_plan.output(b), T4) for b in range(2)] if counted else None
+            t_ex = t_join = 0.0
+            pending = {}
+            lookahead = True
+            ex_stream = torch.cuda.Stream() if counted else None
+
             def step(s):
+                nonlocal t_ex, t_join
+                if counted:
+                    # N>1: the exchange of batch s+1 is enqueued (its own stream) before the join of batch s is
+                    # launched; the join waits for its exchange ON THE DEVICE (event) and reads the received row
+                    # count there (rwgpu_join_push_device_counted): the only host synchronisation of a step is the
+                    # join's own status read-back, and the GPU has the next exchange queued while the host works.
+                    ta = time.perf_counter()
+                    if s not in pending:
+                        pending[s] = ex_plan.start(chunks_dev[s], ex_stream)
+                    if lookahead and s + 1 < W + K and s + 1 != W:  # (nothing of the timed region starts before e0)
+                        pending[s + 1] = ex_plan.start(chunks_dev[s + 1], ex_stream)
+                    b = pending.pop(s)
+                    stream.wait_event(ex_plan.events[b])
+                    tb = time.perf_counter()
+                    out = device.join_push_device(join, abi.SIDE_LEFT, recv_chunks[b], stream, n_rows_dev=ex_plan.count_ptr(b))
+                    t_ex += tb - ta
+                    t_join += time.perf_counter() - tb
+                    return out
                 if not trace:
                     ch = chunks_dev[s] if world == 1 else device.DeviceChunk(*ex_plan.exchange(chunks_dev[s], stream), T4)
                     return device.join_push_device(join, abi.SIDE_LEFT, ch, stream)
@@ -441,28 +455,9 @@ def run_ours(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             out_rows = 0
-            if world == 1 or trace:
-                for s in range(W, W + K):
-                    out_rows += step(s).n_rows
-            else:
-                # N>1: the exchange of batch s+1 (stream ex_stream) overlaps the join of batch s -- upstream
-                # dispatcher and join executor are separate actors.  Nothing is in flight when e0 is recorded.
-                t_fin = t_sta = t_join = 0.0
-                token = shuffle_start(chunks_dev[W])
-                for s in range(W, W + K):
-                    ta = time.perf_counter()
-                    ch = shuffle_finish(token)
-                    tb = time.perf_counter()
-                    if s + 1 < W + K:
-                        token = shuffle_start(chunks_dev[s + 1])
-                    tc = time.perf_counter()
-                    out_rows += device.join_push_device(join, abi.SIDE_LEFT, ch, stream).n_rows
-                    td = time.perf_counter()
-                    t_fin += tb - ta
-                    t_sta += tc - tb
-                    t_join += td - tc
-                host_phases = {"wait_exchange_ms": 1e3 * t_fin / K, "enqueue_next_exchange_ms": 1e3 * t_sta / K,
-                               "join_push_ms": 1e3 * t_join / K}
+            t_ex = t_join = 0.0
+            for s in range(W, W + K):
+                out_rows += step(s).n_rows
             e1.record(stream)
             torch.cuda.synchronize()
             if world > 1:
@@ -490,7 +485,7 @@ def run_ours(args):
                            "join": "inner bid.auction = auction.id, Key64, 4+4 int64 cols, 8 out cols",
                            "l2": "inputs_larger_than_l2 (fresh 32 MiB batch per step; >1.3 GB of join state)",
                            "exchange": None if world == 1 else ex_name},
-                "host_phases_per_step": host_phases if (world > 1 and not trace) else None,
+                "host_ms_per_step": {"enqueue_exchange": 1e3 * t_ex / K, "join_push_incl_sync": 1e3 * t_join / K} if counted else None,
                 "build_rows_per_s": N_BUILD * world / build_s, "out_rows": out_rows, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "join_inner_q4_kernel<false> (probe + emit + own-side append, 4 lanes per row)",
                              "achieved": fused_gbs, "peak": peak, "unit": "GB/s", "frac": fused_gbs / peak if fused_gbs else None,

@@ -222,6 +222,12 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* chunk, rwgp
  * next push on this handle).  *view.n_rows is read back (one 8-byte D2H).                    */
 int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* chunk, rw_chunk* view,
                                void* cuda_stream);
+/* same, for a chunk whose row count is produced ON THE DEVICE by earlier work of `cuda_stream` (the
+ * exchange's unpack kernel): chunk->n_rows is the capacity of its buffers, *n_rows_dev (DEVICE int64,
+ * 0 <= *n_rows_dev <= n_rows) the rows to process.  No host round trip between producer and join.
+ * n_rows_dev == NULL behaves like rwgpu_join_push_device.                                     */
+int32_t rwgpu_join_push_device_counted(rwgpu_join* h, int32_t side, const rw_chunk* chunk,
+                                       const int64_t* n_rows_dev, rw_chunk* view, void* cuda_stream);
 int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t epoch);
 int32_t rwgpu_join_stats(rwgpu_join* h, uint64_t* left_rows, uint64_t* right_rows,
                          uint64_t* kernel_launches);
@@ -280,6 +286,8 @@ int32_t rwgpu_shuffle_unpack_device(const void* recv_base, int32_t n_src, const 
  *                strictly increasing per flag array) stores `epoch` into slot my_rank of every rank's
  *                array and waits until every slot of its own array holds >= epoch.
  *   recv_base  : this rank's receive buffer (== peer_bases[my_rank]).
+ *                The DEVICE copy of the unpacked row count is the int64 at byte 512 + 8 * (epoch & 1) of this
+ *                rank's flag block (feed it to rwgpu_join_push_device_counted: no host round trip).
  *   total_host : PINNED host int64 (device-addressable): receives the row count (-1 = a region
  *                overflowed) when the unpack kernel has run; the caller waits on the stream / an event. */
 int32_t rwgpu_shuffle_exchange_p2p_device(const rw_chunk* chunk, const int32_t* key_indices, int32_t n_keys,

@@ -61,6 +61,7 @@ int devchunk_from_abi(const rw_chunk* c, DevChunk* out) {
   out->vis_bits = c->visibility;
   out->n_cols = c->n_cols;
   out->pad = 0;
+  out->n_dev = nullptr;
   for (int k = 0; k < c->n_cols; k++) {
     int w = type_width(c->columns[k].type);
     if (!w) return fail(RW_ERR_UNSUPPORTED, "chunk: unsupported column type");

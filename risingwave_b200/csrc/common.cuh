@@ -248,6 +248,7 @@ struct DevChunk {
   const uint64_t* vis_bits;    // or nullptr
   int32_t n_cols;
   int32_t pad;
+  const int64_t* n_dev;        // or nullptr: the row count lives on the device (<= n, which is then the capacity)
   ColRef cols[RW_MAX_COLS];
 };
 

@@ -66,6 +66,7 @@ __device__ __host__ __forceinline__ uint32_t W_count(uint64_t W) { return (uint3
 #define JERR_OUT_CAPACITY 2u
 #define JERR_APPEND_ONLY_MULTI 4u
 #define JERR_STORE_CAPACITY 8u
+#define JERR_BAD_COUNT 16u
 
 struct JoinPlanDev {
   int T;
@@ -112,6 +113,7 @@ struct JoinStatus {
   unsigned long long n_keys[2];  // distinct keys ever claimed per side
   unsigned int err;
   unsigned int pad;
+  unsigned long long n_in;       // rows of the input chunk as the kernel saw them (device-resident row count)
 };
 
 struct JoinOutDev {
@@ -1037,6 +1039,18 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinP
   }
 }
 
+// a chunk whose row count lives on the device (e.g. the output of the exchange): clamp the capacity
+__device__ __forceinline__ int64_t chunk_rows(const DevChunk& ch, JoinStatus* st, bool report) {
+  if (!ch.n_dev) return ch.n;
+  const int64_t n = *ch.n_dev;
+  if (n < 0 || n > ch.n) {
+    if (report) atomicOr(&st->err, JERR_BAD_COUNT);
+    return 0;
+  }
+  if (report) st->n_in = (unsigned long long)n;
+  return n;
+}
+
 // ------------------------------------------------------------------ quad-cooperative Key64 kernel (<= 4 + 4 columns)
 // tools/ubench_bucket.cu (profiles/r1_ubench_bucket.txt): what a random bucket access costs is the
 // number of memory INSTRUCTIONS that touch the line, not its bytes -- one thread reading a 64-byte
@@ -1068,6 +1082,7 @@ template <bool PROBE_ONLY, int MINB>
 __global__ void __launch_bounds__(JF_BLOCK, MINB) join_inner_q4_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch,
                                                                      JoinSideDev own, JoinSideDev other, JoinOutDev o, JoinStatus* st,
                                                                      uint32_t store_base, uint32_t seq_base, int64_t out_base, uint32_t pool_chunk) {
+  ch.n = chunk_rows(ch, st, blockIdx.x == 0 && threadIdx.x == 0);
   const int lane = lane_id(), q = lane & 3, qlead = lane & ~3;
   // Overflow row ids come from a per-warp pool that persists across launches: one atomicAdd on the
   // shared counter hands a warp `pool_chunk` ids.  (One atomicAdd per 8 rows on that single address
@@ -1321,12 +1336,13 @@ __device__ __forceinline__ void join_status_publish(JoinStatus* st, JoinStatus* 
   *(unsigned long long*)(host + 1) = tag;
   __threadfence_system();
   if (reset & 1) { st->n_store = 0ull; st->n_del = 0ull; st->null_mask = 0ull; }
-  if (reset & 2) { st->out_rows = 0ull; st->pad = 0u; }
+  if (reset & 2) { st->out_rows = 0ull; st->pad = 0u; st->n_in = 0ull; }
 }
 
 __global__ void __launch_bounds__(256) join_inner_delete_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch,
                                                                  JoinSideDev own, JoinStatus* st, uint32_t seq_base,
                                                                  JoinStatus* status_host, unsigned long long tag, int reset) {
+  ch.n = chunk_rows(ch, st, false);
   if (*(volatile unsigned long long*)&st->n_del == 0ull) {
     // nothing to delete (the usual case): this launch doubles as the status read-back
     if (status_host && blockIdx.x == 0 && threadIdx.x == 0) join_status_publish(st, status_host, tag, reset);
@@ -1632,6 +1648,7 @@ static int join_check_err(rwgpu_join* h, const JoinStatus& s, cudaStream_t st) {
   if (e & JERR_DOUBLE_DELETE) return fail(RW_ERR_INCONSISTENT, "removing a join state entry but it is not in the cache");
   if (e & JERR_APPEND_ONLY_MULTI) return fail(RW_ERR_INCONSISTENT, "append-only optimisation: more than one matched row");
   if (e & JERR_STORE_CAPACITY) return fail(RW_ERR_CUDA, "internal: join record store capacity");
+  if (e & JERR_BAD_COUNT) return fail(RW_ERR_INVALID, "device row count out of range");
   return fail(RW_ERR_CUDA, "internal: join output capacity");
 }
 
@@ -1639,12 +1656,31 @@ static int join_check_err(rwgpu_join* h, const JoinStatus& s, cudaStream_t st) {
 // *null_mask: bit k = output column k holds NULLs, bit 63 = some rows are invisible.
 // `out_base` rows of the device output buffers are already occupied by earlier sub-batches of the
 // same API call (the caller zeroed status.out_rows / null_mask before the first one).
-static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t st, int64_t out_base, int64_t* out_rows,
+static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream_t st, int64_t out_base, int64_t* out_rows,
                          unsigned long long* null_mask) {
   *out_rows = 0;
-  const int64_t n = ch.n;
-  if (n <= 0) return RW_OK;
-  if (n >= (1ll << 31)) return fail(RW_ERR_INVALID, "chunk too large");
+  DevChunk ch = ch_in;
+  if (ch.n <= 0) return RW_OK;
+  if (ch.n >= (1ll << 31)) return fail(RW_ERR_INVALID, "chunk too large");
+  // Key64 / 8-byte-column specialisations need a chunk without bitmaps (ops == 0 still hides rows)
+  bool plain_cols = ch.vis_bits == nullptr;
+  for (int c = 0; c < ch.n_cols && plain_cols; c++)
+    plain_cols = !ch.cols[c].valid_bits && !ch.cols[c].valid_bytes && (((uintptr_t)ch.cols[c].data & 7) == 0);
+  static const bool no_q4_env = getenv("RWGPU_NO_Q4") != nullptr;
+  // device-resident row count: only the quad-cooperative kernel reads it on the device; every other path
+  // fetches it first (one 8-byte read-back) and proceeds with an ordinary chunk
+  bool counted = ch.n_dev != nullptr;
+  if (counted && !(h->fast_inner && h->q4_ok && !no_q4_env && h->w8_ok[S] && plain_cols)) {
+    int64_t nh = 0;
+    RW_CUDA(cudaMemcpyAsync(&nh, ch.n_dev, sizeof(nh), cudaMemcpyDeviceToHost, st));
+    RW_CUDA(cudaStreamSynchronize(st));
+    if (nh < 0 || nh > ch.n) return fail(RW_ERR_INVALID, "device row count out of range");
+    ch.n = nh;
+    ch.n_dev = nullptr;
+    counted = false;
+    if (nh == 0) return RW_OK;
+  }
+  const int64_t n = ch.n;  // capacity when `counted`
   JoinSideHost& own = h->side[S];
   static const bool trace = getenv("RWGPU_TRACE") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1652,8 +1688,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
   const uint64_t cap0 = own.slot_cap, rcap0 = own.row_cap;
   // quad-cooperative kernel: its warps draw overflow row ids from persistent pools in chunks, so the
   // id counter can run ahead of the rows really stored by one chunk per warp
-  static const bool no_q4 = getenv("RWGPU_NO_Q4") != nullptr;
-  const bool q4 = h->fast_inner && h->q4_ok && !no_q4;
+  const bool q4 = h->fast_inner && h->q4_ok && !no_q4_env;
   const int q4_grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 63) / 64, Q4_MAX_GRID));
   uint32_t pool_chunk = 32;
   while (pool_chunk < 256 && (int64_t)pool_chunk * q4_grid * 8 < 4 * n) pool_chunk <<= 1;
@@ -1673,9 +1708,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
   JoinStatus hs;
   if (h->fast_inner) {
     // Key64 / 8-byte-column specialisation when the chunk carries no bitmaps (ops == 0 still hides rows)
-    bool use_w8 = h->w8_ok[S] && ch.vis_bits == nullptr;
-    for (int c = 0; c < ch.n_cols && use_w8; c++)
-      use_w8 = !ch.cols[c].valid_bits && !ch.cols[c].valid_bytes && (((uintptr_t)ch.cols[c].data & 7) == 0);
+    const bool use_w8 = h->w8_ok[S] && plain_cols;
     static const bool dbg_probe_only = getenv("RWGPU_DBG_PROBE_ONLY") != nullptr;  // timing experiments only (state is not updated)
     if (use_w8) {
       // positional output: n rows aligned with the input + extra matches behind them
@@ -1735,7 +1768,8 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch, cudaStream_t 
       hs.err = err;
       rc = join_check_err(h, hs, st);
       if (rc != RW_OK) return rc;
-      *out_rows = (any_match || hs.out_rows) ? n + (int64_t)hs.out_rows : 0;
+      const int64_t n_eff = counted ? (int64_t)hs.n_in : n;  // positional rows = rows of the input chunk
+      *out_rows = (any_match || hs.out_rows) ? n_eff + (int64_t)hs.out_rows : 0;
     } else {
       rc = join_ensure_out(h, out_base + std::max<int64_t>(2 * n, 4096), st, out_base);
       if (rc != RW_OK) return rc;
@@ -2004,12 +2038,18 @@ void rwgpu_join_destroy(rwgpu_join* h) {
 }
 
 int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* c, rw_chunk* view, void* cuda_stream) {
+  return rwgpu_join_push_device_counted(h, side, c, nullptr, view, cuda_stream);
+}
+
+int32_t rwgpu_join_push_device_counted(rwgpu_join* h, int32_t side, const rw_chunk* c, const int64_t* n_rows_dev, rw_chunk* view,
+                                       void* cuda_stream) {
   if (!h || !c || !view) return fail(RW_ERR_INVALID, "null");
   if (side != 0 && side != 1) return fail(RW_ERR_INVALID, "side");
   if (c->n_cols != h->side[side].n_cols) return fail(RW_ERR_INVALID, "chunk schema mismatch");
   DevChunk ch;
   int rc = devchunk_from_abi(c, &ch);
   if (rc != RW_OK) return rc;
+  ch.n_dev = n_rows_dev;
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
   int64_t n = 0;
   unsigned long long nullm = 0;

@@ -122,6 +122,14 @@ def _lib():
         lib.rwgpu_shuffle_unpack_device.restype = C.c_int32
         lib.rwgpu_shuffle_unpack_device.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_void_p,
                                                     C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
+        lib.rwgpu_join_push_device_counted.restype = C.c_int32
+        lib.rwgpu_join_push_device_counted.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.RwChunk), C.c_void_p, C.POINTER(abi.RwChunk),
+                                                       C.c_void_p]
+        lib.rwgpu_shuffle_exchange_p2p_device.restype = C.c_int32
+        lib.rwgpu_shuffle_exchange_p2p_device.argtypes = [C.POINTER(abi.RwChunk), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p,
+                                                          C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint64,
+                                                          C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p,
+                                                          C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rwgpu_last_error.restype = C.c_char_p
         lib._dev_sigs = True
     return lib
@@ -147,10 +155,17 @@ def agg_flush_device(executor, epoch: int, stream: Optional[torch.cuda.Stream] =
     return DeviceView(view)
 
 
-def join_push_device(executor, side: int, chunk: DeviceChunk, stream: Optional[torch.cuda.Stream] = None) -> DeviceView:
+def join_push_device(executor, side: int, chunk: DeviceChunk, stream: Optional[torch.cuda.Stream] = None,
+                     n_rows_dev: Optional[int] = None) -> DeviceView:
+    """`n_rows_dev`: device address of an int64 row count produced by earlier work of `stream` (the chunk's
+    tensors are then the capacity); no host round trip between the producer and the join."""
     ch, keep = chunk.to_abi()
     view = abi.RwChunk()
-    _check(_lib().rwgpu_join_push_device(executor._h, side, C.byref(ch), C.byref(view), _stream_ptr(stream)))
+    if n_rows_dev is None:
+        _check(_lib().rwgpu_join_push_device(executor._h, side, C.byref(ch), C.byref(view), _stream_ptr(stream)))
+    else:
+        _check(_lib().rwgpu_join_push_device_counted(executor._h, side, C.byref(ch), C.c_void_p(n_rows_dev), C.byref(view),
+                                                     _stream_ptr(stream)))
     return DeviceView(view)
 
 

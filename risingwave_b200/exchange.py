@@ -123,6 +123,8 @@ class P2PShufflePlan:
         self.flags.zero_()
         self.flags_hdl = symm_mem.rendezvous(self.flags, group)
         flag_ptrs = [int(self.flags_hdl.buffer_ptrs[r]) for r in range(world)]
+        self._count_base = self.flags.data_ptr() + 512  # device int64 row counts (rwgpu.h): slot = epoch & 1
+        self._count_ptr = [0, 0]
         torch.cuda.synchronize()
         self.flags_hdl.barrier(channel=0)  # every rank's flags are zero before anybody signals
         torch.cuda.synchronize()
@@ -143,8 +145,18 @@ class P2PShufflePlan:
         self.step += 1
         stream = stream if stream is not None else torch.cuda.current_stream()
         self.calls[b](chunk, self.step, stream)  # epoch = batch number (1, 2, ...)
+        self._count_ptr[b] = self._count_base + 8 * (self.step & 1)
         self.events[b].record(stream)
         return b
+
+    def count_ptr(self, b) -> int:
+        """device address of the int64 row count of token `b` (valid until the second `start` after it)"""
+        return self._count_ptr[b]
+
+    def output(self, b):
+        """the FULL output buffers of token `b` (capacity `max_rows`); the row count is on the device at
+        `total_dev_ptr` once the batch's work on the stream has run -- for consumers that read it there"""
+        return self.out[b]
 
     def finish(self, b):
         """wait for the batch of token `b`; -> (ops, cols) views of the received rows (valid until the

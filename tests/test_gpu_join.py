@@ -222,3 +222,87 @@ def test_large_inner_join_properties(cuda):
     upd = StreamChunk.from_pretty(f" I I\n U- {k} {seller_of[k]}\n U+ {k} 5555")
     o = ex.eq_join_oneside(1, upd)
     assert sum(c.capacity() for c in o) == 2 * int(cnt[k])
+
+
+class StreamGen4(StreamGen):
+    """StreamGen with a second payload column: rows are (key, pk, payload, payload2)."""
+
+    def new_row(self, side):
+        return super().new_row(side) + (int(self.rng.integers(0, 1 << 40)),)
+
+
+def test_inner_key64_four_columns_large_chunks(cuda, oracle):
+    """Inner join, one int64 key, 4 + 4 int64 columns = the quad-cooperative kernel (join_inner_q4_kernel):
+    chunks large enough for many warps and overflow-pool refills, hot keys (several matches per row),
+    deletes / updates, invisible rows, and the key that equals the table's EMPTY sentinel."""
+    types = [abi.T_INT64] * 4
+    exs = make_pair(cuda, oracle, abi.JOIN_INNER, types, [0], [1], [1], [False])
+    gen = StreamGen4(seed=5, key_range=600)
+    pushes = []
+    for i in range(12):
+        side = int(gen.rng.integers(2))
+        pushes.append((side, gen.chunk(side, int(gen.rng.integers(300, 3000)), types=types, vis_frac=0.95)))
+    total = drive(exs, pushes)
+    assert total > 10000
+    lo = -(1 << 63)
+    sent = [(0, StreamChunk.from_rows(types, [(abi.OP_INSERT, (lo, 10 ** 9 + 1, 7, 8)), (abi.OP_INSERT, (lo, 10 ** 9 + 2, 9, 10))])),
+            (1, StreamChunk.from_rows(types, [(abi.OP_INSERT, (lo, 10 ** 9 + 3, 1, 2)), (abi.OP_INSERT, (5, 10 ** 9 + 4, 3, 4))])),
+            (0, StreamChunk.from_rows(types, [(abi.OP_DELETE, (lo, 10 ** 9 + 1, 7, 8))])),
+            (1, StreamChunk.from_rows(types, [(abi.OP_UPDATE_DELETE, (lo, 10 ** 9 + 3, 1, 2)), (abi.OP_UPDATE_INSERT, (lo, 10 ** 9 + 3, 1, 99))]))]
+    assert drive(exs, sent) > 0
+
+
+def test_join_push_device_counted_matches_exact_chunk(cuda):
+    """rwgpu_join_push_device_counted: a chunk whose buffers are larger than its row count, the count living
+    on the device, gives the same output as the exact chunk (both through the quad-cooperative kernel)."""
+    import torch
+    from risingwave_b200 import device
+    rng = np.random.default_rng(11)
+    types = [abi.T_INT64] * 4
+    nb, n, cap = 50000, 20000, 32768
+
+    def make():
+        _, sl = MockSource.channel()
+        _, sr = MockSource.channel()
+        ex = HashJoinExecutor(cuda, abi.JOIN_INNER, sl.into_executor(types, [1]), sr.into_executor(types, [0]),
+                              JoinParams([0], [1]), JoinParams([0], []), [False], capacity_hint=nb)
+        ids = np.arange(nb, dtype=np.int64)
+        cols = [torch.from_numpy(ids).cuda()] + [torch.from_numpy(rng.integers(0, 1000, nb).astype(np.int64)).cuda() for _ in range(3)]
+        device.join_push_device(ex, abi.SIDE_RIGHT, device.DeviceChunk(torch.ones(nb, dtype=torch.uint8, device="cuda"), cols, types))
+        return ex
+
+    rng = np.random.default_rng(11)
+    a = make()
+    rng = np.random.default_rng(11)
+    b = make()
+    bid = [np.concatenate([rng.integers(0, nb + 100, n), np.full(cap - n, -77)]).astype(np.int64)] + \
+          [np.concatenate([rng.integers(0, 1 << 30, n), np.full(cap - n, -1)]).astype(np.int64) for _ in range(3)]
+    bid[1][:n] = np.arange(n)  # stream key
+    ops = np.full(cap, abi.OP_INSERT, np.uint8)
+    ops[rng.integers(0, n, 50)] = 0  # a few invisible rows
+    full = [torch.from_numpy(c).cuda() for c in bid]
+    ops_d = torch.from_numpy(ops).cuda()
+    va = device.join_push_device(a, abi.SIDE_LEFT, device.DeviceChunk(ops_d[:n].contiguous(), [c[:n].contiguous() for c in full], types))
+    got_a = (va.n_rows, va.ops().cpu().numpy(), [va.column(k).cpu().numpy() for k in range(va.n_cols)])
+    count = torch.tensor([n], dtype=torch.int64, device="cuda")
+    vb = device.join_push_device(b, abi.SIDE_LEFT, device.DeviceChunk(ops_d, full, types), n_rows_dev=count.data_ptr())
+    got_b = (vb.n_rows, vb.ops().cpu().numpy(), [vb.column(k).cpu().numpy() for k in range(vb.n_cols)])
+    assert got_a[0] == got_b[0] == n
+    # positional output: row r of the output belongs to input row r; compare the visible rows
+    def visible(view, got):
+        import ctypes as C
+        if view.vis_ptr is None:
+            return np.ones(got[0], bool)
+        words = torch.empty((got[0] + 63) // 64, dtype=torch.int64, device="cuda")
+        device.cudart().cudaMemcpy(C.c_void_p(words.data_ptr()), C.c_void_p(view.vis_ptr), C.c_size_t(words.numel() * 8), 3)
+        bits = np.unpackbits(words.cpu().numpy().view(np.uint8), bitorder="little")[:got[0]]
+        return bits.astype(bool)
+    ma, mb = visible(va, got_a), visible(vb, got_b)
+    assert np.array_equal(ma, mb) and ma.sum() > n * 0.9
+    assert np.array_equal(got_a[1][ma], got_b[1][mb])
+    for ca, cb in zip(got_a[2], got_b[2]):
+        assert np.array_equal(ca[ma], cb[mb])
+    # a count outside [0, capacity] is rejected
+    bad = torch.tensor([cap + 1], dtype=torch.int64, device="cuda")
+    with pytest.raises(abi.RwError):
+        device.join_push_device(b, abi.SIDE_LEFT, device.DeviceChunk(ops_d, full, types), n_rows_dev=bad.data_ptr())
