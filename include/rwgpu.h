@@ -297,6 +297,36 @@ int32_t rwgpu_shuffle_exchange_p2p_device(const rw_chunk* chunk, const int32_t* 
                                           uint8_t* out_ops, void* const* out_cols, int64_t* counts,
                                           int32_t* overflow, int64_t* total_host, void* cuda_stream);
 
+/* ================================================================ Filter (operator chaining on the device)
+ * Replaces FilterExecutorInner::filter           src/stream/src/executor/filter.rs:58-150
+ * for predicates that are a CONJUNCTION of integer comparisons `col cmp col` / `col cmp constant`
+ * (Int16/32/64, Date, Time, Timestamptz, Serial, Bool).  A NULL operand makes its term NULL and
+ * the row's result false (filter.rs:79 `res.unwrap_or(false)`); everything else the expression
+ * framework can evaluate stays on the CPU FilterExecutor.  Project with InputRef expressions
+ * (project_scalar.rs:100-120) is a re-ordering of column pointers in the caller and needs no kernel.
+ *
+ * Output: out_ops[n_rows] and the packed visibility out_visibility[(n_rows+63)/64] of a chunk that
+ * has the input's columns.  Rows that were invisible in the input stay invisible with their op
+ * unchanged (the reference compacts them away first, filter.rs:182); the visible rows carry exactly
+ * the ops / visibility the reference produces, U-/U+ pairs included (filter.rs:107-141; a pair is a
+ * visible U- and the next visible row, which must be U+).  upsert != 0 selects the UPSERT rules
+ * (filter.rs:82-106).  *n_visible (may be NULL) receives the number of visible output rows
+ * (0 => the reference yields no chunk, filter.rs:146-150).                                       */
+typedef struct rw_filter_term {
+  int32_t cmp;       /* RW_CMP_LT .. RW_CMP_NE                                  */
+  int32_t lhs_col;
+  int32_t rhs_col;   /* >= 0: column; -1: rhs_const                             */
+  int32_t reserved;
+  int64_t rhs_const;
+} rw_filter_term;
+/* HOST chunk, host outputs */
+int32_t rwgpu_filter(const rw_chunk* chunk, const rw_filter_term* terms, int32_t n_terms, int32_t upsert,
+                     uint8_t* out_ops, uint64_t* out_visibility, int64_t* n_visible);
+/* DEVICE chunk (e.g. the view a join push returned), DEVICE outputs; *n_visible_dev: DEVICE int64 or NULL */
+int32_t rwgpu_filter_device(const rw_chunk* chunk, const rw_filter_term* terms, int32_t n_terms, int32_t upsert,
+                            uint8_t* out_ops, uint64_t* out_visibility, int64_t* n_visible_dev,
+                            void* cuda_stream);
+
 /* ================================================================ misc */
 const char* rwgpu_last_error(void);
 /* 0 if a CUDA device is usable, else RW_ERR_NO_DEVICE (and every create() fails loudly). */

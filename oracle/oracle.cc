@@ -926,6 +926,88 @@ int32_t rwo_eliminate_adjacent_noop_update(const rw_chunk* ch, uint8_t* out_ops,
 
 }  // extern "C"
 
+// FilterExecutorInner::filter (src/stream/src/executor/filter.rs:58-150), restated literally: the chunk is
+// compacted first (execute_inner, filter.rs:182), the predicate gives Option<bool> per row
+// (`res.unwrap_or(false)`, :79), then the op rules produce new ops / visibility for the compacted rows.
+// The results are scattered back to the positions of the input's visible rows (invisible input rows keep
+// their op and stay invisible) so that the signature equals rwgpu_filter's.
+// Predicate = conjunction of integer comparisons with SQL three-valued logic: a NULL operand makes the
+// term NULL; AND of terms is NULL/false unless every term is true -> unwrap_or(false) == "all terms true".
+extern "C" int32_t rwo_filter(const rw_chunk* ch, const rw_filter_term* terms, int32_t n_terms, int32_t upsert, uint8_t* out_ops,
+                              uint64_t* out_visibility, int64_t* n_visible) {
+  const int64_t n = ch->n_rows;
+  if (n_terms < 1 || n_terms > 8) { g_err = "filter: 1..8 conjuncts"; return RW_ERR_UNSUPPORTED; }
+  for (int k = 0; k < n_terms; k++) {
+    auto ok = [&](int c) { return c >= 0 && c < ch->n_cols && !is_float(ch->columns[c].type) && ch->columns[c].type != RW_T_DECIMAL &&
+                                  ch->columns[c].type != RW_T_TIMESTAMP; };
+    if (terms[k].cmp < RW_CMP_LT || terms[k].cmp > RW_CMP_NE) { g_err = "filter: comparison"; return RW_ERR_INVALID; }
+    if (!ok(terms[k].lhs_col) || terms[k].rhs_col < -1 || (terms[k].rhs_col >= 0 && !ok(terms[k].rhs_col))) {
+      g_err = "filter: only integer-typed columns are compared";
+      return RW_ERR_UNSUPPORTED;
+    }
+  }
+  // compact_vis
+  std::vector<int64_t> pos;
+  for (int64_t r = 0; r < n; r++)
+    if (bit_get(ch->visibility, r)) pos.push_back(r);
+  // pred_output: Option<bool> per compacted row
+  auto pred = [&](int64_t r) -> int {  // 1 true, 0 false, -1 NULL
+    bool any_null = false, any_false = false;
+    for (int k = 0; k < n_terms; k++) {
+      const rw_filter_term& t = terms[k];
+      Datum a = read_datum(ch->columns[t.lhs_col], r), b;
+      if (t.rhs_col >= 0) b = read_datum(ch->columns[t.rhs_col], r);
+      else { b.null = false; b.i = t.rhs_const; }
+      if (a.null || b.null) { any_null = true; continue; }
+      bool v = false;
+      switch (t.cmp) {
+        case RW_CMP_LT: v = a.i < b.i; break;
+        case RW_CMP_LE: v = a.i <= b.i; break;
+        case RW_CMP_GT: v = a.i > b.i; break;
+        case RW_CMP_GE: v = a.i >= b.i; break;
+        case RW_CMP_EQ: v = a.i == b.i; break;
+        default: v = a.i != b.i; break;
+      }
+      if (!v) any_false = true;
+    }
+    return any_false ? 0 : (any_null ? -1 : 1);
+  };
+  std::vector<uint8_t> new_ops;
+  std::vector<bool> new_vis;
+  bool last_res = false;
+  for (size_t i = 0; i < pos.size(); i++) {
+    const uint8_t op = ch->ops[pos[i]];
+    const bool res = pred(pos[i]) == 1;  // unwrap_or(false)
+    if (upsert) {  // :82-106
+      if (op == RW_OP_INSERT || op == RW_OP_UPDATE_INSERT) { new_ops.push_back(res ? RW_OP_INSERT : RW_OP_DELETE); new_vis.push_back(true); }
+      else { new_ops.push_back(RW_OP_DELETE); new_vis.push_back(true); }
+    } else if (op == RW_OP_INSERT || op == RW_OP_DELETE) {  // :108-111
+      new_ops.push_back(op);
+      new_vis.push_back(res);
+    } else if (op == RW_OP_UPDATE_DELETE) {  // :112-114
+      last_res = res;
+    } else {  // UpdateInsert :115-141
+      if (last_res && !res) { new_ops.push_back(RW_OP_DELETE); new_ops.push_back(RW_OP_UPDATE_INSERT); new_vis.push_back(true); new_vis.push_back(false); }
+      else if (!last_res && res) { new_ops.push_back(RW_OP_UPDATE_DELETE); new_ops.push_back(RW_OP_INSERT); new_vis.push_back(false); new_vis.push_back(true); }
+      else if (last_res && res) { new_ops.push_back(RW_OP_UPDATE_DELETE); new_ops.push_back(RW_OP_UPDATE_INSERT); new_vis.push_back(true); new_vis.push_back(true); }
+      else { new_ops.push_back(RW_OP_UPDATE_DELETE); new_ops.push_back(RW_OP_UPDATE_INSERT); new_vis.push_back(false); new_vis.push_back(false); }
+    }
+  }
+  if (new_ops.size() != pos.size()) {  // a U- without its U+ (StreamChunk::with_visibility would panic on the length)
+    g_err = "filter: UpdateDelete without a following UpdateInsert";
+    return RW_ERR_INCONSISTENT;
+  }
+  memcpy(out_ops, ch->ops, (size_t)n);
+  memset(out_visibility, 0, (size_t)((n + 63) / 64) * 8);
+  int64_t cnt = 0;
+  for (size_t i = 0; i < pos.size(); i++) {
+    out_ops[pos[i]] = new_ops[i];
+    if (new_vis[i]) { out_visibility[pos[i] >> 6] |= 1ull << (pos[i] & 63); cnt++; }
+  }
+  if (n_visible) *n_visible = cnt;
+  return RW_OK;
+}
+
 // single-state evaluation used to pin agg_apply against the reference's aggregate-function
 // tests (src/expr/impl/src/aggregate/general.rs:175-186 `test_agg`): create_state, update over the
 // visible rows of `ch`, get_result.

@@ -64,6 +64,11 @@ class RwJoinCond(C.Structure):
     _fields_ = [("cmp", C.c_int32), ("lhs", C.c_int32), ("rhs", C.c_int32), ("reserved", C.c_int32)]
 
 
+class RwFilterTerm(C.Structure):
+    _fields_ = [("cmp", C.c_int32), ("lhs_col", C.c_int32), ("rhs_col", C.c_int32), ("reserved", C.c_int32),
+                ("rhs_const", C.c_int64)]
+
+
 class RwJoinSideDesc(C.Structure):
     _fields_ = [("n_cols", C.c_int32), ("types", C.POINTER(C.c_int32)),
                 ("key_indices", C.POINTER(C.c_int32)),
@@ -116,5 +121,5 @@ ABI_SYMBOLS = [
     "rwgpu_join_create", "rwgpu_join_destroy", "rwgpu_join_push", "rwgpu_join_push_device", "rwgpu_join_push_device_counted",
     "rwgpu_join_barrier", "rwgpu_join_stats", "rwgpu_join_profile", "rwgpu_vnode_compute", "rwgpu_dispatch_rewrite_ops",
     "rwgpu_shuffle_partition_device", "rwgpu_shuffle_p2p_region_bytes",
-    "rwgpu_shuffle_partition_p2p_device", "rwgpu_shuffle_unpack_device", "rwgpu_shuffle_exchange_p2p_device", "rwgpu_last_error", "rwgpu_device_check", "rwgpu_version",
+    "rwgpu_shuffle_partition_p2p_device", "rwgpu_shuffle_unpack_device", "rwgpu_shuffle_exchange_p2p_device", "rwgpu_filter", "rwgpu_filter_device", "rwgpu_last_error", "rwgpu_device_check", "rwgpu_version",
 ]

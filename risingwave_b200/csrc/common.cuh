@@ -254,6 +254,8 @@ struct DevChunk {
 
 // host: build a DevChunk from an rw_chunk whose pointers are DEVICE pointers
 int devchunk_from_abi(const rw_chunk* c, DevChunk* out);
+// host: upload a HOST rw_chunk into one temporary device allocation (shuffle.cu)
+int upload_chunk(const rw_chunk* c, DevBuf& buf, DevChunk* out, cudaStream_t st);
 
 // ------------------------------------------------------------------ output object (host side)
 struct OutColHost {

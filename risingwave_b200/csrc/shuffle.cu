@@ -453,7 +453,7 @@ static int grid_rows(int64_t n, int block) {
 }
 
 // upload a HOST rw_chunk into one temporary device allocation
-static int upload_chunk(const rw_chunk* c, DevBuf& buf, DevChunk* out, cudaStream_t st) {
+int upload_chunk(const rw_chunk* c, DevBuf& buf, DevChunk* out, cudaStream_t st) {
   if (c->n_cols > RW_MAX_COLS) return fail(RW_ERR_UNSUPPORTED, "too many columns");
   int64_t n = c->n_rows;
   size_t nw = (size_t)((n + 63) / 64) * 8;

@@ -130,6 +130,9 @@ def _lib():
                                                           C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint64,
                                                           C.c_int64, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p,
                                                           C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.rwgpu_filter_device.restype = C.c_int32
+        lib.rwgpu_filter_device.argtypes = [C.POINTER(abi.RwChunk), C.POINTER(abi.RwFilterTerm), C.c_int32, C.c_int32, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
         lib.rwgpu_last_error.restype = C.c_char_p
         lib._dev_sigs = True
     return lib
@@ -256,3 +259,14 @@ class P2PExchangeCall:
                                                         self.flags, C.c_uint64(epoch), C.c_int64(self.cap_rows), self.recv,
                                                         self.out_ops, self.colp, self.counts, self.overflow, self.total_host,
                                                         _stream_ptr(stream)))
+
+
+def filter_device(chunk_abi, n_rows: int, terms, upsert: bool = False, stream: Optional[torch.cuda.Stream] = None):
+    """rwgpu_filter_device on an `abi.RwChunk` with DEVICE pointers (a DeviceChunk.to_abi()[0] or the view of a
+    `*_device` call).  -> (ops uint8[n], visibility int64[(n+63)//64] packed bits, n_visible int64[1]) CUDA tensors."""
+    ops = torch.empty(max(n_rows, 1), dtype=torch.uint8, device="cuda")
+    vis = torch.zeros(max((n_rows + 63) // 64, 1), dtype=torch.int64, device="cuda")
+    nvis = torch.zeros(1, dtype=torch.int64, device="cuda")
+    _check(_lib().rwgpu_filter_device(C.byref(chunk_abi), terms, len(terms), int(upsert), C.c_void_p(ops.data_ptr()),
+                                      C.c_void_p(vis.data_ptr()), C.c_void_p(nvis.data_ptr()), _stream_ptr(stream)))
+    return ops[:n_rows], vis, nvis

@@ -22,6 +22,8 @@ from collections import deque
 from dataclasses import dataclass, field
 from typing import Deque, Iterator, List, Optional, Sequence, Tuple
 
+import numpy as np
+
 from . import abi
 from .stream_chunk import StreamChunk
 
@@ -50,6 +52,8 @@ class Backend:
                                        C.POINTER(C.c_uint16)])
         f("dispatch_rewrite_ops", C.c_int32, [C.POINTER(abi.RwChunk), C.POINTER(C.c_int32), C.c_int32,
                                               C.POINTER(C.c_uint8)])
+        f("filter", C.c_int32, [C.POINTER(abi.RwChunk), C.POINTER(abi.RwFilterTerm), C.c_int32, C.c_int32, C.POINTER(C.c_uint8),
+                                C.POINTER(C.c_uint64), C.POINTER(C.c_int64)])
         f("last_error", C.c_char_p, [])
 
     @staticmethod
@@ -433,3 +437,73 @@ class HashJoinExecutor:
                 break
             if not progressed:
                 yield PENDING
+
+
+# =============================================================================== Filter
+def parse_filter_expr(text: str) -> List[Tuple[int, int, int, int]]:
+    """build_from_pretty subset -> conjunction terms (cmp, lhs_col, rhs_col or -1, rhs_const):
+    `(greater_than:boolean $0:int8 $1:int8)`, `(greater_than:boolean $1:int8 10:int8)`,
+    `(and:boolean (...) (...))`."""
+    text = text.strip()
+    m = re.fullmatch(r"\(\s*and:boolean\s+(\(.*\))\s+(\(.*\))\s*\)", text, re.S)
+    if m:
+        # split the two operands at the top-level parenthesis boundary
+        body = text[text.index("and:boolean") + len("and:boolean"):-1].strip()
+        depth, cut = 0, None
+        for i, c in enumerate(body):
+            depth += c == "("
+            depth -= c == ")"
+            if depth == 0:
+                cut = i + 1
+                break
+        return parse_filter_expr(body[:cut]) + parse_filter_expr(body[cut:])
+    m = re.fullmatch(r"\(\s*(\w+):boolean\s+\$(\d+):\w+\s+(?:\$(\d+)|(-?\d+)):\w+\s*\)", text)
+    if not m or m.group(1) not in _CMP:
+        raise ValueError(f"unsupported filter expression {text!r}")
+    if m.group(3) is not None:
+        return [(_CMP[m.group(1)], int(m.group(2)), int(m.group(3)), 0)]
+    return [(_CMP[m.group(1)], int(m.group(2)), -1, int(m.group(4)))]
+
+
+class FilterExecutor:
+    """Mirror of FilterExecutor / UpsertFilterExecutor::new(ctx, input, expr) (filter.rs:33-56) for predicates
+    the device path evaluates (conjunctions of integer comparisons)."""
+
+    def __init__(self, backend: Backend, input: MockSource, expr: str, upsert: bool = False):
+        self.backend, self.input, self.upsert = backend, input, upsert
+        terms = parse_filter_expr(expr)
+        self._terms = (abi.RwFilterTerm * len(terms))()
+        for k, (cmp, lhs, rhs, const) in enumerate(terms):
+            self._terms[k].cmp, self._terms[k].lhs_col, self._terms[k].rhs_col, self._terms[k].rhs_const = cmp, lhs, rhs, const
+        self.schema = list(input.schema)
+
+    def filter(self, chunk: StreamChunk) -> Optional[StreamChunk]:
+        """FilterExecutorInner::filter (filter.rs:58-150): same columns, new ops / visibility; None if no row stays visible"""
+        ch, keep = chunk.to_abi()
+        n = chunk.capacity()
+        ops = np.zeros(max(n, 1), dtype=np.uint8)
+        vis = np.zeros(max((n + 63) // 64, 1), dtype=np.uint64)
+        nvis = C.c_int64(0)
+        self.backend.check(self.backend._filter(C.byref(ch), self._terms, len(self._terms), int(self.upsert),
+                                                ops.ctypes.data_as(C.POINTER(C.c_uint8)), vis.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                C.byref(nvis)))
+        if nvis.value == 0:
+            return None
+        bits = np.unpackbits(vis.view(np.uint8), bitorder="little")[:n].astype(bool)
+        return StreamChunk(ops[:n].copy(), chunk.columns, bits)
+
+    def execute(self) -> MessageStream:
+        return MessageStream(self._run())
+
+    def _run(self):
+        # execute_inner (filter.rs:172-194): chunks are filtered, everything else passes through
+        while True:
+            m = self.input.poll()
+            if m is PENDING:
+                yield PENDING
+            elif m.chunk is not None:
+                out = self.filter(m.chunk)
+                if out is not None:
+                    yield Message(chunk=out)
+            else:
+                yield m

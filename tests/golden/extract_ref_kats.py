@@ -9,6 +9,7 @@ Outputs (committed):
     tests/golden/hash_join_kats.json   <- src/stream/src/executor/hash_join.rs  #[tokio::test]s
     tests/golden/hash_agg_kats.json    <- src/stream/tests/integration_tests/hash_agg.rs
     tests/golden/agg_func_kats.json    <- src/expr/impl/src/aggregate/general.rs tests
+    tests/golden/filter_kats.json      <- src/stream/src/executor/filter.rs tests
 
 Only test DATA is transcribed (the `from_pretty` literals, the executor configuration and the
 push / expect script of each test); no reference code is copied.
@@ -187,6 +188,28 @@ def extract_agg_funcs():
     return out
 
 
+# ----------------------------------------------------------------------------------- filter
+def extract_filter():
+    """src/stream/src/executor/filter.rs tests: input chunks, the predicate, expected output chunks"""
+    path = os.path.join(REF, "src/stream/src/executor/filter.rs")
+    src = open(path).read()
+    tests_start = src.index("#[cfg(test)]")
+    src_tests = src[tests_start:]
+    line_of = lambda pos: src[: tests_start + pos].count("\n") + 1  # noqa: E731
+    out = []
+    for name, body in split_tests(src_tests):
+        pos0 = src_tests.index("async fn " + name)
+        lits = [clean_pretty(re.sub(r"//[^\n]*", "", m.group(1)))
+                for m in re.finditer(r"StreamChunk::from_pretty\(\s*\"([^\"]*)\",?\s*\)", body)]
+        mexpr = re.search(r"build_from_pretty\(\"([^\"]+)\"\)", body)
+        n_in = len(re.findall(r"let chunk\d* = StreamChunk::from_pretty", body))
+        assert mexpr and n_in >= 1 and len(lits) == 2 * n_in, name
+        out.append({"name": name, "source": f"src/stream/src/executor/filter.rs:{line_of(pos0)}",
+                    "upsert": "UpsertFilterExecutor::new" in body, "expr": mexpr.group(1),
+                    "inputs": lits[:n_in], "expected": lits[n_in:]})
+    return out
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference not mounted; fixtures are committed, nothing to do")
@@ -196,6 +219,9 @@ def main():
     json.dump(ha, open(os.path.join(OUT, "hash_agg_kats.json"), "w"), indent=1)
     af = extract_agg_funcs()
     json.dump(af, open(os.path.join(OUT, "agg_func_kats.json"), "w"), indent=1)
+    fl = extract_filter()
+    json.dump(fl, open(os.path.join(OUT, "filter_kats.json"), "w"), indent=1)
+    print(f"filter: {len(fl)} tests")
     print(f"hash_join: {len(hj)} tests ({sum('skipped' in t for t in hj)} skipped); "
           f"hash_agg: {len(ha)}; agg funcs: {len(af)}")
 
