@@ -298,6 +298,45 @@ class HashAggExecutor : public Execute {
   std::vector<int32_t> schema_, key_;
 };
 
+// ------------------------------------------------------------------------------------ Filter
+// FilterExecutor / UpsertFilterExecutor::new(ctx, input, expr) (filter.rs:33-56) for the predicates the device
+// evaluates: a conjunction of integer comparisons (col cmp col | col cmp constant).
+class FilterExecutor : public Execute {
+ public:
+  FilterExecutor(std::shared_ptr<Execute> input, std::vector<rw_filter_term> conjuncts, bool upsert = false)
+      : input_(std::move(input)), terms_(std::move(conjuncts)), upsert_(upsert) {}
+  // FilterExecutorInner::filter (filter.rs:58-150): same columns, new ops / visibility; nullopt = nothing visible
+  std::optional<StreamChunk> filter(const StreamChunk& c) const {
+    StreamChunk out = c;
+    out.visibility.assign((size_t)((c.capacity() + 63) / 64), 0);
+    int64_t n_visible = 0;
+    auto v = c.view();
+    check(rwgpu_filter(&v.raw, terms_.data(), (int32_t)terms_.size(), upsert_ ? 1 : 0, out.ops.data(), out.visibility.data(), &n_visible));
+    if (n_visible == 0) return std::nullopt;
+    return out;
+  }
+  // execute_inner (filter.rs:172-194)
+  std::optional<Message> poll_next() override {
+    while (true) {
+      auto m = input_->poll_next();
+      if (!m) return std::nullopt;
+      if (auto* c = std::get_if<StreamChunk>(&*m)) {
+        auto out = filter(*c);
+        if (out) return Message(std::move(*out));
+        continue;
+      }
+      return m;
+    }
+  }
+  const std::vector<int32_t>& schema() const override { return input_->schema(); }
+  const std::vector<int32_t>& stream_key() const override { return input_->stream_key(); }
+
+ private:
+  std::shared_ptr<Execute> input_;
+  std::vector<rw_filter_term> terms_;
+  bool upsert_;
+};
+
 // ------------------------------------------------------------------------------------ HashJoin
 struct JoinParams { std::vector<int32_t> join_key_indices, deduped_pk_indices; };
 

@@ -3,6 +3,7 @@
 //   src/stream/src/executor/hash_join.rs:1812-1880  test_streaming_hash_inner_join
 //   src/stream/src/executor/hash_join.rs:3347-3430  test_streaming_hash_full_outer_join
 //   src/stream/tests/integration_tests/hash_agg.rs:21-96  test_hash_agg_count_sum
+//   src/stream/src/executor/filter.rs:208-272  test_filter  (exact: ops and visibility of every row)
 // Comparison is the net applied multiset per expected chunk (the reference's output order is not
 // deterministic).  Exit code 0 = all passed.
 #include <cstdio>
@@ -87,11 +88,29 @@ static void test_hash_agg_count_sum() {
   }
 }
 
+static void expect_exact(const StreamChunk& got, const char* want_pretty) {
+  const StreamChunk want = StreamChunk::from_pretty(want_pretty);
+  bool same = got.capacity() == want.capacity() && got.ops == want.ops;
+  for (int64_t r = 0; same && r < got.capacity(); r++) same = got.is_visible(r) == want.is_visible(r);
+  EXPECT(same, want_pretty);
+}
+
+static void test_filter() {
+  auto tx = std::make_shared<MockSource>(std::vector<int32_t>{RW_T_INT64, RW_T_INT64}, std::vector<int32_t>{});
+  // (greater_than:boolean $0:int8 $1:int8)
+  FilterExecutor filter(tx, {rw_filter_term{RW_CMP_GT, 0, 1, 0, 0}});
+  tx->push_chunk(StreamChunk::from_pretty(" I I\n + 1 4\n + 5 2\n + 6 6\n - 7 5"));
+  tx->push_chunk(StreamChunk::from_pretty(" I I\n U- 5 3\n U+ 7 5\n U- 5 3\n U+ 3 5\n U- 3 5\n U+ 5 3\n U- 3 5\n U+ 4 6"));
+  expect_exact(next_chunk(filter), " I I\n + 1 4 D\n + 5 2\n + 6 6 D\n - 7 5");
+  expect_exact(next_chunk(filter), " I I\n U- 5 3\n U+ 7 5\n - 5 3\n U+ 3 5 D\n U- 3 5 D\n + 5 3\n U- 3 5 D\n U+ 4 6 D");
+}
+
 int main() {
   if (rwgpu_device_check() != RW_OK) { std::printf("no CUDA device: %s\n", rwgpu_last_error()); return 2; }
   test_streaming_hash_inner_join();
   test_streaming_hash_full_outer_join();
   test_hash_agg_count_sum();
+  test_filter();
   std::printf(failures ? "%d FAILED\n" : "all C++ host-layer KATs passed (%d failures)\n", failures);
   return failures ? 1 : 0;
 }
