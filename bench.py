@@ -582,6 +582,73 @@ def run_ours(args):
                              "frac": agbs / peak if agbs else None, "traffic": ncu_traffic("agg_apply_fast_kernel"), "peak_source": which,
                              "algorithmic_bytes_per_row": AGG_BYTES_PER_ROW_FLOOR, "kernel_ms_avg": akern_ms / max(akern_n, 1)}}
 
+        # ================================================================ leg: chain (join -> filter -> project -> agg in HBM)
+        if "chain" in legs and world == 1:
+            from risingwave_b200.executor import parse_filter_expr
+            join3 = new_join()
+            build(join3, shuffle=False)
+            _, src3 = MockSource.channel()
+            agg3 = HashAggExecutor(be, src3.into_executor([abi.T_INT64] * 2, []), True,
+                                   [AggCall.from_pretty(c) for c in ("(count:int8)", "(max:int8 $1:int8)")], 0, [0],
+                                   group_capacity_hint=2 * N_BUILD)
+            # join output: bid (auction, date_time, bidder, price) | auction (id, seller, category, expires)
+            expr = "(and:boolean (less_than_or_equal:boolean $2:int8 $5:int8) (greater_than_or_equal:boolean $3:int8 1048576:int8))"
+            tp = parse_filter_expr(expr)
+            terms = (abi.RwFilterTerm * len(tp))()
+            for k, (cmp, lhs, rhs, const) in enumerate(tp):
+                terms[k].cmp, terms[k].lhs_col, terms[k].rhs_col, terms[k].rhs_const = cmp, lhs, rhs, const
+            KC, WC = min(K, 12), 3
+            cdev = [dchunk(to_dev(b)) for b in batches_host[:KC + WC]]
+            torch.cuda.synchronize()
+            f0 = [torch.cuda.Event(enable_timing=True) for _ in range(KC + WC)]
+            f1 = [torch.cuda.Event(enable_timing=True) for _ in range(KC + WC)]
+            passed = deltas = 0
+
+            def chain_step(s):
+                nonlocal passed, deltas
+                view = device.join_push_device(join3, abi.SIDE_LEFT, cdev[s], stream)
+                raw = abi.RwChunk()
+                cols = (abi.RwColumn * view.n_cols)()
+                for k in range(view.n_cols):
+                    cols[k].type, cols[k].data, cols[k].validity = view.col_types[k], view.col_ptrs[k], view.valid_ptrs[k]
+                raw.n_rows, raw.n_cols, raw.ops, raw.visibility, raw.columns = view.n_rows, view.n_cols, view.ops_ptr, view.vis_ptr, cols
+                f0[s].record(stream)
+                f_ops, f_vis, f_n = device.filter_device(raw, view.n_rows, terms, False, stream)
+                f1[s].record(stream)
+                proj = abi.RwChunk()  # Project (auction, price): column pointers only
+                pcols = (abi.RwColumn * 2)()
+                for k, c in enumerate((0, 3)):
+                    pcols[k].type, pcols[k].data, pcols[k].validity = view.col_types[c], view.col_ptrs[c], view.valid_ptrs[c]
+                proj.n_rows, proj.n_cols, proj.ops, proj.visibility, proj.columns = view.n_rows, 2, f_ops.data_ptr(), f_vis.data_ptr(), pcols
+                device._check(device._lib().rwgpu_agg_push_device(agg3._h, C.byref(proj), C.c_void_p(stream.cuda_stream)))
+                deltas += device.agg_flush_device(agg3, s + 1, stream).n_rows  # a barrier after every 2^20-row batch
+                passed += int(f_n.item())
+
+            for s in range(WC):
+                chain_step(s)
+            passed = deltas = 0
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            for s in range(WC, WC + KC):
+                chain_step(s)
+            c1.record(stream)
+            torch.cuda.synchronize()
+            cms = c0.elapsed_time(c1)
+            fms = sum(a.elapsed_time(b) for a, b in zip(f0[WC:], f1[WC:])) / KC
+            FILTER_BYTES_PER_ROW = 3 * 8 + 1 + 1 + 0.125  # three predicate columns + ops read; ops + visibility written
+            fgbs = FILTER_BYTES_PER_ROW * BATCH / (fms / 1e3) / 1e9
+            line["chain"] = {
+                "workload": "q4-shaped device-resident chain: bid JOIN auction -> Filter(bidder <= seller AND price >= 2^20) -> "
+                            "Project(auction, price) -> HashAgg(count, max GROUP BY auction), a barrier per 2^20-row batch",
+                "metric": "bid rows/s through the whole chain", "value": KC * BATCH / (cms / 1e3), "steps": KC, "ms_per_step": cms / KC,
+                "filter_selectivity": passed / (KC * BATCH), "agg_delta_rows_per_step": deltas / KC,
+                "filter_roofline": {"bound": "hbm", "kernel": "filter_kernel", "achieved": fgbs, "peak": peak, "unit": "GB/s",
+                                    "frac": fgbs / peak, "algorithmic_bytes_per_row": FILTER_BYTES_PER_ROW, "kernel_ms_avg": fms,
+                                    "traffic": None}}
+            del join3, agg3, cdev
+            torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -631,7 +698,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--legs", default="value,e2e,agg,cpu", help="comma list of: value,e2e,agg,cpu (subset for ncu runs)")
+    ap.add_argument("--legs", default="value,e2e,agg,chain,cpu", help="comma list of: value,e2e,agg,chain,cpu (subset for ncu runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
