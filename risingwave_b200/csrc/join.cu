@@ -1082,7 +1082,8 @@ template <bool PROBE_ONLY, int MINB>
 __global__ void __launch_bounds__(JF_BLOCK, MINB) join_inner_q4_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch,
                                                                      JoinSideDev own, JoinSideDev other, JoinOutDev o, JoinStatus* st,
                                                                      uint32_t store_base, uint32_t seq_base, int64_t out_base, uint32_t pool_chunk) {
-  ch.n = chunk_rows(ch, st, blockIdx.x == 0 && threadIdx.x == 0);
+  // (kept in a register: writing ch.n would force a local-memory copy of the whole parameter struct)
+  const int64_t n_rows = chunk_rows(ch, st, blockIdx.x == 0 && threadIdx.x == 0);
   const int lane = lane_id(), q = lane & 3, qlead = lane & ~3;
   // Overflow row ids come from a per-warp pool that persists across launches: one atomicAdd on the
   // shared counter hands a warp `pool_chunk` ids.  (One atomicAdd per 8 rows on that single address
@@ -1114,7 +1115,7 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) join_inner_q4_kernel(const Joi
   uint64_t* po0 = oc0 >= 0 ? (uint64_t*)o.col[oc0] : nullptr;
   uint64_t* po1 = oc1 >= 0 ? (uint64_t*)o.col[oc1] : nullptr;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t groups = (ch.n + 7) >> 3;
+  const int64_t groups = (n_rows + 7) >> 3;
   ulonglong2 cas_empty, cas_want;
   cas_empty.x = J_EMPTY;
   cas_empty.y = W_EMPTY;
@@ -1129,7 +1130,7 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) join_inner_q4_kernel(const Joi
   auto fetch = [&](int64_t g2) {
     const int64_t r2 = g2 * 8 + (lane >> 2);
     n_op = 0;
-    if (g2 < groups && r2 < ch.n) {
+    if (g2 < groups && r2 < n_rows) {
       n_op = ch.ops[r2];
       n_key = __ldg(pk + r2);
       if (pa) n_va = __ldg(pa + r2);
@@ -1139,7 +1140,7 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) join_inner_q4_kernel(const Joi
   fetch(warp_global);
   for (int64_t g = warp_global; g < groups; g += nwarps) {
     const int64_t r = g * 8 + (lane >> 2);
-    const bool in = r < ch.n;
+    const bool in = r < n_rows;
     const uint8_t op = n_op;
     const uint64_t key = n_key, va = n_va, vb = n_vb;
     const int64_t pos = out_base + r;
@@ -1214,7 +1215,7 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) join_inner_q4_kernel(const Joi
         uint32_t left = cnt;
         int64_t xpos = 0;
         if (cnt > 1u) {
-          xpos = out_base + ch.n + (int64_t)atomicAdd(&st->out_rows, (unsigned long long)(cnt - 1));
+          xpos = out_base + n_rows + (int64_t)atomicAdd(&st->out_rows, (unsigned long long)(cnt - 1));
           if (xpos + (cnt - 1) > o.capacity) { atomicOr(&st->err, JERR_OUT_CAPACITY); left = 1; }
         }
         bool first = true;
@@ -1342,13 +1343,13 @@ __device__ __forceinline__ void join_status_publish(JoinStatus* st, JoinStatus* 
 __global__ void __launch_bounds__(256) join_inner_delete_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch,
                                                                  JoinSideDev own, JoinStatus* st, uint32_t seq_base,
                                                                  JoinStatus* status_host, unsigned long long tag, int reset) {
-  ch.n = chunk_rows(ch, st, false);
+  const int64_t n_rows = chunk_rows(ch, st, false);
   if (*(volatile unsigned long long*)&st->n_del == 0ull) {
     // nothing to delete (the usual case): this launch doubles as the status read-back
     if (status_host && blockIdx.x == 0 && threadIdx.x == 0) join_status_publish(st, status_host, tag, reset);
     return;
   }
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
     const uint8_t op = ch.ops[r];
     if (!row_visible(ch, r, op) || !(op == RW_OP_DELETE || op == RW_OP_UPDATE_DELETE)) continue;
     uint64_t kw[RW_MAX_KEYS];
@@ -2020,7 +2021,9 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
     h->side[s].slot_cap = cap;
     rc = join_alloc_slots(h, s, h->side[s].slots, cap);
     if (rc != RW_OK) return rc;
-    rc = join_grow_store(h, s, 1024);  // overflow rows only; grows on demand
+    // overflow rows only; sized from the planner's cardinality hint (2 rows per expected key) so that a
+    // stream of the expected size never pays a doubling (allocate + copy + free) in its data path
+    rc = join_grow_store(h, s, std::max<uint64_t>(1024, std::min<uint64_t>(2 * hint, 0x40000000ull)));
     if (rc != RW_OK) return rc;
     RW_CUDA(h->side[s].pools.reserve((size_t)Q4_MAX_GRID * (JF_BLOCK / 32) * sizeof(uint2)));
     RW_CUDA(cudaMemsetAsync(h->side[s].pools.p, 0, h->side[s].pools.bytes, h->stream));
