@@ -512,6 +512,8 @@ def run_ours(args):
                     chunks_host.append(ch.to_abi())  # (rw_chunk with HOST pointers, keepalive)
             per_step = BATCH // FFI_ROWS
 
+            aliased = [0]
+
             def host_step(s):
                 """the calls a Rust shim makes: rwgpu_join_push(host chunk) -> out (pinned host memory); take the
                 chunk views; release.  The first and last 1024-row views are fetched and read here -- walking all
@@ -524,6 +526,12 @@ def run_ours(args):
                     nch = be._out_num_chunks(out)
                     for i in ((0, nch - 1) if nch > 1 else range(nch)):
                         be._out_chunk(out, i, C.byref(view))
+                        if i == 0 and view.n_rows:
+                            # output columns that alias the input chunk's host buffers were not copied back
+                            inp = chunks_host[s * per_step + j][0]
+                            lo = [int(inp.columns[k].data or 0) for k in range(inp.n_cols)]
+                            aliased[0] = sum(any(a <= int(view.columns[k].data or 0) < a + 8 * FFI_ROWS for a in lo if a)
+                                             for k in range(view.n_cols))
                         if view.n_rows:
                             last = C.cast(view.columns[view.n_cols - 1].data, C.POINTER(C.c_int64))[view.n_rows - 1]
                             tot += 0 * int(last)  # a host read of the result
@@ -541,8 +549,10 @@ def run_ours(args):
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             line["e2e"] = {"value": K * BATCH / dt, "unit": "rows/s", "h2d_bytes_per_step": BATCH * (4 * 8 + 1),
-                           "d2h_bytes_per_step": tot * (8 * 8 + 1) // K, "ffi_batch_rows": FFI_ROWS, "ms_per_step": dt / K * 1e3,
-                           "note": "pinned host StreamChunk buffers -> rwgpu_join_push -> pinned host output chunk views (C ABI via ctypes)"}
+                           "d2h_bytes_per_step": tot * (8 * (8 - aliased[0]) + 1) // K, "ffi_batch_rows": FFI_ROWS, "ms_per_step": dt / K * 1e3,
+                           "output_columns_aliasing_input": aliased[0],
+                           "note": "pinned host StreamChunk buffers -> rwgpu_join_push -> host output chunk views (C ABI via ctypes); "
+                                   "the bid-side output columns alias the caller's input buffers (rwgpu.h), the rest is read back"}
             del join2, chunks_host
             torch.cuda.empty_cache()
 

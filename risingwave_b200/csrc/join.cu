@@ -2166,6 +2166,17 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
   // pinned host block laid out for `host_cap` rows; re-laid (host copy of the prefix) if outputs exceed it
   int64_t host_cap = std::max<int64_t>(2 * n, 1024);
   if (!o->layout(host_cap, h->out_types, ~0ull >> 1, true, h->pool)) return fail(RW_ERR_OOM, "pinned output block");
+  // Positional inner-join output (row r of the output = input row r): the update side's output columns are
+  // byte-for-byte the caller's input columns, which already sit in host memory -- they are not copied back
+  // over PCIe; the output chunk views alias the input buffers instead (contract in rwgpu.h).
+  static const bool no_alias = getenv("RWGPU_NO_ALIAS") != nullptr;
+  bool alias_ok = !no_alias && h->fast_inner && h->w8_ok[side] && !c->visibility && n > 0;
+  for (int k = 0; k < c->n_cols && alias_ok; k++) alias_ok = c->columns[k].validity == nullptr;
+  std::vector<int> alias_src(h->out_types.size(), -1);
+  if (alias_ok)
+    for (int k = 0; k < c->n_cols; k++)
+      if (h->w8[side].u_out[k] >= 0) alias_src[(size_t)h->w8[side].u_out[k]] = k;
+  bool aligned = true;  // every sub-batch produced exactly its positional rows (no extras, no empty result)
   int64_t total = 0;
   unsigned long long nullm = 0;
   int js = 0;
@@ -2192,6 +2203,7 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
     rc = join_push_dev(h, side, ch, h->stream, total, &rows, &nullm);
     if (trace) fprintf(stderr, "   sub %d: wait-h2d %.3f  push_dev %.3f ms\n", js, tb - ta, now() - tb);
     if (rc != RW_OK) { cudaStreamSynchronize(h->s_d2h); return rc; }
+    aligned = aligned && rows == m;
     if (total + rows > host_cap) {  // rare: amplification above 2x -- grow the host block, keep the copied prefix
       RW_CUDA(cudaStreamSynchronize(h->s_d2h));
       auto o2 = new rwgpu_out();
@@ -2211,12 +2223,22 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
       RW_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_main[js], 0));
       cudaMemcpyAsync(o->ops + total, h->out_ops.as<uint8_t>() + total, (size_t)rows, cudaMemcpyDeviceToHost, h->s_d2h);
       for (size_t k = 0; k < h->out_types.size(); k++) {
+        if (alias_src[k] >= 0) continue;  // decided after the last sub-batch
         const size_t w = type_width(h->out_types[k]);
         cudaMemcpyAsync(o->data[k] + (size_t)total * w, h->out_col[k].as<uint8_t>() + (size_t)total * w, (size_t)rows * w,
                         cudaMemcpyDeviceToHost, h->s_d2h);
       }
     }
     total += rows;
+  }
+  for (size_t k = 0; k < h->out_types.size(); k++) {
+    if (alias_src[k] < 0) continue;
+    if (aligned && total == n) {
+      o->data[k] = (uint8_t*)const_cast<void*>(c->columns[alias_src[k]].data);  // zero-copy: the caller's input column
+    } else if (total > 0) {  // extra matches or an empty sub-batch broke the row alignment: ordinary copy
+      // (every sub-batch's kernels have completed: join_push_dev synchronises on its status read-back)
+      cudaMemcpyAsync(o->data[k], h->out_col[k].p, (size_t)total * type_width(h->out_types[k]), cudaMemcpyDeviceToHost, h->s_d2h);
+    }
   }
   // NULL / visibility bytes only for the columns that need them (known once all sub-batches ran)
   if (total > 0) {
