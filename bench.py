@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """bench.py -- Nexmark-shaped streaming HashJoin (headline) and HashAgg (secondary) throughput.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload join|agg]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--legs value,e2e,agg,chain,cpu]
 
 Workload (BASELINE.json configs[2], "Nexmark q7/q8 streaming HashJoin (bid x auction) 1xB200, 10M build
 rows in HBM"):  the auction side (10 000 000 rows: id, seller, category, expires)
@@ -9,14 +9,20 @@ is loaded into the right-side join state, then every STEP pushes one batch of 2^
 (auction, date_time, bidder, price; 1024 StreamChunks of 1024 rows coalesced into one device batch)
 through the inner-join operator: each bid probes the auction state (1 match), the joined 8-column
 rows are emitted, and the bid is inserted into the left-side state.  metric = input rows / s.
-N > 1 (configs[3]): every rank generates its own bid / auction shard, partitions it by the
-reference's CRC32 vnode on the GPU, exchanges rows with NCCL all-to-all-v and joins its vnode
-range (weak scaling: 10M build rows and 2^20 bid rows per step PER GPU).
+N > 1 (configs[3]): every rank generates its own bid / auction shard; a step partitions the bids by the
+reference's CRC32 vnode on the GPU, stores them straight into the owning rank's receive region over
+NVLink peer memory (one library call, device barrier), and the join consumes the received rows with
+the row count read on the device -- weak scaling: 10M build rows and 2^20 bid rows per step PER GPU.
+RWGPU_EXCHANGE=nccl selects partition + NCCL all-to-all-v instead.
 
-`value`   : inputs already resident in HBM, `rwgpu_join_push_device` (CUDA-event timed).
-`e2e`     : the same steps through the host-buffer C-ABI call `rwgpu_join_push` (host numpy chunks in,
-            host output chunks out; H2D / D2H inside the timed region).
+`value`   : inputs already resident in HBM, `rwgpu_join_push_device` (CUDA-event timed, max over ranks).
+`e2e`     : the same steps through the host-buffer C-ABI call `rwgpu_join_push` (pinned host chunks in,
+            host output chunk views out; H2D / D2H inside the timed region; N>1: host input partitioned
+            per rank, no exchange).
 `secondary`: BASELINE configs[1] (q4-shaped HashAgg: count(*), sum, max GROUP BY auction, 2^18-row epochs).
+`chain`   : join -> Filter -> Project -> HashAgg without leaving HBM, a barrier per batch.
+`roofline`: dominant kernel, algorithmic bytes / CUDA-event time against MEASURED_PEAKS.json; `traffic` from the
+            committed ncu capture (profiles/r1_traffic.json).  `clocks`: in-process NVML samples during the region.
 `--impl reference`: the CPU restatement of the reference algorithm (oracle/fastcpu.cc, one
 single-threaded actor per host core, inputs pre-partitioned by vnode) on a bounded sample.
 """

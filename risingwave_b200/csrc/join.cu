@@ -1720,14 +1720,14 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream
       const int grid = q4 ? q4_grid : jgrid(n, JF_BLOCK);
       auto launch = [&](bool probe_only, uint32_t store_base) {
         if (q4) {
-          static const int minb = getenv("RWGPU_Q4_MINB") ? atoi(getenv("RWGPU_Q4_MINB")) : 4;  // occupancy experiment
-#define Q4_LAUNCH(PO, MB)                                                                                                              \
-  join_inner_q4_kernel<PO, MB><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds, \
-                                                          store_base, seq_base, out_base, pool_chunk)
-          if (probe_only) Q4_LAUNCH(true, 4);
-          else if (minb == 6) Q4_LAUNCH(false, 6);
-          else Q4_LAUNCH(false, 4);  // measured: 3 blocks/SM 0.262 ms, 4: 0.227, 5: 0.267, 6: 0.300, 8: 0.329 per 2^20 rows
-#undef Q4_LAUNCH
+          // 4 blocks of 256 threads per SM (64 registers).  Measured per 2^20 rows: 3 blocks/SM 0.262 ms, 4: 0.227,
+          // 5: 0.267, 6: 0.300, 8: 0.329 -- the kernel is bound by random DRAM transactions, not by occupancy.
+          if (probe_only)
+            join_inner_q4_kernel<true, 4><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h),
+                                                                      ds, store_base, seq_base, out_base, pool_chunk);
+          else
+            join_inner_q4_kernel<false, 4><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h),
+                                                                       ds, store_base, seq_base, out_base, pool_chunk);
         } else {
           if (probe_only)
             join_inner_w8p_kernel<true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, side_dev(h, S), side_dev(h, 1 - S), out_dev(h), ds,
