@@ -645,9 +645,9 @@ int32_t rwo_join_create(const rw_join_desc* d, rwo_join** out) {
   j.side[0].need_degree = need_left_degree(j.T) && !j.side[1].pk_in_jk;   // :397
   j.side[1].need_degree = need_right_degree(j.T) && !j.side[0].pk_in_jk;  // :398
   // output schema :337-359 and i2o mapping :400-410 / builder.rs:63-80
-  int left_len = j.side[0].n_cols, right_len = j.side[1].n_cols;
+  int left_len = j.side[0].n_cols;  // columns of the natural output that come from the left input
   std::vector<int> nat;
-  if (j.T == RW_JOIN_LEFT_SEMI || j.T == RW_JOIN_LEFT_ANTI) { nat = j.side[0].types; right_len = 0; }
+  if (j.T == RW_JOIN_LEFT_SEMI || j.T == RW_JOIN_LEFT_ANTI) { nat = j.side[0].types; }
   else if (j.T == RW_JOIN_RIGHT_SEMI || j.T == RW_JOIN_RIGHT_ANTI) { nat = j.side[1].types; left_len = 0; }
   else { nat = j.side[0].types; nat.insert(nat.end(), j.side[1].types.begin(), j.side[1].types.end()); }
   for (int oi = 0; oi < d->n_output; oi++) {
