@@ -10,6 +10,7 @@ Outputs (committed):
     tests/golden/hash_agg_kats.json    <- src/stream/tests/integration_tests/hash_agg.rs
     tests/golden/agg_func_kats.json    <- src/expr/impl/src/aggregate/general.rs tests
     tests/golden/filter_kats.json      <- src/stream/src/executor/filter.rs tests
+    tests/golden/nexmark_q4_fixture.json <- e2e_test/nexmark/insert_{auction,bid}.slt.part + e2e_test/streaming/nexmark/q4.slt.part
 
 Only test DATA is transcribed (the `from_pretty` literals, the executor configuration and the
 push / expect script of each test); no reference code is copied.
@@ -210,6 +211,41 @@ def extract_filter():
     return out
 
 
+# ----------------------------------------------------------------------------------- nexmark e2e fixture (q4)
+def extract_nexmark_q4():
+    """e2e_test/nexmark/insert_{auction,bid}.slt.part + the expected rows of e2e_test/streaming/nexmark/q4.slt.part
+    (view: e2e_test/streaming/nexmark/views/q4.slt.part).  Only the columns q4 reads are kept; timestamps become
+    microseconds since the epoch (the in-memory representation of TIMESTAMP)."""
+    import ast
+    from datetime import datetime, timezone
+
+    def ts(x):
+        fmt = "%Y-%m-%d %H:%M:%S.%f" if "." in x else "%Y-%m-%d %H:%M:%S"
+        d = datetime.strptime(x, fmt).replace(tzinfo=timezone.utc)
+        return int(d.timestamp()) * 1_000_000 + d.microsecond
+
+    def rows(path):
+        out = []
+        for ln in open(os.path.join(REF, path)):
+            ln = ln.strip()
+            if ln.startswith("(") and not ln.startswith("(\n") and ln[1:2].isdigit():
+                out.append(ast.literal_eval(ln.rstrip(",;")))
+        return out
+
+    auction = [[r[0], ts(r[5]), ts(r[6]), r[8]] for r in rows("e2e_test/nexmark/insert_auction.slt.part")]   # id, date_time, expires, category
+    bid = [[r[0], r[2], ts(r[5])] for r in rows("e2e_test/nexmark/insert_bid.slt.part")]                      # auction, price, date_time
+    exp = []
+    seen = False
+    for ln in open(os.path.join(REF, "e2e_test/streaming/nexmark/q4.slt.part")):
+        if ln.startswith("----"):
+            seen = True
+        elif seen and ln.strip():
+            exp.append(ln.split())
+    return {"source": "e2e_test/nexmark/insert_auction.slt.part, insert_bid.slt.part; expected e2e_test/streaming/nexmark/q4.slt.part",
+            "auction_columns": ["id", "date_time_us", "expires_us", "category"], "auction": auction,
+            "bid_columns": ["auction", "price", "date_time_us"], "bid": bid, "expected_q4": exp}
+
+
 def main():
     if not os.path.isdir(REF):
         sys.exit("reference not mounted; fixtures are committed, nothing to do")
@@ -219,6 +255,9 @@ def main():
     json.dump(ha, open(os.path.join(OUT, "hash_agg_kats.json"), "w"), indent=1)
     af = extract_agg_funcs()
     json.dump(af, open(os.path.join(OUT, "agg_func_kats.json"), "w"), indent=1)
+    q4 = extract_nexmark_q4()
+    json.dump(q4, open(os.path.join(OUT, "nexmark_q4_fixture.json"), "w"), indent=0)
+    print(f"nexmark q4 fixture: {len(q4['auction'])} auctions, {len(q4['bid'])} bids, {len(q4['expected_q4'])} expected rows")
     fl = extract_filter()
     json.dump(fl, open(os.path.join(OUT, "filter_kats.json"), "w"), indent=1)
     print(f"filter: {len(fl)} tests")

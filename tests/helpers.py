@@ -127,3 +127,63 @@ def rand_chunk(rng, n, types, key_cols=(), key_range=16, null_frac=0.0, ops=None
         ops = np.full(n, abi.OP_INSERT, np.uint8)
     vis = None if vis_frac >= 1.0 else rng.random(n) < vis_frac
     return StreamChunk(ops, cols, vis)
+
+
+def run_nexmark_q4(oracle):
+    """The reference's own SQL-level fixture for q4 (e2e_test/nexmark/insert_{auction,bid}.slt.part ->
+    e2e_test/streaming/nexmark/views/q4.slt.part -> expected rows of e2e_test/streaming/nexmark/q4.slt.part),
+    run incrementally through the oracle's operators exactly as the streaming plan does:
+    bid JOIN auction ON auction = id -> Filter(date_time BETWEEN a.date_time AND a.expires) -> Project ->
+    HashAgg(max(price) GROUP BY id, category) -> Project -> HashAgg(count, sum GROUP BY category) -> avg.
+    Several barriers, so the first aggregation retracts and re-emits groups whose max changed."""
+    from decimal import Decimal
+    from fractions import Fraction
+    from risingwave_b200.executor import AggCall, FilterExecutor, HashAggExecutor, HashJoinExecutor, JoinParams, MockSource
+    from risingwave_b200.stream_chunk import Column, StreamChunk
+    fx = load_golden("nexmark_q4_fixture.json")
+    I = abi.T_INT64
+    _, sl = MockSource.channel()
+    _, sr = MockSource.channel()
+    join = HashJoinExecutor(oracle, abi.JOIN_INNER, sl.into_executor([I] * 4, [3]), sr.into_executor([I] * 4, [0]),
+                            JoinParams([0], [3]), JoinParams([0], [0]), [False])
+    _, sf = MockSource.channel()
+    flt = FilterExecutor(oracle, sf.into_executor([I] * 8, []),
+                         "(and:boolean (greater_than_or_equal:boolean $2:int8 $5:int8) (less_than_or_equal:boolean $2:int8 $6:int8))")
+    _, s1 = MockSource.channel()
+    agg1 = HashAggExecutor(oracle, s1.into_executor([I] * 3, []), True,
+                           [AggCall.from_pretty(c) for c in ("(count:int8)", "(max:int8 $2:int8)")], 0, [0, 1])
+    _, s2 = MockSource.channel()
+    agg2 = HashAggExecutor(oracle, s2.into_executor([I] * 2, []), False,
+                           [AggCall.from_pretty(c) for c in ("(count:int8)", "(sum:int8 $1:int8)")], 0, [0])
+    mv = {}  # category -> (count, sum)
+
+    def ins(rows):
+        cols = list(zip(*rows))
+        return StreamChunk(np.full(len(rows), abi.OP_INSERT, np.uint8), [Column(I, np.array(c, dtype=np.int64)) for c in cols])
+
+    def after_join(chunks):
+        for ch in chunks:
+            f = flt.filter(ch)
+            if f is not None:  # Project (a.id, a.category, b.price)
+                agg1.apply_chunk(StreamChunk(f.ops, [f.columns[4], f.columns[7], f.columns[1]], f.vis))
+
+    def barrier(epoch):
+        for ch in agg1.flush_data(epoch):  # (id, category, count, max) -> Project (category, max)
+            agg2.apply_chunk(StreamChunk(ch.ops, [ch.columns[1], ch.columns[3]], ch.vis))
+        for ch in agg2.flush_data(epoch):
+            for op, row in ch.rows():
+                if op in (abi.OP_INSERT, abi.OP_UPDATE_INSERT):
+                    mv[row[0]] = (row[1], row[2])
+                elif mv.get(row[0]) == (row[1], row[2]):
+                    del mv[row[0]]
+
+    bids = [r + [k] for k, r in enumerate(fx["bid"])]  # + a row id as the stream key
+    auct, epoch = fx["auction"], 0
+    for step in range(5):  # interleave the two inputs, a barrier after every slice
+        after_join(join.eq_join_oneside(1, ins(auct[step * 8:(step + 1) * 8])))
+        after_join(join.eq_join_oneside(0, ins(bids[step * 10:(step + 1) * 10])))
+        epoch += 1
+        barrier(epoch)
+    want = {int(c): Fraction(Decimal(v)) for c, v in fx["expected_q4"]}
+    got = {c: Fraction(s, n) for c, (n, s) in mv.items()}
+    assert got == want

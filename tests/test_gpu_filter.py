@@ -9,7 +9,7 @@ from risingwave_b200 import abi
 from risingwave_b200.executor import AggCall, FilterExecutor, HashAggExecutor, HashJoinExecutor, JoinParams, MockSource, parse_filter_expr
 from risingwave_b200.stream_chunk import Column, StreamChunk, net_multiset
 
-from helpers import load_golden
+from helpers import load_golden, run_nexmark_q4
 from test_oracle_golden import run_filter_kat
 
 pytestmark = pytest.mark.gpu
@@ -134,3 +134,9 @@ def test_join_filter_agg_chain_on_device(cuda, oracle):
         got = net_multiset(ag.flush_data(e + 1))
         assert got == want, f"epoch {e}: agg deltas differ"
         assert sum(abs(v) for v in want.values()) > 0
+
+
+def test_nexmark_q4_end_to_end_fixture(cuda):
+    """the reference's SQL-level q4 fixture (expected rows of e2e_test/streaming/nexmark/q4.slt.part) through the
+    CUDA operators: join -> filter -> agg(max, two group keys) -> agg(count, sum with retractions) -> avg"""
+    run_nexmark_q4(cuda)

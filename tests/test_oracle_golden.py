@@ -19,7 +19,7 @@ from risingwave_b200 import abi
 from risingwave_b200.executor import AggCall, FilterExecutor, MockSource
 from risingwave_b200.stream_chunk import StreamChunk
 
-from helpers import load_golden, run_agg_kat, run_join_kat
+from helpers import load_golden, run_agg_kat, run_join_kat, run_nexmark_q4
 
 JOIN_KATS = [k for k in load_golden("hash_join_kats.json") if "skipped" not in k]
 AGG_KATS = [k for k in load_golden("hash_agg_kats.json") if "skipped" not in k]
@@ -154,3 +154,8 @@ def test_filter_oracle_three_valued_and_all_hidden(oracle):
     assert ex.filter(StreamChunk.from_pretty(" I I\n + 1 2 \n - 1 2")) is None
     with pytest.raises(abi.RwError):  # a U- whose U+ is missing: StreamChunk::with_visibility would panic on the lengths
         ex.filter(StreamChunk.from_pretty(" I I\n U- 5 1 \n + 7 3"))
+
+
+def test_nexmark_q4_end_to_end_fixture(oracle):
+    """the reference's SQL-level q4 fixture through the oracle's operators (helpers.run_nexmark_q4)"""
+    run_nexmark_q4(oracle)
