@@ -11,6 +11,7 @@ Outputs (committed):
     tests/golden/agg_func_kats.json    <- src/expr/impl/src/aggregate/general.rs tests
     tests/golden/filter_kats.json      <- src/stream/src/executor/filter.rs tests
     tests/golden/nexmark_q4_fixture.json <- e2e_test/nexmark/insert_{auction,bid}.slt.part + e2e_test/streaming/nexmark/q4.slt.part
+    tests/golden/nexmark_q7_fixture.json <- e2e_test/nexmark/insert_bid.slt.part + e2e_test/streaming/nexmark/q7.slt.part
 
 Only test DATA is transcribed (the `from_pretty` literals, the executor configuration and the
 push / expect script of each test); no reference code is copied.
@@ -241,6 +242,19 @@ def extract_nexmark_q4():
             seen = True
         elif seen and ln.strip():
             exp.append(ln.split())
+    exp7, seen = [], False
+    for ln in open(os.path.join(REF, "e2e_test/streaming/nexmark/q7.slt.part")):
+        if ln.startswith("----"):
+            seen = True
+        elif seen and ln.strip():
+            f = ln.split()
+            exp7.append([int(f[0]), int(f[1]), int(f[2]), ts(f[3] + " " + f[4])])
+    q7 = {"source": "e2e_test/nexmark/insert_bid.slt.part; view e2e_test/streaming/nexmark/views/q7.slt.part; expected "
+                    "e2e_test/streaming/nexmark/q7.slt.part",
+          "bid_columns": ["auction", "bidder", "price", "date_time_us"],
+          "bid": [[r[0], r[1], r[2], ts(r[5])] for r in rows("e2e_test/nexmark/insert_bid.slt.part")],
+          "expected_columns": ["auction", "price", "bidder", "date_time_us"], "expected_q7": exp7}
+    json.dump(q7, open(os.path.join(OUT, "nexmark_q7_fixture.json"), "w"), indent=0)
     return {"source": "e2e_test/nexmark/insert_auction.slt.part, insert_bid.slt.part; expected e2e_test/streaming/nexmark/q4.slt.part",
             "auction_columns": ["id", "date_time_us", "expires_us", "category"], "auction": auction,
             "bid_columns": ["auction", "price", "date_time_us"], "bid": bid, "expected_q4": exp}

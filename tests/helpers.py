@@ -187,3 +187,59 @@ def run_nexmark_q4(oracle):
     want = {int(c): Fraction(Decimal(v)) for c, v in fx["expected_q4"]}
     got = {c: Fraction(s, n) for c, (n, s) in mv.items()}
     assert got == want
+
+
+def run_nexmark_q7(backend):
+    """The reference's SQL-level fixture for Nexmark q7 (e2e_test/streaming/nexmark/views/q7.slt.part -> expected rows
+    of e2e_test/streaming/nexmark/q7.slt.part), incrementally:
+      bid -> [Project: + window_end = tumble_end(date_time, 10 s)] -> HashAgg(max(price) GROUP BY window_end)
+          -> [Project: (maxprice, window_end, window_end - 10 s)] = B1
+      bid B JOIN B1 ON B.price = B1.maxprice -> Filter(B.date_time BETWEEN B1.window_end - 10 s AND B1.window_end)
+    The aggregate is re-emitted at every barrier, so the join's right side sees U-/U+ retractions of old maxima.
+    (The two Projects carry arithmetic and stay on the host, as in the shim.)"""
+    from collections import Counter
+    from risingwave_b200.executor import AggCall, FilterExecutor, HashAggExecutor, HashJoinExecutor, JoinParams, MockSource
+    from risingwave_b200.stream_chunk import Column, StreamChunk
+    fx = load_golden("nexmark_q7_fixture.json")
+    I = abi.T_INT64
+    W = 10_000_000  # 10 s in microseconds
+    _, sa = MockSource.channel()
+    agg = HashAggExecutor(backend, sa.into_executor([I, I], []), True,
+                          [AggCall.from_pretty(c) for c in ("(count:int8)", "(max:int8 $1:int8)")], 0, [0])
+    _, sl = MockSource.channel()
+    _, sr = MockSource.channel()
+    # left: bid (auction, bidder, price, date_time, row id)   right: B1 (maxprice, window_end, window_start)
+    join = HashJoinExecutor(backend, abi.JOIN_INNER, sl.into_executor([I] * 5, [4]), sr.into_executor([I] * 3, [1]),
+                            JoinParams([2], [4]), JoinParams([0], [1]), [False])
+    _, sf = MockSource.channel()
+    flt = FilterExecutor(backend, sf.into_executor([I] * 8, []),
+                         "(and:boolean (greater_than_or_equal:boolean $3:int8 $7:int8) (less_than_or_equal:boolean $3:int8 $6:int8))")
+    mv = Counter()
+
+    def sink(chunks):
+        for ch in chunks:
+            f = flt.filter(ch)
+            if f is None:
+                continue
+            for op, row in f.rows():  # (visible rows only)
+                key = (row[0], row[2], row[1], row[3])  # auction, price, bidder, date_time
+                mv[key] += 1 if op in (abi.OP_INSERT, abi.OP_UPDATE_INSERT) else -1
+
+    def ins(rows, ops=None):
+        cols = list(zip(*rows))
+        return StreamChunk(np.full(len(rows), abi.OP_INSERT, np.uint8) if ops is None else ops,
+                           [Column(I, np.array(c, dtype=np.int64)) for c in cols])
+
+    bids = [r + [k] for k, r in enumerate(fx["bid"])]
+    for e, lo in enumerate(range(0, len(bids), 7)):
+        part = bids[lo:lo + 7]
+        sink(join.eq_join_oneside(0, ins(part)))
+        agg.apply_chunk(ins([[(r[3] // W) * W + W, r[2]] for r in part]))  # (window_end, price)
+        for ch in agg.flush_data(e + 1):  # (window_end, count, max) -> B1 rows, ops preserved (U-/U+ on a changed max)
+            rows = [[row[2], row[0], row[0] - W] for _, row in ch.rows()]
+            ops = np.array([op for op, _ in ch.rows()], dtype=np.uint8)
+            if rows:
+                sink(join.eq_join_oneside(1, ins(rows, ops)))
+    got = sorted(k for k, v in mv.items() for _ in range(v))
+    assert all(v >= 0 for v in mv.values())
+    assert got == sorted(tuple(r) for r in fx["expected_q7"])
