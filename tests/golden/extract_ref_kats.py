@@ -12,6 +12,7 @@ Outputs (committed):
     tests/golden/filter_kats.json      <- src/stream/src/executor/filter.rs tests
     tests/golden/nexmark_q4_fixture.json <- e2e_test/nexmark/insert_{auction,bid}.slt.part + e2e_test/streaming/nexmark/q4.slt.part
     tests/golden/nexmark_q7_fixture.json <- e2e_test/nexmark/insert_bid.slt.part + e2e_test/streaming/nexmark/q7.slt.part
+    tests/golden/nexmark_q8_fixture.json <- e2e_test/nexmark/insert_{person,auction}.slt.part + e2e_test/streaming/nexmark/q8.slt.part
 
 Only test DATA is transcribed (the `from_pretty` literals, the executor configuration and the
 push / expect script of each test); no reference code is copied.
@@ -255,6 +256,21 @@ def extract_nexmark_q4():
           "bid": [[r[0], r[1], r[2], ts(r[5])] for r in rows("e2e_test/nexmark/insert_bid.slt.part")],
           "expected_columns": ["auction", "price", "bidder", "date_time_us"], "expected_q7": exp7}
     json.dump(q7, open(os.path.join(OUT, "nexmark_q7_fixture.json"), "w"), indent=0)
+    exp8, seen = [], False
+    for ln in open(os.path.join(REF, "e2e_test/streaming/nexmark/q8.slt.part")):
+        if ln.startswith("----"):
+            seen = True
+        elif seen and ln.strip():
+            f = ln.rstrip("\n").split("\t")
+            exp8.append([int(f[0]), f[1], ts(f[2])])
+    q8 = {"source": "e2e_test/nexmark/insert_person.slt.part, insert_auction.slt.part; view e2e_test/streaming/nexmark/views/"
+                    "q8.slt.part; expected e2e_test/streaming/nexmark/q8.slt.part",
+          "person_columns": ["id", "name", "date_time_us"],
+          "person": [[r[0], r[1], ts(r[6])] for r in rows("e2e_test/nexmark/insert_person.slt.part")],
+          "auction_columns": ["seller", "date_time_us"],
+          "auction": [[r[7], ts(r[5])] for r in rows("e2e_test/nexmark/insert_auction.slt.part")],
+          "expected_columns": ["id", "name", "starttime_us"], "expected_q8": exp8}
+    json.dump(q8, open(os.path.join(OUT, "nexmark_q8_fixture.json"), "w"), indent=0)
     return {"source": "e2e_test/nexmark/insert_auction.slt.part, insert_bid.slt.part; expected e2e_test/streaming/nexmark/q4.slt.part",
             "auction_columns": ["id", "date_time_us", "expires_us", "category"], "auction": auction,
             "bid_columns": ["auction", "price", "date_time_us"], "bid": bid, "expected_q4": exp}

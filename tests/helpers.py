@@ -243,3 +243,56 @@ def run_nexmark_q7(backend):
     got = sorted(k for k, v in mv.items() for _ in range(v))
     assert all(v >= 0 for v in mv.values())
     assert got == sorted(tuple(r) for r in fx["expected_q7"])
+
+
+def run_nexmark_q8(backend):
+    """The reference's SQL-level fixture for Nexmark q8 (e2e_test/streaming/nexmark/views/q8.slt.part -> expected rows
+    of e2e_test/streaming/nexmark/q8.slt.part), incrementally:
+      person  -> [Project: id, tumble window (start, end)] -> HashAgg(GROUP BY id, start, end) = P
+      auction -> [Project: seller, tumble window]         -> HashAgg(GROUP BY seller, start, end) = A
+      P JOIN A ON id = seller AND starttime = starttime AND endtime = endtime      (three-column join key)
+    `name` is functionally dependent on `id` and is attached at the end (varchar columns stay on the host)."""
+    from collections import Counter
+    from risingwave_b200.executor import AggCall, HashAggExecutor, HashJoinExecutor, JoinParams, MockSource
+    from risingwave_b200.stream_chunk import Column, StreamChunk
+    fx = load_golden("nexmark_q8_fixture.json")
+    I = abi.T_INT64
+    W = 10_000_000
+    aggs = []
+    for _ in range(2):
+        _, s = MockSource.channel()
+        aggs.append(HashAggExecutor(backend, s.into_executor([I] * 3, []), True, [AggCall.from_pretty("(count:int8)")], 0, [0, 1, 2]))
+    _, sl = MockSource.channel()
+    _, sr = MockSource.channel()
+    join = HashJoinExecutor(backend, abi.JOIN_INNER, sl.into_executor([I] * 3, [0, 1, 2]), sr.into_executor([I] * 3, [0, 1, 2]),
+                            JoinParams([0, 1, 2], [0, 1, 2]), JoinParams([0, 1, 2], [0, 1, 2]), [False, False, False])
+    mv = Counter()
+
+    def ins(rows, ops=None):
+        cols = list(zip(*rows))
+        return StreamChunk(np.full(len(rows), abi.OP_INSERT, np.uint8) if ops is None else ops,
+                           [Column(I, np.array(c, dtype=np.int64)) for c in cols])
+
+    def sink(chunks):
+        for ch in chunks:
+            for op, row in ch.rows():
+                mv[(row[0], row[1])] += 1 if op in (abi.OP_INSERT, abi.OP_UPDATE_INSERT) else -1
+
+    def window(t):
+        return (t // W) * W, (t // W) * W + W
+
+    person = [[r[0], *window(r[2])] for r in fx["person"]]
+    auction = [[r[0], *window(r[1])] for r in fx["auction"]]
+    for e in range(5):
+        for side, rows in ((0, person[e * 4:(e + 1) * 4]), (1, auction[e * 8:(e + 1) * 8])):
+            if rows:
+                aggs[side].apply_chunk(ins(rows))
+            for ch in aggs[side].flush_data(e + 1):  # (k0, k1, k2, count): the count is projected away
+                keyrows = [list(row[:3]) for _, row in ch.rows()]
+                ops = np.array([op for op, _ in ch.rows()], dtype=np.uint8)
+                if keyrows:
+                    sink(join.eq_join_oneside(side, ins(keyrows, ops)))
+    name = {r[0]: r[1] for r in fx["person"]}
+    assert all(v in (0, 1) for v in mv.values())
+    got = sorted([k[0], name[k[0]], k[1]] for k, v in mv.items() if v)
+    assert got == sorted(fx["expected_q8"])

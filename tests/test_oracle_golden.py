@@ -19,7 +19,7 @@ from risingwave_b200 import abi
 from risingwave_b200.executor import AggCall, FilterExecutor, MockSource
 from risingwave_b200.stream_chunk import StreamChunk
 
-from helpers import load_golden, run_agg_kat, run_join_kat, run_nexmark_q4, run_nexmark_q7
+from helpers import load_golden, run_agg_kat, run_join_kat, run_nexmark_q4, run_nexmark_q7, run_nexmark_q8
 
 JOIN_KATS = [k for k in load_golden("hash_join_kats.json") if "skipped" not in k]
 AGG_KATS = [k for k in load_golden("hash_agg_kats.json") if "skipped" not in k]
@@ -165,3 +165,9 @@ def test_nexmark_q7_end_to_end_fixture(oracle):
     """the reference's SQL-level q7 fixture through the oracle's operators (helpers.run_nexmark_q7): the join's right
     side is an aggregate that retracts and re-emits its maxima"""
     run_nexmark_q7(oracle)
+
+
+def test_nexmark_q8_end_to_end_fixture(oracle):
+    """the reference's SQL-level q8 fixture through the oracle's operators (helpers.run_nexmark_q8): two group-by
+    aggregates feeding a join on a three-column key, both sides updating"""
+    run_nexmark_q8(oracle)
