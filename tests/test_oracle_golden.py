@@ -171,3 +171,23 @@ def test_nexmark_q8_end_to_end_fixture(oracle):
     """the reference's SQL-level q8 fixture through the oracle's operators (helpers.run_nexmark_q8): two group-by
     aggregates feeding a join on a three-column key, both sides updating"""
     run_nexmark_q8(oracle)
+
+
+def test_join_entry_state_iteration_order(oracle):
+    """join/hash_join.rs:889-918 `test_managed_join_state`: a key's rows iterate in insertion order while they live in
+    the inline `Vec` (<= 4 rows: pk 3, 2, 1) and in pk order once the set spilled to the `BTreeMap` (1, 2, 3, 4, 5).
+    Observed through the order of the matches a probe emits (same data; the join key is a constant column).  The
+    first probe makes the key's entry resident in the cache (a miss reads the state table in pk order instead:
+    hash_join.rs `take_state`), the rows inserted afterwards go into that cached entry."""
+    from risingwave_b200.executor import HashJoinExecutor, JoinParams
+    I = abi.T_INT64
+    _, sl = MockSource.channel()
+    _, sr = MockSource.channel()
+    ex = HashJoinExecutor(oracle, abi.JOIN_INNER, sl.into_executor([I, I], [1]), sr.into_executor([I, I, I], [1]),
+                          JoinParams([0], [1]), JoinParams([0], [1]), [False])
+    matched = lambda out: [(r[1][3], r[1][4]) for c in out for r in c.rows()]
+    assert ex.eq_join_oneside(0, StreamChunk.from_pretty(" I I\n + 7 100")) == []          # miss: caches the (empty) entry of key 7
+    assert matched(ex.eq_join_oneside(1, StreamChunk.from_pretty(" I I I\n + 7 3 4\n + 7 2 5\n + 7 1 6"))) == [(3, 4), (2, 5), (1, 6)]
+    assert matched(ex.eq_join_oneside(0, StreamChunk.from_pretty(" I I\n + 7 101"))) == [(3, 4), (2, 5), (1, 6)]   # `Vec`
+    ex.eq_join_oneside(1, StreamChunk.from_pretty(" I I I\n + 7 5 8\n + 7 4 9"))
+    assert matched(ex.eq_join_oneside(0, StreamChunk.from_pretty(" I I\n + 7 102"))) == [(1, 6), (2, 5), (3, 4), (4, 9), (5, 8)]  # `BTreeMap`
