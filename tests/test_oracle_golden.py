@@ -191,3 +191,15 @@ def test_join_entry_state_iteration_order(oracle):
     assert matched(ex.eq_join_oneside(0, StreamChunk.from_pretty(" I I\n + 7 101"))) == [(3, 4), (2, 5), (1, 6)]   # `Vec`
     ex.eq_join_oneside(1, StreamChunk.from_pretty(" I I I\n + 7 5 8\n + 7 4 9"))
     assert matched(ex.eq_join_oneside(0, StreamChunk.from_pretty(" I I\n + 7 102"))) == [(1, 6), (2, 5), (3, 4), (4, 9), (5, 8)]  # `BTreeMap`
+
+
+def test_group_key_null_positions_are_kept_apart(oracle):
+    """hash/key.rs:839-866 `test_simple_hash_key_nullable_serde`: the keys <1, NULL> and <NULL, 2> (two Int32 columns)
+    are different keys and deserialize back losslessly -- here: they form two groups whose key columns come back
+    exactly as they went in."""
+    from risingwave_b200.executor import HashAggExecutor
+    _, src = MockSource.channel()
+    agg = HashAggExecutor(oracle, src.into_executor([abi.T_INT32, abi.T_INT32], []), True, [AggCall.from_pretty("(count:int8)")], 0, [0, 1])
+    agg.apply_chunk(StreamChunk.from_pretty(" i i\n + 1 .\n + . 2\n + 1 .\n + . ."))
+    rows = sorted((r[1] for c in agg.flush_data(1) for r in c.rows()), key=repr)
+    assert rows == sorted([(1, None, 2), (None, 2, 1), (None, None, 1)], key=repr)
