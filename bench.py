@@ -279,10 +279,16 @@ def cpu_join_run(n_build, batches, n_actors, warmup, steps, chunk=CHUNK):
     """P single-threaded actors (one OS thread each, vnode-partitioned input), each fed 1024-row chunks
     of its partition.  Returns rows/s over the timed steps (wall clock, all actors in parallel)."""
     fc = FastCpu().f
-    fc.rwf_join_push_parallel.restype = C.c_int64
-    fc.rwf_join_push_parallel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p] + [C.c_void_p] * 5 + [C.c_int]
+    fc.rwf_pool_new.restype = C.c_void_p
+    fc.rwf_pool_new.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    fc.rwf_pool_push.restype = C.c_int64
+    fc.rwf_pool_push.argtypes = [C.c_void_p, C.c_int, C.c_void_p] + [C.c_void_p] * 5 + [C.c_int]
+    fc.rwf_pool_free.argtypes = [C.c_void_p]
     actors = [fc.rwf_join_new() for _ in range(n_actors)]
     act_arr = (C.c_void_p * n_actors)(*actors)
+    # long-lived worker threads, one per actor, pinned when there is a CPU for each of them
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    pool = fc.rwf_pool_new(act_arr, n_actors, int(1 < n_actors <= ncpu))
 
     def parts_of(cols):
         """-> ctypes argument pack for rwf_join_push_parallel (keeps the numpy arrays alive)."""
@@ -297,7 +303,7 @@ def cpu_join_run(n_build, batches, n_actors, warmup, steps, chunk=CHUNK):
 
     def push(side, pack):
         cnt, ops_p, col_p, _ = pack
-        return fc.rwf_join_push_parallel(act_arr, n_actors, side, cnt.ctypes.data, ops_p, *col_p, chunk)
+        return fc.rwf_pool_push(pool, side, cnt.ctypes.data, ops_p, *col_p, chunk)
 
     auct = gen_auctions(n_build, SEED)
     ap = parts_of(auct)
@@ -313,6 +319,7 @@ def cpu_join_run(n_build, batches, n_actors, warmup, steps, chunk=CHUNK):
         push(0, packs[s])
     dt = time.perf_counter() - t0
     rows = sum(len(batches[s][0]) for s in range(warmup, warmup + steps))
+    fc.rwf_pool_free(pool)
     for a in actors:
         fc.rwf_join_free(a)
     return rows / dt, dt
@@ -712,8 +719,8 @@ def run_reference(args):
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cores = os.cpu_count() or 1
-    P = max(1, min(cores, 256))
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    P = max(1, min(cores, 256))  # one long-lived, pinned worker thread per actor (oracle/fastcpu.cc rwf_pool_*)
     K, W = args.steps, args.warmup
     step_rows = BATCH
     n_steps = min(K, 20)

@@ -287,3 +287,92 @@ extern "C" int64_t rwf_join_push_parallel(rwf_join** actors, int P, int side, co
   for (int a = 0; a < P; a++) { th[a].join(); tot += outs[a]; }
   return tot;
 }
+
+
+// Persistent worker pool: one long-lived OS thread per actor (the reference's actors are long-lived tasks on
+// a worker pool, actor.rs:209-232), woken once per batch.  Spawning P threads for every batch -- the first
+// version of this driver -- cost more than the work of a batch on a 128-thread host.  Worker a is pinned to
+// CPU a % ncpu when `pin` is set, so an actor's state stays on the socket that first touched it.
+#include <condition_variable>
+#include <mutex>
+#include <pthread.h>
+#include <sched.h>
+#include <unistd.h>
+struct rwf_pool {
+  int P = 0;
+  rwf_join** actors = nullptr;
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv_start, cv_done;
+  uint64_t gen = 0;
+  int remaining = 0;
+  bool stop = false;
+  // task of the current generation
+  int side = 0, chunk = 1024;
+  const int64_t* n = nullptr;
+  const uint8_t* const* ops = nullptr;
+  const int64_t* const* c[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<int64_t> outs;
+};
+static void rwf_pool_worker(rwf_pool* p, int a, int pin) {
+  if (pin) {
+    long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    CPU_SET((int)(a % (ncpu > 0 ? ncpu : 1)), &set);
+    pthread_setaffinity_np(pthread_self(), sizeof(set), &set);  // best effort
+  }
+  uint64_t seen = 0;
+  while (true) {
+    {
+      std::unique_lock<std::mutex> lk(p->m);
+      p->cv_start.wait(lk, [&] { return p->stop || p->gen != seen; });
+      if (p->stop) return;
+      seen = p->gen;
+    }
+    int64_t tot = 0;
+    const int64_t na = p->n[a];
+    for (int64_t i = 0; i < na; i += p->chunk) {
+      const int64_t m = na - i < p->chunk ? na - i : p->chunk;
+      tot += rwf_join_push(p->actors[a], p->side, m, p->ops[a] + i, p->c[0][a] + i, p->c[1][a] + i, p->c[2][a] + i, p->c[3][a] + i);
+    }
+    p->outs[a] = tot;
+    {
+      std::lock_guard<std::mutex> lk(p->m);
+      if (--p->remaining == 0) p->cv_done.notify_one();
+    }
+  }
+}
+extern "C" rwf_pool* rwf_pool_new(rwf_join** actors, int P, int pin) {
+  rwf_pool* p = new rwf_pool();
+  p->P = P;
+  p->actors = actors;
+  p->outs.assign(P, 0);
+  for (int a = 0; a < P; a++) p->th.emplace_back(rwf_pool_worker, p, a, pin);
+  return p;
+}
+extern "C" int64_t rwf_pool_push(rwf_pool* p, int side, const int64_t* n, const uint8_t* const* ops, const int64_t* const* c0,
+                                 const int64_t* const* c1, const int64_t* const* c2, const int64_t* const* c3, int chunk) {
+  {
+    std::lock_guard<std::mutex> lk(p->m);
+    p->side = side; p->n = n; p->ops = ops; p->chunk = chunk;
+    p->c[0] = c0; p->c[1] = c1; p->c[2] = c2; p->c[3] = c3;
+    p->remaining = p->P;
+    p->gen++;
+  }
+  p->cv_start.notify_all();
+  std::unique_lock<std::mutex> lk(p->m);
+  p->cv_done.wait(lk, [&] { return p->remaining == 0; });
+  int64_t tot = 0;
+  for (int a = 0; a < p->P; a++) tot += p->outs[a];
+  return tot;
+}
+extern "C" void rwf_pool_free(rwf_pool* p) {
+  {
+    std::lock_guard<std::mutex> lk(p->m);
+    p->stop = true;
+  }
+  p->cv_start.notify_all();
+  for (auto& t : p->th) t.join();
+  delete p;
+}
