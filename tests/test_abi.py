@@ -41,6 +41,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(abi.RwAggDesc) == 72
     assert ctypes.sizeof(abi.RwJoinSideDesc) == 64
     assert ctypes.sizeof(abi.RwJoinDesc) == 192
+    assert ctypes.sizeof(abi.RwFilterTerm) == 24
 
 
 def test_product_does_not_reference_oracle():
