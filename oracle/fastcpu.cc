@@ -92,7 +92,11 @@ struct OutBuilder {  // StreamChunkBuilder with 8 int64 columns, cut at 1024 row
     const int64_t* r = u_left ? m : u;
     for (int k = 0; k < 4; k++) col[k].push_back(l[k]);
     for (int k = 0; k < 4; k++) col[4 + k].push_back(r[k]);
-    checksum += (uint64_t)(l[1] * 31 + r[1]) * (op == 1 ? 1 : (uint64_t)-1);
+    // order-independent checksum of the emitted (op, row) multiset: every column enters with its own odd weight
+    static const uint64_t W[8] = {3, 31, 5, 7, 11, 1, 17, 19};
+    uint64_t v = 0;
+    for (int k = 0; k < 4; k++) v += W[k] * (uint64_t)l[k] + W[4 + k] * (uint64_t)r[k];
+    checksum += v * (op == 1 ? 1 : (uint64_t)-1);
     total++;
     if (ops.size() == 1024) take();
   }
@@ -265,34 +269,19 @@ extern "C" void rwf_agg_reserve(rwf_agg* h, uint64_t n) {
   if (cap > h->slots.size()) h->resize(cap);
 }
 
-// P actors in parallel, one OS thread each (the reference runs one tokio task per actor on a worker
-// pool, actor.rs:209-232): actor a consumes its n[a] rows in `chunk`-row StreamChunks.
 #include <thread>
-extern "C" int64_t rwf_join_push_parallel(rwf_join** actors, int P, int side, const int64_t* n, const uint8_t* const* ops,
-                                          const int64_t* const* c0, const int64_t* const* c1, const int64_t* const* c2,
-                                          const int64_t* const* c3, int chunk) {
-  std::vector<std::thread> th;
-  std::vector<int64_t> outs(P, 0);
-  for (int a = 0; a < P; a++) {
-    th.emplace_back([&, a]() {
-      int64_t tot = 0;
-      for (int64_t i = 0; i < n[a]; i += chunk) {
-        int64_t m = n[a] - i < chunk ? n[a] - i : chunk;
-        tot += rwf_join_push(actors[a], side, m, ops[a] + i, c0[a] + i, c1[a] + i, c2[a] + i, c3[a] + i);
-      }
-      outs[a] = tot;
-    });
-  }
-  int64_t tot = 0;
-  for (int a = 0; a < P; a++) { th[a].join(); tot += outs[a]; }
-  return tot;
-}
-
-
-// Persistent worker pool: one long-lived OS thread per actor (the reference's actors are long-lived tasks on
-// a worker pool, actor.rs:209-232), woken once per batch.  Spawning P threads for every batch -- the first
-// version of this driver -- cost more than the work of a batch on a 128-thread host.  Worker a is pinned to
-// CPU a % ncpu when `pin` is set, so an actor's state stays on the socket that first touched it.
+// Actor pool: P long-lived OS threads, one actor each (the reference runs one long-lived task per actor on a
+// worker pool, actor.rs:209-232,272).  What round 1 got wrong and this version fixes:
+//   * worker a is pinned to cpu_ids[a], a list the caller takes from sched_getaffinity (one entry per
+//     PHYSICAL core), not to `a % nprocs` -- CPU ids of an allowed set need not be 0..P-1; the return code of
+//     the pin is kept and reported;
+//   * every actor and its tables are created and first-touched ON ITS OWN THREAD (NUMA first touch);
+//   * actors do not meet at a condition variable after every 2^20-row step: each consumes ITS stream of
+//     batches independently, exactly as the reference's actors do between barriers; one spin barrier after the
+//     warm-up batches opens the timed region, wall time = last finish - first start, per-actor busy time is
+//     reported so the caller can state the parallel efficiency.
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <pthread.h>
@@ -300,29 +289,39 @@ extern "C" int64_t rwf_join_push_parallel(rwf_join** actors, int P, int side, co
 #include <unistd.h>
 struct rwf_pool {
   int P = 0;
-  rwf_join** actors = nullptr;
+  std::vector<rwf_join*> actors;
   std::vector<std::thread> th;
+  std::vector<int> cpu, pin_rc;
   std::mutex m;
   std::condition_variable cv_start, cv_done;
   uint64_t gen = 0;
   int remaining = 0;
   bool stop = false;
   // task of the current generation
-  int side = 0, chunk = 1024;
-  const int64_t* n = nullptr;
-  const uint8_t* const* ops = nullptr;
+  int kind = 0;  // 0 = reserve, 1 = run
+  const uint64_t* reserve[2] = {nullptr, nullptr};
+  int side = 0, chunk = 1024, nb = 0, warm = 0;
+  const int64_t* n = nullptr;                 // [nb][P]
+  const uint8_t* const* ops = nullptr;        // [nb][P]
   const int64_t* const* c[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::atomic<int> at_barrier{0};
   std::vector<int64_t> outs;
+  std::vector<double> t0, t1;
 };
-static void rwf_pool_worker(rwf_pool* p, int a, int pin) {
-  if (pin) {
-    long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+static inline double rwf_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static void rwf_pool_worker(rwf_pool* p, int a) {
+  if (p->cpu[a] >= 0) {
     cpu_set_t set;
     CPU_ZERO(&set);
-    CPU_SET((int)(a % (ncpu > 0 ? ncpu : 1)), &set);
-    pthread_setaffinity_np(pthread_self(), sizeof(set), &set);  // best effort
+    CPU_SET(p->cpu[a], &set);
+    p->pin_rc[a] = pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
   }
+  p->actors[a] = new rwf_join();  // first touch on this thread
   uint64_t seen = 0;
+  {
+    std::lock_guard<std::mutex> lk(p->m);
+    if (--p->remaining == 0) p->cv_done.notify_one();
+  }
   while (true) {
     {
       std::unique_lock<std::mutex> lk(p->m);
@@ -330,42 +329,100 @@ static void rwf_pool_worker(rwf_pool* p, int a, int pin) {
       if (p->stop) return;
       seen = p->gen;
     }
-    int64_t tot = 0;
-    const int64_t na = p->n[a];
-    for (int64_t i = 0; i < na; i += p->chunk) {
-      const int64_t m = na - i < p->chunk ? na - i : p->chunk;
-      tot += rwf_join_push(p->actors[a], p->side, m, p->ops[a] + i, p->c[0][a] + i, p->c[1][a] + i, p->c[2][a] + i, p->c[3][a] + i);
+    if (p->kind == 0) {
+      for (int s = 0; s < 2; s++)
+        if (p->reserve[s]) rwf_join_reserve(p->actors[a], s, p->reserve[s][a]);
+    } else {
+      int64_t tot = 0;
+      auto run_batch = [&](int b) {
+        const int64_t na = p->n[(size_t)b * p->P + a];
+        const size_t k = (size_t)b * p->P + a;
+        for (int64_t i = 0; i < na; i += p->chunk) {
+          const int64_t m = na - i < p->chunk ? na - i : p->chunk;
+          tot += rwf_join_push(p->actors[a], p->side, m, p->ops[k] + i, p->c[0][k] + i, p->c[1][k] + i, p->c[2][k] + i, p->c[3][k] + i);
+        }
+      };
+      for (int b = 0; b < p->warm; b++) run_batch(b);
+      p->at_barrier.fetch_add(1);
+      while (p->at_barrier.load(std::memory_order_acquire) < p->P) sched_yield();
+      p->t0[a] = rwf_now();
+      tot = 0;
+      for (int b = p->warm; b < p->nb; b++) run_batch(b);
+      p->t1[a] = rwf_now();
+      p->outs[a] = tot;
     }
-    p->outs[a] = tot;
     {
       std::lock_guard<std::mutex> lk(p->m);
       if (--p->remaining == 0) p->cv_done.notify_one();
     }
   }
 }
-extern "C" rwf_pool* rwf_pool_new(rwf_join** actors, int P, int pin) {
-  rwf_pool* p = new rwf_pool();
-  p->P = P;
-  p->actors = actors;
-  p->outs.assign(P, 0);
-  for (int a = 0; a < P; a++) p->th.emplace_back(rwf_pool_worker, p, a, pin);
-  return p;
-}
-extern "C" int64_t rwf_pool_push(rwf_pool* p, int side, const int64_t* n, const uint8_t* const* ops, const int64_t* const* c0,
-                                 const int64_t* const* c1, const int64_t* const* c2, const int64_t* const* c3, int chunk) {
+static void rwf_pool_dispatch(rwf_pool* p) {
   {
     std::lock_guard<std::mutex> lk(p->m);
-    p->side = side; p->n = n; p->ops = ops; p->chunk = chunk;
-    p->c[0] = c0; p->c[1] = c1; p->c[2] = c2; p->c[3] = c3;
     p->remaining = p->P;
     p->gen++;
   }
   p->cv_start.notify_all();
   std::unique_lock<std::mutex> lk(p->m);
   p->cv_done.wait(lk, [&] { return p->remaining == 0; });
+}
+// cpu_ids: P CPU ids (-1 = do not pin) or NULL (no pinning)
+extern "C" rwf_pool* rwf_pool_new(int P, const int* cpu_ids) {
+  rwf_pool* p = new rwf_pool();
+  p->P = P;
+  p->actors.assign(P, nullptr);
+  p->cpu.assign(P, -1);
+  p->pin_rc.assign(P, 0);
+  if (cpu_ids) p->cpu.assign(cpu_ids, cpu_ids + P);
+  p->outs.assign(P, 0);
+  p->t0.assign(P, 0);
+  p->t1.assign(P, 0);
+  p->remaining = P;
+  for (int a = 0; a < P; a++) p->th.emplace_back(rwf_pool_worker, p, a);
+  std::unique_lock<std::mutex> lk(p->m);
+  p->cv_done.wait(lk, [&] { return p->remaining == 0; });
+  return p;
+}
+extern "C" int rwf_pool_pin_failures(rwf_pool* p) {
+  int f = 0;
+  for (int a = 0; a < p->P; a++) f += p->cpu[a] >= 0 && p->pin_rc[a] != 0;
+  return f;
+}
+extern "C" rwf_join* rwf_pool_actor(rwf_pool* p, int a) { return p->actors[a]; }
+// table sizing per actor, done by the actor's own thread (keys_left / keys_right: P entries each, may be NULL)
+extern "C" void rwf_pool_reserve(rwf_pool* p, const uint64_t* keys_left, const uint64_t* keys_right) {
+  p->kind = 0;
+  p->reserve[0] = keys_left;
+  p->reserve[1] = keys_right;
+  rwf_pool_dispatch(p);
+}
+// every actor consumes its `nb` batches of side `side` (n / ops / c0..c3 indexed [batch * P + actor]) in `chunk`-row
+// StreamChunks; the first `warm` batches are untimed.  *wall_s = last finish - first start of the timed part,
+// busy_s[P] = per-actor time in the timed part.  Returns the rows emitted in the timed part.
+extern "C" int64_t rwf_pool_run(rwf_pool* p, int side, int nb, int warm, const int64_t* n, const uint8_t* const* ops,
+                                const int64_t* const* c0, const int64_t* const* c1, const int64_t* const* c2,
+                                const int64_t* const* c3, int chunk, double* wall_s, double* busy_s) {
+  p->kind = 1;
+  p->side = side; p->nb = nb; p->warm = warm; p->n = n; p->ops = ops; p->chunk = chunk;
+  p->c[0] = c0; p->c[1] = c1; p->c[2] = c2; p->c[3] = c3;
+  p->at_barrier.store(0);
+  rwf_pool_dispatch(p);
+  double first = p->t0[0], last = p->t1[0];
   int64_t tot = 0;
-  for (int a = 0; a < p->P; a++) tot += p->outs[a];
+  for (int a = 0; a < p->P; a++) {
+    first = p->t0[a] < first ? p->t0[a] : first;
+    last = p->t1[a] > last ? p->t1[a] : last;
+    if (busy_s) busy_s[a] = p->t1[a] - p->t0[a];
+    tot += p->outs[a];
+  }
+  if (wall_s) *wall_s = last - first;
   return tot;
+}
+extern "C" uint64_t rwf_pool_checksum(rwf_pool* p) {
+  uint64_t s = 0;
+  for (auto* a : p->actors) s += a->out.checksum;
+  return s;
 }
 extern "C" void rwf_pool_free(rwf_pool* p) {
   {
@@ -374,5 +431,6 @@ extern "C" void rwf_pool_free(rwf_pool* p) {
   }
   p->cv_start.notify_all();
   for (auto& t : p->th) t.join();
+  for (auto* a : p->actors) if (a) rwf_join_free(a);
   delete p;
 }

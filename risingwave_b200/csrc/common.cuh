@@ -88,6 +88,11 @@ struct GrowBuf {
   GrowBuf(const GrowBuf&) = delete;
   GrowBuf& operator=(const GrowBuf&) = delete;
   ~GrowBuf() { release(); }
+  void swap(GrowBuf& o) {
+    std::swap(base, o.base); std::swap(reserved, o.reserved); std::swap(mapped, o.mapped); std::swap(gran, o.gran);
+    std::swap(dev, o.dev); chunks.swap(o.chunks); std::swap(use_vmm, o.use_vmm); std::swap(decided, o.decided);
+    DevBuf t = std::move(plain); plain = std::move(o.plain); o.plain = std::move(t);
+  }
   void* p() const { return use_vmm ? (void*)base : plain.p; }
   size_t bytes() const { return use_vmm ? mapped : plain.bytes; }
   template <class T> T* as() const { return (T*)p(); }

@@ -114,6 +114,8 @@ struct JoinStatus {
   unsigned int err;
   unsigned int pad;
   unsigned long long n_in;       // rows of the input chunk as the kernel saw them (device-resident row count)
+  unsigned long long log_next[2];  // unified table: log ids handed out per side (copied from the device counters)
+  unsigned long long n_dead[2];    // unified table: dead log records per side
 };
 
 struct JoinOutDev {
@@ -1427,6 +1429,8 @@ static inline size_t align_up_j(size_t x, size_t a) { return (x + a - 1) / a * a
 
 }  // namespace rw
 
+#include "join_uni.cuh"
+
 // =============================================================================== host handle
 using namespace rw;
 
@@ -1456,6 +1460,13 @@ struct rwgpu_join {
   bool w8_ok[2] = {false, false};  // per update side: Key64 + all-8-byte columns specialisation usable
   bool q4_ok = false;              // both sides: 3..4 columns, 64-byte buckets -> quad-cooperative kernel
   W8Plan w8[2];
+  // unified table (join_uni.cuh): Key64 inner join, <= 4 eight-byte columns per side -- ONE bucket array for both sides
+  bool uni = false;
+  int uni_is = 1;                  // inline side
+  DevBuf uni_buckets, uni_counters;  // counters: log_next[2], n_dead[2], scratch
+  uint64_t uni_cap = 0, uni_keys = 0;
+  uint64_t uni_dead[2] = {0, 0};
+  uint64_t compactions = 0;
   uint64_t launches = 0;
   uint64_t seq = 0;
   unsigned long long status_tag = 0;
@@ -1653,6 +1664,183 @@ static int join_check_err(rwgpu_join* h, const JoinStatus& s, cudaStream_t st) {
   return fail(RW_ERR_CUDA, "internal: join output capacity");
 }
 
+// =============================================================================== unified-table path (join_uni.cuh)
+static UniDev uni_dev(rwgpu_join* h) {
+  UniDev t;
+  t.buckets = h->uni_buckets.as<uint8_t>();
+  t.cap = h->uni_cap;
+  unsigned long long* ctr = h->uni_counters.as<unsigned long long>();
+  for (int s = 0; s < 2; s++) {
+    t.log[s] = h->side[s].recs.as<uint8_t>();
+    t.log_cap[s] = h->side[s].row_cap;
+    t.pools[s] = h->side[s].pools.as<uint2>();
+    t.log_next[s] = ctr + s;
+    t.n_dead[s] = ctr + 2 + s;
+  }
+  t.is = h->uni_is;
+  return t;
+}
+
+static int uni_alloc_buckets(rwgpu_join* h, DevBuf& buf, uint64_t cap) {
+  RW_CUDA(buf.reserve((cap + 2) * 64));
+  uni_init_kernel<<<jgrid((int64_t)cap + 2, 256), 256, 0, h->stream>>>(buf.as<uint8_t>(), 0, cap + 2);
+  RW_CUDA(cudaGetLastError());
+  h->launches++;
+  return RW_OK;
+}
+
+// keep the load of the bucket array <= 0.5 (every extra probe is one more random 64-byte transaction)
+static int uni_grow_table(rwgpu_join* h, uint64_t need_keys) {
+  if (need_keys * 2 <= h->uni_cap) return RW_OK;
+  uint64_t ncap = h->uni_cap;
+  while (ncap < need_keys * 4) ncap <<= 1;
+  RW_CUDA(cudaDeviceSynchronize());  // every push in flight on any stream has finished with the old array
+  DevBuf nb;
+  int rc = uni_alloc_buckets(h, nb, ncap);
+  if (rc != RW_OK) return rc;
+  uni_rehash_kernel<<<jgrid((int64_t)h->uni_cap + 2, 256), 256, 0, h->stream>>>(h->uni_buckets.as<uint8_t>(), h->uni_cap, nb.as<uint8_t>(), ncap);
+  RW_CUDA(cudaGetLastError());
+  h->launches++;
+  RW_CUDA(cudaStreamSynchronize(h->stream));
+  h->uni_buckets = std::move(nb);
+  h->uni_cap = ncap;
+  return RW_OK;
+}
+
+// barrier-time compaction of side s's log: live records only, in chain order (join_uni.cuh uni_compact_kernel)
+static int uni_compact(rwgpu_join* h, int s) {
+  JoinSideHost& sd = h->side[s];
+  RW_CUDA(cudaDeviceSynchronize());
+  GrowBuf fresh;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const size_t va_limit = std::min<size_t>((size_t)0x7ffffff0ull * 48, std::max<size_t>(total_b, (size_t)1 << 30));
+  cudaError_t e = fresh.ensure((size_t)sd.row_cap * 48, 0, va_limit, h->stream);
+  if (e != cudaSuccess) { cudaGetLastError(); return RW_OK; }  // no room for a second log right now: keep the old one
+  unsigned long long* ctr = h->uni_counters.as<unsigned long long>();
+  RW_CUDA(cudaMemsetAsync(ctr + 4, 0, 8, h->stream));
+  uni_compact_kernel<<<jgrid((int64_t)h->uni_cap + 2, 256), 256, 0, h->stream>>>(uni_dev(h), s, fresh.as<uint8_t>(), ctr + 4);
+  RW_CUDA(cudaGetLastError());
+  h->launches++;
+  unsigned long long live = 0;
+  RW_CUDA(cudaMemcpyAsync(&live, ctr + 4, 8, cudaMemcpyDeviceToHost, h->stream));
+  RW_CUDA(cudaStreamSynchronize(h->stream));
+  sd.recs.swap(fresh);
+  sd.row_cap = std::min<uint64_t>(sd.recs.bytes() / 48, 0x7ffffff0ull);
+  sd.n_rows = live;
+  h->uni_dead[s] = 0;
+  const unsigned long long zero = 0;
+  RW_CUDA(cudaMemcpyAsync(ctr + s, &live, 8, cudaMemcpyHostToDevice, h->stream));
+  RW_CUDA(cudaMemcpyAsync(ctr + 2 + s, &zero, 8, cudaMemcpyHostToDevice, h->stream));
+  RW_CUDA(cudaMemsetAsync(sd.pools.p, 0, sd.pools.bytes, h->stream));  // the warps' id pools pointed into the old log
+  RW_CUDA(cudaStreamSynchronize(h->stream));
+  h->compactions++;
+  return RW_OK;
+}
+
+static int join_push_dev_uni(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream_t st, int64_t out_base, int64_t* out_rows,
+                             unsigned long long* null_mask) {
+  DevChunk ch = ch_in;
+  bool plain_cols = ch.vis_bits == nullptr;
+  for (int c = 0; c < ch.n_cols && plain_cols; c++)
+    plain_cols = !ch.cols[c].valid_bits && !ch.cols[c].valid_bytes && (((uintptr_t)ch.cols[c].data & 7) == 0);
+  bool counted = ch.n_dev != nullptr;
+  if (counted && !plain_cols) {  // only the quad-cooperative kernel reads the row count on the device
+    int64_t nh = 0;
+    RW_CUDA(cudaMemcpyAsync(&nh, ch.n_dev, sizeof(nh), cudaMemcpyDeviceToHost, st));
+    RW_CUDA(cudaStreamSynchronize(st));
+    if (nh < 0 || nh > ch.n) return fail(RW_ERR_INVALID, "device row count out of range");
+    ch.n = nh;
+    ch.n_dev = nullptr;
+    counted = false;
+    if (nh == 0) return RW_OK;
+  }
+  const int64_t n = ch.n;  // capacity when `counted`
+  JoinSideHost& own = h->side[S];
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 63) / 64, Q4_MAX_GRID));
+  uint32_t pool_chunk = 32;
+  while (pool_chunk < 256 && (int64_t)pool_chunk * grid * 8 < 4 * n) pool_chunk <<= 1;
+  // the warps draw log ids from persistent pools in chunks: the id counter can run ahead of the rows stored by one chunk per warp
+  int rc = join_grow_store(h, S, own.n_rows + (uint64_t)n + (uint64_t)grid * 8 * pool_chunk);
+  if (rc != RW_OK) return rc;
+  rc = uni_grow_table(h, h->uni_keys + (uint64_t)n);
+  if (rc != RW_OK) return rc;
+  JoinStatus* ds = h->status.as<JoinStatus>();
+  const JoinPlanDev* pd = h->plan_dev.as<JoinPlanDev>();
+  const uint64_t seq_base = h->seq;
+  h->seq += (uint64_t)n;
+  rc = join_ensure_out(h, out_base + n + std::max<int64_t>(n / 2, 4096), st, out_base);
+  if (rc != RW_OK) return rc;
+  const bool is_row = S == h->uni_is;
+  auto launch = [&](bool probe_only) {
+    const UniDev t = uni_dev(h);
+    if (plain_cols) {
+      if (probe_only) {
+        if (is_row) uni_quad_kernel<true, true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, t, out_dev(h), ds, seq_base, out_base, pool_chunk);
+        else uni_quad_kernel<true, false><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, t, out_dev(h), ds, seq_base, out_base, pool_chunk);
+      } else {
+        if (is_row) uni_quad_kernel<false, true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, t, out_dev(h), ds, seq_base, out_base, pool_chunk);
+        else uni_quad_kernel<false, false><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, t, out_dev(h), ds, seq_base, out_base, pool_chunk);
+      }
+    } else {
+      if (probe_only) uni_slow_kernel<true><<<jgrid(n, 256), 256, 0, st>>>(pd, h->w8[S], S, ch, t, out_dev(h), ds, seq_base, out_base);
+      else uni_slow_kernel<false><<<jgrid(n, 256), 256, 0, st>>>(pd, h->w8[S], S, ch, t, out_dev(h), ds, seq_base, out_base);
+    }
+  };
+  JoinStatus hs;
+  auto read_status = [&](int reset) -> int {  // one-thread kernel: counters -> status block -> pinned host memory
+    uni_status_kernel<<<1, 1, 0, st>>>(uni_dev(h), ds, h->status_host.as<JoinStatus>(), 0ull, reset);
+    RW_CUDA(cudaGetLastError());
+    h->launches++;
+    RW_CUDA(cudaStreamSynchronize(st));
+    memcpy(&hs, h->status_host.as<JoinStatus>(), sizeof(JoinStatus));
+    return RW_OK;
+  };
+  static const bool dbg_probe_only = getenv("RWGPU_DBG_PROBE_ONLY") != nullptr;  // timing experiments only (state is not updated)
+  h->prof.begin(st);
+  launch(dbg_probe_only && S == 0);
+  h->prof.end(st);
+  const unsigned long long tag = ++h->status_tag;
+  uni_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, uni_dev(h), ds, seq_base, h->status_host.as<JoinStatus>(), tag, 3);
+  RW_CUDA(cudaGetLastError());
+  h->launches += 2;
+  RW_CUDA(cudaStreamSynchronize(st));
+  if (*(volatile unsigned long long*)(h->status_host.as<JoinStatus>() + 1) == tag) memcpy(&hs, h->status_host.as<JoinStatus>(), sizeof(JoinStatus));
+  else { rc = read_status(3); if (rc != RW_OK) return rc; }  // the delete kernel had real work: it did not publish
+  unsigned int err = hs.err;
+  const unsigned long long first_null = hs.null_mask;
+  const bool first_match = hs.pad != 0;
+  if (hs.err & JERR_OUT_CAPACITY) {
+    // the extra-match area overflowed: redo the (state-free) probe + emit with room for every reservation
+    const int64_t extras = (int64_t)hs.out_rows;
+    RW_CUDA(cudaMemsetAsync(&ds->err, 0, 4, st));
+    rc = join_ensure_out(h, out_base + n + extras + (int64_t)grid * 8 * U_XCHUNK, st, out_base);
+    if (rc != RW_OK) return rc;
+    launch(true);
+    RW_CUDA(cudaGetLastError());
+    h->launches++;
+    rc = read_status(3);
+    if (rc != RW_OK) return rc;
+    err = (err & ~JERR_OUT_CAPACITY) | hs.err;
+    hs.null_mask |= first_null & ~(1ull << 63);
+    hs.pad = hs.pad || first_match;
+  }
+  for (int s = 0; s < 2; s++) {
+    h->side[s].n_rows = hs.log_next[s];
+    h->uni_dead[s] = hs.n_dead[s];
+  }
+  h->uni_keys = hs.n_keys[0];
+  hs.err = err;
+  rc = join_check_err(h, hs, st);
+  if (rc != RW_OK) return rc;
+  const int64_t n_eff = counted ? (int64_t)hs.n_in : n;
+  *out_rows = (hs.pad != 0 || hs.out_rows) ? n_eff + (int64_t)hs.out_rows : 0;
+  h->call_null_mask |= hs.null_mask;
+  *null_mask = h->call_null_mask;
+  h->valid_dirty |= hs.null_mask & ((1ull << 63) - 1);
+  return RW_OK;
+}
+
 // one push of a device-resident chunk; on return the output sits in the device output buffers.
 // *null_mask: bit k = output column k holds NULLs, bit 63 = some rows are invisible.
 // `out_base` rows of the device output buffers are already occupied by earlier sub-batches of the
@@ -1663,6 +1851,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream
   DevChunk ch = ch_in;
   if (ch.n <= 0) return RW_OK;
   if (ch.n >= (1ll << 31)) return fail(RW_ERR_INVALID, "chunk too large");
+  if (h->uni) return join_push_dev_uni(h, S, ch_in, st, out_base, out_rows, null_mask);
   // Key64 / 8-byte-column specialisations need a chunk without bitmaps (ops == 0 still hides rows)
   bool plain_cols = ch.vis_bits == nullptr;
   for (int c = 0; c < ch.n_cols && plain_cols; c++)
@@ -2008,13 +2197,36 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
   h->q4_ok = h->w8_ok[0] && h->w8_ok[1] && p.bhdr == 16 && p.stride[0] == 48 && p.stride[1] == 48 && p.bstride[0] == 64 &&
              p.bstride[1] == 64 && p.n_cols[0] <= 4 && p.n_cols[1] <= 4;
 
+  // unified table: one bucket array for both sides (join_uni.cuh).  RWGPU_NO_UNI=1 keeps the two-table kernels.
+  h->uni = h->fast_inner && h->w8_ok[0] && h->w8_ok[1] && p.n_cols[0] <= 4 && p.n_cols[1] <= 4 && getenv("RWGPU_NO_UNI") == nullptr;
+  h->uni_is = pk_in_jk[1] ? 1 : (pk_in_jk[0] ? 0 : 1);
+
   RW_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   RW_CUDA(h->plan_dev.reserve(sizeof(JoinPlanDev)));
   RW_CUDA(cudaMemcpyAsync(h->plan_dev.p, &p, sizeof(p), cudaMemcpyHostToDevice, h->stream));
   RW_CUDA(h->status.reserve(sizeof(JoinStatus)));
   RW_CUDA(cudaMemsetAsync(h->status.p, 0, sizeof(JoinStatus), h->stream));
   RW_CUDA(h->status_host.reserve(1024));
-  for (int s = 0; s < 2; s++) {
+  if (h->uni) {
+    const uint64_t hint = std::max(d->left.row_capacity_hint, d->right.row_capacity_hint);
+    uint64_t cap = 1024;
+    while (cap * 4 < hint * 10) cap <<= 1;  // load <= 0.4 at `hint` keys
+    h->uni_cap = cap;
+    rc = uni_alloc_buckets(h, h->uni_buckets, cap);
+    if (rc != RW_OK) return rc;
+    RW_CUDA(h->uni_counters.reserve(8 * sizeof(unsigned long long)));
+    RW_CUDA(cudaMemsetAsync(h->uni_counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
+    for (int s = 0; s < 2; s++) {
+      h->side[s].stride = 48;
+      // chained side: every row lives in its log; inline side: only the 2nd, 3rd ... row of a key
+      const uint64_t rows = s == h->uni_is ? std::max<uint64_t>(4096, sd[s]->row_capacity_hint / 4) : std::max<uint64_t>(4096, 2 * sd[s]->row_capacity_hint);
+      rc = join_grow_store(h, s, std::min<uint64_t>(rows, 0x40000000ull));
+      if (rc != RW_OK) return rc;
+      RW_CUDA(h->side[s].pools.reserve((size_t)Q4_MAX_GRID * (JF_BLOCK / 32) * sizeof(uint2)));
+      RW_CUDA(cudaMemsetAsync(h->side[s].pools.p, 0, h->side[s].pools.bytes, h->stream));
+    }
+  }
+  for (int s = 0; s < 2 && !h->uni; s++) {
     uint64_t hint = sd[s]->row_capacity_hint;
     uint64_t cap = 1024;
     while (cap * 4 < hint * 10) cap <<= 1;  // load <= 0.4 at `hint` keys (every extra probe is a 64 B HBM access)
@@ -2267,6 +2479,14 @@ int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t /*epoch*/) {
   if (!h) return fail(RW_ERR_INVALID, "null");
   // state lives in HBM (StateStore stubbed to memory, north_star): a barrier is an ordering point
   RW_CUDA(cudaStreamSynchronize(h->stream));
+  // ... and the point where deleted rows are reclaimed (the reference's delete frees the entry at once,
+  // join/hash_join.rs:659-681): a log that is more than half dead is rebuilt from its live records
+  if (h->uni)
+    for (int s = 0; s < 2; s++)
+      if (h->uni_dead[s] >= 4096 && h->uni_dead[s] * 2 >= h->side[s].n_rows) {
+        int rc = uni_compact(h, s);
+        if (rc != RW_OK) return rc;
+      }
   return RW_OK;
 }
 

@@ -77,6 +77,33 @@ class DeviceView:
             cudart().cudaMemcpy(C.c_void_p(out.data_ptr()), C.c_void_p(self.ops_ptr), C.c_size_t(self.n_rows), 3)
         return out
 
+    def visible(self) -> Optional[torch.Tensor]:
+        """bool[n_rows] from the packed visibility words, or None when every row is visible."""
+        if not self.vis_ptr or not self.n_rows:
+            return None
+        nw = (self.n_rows + 63) // 64
+        words = torch.empty(nw, dtype=torch.int64, device="cuda")
+        cudart().cudaMemcpy(C.c_void_p(words.data_ptr()), C.c_void_p(self.vis_ptr), C.c_size_t(nw * 8), 3)
+        bits = (words.unsqueeze(1) >> torch.arange(64, device="cuda", dtype=torch.int64).unsqueeze(0)) & 1
+        return bits.reshape(-1)[:self.n_rows].to(torch.bool)
+
+    def checksum(self, weights: Sequence[int]) -> tuple:
+        """-> (visible rows, order-independent checksum mod 2^64 of the (op, row) multiset): sum over visible rows of
+        sign(op) * sum_k weights[k] * col_k, sign = +1 for Insert / UpdateInsert, -1 for Delete / UpdateDelete (the
+        same function the CPU baseline of bench.py accumulates; verification only, never inside a timed region)."""
+        if not self.n_rows:
+            return 0, 0
+        acc = torch.zeros(self.n_rows, dtype=torch.int64, device="cuda")
+        for k, w in enumerate(weights):
+            acc += self.column(k).to(torch.int64) * int(w)
+        ops = self.ops()
+        sign = torch.where((ops == abi.OP_INSERT) | (ops == abi.OP_UPDATE_INSERT), 1, -1).to(torch.int64)
+        acc *= sign
+        vis = self.visible()
+        if vis is not None:
+            acc = acc[vis]
+        return int(acc.numel()), int(acc.sum().item()) & ((1 << 64) - 1)
+
 
 _cudart = None
 

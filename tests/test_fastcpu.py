@@ -50,7 +50,7 @@ def test_join_matches_oracle(oracle):
         for o in outs:
             for op, row in o.rows():
                 want_rows += 1
-                v = (row[1] * 31 + row[5]) & M64
+                v = sum(w * c for w, c in zip(bench.CHECKSUM_WEIGHTS, row)) & M64
                 want_sum = (want_sum + (v if op == abi.OP_INSERT else -v)) & M64
     assert got_rows == want_rows and want_rows > 5000
     assert fc.rwf_join_checksum(h) == want_sum
