@@ -235,6 +235,15 @@ int32_t rwgpu_join_push_device_counted(rwgpu_join* h, int32_t side, const rw_chu
 int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t epoch);
 int32_t rwgpu_join_stats(rwgpu_join* h, uint64_t* left_rows, uint64_t* right_rows,
                          uint64_t* kernel_launches);
+/* State reclamation: a delete marks the stored row dead; rwgpu_join_barrier rebuilds a side's row log from its live
+ * rows once more than half of it is dead (the reference frees the entry at delete time, join/hash_join.rs:659-681).
+ * -> number of such rebuilds so far (diagnostics).  State-lifetime limit: a side holds < 2^31 - 16 log rows between
+ * two rebuilds (RW_ERR_OOM beyond).                                                                      */
+uint64_t rwgpu_join_compactions(rwgpu_join* h);
+/* TEST HOOK: set the operator's arrival counter (rows pushed so far, both sides).  Stored rows carry their 64-bit
+ * arrival number; the own-side delete rule compares them.  Tests move the counter next to 2^31 / 2^32 to pin
+ * the behaviour across those boundaries without pushing billions of rows.                              */
+int32_t rwgpu_join_debug_set_seq(rwgpu_join* h, uint64_t seq);
 /* same as rwgpu_agg_profile for the join's dominant kernel (probe + emit). */
 int32_t rwgpu_join_profile(rwgpu_join* h, int32_t enable, double* kernel_ms, uint64_t* kernel_launches);
 

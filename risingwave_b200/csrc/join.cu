@@ -676,7 +676,7 @@ __global__ void __launch_bounds__(128) join_serial_kernel(const JoinPlanDev* __r
 template <bool PROBE_ONLY>
 __global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch,
                                                                         JoinSideDev own, JoinSideDev other, JoinOutDev o,
-                                                                        JoinStatus* st, uint32_t store_base, uint32_t seq_base) {
+                                                                        JoinStatus* st, uint32_t store_base, uint64_t seq_base) {
   __shared__ unsigned long long s_cnt[JF_R][JF_BLOCK / 32];
   __shared__ unsigned int s_sto[JF_R][JF_BLOCK / 32];
   __shared__ unsigned long long s_out_base;
@@ -786,7 +786,9 @@ __global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const Joi
         const int64_t b = js_find_or_insert(own, p, kw, nm, &created);
         if (created) new_keys++;
         own_b[k] = b;
-        if (w_claim_inline(bkt_W(own, p, b))) rec_write(p, S, bkt_inline(own, p, b), ch, r, 0u, seq_base + (uint32_t)r, 0);
+        // (inner join: no degrees -- the degree word carries the high half of the 64-bit arrival number)
+        if (w_claim_inline(bkt_W(own, p, b)))
+          rec_write(p, S, bkt_inline(own, p, b), ch, r, 0u, (uint32_t)(seq_base + (uint64_t)r), (uint32_t)((seq_base + (uint64_t)r) >> 32));
         else overflow[k] = true;
       }
       unsigned int sincl[JF_R];
@@ -814,7 +816,7 @@ __global__ void __launch_bounds__(JF_BLOCK, 8) join_inner_fused_kernel(const Joi
         const int64_t r = base + (int64_t)k * JF_BLOCK + threadIdx.x;
         const uint32_t row = store_base + s_store_base + s_sto[k][wid] + sincl[k] - 1;
         const uint32_t old = w_push_overflow(bkt_W(own, p, own_b[k]), row);
-        rec_write(p, S, rec_ptr(own, row), ch, r, old, seq_base + (uint32_t)r, 0);
+        rec_write(p, S, rec_ptr(own, row), ch, r, old, (uint32_t)(seq_base + (uint64_t)r), (uint32_t)((seq_base + (uint64_t)r) >> 32));
       }
     }
     __syncthreads();
@@ -874,7 +876,7 @@ __device__ __forceinline__ void for_each_overflow_live(const JoinSideDev& s, uin
 template <bool PROBE_ONLY>
 __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch,
                                                                       JoinSideDev own, JoinSideDev other, JoinOutDev o, JoinStatus* st,
-                                                                      uint32_t store_base, uint32_t seq_base, int64_t out_base) {
+                                                                      uint32_t store_base, uint64_t seq_base, int64_t out_base) {
   const int lane = lane_id();
   const uint64_t omask = other.cap - 1, wmask = own.cap - 1;
   unsigned int new_keys = 0, n_del = 0;
@@ -1014,7 +1016,7 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) join_inner_w8p_kernel(const JoinP
         rec = rec_ptr(own, row);
       }
       uint4 hh;
-      hh.x = link; hh.y = 0u; hh.z = seq_base + (uint32_t)r; hh.w = 0u;
+      hh.x = link; hh.y = 0u; hh.z = (uint32_t)(seq_base + (uint64_t)r); hh.w = (uint32_t)((seq_base + (uint64_t)r) >> 32);
       *(uint4*)rec = hh;
 #pragma unroll
       for (int c = 0; c < W8_MAXC / 2; c++)
@@ -1083,7 +1085,7 @@ __device__ __forceinline__ uint64_t shfl64m(unsigned mask, uint64_t v, int src) 
 template <bool PROBE_ONLY, int MINB>
 __global__ void __launch_bounds__(JF_BLOCK, MINB) join_inner_q4_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch,
                                                                      JoinSideDev own, JoinSideDev other, JoinOutDev o, JoinStatus* st,
-                                                                     uint32_t store_base, uint32_t seq_base, int64_t out_base, uint32_t pool_chunk) {
+                                                                     uint32_t store_base, uint64_t seq_base, int64_t out_base, uint32_t pool_chunk) {
   // (kept in a register: writing ch.n would force a local-memory copy of the whole parameter struct)
   const int64_t n_rows = chunk_rows(ch, st, blockIdx.x == 0 && threadIdx.x == 0);
   const int lane = lane_id(), q = lane & 3, qlead = lane & ~3;
@@ -1302,7 +1304,7 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) join_inner_q4_kernel(const Joi
         ulonglong2 v;
         if (q == 1) {  // RecHdr {link, nullmask = 0, seq, degree = 0}
           v.x = (unsigned long long)link;
-          v.y = (unsigned long long)(seq_base + (uint32_t)r);
+          v.y = (unsigned long long)(seq_base + (uint64_t)r);  // {seq, degree} = the 64-bit arrival number
         } else {       // lane 2: columns 0,1   lane 3: columns 2,3
           v.x = va;
           v.y = vb;
@@ -1329,7 +1331,7 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) join_inner_q4_kernel(const Joi
 
 // own-side deletes of the fast path (after the fused kernel; exits at once when the batch has none).
 // Sequential rule: the delete at chunk position r removes the live record with equal pk that
-// arrived most recently BEFORE r (largest seq below seq_base + r, wrap-aware).
+// arrived most recently BEFORE r (64-bit arrival numbers, see the kernel).
 // status block -> pinned host memory (UVA), tagged so the host can tell a fresh copy from a stale one;
 // then the per-push counters are zeroed for the next push (reset bit 0: n_store / n_del / null_mask,
 // bit 1: out_rows / pad of the positional kernels).
@@ -1343,7 +1345,7 @@ __device__ __forceinline__ void join_status_publish(JoinStatus* st, JoinStatus* 
 }
 
 __global__ void __launch_bounds__(256) join_inner_delete_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch,
-                                                                 JoinSideDev own, JoinStatus* st, uint32_t seq_base,
+                                                                 JoinSideDev own, JoinStatus* st, uint64_t seq_base,
                                                                  JoinStatus* status_host, unsigned long long tag, int reset) {
   const int64_t n_rows = chunk_rows(ch, st, false);
   if (*(volatile unsigned long long*)&st->n_del == 0ull) {
@@ -1361,15 +1363,19 @@ __global__ void __launch_bounds__(256) join_inner_delete_kernel(const JoinPlanDe
     const int64_t slot = js_find(own, p, kw, nm, &hc);
     bool found = false;
     if (slot >= 0) {
-      const uint32_t my_seq = seq_base + (uint32_t)r;
       while (!found) {
+        // 64-bit arrival numbers ({seq, degree} of the record header; the inner join keeps no degrees): rows this
+        // very chunk inserted at positions >= r are excluded, every other live pk-equal row arrived before r; the
+        // newest wins.  (A 32-bit wrap-aware age, the first version, lost deletes after 2^31 rows.)
         uint8_t* best = nullptr;
-        uint32_t best_age = 0xffffffffu;
+        uint64_t best_seq = 0;
         for_each_live(own, p, slot, [&](uint8_t* mrec) -> bool {
-          const uint32_t age = my_seq - ((const RecHdr*)mrec)->seq;  // in (0, 2^31) for records that arrived before r
-          if (age != 0 && age < 0x80000000u && age < best_age && pk_equal(p, S, mrec, ch, r)) {
+          const RecHdr* mh = (const RecHdr*)mrec;
+          const uint64_t sq = (uint64_t)mh->seq | ((uint64_t)mh->degree << 32);
+          const bool later = sq >= seq_base + (uint64_t)r && sq < seq_base + (uint64_t)n_rows;
+          if (!later && (!best || sq > best_seq) && pk_equal(p, S, mrec, ch, r)) {
             best = mrec;
-            best_age = age;
+            best_seq = sq;
           }
           return true;
         });
@@ -1893,7 +1899,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream
   JoinStatus* ds = h->status.as<JoinStatus>();
   const JoinPlanDev* pd = h->plan_dev.as<JoinPlanDev>();
   // n_store / n_del are zero here: every status read-back resets them (join_status_publish)
-  const uint32_t seq_base = (uint32_t)h->seq;
+  const uint64_t seq_base = h->seq;
   h->seq += (uint64_t)n;
   JoinStatus hs;
   if (h->fast_inner) {
@@ -2034,7 +2040,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream
     if (reserved > 0) RW_CUDA(cudaMemsetAsync(h->out_vis.as<uint8_t>() + out_base, 1, (size_t)reserved, st));
     h->prof.begin(st);
     join_serial_kernel<<<jgrid(n, 128), 128, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), sc, db.Current(), out_dev(h), ds,
-                                                        (uint32_t)own.n_rows, seq_base, out_base);
+                                                        (uint32_t)own.n_rows, (uint32_t)seq_base, out_base);
     h->prof.end(st);
     RW_CUDA(cudaGetLastError());
     h->launches++;
@@ -2487,6 +2493,14 @@ int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t /*epoch*/) {
         int rc = uni_compact(h, s);
         if (rc != RW_OK) return rc;
       }
+  return RW_OK;
+}
+
+uint64_t rwgpu_join_compactions(rwgpu_join* h) { return h ? h->compactions : 0; }
+
+int32_t rwgpu_join_debug_set_seq(rwgpu_join* h, uint64_t seq) {
+  if (!h) return fail(RW_ERR_INVALID, "null");
+  h->seq = seq;
   return RW_OK;
 }
 

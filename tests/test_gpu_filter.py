@@ -9,7 +9,7 @@ from risingwave_b200 import abi
 from risingwave_b200.executor import AggCall, FilterExecutor, HashAggExecutor, HashJoinExecutor, JoinParams, MockSource, parse_filter_expr
 from risingwave_b200.stream_chunk import Column, StreamChunk, net_multiset
 
-from helpers import load_golden, run_nexmark_q4
+from helpers import load_golden, run_nexmark_q4, run_nexmark_q7, run_nexmark_q8
 from test_oracle_golden import run_filter_kat
 
 pytestmark = pytest.mark.gpu
@@ -140,3 +140,15 @@ def test_nexmark_q4_end_to_end_fixture(cuda):
     """the reference's SQL-level q4 fixture (expected rows of e2e_test/streaming/nexmark/q4.slt.part) through the
     CUDA operators: join -> filter -> agg(max, two group keys) -> agg(count, sum with retractions) -> avg"""
     run_nexmark_q4(cuda)
+
+
+def test_nexmark_q7_end_to_end_fixture(cuda):
+    """the reference's SQL-level q7 fixture (expected rows of e2e_test/streaming/nexmark/q7.slt.part) through the CUDA
+    operators: a join whose right side is an aggregate that retracts and re-emits its maxima, then the filter"""
+    run_nexmark_q7(cuda)
+
+
+def test_nexmark_q8_end_to_end_fixture(cuda):
+    """the reference's SQL-level q8 fixture (e2e_test/streaming/nexmark/q8.slt.part) through the CUDA operators:
+    two group-by aggregates feeding a join on a three-column key"""
+    run_nexmark_q8(cuda)
