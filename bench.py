@@ -681,10 +681,15 @@ def run_ours(args):
             device.profile(agg, "agg", True)
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record(stream)
+            # launch / collect split: barrier e is only ENQUEUED after its epoch's rows; its delta is collected while the
+            # GPU already works on epoch e + 1 (two output sets), so the host never sits between two launches
             delta_rows = 0
             for e in range(n_ep_w, n_ep_w + n_ep):
                 device.agg_push_device(agg, ep_dev[e], stream)
-                delta_rows += device.agg_flush_device(agg, e + 1, stream).n_rows
+                device.agg_flush_device_async(agg, e + 1, stream)
+                if e > n_ep_w:
+                    delta_rows += device.agg_flush_collect(agg, stream).n_rows
+            delta_rows += device.agg_flush_collect(agg, stream).n_rows
             a1.record(stream)
             torch.cuda.synchronize()
             ams = a0.elapsed_time(a1)

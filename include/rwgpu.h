@@ -145,6 +145,14 @@ int32_t rwgpu_agg_flush(rwgpu_agg* h, uint64_t epoch, rwgpu_out** out);
 /* barrier with the delta left in HBM: `view` receives DEVICE pointers to one un-cut chunk
  * (valid until the next flush on this handle); *n_rows is read back (one 8-byte D2H).       */
 int32_t rwgpu_agg_flush_device(rwgpu_agg* h, uint64_t epoch, rw_chunk* view, void* cuda_stream);
+/* the same barrier split in two, so that a caller never waits for the GPU between a barrier and the next epoch's
+ * pushes: `_async` only ENQUEUES the delta computation (one launch on `cuda_stream`, nothing is waited for);
+ * `_collect` waits for the OLDEST outstanding barrier and returns its delta like rwgpu_agg_flush_device.  At most two
+ * barriers may be outstanding (two output sets); a view stays valid until the second `_async` after its own.  All
+ * work of one handle forms ONE logical stream: a call on another cuda_stream than the previous call's is ordered
+ * behind it on the device (event), whichever streams are used.                                                */
+int32_t rwgpu_agg_flush_device_async(rwgpu_agg* h, uint64_t epoch, void* cuda_stream);
+int32_t rwgpu_agg_flush_collect(rwgpu_agg* h, rw_chunk* view, void* cuda_stream);
 /* number of groups currently held / table capacity (diagnostics, join_cached_entry_count-like) */
 int32_t rwgpu_agg_stats(rwgpu_agg* h, uint64_t* n_groups, uint64_t* capacity, uint64_t* kernel_launches);
 /* device-time accounting of the dominant kernel (the fused group-by + aggregate apply kernel):

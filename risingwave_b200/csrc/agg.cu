@@ -32,6 +32,8 @@ struct AggStatus {
   unsigned long long n_groups;
   unsigned int err;
   unsigned int n_dirty;  // entries of the dirty list
+  unsigned int blocks_done;  // flush kernel: blocks that have finished (the last one publishes the status)
+  unsigned int pad;
 };
 
 struct AggPlanDev {
@@ -244,68 +246,110 @@ __global__ void __launch_bounds__(256) agg_apply_kernel(AggTable t, AggPlanDev p
 // ------------------------------------------------------------------ fast path: 1 x 8-byte key, no NULLs anywhere,
 // calls = {count(*), sum(int8)->int8, max/min(int8)} in any order (BASELINE cfg2 / Nexmark q4 shape).
 // Two rows per thread with 128-bit loads of the key / argument columns.
+// One atomic per BLOCK and loop round reserves the dirty-list entries of the block's first-touched groups, one per
+// block at the end counts the new groups: an atomicAdd per warp on those two shared counters (the first version)
+// serialised in one L2 slice -- ~8 K same-address atomics per 2^18-row epoch at one per ~7 cycles were the
+// kernel's whole duration.
 template <int NCALLS>
 __global__ void __launch_bounds__(256) agg_apply_fast_kernel(AggTable t, AggPlanDev p, DevChunk ch) {
+  __shared__ unsigned int s_warp[8];
+  __shared__ unsigned int s_base;
   unsigned int created_local = 0;
+  const int lane = lane_id(), wid = threadIdx.x >> 5;
   const int64_t npair = (ch.n + 1) >> 1;
   const longlong2* keyv = (const longlong2*)ch.cols[p.key_col[0]].data;
   const unsigned short* opv = (const unsigned short*)ch.ops;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npair; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r0 = i * 2;
-    const bool two = (r0 + 1 < ch.n);
-    long long k[2];
-    uint8_t op[2];
-    long long a[NCALLS][2];
-    if (two) {
-      longlong2 kv = __ldg(keyv + i);
-      k[0] = kv.x; k[1] = kv.y;
-      unsigned short o2 = __ldg(opv + i);
-      op[0] = (uint8_t)(o2 & 0xff); op[1] = (uint8_t)(o2 >> 8);
+  for (int64_t base = blockIdx.x * (int64_t)blockDim.x; base < npair; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    uint64_t slot[2] = {0, 0};
+    bool first[2] = {false, false};
+    if (i < npair) {
+      const int64_t r0 = i * 2;
+      const bool two = (r0 + 1 < ch.n);
+      long long k[2];
+      uint8_t op[2];
+      long long a[NCALLS][2];
+      if (two) {
+        longlong2 kv = __ldg(keyv + i);
+        k[0] = kv.x; k[1] = kv.y;
+        unsigned short o2 = __ldg(opv + i);
+        op[0] = (uint8_t)(o2 & 0xff); op[1] = (uint8_t)(o2 >> 8);
 #pragma unroll
-      for (int c = 0; c < NCALLS; c++) {
-        if (p.arg_col[c] >= 0) {
-          longlong2 av = __ldg((const longlong2*)ch.cols[p.arg_col[c]].data + i);
-          a[c][0] = av.x; a[c][1] = av.y;
+        for (int c = 0; c < NCALLS; c++) {
+          if (p.arg_col[c] >= 0) {
+            longlong2 av = __ldg((const longlong2*)ch.cols[p.arg_col[c]].data + i);
+            a[c][0] = av.x; a[c][1] = av.y;
+          }
+        }
+      } else {
+        k[0] = ((const long long*)ch.cols[p.key_col[0]].data)[r0]; k[1] = 0;
+        op[0] = ch.ops[r0]; op[1] = 0;
+#pragma unroll
+        for (int c = 0; c < NCALLS; c++)
+          if (p.arg_col[c] >= 0) { a[c][0] = ((const long long*)ch.cols[p.arg_col[c]].data)[r0]; a[c][1] = 0; }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        if (op[j] == 0) continue;
+        bool created = false;
+        const uint64_t sl = ((uint64_t)k[j] == AGG_EMPTY) ? t.cap + 1 : find_or_insert_single(t, p.HW, (uint64_t)k[j], &created);
+        if (created) created_local++;
+        slot[j] = sl;
+        {  // first touch of the group in this epoch ?
+          const uint32_t bit = 1u << (sl & 31);
+          uint32_t* dw = t.dirty + (sl >> 5);
+          if (!(__ldcg(dw) & bit)) first[j] = !(atomicOr(dw, bit) & bit);
+        }
+        unsigned long long* sp = (unsigned long long*)(t.hot + sl * p.HW + 1);
+        const bool retract = (op[j] == RW_OP_DELETE || op[j] == RW_OP_UPDATE_DELETE);
+#pragma unroll
+        for (int c = 0; c < NCALLS; c++) {
+          const int kind = p.kind[c];
+          if (kind == RW_AGG_COUNT) {
+            atomicAdd(sp + c, retract ? ~0ull : 1ull);
+          } else if (kind == RW_AGG_SUM || kind == RW_AGG_SUM0) {
+            long long x = a[c][j];
+            unsigned long long add = retract ? (0ull - (unsigned long long)x) : (unsigned long long)x;
+            bool neg = retract ? (x > 0) : (x < 0);
+            unsigned long long old = atomicAdd(sp + c, add);
+            unsigned long long nw = old + add;
+            long long hd = (neg ? -1ll : 0ll) + ((nw < old) ? 1ll : 0ll);
+            if (hd != 0) atomicAdd((unsigned long long*)(t.cold + sl * p.CW + p.hi_off[c]), (unsigned long long)hd);
+          } else {
+            if (op[j] != RW_OP_INSERT) { atomicOr(&t.status->err, AGG_ERR_RETRACT_APPEND_ONLY); continue; }
+            if (kind == RW_AGG_MIN) atomicMin((long long*)(sp + c), a[c][j]); else atomicMax((long long*)(sp + c), a[c][j]);
+          }
         }
       }
-    } else {
-      k[0] = ((const long long*)ch.cols[p.key_col[0]].data)[r0]; k[1] = 0;
-      op[0] = ch.ops[r0]; op[1] = 0;
-#pragma unroll
-      for (int c = 0; c < NCALLS; c++)
-        if (p.arg_col[c] >= 0) { a[c][0] = ((const long long*)ch.cols[p.arg_col[c]].data)[r0]; a[c][1] = 0; }
     }
-#pragma unroll
-    for (int j = 0; j < 2; j++) {
-      if (op[j] == 0) continue;
-      bool created = false;
-      uint64_t slot = ((uint64_t)k[j] == AGG_EMPTY) ? t.cap + 1 : find_or_insert_single(t, p.HW, (uint64_t)k[j], &created);
-      if (created) created_local++;
-      mark_dirty(t, slot);
-      unsigned long long* sp = (unsigned long long*)(t.hot + slot * p.HW + 1);
-      const bool retract = (op[j] == RW_OP_DELETE || op[j] == RW_OP_UPDATE_DELETE);
-#pragma unroll
-      for (int c = 0; c < NCALLS; c++) {
-        const int kind = p.kind[c];
-        if (kind == RW_AGG_COUNT) {
-          atomicAdd(sp + c, retract ? ~0ull : 1ull);
-        } else if (kind == RW_AGG_SUM || kind == RW_AGG_SUM0) {
-          long long x = a[c][j];
-          unsigned long long add = retract ? (0ull - (unsigned long long)x) : (unsigned long long)x;
-          bool neg = retract ? (x > 0) : (x < 0);
-          unsigned long long old = atomicAdd(sp + c, add);
-          unsigned long long nw = old + add;
-          long long hd = (neg ? -1ll : 0ll) + ((nw < old) ? 1ll : 0ll);
-          if (hd != 0) atomicAdd((unsigned long long*)(t.cold + slot * p.CW + p.hi_off[c]), (unsigned long long)hd);
-        } else {
-          if (op[j] != RW_OP_INSERT) { atomicOr(&t.status->err, AGG_ERR_RETRACT_APPEND_ONLY); continue; }
-          if (kind == RW_AGG_MIN) atomicMin((long long*)(sp + c), a[c][j]); else atomicMax((long long*)(sp + c), a[c][j]);
-        }
-      }
+    // dirty-list entries of the block's first touches: warp scan -> block scan -> ONE atomicAdd
+    const unsigned int mine = (first[0] ? 1u : 0u) + (first[1] ? 1u : 0u);
+    unsigned int incl = mine;
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
     }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int run = 0;
+      for (int w = 0; w < 8; w++) { const unsigned int v = s_warp[w]; s_warp[w] = run; run += v; }
+      s_base = run ? atomicAdd(&t.status->n_dirty, run) : 0u;
+    }
+    __syncthreads();
+    unsigned int at = s_base + s_warp[wid] + incl - mine;
+    if (first[0]) t.dirty_list[at++] = (uint32_t)slot[0];
+    if (first[1]) t.dirty_list[at] = (uint32_t)slot[1];
+    __syncthreads();  // s_warp / s_base are rewritten by the next round
   }
   for (int o = 16; o > 0; o >>= 1) created_local += __shfl_xor_sync(0xffffffffu, created_local, o);
-  if (lane_id() == 0 && created_local) atomicAdd(&t.status->n_groups, (unsigned long long)created_local);
+  if (lane == 0) s_warp[wid] = created_local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int tot = 0;
+    for (int w = 0; w < 8; w++) tot += s_warp[w];
+    if (tot) atomicAdd(&t.status->n_groups, (unsigned long long)tot);
+  }
 }
 
 // ------------------------------------------------------------------ mark "state non-NULL" for all dirty groups
@@ -374,14 +418,50 @@ __device__ __forceinline__ void write_out_val(const AggOutDev& o, const AggPlanD
   }
 }
 
-// one thread per dirty group (the dirty LIST keeps every lane busy however sparse the epoch's
-// touched set is); the 0 / 1 / 2 output rows of a warp are compacted with a shuffle scan and one
-// atomicAdd, so a U-/U+ pair stays adjacent.
-__global__ void __launch_bounds__(256) agg_flush_kernel(AggTable t, AggPlanDev p, AggOutDev o, uint32_t epoch_flag_mask) {
-  const unsigned int n_dirty = t.status->n_dirty;
-  const int lane = lane_id();
-  const unsigned int n_round = (n_dirty + 31u) & ~31u;
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+// where the last block of the flush kernel publishes the barrier's status (pinned host memory, UVA)
+struct AggPublish {
+  AggStatus* st_host;
+  unsigned int* has_null_host;
+  unsigned long long* tag_host;
+  unsigned long long tag;
+};
+
+__device__ __forceinline__ void agg_publish(AggStatus* st, unsigned int* has_null, const AggPublish& pub, int t) {
+  if (t < RW_MAX_KEYS + RW_MAX_CALLS) { pub.has_null_host[t] = __ldcg(has_null + t); has_null[t] = 0; }
+  if (t == 0) {
+    AggStatus s;
+    s.out_rows = __ldcg(&st->out_rows);
+    s.n_groups = __ldcg(&st->n_groups);
+    s.err = __ldcg(&st->err);
+    s.n_dirty = __ldcg(&st->n_dirty);
+    s.blocks_done = 0;
+    s.pad = 0;
+    *pub.st_host = s;
+    st->out_rows = 0;
+    st->n_dirty = 0;
+    st->blocks_done = 0;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t == 0) {
+    *(volatile unsigned long long*)pub.tag_host = pub.tag;  // written last: the host polls it
+    __threadfence_system();
+  }
+}
+
+// one thread per dirty group (the dirty LIST keeps every lane busy however sparse the epoch's touched set is);
+// the 0 / 1 / 2 output rows of a BLOCK are compacted with a warp-shuffle scan + one shared-memory pass and ONE
+// atomicAdd (an atomic per warp on the shared row counter serialised in one L2 slice), so a U-/U+ pair stays
+// adjacent.  The last block to finish publishes the status block to pinned host memory and re-arms the
+// per-barrier counters: a barrier is one launch.
+__global__ void __launch_bounds__(256) agg_flush_kernel(AggTable t, AggPlanDev p, AggOutDev o, uint32_t epoch_flag_mask, AggPublish pub) {
+  __shared__ int s_warp[8];
+  __shared__ unsigned long long s_base;
+  __shared__ bool s_last;
+  const unsigned int n_dirty = __ldcg(&t.status->n_dirty);
+  const int lane = lane_id(), wid = threadIdx.x >> 5;
+  for (unsigned int base0 = blockIdx.x * blockDim.x; base0 < n_dirty; base0 += gridDim.x * blockDim.x) {
+    const unsigned int i = base0 + threadIdx.x;
     const bool active = i < n_dirty;
     int nrows = 0;
     uint8_t op0 = 0, op1 = 0;
@@ -434,20 +514,24 @@ __global__ void __launch_bounds__(256) agg_flush_kernel(AggTable t, AggPlanDev p
       else if (rc == 0) { nrows = 1; op0 = RW_OP_DELETE; }
       else if (!same) { nrows = 2; op0 = RW_OP_UPDATE_DELETE; op1 = RW_OP_UPDATE_INSERT; store_prev = true; }
     }
-    // warp-scan compaction of the emitted rows
+    // block-wide compaction of the emitted rows
     int incl = nrows;
     for (int d = 1; d < 32; d <<= 1) {
       int v = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += v;
     }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned long long base = 0;
-    if (lane == 0 && total) base = atomicAdd(&t.status->out_rows, (unsigned long long)total);
-    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int run = 0;
+      for (int w = 0; w < 8; w++) { const int v = s_warp[w]; s_warp[w] = run; run += v; }
+      s_base = run ? atomicAdd(&t.status->out_rows, (unsigned long long)run) : 0ull;
+    }
+    __syncthreads();
     if (active) {
       uint64_t* hot = t.hot + slot * p.HW;
       uint64_t* cold = t.cold + slot * p.CW;
-      const int64_t row = (int64_t)base + (incl - nrows);
+      const int64_t row = (int64_t)s_base + s_warp[wid] + (incl - nrows);
       if (nrows && row + nrows > o.capacity) {
         atomicOr(&t.status->err, AGG_ERR_OUT_CAPACITY);
       } else if (nrows) {
@@ -503,20 +587,21 @@ __global__ void __launch_bounds__(256) agg_flush_kernel(AggTable t, AggPlanDev p
       cold[0] = nf;
       t.dirty[slot >> 5] = 0;  // every dirty slot of this word is in the list; racing zero-stores are benign
     }
+    __syncthreads();  // s_warp / s_base are rewritten by the next round
+  }
+  // the last block to get here publishes the barrier's status
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&t.status->blocks_done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    agg_publish(t.status, o.has_null, pub, threadIdx.x);
   }
 }
 
-// status + per-column NULL flags -> pinned host memory (UVA), then reset the per-barrier counters
-__global__ void agg_epilogue_kernel(AggStatus* st, unsigned int* has_null, AggStatus* st_host, unsigned int* has_null_host) {
-  const int t = threadIdx.x;
-  if (t < RW_MAX_KEYS + RW_MAX_CALLS) { has_null_host[t] = has_null[t]; has_null[t] = 0; }
-  if (t == 0) {
-    *st_host = *st;
-    st->out_rows = 0;
-    st->n_dirty = 0;
-  }
-  __threadfence_system();
-}
+// a barrier over an epoch without input rows: only the status publication
+__global__ void agg_epilogue_kernel(AggStatus* st, unsigned int* has_null, AggPublish pub) { agg_publish(st, has_null, pub, threadIdx.x); }
 
 // ------------------------------------------------------------------ rehash (growth) kernel
 __global__ void agg_rehash_kernel(AggTable o, AggTable n, AggPlanDev p) {
@@ -619,11 +704,28 @@ struct rwgpu_agg {
   int64_t stage_cap = 1 << 18;
   size_t off_ops = 0, stage_bytes = 0;
   size_t off_data[RW_MAX_COLS], off_valid[RW_MAX_COLS];
-  // output buffers (device)
-  DevBuf out_ops, out_hasnull, out_col[RW_MAX_KEYS + RW_MAX_CALLS], out_valid[RW_MAX_KEYS + RW_MAX_CALLS],
-      out_bits[RW_MAX_KEYS + RW_MAX_CALLS];
-  int64_t out_cap = 0;
-  PinnedBuf status_host;
+  // output buffers (device): two sets, so the delta of barrier e can still be read while barrier e + 1 is computed
+  struct OutSet {
+    DevBuf ops, col[RW_MAX_KEYS + RW_MAX_CALLS], valid[RW_MAX_KEYS + RW_MAX_CALLS], bits[RW_MAX_KEYS + RW_MAX_CALLS];
+    int64_t cap = 0;
+  } outs[2];
+  int flip = 0;
+  DevBuf out_hasnull;
+  // barriers enqueued but not collected yet (at most two): status slot = output set
+  struct Pending {
+    int set;
+    unsigned long long tag;
+    uint64_t rows_total;
+    cudaStream_t st;
+  } pending[2];
+  int n_pending = 0;
+  unsigned long long tag = 0;
+  uint64_t rows_total = 0;  // rows ever pushed
+  cudaEvent_t pend_ev[2] = {nullptr, nullptr};
+  // one logical stream of work per handle: a call on another stream than the previous one waits for it on the device
+  cudaStream_t last_st = nullptr;
+  cudaEvent_t order_ev = nullptr;
+  PinnedBuf status_host;  // per set: AggStatus @0, has_null flags @64, tag @192 (256 bytes each)
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
   std::vector<rw_column> dev_view_cols;
 
@@ -639,6 +741,8 @@ struct rwgpu_agg {
   }
   ~rwgpu_agg() {
     for (auto& s : stage) if (s.done) cudaEventDestroy(s.done);
+    for (auto e : pend_ev) if (e) cudaEventDestroy(e);
+    if (order_ev) cudaEventDestroy(order_ev);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -669,10 +773,13 @@ static int agg_init_table(rwgpu_agg* h, AggTable t) {
 // make room for `incoming` more rows (each may open a new group); grows + rehashes when needed
 static int agg_ensure_capacity(rwgpu_agg* h, uint64_t incoming) {
   if ((h->groups_upper + incoming) * 2 <= h->cap) return RW_OK;
-  // the bound is pessimistic: read the real group count
-  AggStatus* sh = h->status_host.as<AggStatus>();
-  RW_CUDA(cudaMemcpyAsync(sh, h->status.p, sizeof(AggStatus), cudaMemcpyDeviceToHost, h->stream));
-  RW_CUDA(cudaStreamSynchronize(h->stream));
+  // the bound is pessimistic: read the real group count.  Work of this handle may be in flight on the handle's own
+  // stream AND on a caller's stream (rwgpu_agg_push_device / flush_device): wait for all of it -- reading the
+  // count, or re-hashing the table, under a running apply kernel would lose groups or updates.
+  RW_CUDA(cudaDeviceSynchronize());
+  AggStatus sh_local;
+  AggStatus* sh = &sh_local;
+  RW_CUDA(cudaMemcpy(sh, h->status.p, sizeof(AggStatus), cudaMemcpyDeviceToHost));
   h->groups_upper = sh->n_groups;
   if ((h->groups_upper + incoming) * 2 <= h->cap) return RW_OK;
   uint64_t need = (h->groups_upper + incoming) * 4;
@@ -714,10 +821,23 @@ static bool chunk_fast_ok(const rwgpu_agg* h, const DevChunk& ch) {
 }
 
 // enqueue the apply kernel for a device-resident chunk
+static int agg_order(rwgpu_agg* h, cudaStream_t st) {
+  if (h->last_st && h->last_st != st) {
+    if (!h->order_ev) RW_CUDA(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+    RW_CUDA(cudaEventRecord(h->order_ev, h->last_st));
+    RW_CUDA(cudaStreamWaitEvent(st, h->order_ev, 0));
+  }
+  h->last_st = st;
+  return RW_OK;
+}
+
 static int agg_apply_dev(rwgpu_agg* h, const DevChunk& ch, cudaStream_t st) {
   if (ch.n <= 0) return RW_OK;
   int rc = agg_ensure_capacity(h, (uint64_t)ch.n);
   if (rc != RW_OK) return rc;
+  rc = agg_order(h, st);
+  if (rc != RW_OK) return rc;
+  h->rows_total += (uint64_t)ch.n;
   bool has_nulls = false;
   for (int c : h->used_cols) if (ch.cols[c].valid_bits || ch.cols[c].valid_bytes) has_nulls = true;
   if (has_nulls) {
@@ -756,6 +876,10 @@ static int agg_launch_stage(rwgpu_agg* h) {
   if (s.rows == 0) return RW_OK;
   uint8_t* hp = s.host.as<uint8_t>();
   uint8_t* dp = s.dev.as<uint8_t>();
+  {
+    int rc0 = agg_order(h, h->stream);
+    if (rc0 != RW_OK) return rc0;
+  }
   RW_CUDA(cudaMemcpyAsync(dp + h->off_ops, hp + h->off_ops, (size_t)s.rows, cudaMemcpyHostToDevice, h->stream));
   DevChunk ch;
   memset(&ch, 0, sizeof(ch));
@@ -792,16 +916,18 @@ static int agg_launch_stage(rwgpu_agg* h) {
   return RW_OK;
 }
 
-static int agg_ensure_out(rwgpu_agg* h, int64_t rows) {
-  if (rows <= h->out_cap) return RW_OK;
+static int agg_ensure_out(rwgpu_agg* h, int set, int64_t rows) {
+  rwgpu_agg::OutSet& os = h->outs[set];
+  if (rows <= os.cap) return RW_OK;
   int64_t cap = std::max<int64_t>(rows, 4096);
-  RW_CUDA(h->out_ops.reserve((size_t)cap));
+  RW_CUDA(cudaDeviceSynchronize());  // (growth only) nobody reads the old buffers any more
+  RW_CUDA(os.ops.reserve((size_t)cap));
   for (size_t k = 0; k < h->out_types.size(); k++) {
-    RW_CUDA(h->out_col[k].reserve((size_t)cap * type_width(h->out_types[k])));
-    RW_CUDA(h->out_valid[k].reserve((size_t)cap));
-    RW_CUDA(h->out_bits[k].reserve((size_t)((cap + 63) / 64) * 8));
+    RW_CUDA(os.col[k].reserve((size_t)cap * type_width(h->out_types[k])));
+    RW_CUDA(os.valid[k].reserve((size_t)cap));
+    RW_CUDA(os.bits[k].reserve((size_t)((cap + 63) / 64) * 8));
   }
-  h->out_cap = cap;
+  os.cap = cap;
   return RW_OK;
 }
 
@@ -818,45 +944,107 @@ static int agg_err_code(unsigned int e) {
   return RW_ERR_CUDA;
 }
 
-// run the flush kernel; on return *n_rows rows sit in the device output buffers
-static int agg_flush_dev(rwgpu_agg* h, cudaStream_t st, int64_t* n_rows, unsigned int* has_null_host) {
+// enqueue the barrier's delta computation on `st` (one launch; nothing is waited for): the rows go to output set
+// h->flip, the status to that set's pinned slot.  At most two barriers may be outstanding.
+static int agg_flush_enqueue(rwgpu_agg* h, cudaStream_t st) {
+  if (h->n_pending >= 2) return fail(RW_ERR_INVALID, "two barriers are already outstanding: collect one first");
   int rc = agg_launch_stage(h);
   if (rc != RW_OK) return rc;
-  int64_t bound = (int64_t)std::min<uint64_t>(h->epoch_rows, h->groups_upper + 2) * 2 + 2;
-  rc = agg_ensure_out(h, bound);
+  rc = agg_order(h, st);
   if (rc != RW_OK) return rc;
+  const int set = h->flip;
+  int64_t bound = (int64_t)std::min<uint64_t>(h->epoch_rows, h->groups_upper + 2) * 2 + 2;
+  rc = agg_ensure_out(h, set, bound);
+  if (rc != RW_OK) return rc;
+  rwgpu_agg::OutSet& os = h->outs[set];
   AggStatus* ds = h->status.as<AggStatus>();
   AggOutDev o;
-  o.ops = h->out_ops.as<uint8_t>();
-  for (size_t k = 0; k < h->out_types.size(); k++) { o.col[k] = h->out_col[k].p; o.valid[k] = h->out_valid[k].as<uint8_t>(); }
+  o.ops = os.ops.as<uint8_t>();
+  for (size_t k = 0; k < h->out_types.size(); k++) { o.col[k] = os.col[k].p; o.valid[k] = os.valid[k].as<uint8_t>(); }
   o.has_null = h->out_hasnull.as<unsigned int>();
-  o.capacity = h->out_cap;
+  o.capacity = os.cap;
+  uint8_t* sh = h->status_host.as<uint8_t>() + 256 * set;
+  AggPublish pub;
+  pub.st_host = (AggStatus*)sh;
+  pub.has_null_host = (unsigned int*)(sh + 64);
+  pub.tag_host = (unsigned long long*)(sh + 192);
+  pub.tag = ++h->tag;
   uint32_t mask = h->per_row_mode ? 0u : h->all_flag_mask;
   if (h->epoch_rows > 0) {
     int64_t max_dirty = (int64_t)std::min<uint64_t>(h->epoch_rows, h->cap + 2);
-    agg_flush_kernel<<<grid_for(max_dirty, 256), 256, 0, st>>>(h->table(), h->plan, o, mask);
-    RW_CUDA(cudaGetLastError());
-    h->launches++;
+    agg_flush_kernel<<<grid_for(max_dirty, 256), 256, 0, st>>>(h->table(), h->plan, o, mask, pub);
+  } else {
+    agg_epilogue_kernel<<<1, 32, 0, st>>>(ds, o.has_null, pub);
   }
-  // epilogue: publish status + NULL flags to pinned host memory (no copy-engine round trip) and
-  // re-arm the per-barrier counters
-  uint8_t* sh = h->status_host.as<uint8_t>();
-  agg_epilogue_kernel<<<1, 32, 0, st>>>(ds, o.has_null, (AggStatus*)sh, (unsigned int*)(sh + 64));
   RW_CUDA(cudaGetLastError());
   h->launches++;
-  RW_CUDA(cudaStreamSynchronize(st));
-  AggStatus* s = (AggStatus*)sh;
-  h->groups_upper = s->n_groups;
+  if (!h->pend_ev[set]) RW_CUDA(cudaEventCreateWithFlags(&h->pend_ev[set], cudaEventDisableTiming));
+  RW_CUDA(cudaEventRecord(h->pend_ev[set], st));
+  rwgpu_agg::Pending& pd = h->pending[h->n_pending++];
+  pd.set = set;
+  pd.tag = pub.tag;
+  pd.rows_total = h->rows_total;
+  pd.st = st;
+  h->flip ^= 1;
   h->epoch_rows = 0;
   h->per_row_mode = false;
   h->nullfree_push_seen = false;
+  return RW_OK;
+}
+
+// wait for the OLDEST outstanding barrier; its *n_rows rows sit in output set *set
+static int agg_flush_collect(rwgpu_agg* h, int64_t* n_rows, unsigned int* has_null_host, int* set) {
+  if (h->n_pending == 0) return fail(RW_ERR_INVALID, "no barrier outstanding");
+  const rwgpu_agg::Pending pd = h->pending[0];
+  h->pending[0] = h->pending[1];
+  h->n_pending--;
+  RW_CUDA(cudaEventSynchronize(h->pend_ev[pd.set]));
+  uint8_t* sh = h->status_host.as<uint8_t>() + 256 * pd.set;
+  if (*(volatile unsigned long long*)(sh + 192) != pd.tag) return fail(RW_ERR_CUDA, "internal: barrier status was not published");
+  AggStatus* s = (AggStatus*)sh;
+  h->groups_upper = s->n_groups + (h->rows_total - pd.rows_total);
+  *set = pd.set;
   if (s->err) {
     unsigned int e = s->err;
-    cudaMemsetAsync(&ds->err, 0, sizeof(unsigned int), st);
+    cudaMemsetAsync(&h->status.as<AggStatus>()->err, 0, sizeof(unsigned int), pd.st);
     return fail(agg_err_code(e), agg_err_msg(e));
   }
   *n_rows = (int64_t)s->out_rows;
   memcpy(has_null_host, sh + 64, sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS));
+  return RW_OK;
+}
+
+// synchronous barrier: collect whatever is outstanding first (results discarded would be a caller bug: refuse)
+static int agg_flush_dev(rwgpu_agg* h, cudaStream_t st, int64_t* n_rows, unsigned int* has_null_host, int* set) {
+  if (h->n_pending) return fail(RW_ERR_INVALID, "collect the outstanding asynchronous barriers first");
+  int rc = agg_flush_enqueue(h, st);
+  if (rc != RW_OK) return rc;
+  return agg_flush_collect(h, n_rows, has_null_host, set);
+}
+
+// fill `view` with device pointers into output set `set` (validity bitmaps are packed on `st` when a column has NULLs)
+static int agg_fill_view(rwgpu_agg* h, int set, int64_t n, const unsigned int* has_null, rw_chunk* view, cudaStream_t st) {
+  rwgpu_agg::OutSet& os = h->outs[set];
+  h->dev_view_cols.resize(h->out_types.size());
+  for (size_t k = 0; k < h->out_types.size(); k++) {
+    rw_column& c = h->dev_view_cols[k];
+    c.type = h->out_types[k];
+    c.reserved = 0;
+    c.data = os.col[k].p;
+    c.validity = nullptr;
+    if (has_null[k] && n > 0) {
+      pack_bytes_to_bits_kernel<<<grid_for((n + 63) / 64, 256), 256, 0, st>>>(os.valid[k].as<uint8_t>(), os.bits[k].as<uint64_t>(), n);
+      RW_CUDA(cudaGetLastError());
+      h->launches++;
+      c.validity = os.bits[k].as<uint64_t>();
+    }
+  }
+  view->n_rows = n;
+  view->n_cols = (int32_t)h->out_types.size();
+  view->reserved = 0;
+  view->ops = os.ops.as<uint8_t>();
+  view->visibility = nullptr;
+  view->columns = h->dev_view_cols.data();
   return RW_OK;
 }
 
@@ -961,7 +1149,8 @@ int32_t rwgpu_agg_create(const rw_agg_desc* d, rwgpu_agg** out) {
   RW_CUDA(cudaMemsetAsync(h->status.p, 0, sizeof(AggStatus), h->stream));
   RW_CUDA(h->out_hasnull.reserve(sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS)));
   RW_CUDA(cudaMemsetAsync(h->out_hasnull.p, 0, sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS), h->stream));
-  RW_CUDA(h->status_host.reserve(256));
+  RW_CUDA(h->status_host.reserve(512));
+  memset(h->status_host.p, 0, 512);
   rc = agg_init_table(h, h->table());
   if (rc != RW_OK) return rc;
   // staging layout: [ops | per used column: data, valid bytes], 256-byte aligned regions
@@ -1057,19 +1246,21 @@ int32_t rwgpu_agg_flush(rwgpu_agg* h, uint64_t /*epoch*/, rwgpu_out** out) {
   if (!h || !out) return fail(RW_ERR_INVALID, "null");
   int64_t n = 0;
   unsigned int has_null[RW_MAX_KEYS + RW_MAX_CALLS];
-  int rc = agg_flush_dev(h, h->stream, &n, has_null);
+  int set = 0;
+  int rc = agg_flush_dev(h, h->stream, &n, has_null, &set);
   if (rc != RW_OK) return rc;
+  rwgpu_agg::OutSet& os = h->outs[set];
   auto o = new rwgpu_out();
   o->chunk_size = h->chunk_size;
   unsigned long long nullm = 0;
   for (size_t k = 0; k < h->out_types.size(); k++) if (has_null[k]) nullm |= 1ull << k;
   if (!o->layout(n, h->out_types, nullm, false, h->pool)) { delete o; return fail(RW_ERR_OOM, "pinned output block"); }
   if (n > 0) {
-    cudaMemcpyAsync(o->ops, h->out_ops.p, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(o->ops, os.ops.p, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
     for (size_t k = 0; k < h->out_types.size(); k++) {
       size_t w = type_width(h->out_types[k]);
-      cudaMemcpyAsync(o->data[k], h->out_col[k].p, (size_t)n * w, cudaMemcpyDeviceToHost, h->stream);
-      if (o->valid_bytes[k]) cudaMemcpyAsync(o->valid_bytes[k], h->out_valid[k].p, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+      cudaMemcpyAsync(o->data[k], os.col[k].p, (size_t)n * w, cudaMemcpyDeviceToHost, h->stream);
+      if (o->valid_bytes[k]) cudaMemcpyAsync(o->valid_bytes[k], os.valid[k].p, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
     }
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) { delete o; return fail(RW_ERR_CUDA, cudaGetErrorString(e)); }
@@ -1084,29 +1275,25 @@ int32_t rwgpu_agg_flush_device(rwgpu_agg* h, uint64_t /*epoch*/, rw_chunk* view,
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
   int64_t n = 0;
   unsigned int has_null[RW_MAX_KEYS + RW_MAX_CALLS];
-  int rc = agg_flush_dev(h, st, &n, has_null);
+  int set = 0;
+  int rc = agg_flush_dev(h, st, &n, has_null, &set);
   if (rc != RW_OK) return rc;
-  h->dev_view_cols.resize(h->out_types.size());
-  for (size_t k = 0; k < h->out_types.size(); k++) {
-    rw_column& c = h->dev_view_cols[k];
-    c.type = h->out_types[k];
-    c.reserved = 0;
-    c.data = h->out_col[k].p;
-    c.validity = nullptr;
-    if (has_null[k] && n > 0) {
-      pack_bytes_to_bits_kernel<<<grid_for((n + 63) / 64, 256), 256, 0, st>>>(h->out_valid[k].as<uint8_t>(), h->out_bits[k].as<uint64_t>(), n);
-      RW_CUDA(cudaGetLastError());
-      h->launches++;
-      c.validity = h->out_bits[k].as<uint64_t>();
-    }
-  }
-  view->n_rows = n;
-  view->n_cols = (int32_t)h->out_types.size();
-  view->reserved = 0;
-  view->ops = h->out_ops.as<uint8_t>();
-  view->visibility = nullptr;
-  view->columns = h->dev_view_cols.data();
-  return RW_OK;
+  return agg_fill_view(h, set, n, has_null, view, st);
+}
+
+int32_t rwgpu_agg_flush_device_async(rwgpu_agg* h, uint64_t /*epoch*/, void* cuda_stream) {
+  if (!h) return fail(RW_ERR_INVALID, "null");
+  return agg_flush_enqueue(h, cuda_stream ? (cudaStream_t)cuda_stream : h->stream);
+}
+
+int32_t rwgpu_agg_flush_collect(rwgpu_agg* h, rw_chunk* view, void* cuda_stream) {
+  if (!h || !view) return fail(RW_ERR_INVALID, "null");
+  int64_t n = 0;
+  unsigned int has_null[RW_MAX_KEYS + RW_MAX_CALLS];
+  int set = 0;
+  int rc = agg_flush_collect(h, &n, has_null, &set);
+  if (rc != RW_OK) return rc;
+  return agg_fill_view(h, set, n, has_null, view, cuda_stream ? (cudaStream_t)cuda_stream : h->stream);
 }
 
 int32_t rwgpu_agg_profile(rwgpu_agg* h, int32_t enable, double* ms, uint64_t* launches) {

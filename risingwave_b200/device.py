@@ -126,6 +126,10 @@ def _lib():
         lib.rwgpu_agg_push_device.argtypes = [C.c_void_p, C.POINTER(abi.RwChunk), C.c_void_p]
         lib.rwgpu_agg_flush_device.restype = C.c_int32
         lib.rwgpu_agg_flush_device.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(abi.RwChunk), C.c_void_p]
+        lib.rwgpu_agg_flush_device_async.restype = C.c_int32
+        lib.rwgpu_agg_flush_device_async.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.rwgpu_agg_flush_collect.restype = C.c_int32
+        lib.rwgpu_agg_flush_collect.argtypes = [C.c_void_p, C.POINTER(abi.RwChunk), C.c_void_p]
         lib.rwgpu_join_push_device.restype = C.c_int32
         lib.rwgpu_join_push_device.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.RwChunk), C.POINTER(abi.RwChunk), C.c_void_p]
         for name in ("rwgpu_agg_profile", "rwgpu_join_profile"):
@@ -182,6 +186,18 @@ def agg_push_device(executor, chunk: DeviceChunk, stream: Optional[torch.cuda.St
 def agg_flush_device(executor, epoch: int, stream: Optional[torch.cuda.Stream] = None) -> DeviceView:
     view = abi.RwChunk()
     _check(_lib().rwgpu_agg_flush_device(executor._h, epoch, C.byref(view), _stream_ptr(stream)))
+    return DeviceView(view)
+
+
+def agg_flush_device_async(executor, epoch: int, stream: Optional[torch.cuda.Stream] = None):
+    """enqueue the barrier's delta computation (nothing is waited for); collect it with `agg_flush_collect`"""
+    _check(_lib().rwgpu_agg_flush_device_async(executor._h, epoch, _stream_ptr(stream)))
+
+
+def agg_flush_collect(executor, stream: Optional[torch.cuda.Stream] = None) -> DeviceView:
+    """wait for the oldest outstanding barrier; -> its delta (device pointers)"""
+    view = abi.RwChunk()
+    _check(_lib().rwgpu_agg_flush_collect(executor._h, C.byref(view), _stream_ptr(stream)))
     return DeviceView(view)
 
 

@@ -245,3 +245,87 @@ def test_large_against_numpy(cuda):
     assert np.array_equal(sm[order], usum) and np.array_equal(mx[order], umax)
     # idempotence: a barrier with no input emits nothing
     assert ex.flush_data(2) == []
+
+
+# ------------------------------------------------------------------------------------------ round 2: device-resident API
+def _device_epochs(cuda, n_epochs, rows, keys, seed, hint):
+    """q4-shaped input (count(*), sum, max GROUP BY key) as device chunks + the same rows for the oracle"""
+    import torch
+    from risingwave_b200 import device
+    rng = np.random.default_rng(seed)
+    eps = []
+    for e in range(n_epochs):
+        k = rng.integers(0, keys, rows).astype(np.int64)
+        v = rng.integers(0, 1 << 24, rows).astype(np.int64)
+        host = StreamChunk(np.full(rows, abi.OP_INSERT, np.uint8), [Column(abi.T_INT64, k), Column(abi.T_INT64, v)])
+        dev = device.DeviceChunk(torch.ones(rows, dtype=torch.uint8, device="cuda"), [torch.from_numpy(k).cuda(), torch.from_numpy(v).cuda()],
+                                 [abi.T_INT64] * 2)
+        eps.append((host, dev))
+    return eps
+
+
+def _view_net(view):
+    """net applied change of a device delta: {row: #inserts - #deletes}, zero entries dropped"""
+    from collections import Counter
+    ops = view.ops().cpu().numpy()
+    cols = [view.column(k).cpu().numpy() for k in range(view.n_cols)]
+    c = Counter()
+    for i in range(view.n_rows):
+        row = tuple(int(col[i]) for col in cols)
+        c[row] += 1 if ops[i] in (abi.OP_INSERT, abi.OP_UPDATE_INSERT) else -1
+    return {k: v for k, v in c.items() if v}
+
+
+def test_async_barriers_two_outstanding_match_oracle(cuda, oracle):
+    """rwgpu_agg_flush_device_async / _collect: the delta of barrier e is collected while epoch e + 1 has already been
+    pushed (and its barrier enqueued): two output sets.  Every collected delta equals the oracle's for that epoch."""
+    import torch
+    from risingwave_b200 import device
+    calls = ["(count:int8)", "(sum:int8 $1:int8)", "(max:int8 $1:int8)"]
+    exs = []
+    for be in (cuda, oracle):
+        _, src = MockSource.channel()
+        exs.append(HashAggExecutor(be, src.into_executor([abi.T_INT64] * 2, []), True, [AggCall.from_pretty(c) for c in calls], 0, [0],
+                                   group_capacity_hint=64))  # tiny hint: the table grows while barriers are outstanding
+    eps = _device_epochs(cuda, 7, 5000, 3000, seed=4, hint=64)
+    stream = torch.cuda.Stream()
+    want = []
+    for e, (host, _) in enumerate(eps):
+        exs[1].apply_chunk(host)
+        want.append(net_multiset(exs[1].flush_data(e + 1)))
+    got = []
+    with torch.cuda.stream(stream):
+        for e, (_, dev) in enumerate(eps):
+            device.agg_push_device(exs[0], dev, stream)
+            device.agg_flush_device_async(exs[0], e + 1, stream)
+            if e > 0:
+                got.append(_view_net(device.agg_flush_collect(exs[0], stream)))
+        got.append(_view_net(device.agg_flush_collect(exs[0], stream)))
+        with pytest.raises(abi.RwError):
+            device.agg_flush_collect(exs[0], stream)  # nothing outstanding
+    assert len(got) == len(want)
+    for e, (g, w) in enumerate(zip(got, want)):
+        assert g == dict(w), f"epoch {e}"
+
+
+def test_pushes_on_a_caller_stream_with_growth_inside_an_epoch(cuda, oracle):
+    """several rwgpu_agg_push_device calls on a CALLER's stream inside one epoch, the later ones
+    forcing the table to grow -- growth used to read the group count and re-hash on the handle's own stream,
+    racing with the apply kernels still running on the caller's stream."""
+    import torch
+    from risingwave_b200 import device
+    calls = ["(count:int8)", "(sum:int8 $1:int8)"]
+    exs = []
+    for be in (cuda, oracle):
+        _, src = MockSource.channel()
+        exs.append(HashAggExecutor(be, src.into_executor([abi.T_INT64] * 2, []), True, [AggCall.from_pretty(c) for c in calls], 0, [0],
+                                   group_capacity_hint=16))
+    stream = torch.cuda.Stream()
+    for epoch in range(3):
+        eps = _device_epochs(cuda, 6, 40000, 200000, seed=50 + epoch, hint=16)
+        with torch.cuda.stream(stream):
+            for host, dev in eps:
+                device.agg_push_device(exs[0], dev, stream)  # no sync in between
+                exs[1].apply_chunk(host)
+            g = _view_net(device.agg_flush_device(exs[0], epoch + 1, stream))
+        assert g == dict(net_multiset(exs[1].flush_data(epoch + 1))), f"epoch {epoch}"
