@@ -475,43 +475,64 @@ def run_ours(args):
             lookahead = True
             ex_stream = torch.cuda.Stream() if counted else None
 
-            def step(s):
+            join_done = {}
+            keep = {}
+
+            def launch(s):
+                """LAUNCH half of step s: (N>1) the exchange, then the push -- everything is only enqueued"""
                 nonlocal t_ex, t_join
                 if counted:
-                    # N>1: the exchange of batch s+1 is enqueued (its own stream) before the join of batch s is
-                    # launched; the join waits for its exchange ON THE DEVICE (event) and reads the received row
-                    # count there (rwgpu_join_push_device_counted): the only host synchronisation of a step is the
-                    # join's own status read-back, and the GPU has the next exchange queued while the host works.
+                    # N>1: the exchange of batch s+1 is enqueued (its own stream) before the join of batch s is launched;
+                    # the join waits for its exchange ON THE DEVICE (event) and reads the received row count there
+                    # (n_rows_dev).  Receive buffer b = s & 1 is reused by exchange s+2, which therefore waits (on the
+                    # device) for the join of batch s.
                     ta = time.perf_counter()
-                    if s not in pending:
-                        pending[s] = ex_plan.start(chunks_dev[s], ex_stream)
-                    if lookahead and s + 1 < W + K and s + 1 != W:  # (nothing of the timed region starts before e0)
-                        pending[s + 1] = ex_plan.start(chunks_dev[s + 1], ex_stream)
+                    for t in (s, s + 1):
+                        if t in pending or t >= len(chunks_dev) or (t == s + 1 and (not lookahead or t == W)):
+                            continue  # (nothing of the timed region starts before e0)
+                        if t - 2 in join_done:
+                            ex_stream.wait_event(join_done.pop(t - 2))
+                        pending[t] = ex_plan.start(chunks_dev[t], ex_stream)
                     b = pending.pop(s)
                     stream.wait_event(ex_plan.events[b])
                     tb = time.perf_counter()
-                    out = device.join_push_device(join, abi.SIDE_LEFT, recv_chunks[b], stream, n_rows_dev=ex_plan.count_ptr(b))
+                    device.join_push_device_async(join, abi.SIDE_LEFT, recv_chunks[b], stream, n_rows_dev=ex_plan.count_ptr(b))
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+                    join_done[s] = ev
                     t_ex += tb - ta
                     t_join += time.perf_counter() - tb
-                    return out
-                if not trace:
-                    ch = chunks_dev[s] if world == 1 else device.DeviceChunk(*ex_plan.exchange(chunks_dev[s], stream), T4)
-                    return device.join_push_device(join, abi.SIDE_LEFT, ch, stream)
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
+                    return
                 ch = chunks_dev[s] if world == 1 else device.DeviceChunk(*ex_plan.exchange(chunks_dev[s], stream), T4)
-                torch.cuda.synchronize()
-                t1 = time.perf_counter()
-                out = device.join_push_device(join, abi.SIDE_LEFT, ch, stream)
-                torch.cuda.synchronize()
-                t2 = time.perf_counter()
-                print(f"[rank {rank}] step {s}: exchange {1e3 * (t1 - t0):.3f} ms  push {1e3 * (t2 - t1):.3f} ms  rows in {ch.n_rows()} out {out.n_rows}",
-                      file=sys.stderr, flush=True)
+                keep[s] = ch  # the input buffers stay alive until the push is collected
+                device.join_push_device_async(join, abi.SIDE_LEFT, ch, stream)
+
+            def collect(s):
+                nonlocal t_join
+                tb = time.perf_counter()
+                out = device.join_collect(join, stream)
+                t_join += time.perf_counter() - tb
+                keep.pop(s, None)
                 return out
 
+            def run_steps(lo, hi, each=None):
+                """steps lo..hi-1, push s+1 launched before push s is collected (two output sets)"""
+                tot = 0
+                for s in range(lo, hi):
+                    launch(s)
+                    if s > lo:
+                        o = collect(s - 1)
+                        tot += o.n_rows
+                        if each:
+                            each(o)
+                o = collect(hi - 1)
+                tot += o.n_rows
+                if each:
+                    each(o)
+                return tot
+
             sampler = ClockSampler(local_rank)
-            for s in range(W):
-                step(s)
+            run_steps(0, W)
             device.profile(join, "join", True)
             l0 = device.launches(join, "join")
             if world > 1:
@@ -521,10 +542,8 @@ def run_ours(args):
                 sampler.start()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            out_rows = 0
             t_ex = t_join = 0.0
-            for s in range(W, W + K):
-                out_rows += step(s).n_rows
+            out_rows = run_steps(W, W + K)
             e1.record(stream)
             torch.cuda.synchronize()
             if world > 1:
@@ -551,7 +570,7 @@ def run_ours(args):
                                   "join": "inner bid.auction = auction.id, Key64, 4+4 int64 cols, 8 out cols",
                                   "l2": "inputs_larger_than_l2 (fresh 32 MiB batch per step; >1.3 GB of join state)",
                                   "exchange": None if world == 1 else ex_name},
-                "host_ms_per_step": {"enqueue_exchange": 1e3 * t_ex / K, "join_push_incl_sync": 1e3 * t_join / K} if counted else None,
+                "host_ms_per_step": {"enqueue_exchange": 1e3 * t_ex / K, "join_launch_and_collect": 1e3 * t_join / K},
                 "build_rows_per_s": N_BUILD * world / build_s, "out_rows": out_rows, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "join_inner_q4_kernel<false> (probe + emit + own-side append, 4 lanes per row)",
                              "achieved": fused_gbs, "peak": peak, "unit": "GB/s", "frac": fused_gbs / peak if fused_gbs else None,
@@ -567,10 +586,15 @@ def run_ours(args):
                 vr = vc = 0
                 for v in range(V):
                     chunks_dev.append(dchunk(to_dev(batches_host[K + W + v])))
-                for v in range(V):
-                    rows_v, cs_v = step(K + W + v).checksum(CHECKSUM_WEIGHTS)
+
+                def add_checksum(o):
+                    nonlocal vr, vc
+                    rows_v, cs_v = o.checksum(CHECKSUM_WEIGHTS)
                     vr += rows_v
                     vc = (vc + cs_v) & ((1 << 64) - 1)
+
+                for v in range(V):  # (one at a time: the checksum reads the view before the next push reuses the set)
+                    run_steps(K + W + v, K + W + v + 1, add_checksum)
                 if world > 1:
                     t = torch.tensor([vr, vc & 0xffffffff, vc >> 32], device="cuda", dtype=torch.int64)
                     dist.all_reduce(t)

@@ -240,6 +240,20 @@ int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* chun
  * n_rows_dev == NULL behaves like rwgpu_join_push_device.                                     */
 int32_t rwgpu_join_push_device_counted(rwgpu_join* h, int32_t side, const rw_chunk* chunk,
                                        const int64_t* n_rows_dev, rw_chunk* view, void* cuda_stream);
+/* LAUNCH / COLLECT split of rwgpu_join_push_device_counted, so that the caller never sits between two launches:
+ * `_async` only ENQUEUES the push on `cuda_stream` (n_rows_dev may be NULL) and returns; `rwgpu_join_collect` waits
+ * for the OLDEST outstanding push and returns its output like the synchronous call.  Rules:
+ *  - at most two pushes outstanding (two output sets); a view stays valid until the second `_async` after its own;
+ *  - `chunk`'s DEVICE buffers (and *n_rows_dev) stay valid and unmodified until the push is collected;
+ *  - pushes of DIFFERENT sides are never outstanding together (RW_ERR_INVALID): a side's probe reads the other side's
+ *    state, and the collect step may have to re-run that probe when the output area was too small;
+ *  - errors of the push (RW_ERR_INCONSISTENT ...) are reported by its collect;
+ *  - all work of one handle is ONE logical stream: a call on another cuda_stream than the previous call's is ordered
+ *    behind it on the device.
+ * Plan shapes without an asynchronous kernel path complete inside `_async`; the protocol is the same.           */
+int32_t rwgpu_join_push_device_async(rwgpu_join* h, int32_t side, const rw_chunk* chunk, const int64_t* n_rows_dev,
+                                     void* cuda_stream);
+int32_t rwgpu_join_collect(rwgpu_join* h, rw_chunk* view, void* cuda_stream);
 int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t epoch);
 int32_t rwgpu_join_stats(rwgpu_join* h, uint64_t* left_rows, uint64_t* right_rows,
                          uint64_t* kernel_launches);

@@ -1453,6 +1453,20 @@ struct JoinSideHost {
   uint64_t keys_upper = 0;
 };
 
+// one push between its launch and its collection
+struct JoinPending {
+  int S = 0, set = 0, grid = 0;
+  DevChunk ch;            // the caller keeps the chunk's buffers valid until the push is collected
+  cudaStream_t st = nullptr;
+  int64_t out_base = 0;
+  bool plain = true, counted = false, sync_done = false;
+  uint32_t pool_chunk = 0;
+  uint64_t seq_base = 0, ids_before = 0, keys_before = 0;
+  unsigned long long tag = 0;
+  int64_t rows = 0;               // sync_done: the result of a push that was completed at launch time
+  unsigned long long nullm = 0;
+};
+
 struct rwgpu_join {
   JoinPlanDev plan;
   DevBuf plan_dev, status;
@@ -1473,6 +1487,12 @@ struct rwgpu_join {
   uint64_t uni_cap = 0, uni_keys = 0;
   uint64_t uni_dead[2] = {0, 0};
   uint64_t compactions = 0;
+  // launch / collect split (rwgpu_join_push_device_async / rwgpu_join_collect): pushes enqueued but not collected
+  JoinPending pending[2];
+  int n_pending = 0;
+  cudaEvent_t pend_ev[2] = {nullptr, nullptr};
+  cudaStream_t last_st = nullptr;
+  cudaEvent_t order_ev = nullptr;
   uint64_t launches = 0;
   uint64_t seq = 0;
   unsigned long long status_tag = 0;
@@ -1485,17 +1505,25 @@ struct rwgpu_join {
   uint64_t gcap = 0;
   size_t cub_bytes = 0;
   // output (device)
-  DevBuf out_ops, out_vis, out_col[J_MAX_OUT], out_valid[J_MAX_OUT], out_bits[J_MAX_OUT], out_visbits;
-  int64_t out_cap = 0;
-  unsigned long long valid_dirty = 0;  // columns whose valid bytes hold zeros from the previous push
+  // two output sets: the rows of push s can still be read while push s + 1 is computed (launch / collect split);
+  // the synchronous entry points only ever use the current one
+  struct OutSet {
+    DevBuf out_ops, out_vis, out_col[J_MAX_OUT], out_valid[J_MAX_OUT], out_bits[J_MAX_OUT], out_visbits;
+    int64_t out_cap = 0;
+    unsigned long long valid_dirty = 0;  // columns whose valid bytes hold zeros from the previous push
+  } oset[2];
+  int cur = 0;
+  OutSet& os() { return oset[cur]; }
   // host staging
   DevBuf up;
   PinnedBuf up_host;
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
-  std::vector<rw_column> dev_view_cols;
+  std::vector<rw_column> dev_view_cols[2];  // per output set
   ~rwgpu_join() {
     for (auto e : ev_h2d) if (e) cudaEventDestroy(e);
     for (auto e : ev_main) if (e) cudaEventDestroy(e);
+    for (auto e : pend_ev) if (e) cudaEventDestroy(e);
+    if (order_ev) cudaEventDestroy(order_ev);
     if (s_h2d) cudaStreamDestroy(s_h2d);
     if (s_d2h) cudaStreamDestroy(s_d2h);
     if (stream) cudaStreamDestroy(stream);
@@ -1538,7 +1566,9 @@ static int join_grow_store(rwgpu_join* h, int S, uint64_t rows) {
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   const size_t va_limit = std::min<size_t>((size_t)0x7ffffff0ull * (size_t)s.stride, std::max<size_t>(total_b, (size_t)1 << 30));
-  cudaError_t e = s.recs.ensure((size_t)rows * (size_t)s.stride, (size_t)s.n_rows * (size_t)s.stride, va_limit, h->stream);
+  RW_CUDA(cudaDeviceSynchronize());  // (growth only) pushes may be in flight on a caller's stream
+  const uint64_t live_rows = std::min<uint64_t>(s.n_rows, s.row_cap);  // n_rows is an upper bound while pushes are outstanding
+  cudaError_t e = s.recs.ensure((size_t)rows * (size_t)s.stride, (size_t)live_rows * (size_t)s.stride, va_limit, h->stream);
   if (e != cudaSuccess) return fail(RW_ERR_OOM, std::string("join record store: ") + cudaGetErrorString(e));
   s.row_cap = std::min<uint64_t>(s.recs.bytes() / (size_t)s.stride, 0x7ffffff0ull);
   return RW_OK;
@@ -1588,7 +1618,7 @@ static int join_ensure_scratch(rwgpu_join* h, int64_t n) {
 
 // make room for `rows` output rows; the first `keep` rows already written are preserved
 static int join_ensure_out(rwgpu_join* h, int64_t rows, cudaStream_t st, int64_t keep = 0) {
-  if (rows <= h->out_cap) return RW_OK;
+  if (rows <= h->os().out_cap) return RW_OK;
   int64_t cap = std::max<int64_t>(rows + rows / 4, 4096);
   RW_CUDA(cudaDeviceSynchronize());
   auto grow = [&](DevBuf& b, size_t elt, bool fill_one) -> int {
@@ -1599,38 +1629,38 @@ static int join_ensure_out(rwgpu_join* h, int64_t rows, cudaStream_t st, int64_t
     b = std::move(nb);
     return RW_OK;
   };
-  int rc = grow(h->out_ops, 1, false);
+  int rc = grow(h->os().out_ops, 1, false);
   if (rc != RW_OK) return rc;
-  rc = grow(h->out_vis, 1, false);
+  rc = grow(h->os().out_vis, 1, false);
   if (rc != RW_OK) return rc;
-  RW_CUDA(h->out_visbits.reserve((size_t)((cap + 63) / 64) * 8));
+  RW_CUDA(h->os().out_visbits.reserve((size_t)((cap + 63) / 64) * 8));
   for (size_t k = 0; k < h->out_types.size(); k++) {
-    rc = grow(h->out_col[k], (size_t)type_width(h->out_types[k]), false);
+    rc = grow(h->os().out_col[k], (size_t)type_width(h->out_types[k]), false);
     if (rc != RW_OK) return rc;
-    rc = grow(h->out_valid[k], 1, true);  // invariant: valid bytes are 1 between pushes
+    rc = grow(h->os().out_valid[k], 1, true);  // invariant: valid bytes are 1 between pushes
     if (rc != RW_OK) return rc;
-    RW_CUDA(h->out_bits[k].reserve((size_t)((cap + 63) / 64) * 8));
+    RW_CUDA(h->os().out_bits[k].reserve((size_t)((cap + 63) / 64) * 8));
   }
-  if (keep == 0) h->valid_dirty = 0;
-  h->out_cap = cap;
+  if (keep == 0) h->os().valid_dirty = 0;
+  h->os().out_cap = cap;
   return RW_OK;
 }
 
 // restore the "valid bytes are all 1" invariant for the columns the previous push wrote NULLs to
 static int join_clean_valid(rwgpu_join* h, cudaStream_t st) {
   for (size_t k = 0; k < h->out_types.size(); k++)
-    if ((h->valid_dirty >> k) & 1) RW_CUDA(cudaMemsetAsync(h->out_valid[k].p, 1, (size_t)h->out_cap, st));
-  h->valid_dirty = 0;
+    if ((h->os().valid_dirty >> k) & 1) RW_CUDA(cudaMemsetAsync(h->os().out_valid[k].p, 1, (size_t)h->os().out_cap, st));
+  h->os().valid_dirty = 0;
   return RW_OK;
 }
 
 static JoinOutDev out_dev(rwgpu_join* h) {
   JoinOutDev o;
   memset(&o, 0, sizeof(o));
-  o.ops = h->out_ops.as<uint8_t>();
-  o.vis = h->out_vis.as<uint8_t>();
-  for (size_t k = 0; k < h->out_types.size(); k++) { o.col[k] = h->out_col[k].p; o.valid[k] = h->out_valid[k].as<uint8_t>(); }
-  o.capacity = h->out_cap;
+  o.ops = h->os().out_ops.as<uint8_t>();
+  o.vis = h->os().out_vis.as<uint8_t>();
+  for (size_t k = 0; k < h->out_types.size(); k++) { o.col[k] = h->os().out_col[k].p; o.valid[k] = h->os().out_valid[k].as<uint8_t>(); }
+  o.capacity = h->os().out_cap;
   return o;
 }
 
@@ -1744,8 +1774,41 @@ static int uni_compact(rwgpu_join* h, int s) {
   return RW_OK;
 }
 
-static int join_push_dev_uni(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream_t st, int64_t out_base, int64_t* out_rows,
-                             unsigned long long* null_mask) {
+// all work of one handle forms ONE logical stream: a call on another cuda stream than the previous call's waits
+// for it on the device
+static int join_order(rwgpu_join* h, cudaStream_t st) {
+  if (h->last_st && h->last_st != st) {
+    if (!h->order_ev) RW_CUDA(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
+    RW_CUDA(cudaEventRecord(h->order_ev, h->last_st));
+    RW_CUDA(cudaStreamWaitEvent(st, h->order_ev, 0));
+  }
+  h->last_st = st;
+  return RW_OK;
+}
+
+static void uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_only) {
+  const UniDev t = uni_dev(h);
+  const JoinPlanDev* pdev = h->plan_dev.as<JoinPlanDev>();
+  JoinStatus* ds = h->status.as<JoinStatus>();
+  const int S = pd.S;
+  const bool is_row = S == h->uni_is;
+  if (pd.plain) {
+    if (probe_only) {
+      if (is_row) uni_quad_kernel<true, true><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base, pd.pool_chunk);
+      else uni_quad_kernel<true, false><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base, pd.pool_chunk);
+    } else {
+      if (is_row) uni_quad_kernel<false, true><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base, pd.pool_chunk);
+      else uni_quad_kernel<false, false><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base, pd.pool_chunk);
+    }
+  } else {
+    if (probe_only) uni_slow_kernel<true><<<jgrid(pd.ch.n, 256), 256, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base);
+    else uni_slow_kernel<false><<<jgrid(pd.ch.n, 256), 256, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base);
+  }
+}
+
+// LAUNCH half of a push: main kernel + delete kernel (which publishes the status block into the output set's pinned
+// slot) are enqueued on `st`; nothing is waited for.  The output goes to the CURRENT output set (h->cur).
+static int uni_enqueue(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream_t st, int64_t out_base, JoinPending* pd) {
   DevChunk ch = ch_in;
   bool plain_cols = ch.vis_bits == nullptr;
   for (int c = 0; c < ch.n_cols && plain_cols; c++)
@@ -1759,70 +1822,84 @@ static int join_push_dev_uni(rwgpu_join* h, int S, const DevChunk& ch_in, cudaSt
     ch.n = nh;
     ch.n_dev = nullptr;
     counted = false;
-    if (nh == 0) return RW_OK;
   }
   const int64_t n = ch.n;  // capacity when `counted`
   JoinSideHost& own = h->side[S];
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 63) / 64, Q4_MAX_GRID));
   uint32_t pool_chunk = 32;
   while (pool_chunk < 256 && (int64_t)pool_chunk * grid * 8 < 4 * n) pool_chunk <<= 1;
-  // the warps draw log ids from persistent pools in chunks: the id counter can run ahead of the rows stored by one chunk per warp
-  int rc = join_grow_store(h, S, own.n_rows + (uint64_t)n + (uint64_t)grid * 8 * pool_chunk);
+  // the warps draw log ids from persistent pools in chunks: the id counter can run ahead of the rows stored by one chunk
+  // per warp.  own.n_rows / uni_keys are UPPER bounds while pushes are outstanding (corrected when they are collected).
+  const uint64_t id_slack = (uint64_t)grid * 8 * pool_chunk;
+  int rc = join_grow_store(h, S, own.n_rows + (uint64_t)n + id_slack);
   if (rc != RW_OK) return rc;
   rc = uni_grow_table(h, h->uni_keys + (uint64_t)n);
   if (rc != RW_OK) return rc;
-  JoinStatus* ds = h->status.as<JoinStatus>();
-  const JoinPlanDev* pd = h->plan_dev.as<JoinPlanDev>();
-  const uint64_t seq_base = h->seq;
-  h->seq += (uint64_t)n;
   rc = join_ensure_out(h, out_base + n + std::max<int64_t>(n / 2, 4096), st, out_base);
   if (rc != RW_OK) return rc;
-  const bool is_row = S == h->uni_is;
-  auto launch = [&](bool probe_only) {
-    const UniDev t = uni_dev(h);
-    if (plain_cols) {
-      if (probe_only) {
-        if (is_row) uni_quad_kernel<true, true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, t, out_dev(h), ds, seq_base, out_base, pool_chunk);
-        else uni_quad_kernel<true, false><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, t, out_dev(h), ds, seq_base, out_base, pool_chunk);
-      } else {
-        if (is_row) uni_quad_kernel<false, true><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, t, out_dev(h), ds, seq_base, out_base, pool_chunk);
-        else uni_quad_kernel<false, false><<<grid, JF_BLOCK, 0, st>>>(pd, h->w8[S], S, ch, t, out_dev(h), ds, seq_base, out_base, pool_chunk);
-      }
-    } else {
-      if (probe_only) uni_slow_kernel<true><<<jgrid(n, 256), 256, 0, st>>>(pd, h->w8[S], S, ch, t, out_dev(h), ds, seq_base, out_base);
-      else uni_slow_kernel<false><<<jgrid(n, 256), 256, 0, st>>>(pd, h->w8[S], S, ch, t, out_dev(h), ds, seq_base, out_base);
-    }
-  };
+  rc = join_order(h, st);
+  if (rc != RW_OK) return rc;
+  pd->S = S;
+  pd->ch = ch;
+  pd->st = st;
+  pd->out_base = out_base;
+  pd->set = h->cur;
+  pd->plain = plain_cols;
+  pd->counted = counted;
+  pd->grid = grid;
+  pd->pool_chunk = pool_chunk;
+  pd->seq_base = h->seq;
+  pd->tag = ++h->status_tag;
+  pd->ids_before = own.n_rows;
+  pd->keys_before = h->uni_keys;
+  h->seq += (uint64_t)n;
+  own.n_rows += (uint64_t)n + id_slack;  // upper bounds until the status comes back
+  h->uni_keys += (uint64_t)n;
+  static const bool dbg_probe_only = getenv("RWGPU_DBG_PROBE_ONLY") != nullptr;  // timing experiments only (state is not updated)
+  h->prof.begin(st);
+  uni_launch_main(h, *pd, dbg_probe_only && S == 0);
+  h->prof.end(st);
+  JoinStatus* slot = (JoinStatus*)(h->status_host.as<uint8_t>() + 512 * pd->set);
+  uni_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(h->plan_dev.as<JoinPlanDev>(), S, ch, uni_dev(h), h->status.as<JoinStatus>(), pd->seq_base, slot,
+                                                     pd->tag, 3);
+  RW_CUDA(cudaGetLastError());
+  h->launches += 2;
+  if (!h->pend_ev[pd->set]) RW_CUDA(cudaEventCreateWithFlags(&h->pend_ev[pd->set], cudaEventDisableTiming));
+  RW_CUDA(cudaEventRecord(h->pend_ev[pd->set], st));
+  return RW_OK;
+}
+
+// COLLECT half: wait for the push, read its status, redo the (state-free) emission if the extra-match area was too
+// small, settle the host's bookkeeping.  h->cur must be pd.set.
+static int uni_finish(rwgpu_join* h, const JoinPending& pd, int64_t* out_rows, unsigned long long* null_mask) {
+  cudaStream_t st = pd.st;
+  JoinStatus* ds = h->status.as<JoinStatus>();
+  JoinStatus* slot = (JoinStatus*)(h->status_host.as<uint8_t>() + 512 * pd.set);
   JoinStatus hs;
   auto read_status = [&](int reset) -> int {  // one-thread kernel: counters -> status block -> pinned host memory
-    uni_status_kernel<<<1, 1, 0, st>>>(uni_dev(h), ds, h->status_host.as<JoinStatus>(), 0ull, reset);
+    uni_status_kernel<<<1, 1, 0, st>>>(uni_dev(h), ds, slot, 0ull, reset);
     RW_CUDA(cudaGetLastError());
     h->launches++;
     RW_CUDA(cudaStreamSynchronize(st));
-    memcpy(&hs, h->status_host.as<JoinStatus>(), sizeof(JoinStatus));
+    memcpy(&hs, slot, sizeof(JoinStatus));
     return RW_OK;
   };
-  static const bool dbg_probe_only = getenv("RWGPU_DBG_PROBE_ONLY") != nullptr;  // timing experiments only (state is not updated)
-  h->prof.begin(st);
-  launch(dbg_probe_only && S == 0);
-  h->prof.end(st);
-  const unsigned long long tag = ++h->status_tag;
-  uni_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(pd, S, ch, uni_dev(h), ds, seq_base, h->status_host.as<JoinStatus>(), tag, 3);
-  RW_CUDA(cudaGetLastError());
-  h->launches += 2;
-  RW_CUDA(cudaStreamSynchronize(st));
-  if (*(volatile unsigned long long*)(h->status_host.as<JoinStatus>() + 1) == tag) memcpy(&hs, h->status_host.as<JoinStatus>(), sizeof(JoinStatus));
+  RW_CUDA(cudaEventSynchronize(h->pend_ev[pd.set]));
+  int rc;
+  if (*(volatile unsigned long long*)(slot + 1) == pd.tag) memcpy(&hs, slot, sizeof(JoinStatus));
   else { rc = read_status(3); if (rc != RW_OK) return rc; }  // the delete kernel had real work: it did not publish
   unsigned int err = hs.err;
   const unsigned long long first_null = hs.null_mask;
   const bool first_match = hs.pad != 0;
   if (hs.err & JERR_OUT_CAPACITY) {
-    // the extra-match area overflowed: redo the (state-free) probe + emit with room for every reservation
-    const int64_t extras = (int64_t)hs.out_rows;
+    // the extra-match area overflowed: redo the probe + emit with room for every reservation.  The probe reads the
+    // OTHER side's state only, which no later push of the same side has touched (pushes of different sides are never
+    // outstanding together), so the redo is exact.
+    const int64_t extras = (int64_t)hs.out_rows, n = pd.ch.n;
     RW_CUDA(cudaMemsetAsync(&ds->err, 0, 4, st));
-    rc = join_ensure_out(h, out_base + n + extras + (int64_t)grid * 8 * U_XCHUNK, st, out_base);
+    rc = join_ensure_out(h, pd.out_base + n + extras + (int64_t)pd.grid * 8 * U_XCHUNK, st, pd.out_base);
     if (rc != RW_OK) return rc;
-    launch(true);
+    uni_launch_main(h, pd, true);
     RW_CUDA(cudaGetLastError());
     h->launches++;
     rc = read_status(3);
@@ -1831,20 +1908,32 @@ static int join_push_dev_uni(rwgpu_join* h, int S, const DevChunk& ch_in, cudaSt
     hs.null_mask |= first_null & ~(1ull << 63);
     hs.pad = hs.pad || first_match;
   }
-  for (int s = 0; s < 2; s++) {
-    h->side[s].n_rows = hs.log_next[s];
-    h->uni_dead[s] = hs.n_dead[s];
+  // bookkeeping: what the device really used, plus the upper bounds of the pushes enqueued after this one
+  for (int s = 0; s < 2; s++) h->uni_dead[s] = hs.n_dead[s];
+  {
+    JoinSideHost& own = h->side[pd.S];
+    const uint64_t n = (uint64_t)pd.ch.n, slack = (uint64_t)pd.grid * 8 * pd.pool_chunk;
+    own.n_rows = hs.log_next[pd.S] + (own.n_rows - (pd.ids_before + n + slack));
+    h->uni_keys = hs.n_keys[0] + (h->uni_keys - (pd.keys_before + n));
   }
-  h->uni_keys = hs.n_keys[0];
   hs.err = err;
   rc = join_check_err(h, hs, st);
   if (rc != RW_OK) return rc;
-  const int64_t n_eff = counted ? (int64_t)hs.n_in : n;
+  const int64_t n_eff = pd.counted ? (int64_t)hs.n_in : pd.ch.n;
   *out_rows = (hs.pad != 0 || hs.out_rows) ? n_eff + (int64_t)hs.out_rows : 0;
   h->call_null_mask |= hs.null_mask;
   *null_mask = h->call_null_mask;
-  h->valid_dirty |= hs.null_mask & ((1ull << 63) - 1);
+  h->os().valid_dirty |= hs.null_mask & ((1ull << 63) - 1);
   return RW_OK;
+}
+
+static int join_push_dev_uni(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream_t st, int64_t out_base, int64_t* out_rows,
+                             unsigned long long* null_mask) {
+  if (h->n_pending) return fail(RW_ERR_INVALID, "collect the outstanding asynchronous pushes first");
+  JoinPending pd;
+  int rc = uni_enqueue(h, S, ch_in, st, out_base, &pd);
+  if (rc != RW_OK) return rc;
+  return uni_finish(h, pd, out_rows, null_mask);
 }
 
 // one push of a device-resident chunk; on return the output sits in the device output buffers.
@@ -2037,7 +2126,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream
     const int64_t reserved = (int64_t)hs.out_rows;
     rc = join_ensure_out(h, out_base + reserved, st, out_base);
     if (rc != RW_OK) return rc;
-    if (reserved > 0) RW_CUDA(cudaMemsetAsync(h->out_vis.as<uint8_t>() + out_base, 1, (size_t)reserved, st));
+    if (reserved > 0) RW_CUDA(cudaMemsetAsync(h->os().out_vis.as<uint8_t>() + out_base, 1, (size_t)reserved, st));
     h->prof.begin(st);
     join_serial_kernel<<<jgrid(n, 128), 128, 0, st>>>(pd, S, ch, side_dev(h, S), side_dev(h, 1 - S), sc, db.Current(), out_dev(h), ds,
                                                         (uint32_t)own.n_rows, (uint32_t)seq_base, out_base);
@@ -2054,7 +2143,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream
   }
   h->call_null_mask |= hs.null_mask;  // the device copy restarts from zero after every read-back
   *null_mask = h->call_null_mask;
-  h->valid_dirty |= hs.null_mask & ((1ull << 63) - 1);
+  h->os().valid_dirty |= hs.null_mask & ((1ull << 63) - 1);
   return RW_OK;
 }
 
@@ -2262,11 +2351,42 @@ int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* c, r
   return rwgpu_join_push_device_counted(h, side, c, nullptr, view, cuda_stream);
 }
 
+// device view of the current output set's first n rows (bitmaps are packed on `st` where NULLs / holes exist)
+static int join_fill_view(rwgpu_join* h, int64_t n, unsigned long long nullm, rw_chunk* view, cudaStream_t st) {
+  std::vector<rw_column>& cols = h->dev_view_cols[h->cur];
+  cols.resize(h->out_types.size());
+  for (size_t k = 0; k < h->out_types.size(); k++) {
+    rw_column& col = cols[k];
+    col.type = h->out_types[k];
+    col.reserved = 0;
+    col.data = h->os().out_col[k].p;
+    col.validity = nullptr;
+    if (((nullm >> k) & 1) && n > 0) {
+      pack_bytes_to_bits_kernel<<<jgrid((n + 63) / 64, 256), 256, 0, st>>>(h->os().out_valid[k].as<uint8_t>(), h->os().out_bits[k].as<uint64_t>(), n);
+      RW_CUDA(cudaGetLastError());
+      col.validity = h->os().out_bits[k].as<uint64_t>();
+    }
+  }
+  view->n_rows = n;
+  view->n_cols = (int32_t)h->out_types.size();
+  view->reserved = 0;
+  view->ops = h->os().out_ops.as<uint8_t>();
+  view->visibility = nullptr;
+  if ((nullm >> 63) && n > 0) {
+    pack_bytes_to_bits_kernel<<<jgrid((n + 63) / 64, 256), 256, 0, st>>>(h->os().out_vis.as<uint8_t>(), h->os().out_visbits.as<uint64_t>(), n);
+    RW_CUDA(cudaGetLastError());
+    view->visibility = h->os().out_visbits.as<uint64_t>();
+  }
+  view->columns = cols.data();
+  return RW_OK;
+}
+
 int32_t rwgpu_join_push_device_counted(rwgpu_join* h, int32_t side, const rw_chunk* c, const int64_t* n_rows_dev, rw_chunk* view,
                                        void* cuda_stream) {
   if (!h || !c || !view) return fail(RW_ERR_INVALID, "null");
   if (side != 0 && side != 1) return fail(RW_ERR_INVALID, "side");
   if (c->n_cols != h->side[side].n_cols) return fail(RW_ERR_INVALID, "chunk schema mismatch");
+  if (h->n_pending) return fail(RW_ERR_INVALID, "collect the outstanding asynchronous pushes first");
   DevChunk ch;
   int rc = devchunk_from_abi(c, &ch);
   if (rc != RW_OK) return rc;
@@ -2278,31 +2398,60 @@ int32_t rwgpu_join_push_device_counted(rwgpu_join* h, int32_t side, const rw_chu
   if (rc != RW_OK) return rc;
   rc = join_push_dev(h, side, ch, st, 0, &n, &nullm);
   if (rc != RW_OK) return rc;
-  h->dev_view_cols.resize(h->out_types.size());
-  for (size_t k = 0; k < h->out_types.size(); k++) {
-    rw_column& col = h->dev_view_cols[k];
-    col.type = h->out_types[k];
-    col.reserved = 0;
-    col.data = h->out_col[k].p;
-    col.validity = nullptr;
-    if (((nullm >> k) & 1) && n > 0) {
-      pack_bytes_to_bits_kernel<<<jgrid((n + 63) / 64, 256), 256, 0, st>>>(h->out_valid[k].as<uint8_t>(), h->out_bits[k].as<uint64_t>(), n);
-      RW_CUDA(cudaGetLastError());
-      col.validity = h->out_bits[k].as<uint64_t>();
-    }
+  return join_fill_view(h, n, nullm, view, st);
+}
+
+// LAUNCH half (see rwgpu.h).  Unified-table handles really only enqueue; other plan shapes run the push to
+// completion here and hand the result over at collect time, so callers need not care which kind they hold.
+int32_t rwgpu_join_push_device_async(rwgpu_join* h, int32_t side, const rw_chunk* c, const int64_t* n_rows_dev, void* cuda_stream) {
+  if (!h || !c) return fail(RW_ERR_INVALID, "null");
+  if (side != 0 && side != 1) return fail(RW_ERR_INVALID, "side");
+  if (c->n_cols != h->side[side].n_cols) return fail(RW_ERR_INVALID, "chunk schema mismatch");
+  if (h->n_pending >= 2) return fail(RW_ERR_INVALID, "two pushes are already outstanding: collect one first");
+  if (h->n_pending && h->pending[0].S != side)
+    return fail(RW_ERR_INVALID, "pushes of different sides cannot be outstanding together: collect first");
+  DevChunk ch;
+  int rc = devchunk_from_abi(c, &ch);
+  if (rc != RW_OK) return rc;
+  ch.n_dev = n_rows_dev;
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  h->cur = h->n_pending ? 1 - h->pending[h->n_pending - 1].set : h->cur;
+  rc = join_begin_call(h, st);
+  if (rc != RW_OK) return rc;
+  JoinPending pd;
+  if (h->uni && ch.n > 0 && ch.n < (1ll << 31)) {
+    rc = uni_enqueue(h, side, ch, st, 0, &pd);
+    if (rc != RW_OK) return rc;
+  } else {
+    pd.S = side;
+    pd.set = h->cur;
+    pd.st = st;
+    pd.sync_done = true;
+    rc = join_push_dev(h, side, ch, st, 0, &pd.rows, &pd.nullm);
+    if (rc != RW_OK) return rc;
   }
-  view->n_rows = n;
-  view->n_cols = (int32_t)h->out_types.size();
-  view->reserved = 0;
-  view->ops = h->out_ops.as<uint8_t>();
-  view->visibility = nullptr;
-  if ((nullm >> 63) && n > 0) {
-    pack_bytes_to_bits_kernel<<<jgrid((n + 63) / 64, 256), 256, 0, st>>>(h->out_vis.as<uint8_t>(), h->out_visbits.as<uint64_t>(), n);
-    RW_CUDA(cudaGetLastError());
-    view->visibility = h->out_visbits.as<uint64_t>();
-  }
-  view->columns = h->dev_view_cols.data();
+  h->pending[h->n_pending++] = pd;
   return RW_OK;
+}
+
+int32_t rwgpu_join_collect(rwgpu_join* h, rw_chunk* view, void* cuda_stream) {
+  if (!h || !view) return fail(RW_ERR_INVALID, "null");
+  if (h->n_pending == 0) return fail(RW_ERR_INVALID, "no push outstanding");
+  const JoinPending pd = h->pending[0];
+  h->pending[0] = h->pending[1];
+  h->n_pending--;
+  h->cur = pd.set;
+  int64_t n = pd.rows;
+  unsigned long long nullm = pd.nullm;
+  if (!pd.sync_done) {
+    h->call_null_mask = 0;
+    int rc = uni_finish(h, pd, &n, &nullm);
+    if (rc != RW_OK) return rc;
+  }
+  int rc = join_fill_view(h, n, nullm, view, cuda_stream ? (cudaStream_t)cuda_stream : pd.st);
+  // the next synchronous push must not land in the set a still-outstanding push writes to
+  if (h->n_pending) h->cur = h->pending[h->n_pending - 1].set;
+  return rc;
 }
 
 // HOST chunk.  Large chunks are cut into sub-batches (multiples of 64 rows, so bitmap words split
@@ -2315,6 +2464,7 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
   if (c->n_cols != h->side[side].n_cols) return fail(RW_ERR_INVALID, "chunk schema mismatch");
   for (int k = 0; k < c->n_cols; k++)
     if (c->columns[k].type != h->side[side].types[k]) return fail(RW_ERR_INVALID, "chunk column type mismatch");
+  if (h->n_pending) return fail(RW_ERR_INVALID, "collect the outstanding asynchronous pushes first");
   const int64_t n = c->n_rows;
   static const bool trace = getenv("RWGPU_TRACE") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -2439,11 +2589,11 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
     if (rows > 0) {
       RW_CUDA(cudaEventRecord(h->ev_main[js], h->stream));
       RW_CUDA(cudaStreamWaitEvent(h->s_d2h, h->ev_main[js], 0));
-      cudaMemcpyAsync(o->ops + total, h->out_ops.as<uint8_t>() + total, (size_t)rows, cudaMemcpyDeviceToHost, h->s_d2h);
+      cudaMemcpyAsync(o->ops + total, h->os().out_ops.as<uint8_t>() + total, (size_t)rows, cudaMemcpyDeviceToHost, h->s_d2h);
       for (size_t k = 0; k < h->out_types.size(); k++) {
         if (alias_src[k] >= 0) continue;  // decided after the last sub-batch
         const size_t w = type_width(h->out_types[k]);
-        cudaMemcpyAsync(o->data[k] + (size_t)total * w, h->out_col[k].as<uint8_t>() + (size_t)total * w, (size_t)rows * w,
+        cudaMemcpyAsync(o->data[k] + (size_t)total * w, h->os().out_col[k].as<uint8_t>() + (size_t)total * w, (size_t)rows * w,
                         cudaMemcpyDeviceToHost, h->s_d2h);
       }
     }
@@ -2455,14 +2605,14 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
       o->data[k] = (uint8_t*)const_cast<void*>(c->columns[alias_src[k]].data);  // zero-copy: the caller's input column
     } else if (total > 0) {  // extra matches or an empty sub-batch broke the row alignment: ordinary copy
       // (every sub-batch's kernels have completed: join_push_dev synchronises on its status read-back)
-      cudaMemcpyAsync(o->data[k], h->out_col[k].p, (size_t)total * type_width(h->out_types[k]), cudaMemcpyDeviceToHost, h->s_d2h);
+      cudaMemcpyAsync(o->data[k], h->os().out_col[k].p, (size_t)total * type_width(h->out_types[k]), cudaMemcpyDeviceToHost, h->s_d2h);
     }
   }
   // NULL / visibility bytes only for the columns that need them (known once all sub-batches ran)
   if (total > 0) {
-    if (nullm >> 63) cudaMemcpyAsync(o->vis_bytes, h->out_vis.p, (size_t)total, cudaMemcpyDeviceToHost, h->s_d2h);
+    if (nullm >> 63) cudaMemcpyAsync(o->vis_bytes, h->os().out_vis.p, (size_t)total, cudaMemcpyDeviceToHost, h->s_d2h);
     for (size_t k = 0; k < h->out_types.size(); k++)
-      if ((nullm >> k) & 1) cudaMemcpyAsync(o->valid_bytes[k], h->out_valid[k].p, (size_t)total, cudaMemcpyDeviceToHost, h->s_d2h);
+      if ((nullm >> k) & 1) cudaMemcpyAsync(o->valid_bytes[k], h->os().out_valid[k].p, (size_t)total, cudaMemcpyDeviceToHost, h->s_d2h);
   }
   const double t3 = now();
   RW_CUDA(cudaStreamSynchronize(h->stream));
@@ -2483,8 +2633,10 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
 
 int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t /*epoch*/) {
   if (!h) return fail(RW_ERR_INVALID, "null");
+  if (h->n_pending) return fail(RW_ERR_INVALID, "collect the outstanding asynchronous pushes before the barrier");
   // state lives in HBM (StateStore stubbed to memory, north_star): a barrier is an ordering point
   RW_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->last_st && h->last_st != h->stream) RW_CUDA(cudaStreamSynchronize(h->last_st));
   // ... and the point where deleted rows are reclaimed (the reference's delete frees the entry at once,
   // join/hash_join.rs:659-681): a log that is more than half dead is rebuilt from its live records
   if (h->uni)

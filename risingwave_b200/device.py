@@ -156,6 +156,10 @@ def _lib():
         lib.rwgpu_join_push_device_counted.restype = C.c_int32
         lib.rwgpu_join_push_device_counted.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.RwChunk), C.c_void_p, C.POINTER(abi.RwChunk),
                                                        C.c_void_p]
+        lib.rwgpu_join_push_device_async.restype = C.c_int32
+        lib.rwgpu_join_push_device_async.argtypes = [C.c_void_p, C.c_int32, C.POINTER(abi.RwChunk), C.c_void_p, C.c_void_p]
+        lib.rwgpu_join_collect.restype = C.c_int32
+        lib.rwgpu_join_collect.argtypes = [C.c_void_p, C.POINTER(abi.RwChunk), C.c_void_p]
         lib.rwgpu_shuffle_exchange_p2p_device.restype = C.c_int32
         lib.rwgpu_shuffle_exchange_p2p_device.argtypes = [C.POINTER(abi.RwChunk), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p,
                                                           C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint64,
@@ -212,6 +216,21 @@ def join_push_device(executor, side: int, chunk: DeviceChunk, stream: Optional[t
     else:
         _check(_lib().rwgpu_join_push_device_counted(executor._h, side, C.byref(ch), C.c_void_p(n_rows_dev), C.byref(view),
                                                      _stream_ptr(stream)))
+    return DeviceView(view)
+
+
+def join_push_device_async(executor, side: int, chunk: DeviceChunk, stream: Optional[torch.cuda.Stream] = None,
+                           n_rows_dev: Optional[int] = None):
+    """LAUNCH half of a push (nothing is waited for); the chunk's tensors must stay alive until `join_collect`"""
+    ch, keep = chunk.to_abi()
+    _check(_lib().rwgpu_join_push_device_async(executor._h, side, C.byref(ch), C.c_void_p(n_rows_dev) if n_rows_dev else None,
+                                               _stream_ptr(stream)))
+
+
+def join_collect(executor, stream: Optional[torch.cuda.Stream] = None) -> DeviceView:
+    """COLLECT half: wait for the oldest outstanding push; -> its output (device pointers)"""
+    view = abi.RwChunk()
+    _check(_lib().rwgpu_join_collect(executor._h, C.byref(view), _stream_ptr(stream)))
     return DeviceView(view)
 
 
