@@ -301,9 +301,10 @@ int32_t rwgpu_shuffle_p2p_region_bytes(const int32_t* types, int32_t n_cols, int
 /* sender: stable-partition the visible rows of a DEVICE chunk by destination and store them straight into
  * region `my_rank` of each destination's buffer (`peer_bases`: HOST array of n_dest peer-mapped device
  * pointers), then publish the row counts in the region headers.  `counts`: DEVICE int64[n_dest];
- * `overflow`: DEVICE int32 set to 1 if some (src,dst) pair exceeded cap_rows (rows beyond it are dropped:
- * the caller must fall back to the NCCL path for that batch).  The caller runs a cross-rank barrier on
- * the same stream before anybody unpacks.                                                               */
+ * `overflow`: DEVICE int32 set to 1 if some (src,dst) pair exceeded cap_rows (rows beyond it are dropped and the
+ * receiver's total reads -1): size cap_rows for the worst case -- every row of a source batch going to ONE
+ * destination -- and it cannot happen.  Columns with validity bitmaps => RW_ERR_UNSUPPORTED (the regions carry ops
+ * and column data only).  The caller runs a cross-rank barrier on the same stream before anybody unpacks.   */
 int32_t rwgpu_shuffle_partition_p2p_device(const rw_chunk* chunk, const int32_t* key_indices, int32_t n_keys,
                                            int32_t vnode_count, const int32_t* vnode_to_dest, int32_t n_dest,
                                            int32_t my_rank, void* const* peer_bases, int64_t cap_rows,

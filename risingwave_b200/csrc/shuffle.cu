@@ -546,6 +546,9 @@ int32_t rwgpu_shuffle_partition_device(const rw_chunk* c, const int32_t* keys, i
                                        int64_t* offsets, void* cuda_stream) {
   if (!c || !keys || !vnode_to_dest || !out_ops || !out_cols || !counts || !offsets) return fail(RW_ERR_INVALID, "null");
   if (n_dest < 1 || n_dest > PART_MAX_DEST) return fail(RW_ERR_UNSUPPORTED, "1..64 destinations");
+  for (int k = 0; k < c->n_cols; k++)
+    if (c->columns[k].validity && !(out_valid_bytes && out_valid_bytes[k]))
+      return fail(RW_ERR_UNSUPPORTED, "a column carries a validity bitmap but no out_valid_bytes buffer was given for it");
   VnodePlan p;
   int rc = make_vnode_plan(c, keys, n_keys, vnode_count, &p);
   if (rc != RW_OK) return rc;
@@ -592,6 +595,9 @@ int32_t rwgpu_shuffle_partition_p2p_device(const rw_chunk* c, const int32_t* key
                                            void* cuda_stream) {
   if (!c || !keys || !vnode_to_dest || !peer_bases || !counts || !overflow) return fail(RW_ERR_INVALID, "null");
   if (n_dest < 1 || n_dest > PART_MAX_DEST || my_rank < 0 || my_rank >= n_dest) return fail(RW_ERR_INVALID, "ranks");
+  // the receive regions carry ops + column data only: a validity bitmap would be dropped and NULLs arrive as garbage
+  for (int k = 0; k < c->n_cols; k++)
+    if (c->columns[k].validity) return fail(RW_ERR_UNSUPPORTED, "the peer-memory exchange does not carry validity bitmaps");
   VnodePlan p;
   int rc = make_vnode_plan(c, keys, n_keys, vnode_count, &p);
   if (rc != RW_OK) return rc;

@@ -65,6 +65,8 @@ class ShufflePlan:
     def exchange(self, chunk, stream=None):
         """DeviceChunk -> (ops, cols) holding the rows this rank owns, from all ranks."""
         from . import device
+        if chunk.visibility is not None or any(v is not None for v in chunk.validity):
+            raise ValueError("the exchange does not carry validity / visibility bitmaps (fold visibility into ops; NULLs are unsupported)")
         ops, cols, counts, offsets = device.shuffle_partition(chunk, self.keys, self.v2d, self.world, self.vnode_count, stream)
         ins, outs = plan_splits(counts)
         return all_to_all_columns(ops, cols, ins, outs)
@@ -90,8 +92,13 @@ class P2PShufflePlan:
     can only start writing buffer b again after every rank passed the barrier of the batch in between,
     which each rank enqueues AFTER its own unpack of buffer b (stream order).
 
-    `cap_rows` bounds the rows of one (source, destination) pair per batch; if it overflows (heavy key
-    skew) the batch is redone through the NCCL all-to-all-v path of `ShufflePlan`."""
+    Every (source, destination) region is sized for the WORST case -- all `batch_rows` rows of a source going to one
+    destination (hot keys) -- so a batch can never overflow its region: W x batch_rows x row bytes per receive buffer
+    (8 GPUs, 2^20-row batches of four int64 columns: 277 MB of 180 GB).  The kernels still raise the overflow flag
+    for a caller that hands in more rows than it announced; `finish` then raises.
+
+    Columns with validity bitmaps are not carried by either exchange plan (RW_ERR_UNSUPPORTED-style ValueError):
+    NULLs would arrive as garbage."""
 
     def __init__(self, world: int, rank: int, key_indices: Sequence[int], types: Sequence[int], batch_rows: int,
                  group=None, vnode_count: int = 256):
@@ -100,7 +107,7 @@ class P2PShufflePlan:
         self.world, self.rank = world, rank
         self.keys, self.types, self.vnode_count = list(key_indices), list(types), vnode_count
         self.v2d = vnode_to_dest_table(world, vnode_count).cuda()
-        self.cap = int(batch_rows / world * 1.25) + 8192
+        self.cap = int(batch_rows)  # worst case: no skew can overflow a region
         self.region = device.p2p_region_bytes(self.types, self.cap)
         group = group if group is not None else dist.group.WORLD
         self.bufs, self.hdls, self.peers = [], [], []
@@ -141,6 +148,10 @@ class P2PShufflePlan:
     def start(self, chunk, stream=None):
         """enqueue partition + peer stores + barrier + unpack of one batch on `stream` (one library call, five
         launches); returns a token"""
+        if chunk.n_rows() > self.cap:
+            raise ValueError(f"batch of {chunk.n_rows()} rows exceeds the plan's batch_rows {self.cap}")
+        if chunk.visibility is not None or any(v is not None for v in chunk.validity):
+            raise ValueError("the exchange does not carry validity / visibility bitmaps (fold visibility into ops; NULLs are unsupported)")
         b = self.step & 1
         self.step += 1
         stream = stream if stream is not None else torch.cuda.current_stream()

@@ -378,3 +378,78 @@ def test_unified_log_compaction_at_barrier(cuda, oracle):
     cuda.lib.rwgpu_join_compactions.restype = C.c_uint64
     cuda.lib.rwgpu_join_compactions.argtypes = [C.c_void_p]
     assert cuda.lib.rwgpu_join_compactions(exs[0]._h) >= 1
+
+
+def test_async_pushes_two_outstanding_match_synchronous(cuda):
+    """rwgpu_join_push_device_async / rwgpu_join_collect: push s + 1 is launched before push s is collected (two output
+    sets); every collected output equals the synchronous call's on an identical handle.  A push of the other side while
+    one is outstanding is refused, so is a barrier."""
+    import torch
+    from risingwave_b200 import device
+    rng = np.random.default_rng(5)
+    types = [abi.T_INT64] * 4
+    nb = 40000
+
+    def make():
+        _, sl = MockSource.channel()
+        _, sr = MockSource.channel()
+        ex = HashJoinExecutor(cuda, abi.JOIN_INNER, sl.into_executor(types, [1]), sr.into_executor(types, [0]),
+                              JoinParams([0], [1]), JoinParams([0], []), [False], capacity_hint=1000)  # small hint: growth on the way
+        return ex
+
+    auct = [np.arange(nb, dtype=np.int64)] + [rng.integers(0, 1000, nb).astype(np.int64) for _ in range(3)]
+    bids = []
+    for s in range(6):
+        n = 30000 + 1000 * s
+        cols = [rng.integers(0, nb + 50, n).astype(np.int64), (np.arange(n) + 10 ** 6 * s).astype(np.int64),
+                rng.integers(0, 1 << 30, n).astype(np.int64), rng.integers(0, 1 << 30, n).astype(np.int64)]
+        bids.append(cols)
+
+    def dev(cols, ops=None):
+        n = len(cols[0])
+        o = torch.ones(n, dtype=torch.uint8, device="cuda") if ops is None else torch.from_numpy(ops).cuda()
+        return device.DeviceChunk(o, [torch.from_numpy(c).cuda() for c in cols], types)
+
+    def snapshot(v):
+        vis = v.visible()
+        cols = [v.column(k) for k in range(v.n_cols)]
+        ops = v.ops()
+        if vis is not None:
+            cols, ops = [c[vis] for c in cols], ops[vis]
+        return ops.cpu().numpy(), [c.cpu().numpy() for c in cols]
+
+    a, b = make(), make()
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for ex in (a, b):
+            assert device.join_push_device(ex, abi.SIDE_RIGHT, dev(auct), stream).n_rows == 0
+        want = [snapshot(device.join_push_device(a, abi.SIDE_LEFT, dev(c), stream)) for c in bids]
+        chunks = [dev(c) for c in bids]
+        got = []
+        for s, ch in enumerate(chunks):
+            device.join_push_device_async(b, abi.SIDE_LEFT, ch, stream)
+            if s == 0:
+                with pytest.raises(abi.RwError):  # other side while one is outstanding
+                    device.join_push_device_async(b, abi.SIDE_RIGHT, dev(auct), stream)
+                with pytest.raises(abi.RwError):
+                    b.flush_data(1)
+            if s > 0:
+                got.append(snapshot(device.join_collect(b, stream)))
+        got.append(snapshot(device.join_collect(b, stream)))
+        with pytest.raises(abi.RwError):
+            device.join_collect(b, stream)
+    assert len(got) == len(want)
+    for s, ((go, gc), (wo, wc)) in enumerate(zip(got, want)):
+        assert np.array_equal(go, wo), f"push {s}"
+        for x, y in zip(gc, wc):
+            assert np.array_equal(x, y), f"push {s}"
+    # the same protocol on a plan without an asynchronous kernel path (outer join): completes inside _async
+    types2 = [abi.T_INT64] * 2
+    _, sl = MockSource.channel()
+    _, sr = MockSource.channel()
+    ex = HashJoinExecutor(cuda, abi.JOIN_LEFT_OUTER, sl.into_executor(types2, [1]), sr.into_executor(types2, [1]),
+                          JoinParams([0], [1]), JoinParams([0], [1]), [False])
+    c2 = device.DeviceChunk(torch.ones(3, dtype=torch.uint8, device="cuda"),
+                            [torch.tensor([1, 2, 3], device="cuda"), torch.tensor([7, 8, 9], device="cuda")], types2)
+    device.join_push_device_async(ex, abi.SIDE_LEFT, c2)
+    assert device.join_collect(ex).n_rows == 3
