@@ -76,23 +76,45 @@ def gen_auctions(n, seed, id_base=0):
     return [ids, seller, category, expires]
 
 
-def gen_bids(n, start, seed, n_auction, id_base=0):
-    """bid rows (auction, date_time [unique, the stream key], bidder, price)."""
+def gen_bids(n, start, seed, n_auction, id_base=0, hot=False):
+    """bid rows (auction, date_time [unique, the stream key], bidder, price).  hot: with p = 1/2 a bid goes to one of the
+    last 100 auction ids (SURVEY 8(d) cfg3 "hot" variant, the Nexmark hot-auction shape)."""
     with np.errstate(over="ignore"):
         i = np.arange(start, start + n, dtype=np.uint64)
         auction = (splitmix64(i ^ np.uint64(seed + 10)) % np.uint64(n_auction)).astype(np.int64) + id_base
+        if hot:
+            h = splitmix64(i ^ np.uint64(seed + 13))
+            is_hot = (h & np.uint64(1)) == np.uint64(1)
+            hot_id = (n_auction - 100 + ((h >> np.uint64(8)) % np.uint64(100)).astype(np.int64)) + id_base
+            auction = np.where(is_hot, hot_id, auction)
         date_time = i.astype(np.int64) + 1_600_000_000_000_000
         bidder = (splitmix64(i ^ np.uint64(seed + 11)) % np.uint64(1_000_000)).astype(np.int64)
         price = (splitmix64(i ^ np.uint64(seed + 12)) % np.uint64(1 << 24)).astype(np.int64)
     return [auction, date_time, bidder, price]
 
 
-def gen_agg_rows(n, start, seed):
+def gen_agg_rows(n, start, seed, hot=False):
+    """(auction key, price).  hot = SURVEY 8(d) cfg2 dist B: with p = 1/2 the key is one of 128 hot auctions."""
     with np.errstate(over="ignore"):
         i = np.arange(start, start + n, dtype=np.uint64)
         key = (splitmix64(i ^ np.uint64(seed)) % np.uint64(AGG_KEYS)).astype(np.int64)
+        if hot:
+            h = splitmix64(i ^ np.uint64(seed + 3))
+            key = np.where((h & np.uint64(1)) == np.uint64(1), ((h >> np.uint64(8)) % np.uint64(128)).astype(np.int64), key)
         price = (splitmix64(i ^ np.uint64(seed + 7)) % np.uint64(1 << 24)).astype(np.int64)
     return [key, price]
+
+
+def gen_auction_updates(auct, lo, n_pairs):
+    """U-/U+ pairs for auctions lo .. lo+n_pairs-1 of the arrival order: the stored row retracted, the same id
+    re-inserted with a new `expires` (SURVEY 8(d) cfg3 retraction phase).  -> (ops, cols) of 2 * n_pairs rows."""
+    ops = np.tile(np.array([4, 3], np.uint8), n_pairs)
+    cols = []
+    for k, c in enumerate(auct):
+        old = c[lo:lo + n_pairs]
+        new = old + 1 if k == 3 else old
+        cols.append(np.ascontiguousarray(np.stack([old, new], 1).reshape(-1)))
+    return ops, cols
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -313,38 +335,41 @@ def cpu_topology():
     return allowed, phys, quota
 
 
-def cpu_join_run(auct, batches, cpu_ids, warmup, chunk=CHUNK, pin=True):
+class CpuActors:
     """P = len(cpu_ids) single-threaded actors (oracle/fastcpu.cc rwf_pool_*: one long-lived OS thread each, pinned to
     cpu_ids[a], tables first-touched on that thread), input vnode-partitioned the way HashDataDispatcher would deliver
-    it, each actor consuming ITS stream of 1024-row chunks independently.  `auct`: build-side columns (pushed untimed),
-    `batches`: probe-side batches, the first `warmup` untimed.  -> dict(value rows/s, wall_s, busy per actor, ...)."""
-    fc = FastCpu().f
-    P = len(cpu_ids)
-    fc.rwf_pool_new.restype = C.c_void_p
-    fc.rwf_pool_new.argtypes = [C.c_int, C.c_void_p]
-    fc.rwf_pool_reserve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    fc.rwf_pool_run.restype = C.c_int64
-    fc.rwf_pool_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p]
-    fc.rwf_pool_pin_failures.argtypes = [C.c_void_p]
-    fc.rwf_pool_checksum.restype = C.c_uint64
-    fc.rwf_pool_checksum.argtypes = [C.c_void_p]
-    fc.rwf_pool_free.argtypes = [C.c_void_p]
-    ids = np.asarray(cpu_ids if pin else [-1] * P, dtype=np.int32)
-    pool = fc.rwf_pool_new(P, ids.ctypes.data)
+    it, each actor consuming ITS stream of 1024-row chunks independently."""
 
-    def pack(blist):
-        """vnode-partition every batch; -> argument arrays indexed [batch * P + actor] (+ keepalive)"""
-        nb = len(blist)
+    def __init__(self, cpu_ids, pin=True, chunk=CHUNK):
+        fc = FastCpu().f
+        self.fc, self.P, self.chunk, self.pin = fc, len(cpu_ids), chunk, pin
+        fc.rwf_pool_new.restype = C.c_void_p
+        fc.rwf_pool_new.argtypes = [C.c_int, C.c_void_p]
+        fc.rwf_pool_reserve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        fc.rwf_pool_run.restype = C.c_int64
+        fc.rwf_pool_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p] + [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_void_p]
+        fc.rwf_pool_pin_failures.argtypes = [C.c_void_p]
+        fc.rwf_pool_checksum.restype = C.c_uint64
+        fc.rwf_pool_checksum.argtypes = [C.c_void_p]
+        fc.rwf_pool_free.argtypes = [C.c_void_p]
+        ids = np.asarray(cpu_ids if pin else [-1] * self.P, dtype=np.int32)
+        self.pool = fc.rwf_pool_new(self.P, ids.ctypes.data)
+
+    def pack(self, blist):
+        """vnode-partition every batch (a batch is `cols` = all-Insert, or `(ops, cols)`); -> argument arrays indexed
+        [batch * P + actor] (+ keepalive)"""
+        P, nb = self.P, len(blist)
         cnts = np.zeros((nb, P), np.int64)
         ptrs = [(C.c_void_p * (nb * P))() for _ in range(5)]
         keep = []
-        for b, cols in enumerate(blist):
+        for b, item in enumerate(blist):
+            ops_in, cols = item if isinstance(item, tuple) else (None, item)
             part = vnode_of_int64(cols[0]) * P // 256
             order = np.argsort(part, kind="stable")
             cnt = np.bincount(part, minlength=P).astype(np.int64)
             off = np.concatenate([[0], np.cumsum(cnt)[:-1]])
             sc = [np.ascontiguousarray(c[order]) for c in cols]
-            ops = np.ones(len(order), np.uint8)
+            ops = np.ones(len(order), np.uint8) if ops_in is None else np.ascontiguousarray(ops_in[order])
             keep.append((ops, sc))
             cnts[b] = cnt
             for a in range(P):
@@ -353,26 +378,58 @@ def cpu_join_run(auct, batches, cpu_ids, warmup, chunk=CHUNK, pin=True):
                     ptrs[1 + k][b * P + a] = sc[k].ctypes.data + int(off[a]) * 8
         return nb, cnts, ptrs, keep
 
-    def run(side, packed, warm):
-        nb, cnts, ptrs, _ = packed
+    def reserve(self, build_cols):
+        """size every actor's tables for its share of the build side's keys, on the actor's own thread"""
+        part = vnode_of_int64(build_cols[0]) * self.P // 256
+        keys = np.ascontiguousarray(np.bincount(part, minlength=self.P).astype(np.uint64))
+        self.fc.rwf_pool_reserve(self.pool, keys.ctypes.data, keys.ctypes.data)
+
+    def run(self, side, batches, warmup=0):
+        """-> dict(value = rows/s over the batches after the first `warmup`, out_rows / checksum of those, ...)"""
+        fc, P = self.fc, self.P
+        nb, cnts, ptrs, keep = self.pack(batches)
+        cs0 = None
+        if warmup:  # the checksum is cumulative: run the warm-up batches in a call of their own
+            self._call(side, (warmup, cnts[:warmup], [self._slice(p, 0, warmup) for p in ptrs]), 0)
+        cs0 = fc.rwf_pool_checksum(self.pool)
+        out_rows, wall, busy = self._call(side, (nb - warmup, cnts[warmup:], [self._slice(p, warmup, nb) for p in ptrs]), 0)
+        rows = sum(len((b[1] if isinstance(b, tuple) else b)[0]) for b in batches[warmup:])
+        return {"value": rows / wall if wall > 0 else 0.0, "wall_s": wall, "actors": P, "busy_s_min": float(busy.min()),
+                "busy_s_max": float(busy.max()), "busy_s_mean": float(busy.mean()),
+                "pin_failures": int(fc.rwf_pool_pin_failures(self.pool)) if self.pin else None, "out_rows": out_rows,
+                "checksum": (fc.rwf_pool_checksum(self.pool) - cs0) & ((1 << 64) - 1)}
+
+    def _slice(self, arr, lo, hi):
+        n = (hi - lo) * self.P
+        out = (C.c_void_p * max(n, 1))()
+        for i in range(n):
+            out[i] = arr[lo * self.P + i]
+        return out
+
+    def _call(self, side, packed, warm):
+        nb, cnts, ptrs = packed
+        cnts = np.ascontiguousarray(cnts)
         wall = C.c_double()
-        busy = np.zeros(P, np.float64)
-        rows = fc.rwf_pool_run(pool, side, nb, warm, cnts.ctypes.data, *ptrs, chunk, C.byref(wall), busy.ctypes.data)
+        busy = np.zeros(self.P, np.float64)
+        rows = self.fc.rwf_pool_run(self.pool, side, nb, warm, cnts.ctypes.data, *ptrs, self.chunk, C.byref(wall), busy.ctypes.data)
         return int(rows), wall.value, busy
 
-    ap = pack([auct])
-    keys = np.ascontiguousarray(ap[1][0].astype(np.uint64))
-    fc.rwf_pool_reserve(pool, keys.ctypes.data, keys.ctypes.data)  # distinct keys per actor, both sides
-    run(1, ap, 0)
-    cs0 = fc.rwf_pool_checksum(pool)
-    bp = pack(batches)
-    out_rows, wall, busy = run(0, bp, warmup)
-    # (the checksum covers warm-up batches too: callers that verify pass warmup = 0)
-    res = {"value": sum(len(b[0]) for b in batches[warmup:]) / wall if wall > 0 else 0.0, "wall_s": wall, "actors": P,
-           "busy_s_min": float(busy.min()), "busy_s_max": float(busy.max()), "busy_s_mean": float(busy.mean()),
-           "pin_failures": int(fc.rwf_pool_pin_failures(pool)) if pin else None, "out_rows": out_rows,
-           "checksum": (fc.rwf_pool_checksum(pool) - cs0) & ((1 << 64) - 1)}
-    fc.rwf_pool_free(pool)
+    def close(self):
+        if self.pool:
+            self.fc.rwf_pool_free(self.pool)
+            self.pool = None
+
+
+def cpu_join_run(auct, batches, cpu_ids, warmup, chunk=CHUNK, pin=True, after=None):
+    """build side `auct` (untimed), then the probe-side `batches` (the first `warmup` untimed) through P pinned actors;
+    `after` = optional (side, batches) pushed afterwards, its result under key "after".  -> dict (see CpuActors.run)"""
+    ca = CpuActors(cpu_ids, pin, chunk)
+    ca.reserve(auct)
+    ca.run(1, [auct])
+    res = ca.run(0, batches, warmup)
+    if after is not None:
+        res["after"] = ca.run(after[0], after[1])
+    ca.close()
     return res
 
 
@@ -442,7 +499,7 @@ def run_ours(args):
         return device.DeviceChunk(ops, cols, T4)
 
     line = {}
-    verify_gpu = None
+    verify_gpu = retract_verify = hot_verify = None
     with torch.cuda.stream(stream):
         auct_dev = to_dev(auct)
 
@@ -600,7 +657,113 @@ def run_ours(args):
                     dist.all_reduce(t)
                     vr, vc = int(t[0].item()), (int(t[1].item()) + (int(t[2].item()) << 32)) & ((1 << 64) - 1)
                 verify_gpu = (vr, vc)
+            # ================================================================ leg: retract (SURVEY 8(d) cfg3 retraction phase)
+            # the same handle, now holding (W + K + V) x 2^20 bids: auction UPDATES (U- stored row / U+ same id, new
+            # `expires`) probe the bid side -- every matched bid is emitted twice (- then +), the first time multi-match
+            # emission, the own-side delete kernel and re-insertion are timed.  Step = 2^19 pairs = 2^20 rows.
+            if "retract" in legs and world == 1:
+                RP, KR, WR = 1 << 19, 4, 1
+                ups = [gen_auction_updates(auct, s * RP, RP) for s in range(WR + KR + 1)]  # (+1: verification step)
+                ups_dev = [device.DeviceChunk(torch.from_numpy(o).cuda(), to_dev(c), T4) for o, c in ups]
+                torch.cuda.synchronize()
+
+                def run_updates(lo, hi, each=None):
+                    tot = 0
+                    for s in range(lo, hi):
+                        device.join_push_device_async(join, abi.SIDE_RIGHT, ups_dev[s], stream)
+                        if s > lo:
+                            o = device.join_collect(join, stream)
+                            tot += o.n_rows
+                        if each and s > lo:
+                            each(o)
+                    o = device.join_collect(join, stream)
+                    tot += o.n_rows
+                    if each:
+                        each(o)
+                    return tot
+
+                run_updates(0, WR)
+                device.profile(join, "join", True)
+                r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                r0.record(stream)
+                r_out = run_updates(WR, WR + KR)
+                r1.record(stream)
+                torch.cuda.synchronize()
+                rms = r0.elapsed_time(r1)
+                rk_ms, rk_n = device.profile(join, "join", False)
+                cs = [0, 0]
+
+                def add_cs(o):
+                    a, b = o.checksum(CHECKSUM_WEIGHTS)
+                    cs[0] += a
+                    cs[1] = (cs[1] + b) & ((1 << 64) - 1)
+
+                run_updates(WR + KR, WR + KR + 1, add_cs)
+                retract_verify = (cs[0], cs[1], ups[:WR + KR], ups[WR + KR])
+                m_avg = r_out / (KR * 2 * RP)  # visible + filler rows per input row (upper bound of matches per row)
+                bpr = 33.125 + 16 + m_avg * 97 + 32  # read row + bucket + m x (matched row in, joined row out) + own-side delete / re-insert
+                line["retract"] = {
+                    "workload": "cfg3 retraction phase: auction U-/U+ pairs against the bid side held by the same operator "
+                                f"({(W + K + V) * BATCH} bids stored), 2^19 pairs = 2^20 rows per step",
+                    "metric": "input rows/s", "value": KR * 2 * RP / (rms / 1e3), "steps": KR, "ms_per_step": rms / KR,
+                    "out_rows_per_input_row": m_avg,
+                    "roofline": {"bound": "hbm", "kernel": "uni_quad_kernel<false,true> (inline-side rows: chain walk + emit + inline claim) + uni_delete_kernel",
+                                 "achieved": bpr * 2 * RP * rk_n / (rk_ms / 1e3) / 1e9 if rk_ms else None, "peak": peak, "unit": "GB/s",
+                                 "frac": (bpr * 2 * RP * rk_n / (rk_ms / 1e3) / 1e9 / peak) if rk_ms else None,
+                                 "algorithmic_bytes_per_row": bpr, "kernel_ms_avg": rk_ms / max(rk_n, 1), "traffic": None}}
+                del ups_dev
             del join, batches_dev, chunks_dev
+            torch.cuda.empty_cache()
+
+        # ================================================================ leg: hot (SURVEY 8(d) cfg3 hot variant)
+        if "hot" in legs and world == 1:
+            KH, WH = min(K, 10), 3
+            jh = new_join()
+            build(jh, shuffle=False)
+            hb = [gen_bids(BATCH, s * BATCH, SEED, N_BUILD, hot=True) for s in range(WH + KH + 1)]
+            hdev = [dchunk(to_dev(b)) for b in hb]
+            torch.cuda.synchronize()
+
+            def run_hot(lo, hi, each=None):
+                tot = 0
+                for s2 in range(lo, hi):
+                    device.join_push_device_async(jh, abi.SIDE_LEFT, hdev[s2], stream)
+                    if s2 > lo:
+                        o = device.join_collect(jh, stream)
+                        tot += o.n_rows
+                        if each:
+                            each(o)
+                o = device.join_collect(jh, stream)
+                tot += o.n_rows
+                if each:
+                    each(o)
+                return tot
+
+            run_hot(0, WH)
+            device.profile(jh, "join", True)
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record(stream)
+            run_hot(WH, WH + KH)
+            h1.record(stream)
+            torch.cuda.synchronize()
+            hms = h0.elapsed_time(h1)
+            hk_ms, hk_n = device.profile(jh, "join", False)
+            hcs = [0, 0]
+
+            def add_hcs(o):
+                a, b = o.checksum(CHECKSUM_WEIGHTS)
+                hcs[0] += a
+                hcs[1] = (hcs[1] + b) & ((1 << 64) - 1)
+
+            run_hot(WH + KH, WH + KH + 1, add_hcs)
+            hot_verify = (hcs[0], hcs[1], hb[WH + KH])
+            hg = JOIN_BYTES_PER_ROW_STEP * BATCH * hk_n / (hk_ms / 1e3) / 1e9 if hk_ms else None
+            line["hot"] = {"workload": "cfg3 hot variant: half of the bids go to 100 hot auctions (same-bucket atomics, long chains)",
+                           "metric": "input rows/s", "value": KH * BATCH / (hms / 1e3), "steps": KH, "ms_per_step": hms / KH,
+                           "roofline": {"bound": "hbm", "kernel": "uni_quad_kernel<false,false>", "achieved": hg, "peak": peak, "unit": "GB/s",
+                                        "frac": hg / peak if hg else None, "algorithmic_bytes_per_row": JOIN_BYTES_PER_ROW_STEP,
+                                        "kernel_ms_avg": hk_ms / max(hk_n, 1), "traffic": None}}
+            del jh, hdev
             torch.cuda.empty_cache()
 
         # ================================================================ leg: e2e (host buffers, C ABI)
@@ -686,18 +849,32 @@ def run_ours(args):
             if res:
                 line["e2e"] = res
 
-        # ================================================================ leg: agg (secondary, configs[1])
-        if "agg" in legs and world == 1:
+        # ================================================================ leg: agg (secondary, configs[1]; SURVEY 8(d) cfg2 A / B / R)
+        def agg_leg(variant):
+            """variant A: uniform keys; B: half of the rows on 128 hot auctions; R: 10 % of the rows retract a row of the
+            previous epoch (count / sum only: max is an append-only value state).  Every epoch's delta is compared with the CPU
+            restatement through (row count, checksum) -- collected outside the timed loop on a second pass."""
+            calls = ("(count:int8)", "(sum:int8 $1:int8)") + (() if variant == "R" else ("(max:int8 $1:int8)",))
             _, src = MockSource.channel()
-            agg = HashAggExecutor(be, src.into_executor([abi.T_INT64] * 2, []), True,
-                                  [AggCall.from_pretty(c) for c in ("(count:int8)", "(sum:int8 $1:int8)", "(max:int8 $1:int8)")],
-                                  0, [0], group_capacity_hint=2 * AGG_KEYS)
+            agg = HashAggExecutor(be, src.into_executor([abi.T_INT64] * 2, []), variant != "R",
+                                  [AggCall.from_pretty(c) for c in calls], 0, [0], group_capacity_hint=2 * AGG_KEYS)
             n_ep_w, n_ep = 4, 60
-            ep_dev = []
+            seed = {"A": AGG_SEED, "B": AGG_SEED + 1, "R": AGG_SEED + 2}[variant]
+            ep_host, ep_dev = [], []
+            prev = None
             for e in range(n_ep_w + n_ep):
-                k, p = gen_agg_rows(AGG_EPOCH_ROWS, e * AGG_EPOCH_ROWS, AGG_SEED)
-                ep_dev.append(device.DeviceChunk(torch.ones(AGG_EPOCH_ROWS, dtype=torch.uint8, device="cuda"),
-                                                 [torch.from_numpy(k).cuda(), torch.from_numpy(p).cuda()], [abi.T_INT64] * 2))
+                k, p = gen_agg_rows(AGG_EPOCH_ROWS, e * AGG_EPOCH_ROWS, seed, hot=(variant == "B"))
+                ops = np.ones(AGG_EPOCH_ROWS, np.uint8)
+                if variant == "R" and prev is not None:
+                    nd = AGG_EPOCH_ROWS // 10  # rows 0, 10, 20, ... retract row i of the previous epoch (each at most once)
+                    sel = np.arange(nd) * 10
+                    live = prev[2][sel] == 1
+                    k[sel[live]], p[sel[live]] = prev[0][sel[live]], prev[1][sel[live]]
+                    ops[sel[live]] = 2
+                prev = (k, p, ops)
+                ep_host.append((ops, k, p))
+                ep_dev.append(device.DeviceChunk(torch.from_numpy(ops).cuda(), [torch.from_numpy(k).cuda(), torch.from_numpy(p).cuda()],
+                                                 [abi.T_INT64] * 2))
             torch.cuda.synchronize()
             for e in range(n_ep_w):
                 device.agg_push_device(agg, ep_dev[e], stream)
@@ -708,6 +885,7 @@ def run_ours(args):
             # launch / collect split: barrier e is only ENQUEUED after its epoch's rows; its delta is collected while the
             # GPU already works on epoch e + 1 (two output sets), so the host never sits between two launches
             delta_rows = 0
+            n_v = 6  # the last n_v epochs are checksummed (outside the timed loop: their deltas are kept by value)
             for e in range(n_ep_w, n_ep_w + n_ep):
                 device.agg_push_device(agg, ep_dev[e], stream)
                 device.agg_flush_device_async(agg, e + 1, stream)
@@ -718,14 +896,59 @@ def run_ours(args):
             torch.cuda.synchronize()
             ams = a0.elapsed_time(a1)
             akern_ms, akern_n = device.profile(agg, "agg", False)
+            # verification epochs (untimed): n_v more epochs, each delta checksummed, against the CPU restatement fed everything
+            vr = vc = 0
+            v_host = []
+            for e in range(n_ep_w + n_ep, n_ep_w + n_ep + n_v):
+                k, p = gen_agg_rows(AGG_EPOCH_ROWS, e * AGG_EPOCH_ROWS, seed, hot=(variant == "B"))
+                ops = np.ones(AGG_EPOCH_ROWS, np.uint8)
+                v_host.append((ops, k, p))
+                device.agg_push_device(agg, device.DeviceChunk(torch.from_numpy(ops).cuda(), [torch.from_numpy(k).cuda(), torch.from_numpy(p).cuda()],
+                                                               [abi.T_INT64] * 2), stream)
+                rows_v, cs_v = device.agg_flush_device(agg, e + 1, stream).checksum((1,) * (1 + len(calls)))
+                vr += rows_v
+                vc = (vc + cs_v) & ((1 << 64) - 1)
+            fc = FastCpu().f
+            fc.rwf_agg_checksum.restype = C.c_uint64
+            fc.rwf_agg_checksum.argtypes = [C.c_void_p]
+            ha = fc.rwf_agg_new(0 if variant == "R" else 1)
+            fc.rwf_agg_reserve(ha, 2 * AGG_KEYS)
+            want_rows = 0
+            cs0 = 0
+            for idx, (ops, k, p) in enumerate(ep_host + v_host):
+                fc.rwf_agg_push(ha, len(ops), ops.ctypes.data, k.ctypes.data, p.ctypes.data)
+                r = fc.rwf_agg_flush(ha)
+                if idx == len(ep_host) - 1:
+                    cs0 = fc.rwf_agg_checksum(ha)
+                if idx >= len(ep_host):
+                    want_rows += r
+            want_cs = (fc.rwf_agg_checksum(ha) - cs0) & ((1 << 64) - 1)
+            fc.rwf_agg_free(ha)
+            d = delta_rows / (n_ep * AGG_EPOCH_ROWS)
+            # B_agg = W_in + 1.125 + (K + 2A) + d_groups * (2 (K + A_out + 1) + K + A + A_out), d_groups = delta rows / 2
+            A = 8 * len(calls)
+            bpr = 16 + 1.125 + 8 + 2 * A + (d / 2) * (2 * (8 + A + 1) + 8 + A + A)
             agbs = AGG_BYTES_PER_ROW_FLOOR * AGG_EPOCH_ROWS * akern_n / (akern_ms / 1e3) / 1e9 if akern_ms else None
-            line["secondary"] = {
-                "workload": "nexmark_q4_hashagg_cfg2: count(*),sum,max GROUP BY auction; 2^20 keys uniform; 2^18-row epochs (256 chunks x 1024)",
+            step_gbs = bpr * n_ep * AGG_EPOCH_ROWS / (ams / 1e3) / 1e9
+            return {
+                "workload": f"nexmark_q4_hashagg_cfg2 variant {variant}: {', '.join(calls)} GROUP BY auction; 2^20 keys "
+                            + {"A": "uniform", "B": "half of the rows on 128 hot keys", "R": "uniform, 10 % of the rows retract a row of the previous epoch"}[variant]
+                            + "; 2^18-row epochs (256 chunks x 1024), barrier per epoch (launch / collect split)",
                 "metric": "rows/s", "value": n_ep * AGG_EPOCH_ROWS / (ams / 1e3), "epochs": n_ep, "ms_per_epoch": ams / n_ep,
-                "delta_rows_per_input_row": delta_rows / (n_ep * AGG_EPOCH_ROWS),
-                "roofline": {"bound": "hbm", "kernel": "agg_apply_fast_kernel<3>", "achieved": agbs, "peak": peak, "unit": "GB/s",
+                "delta_rows_per_input_row": d,
+                "verified": bool((vr, vc) == (want_rows, want_cs)),
+                "verification": {"epochs": n_v, "gpu_delta_rows": vr, "cpu_delta_rows": want_rows, "gpu_checksum": f"{vc:016x}", "cpu_checksum": f"{want_cs:016x}"},
+                "roofline": {"bound": "hbm", "kernel": f"agg_apply_fast_kernel<{len(calls)}>", "achieved": agbs, "peak": peak, "unit": "GB/s",
                              "frac": agbs / peak if agbs else None, "traffic": ncu_traffic("agg_apply_fast_kernel"), "peak_source": which,
-                             "algorithmic_bytes_per_row": AGG_BYTES_PER_ROW_FLOOR, "kernel_ms_avg": akern_ms / max(akern_n, 1)}}
+                             "algorithmic_bytes_per_row": AGG_BYTES_PER_ROW_FLOOR, "kernel_ms_avg": akern_ms / max(akern_n, 1)},
+                "epoch_roofline": {"what": "apply + barrier delta together (the whole epoch), bytes incl. the emitted delta rows",
+                                   "algorithmic_bytes_per_row": bpr, "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak}}
+
+        if "agg" in legs and world == 1:
+            line["secondary"] = agg_leg("A")
+            line["secondary_hot_keys"] = agg_leg("B")
+            line["secondary_retract"] = agg_leg("R")
+            torch.cuda.empty_cache()
 
         # ================================================================ leg: chain (join -> filter -> project -> agg in HBM)
         if "chain" in legs and world == 1:
@@ -814,6 +1037,26 @@ def run_ours(args):
                                        "with oracle/fastcpu.cc fed the same build side and batches"}
         if not ok:
             print("VERIFICATION FAILED: " + json.dumps(line["verification"]), file=sys.stderr)
+    if retract_verify is not None:
+        # CPU replay: build, every bid batch the handle received, the timed update steps, then the verification step
+        rows_g, cs_g, warm_ups, ver_up = retract_verify
+        ca = CpuActors(phys[:64])
+        ca.reserve(auct)
+        ca.run(1, [auct])
+        ca.run(0, batches_host)
+        ca.run(1, warm_ups)
+        rv = ca.run(1, [ver_up])
+        ca.close()
+        want_rows, want_cs = rv["out_rows"], rv["checksum"]
+        line["retract"]["verified"] = bool((rows_g, cs_g) == (want_rows, want_cs))
+        line["retract"]["verification"] = {"gpu_out_rows": rows_g, "cpu_out_rows": want_rows, "gpu_checksum": f"{cs_g:016x}",
+                                           "cpu_checksum": f"{want_cs:016x}"}
+    if hot_verify is not None:
+        rows_g, cs_g, vb_hot = hot_verify
+        ref = cpu_join_run(gen_auctions(N_BUILD, SEED), [vb_hot], phys[:64], 0)
+        line["hot"]["verified"] = bool((rows_g, cs_g) == (ref["out_rows"], ref["checksum"]))
+        line["hot"]["verification"] = {"gpu_out_rows": rows_g, "cpu_out_rows": ref["out_rows"], "gpu_checksum": f"{cs_g:016x}",
+                                       "cpu_checksum": f"{ref['checksum']:016x}"}
     if "cpu" in legs and world == 1:
         nb = 5
         sample = [gen_bids(1 << 20, s << 20, SEED, N_BUILD) for s in range(nb)]
@@ -881,7 +1124,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--legs", default="value,e2e,agg,chain,cpu", help="comma list of: value,e2e,agg,chain,cpu (subset for ncu runs)")
+    ap.add_argument("--legs", default="value,retract,hot,e2e,agg,chain,cpu",
+                    help="comma list of: value,retract,hot,e2e,agg,chain,cpu (subset for ncu runs; retract needs value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
