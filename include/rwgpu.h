@@ -96,12 +96,15 @@ void rwgpu_out_release(rwgpu_out* out);
  * replaces HashAggExecutor (src/stream/src/executor/aggregate/hash_agg.rs):
  *   rwgpu_agg_push   <-> apply_chunk            hash_agg.rs:332-409
  *   rwgpu_agg_flush  <-> flush_data at barrier  hash_agg.rs:412-514, 651-676
- * Only value-state calls are offloaded (agg_state.rs:49-56): count, sum, and min/max on
- * append-only input.  Others => RW_ERR_UNSUPPORTED.                           */
+ * Offloaded states (agg_state.rs:49-56): the value states count, sum, and min/max on append-only input, and
+ * -- is_append_only == 0 -- RETRACTABLE min/max, the reference's MaterializedInput state (minput.rs): the call's
+ * non-NULL input values are kept as a chained multiset in HBM; a retraction kills one record, and if it was the
+ * group's extreme the barrier recomputes it from the live records.  string_agg / array_agg / DISTINCT / EOWC
+ * => RW_ERR_UNSUPPORTED.  (The value log only grows between restarts; 2^31 values per operator.)            */
 #define RW_AGG_COUNT 1     /* count(*) when arg_col < 0, else count(col)   general.rs:155-162 */
 #define RW_AGG_SUM 2       /* general.rs:28-41                                                 */
-#define RW_AGG_MIN 3       /* general.rs:91-108 (append-only)                                  */
-#define RW_AGG_MAX 4       /* general.rs:110-125 (append-only)                                 */
+#define RW_AGG_MIN 3       /* general.rs:91-108 (append-only) / minput.rs (retractable)        */
+#define RW_AGG_MAX 4       /* general.rs:110-125 (append-only) / minput.rs (retractable)       */
 #define RW_AGG_SUM0 5      /* sum0(int8)->int8, init 0     general.rs:28                      */
 
 typedef struct rw_agg_call {

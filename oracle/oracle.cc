@@ -269,6 +269,9 @@ struct AggOracle {
     bool has_prev = false;
     Row prev;
     bool dirty = false;
+    // AggState::MaterializedInput (agg_state.rs:49-56, minput.rs:45-): the retractable min / max of call c is the
+    // first row of the call's materialized input in (value, pk) order -- here the multiset of its non-NULL values
+    std::vector<std::vector<Datum>> minput;
   };
   std::unordered_map<std::string, size_t> index;
   std::vector<Group> groups;
@@ -319,6 +322,7 @@ int agg_apply(const AggOracle& a, const rw_agg_call& c, Datum& st, const Datum& 
     case RW_AGG_MAX: {
       // assert_eq!(op, Op::Insert, "attempt to retract on aggregate function .., but it is append-only")
       if (v.null) return RW_OK;  // also filtered by agg_call_filter_res (aggregate/mod.rs:81-109)
+      if (!a.append_only) return fail(RW_ERR_CUDA, "internal: retractable min/max goes through agg_apply_minput");
       if (op != RW_OP_INSERT) return fail(RW_ERR_INCONSISTENT, "attempt to retract on append-only min/max");
       if (st.null) { st = v; return RW_OK; }  // state = "ref": first value
       int cmp = datum_cmp_nonnull(v, st, arg_type);
@@ -327,6 +331,34 @@ int agg_apply(const AggOracle& a, const rw_agg_call& c, Datum& st, const Datum& 
     }
   }
   return fail(RW_ERR_UNSUPPORTED, "agg kind");
+}
+
+// retractable min / max: MaterializedInputState::apply_chunk (minput.rs:172-182) inserts / deletes the row in the call's
+// materialized input (rows with a NULL argument are filtered out before, aggregate/mod.rs:81-109); get_output
+// (minput.rs:184-245) returns the first row in order.  The state datum mirrors that output after every row.
+int agg_apply_minput(const AggOracle& a, const rw_agg_call& c, std::vector<Datum>& rows, Datum& st, const Datum& v, int arg_type,
+                     uint8_t op) {
+  if (v.null) return RW_OK;
+  const bool retract = (op == RW_OP_DELETE || op == RW_OP_UPDATE_DELETE);
+  if (!retract) {
+    rows.push_back(v);
+  } else {
+    size_t i = 0;
+    while (i < rows.size() && datum_cmp_nonnull(rows[i], v, arg_type) != 0) i++;
+    if (i == rows.size()) {
+      if (a.strict) return fail(RW_ERR_INCONSISTENT, "retracting a row that is not in the materialized input");
+    } else {
+      rows[i] = rows.back();
+      rows.pop_back();
+    }
+  }
+  st = Datum();
+  for (const Datum& x : rows) {
+    if (st.null) { st = x; continue; }
+    const int cmp = datum_cmp_nonnull(x, st, arg_type);
+    if ((c.kind == RW_AGG_MIN && cmp < 0) || (c.kind == RW_AGG_MAX && cmp > 0)) st = x;
+  }
+  return RW_OK;
 }
 
 }  // namespace
@@ -372,12 +404,6 @@ int32_t rwo_agg_create(const rw_agg_desc* d, rwo_agg** out) {
   a.append_only = d->is_append_only != 0;
   a.strict = d->strict_consistency != 0;
   a.chunk_size = d->chunk_size > 0 ? d->chunk_size : 1024;
-  for (auto& c : a.calls) {
-    if ((c.kind == RW_AGG_MIN || c.kind == RW_AGG_MAX) && !a.append_only) {
-      delete h;
-      return fail(RW_ERR_UNSUPPORTED, "retractable min/max uses MaterializedInput state (agg_state.rs:49-56)");
-    }
-  }
   for (int k : a.key_idx) a.out_types.push_back(a.in_types[k]);
   for (auto& c : a.calls) a.out_types.push_back(c.ret_type);
   a.builder = ChunkBuilder((size_t)a.chunk_size, a.out_types);
@@ -406,6 +432,7 @@ int32_t rwo_agg_push(rwo_agg* h, const rw_chunk* ch) {
       AggOracle::Group& g = a.groups.back();
       g.key = key;
       for (auto& c : a.calls) g.states.push_back(a.init_state(c));
+      g.minput.resize(a.calls.size());
     } else {
       gi = it->second;
     }
@@ -419,7 +446,8 @@ int32_t rwo_agg_push(rwo_agg* h, const rw_chunk* ch) {
         v = read_datum(ch->columns[a.calls[c].arg_col], r);
         at = a.in_types[a.calls[c].arg_col];
       }
-      int rc = agg_apply(a, a.calls[c], g.states[c], v, at, op);
+      const bool minput = !a.append_only && (a.calls[c].kind == RW_AGG_MIN || a.calls[c].kind == RW_AGG_MAX);
+      int rc = minput ? agg_apply_minput(a, a.calls[c], g.minput[c], g.states[c], v, at, op) : agg_apply(a, a.calls[c], g.states[c], v, at, op);
       if (rc != RW_OK) return rc;
     }
   }
@@ -441,8 +469,12 @@ int32_t rwo_agg_flush(rwo_agg* h, uint64_t /*epoch*/, rwgpu_out** out) {
       if (a.strict) { delete o; return fail(RW_ERR_INCONSISTENT, "row count should be non-negative"); }
       rc = 0;
     }
-    if (rc == 0) {  // reset value states (agg_group.rs:438-446)
-      for (size_t c = 0; c < a.calls.size(); c++) g.states[c] = a.init_state(a.calls[c]);
+    if (rc == 0) {  // reset value states (agg_group.rs:438-446); a materialized input is NOT reset ("in fact only
+      // value states will be reset"): with zero rows it is empty anyway unless the stream is inconsistent
+      for (size_t c = 0; c < a.calls.size(); c++) {
+        const bool minput = !a.append_only && (a.calls[c].kind == RW_AGG_MIN || a.calls[c].kind == RW_AGG_MAX);
+        if (!minput) g.states[c] = a.init_state(a.calls[c]);
+      }
     }
     Row curr = g.states;  // value-state output == state datum
     int64_t prev_rc = 0;
@@ -1014,6 +1046,7 @@ extern "C" int32_t rwo_filter(const rw_chunk* ch, const rw_filter_term* terms, i
 extern "C" int32_t rwo_agg_eval(const rw_agg_call* call, int32_t arg_type, const rw_chunk* ch, int32_t* is_null,
                                 int64_t* out_lo, int64_t* out_hi, double* out_f) {
   AggOracle a;
+  a.append_only = true;  // the aggregate FUNCTIONS of general.rs are the append-only value states
   Datum st = a.init_state(*call);
   for (int64_t r = 0; r < ch->n_rows; r++) {
     if (!bit_get(ch->visibility, r)) continue;

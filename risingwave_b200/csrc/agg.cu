@@ -26,6 +26,8 @@ namespace rw {
 #define AGG_ERR_NEG_COUNT 2u
 #define AGG_ERR_RETRACT_APPEND_ONLY 4u
 #define AGG_ERR_OUT_CAPACITY 8u
+#define AGG_ERR_MM_MISSING 16u   // retracting a value that is not in the call's materialized input
+#define AGG_ERR_MM_CAPACITY 32u  // internal: materialized-input log full
 
 struct AggStatus {
   unsigned long long out_rows;
@@ -47,6 +49,7 @@ struct AggPlanDev {
   int ret_type[RW_MAX_CALLS];
   int hi_off[RW_MAX_CALLS];      // cold word of the sum carry (hi) word, -1 if none
   int prevhi_off[RW_MAX_CALLS];  // cold word of prev output hi (decimal ret), -1 if none
+  int mm_off[RW_MAX_CALLS];      // retractable min / max: cold word holding the head of the call's value chain, -1 if none
   int KW, HW, CW;
   int single_key;
   int row_count_call;
@@ -60,7 +63,14 @@ struct AggTable {
   uint32_t* dirty_list;  // slots touched since the last barrier (each exactly once)
   AggStatus* status;
   uint64_t cap;  // power of two
+  // retractable min / max (AggState::MaterializedInput, agg_state.rs:49-56 / minput.rs): every non-NULL input value of
+  // such a call is a 16-byte record {u32 link | DEAD, u32 -, i64 value (sortable form)} chained from the group's cold row
+  ulonglong2* mm_log;
+  unsigned long long* mm_next;  // next free record id (ids start at 1: 0 = end of chain)
+  uint64_t mm_cap;
 };
+#define MM_DEAD 0x80000000u
+#define COLD_RECOMPUTE_SHIFT 48  // cold word 0, bit 48 + c: call c's extreme was retracted -> recompute at the barrier
 
 // mark `slot` dirty; the thread that flips the bit appends the slot to the dirty list
 // (opportunistic warp aggregation: one atomicAdd per group of converged first-touchers)
@@ -196,6 +206,20 @@ __device__ __forceinline__ void agg_apply_row(const AggTable& t, const AggPlanDe
           atomicAdd(sp, add);  // |x| < 2^31: cannot leave int64 below 2^32 rows per group
         }
       }
+    } else if (p.mm_off[c] >= 0) {  // retractable MIN / MAX: materialized input (minput.rs:172-182)
+      if (retract) { setflags &= ~(1u << c); continue; }  // retractions are applied by agg_mm_delete_kernel after this kernel
+      long long v = isf ? (long long)f64_sortable(load_f64(ch.cols[ac], r)) : (long long)load_i64(ch.cols[ac], r);
+      // one record per value: id from the shared counter (aggregated over the converged lanes), pushed on the chain
+      const unsigned m = __activemask();
+      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(t.mm_next, (unsigned long long)__popc(m));
+      base = __shfl_sync(m, base, leader);
+      const unsigned long long id = base + __popc(m & ((1u << lane) - 1));
+      if (id >= t.mm_cap) { atomicOr(&t.status->err, AGG_ERR_MM_CAPACITY); continue; }
+      const uint32_t old = atomicExch((uint32_t*)(cold + p.mm_off[c]), (uint32_t)id);
+      t.mm_log[id] = make_ulonglong2((unsigned long long)old, (unsigned long long)v);
+      if (kind == RW_AGG_MIN) atomicMin((long long*)sp, v); else atomicMax((long long*)sp, v);
     } else {  // MIN / MAX (append-only value state, general.rs:91-125)
       if (op != RW_OP_INSERT) { atomicOr(&t.status->err, AGG_ERR_RETRACT_APPEND_ONLY); continue; }
       long long v = isf ? (long long)f64_sortable(load_f64(ch.cols[ac], r)) : (long long)load_i64(ch.cols[ac], r);
@@ -241,6 +265,61 @@ __global__ void __launch_bounds__(256) agg_apply_kernel(AggTable t, AggPlanDev p
   // warp-aggregated group counter
   for (int o = 16; o > 0; o >>= 1) created_local += __shfl_xor_sync(0xffffffffu, created_local, o);
   if (lane_id() == 0 && created_local) atomicAdd(&t.status->n_groups, (unsigned long long)created_local);
+}
+
+// ------------------------------------------------------------------ retractable min / max: the retractions of a chunk
+// Runs after the apply kernel (every insert of the chunk is in its chain by then).  A retracted value kills ONE live
+// record with that value (the materialized input is a multiset); if it was the group's current extreme the call is
+// flagged and the barrier recomputes the extreme from the live records.
+__global__ void __launch_bounds__(256) agg_mm_delete_kernel(AggTable t, AggPlanDev p, DevChunk ch) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t op = ch.ops[r];
+    if (!row_visible(ch, r, op) || !(op == RW_OP_DELETE || op == RW_OP_UPDATE_DELETE)) continue;
+    uint64_t slot;
+    bool created = false;
+    if (p.single_key) {
+      const ColRef& kc = ch.cols[p.key_col[0]];
+      if (col_is_null(kc, r)) slot = t.cap;
+      else {
+        const uint64_t key = load_key_word(kc, r);
+        slot = key == AGG_EMPTY ? t.cap + 1 : find_or_insert_single(t, p.HW, key, &created);
+      }
+    } else {
+      uint64_t kw[RW_MAX_KEYS];
+      uint32_t nm = 0;
+      for (int k = 0; k < p.n_keys; k++) {
+        const ColRef& kc = ch.cols[p.key_col[k]];
+        if (col_is_null(kc, r)) { nm |= 1u << k; kw[k] = 0; }
+        else kw[k] = load_key_word(kc, r);
+      }
+      slot = find_or_insert_multi(t, p, kw, nm, &created);
+    }
+    uint64_t* cold = t.cold + slot * p.CW;
+    for (int c = 0; c < p.n_calls; c++) {
+      if (p.mm_off[c] < 0) continue;
+      const int ac = p.arg_col[c];
+      if (col_is_null(ch.cols[ac], r)) continue;  // NULL arguments never entered the input (aggregate/mod.rs:81-109)
+      const int at = p.arg_type[c];
+      const long long v = (at == RW_T_FLOAT32 || at == RW_T_FLOAT64) ? (long long)f64_sortable(load_f64(ch.cols[ac], r))
+                                                                     : (long long)load_i64(ch.cols[ac], r);
+      bool found = false;
+      uint32_t id = __ldcg((const uint32_t*)(cold + p.mm_off[c]));
+      while (id != 0u && !found) {
+        const ulonglong2 rec = __ldcg(t.mm_log + id);
+        const uint32_t lk = (uint32_t)rec.x;
+        if (!(lk & MM_DEAD) && (long long)rec.y == v) {
+          const uint32_t old = atomicOr((uint32_t*)(t.mm_log + id), MM_DEAD);
+          if (!(old & MM_DEAD)) found = true;  // (else another retraction of the same value took this record: go on)
+        }
+        id = lk & ~MM_DEAD;
+      }
+      if (!found) {
+        if (p.strict) atomicOr(&t.status->err, AGG_ERR_MM_MISSING);
+        continue;
+      }
+      if ((long long)__ldcg(t.hot + slot * p.HW + p.KW + c) == v) atomicOr((unsigned long long*)cold, 1ull << (COLD_RECOMPUTE_SHIFT + c));
+    }
+  }
 }
 
 // ------------------------------------------------------------------ fast path: 1 x 8-byte key, no NULLs anywhere,
@@ -473,6 +552,29 @@ __global__ void __launch_bounds__(256) agg_flush_kernel(AggTable t, AggPlanDev p
       uint64_t* hot = t.hot + slot * p.HW;
       uint64_t* cold = t.cold + slot * p.CW;
       flags = cold[0] | (uint64_t)epoch_flag_mask;
+      // retractable min / max whose extreme was retracted: the first row of the materialized input in order
+      // (MaterializedInputState::get_output, minput.rs:184-245) = the extreme of the live records
+      if (flags >> COLD_RECOMPUTE_SHIFT) {
+        for (int c = 0; c < p.n_calls; c++) {
+          if (p.mm_off[c] < 0 || !((flags >> (COLD_RECOMPUTE_SHIFT + c)) & 1ull)) continue;
+          const bool is_min = p.kind[c] == RW_AGG_MIN;
+          long long best = is_min ? INT64_MAX : INT64_MIN;
+          bool any = false;
+          for (uint32_t id = (uint32_t)cold[p.mm_off[c]]; id != 0u;) {
+            const ulonglong2 rec = t.mm_log[id];
+            const uint32_t lk = (uint32_t)rec.x;
+            if (!(lk & MM_DEAD)) {
+              const long long v = (long long)rec.y;
+              best = is_min ? (v < best ? v : best) : (v > best ? v : best);
+              any = true;
+            }
+            id = lk & ~MM_DEAD;
+          }
+          hot[p.KW + c] = (uint64_t)best;
+          if (!any) flags &= ~(1ull << c);  // empty input: the output is NULL
+        }
+        flags &= (1ull << COLD_RECOMPUTE_SHIFT) - 1;
+      }
       // row_count_of (agg_group.rs:55-79)
       long long rc = (long long)hot[p.KW + p.row_count_call];
       if (rc < 0) {
@@ -483,6 +585,7 @@ __global__ void __launch_bounds__(256) agg_flush_kernel(AggTable t, AggPlanDev p
         for (int c = 0; c < p.n_calls; c++) {
           hot[p.KW + c] = state_init(p.kind[c], p.arg_type[c]);
           if (p.hi_off[c] >= 0) cold[p.hi_off[c]] = 0;
+          if (p.mm_off[c] >= 0) cold[p.mm_off[c]] = 0;  // (a group without rows has no live value: drop the dead chain)
         }
         flags &= ~0xFFFFull;
       }
@@ -698,6 +801,10 @@ struct rwgpu_agg {
   uint64_t launches = 0;
   KernelProf prof;
   bool fast_eligible = false;
+  // retractable min / max: log of input values (grows; ids start at 1)
+  int n_retract = 0;
+  DevBuf mm_log, mm_next;
+  uint64_t mm_cap = 0, mm_upper = 1;
   // staging (host pushes)
   AggStage stage[2];
   int cur = 0;
@@ -737,6 +844,9 @@ struct rwgpu_agg {
     t.dirty_list = dirty_list.as<uint32_t>();
     t.status = status.as<AggStatus>();
     t.cap = cap;
+    t.mm_log = mm_log.as<ulonglong2>();
+    t.mm_next = mm_next.as<unsigned long long>();
+    t.mm_cap = mm_cap;
     return t;
   }
   ~rwgpu_agg() {
@@ -838,7 +948,28 @@ static int agg_apply_dev(rwgpu_agg* h, const DevChunk& ch, cudaStream_t st) {
   rc = agg_order(h, st);
   if (rc != RW_OK) return rc;
   h->rows_total += (uint64_t)ch.n;
-  bool has_nulls = false;
+  if (h->n_retract) {
+    // every non-NULL input value of a retractable min / max call takes a record
+    const uint64_t need = h->mm_upper + (uint64_t)ch.n * (uint64_t)h->n_retract;
+    if (need > h->mm_cap) {
+      RW_CUDA(cudaDeviceSynchronize());
+      unsigned long long used = 1;
+      RW_CUDA(cudaMemcpy(&used, h->mm_next.p, 8, cudaMemcpyDeviceToHost));
+      h->mm_upper = used;  // (NULL arguments and retractions took none)
+      const uint64_t need2 = used + (uint64_t)ch.n * (uint64_t)h->n_retract;
+      if (need2 > h->mm_cap) {
+        uint64_t ncap = std::max<uint64_t>(h->mm_cap * 2, need2 + need2 / 2);
+        if (ncap >= 0x7ffffff0ull) return fail(RW_ERR_OOM, "materialized input of retractable min/max exceeds 2^31 values");
+        DevBuf nl;
+        RW_CUDA(nl.reserve((size_t)ncap * 16));
+        RW_CUDA(cudaMemcpy(nl.p, h->mm_log.p, (size_t)used * 16, cudaMemcpyDeviceToDevice));
+        h->mm_log = std::move(nl);
+        h->mm_cap = ncap;
+      }
+    }
+    h->mm_upper += (uint64_t)ch.n * (uint64_t)h->n_retract;
+  }
+  bool has_nulls = h->n_retract > 0;  // retractable min / max keeps its "state is non-NULL" flags per row
   for (int c : h->used_cols) if (ch.cols[c].valid_bits || ch.cols[c].valid_bytes) has_nulls = true;
   if (has_nulls) {
     if (!h->per_row_mode && h->nullfree_push_seen) {
@@ -866,6 +997,11 @@ static int agg_apply_dev(rwgpu_agg* h, const DevChunk& ch, cudaStream_t st) {
   h->prof.end(st);
   RW_CUDA(cudaGetLastError());
   h->launches++;
+  if (h->n_retract) {
+    agg_mm_delete_kernel<<<grid_for(ch.n, 256), 256, 0, st>>>(t, h->plan, ch);
+    RW_CUDA(cudaGetLastError());
+    h->launches++;
+  }
   h->groups_upper += (uint64_t)ch.n;
   h->epoch_rows += (uint64_t)ch.n;
   return RW_OK;
@@ -935,12 +1071,14 @@ static const char* agg_err_msg(unsigned int e) {
   if (e & AGG_ERR_OVERFLOW) return "Numeric out of range";
   if (e & AGG_ERR_NEG_COUNT) return "row count should be non-negative";
   if (e & AGG_ERR_RETRACT_APPEND_ONLY) return "attempt to retract on append-only min/max";
+  if (e & AGG_ERR_MM_MISSING) return "retracting a value that is not in the aggregate's materialized input";
+  if (e & AGG_ERR_MM_CAPACITY) return "internal: materialized-input log capacity";
   if (e & AGG_ERR_OUT_CAPACITY) return "internal: output capacity";
   return "unknown";
 }
 static int agg_err_code(unsigned int e) {
   if (e & AGG_ERR_OVERFLOW) return RW_ERR_NUMERIC_OUT_OF_RANGE;
-  if (e & (AGG_ERR_NEG_COUNT | AGG_ERR_RETRACT_APPEND_ONLY)) return RW_ERR_INCONSISTENT;
+  if (e & (AGG_ERR_NEG_COUNT | AGG_ERR_RETRACT_APPEND_ONLY | AGG_ERR_MM_MISSING)) return RW_ERR_INCONSISTENT;
   return RW_ERR_CUDA;
 }
 
@@ -1087,6 +1225,7 @@ int32_t rwgpu_agg_create(const rw_agg_desc* d, rwgpu_agg** out) {
     p.ret_type[c] = call.ret_type;
     p.hi_off[c] = -1;
     p.prevhi_off[c] = -1;
+    p.mm_off[c] = -1;
     int at = 0;
     if (call.arg_col >= 0) {
       if (call.arg_col >= d->n_input_cols) return fail(RW_ERR_INVALID, "agg arg index");
@@ -1116,11 +1255,16 @@ int32_t rwgpu_agg_create(const rw_agg_desc* d, rwgpu_agg** out) {
         break;
       case RW_AGG_MIN:
       case RW_AGG_MAX:
-        // retractable min/max is a MaterializedInput state (agg_state.rs:49-56): CPU executor
-        if (!d->is_append_only) return fail(RW_ERR_UNSUPPORTED, "retractable min/max uses MaterializedInput state");
         if (call.arg_col < 0 || at == RW_T_DECIMAL) return fail(RW_ERR_UNSUPPORTED, "min/max over this type");
         if (call.ret_type != at) return fail(RW_ERR_INVALID, "min/max returns the argument type");
         if (type_width(at) != 8 || type_is_float(at)) fast = false;
+        if (!d->is_append_only) {
+          // retractable min/max is a MaterializedInput state (agg_state.rs:49-56, minput.rs): the call's input values
+          // are kept as a chained multiset in HBM, the chain head in a cold word of the group
+          p.mm_off[c] = cw++;
+          h->n_retract++;
+          fast = false;
+        }
         h->all_flag_mask |= 1u << c;
         break;
       default:
@@ -1149,6 +1293,16 @@ int32_t rwgpu_agg_create(const rw_agg_desc* d, rwgpu_agg** out) {
   RW_CUDA(cudaMemsetAsync(h->status.p, 0, sizeof(AggStatus), h->stream));
   RW_CUDA(h->out_hasnull.reserve(sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS)));
   RW_CUDA(cudaMemsetAsync(h->out_hasnull.p, 0, sizeof(unsigned int) * (RW_MAX_KEYS + RW_MAX_CALLS), h->stream));
+  RW_CUDA(h->mm_next.reserve(8));
+  {
+    const unsigned long long one = 1;  // record ids start at 1 (0 terminates a chain)
+    RW_CUDA(cudaMemcpyAsync(h->mm_next.p, &one, 8, cudaMemcpyHostToDevice, h->stream));
+    RW_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  if (h->n_retract) {
+    h->mm_cap = std::max<uint64_t>(1 << 16, d->group_capacity_hint * 4);
+    RW_CUDA(h->mm_log.reserve((size_t)h->mm_cap * 16));
+  }
   RW_CUDA(h->status_host.reserve(512));
   memset(h->status_host.p, 0, 512);
   rc = agg_init_table(h, h->table());

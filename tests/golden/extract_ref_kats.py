@@ -162,7 +162,7 @@ def extract_hash_agg():
                              "append_only": append_only, "row_count_index": 0},
                      steps=steps, expected=expected, sorted=True)
         if "min:int8" in "".join(calls) and not append_only:
-            entry["gpu_scope"] = False  # retractable min => MaterializedInput, CPU fallback
+            entry["retractable_min"] = True  # MaterializedInput state (minput.rs); offloaded since round 2
         out.append(entry)
     return out
 

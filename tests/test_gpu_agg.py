@@ -12,7 +12,7 @@ from helpers import load_golden, make_agg, rand_chunk, run_agg_kat
 
 pytestmark = pytest.mark.gpu
 
-AGG_KATS = [k for k in load_golden("hash_agg_kats.json") if "skipped" not in k and k.get("gpu_scope", True)]
+AGG_KATS = [k for k in load_golden("hash_agg_kats.json") if "skipped" not in k]  # incl. test_hash_agg_min (retractable min)
 
 
 @pytest.mark.parametrize("kat", AGG_KATS, ids=[k["name"] for k in AGG_KATS])
@@ -20,11 +20,61 @@ def test_hash_agg_golden(cuda, kat):
     run_agg_kat(cuda, kat)
 
 
-def test_retractable_min_unsupported(cuda):
-    kat = [k for k in load_golden("hash_agg_kats.json") if k.get("gpu_scope") is False][0]
+def test_retractable_min_max_random_streams(cuda, oracle):
+    """retractable min / max (AggState::MaterializedInput, agg_state.rs:49-56 / minput.rs) on the device: inserts,
+    retractions of arbitrary stored values (incl. the current extreme and duplicates of it), NULL arguments, float
+    arguments, groups that empty out and come back, several barriers -- vs the oracle's multiset restatement."""
+    cfgs = [
+        {"schema": "III", "group_keys": [0], "agg_calls": ["(count:int8)", "(min:int8 $1:int8)", "(max:int8 $2:int8)", "(sum:int8 $1:int8)"],
+         "append_only": False, "row_count_index": 0},
+        {"schema": "IFi", "group_keys": [0], "agg_calls": ["(count:int8)", "(max:float8 $1:float8)", "(min:int4 $2:int4)"],
+         "append_only": False, "row_count_index": 0},
+        {"schema": "IiI", "group_keys": [0, 1], "agg_calls": ["(count:int8)", "(max:int8 $2:int8)"], "append_only": False, "row_count_index": 0},
+    ]
+    TY = {"I": abi.T_INT64, "i": abi.T_INT32, "F": abi.T_FLOAT64}
+    for ci, cfg in enumerate(cfgs):
+        types = [TY[ch] for ch in cfg["schema"]]
+        (_, ex_g), (_, ex_o) = make_agg(cuda, cfg), make_agg(oracle, cfg)
+        rng = np.random.default_rng(90 + ci)
+        live = []  # rows currently in the input
+        store_g, store_o = Store(len(cfg["group_keys"])), Store(len(cfg["group_keys"]))
+        for epoch in range(8):
+            for _ in range(3):
+                rows = []
+                n = int(rng.integers(50, 400))
+                while len(rows) < n:
+                    if live and rng.random() < (0.6 if epoch % 3 == 2 else 0.3):
+                        rows.append((abi.OP_DELETE, live.pop(int(rng.integers(len(live))))))
+                    else:
+                        row = []
+                        for k, t in enumerate(types):
+                            hi = 6 if k in cfg["group_keys"] else 12  # few distinct values: duplicates of the extreme
+                            v = None if (k not in cfg["group_keys"] and rng.random() < 0.1) else int(rng.integers(0, hi))
+                            if t == abi.T_FLOAT64 and v is not None:
+                                v = v / 4 - 1.0
+                            row.append(v)
+                        row = tuple(row)
+                        rows.append((abi.OP_INSERT, row))
+                        live.append(row)
+                ch = StreamChunk.from_rows(types, rows)
+                ex_g.apply_chunk(ch)
+                ex_o.apply_chunk(ch)
+            g, o = ex_g.flush_data(epoch + 1), ex_o.flush_data(epoch + 1)
+            store_g.apply(g)
+            store_o.apply(o)
+            assert store_g.rows == store_o.rows, f"cfg {ci} epoch {epoch}"
+            assert net_multiset(g) == net_multiset(o), f"cfg {ci} epoch {epoch}"
+
+
+def test_retracting_a_value_that_was_never_inserted_is_inconsistent(cuda):
+    cfg = {"schema": "II", "group_keys": [0], "agg_calls": ["(count:int8)", "(min:int8 $1:int8)"], "append_only": False, "row_count_index": 0}
+    _, ex = make_agg(cuda, cfg)
+    ex.apply_chunk(StreamChunk.from_pretty(" I I\n + 1 5\n + 1 7"))
+    ex.flush_data(1)
+    ex.apply_chunk(StreamChunk.from_pretty(" I I\n - 1 6"))
     with pytest.raises(abi.RwError) as e:
-        run_agg_kat(cuda, kat)
-    assert e.value.code == abi.RW_ERR_UNSUPPORTED
+        ex.flush_data(2)
+    assert e.value.code == abi.RW_ERR_INCONSISTENT
 
 
 class Store:

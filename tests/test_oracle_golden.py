@@ -36,17 +36,10 @@ def test_hash_join_golden(oracle, kat):
     run_join_kat(oracle, kat, exact=True)
 
 
-@pytest.mark.parametrize("kat", [k for k in AGG_KATS if k.get("gpu_scope", True)],
-                         ids=[k["name"] for k in AGG_KATS if k.get("gpu_scope", True)])
+@pytest.mark.parametrize("kat", AGG_KATS, ids=[k["name"] for k in AGG_KATS])
 def test_hash_agg_golden(oracle, kat):
+    """incl. test_hash_agg_min (hash_agg.rs:97-170): retractable min = MaterializedInput state (minput.rs)"""
     run_agg_kat(oracle, kat)
-
-
-def test_hash_agg_retractable_min_is_unsupported(oracle):
-    kat = [k for k in AGG_KATS if not k.get("gpu_scope", True)][0]
-    with pytest.raises(abi.RwError) as e:
-        run_agg_kat(oracle, kat)
-    assert e.value.code == abi.RW_ERR_UNSUPPORTED
 
 
 def _expected_value(expr):
