@@ -1437,6 +1437,88 @@ static inline size_t align_up_j(size_t x, size_t a) { return (x + a - 1) / a * a
 
 #include "join_uni.cuh"
 
+// =============================================================================== eliminate_adjacent_noop_update
+// StreamChunk::eliminate_adjacent_noop_update (src/common/src/array/stream_chunk.rs:331-392), applied by
+// JoinChunkBuilder::post_process to every chunk the join yields: walking the visible rows of a chunk, a Delete-then-
+// Insert (or Insert-then-Delete) pair of EQUAL rows is hidden, and the walk restarts after the pair.  In a maximal run
+// of consecutive such pairs  e1 e2 e3 ...  (edges between neighbouring visible rows) the greedy walk therefore takes
+// e1, e3, e5 ...: an edge is taken iff the number of eligible edges directly before it is even -- which every row can
+// decide for itself.  Chunks are the `chunk_size`-row cuts of the device output (rwgpu_out::finalize cuts there).
+namespace rw {
+struct NoopScratch {
+  int32_t* nxt;   // next visible row inside the chunk, -1 if none
+  int32_t* prv;   // previous visible row inside the chunk, -1 if none
+  uint8_t* elig;  // the edge (row, nxt[row]) is an eliminable pair
+};
+
+__device__ __forceinline__ bool out_rows_equal(const JoinOutDev& o, const JoinPlanDev* p, int64_t a, int64_t b) {
+  for (int k = 0; k < p->n_out; k++) {
+    const bool na = o.valid[k][a] == 0, nb = o.valid[k][b] == 0;
+    if (na != nb) return false;
+    if (na) continue;
+    const int w = p->out_width[k];
+    const uint8_t* x = (const uint8_t*)o.col[k] + a * w;
+    const uint8_t* y = (const uint8_t*)o.col[k] + b * w;
+    switch (w) {
+      case 1: if (*x != *y) return false; break;
+      case 2: if (*(const uint16_t*)x != *(const uint16_t*)y) return false; break;
+      case 4: if (*(const uint32_t*)x != *(const uint32_t*)y) return false; break;
+      case 8: if (*(const uint64_t*)x != *(const uint64_t*)y) return false; break;
+      default: if (((const uint64_t*)x)[0] != ((const uint64_t*)y)[0] || ((const uint64_t*)x)[1] != ((const uint64_t*)y)[1]) return false; break;
+    }
+  }
+  return true;
+}
+
+__global__ void noop_edges_kernel(JoinOutDev o, const JoinPlanDev* __restrict__ p, int64_t n, int chunk_size, NoopScratch sc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    sc.elig[i] = 0;
+    sc.nxt[i] = -1;
+    if (!o.vis[i]) continue;
+    int64_t end = (i / chunk_size + 1) * (int64_t)chunk_size;
+    if (end > n) end = n;
+    int64_t j = i + 1;
+    while (j < end && !o.vis[j]) j++;
+    if (j >= end) continue;
+    sc.nxt[i] = (int32_t)j;
+    const uint8_t a = o.ops[i], b = o.ops[j];
+    const bool a_del = a == RW_OP_DELETE || a == RW_OP_UPDATE_DELETE, b_del = b == RW_OP_DELETE || b == RW_OP_UPDATE_DELETE;
+    if (a_del != b_del && out_rows_equal(o, p, i, j)) sc.elig[i] = 1;
+  }
+}
+__global__ void noop_prev_kernel(int64_t n, int chunk_size, NoopScratch sc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (i % chunk_size == 0 || sc.nxt[i] < 0) { /* filled below by the predecessor, or none */ }
+    const int32_t j = sc.nxt[i];
+    if (j >= 0) sc.prv[j] = (int32_t)i;
+  }
+}
+__global__ void noop_take_kernel(JoinOutDev o, int64_t n, NoopScratch sc, unsigned int* hid) {
+  bool any = false;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!sc.elig[i]) continue;
+    int before = 0;  // eligible edges directly before this one
+    for (int32_t q = sc.prv[i]; q >= 0 && sc.elig[q]; q = sc.prv[q]) before++;
+    if (before & 1) continue;
+    o.vis[i] = 0;
+    o.vis[sc.nxt[i]] = 0;
+    any = true;
+  }
+  if (any) *hid = 1u;
+}
+// "Normalize update pairs that became partially invisible" (stream_chunk.rs:377-389)
+__global__ void noop_normalize_kernel(JoinOutDev o, int64_t n, int chunk_size) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i + 1 < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if ((i + 1) % chunk_size == 0) continue;  // the pair would straddle two chunks
+    if (o.ops[i] == RW_OP_UPDATE_DELETE && o.ops[i + 1] == RW_OP_UPDATE_INSERT) {
+      const bool dv = o.vis[i] != 0, iv = o.vis[i + 1] != 0;
+      if (dv && !iv) o.ops[i] = RW_OP_DELETE;
+      else if (!dv && iv) o.ops[i + 1] = RW_OP_INSERT;
+    }
+  }
+}
+}  // namespace rw
+
 // =============================================================================== host handle
 using namespace rw;
 
@@ -1519,6 +1601,10 @@ struct rwgpu_join {
   PinnedBuf up_host;
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
   std::vector<rw_column> dev_view_cols[2];  // per output set
+  DevBuf noop_nxt, noop_prv, noop_elig, noop_flag;  // eliminate_adjacent_noop_update scratch
+  int64_t noop_cap = 0;
+  bool call_had_deletes = false;            // some push of the current API call saw visible Delete / UpdateDelete rows
+  bool call_vis_stale = false;              // the scan-based kernel compacts its output and never writes vis bytes
   ~rwgpu_join() {
     for (auto e : ev_h2d) if (e) cudaEventDestroy(e);
     for (auto e : ev_main) if (e) cudaEventDestroy(e);
@@ -1924,6 +2010,7 @@ static int uni_finish(rwgpu_join* h, const JoinPending& pd, int64_t* out_rows, u
   h->call_null_mask |= hs.null_mask;
   *null_mask = h->call_null_mask;
   h->os().valid_dirty |= hs.null_mask & ((1ull << 63) - 1);
+  if (hs.n_del) h->call_had_deletes = true;
   return RW_OK;
 }
 
@@ -2031,6 +2118,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream
       rc = join_read_status(h, st, &hs, 3, tag);
       if (rc != RW_OK) return rc;
       const uint64_t stored = hs.n_store, keys = hs.n_keys[S];
+      if (hs.n_del) h->call_had_deletes = true;
       unsigned int err = hs.err;
       if (hs.err & JERR_OUT_CAPACITY) {
         // the extra-match area overflowed: redo the (state-free) probe + emit with room for every row
@@ -2059,6 +2147,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream
       rc = join_ensure_out(h, out_base + std::max<int64_t>(2 * n, 4096), st, out_base);
       if (rc != RW_OK) return rc;
       h->out_rows_cumulative = true;
+      h->call_vis_stale = true;
       const int64_t tiles = (n + JF_BLOCK * JF_R - 1) / (JF_BLOCK * JF_R);
       const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, 148 * 8));
       h->prof.begin(st);
@@ -2071,6 +2160,7 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream
       rc = join_read_status(h, st, &hs);
       if (rc != RW_OK) return rc;
       const uint64_t stored = hs.n_store, keys = hs.n_keys[S];
+      if (hs.n_del) h->call_had_deletes = true;
       unsigned int err = hs.err;
       while (hs.err & JERR_OUT_CAPACITY) {
         // the reservation overflowed: redo the (state-free) probe + emit with room for every row
@@ -2141,9 +2231,45 @@ static int join_push_dev(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream
     if (rc != RW_OK) return rc;
     *out_rows = reserved;
   }
+  if (!h->fast_inner) h->call_had_deletes = true;  // outer / semi / anti joins emit Delete rows for Insert inputs too
   h->call_null_mask |= hs.null_mask;  // the device copy restarts from zero after every read-back
   *null_mask = h->call_null_mask;
   h->os().valid_dirty |= hs.null_mask & ((1ull << 63) - 1);
+  return RW_OK;
+}
+
+// eliminate_adjacent_noop_update over the first n rows of the current output set (device).  The positional kernels
+// write vis bytes for every row; the scan-based kernel leaves them untouched, hence `vis_valid`.
+static int join_eliminate_noop(rwgpu_join* h, int64_t n, bool vis_valid, cudaStream_t st, bool* hid_rows) {
+  *hid_rows = false;
+  if (n < 2) return RW_OK;
+  if (n > h->noop_cap) {
+    RW_CUDA(cudaStreamSynchronize(st));
+    const int64_t cap = n + n / 4;
+    RW_CUDA(h->noop_nxt.reserve((size_t)cap * 4));
+    RW_CUDA(h->noop_prv.reserve((size_t)cap * 4));
+    RW_CUDA(h->noop_elig.reserve((size_t)cap));
+    RW_CUDA(h->noop_flag.reserve(8));
+    h->noop_cap = cap;
+  }
+  RW_CUDA(cudaMemsetAsync(h->noop_flag.p, 0, 4, st));
+  if (!vis_valid) RW_CUDA(cudaMemsetAsync(h->os().out_vis.p, 1, (size_t)n, st));
+  NoopScratch sc;
+  sc.nxt = h->noop_nxt.as<int32_t>();
+  sc.prv = h->noop_prv.as<int32_t>();
+  sc.elig = h->noop_elig.as<uint8_t>();
+  RW_CUDA(cudaMemsetAsync(sc.prv, 0xff, (size_t)n * 4, st));
+  const int g = jgrid(n, 256);
+  noop_edges_kernel<<<g, 256, 0, st>>>(out_dev(h), h->plan_dev.as<JoinPlanDev>(), n, h->chunk_size, sc);
+  noop_prev_kernel<<<g, 256, 0, st>>>(n, h->chunk_size, sc);
+  noop_take_kernel<<<g, 256, 0, st>>>(out_dev(h), n, sc, h->noop_flag.as<unsigned int>());
+  noop_normalize_kernel<<<g, 256, 0, st>>>(out_dev(h), n, h->chunk_size);
+  RW_CUDA(cudaGetLastError());
+  h->launches += 4;
+  unsigned int hid = 0;  // did the pass hide anything ?
+  RW_CUDA(cudaMemcpyAsync(&hid, h->noop_flag.p, 4, cudaMemcpyDeviceToHost, st));
+  RW_CUDA(cudaStreamSynchronize(st));
+  *hid_rows = hid != 0;
   return RW_OK;
 }
 
@@ -2155,6 +2281,8 @@ static int join_begin_call(rwgpu_join* h, cudaStream_t st) {
   if (h->out_rows_cumulative) RW_CUDA(cudaMemsetAsync(&ds->out_rows, 0, 8, st));  // scan-based kernel: cumulative over sub-batches
   h->out_rows_cumulative = false;
   h->call_null_mask = 0;
+  h->call_had_deletes = false;
+  h->call_vis_stale = false;
   return RW_OK;
 }
 
@@ -2351,6 +2479,17 @@ int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* c, r
   return rwgpu_join_push_device_counted(h, side, c, nullptr, view, cuda_stream);
 }
 
+// JoinChunkBuilder::post_process (join/builder.rs:166-168): eliminate_adjacent_noop_update on what the call emitted.
+// Only a call that saw Delete rows can have emitted a Delete / Insert pair.
+static int join_post_process(rwgpu_join* h, int64_t n, unsigned long long* nullm, cudaStream_t st) {
+  if (!h->call_had_deletes || n < 2) return RW_OK;
+  bool hid = false;
+  int rc = join_eliminate_noop(h, n, !h->call_vis_stale, st, &hid);
+  if (rc != RW_OK) return rc;
+  if (hid) *nullm |= 1ull << 63;
+  return RW_OK;
+}
+
 // device view of the current output set's first n rows (bitmaps are packed on `st` where NULLs / holes exist)
 static int join_fill_view(rwgpu_join* h, int64_t n, unsigned long long nullm, rw_chunk* view, cudaStream_t st) {
   std::vector<rw_column>& cols = h->dev_view_cols[h->cur];
@@ -2398,6 +2537,8 @@ int32_t rwgpu_join_push_device_counted(rwgpu_join* h, int32_t side, const rw_chu
   if (rc != RW_OK) return rc;
   rc = join_push_dev(h, side, ch, st, 0, &n, &nullm);
   if (rc != RW_OK) return rc;
+  rc = join_post_process(h, n, &nullm, st);
+  if (rc != RW_OK) return rc;
   return join_fill_view(h, n, nullm, view, st);
 }
 
@@ -2429,6 +2570,8 @@ int32_t rwgpu_join_push_device_async(rwgpu_join* h, int32_t side, const rw_chunk
     pd.sync_done = true;
     rc = join_push_dev(h, side, ch, st, 0, &pd.rows, &pd.nullm);
     if (rc != RW_OK) return rc;
+    rc = join_post_process(h, pd.rows, &pd.nullm, st);
+    if (rc != RW_OK) return rc;
   }
   h->pending[h->n_pending++] = pd;
   return RW_OK;
@@ -2445,7 +2588,10 @@ int32_t rwgpu_join_collect(rwgpu_join* h, rw_chunk* view, void* cuda_stream) {
   unsigned long long nullm = pd.nullm;
   if (!pd.sync_done) {
     h->call_null_mask = 0;
+    h->call_had_deletes = false;
     int rc = uni_finish(h, pd, &n, &nullm);
+    if (rc != RW_OK) return rc;
+    rc = join_post_process(h, n, &nullm, pd.st);
     if (rc != RW_OK) return rc;
   }
   int rc = join_fill_view(h, n, nullm, view, cuda_stream ? (cudaStream_t)cuda_stream : pd.st);
@@ -2599,6 +2745,8 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
     }
     total += rows;
   }
+  rc = join_post_process(h, total, &nullm, h->stream);
+  if (rc != RW_OK) { cudaStreamSynchronize(h->s_d2h); return rc; }
   for (size_t k = 0; k < h->out_types.size(); k++) {
     if (alias_src[k] < 0) continue;
     if (aligned && total == n) {
