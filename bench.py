@@ -950,6 +950,42 @@ def run_ours(args):
             line["secondary_retract"] = agg_leg("R")
             torch.cuda.empty_cache()
 
+        # ================================================================ leg: q1 (BASELINE configs[0], SURVEY 8(d) cfg1 plumbing)
+        if "q1" in legs and world == 1:
+            from risingwave_b200.executor import ProjectExecutor
+            from risingwave_b200.stream_chunk import Column as HCol, StreamChunk as HChunk
+            n1 = 1 << 20
+            b1 = gen_bids(n1, 0, SEED, N_BUILD)  # (auction, date_time, bidder, price)
+            cols_h = [b1[0], b1[2], b1[3], b1[1]]  # q1 order: auction, bidder, price, date_time
+            _, s1 = MockSource.channel()
+            expr = "(divide:int8 (multiply:int8 $2:int8 908:int8) 1000:int8)"
+            pe = ProjectExecutor(be, s1.into_executor(T4, []), [expr])
+            hchunk = HChunk(np.ones(n1, np.uint8), [HCol(abi.T_INT64, c) for c in cols_h])
+            pe.apply_project_exprs(hchunk)
+            t0 = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                out1 = pe.apply_project_exprs(hchunk)  # InputRef columns are passed through by pointer; one expression is computed
+            host_s = (time.perf_counter() - t0) / reps
+            dch = dchunk(to_dev(cols_h))
+            q0, q1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            device.project_device(dch, pe._exprs, pe.schema, stream)
+            q0.record(stream)
+            for _ in range(20):
+                dcols, dvalid, dnull = device.project_device(dch, pe._exprs, pe.schema, stream)
+            q1e.record(stream)
+            torch.cuda.synchronize()
+            dev_ms = q0.elapsed_time(q1e) / 20
+            want = (cols_h[2] * 908) // 1000  # prices are non-negative and small: no overflow, truncation == floor
+            ok = bool(np.array_equal(out1.columns[0].data, want) and np.array_equal(dcols[0].cpu().numpy(), want) and int(dnull.sum().item()) == 0)
+            pgbs = 17.0 * n1 / (dev_ms / 1e3) / 1e9  # 8 B read + 8 B + 1 B written per row
+            line["q1"] = {"workload": "nexmark_q1_project_cfg1: one 2^20-row chunk, Project(auction, bidder, price * 908 / 1000, date_time)",
+                          "metric": "rows/s", "value": n1 / (dev_ms / 1e3), "ms_per_chunk": dev_ms,
+                          "e2e": {"value": n1 / host_s, "unit": "rows/s", "note": "rwgpu_project with a HOST chunk: upload, kernel, download"},
+                          "verified": ok,
+                          "roofline": {"bound": "hbm", "kernel": "project_kernel", "achieved": pgbs, "peak": peak, "unit": "GB/s", "frac": pgbs / peak,
+                                       "algorithmic_bytes_per_row": 17.0, "kernel_ms_avg": dev_ms, "traffic": None}}
+
         # ================================================================ leg: chain (join -> filter -> project -> agg in HBM)
         if "chain" in legs and world == 1:
             from risingwave_b200.executor import parse_filter_expr
@@ -1124,8 +1160,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--legs", default="value,retract,hot,e2e,agg,chain,cpu",
-                    help="comma list of: value,retract,hot,e2e,agg,chain,cpu (subset for ncu runs; retract needs value)")
+    ap.add_argument("--legs", default="value,retract,hot,e2e,agg,q1,chain,cpu",
+                    help="comma list of: value,retract,hot,e2e,agg,q1,chain,cpu (subset for ncu runs; retract needs value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -366,6 +366,44 @@ int32_t rwgpu_filter_device(const rw_chunk* chunk, const rw_filter_term* terms, 
                             uint8_t* out_ops, uint64_t* out_visibility, int64_t* n_visible_dev,
                             void* cuda_stream);
 
+/* ================================================================ Project (operator chaining on the device)
+ * Replaces apply_project_exprs                   src/stream/src/executor/project/project_scalar.rs:91-108
+ * for INTEGER expressions in postfix form.  An InputRef projection needs no call at all (re-order the column
+ * pointers).  Evaluation is non-strict like the reference's (`eval_infallible`): a NULL operand, a numeric overflow
+ * (checked_add / checked_sub / checked_mul, also of the narrower result type) or a division by zero makes the ROW's
+ * value NULL, never an error.  Ops and visibility of the chunk pass through unchanged.
+ *   RW_EX_COL    push column `arg` (Int16/32/64, Date, Time, Timestamp(tz), Serial)      RW_EX_CONST  push `value`
+ *   RW_EX_ADD / SUB / MUL / DIV / MOD (b = pop, a = pop, push a op b; Rust semantics: truncating /, sign of a for %)
+ *   RW_EX_NEG    RW_EX_TUMBLE_START / RW_EX_TUMBLE_END  (a = timestamp in us, b = window in us; tumble.rs:91-112)
+ * Everything else the expression framework can evaluate stays on the CPU ProjectExecutor.                       */
+#define RW_EX_COL 1
+#define RW_EX_CONST 2
+#define RW_EX_ADD 3
+#define RW_EX_SUB 4
+#define RW_EX_MUL 5
+#define RW_EX_DIV 6
+#define RW_EX_MOD 7
+#define RW_EX_TUMBLE_START 8
+#define RW_EX_TUMBLE_END 9
+#define RW_EX_NEG 10
+typedef struct rw_expr_op {
+  int32_t op;     /* RW_EX_*                         */
+  int32_t arg;    /* RW_EX_COL: input column          */
+  int64_t value;  /* RW_EX_CONST                     */
+} rw_expr_op;
+typedef struct rw_project_expr {
+  const rw_expr_op* ops;  /* postfix program, leaves exactly one value */
+  int32_t n_ops;
+  int32_t ret_type;       /* RW_T_* (integer-typed)                    */
+} rw_project_expr;
+/* HOST chunk; out_data[e]: n_rows values of expression e; out_validity[e]: (n_rows+63)/64 words, written only when
+ * has_null[e] comes back non-zero (else every value is non-NULL).                                              */
+int32_t rwgpu_project(const rw_chunk* chunk, const rw_project_expr* exprs, int32_t n_exprs, void* const* out_data,
+                      uint64_t* const* out_validity, uint32_t* has_null);
+/* DEVICE chunk, DEVICE outputs: out_valid_bytes[e] = 1 byte per row (1 = non-NULL), has_null = DEVICE uint32[n_exprs]. */
+int32_t rwgpu_project_device(const rw_chunk* chunk, const rw_project_expr* exprs, int32_t n_exprs, void* const* out_data,
+                             uint8_t* const* out_valid_bytes, uint32_t* has_null, void* cuda_stream);
+
 /* ================================================================ misc */
 const char* rwgpu_last_error(void);
 /* 0 if a CUDA device is usable, else RW_ERR_NO_DEVICE (and every create() fails loudly). */

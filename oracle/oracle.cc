@@ -1061,3 +1061,86 @@ extern "C" int32_t rwo_agg_eval(const rw_agg_call* call, int32_t arg_type, const
   *out_f = st.f;
   return RW_OK;
 }
+
+
+// ================================================================== Project
+// apply_project_exprs (src/stream/src/executor/project/project_scalar.rs:91-108) for integer expressions in postfix
+// form (include/rwgpu.h RW_EX_*): NonStrictExpression::eval_infallible -- a NULL operand or a failed evaluation
+// (checked_add / checked_sub / checked_mul overflow: src/expr/impl/src/scalar/arithmetic_op.rs general_*; division by
+// zero; a result that does not fit the expression's integer type) makes the row's value NULL.  tumble_start:
+// src/expr/impl/src/scalar/tumble.rs:91-112 (get_window_start_with_offset, zero offset); tumble_end = start + window.
+extern "C" int32_t rwo_project(const rw_chunk* ch, const rw_project_expr* exprs, int32_t n_exprs, void* const* out_data,
+                               uint64_t* const* out_validity, uint32_t* has_null) {
+  const int64_t n = ch->n_rows;
+  auto int_type = [](int t) {
+    switch (t) {
+      case RW_T_INT16: case RW_T_INT32: case RW_T_INT64: case RW_T_DATE: case RW_T_TIME: case RW_T_TIMESTAMP: case RW_T_TIMESTAMPTZ:
+      case RW_T_SERIAL: return true;
+      default: return false;
+    }
+  };
+  if (n_exprs < 1 || n_exprs > 16) { g_err = "project: 1..16 expressions"; return RW_ERR_UNSUPPORTED; }
+  for (int e = 0; e < n_exprs; e++) {
+    const rw_project_expr& x = exprs[e];
+    if (!int_type(x.ret_type)) { g_err = "project: integer-typed expressions only"; return RW_ERR_UNSUPPORTED; }
+    has_null[e] = 0;
+    std::vector<uint64_t> valid((size_t)((n + 63) / 64), 0);
+    const int w = type_width(x.ret_type);
+    for (int64_t r = 0; r < n; r++) {
+      std::vector<i128> st;
+      bool ok = true;
+      auto window_start = [&](i128 ts, i128 win, i128* out) -> bool {
+        if (win == 0) return false;
+        i128 rem = ts % win;
+        i128 v = ts - (rem < 0 ? rem + win : rem);
+        if (v > (i128)INT64_MAX || v < (i128)INT64_MIN) return false;
+        *out = v;
+        return true;
+      };
+      for (int k = 0; k < x.n_ops && ok; k++) {
+        const rw_expr_op& op = x.ops[k];
+        if (op.op == RW_EX_COL) {
+          if (op.arg < 0 || op.arg >= ch->n_cols || !int_type(ch->columns[op.arg].type)) { g_err = "project: operand column"; return RW_ERR_UNSUPPORTED; }
+          Datum d = read_datum(ch->columns[op.arg], r);
+          if (d.null) ok = false; else st.push_back(d.i);
+        } else if (op.op == RW_EX_CONST) {
+          st.push_back((i128)op.value);
+        } else if (op.op == RW_EX_NEG) {
+          if (st.empty()) { g_err = "project: malformed expression"; return RW_ERR_INVALID; }
+          st.back() = -st.back();
+          if (st.back() > (i128)INT64_MAX) ok = false;
+        } else {
+          if (st.size() < 2) { g_err = "project: malformed expression"; return RW_ERR_INVALID; }
+          const i128 b = st.back();
+          st.pop_back();
+          const i128 a = st.back();
+          i128 v = 0;
+          switch (op.op) {
+            case RW_EX_ADD: v = a + b; break;
+            case RW_EX_SUB: v = a - b; break;
+            case RW_EX_MUL: v = a * b; break;
+            case RW_EX_DIV: if (b == 0) ok = false; else v = a / b; break;
+            case RW_EX_MOD: if (b == 0) ok = false; else v = a % b; break;
+            case RW_EX_TUMBLE_START: ok = window_start(a, b, &v); break;
+            case RW_EX_TUMBLE_END: ok = window_start(a, b, &v); v += b; break;
+            default: g_err = "project: unknown operation"; return RW_ERR_INVALID;
+          }
+          if (v > (i128)INT64_MAX || v < (i128)INT64_MIN) ok = false;  // checked i64 arithmetic
+          st.back() = v;
+        }
+      }
+      if (ok && st.size() != 1) { g_err = "project: malformed expression"; return RW_ERR_INVALID; }
+      int64_t v = ok ? (int64_t)st[0] : 0;
+      if (ok && w == 4 && (v < INT32_MIN || v > INT32_MAX)) { ok = false; v = 0; }
+      if (ok && w == 2 && (v < INT16_MIN || v > INT16_MAX)) { ok = false; v = 0; }
+      switch (w) {
+        case 2: ((int16_t*)out_data[e])[r] = (int16_t)v; break;
+        case 4: ((int32_t*)out_data[e])[r] = (int32_t)v; break;
+        default: ((int64_t*)out_data[e])[r] = v; break;
+      }
+      if (ok) valid[(size_t)(r >> 6)] |= 1ull << (r & 63); else has_null[e] = 1;
+    }
+    if (has_null[e] && out_validity[e]) memcpy(out_validity[e], valid.data(), valid.size() * 8);
+  }
+  return RW_OK;
+}

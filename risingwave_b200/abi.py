@@ -69,6 +69,17 @@ class RwFilterTerm(C.Structure):
                 ("rhs_const", C.c_int64)]
 
 
+class RwExprOp(C.Structure):
+    _fields_ = [("op", C.c_int32), ("arg", C.c_int32), ("value", C.c_int64)]
+
+
+class RwProjectExpr(C.Structure):
+    _fields_ = [("ops", C.POINTER(RwExprOp)), ("n_ops", C.c_int32), ("ret_type", C.c_int32)]
+
+
+EX_COL, EX_CONST, EX_ADD, EX_SUB, EX_MUL, EX_DIV, EX_MOD, EX_TUMBLE_START, EX_TUMBLE_END, EX_NEG = range(1, 11)
+
+
 class RwJoinSideDesc(C.Structure):
     _fields_ = [("n_cols", C.c_int32), ("types", C.POINTER(C.c_int32)),
                 ("key_indices", C.POINTER(C.c_int32)),
@@ -121,5 +132,5 @@ ABI_SYMBOLS = [
     "rwgpu_join_create", "rwgpu_join_destroy", "rwgpu_join_push", "rwgpu_join_push_device", "rwgpu_join_push_device_counted", "rwgpu_join_push_device_async", "rwgpu_join_collect",
     "rwgpu_join_barrier", "rwgpu_join_stats", "rwgpu_join_profile", "rwgpu_join_debug_set_seq", "rwgpu_join_compactions", "rwgpu_vnode_compute", "rwgpu_dispatch_rewrite_ops",
     "rwgpu_shuffle_partition_device", "rwgpu_shuffle_p2p_region_bytes",
-    "rwgpu_shuffle_partition_p2p_device", "rwgpu_shuffle_unpack_device", "rwgpu_shuffle_exchange_p2p_device", "rwgpu_filter", "rwgpu_filter_device", "rwgpu_last_error", "rwgpu_device_check", "rwgpu_version",
+    "rwgpu_shuffle_partition_p2p_device", "rwgpu_shuffle_unpack_device", "rwgpu_shuffle_exchange_p2p_device", "rwgpu_filter", "rwgpu_filter_device", "rwgpu_project", "rwgpu_project_device", "rwgpu_last_error", "rwgpu_device_check", "rwgpu_version",
 ]

@@ -132,11 +132,229 @@ static int filter_launch(const FilterPlanDev& p, const DevChunk& ch, uint8_t* ou
   return RW_OK;
 }
 
+// ------------------------------------------------------------------ Project
+// apply_project_exprs (src/stream/src/executor/project/project_scalar.rs:91-108): every output column is an expression
+// over the input chunk, evaluated NON-STRICTLY (`eval_infallible`): a row whose evaluation fails -- numeric overflow,
+// division by zero -- yields NULL, as does a NULL operand.  Ops and visibility pass through.  Offloaded expression
+// class: integer arithmetic in postfix form over integer-typed columns and constants (add / subtract / multiply /
+// divide / modulus / neg, src/expr/impl/src/scalar/arithmetic_op.rs `general_*` = checked ops) and tumble_start /
+// tumble_end over a microsecond interval (src/expr/impl/src/scalar/tumble.rs:91-112).  One thread per row and
+// expression, an 8-deep value stack in registers.  Roofline: HBM, the referenced columns in, one column out.
+#define PROJ_MAX_EXPRS 16
+#define PROJ_MAX_OPS 24
+#define PROJ_STACK 8
+struct ProjectPlanDev {
+  int n_exprs;
+  int n_ops[PROJ_MAX_EXPRS];
+  int ret_width[PROJ_MAX_EXPRS];
+  rw_expr_op ops[PROJ_MAX_EXPRS][PROJ_MAX_OPS];
+};
+struct ProjectOutDev {
+  void* data[PROJ_MAX_EXPRS];
+  uint8_t* valid[PROJ_MAX_EXPRS];  // 1 byte / row
+  unsigned int* has_null;          // per expression
+};
+
+// checked_add / checked_sub / checked_mul of i64 (true = overflow)
+__device__ __forceinline__ bool add_ovf(long long a, long long b, long long* r) {
+  *r = (long long)((unsigned long long)a + (unsigned long long)b);
+  return ((a ^ *r) & (b ^ *r)) < 0;
+}
+__device__ __forceinline__ bool sub_ovf(long long a, long long b, long long* r) {
+  *r = (long long)((unsigned long long)a - (unsigned long long)b);
+  return ((a ^ b) & (a ^ *r)) < 0;
+}
+__device__ __forceinline__ bool mul_ovf(long long a, long long b, long long* r) {
+  *r = (long long)((unsigned long long)a * (unsigned long long)b);
+  const long long hi = __mul64hi(a, b);
+  return hi != (*r >> 63);
+}
+
+__device__ __forceinline__ bool tumble_window_start(long long ts, long long w, long long* out) {
+  if (w == 0) return false;                 // checked_rem: DivisionByZero
+  if (ts == INT64_MIN && w == -1) return false;
+  const long long r = ts % w;
+  long long sub = r < 0 ? r + w : r;        // tumble.rs:101-111
+  long long res;
+  if (sub_ovf(ts, sub, &res)) return false;
+  *out = res;
+  return true;
+}
+
+__global__ void __launch_bounds__(256) project_kernel(ProjectPlanDev p, DevChunk ch, ProjectOutDev o) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
+    for (int e = 0; e < p.n_exprs; e++) {
+      long long st[PROJ_STACK];
+      int sp = 0;
+      bool ok = true;  // false: NULL (NULL operand or failed evaluation)
+      for (int k = 0; k < p.n_ops[e] && ok; k++) {
+        const rw_expr_op op = p.ops[e][k];
+        if (op.op == RW_EX_COL) {
+          const ColRef& c = ch.cols[op.arg];
+          if (col_is_null(c, r)) ok = false;
+          else st[sp++] = load_i64(c, r);
+        } else if (op.op == RW_EX_CONST) {
+          st[sp++] = op.value;
+        } else if (op.op == RW_EX_NEG) {
+          if (st[sp - 1] == INT64_MIN) ok = false; else st[sp - 1] = -st[sp - 1];
+        } else {
+          const long long b = st[--sp], a = st[sp - 1];
+          long long v = 0;
+          switch (op.op) {
+            case RW_EX_ADD: ok = !add_ovf(a, b, &v); break;
+            case RW_EX_SUB: ok = !sub_ovf(a, b, &v); break;
+            case RW_EX_MUL: ok = !mul_ovf(a, b, &v); break;
+            case RW_EX_DIV: ok = b != 0 && !(a == INT64_MIN && b == -1); if (ok) v = a / b; break;
+            case RW_EX_MOD: ok = b != 0; if (ok) v = (b == -1) ? 0 : a % b; break;
+            case RW_EX_TUMBLE_START: ok = tumble_window_start(a, b, &v); break;
+            default: {  // RW_EX_TUMBLE_END = window start + window size
+              long long s0;
+              ok = tumble_window_start(a, b, &s0) && !add_ovf(s0, b, &v);
+              break;
+            }
+          }
+          st[sp - 1] = v;
+        }
+      }
+      long long v = ok ? st[0] : 0;
+      const int w = p.ret_width[e];
+      if (ok && w < 8) {  // the expression's own width: a result outside it is the overflow of the narrower checked op
+        const long long lo = w == 4 ? (long long)INT32_MIN : (long long)INT16_MIN, hi = w == 4 ? (long long)INT32_MAX : (long long)INT16_MAX;
+        if (v < lo || v > hi) { ok = false; v = 0; }
+      }
+      switch (w) {
+        case 2: ((int16_t*)o.data[e])[r] = (int16_t)v; break;
+        case 4: ((int32_t*)o.data[e])[r] = (int32_t)v; break;
+        default: ((long long*)o.data[e])[r] = v; break;
+      }
+      o.valid[e][r] = ok ? 1 : 0;
+      if (!ok) o.has_null[e] = 1u;
+    }
+  }
+}
+
+static bool proj_int_type(int t) {
+  switch (t) {
+    case RW_T_INT16: case RW_T_INT32: case RW_T_INT64: case RW_T_DATE: case RW_T_TIME: case RW_T_TIMESTAMP: case RW_T_TIMESTAMPTZ:
+    case RW_T_SERIAL: return true;
+    default: return false;
+  }
+}
+
+static int project_plan(const rw_chunk* c, const rw_project_expr* exprs, int32_t n_exprs, ProjectPlanDev* p) {
+  if (n_exprs < 1 || n_exprs > PROJ_MAX_EXPRS) return fail(RW_ERR_UNSUPPORTED, "project: 1..16 expressions");
+  p->n_exprs = n_exprs;
+  for (int e = 0; e < n_exprs; e++) {
+    const rw_project_expr& x = exprs[e];
+    if (!x.ops || x.n_ops < 1 || x.n_ops > PROJ_MAX_OPS) return fail(RW_ERR_UNSUPPORTED, "project: 1..24 postfix operations per expression");
+    if (!proj_int_type(x.ret_type)) return fail(RW_ERR_UNSUPPORTED, "project: only integer-typed expressions are evaluated on the device");
+    p->n_ops[e] = x.n_ops;
+    p->ret_width[e] = type_width(x.ret_type);
+    int depth = 0;
+    for (int k = 0; k < x.n_ops; k++) {
+      const rw_expr_op& op = x.ops[k];
+      if (op.op == RW_EX_COL) {
+        if (op.arg < 0 || op.arg >= c->n_cols || !proj_int_type(c->columns[op.arg].type))
+          return fail(RW_ERR_UNSUPPORTED, "project: operand column must be integer-typed");
+        depth++;
+      } else if (op.op == RW_EX_CONST) {
+        depth++;
+      } else if (op.op == RW_EX_NEG) {
+        if (depth < 1) return fail(RW_ERR_INVALID, "project: malformed postfix expression");
+      } else if (op.op >= RW_EX_ADD && op.op <= RW_EX_TUMBLE_END) {
+        if (depth < 2) return fail(RW_ERR_INVALID, "project: malformed postfix expression");
+        depth--;
+      } else {
+        return fail(RW_ERR_INVALID, "project: unknown operation");
+      }
+      if (depth > PROJ_STACK) return fail(RW_ERR_UNSUPPORTED, "project: expression too deep");
+      p->ops[e][k] = op;
+    }
+    if (depth != 1) return fail(RW_ERR_INVALID, "project: malformed postfix expression");
+  }
+  return RW_OK;
+}
+
 }  // namespace rw
 
 using namespace rw;
 
 extern "C" {
+
+int32_t rwgpu_project_device(const rw_chunk* c, const rw_project_expr* exprs, int32_t n_exprs, void* const* out_data,
+                             uint8_t* const* out_valid_bytes, uint32_t* has_null, void* cuda_stream) {
+  if (!c || !exprs || !out_data || !out_valid_bytes || !has_null) return fail(RW_ERR_INVALID, "null");
+  ProjectPlanDev p;
+  int rc = project_plan(c, exprs, n_exprs, &p);
+  if (rc != RW_OK) return rc;
+  DevChunk ch;
+  rc = devchunk_from_abi(c, &ch);
+  if (rc != RW_OK) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  RW_CUDA(cudaMemsetAsync(has_null, 0, sizeof(uint32_t) * n_exprs, st));
+  if (ch.n == 0) return RW_OK;
+  ProjectOutDev o;
+  memset(&o, 0, sizeof(o));
+  for (int e = 0; e < n_exprs; e++) { o.data[e] = out_data[e]; o.valid[e] = out_valid_bytes[e]; }
+  o.has_null = has_null;
+  const int64_t blocks = (ch.n + 255) / 256;
+  project_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>(blocks, 148 * 8)), 256, 0, st>>>(p, ch, o);
+  RW_CUDA(cudaGetLastError());
+  return RW_OK;
+}
+
+int32_t rwgpu_project(const rw_chunk* c, const rw_project_expr* exprs, int32_t n_exprs, void* const* out_data,
+                      uint64_t* const* out_validity, uint32_t* has_null) {
+  if (!c || !exprs || !out_data || !out_validity || !has_null) return fail(RW_ERR_INVALID, "null");
+  int rc = rwgpu_device_check();
+  if (rc != RW_OK) return rc;
+  ProjectPlanDev p;
+  rc = project_plan(c, exprs, n_exprs, &p);
+  if (rc != RW_OK) return rc;
+  const int64_t n = c->n_rows;
+  for (int e = 0; e < n_exprs; e++) has_null[e] = 0;
+  if (n == 0) return RW_OK;
+  DevBuf in, out;
+  DevChunk ch;
+  rc = upload_chunk(c, in, &ch, 0);
+  if (rc != RW_OK) return rc;
+  // device outputs: per expression data | valid bytes | packed validity words; then the has_null flags
+  const size_t nw = (size_t)((n + 63) / 64) * 8;
+  size_t off = 0;
+  auto region = [&](size_t bytes) { size_t o0 = (off + 255) / 256 * 256; off = o0 + bytes; return o0; };
+  size_t o_data[PROJ_MAX_EXPRS], o_valid[PROJ_MAX_EXPRS], o_bits[PROJ_MAX_EXPRS];
+  for (int e = 0; e < n_exprs; e++) {
+    o_data[e] = region((size_t)n * p.ret_width[e]);
+    o_valid[e] = region((size_t)n);
+    o_bits[e] = region(nw);
+  }
+  const size_t o_flags = region(sizeof(uint32_t) * PROJ_MAX_EXPRS);
+  RW_CUDA(out.reserve(off + 256));
+  uint8_t* d = out.as<uint8_t>();
+  void* dd[PROJ_MAX_EXPRS];
+  uint8_t* dv[PROJ_MAX_EXPRS];
+  for (int e = 0; e < n_exprs; e++) { dd[e] = d + o_data[e]; dv[e] = d + o_valid[e]; }
+  {
+    ProjectOutDev o;
+    memset(&o, 0, sizeof(o));
+    for (int e = 0; e < n_exprs; e++) { o.data[e] = dd[e]; o.valid[e] = dv[e]; }
+    o.has_null = (unsigned int*)(d + o_flags);
+    RW_CUDA(cudaMemset(d + o_flags, 0, sizeof(uint32_t) * PROJ_MAX_EXPRS));
+    const int64_t blocks = (n + 255) / 256;
+    project_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>(blocks, 148 * 8)), 256>>>(p, ch, o);
+    RW_CUDA(cudaGetLastError());
+  }
+  RW_CUDA(cudaMemcpy(has_null, d + o_flags, sizeof(uint32_t) * n_exprs, cudaMemcpyDeviceToHost));
+  for (int e = 0; e < n_exprs; e++) {
+    RW_CUDA(cudaMemcpy(out_data[e], dd[e], (size_t)n * p.ret_width[e], cudaMemcpyDeviceToHost));
+    if (has_null[e] && out_validity[e]) {
+      pack_bytes_to_bits_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>((n + 63) / 64 / 256 + 1, 148 * 8)), 256>>>(dv[e], (uint64_t*)(d + o_bits[e]), n);
+      RW_CUDA(cudaGetLastError());
+      RW_CUDA(cudaMemcpy(out_validity[e], d + o_bits[e], nw, cudaMemcpyDeviceToHost));
+    }
+  }
+  return RW_OK;
+}
 
 int32_t rwgpu_filter_device(const rw_chunk* c, const rw_filter_term* terms, int32_t n_terms, int32_t upsert, uint8_t* out_ops,
                             uint64_t* out_visibility, int64_t* n_visible_dev, void* cuda_stream) {

@@ -323,6 +323,26 @@ class P2PExchangeCall:
                                                         _stream_ptr(stream)))
 
 
+def project_device(chunk: DeviceChunk, exprs, ret_types: Sequence[int], stream: Optional[torch.cuda.Stream] = None):
+    """rwgpu_project_device: `exprs` = (abi.RwProjectExpr * m) postfix programs over the chunk's columns.
+    -> (columns, valid bytes, has_null uint32[m]) as CUDA tensors (ops / visibility of the chunk pass through)."""
+    lib = _lib()
+    if not getattr(lib, "_proj_sig", False):
+        lib.rwgpu_project_device.restype = C.c_int32
+        lib.rwgpu_project_device.argtypes = [C.POINTER(abi.RwChunk), C.POINTER(abi.RwProjectExpr), C.c_int32, C.POINTER(C.c_void_p),
+                                             C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p]
+        lib._proj_sig = True
+    n, m = chunk.n_rows(), len(ret_types)
+    cols = [torch.empty(max(n, 1), dtype=TORCH_DTYPE[t], device="cuda") for t in ret_types]
+    valid = [torch.empty(max(n, 1), dtype=torch.uint8, device="cuda") for _ in ret_types]
+    has_null = torch.zeros(m, dtype=torch.int32, device="cuda")
+    ch, keep = chunk.to_abi()
+    dptr = (C.c_void_p * m)(*[c.data_ptr() for c in cols])
+    vptr = (C.c_void_p * m)(*[v.data_ptr() for v in valid])
+    _check(lib.rwgpu_project_device(C.byref(ch), exprs, m, dptr, vptr, C.c_void_p(has_null.data_ptr()), _stream_ptr(stream)))
+    return [c[:n] for c in cols], [v[:n] for v in valid], has_null
+
+
 def filter_device(chunk_abi, n_rows: int, terms, upsert: bool = False, stream: Optional[torch.cuda.Stream] = None):
     """rwgpu_filter_device on an `abi.RwChunk` with DEVICE pointers (a DeviceChunk.to_abi()[0] or the view of a
     `*_device` call).  -> (ops uint8[n], visibility int64[(n+63)//64] packed bits, n_visible int64[1]) CUDA tensors."""

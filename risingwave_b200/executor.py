@@ -54,6 +54,8 @@ class Backend:
                                               C.POINTER(C.c_uint8)])
         f("filter", C.c_int32, [C.POINTER(abi.RwChunk), C.POINTER(abi.RwFilterTerm), C.c_int32, C.c_int32, C.POINTER(C.c_uint8),
                                 C.POINTER(C.c_uint64), C.POINTER(C.c_int64)])
+        f("project", C.c_int32, [C.POINTER(abi.RwChunk), C.POINTER(abi.RwProjectExpr), C.c_int32, C.POINTER(C.c_void_p),
+                                 C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)])
         f("last_error", C.c_char_p, [])
 
     @staticmethod
@@ -463,6 +465,101 @@ def parse_filter_expr(text: str) -> List[Tuple[int, int, int, int]]:
     if m.group(3) is not None:
         return [(_CMP[m.group(1)], int(m.group(2)), int(m.group(3)), 0)]
     return [(_CMP[m.group(1)], int(m.group(2)), -1, int(m.group(4)))]
+
+
+_EX_BIN = {"add": abi.EX_ADD, "subtract": abi.EX_SUB, "multiply": abi.EX_MUL, "divide": abi.EX_DIV, "modulus": abi.EX_MOD,
+           "tumble_start": abi.EX_TUMBLE_START, "tumble_end": abi.EX_TUMBLE_END}
+_EX_TYPES = {"int2": abi.T_INT16, "int4": abi.T_INT32, "int8": abi.T_INT64, "date": abi.T_DATE, "time": abi.T_TIME,
+             "timestamp": abi.T_TIMESTAMP, "timestamptz": abi.T_TIMESTAMPTZ, "serial": abi.T_SERIAL}
+
+
+def parse_project_expr(text: str) -> Tuple[List[Tuple[int, int, int]], int]:
+    """build_from_pretty subset -> (postfix program [(op, arg, value)], return type): `$1:int8`, `42:int8`,
+    `(add:int8 $0:int8 $1:int8)`, `(divide:int8 (multiply:int8 $2:int8 908:int8) 1000:int8)`, `(neg:int8 $0:int8)`,
+    `(tumble_start:timestamptz $3:timestamptz 10000000:int8)` (the interval in microseconds)."""
+    toks = re.findall(r"\(|\)|[^\s()]+", text)
+    pos = 0
+
+    def parse():
+        nonlocal pos
+        t = toks[pos]
+        pos += 1
+        if t == "(":
+            name, ty = toks[pos].split(":")
+            pos += 1
+            args = []
+            while toks[pos] != ")":
+                args.append(parse())
+            pos += 1
+            if ty not in _EX_TYPES:
+                raise ValueError(f"unsupported expression type in {text!r}")
+            prog = [op for a in args for op in a[0]]
+            if name == "neg" and len(args) == 1:
+                return prog + [(abi.EX_NEG, 0, 0)], _EX_TYPES[ty]
+            if name not in _EX_BIN or len(args) != 2:
+                raise ValueError(f"unsupported expression {name!r} in {text!r}")
+            return prog + [(_EX_BIN[name], 0, 0)], _EX_TYPES[ty]
+        val, ty = t.rsplit(":", 1)
+        if ty not in _EX_TYPES:
+            raise ValueError(f"unsupported expression type in {text!r}")
+        if val.startswith("$"):
+            return [(abi.EX_COL, int(val[1:]), 0)], _EX_TYPES[ty]
+        return [(abi.EX_CONST, 0, int(val))], _EX_TYPES[ty]
+
+    prog, ty = parse()
+    if pos != len(toks):
+        raise ValueError(f"trailing tokens in {text!r}")
+    return prog, ty
+
+
+class ProjectExecutor:
+    """Mirror of ProjectExecutor::new(ctx, input, exprs, ...) (project/project_scalar.rs:40-76) for the expressions the
+    device path evaluates (integer arithmetic, tumble windows); `apply_project_exprs` = :91-108."""
+
+    def __init__(self, backend: Backend, input: MockSource, exprs: Sequence[str]):
+        self.backend, self.input = backend, input
+        self._keep = []
+        self._exprs = (abi.RwProjectExpr * len(exprs))()
+        self.schema = []
+        for k, text in enumerate(exprs):
+            prog, ty = parse_project_expr(text)
+            ops = (abi.RwExprOp * len(prog))()
+            for i, (op, arg, val) in enumerate(prog):
+                ops[i].op, ops[i].arg, ops[i].value = op, arg, val
+            self._keep.append(ops)
+            self._exprs[k].ops, self._exprs[k].n_ops, self._exprs[k].ret_type = ops, len(prog), ty
+            self.schema.append(ty)
+
+    def apply_project_exprs(self, chunk: StreamChunk) -> StreamChunk:
+        from .stream_chunk import NP_DTYPE, Column
+        ch, keep = chunk.to_abi()
+        n, m = chunk.capacity(), len(self.schema)
+        data = [np.zeros(max(n, 1), dtype=NP_DTYPE[t]) for t in self.schema]
+        valid = [np.zeros(max((n + 63) // 64, 1), dtype=np.uint64) for _ in self.schema]
+        dptr = (C.c_void_p * m)(*[d.ctypes.data for d in data])
+        vptr = (C.c_void_p * m)(*[v.ctypes.data for v in valid])
+        has_null = (C.c_uint32 * m)()
+        self.backend.check(self.backend._project(C.byref(ch), self._exprs, m, dptr, vptr, has_null))
+        cols = []
+        for k, t in enumerate(self.schema):
+            v = None
+            if has_null[k]:
+                v = np.unpackbits(valid[k].view(np.uint8), bitorder="little")[:n].astype(bool)
+            cols.append(Column(t, data[k][:n].copy(), v))
+        return StreamChunk(chunk.ops.copy(), cols, chunk.vis)
+
+    def execute(self) -> MessageStream:
+        return MessageStream(self._run())
+
+    def _run(self):
+        while True:
+            m = self.input.poll()
+            if m is PENDING:
+                yield PENDING
+            elif m.chunk is not None:
+                yield Message(chunk=self.apply_project_exprs(m.chunk))
+            else:
+                yield m
 
 
 class FilterExecutor:

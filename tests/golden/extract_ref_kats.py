@@ -213,6 +213,30 @@ def extract_filter():
     return out
 
 
+# ----------------------------------------------------------------------------------- project
+def extract_project():
+    """src/stream/src/executor/project/project_scalar.rs test_projection: input chunks, the expression, expected chunks;
+    src/expr/impl/src/scalar/tumble.rs has no value tests, so tumble_* is pinned by restating :91-112 only."""
+    path = os.path.join(REF, "src/stream/src/executor/project/project_scalar.rs")
+    src = open(path).read()
+    tests_start = src.index("#[cfg(test)]")
+    src_tests = src[tests_start:]
+    line_of = lambda pos: src[: tests_start + pos].count("\n") + 1  # noqa: E731
+    out = []
+    for name, body in split_tests(src_tests):
+        if name != "test_projection":
+            continue  # the watermark tests are about watermark derivation (host side)
+        pos0 = src_tests.index("async fn " + name)
+        lits = [clean_pretty(re.sub(r"//[^\n]*", "", m.group(1)))
+                for m in re.finditer(r"StreamChunk::from_pretty\(\s*\"([^\"]*)\",?\s*\)", body)]
+        exprs = re.findall(r"build_from_pretty\(\"([^\"]+)\"\)", body)
+        n_in = len(re.findall(r"let chunk\d* = StreamChunk::from_pretty", body))
+        assert exprs and n_in >= 1 and len(lits) == 2 * n_in, name
+        out.append({"name": name, "source": f"src/stream/src/executor/project/project_scalar.rs:{line_of(pos0)}",
+                    "exprs": exprs, "inputs": lits[:n_in], "expected": lits[n_in:]})
+    return out
+
+
 # ----------------------------------------------------------------------------------- nexmark e2e fixture (q4)
 def extract_nexmark_q4():
     """e2e_test/nexmark/insert_{auction,bid}.slt.part + the expected rows of e2e_test/streaming/nexmark/q4.slt.part
@@ -291,6 +315,9 @@ def main():
     fl = extract_filter()
     json.dump(fl, open(os.path.join(OUT, "filter_kats.json"), "w"), indent=1)
     print(f"filter: {len(fl)} tests")
+    pj = extract_project()
+    json.dump(pj, open(os.path.join(OUT, "project_kats.json"), "w"), indent=1)
+    print(f"project: {len(pj)} tests")
     print(f"hash_join: {len(hj)} tests ({sum('skipped' in t for t in hj)} skipped); "
           f"hash_agg: {len(ha)}; agg funcs: {len(af)}")
 

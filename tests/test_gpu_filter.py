@@ -152,3 +152,37 @@ def test_nexmark_q8_end_to_end_fixture(cuda):
     """the reference's SQL-level q8 fixture (e2e_test/streaming/nexmark/q8.slt.part) through the CUDA operators:
     two group-by aggregates feeding a join on a three-column key"""
     run_nexmark_q8(cuda)
+
+
+# ------------------------------------------------------------------------------------------ Project (round 2)
+def test_project_golden_on_device(cuda):
+    """project_scalar.rs test_projection through rwgpu_project: exact output chunks"""
+    from test_oracle_golden import run_project_kat
+    for kat in load_golden("project_kats.json"):
+        run_project_kat(cuda, kat)
+
+
+def test_project_expressions_match_oracle(cuda, oracle):
+    """integer expressions (q1 `price * 908 / 1000`, q7 / q8 tumble windows, narrower result types) over random chunks with
+    NULLs, invisible rows and overflowing operands: non-strict evaluation, row by row identical to the oracle"""
+    from risingwave_b200.executor import MockSource, ProjectExecutor
+    types = [abi.T_INT64, abi.T_INT64, abi.T_INT32, abi.T_TIMESTAMPTZ]
+    exprs = ["(divide:int8 (multiply:int8 $0:int8 908:int8) 1000:int8)", "(tumble_start:timestamptz $3:timestamptz 10000000:int8)",
+             "(tumble_end:timestamptz $3:timestamptz 10000000:int8)", "(modulus:int8 $0:int8 $1:int8)", "(subtract:int4 $2:int4 $0:int8)",
+             "(add:int8 (multiply:int8 $0:int8 $1:int8) (neg:int8 $3:timestamptz))", "(divide:int8 $1:int8 $2:int4)"]
+    pes = []
+    for be in (cuda, oracle):
+        _, src = MockSource.channel()
+        pes.append(ProjectExecutor(be, src.into_executor(types, [0]), exprs))
+    rng = np.random.default_rng(4)
+    for n in (1, 63, 64, 65, 5000):
+        a = rng.integers(-(1 << 62), 1 << 62, n) * rng.integers(0, 3, n)  # some overflow 908x, some zero
+        b = rng.integers(-5, 6, n).astype(np.int64) * rng.integers(0, 1 << 33, n)
+        c = rng.integers(-(1 << 31), 1 << 31, n).astype(np.int32)
+        c[rng.random(n) < 0.2] = 0
+        d = rng.integers(-(1 << 50), 1 << 50, n)
+        cols = [Column(abi.T_INT64, a.astype(np.int64), rng.random(n) > 0.1), Column(abi.T_INT64, b, rng.random(n) > 0.1),
+                Column(abi.T_INT32, c, rng.random(n) > 0.1), Column(abi.T_TIMESTAMPTZ, d.astype(np.int64), None)]
+        ch = StreamChunk(rng.integers(1, 5, n).astype(np.uint8), cols, rng.random(n) > 0.05)
+        g, o = (pe.apply_project_exprs(ch) for pe in pes)
+        assert g == o, f"n={n}"

@@ -196,3 +196,66 @@ def test_group_key_null_positions_are_kept_apart(oracle):
     agg.apply_chunk(StreamChunk.from_pretty(" i i\n + 1 .\n + . 2\n + 1 .\n + . ."))
     rows = sorted((r[1] for c in agg.flush_data(1) for r in c.rows()), key=repr)
     assert rows == sorted([(1, None, 2), (None, 2, 1), (None, None, 1)], key=repr)
+
+
+# ------------------------------------------------------------------------------------------ Project
+def run_project_kat(backend, kat):
+    from risingwave_b200.executor import ProjectExecutor
+    types = [abi.T_INT64] * 2
+    _, src = MockSource.channel()
+    pe = ProjectExecutor(backend, src.into_executor(types, [0]), kat["exprs"])
+    for inp, exp in zip(kat["inputs"], kat["expected"]):
+        got = pe.apply_project_exprs(StreamChunk.from_pretty(inp))
+        assert got == StreamChunk.from_pretty(exp), f"{kat['name']}:\n got\n{got}\n want\n{exp}"
+
+
+@pytest.mark.parametrize("kat", load_golden("project_kats.json"), ids=lambda k: k["name"])
+def test_project_golden(oracle, kat):
+    """project_scalar.rs test_projection: exact output chunks"""
+    run_project_kat(oracle, kat)
+
+
+def test_project_arithmetic_is_non_strict_and_tumble_follows_the_reference_formula(oracle):
+    """eval_infallible (project_scalar.rs:98): overflow / division by zero / NULL operand -> NULL for that row only;
+    tumble_start = ts - (r < 0 ? r + w : r), r = ts rem w (tumble.rs:96-111), checked against a Python restatement"""
+    from risingwave_b200.executor import ProjectExecutor
+    types = [abi.T_INT64, abi.T_INT64, abi.T_INT32]
+    _, src = MockSource.channel()
+    exprs = ["(divide:int8 (multiply:int8 $0:int8 908:int8) 1000:int8)", "(tumble_start:int8 $0:int8 10000000:int8)",
+             "(tumble_end:int8 $0:int8 $1:int8)", "(modulus:int8 $0:int8 $1:int8)", "(subtract:int4 $2:int4 $0:int8)", "(neg:int8 $0:int8)"]
+    pe = ProjectExecutor(oracle, src.into_executor(types, [0]), exprs)
+    big = (1 << 63) - 1
+    rows = [(abi.OP_INSERT, (v, w, x)) for v, w, x in
+            [(1000, 7, 5), (-1000, 7, -5), (big, 2, 1), (-big - 1, -1, 1), (None, 3, 2), (12345678901, 0, 0), (-12345678901, 10_000_000, 2 ** 31 - 1),
+             (5, None, None), (0, 1, 0)]]
+    out = pe.apply_project_exprs(StreamChunk.from_rows(types, rows))
+    got = [r for _, r in out.rows()]
+
+    def trunc_div(a, b):
+        q = abs(a) // abs(b)
+        return q if (a < 0) == (b < 0) else -q
+
+    def i64(v):
+        return v if v is not None and -(1 << 63) <= v <= big else None
+
+    def win(ts, w):
+        if w == 0:
+            return None
+        r = ts - trunc_div(ts, w) * w
+        return i64(ts - (r + w if r < 0 else r))
+
+    for (_, (v, w, x)), g in zip(rows, got):
+        want = [None] * 6
+        if v is not None:
+            m = i64(v * 908)
+            want[0] = None if m is None else trunc_div(m, 1000)
+            want[1] = win(v, 10_000_000)
+            want[5] = i64(-v)
+            if w is not None:
+                s0 = win(v, w)
+                want[2] = None if s0 is None else i64(s0 + w)
+                want[3] = None if w == 0 else v - trunc_div(v, w) * w
+            if x is not None:
+                d = x - v
+                want[4] = d if -(1 << 31) <= d < (1 << 31) else None
+        assert list(g) == want, (v, w, x, g, want)
