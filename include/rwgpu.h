@@ -156,6 +156,20 @@ int32_t rwgpu_agg_flush_device(rwgpu_agg* h, uint64_t epoch, rw_chunk* view, voi
  * behind it on the device (event), whichever streams are used.                                                */
 int32_t rwgpu_agg_flush_device_async(rwgpu_agg* h, uint64_t epoch, void* cuda_stream);
 int32_t rwgpu_agg_flush_collect(rwgpu_agg* h, rw_chunk* view, void* cuda_stream);
+/* ---- state persistence (checkpoint / recovery).  What the reference persists per group is the INTERMEDIATE STATE row
+ * `group key | one state datum per call` (AggGroup::build_states_change, agg_group.rs:473-538; a group whose row count
+ * is 0 has no row) and, per retractable min / max call, the rows of its materialized input (minput.rs); on recovery
+ * AggGroup::create (agg_group.rs:260-316) loads the row and derives prev_outputs from it.
+ *   rwgpu_agg_snapshot: between a barrier and the next push.  `*states`: all-Insert chunks, schema = the operator's
+ *     OUTPUT schema (group key columns, then per call its state datum: count int8, sum in its return type, min / max
+ *     in the argument type; NULL = no input yet).  `*minput`: group key columns | int4 call index | int8 value (float
+ *     arguments: the IEEE-754 bits of the f64), one row per live input value of a retractable min / max (0 rows
+ *     otherwise).  The shim hands both to StateTable::write_chunk, which does the value / memcomparable encoding and
+ *     the vnode prefix (state_table.rs:1451-1560).  Release both with rwgpu_out_release.
+ *   rwgpu_agg_restore: into an idle operator; chunks of the same two schemas (HOST).  Afterwards the operator emits
+ *     exactly what the snapshotted one would.                                                                     */
+int32_t rwgpu_agg_snapshot(rwgpu_agg* h, rwgpu_out** states, rwgpu_out** minput);
+int32_t rwgpu_agg_restore(rwgpu_agg* h, const rw_chunk* states, const rw_chunk* minput);
 /* number of groups currently held / table capacity (diagnostics, join_cached_entry_count-like) */
 int32_t rwgpu_agg_stats(rwgpu_agg* h, uint64_t* n_groups, uint64_t* capacity, uint64_t* kernel_launches);
 /* device-time accounting of the dominant kernel (the fused group-by + aggregate apply kernel):
@@ -260,6 +274,16 @@ int32_t rwgpu_join_collect(rwgpu_join* h, rw_chunk* view, void* cuda_stream);
 int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t epoch);
 int32_t rwgpu_join_stats(rwgpu_join* h, uint64_t* left_rows, uint64_t* right_rows,
                          uint64_t* kernel_launches);
+/* ---- state persistence (checkpoint / recovery).  A side's persistent state is the set of its stored input rows: the
+ * reference writes every stored row to the side's StateTable (JoinHashMap::insert, join/hash_join.rs:591-625; table
+ * pk = join key | deduped input pk, stream_plan.proto:628-637), so on the write path the shim passes the INPUT chunks
+ * on to StateTable::write_chunk exactly as the CPU executor does -- nothing has to come back from the GPU.
+ *   rwgpu_join_snapshot: the live rows of `side` as all-Insert chunks in the side's input schema (for a checkpoint of
+ *     an operator that was running without a StateTable, and for moving state when vnodes are re-assigned).
+ *   rwgpu_join_restore: replays state rows (HOST chunk) as inserts with the output discarded -- restore BOTH sides;
+ *     the incremental algorithm itself re-derives the degrees of outer / semi / anti joins.                        */
+int32_t rwgpu_join_snapshot(rwgpu_join* h, int32_t side, rwgpu_out** rows);
+int32_t rwgpu_join_restore(rwgpu_join* h, int32_t side, const rw_chunk* rows);
 /* State reclamation: a delete marks the stored row dead; rwgpu_join_barrier rebuilds a side's row log from its live
  * rows once more than half of it is dead (the reference frees the entry at delete time, join/hash_join.rs:659-681).
  * -> number of such rebuilds so far (diagnostics).  State-lifetime limit: a side holds < 2^31 - 16 log rows between

@@ -760,6 +760,203 @@ __global__ void agg_rehash_kernel(AggTable o, AggTable n, AggPlanDev p) {
   if (lane_id() == 0 && kept) atomicAdd(&n.status->n_groups, (unsigned long long)kept);
 }
 
+// ------------------------------------------------------------------ state persistence
+// What the reference persists per group is the INTERMEDIATE STATE row  group key | one state datum per call
+// (AggGroup::build_states_change agg_group.rs:473-538 -> intermediate_state_table.write_record; a group whose row
+// count is 0 is deleted from the table), plus, per retractable min / max call, the rows of its materialized input
+// (minput.rs).  On recovery AggGroup::create (agg_group.rs:260-316) loads that row and derives prev_outputs from it.
+// The snapshot kernels produce exactly those rows as columnar chunks (the shim hands them to StateTable::write_chunk,
+// which does the value / memcomparable encoding and the vnode prefix); restore rebuilds the table from them.
+struct AggSnapOut {
+  void* col[RW_MAX_KEYS + RW_MAX_CALLS];
+  uint8_t* valid[RW_MAX_KEYS + RW_MAX_CALLS];
+  unsigned long long* n_rows;
+  unsigned int* has_null;  // per column
+  // materialized input: key columns | int32 call index | int64 value (sortable form decoded by the host)
+  void* mcol[RW_MAX_KEYS + 2];
+  uint8_t* mvalid[RW_MAX_KEYS];
+  unsigned long long* m_rows;
+  int64_t capacity, m_capacity;
+};
+
+__device__ __forceinline__ void snap_key(const AggTable& t, const AggPlanDev& p, uint64_t slot, const uint64_t* hot, uint64_t* keyw,
+                                         uint32_t* key_nm) {
+  *key_nm = 0;
+  if (p.single_key) {
+    if (slot == t.cap) { *key_nm = 1; keyw[0] = 0; }
+    else keyw[0] = (slot == t.cap + 1) ? AGG_EMPTY : hot[0];
+  } else {
+    *key_nm = (uint32_t)((hot[0] >> 8) & 0xff);
+    for (int k = 0; k < p.n_keys; k++) keyw[k] = hot[1 + k];
+  }
+}
+
+__global__ void __launch_bounds__(256) agg_snapshot_kernel(AggTable t, AggPlanDev p, AggSnapOut o, int count_only) {
+  const int lane = lane_id();
+  for (uint64_t s0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ull; s0 < t.cap + 2; s0 += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t slot = s0 + lane;
+    bool live = false;
+    const uint64_t* hot = nullptr;
+    const uint64_t* cold = nullptr;
+    if (slot < t.cap + 2) {
+      hot = t.hot + slot * p.HW;
+      cold = t.cold + slot * p.CW;
+      const bool occupied = slot >= t.cap ? true : (p.single_key ? hot[0] != AGG_EMPTY : hot[0] != 0ull);
+      live = occupied && (long long)hot[p.KW + p.row_count_call] > 0;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, live);
+    unsigned long long base = 0;
+    if (lane == 0 && bal) base = atomicAdd(o.n_rows, (unsigned long long)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!live) continue;
+    const int64_t row = (int64_t)base + __popc(bal & ((1u << lane) - 1u));
+    uint64_t keyw[RW_MAX_KEYS];
+    uint32_t key_nm;
+    snap_key(t, p, slot, hot, keyw, &key_nm);
+    if (!count_only && row < o.capacity) {
+      for (int k = 0; k < p.n_keys; k++) {
+        const bool nul = (key_nm >> k) & 1;
+        o.valid[k][row] = nul ? 0 : 1;
+        if (nul) o.has_null[k] = 1;
+        store_word(o.col[k], type_width_dev(p.key_type[k]), p.key_type[k], row, keyw[k]);
+      }
+      const uint64_t flags = cold[0];
+      for (int c = 0; c < p.n_calls; c++) {
+        const OutVal v = call_output(t, p, c, hot, cold, flags);  // a value state's output IS its state datum
+        const int oc = p.n_keys + c;
+        o.valid[oc][row] = v.null ? 0 : 1;
+        if (v.null) o.has_null[oc] = 1;
+        if (p.ret_type[c] == RW_T_DECIMAL) {
+          ((uint64_t*)o.col[oc])[row * 2] = v.lo;
+          ((uint64_t*)o.col[oc])[row * 2 + 1] = v.hi;
+        } else {
+          store_word(o.col[oc], type_width_dev(p.ret_type[c]), p.ret_type[c], row, v.lo);
+        }
+      }
+    }
+    // materialized input of the retractable min / max calls: one row per live value
+    for (int c = 0; c < p.n_calls; c++) {
+      if (p.mm_off[c] < 0) continue;
+      for (uint32_t id = (uint32_t)cold[p.mm_off[c]]; id != 0u;) {
+        const ulonglong2 rec = t.mm_log[id];
+        const uint32_t lk = (uint32_t)rec.x;
+        if (!(lk & MM_DEAD)) {
+          const unsigned long long mr = atomicAdd(o.m_rows, 1ull);
+          if (!count_only && (int64_t)mr < o.m_capacity) {
+            for (int k = 0; k < p.n_keys; k++) {
+              o.mvalid[k][mr] = ((key_nm >> k) & 1) ? 0 : 1;
+              store_word(o.mcol[k], type_width_dev(p.key_type[k]), p.key_type[k], (int64_t)mr, keyw[k]);
+            }
+            ((int32_t*)o.mcol[p.n_keys])[mr] = c;
+            const bool isf = p.arg_type[c] == RW_T_FLOAT32 || p.arg_type[c] == RW_T_FLOAT64;
+            ((long long*)o.mcol[p.n_keys + 1])[mr] = isf ? __double_as_longlong(f64_unsortable((int64_t)rec.y)) : (long long)rec.y;
+          }
+        }
+        id = lk & ~MM_DEAD;
+      }
+    }
+  }
+}
+
+// restore: one intermediate-state row -> one group (states, flags, carry words; prev_outputs = the outputs of the
+// loaded states, agg_group.rs:305-309)
+__global__ void __launch_bounds__(256) agg_restore_kernel(AggTable t, AggPlanDev p, DevChunk ch) {
+  unsigned int created_local = 0;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t slot;
+    bool created = false;
+    if (p.single_key) {
+      const ColRef& kc = ch.cols[0];
+      if (col_is_null(kc, r)) slot = t.cap;
+      else {
+        const uint64_t key = load_key_word(kc, r);
+        slot = key == AGG_EMPTY ? t.cap + 1 : find_or_insert_single(t, p.HW, key, &created);
+      }
+    } else {
+      uint64_t kw[RW_MAX_KEYS];
+      uint32_t nm = 0;
+      for (int k = 0; k < p.n_keys; k++) {
+        if (col_is_null(ch.cols[k], r)) { nm |= 1u << k; kw[k] = 0; }
+        else kw[k] = load_key_word(ch.cols[k], r);
+      }
+      slot = find_or_insert_multi(t, p, kw, nm, &created);
+    }
+    if (created) created_local++;
+    uint64_t* hot = t.hot + slot * p.HW;
+    uint64_t* cold = t.cold + slot * p.CW;
+    uint64_t flags = 0;
+    for (int c = 0; c < p.n_calls; c++) {
+      const ColRef& sc = ch.cols[p.n_keys + c];
+      const int kind = p.kind[c], at = p.arg_type[c];
+      const bool isf = at == RW_T_FLOAT32 || at == RW_T_FLOAT64;
+      if (col_is_null(sc, r)) { hot[p.KW + c] = state_init(kind, at); continue; }
+      if (kind != RW_AGG_COUNT) flags |= 1ull << c;
+      if (kind == RW_AGG_COUNT) {
+        hot[p.KW + c] = (uint64_t)load_i64(sc, r);
+      } else if (kind == RW_AGG_SUM || kind == RW_AGG_SUM0) {
+        if (isf) {
+          hot[p.KW + c] = (uint64_t)__double_as_longlong(load_f64(sc, r));
+        } else if (p.ret_type[c] == RW_T_DECIMAL) {
+          const uint64_t* d = (const uint64_t*)sc.data + r * 2;
+          hot[p.KW + c] = d[0];
+          if (p.hi_off[c] >= 0) cold[p.hi_off[c]] = d[1];
+        } else {
+          const long long v = (long long)load_i64(sc, r);
+          hot[p.KW + c] = (uint64_t)v;
+          if (p.hi_off[c] >= 0) cold[p.hi_off[c]] = (uint64_t)(v >> 63);
+        }
+      } else {
+        hot[p.KW + c] = isf ? (uint64_t)f64_sortable(load_f64(sc, r)) : (uint64_t)load_i64(sc, r);
+      }
+    }
+    // prev_outputs = get_outputs(loaded states)
+    uint32_t prev_nm = 0;
+    for (int c = 0; c < p.n_calls; c++) {
+      const OutVal v = call_output(t, p, c, hot, cold, flags);
+      cold[1 + c] = v.lo;
+      if (p.prevhi_off[c] >= 0) cold[p.prevhi_off[c]] = v.hi;
+      if (v.null) prev_nm |= 1u << c;
+    }
+    cold[0] = flags | ((uint64_t)prev_nm << 16) | COLD_HAS_PREV;
+  }
+  for (int o2 = 16; o2 > 0; o2 >>= 1) created_local += __shfl_xor_sync(0xffffffffu, created_local, o2);
+  if (lane_id() == 0 && created_local) atomicAdd(&t.status->n_groups, (unsigned long long)created_local);
+}
+
+// restore of a materialized-input row: (group key | call index | value) -> one record on the group's chain
+__global__ void __launch_bounds__(256) agg_restore_minput_kernel(AggTable t, AggPlanDev p, DevChunk ch) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < ch.n; r += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t slot;
+    bool created = false;
+    if (p.single_key) {
+      const ColRef& kc = ch.cols[0];
+      if (col_is_null(kc, r)) slot = t.cap;
+      else {
+        const uint64_t key = load_key_word(kc, r);
+        slot = key == AGG_EMPTY ? t.cap + 1 : find_or_insert_single(t, p.HW, key, &created);
+      }
+    } else {
+      uint64_t kw[RW_MAX_KEYS];
+      uint32_t nm = 0;
+      for (int k = 0; k < p.n_keys; k++) {
+        if (col_is_null(ch.cols[k], r)) { nm |= 1u << k; kw[k] = 0; }
+        else kw[k] = load_key_word(ch.cols[k], r);
+      }
+      slot = find_or_insert_multi(t, p, kw, nm, &created);
+    }
+    const int c = (int)load_i64(ch.cols[p.n_keys], r);
+    if (c < 0 || c >= p.n_calls || p.mm_off[c] < 0) { atomicOr(&t.status->err, AGG_ERR_MM_MISSING); continue; }
+    const unsigned long long id = atomicAdd(t.mm_next, 1ull);
+    if (id >= t.mm_cap) { atomicOr(&t.status->err, AGG_ERR_MM_CAPACITY); continue; }
+    uint64_t* cold = t.cold + slot * p.CW;
+    const uint32_t old = atomicExch((uint32_t*)(cold + p.mm_off[c]), (uint32_t)id);
+    const bool isf = p.arg_type[c] == RW_T_FLOAT32 || p.arg_type[c] == RW_T_FLOAT64;
+    long long v = (long long)load_i64(ch.cols[p.n_keys + 1], r);
+    if (isf) v = (long long)f64_sortable(__longlong_as_double(v));
+    t.mm_log[id] = make_ulonglong2((unsigned long long)old, (unsigned long long)v);
+  }
+}
+
 __global__ void pack_bytes_to_bits_kernel(const uint8_t* bytes, uint64_t* words, int64_t n) {
   int64_t nw = (n + 63) >> 6;
   for (int64_t w = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; w < nw; w += (int64_t)gridDim.x * blockDim.x) {
@@ -1448,6 +1645,140 @@ int32_t rwgpu_agg_flush_collect(rwgpu_agg* h, rw_chunk* view, void* cuda_stream)
   int rc = agg_flush_collect(h, &n, has_null, &set);
   if (rc != RW_OK) return rc;
   return agg_fill_view(h, set, n, has_null, view, cuda_stream ? (cudaStream_t)cuda_stream : h->stream);
+}
+
+// ---- state persistence: see the comment above agg_snapshot_kernel
+int32_t rwgpu_agg_snapshot(rwgpu_agg* h, rwgpu_out** states, rwgpu_out** minput) {
+  if (!h || !states || !minput) return fail(RW_ERR_INVALID, "null");
+  if (h->n_pending || h->epoch_rows || h->stage[h->cur].rows) return fail(RW_ERR_INVALID, "snapshot between a barrier and the next push only");
+  RW_CUDA(cudaDeviceSynchronize());
+  const AggPlanDev& p = h->plan;
+  const int n_out = (int)h->out_types.size();
+  DevBuf counters;
+  RW_CUDA(counters.reserve(256));
+  RW_CUDA(cudaMemset(counters.p, 0, 256));
+  AggSnapOut o;
+  memset(&o, 0, sizeof(o));
+  o.n_rows = counters.as<unsigned long long>();
+  o.m_rows = o.n_rows + 1;
+  o.has_null = (unsigned int*)(o.n_rows + 2);
+  const int g = grid_for((int64_t)h->cap + 2, 256);
+  agg_snapshot_kernel<<<g, 256, 0, h->stream>>>(h->table(), p, o, 1);  // pass 1: sizes
+  RW_CUDA(cudaGetLastError());
+  unsigned long long cnt[2] = {0, 0};
+  RW_CUDA(cudaMemcpyAsync(cnt, counters.p, 16, cudaMemcpyDeviceToHost, h->stream));
+  RW_CUDA(cudaStreamSynchronize(h->stream));
+  const int64_t n = (int64_t)cnt[0], nm = (int64_t)cnt[1];
+  // device staging: columns + valid bytes
+  std::vector<DevBuf> col(n_out), val(n_out), mcol(p.n_keys + 2), mval(p.n_keys);
+  for (int k = 0; k < n_out; k++) {
+    RW_CUDA(col[k].reserve((size_t)std::max<int64_t>(n, 1) * type_width(h->out_types[k])));
+    RW_CUDA(val[k].reserve((size_t)std::max<int64_t>(n, 1)));
+    o.col[k] = col[k].p;
+    o.valid[k] = val[k].as<uint8_t>();
+  }
+  std::vector<int> mtypes;
+  for (int k = 0; k < p.n_keys; k++) mtypes.push_back(p.key_type[k]);
+  mtypes.push_back(RW_T_INT32);
+  mtypes.push_back(RW_T_INT64);
+  for (int k = 0; k < p.n_keys + 2; k++) {
+    RW_CUDA(mcol[k].reserve((size_t)std::max<int64_t>(nm, 1) * type_width(mtypes[k])));
+    o.mcol[k] = mcol[k].p;
+  }
+  for (int k = 0; k < p.n_keys; k++) {
+    RW_CUDA(mval[k].reserve((size_t)std::max<int64_t>(nm, 1)));
+    o.mvalid[k] = mval[k].as<uint8_t>();
+  }
+  o.capacity = n;
+  o.m_capacity = nm;
+  RW_CUDA(cudaMemsetAsync(counters.p, 0, 256, h->stream));
+  agg_snapshot_kernel<<<g, 256, 0, h->stream>>>(h->table(), p, o, 0);  // pass 2: rows
+  RW_CUDA(cudaGetLastError());
+  h->launches += 2;
+  unsigned int has_null[RW_MAX_KEYS + RW_MAX_CALLS];
+  RW_CUDA(cudaMemcpyAsync(has_null, o.has_null, sizeof(has_null), cudaMemcpyDeviceToHost, h->stream));
+  RW_CUDA(cudaStreamSynchronize(h->stream));
+  auto to_host = [&](int64_t rows, const std::vector<int>& types, std::vector<DevBuf>& cols, std::vector<DevBuf>& vals, const unsigned int* hn,
+                     int n_valid, rwgpu_out** out) -> int {
+    auto ro = new rwgpu_out();
+    ro->chunk_size = h->chunk_size;
+    unsigned long long nullm = 0;
+    for (int k = 0; k < n_valid; k++) if (hn[k]) nullm |= 1ull << k;
+    if (!ro->layout(rows, types, nullm, false, h->pool)) { delete ro; return fail(RW_ERR_OOM, "pinned output block"); }
+    if (rows > 0) {
+      memset(ro->ops, RW_OP_INSERT, (size_t)rows);
+      for (size_t k = 0; k < types.size(); k++) {
+        cudaMemcpyAsync(ro->data[k], cols[k].p, (size_t)rows * type_width(types[k]), cudaMemcpyDeviceToHost, h->stream);
+        if (ro->valid_bytes[k]) cudaMemcpyAsync(ro->valid_bytes[k], vals[k].p, (size_t)rows, cudaMemcpyDeviceToHost, h->stream);
+      }
+      cudaError_t e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) { delete ro; return fail(RW_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    ro->finalize();
+    *out = ro;
+    return RW_OK;
+  };
+  int rc = to_host(n, h->out_types, col, val, has_null, n_out, states);
+  if (rc != RW_OK) return rc;
+  // (NULL group keys of the materialized input: flagged through the same key-column flags)
+  rc = to_host(nm, mtypes, mcol, mval, has_null, p.n_keys, minput);
+  if (rc != RW_OK) { rwgpu_out_release(*states); *states = nullptr; return rc; }
+  return RW_OK;
+}
+
+int32_t rwgpu_agg_restore(rwgpu_agg* h, const rw_chunk* states, const rw_chunk* minput) {
+  if (!h || !states) return fail(RW_ERR_INVALID, "null");
+  if (h->n_pending || h->epoch_rows) return fail(RW_ERR_INVALID, "restore into an idle operator only");
+  const AggPlanDev& p = h->plan;
+  if (states->n_cols != (int)h->out_types.size()) return fail(RW_ERR_INVALID, "state rows: group key columns followed by one state column per call");
+  for (int k = 0; k < states->n_cols; k++)
+    if (states->columns[k].type != h->out_types[k]) return fail(RW_ERR_INVALID, "state rows: column type mismatch");
+  int rc = agg_ensure_capacity(h, (uint64_t)states->n_rows);
+  if (rc != RW_OK) return rc;
+  if (states->n_rows > 0) {
+    DevBuf buf;
+    DevChunk ch;
+    rc = upload_chunk(states, buf, &ch, h->stream);
+    if (rc != RW_OK) return rc;
+    agg_restore_kernel<<<grid_for(ch.n, 256), 256, 0, h->stream>>>(h->table(), p, ch);
+    RW_CUDA(cudaGetLastError());
+    h->launches++;
+    RW_CUDA(cudaStreamSynchronize(h->stream));
+    h->groups_upper += (uint64_t)states->n_rows;
+  }
+  if (minput && minput->n_rows > 0) {
+    if (!h->n_retract) return fail(RW_ERR_INVALID, "materialized-input rows for a plan without retractable min/max");
+    if (minput->n_cols != p.n_keys + 2 || minput->columns[p.n_keys].type != RW_T_INT32 || minput->columns[p.n_keys + 1].type != RW_T_INT64)
+      return fail(RW_ERR_INVALID, "materialized-input rows: group key columns, int4 call index, int8 value");
+    const uint64_t need = h->mm_upper + (uint64_t)minput->n_rows;
+    if (need > h->mm_cap) {
+      RW_CUDA(cudaDeviceSynchronize());
+      unsigned long long used = 1;
+      RW_CUDA(cudaMemcpy(&used, h->mm_next.p, 8, cudaMemcpyDeviceToHost));
+      uint64_t ncap = std::max<uint64_t>(h->mm_cap * 2, used + (uint64_t)minput->n_rows * 2);
+      DevBuf nl;
+      RW_CUDA(nl.reserve((size_t)ncap * 16));
+      RW_CUDA(cudaMemcpy(nl.p, h->mm_log.p, (size_t)used * 16, cudaMemcpyDeviceToDevice));
+      h->mm_log = std::move(nl);
+      h->mm_cap = ncap;
+    }
+    h->mm_upper += (uint64_t)minput->n_rows;
+    DevBuf buf;
+    DevChunk ch;
+    rc = upload_chunk(minput, buf, &ch, h->stream);
+    if (rc != RW_OK) return rc;
+    agg_restore_minput_kernel<<<grid_for(ch.n, 256), 256, 0, h->stream>>>(h->table(), p, ch);
+    RW_CUDA(cudaGetLastError());
+    h->launches++;
+    RW_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  AggStatus st;
+  RW_CUDA(cudaMemcpy(&st, h->status.p, sizeof(st), cudaMemcpyDeviceToHost));
+  if (st.err) {
+    cudaMemset(&h->status.as<AggStatus>()->err, 0, sizeof(unsigned int));
+    return fail(agg_err_code(st.err), agg_err_msg(st.err));
+  }
+  return RW_OK;
 }
 
 int32_t rwgpu_agg_profile(rwgpu_agg* h, int32_t enable, double* ms, uint64_t* launches) {

@@ -1519,6 +1519,74 @@ __global__ void noop_normalize_kernel(JoinOutDev o, int64_t n, int chunk_size) {
 }
 }  // namespace rw
 
+// =============================================================================== state persistence
+// The join's persistent state is, per side, the set of stored input rows (the reference writes every stored row to the
+// side's StateTable, JoinHashMap::insert join/hash_join.rs:591-625, pk = join key | deduped input pk; degrees live in a
+// second table and are a function of the two row sets).  The snapshot kernels walk every key's chain and emit the live
+// rows in the side's INPUT schema; restore replays them as inserts with the output discarded -- the incremental
+// algorithm itself re-derives the degrees.
+namespace rw {
+struct SnapOut {
+  void* col[RW_MAX_COLS];
+  uint8_t* valid[RW_MAX_COLS];
+  unsigned long long* n_rows;
+  unsigned int* has_null;
+  int64_t capacity;
+};
+
+__device__ __forceinline__ void snap_emit_uni(const SnapOut& o, int n_cols, const uint64_t* c, uint32_t nmask) {
+  const unsigned long long row = atomicAdd(o.n_rows, 1ull);
+  if ((int64_t)row >= o.capacity) return;
+  for (int k = 0; k < n_cols; k++) {
+    const bool nul = (nmask >> k) & 1u;
+    o.valid[k][row] = nul ? 0 : 1;
+    if (nul) o.has_null[k] = 1u;
+    ((uint64_t*)o.col[k])[row] = c[k];
+  }
+}
+
+__global__ void __launch_bounds__(256) uni_snapshot_kernel(UniDev t, int S, int n_cols, SnapOut o) {
+  for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < t.cap + 2; b += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = *(const unsigned long long*)ub(t, (int64_t)b);
+    if (b < t.cap && key == J_EMPTY) continue;
+    uint32_t m;
+    if (S == t.is) {
+      const unsigned long long WI = *ub_WI(t, (int64_t)b);
+      if (W_istate(WI) == 1u) snap_emit_uni(o, n_cols, ub_cols(t, (int64_t)b), (uint32_t)(*ub_IH(t, (int64_t)b) & 0xffull));
+      m = W_head(WI);
+    } else {
+      m = *ub_chead(t, (int64_t)b);
+    }
+    while (m != U_NIL) {
+      const UniRec* rec = urec(t, S, m);
+      if (!(rec->link & J_DEAD)) snap_emit_uni(o, n_cols, rec->c, rec->nullmask);
+      m = rec->link & 0x7fffffffu;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) join_snapshot_kernel(const JoinPlanDev* __restrict__ p, int S, JoinSideDev s, SnapOut o) {
+  for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < s.cap + 2; b += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t w0 = *(const uint64_t*)bkt(s, (int64_t)b);
+    if (b < s.cap && (p->single_key ? w0 == J_EMPTY : w0 == 0ull)) continue;
+    for_each_live(s, p, (int64_t)b, [&](uint8_t* rec) -> bool {
+      const unsigned long long row = atomicAdd(o.n_rows, 1ull);
+      if ((int64_t)row < o.capacity) {
+        const uint32_t nmask = ((const RecHdr*)rec)->nullmask;
+        for (int k = 0; k < p->n_cols[S]; k++) {
+          const bool nul = (nmask >> k) & 1u;
+          o.valid[k][row] = nul ? 0 : 1;
+          if (nul) o.has_null[k] = 1u;
+          const int w = p->col_width[S][k];
+          if (!nul) copy_bytes((uint8_t*)o.col[k] + row * w, rec + p->col_off[S][k], w);
+        }
+      }
+      return true;
+    });
+  }
+}
+}  // namespace rw
+
 // =============================================================================== host handle
 using namespace rw;
 
@@ -2793,6 +2861,106 @@ int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t /*epoch*/) {
         int rc = uni_compact(h, s);
         if (rc != RW_OK) return rc;
       }
+  return RW_OK;
+}
+
+// ---- state persistence: see the comment above uni_snapshot_kernel
+int32_t rwgpu_join_snapshot(rwgpu_join* h, int32_t side, rwgpu_out** out) {
+  if (!h || !out) return fail(RW_ERR_INVALID, "null");
+  if (side != 0 && side != 1) return fail(RW_ERR_INVALID, "side");
+  if (h->n_pending) return fail(RW_ERR_INVALID, "collect the outstanding asynchronous pushes first");
+  RW_CUDA(cudaDeviceSynchronize());
+  const JoinSideHost& sd = h->side[side];
+  const int n_cols = sd.n_cols;
+  // upper bound of the live rows: every log / store record ever handed out + one inline record per key
+  const uint64_t keys = h->uni ? h->uni_keys + 2 : sd.keys_upper + 2;
+  int64_t cap = (int64_t)std::min<uint64_t>(sd.n_rows + keys, (uint64_t)1 << 40);
+  DevBuf counters;
+  RW_CUDA(counters.reserve(256));
+  std::vector<DevBuf> col(n_cols), val(n_cols);
+  SnapOut o;
+  int64_t n = 0;
+  unsigned int has_null[RW_MAX_COLS];
+  for (int attempt = 0; attempt < 2; attempt++) {
+    memset(&o, 0, sizeof(o));
+    RW_CUDA(cudaMemset(counters.p, 0, 256));
+    o.n_rows = counters.as<unsigned long long>();
+    o.has_null = (unsigned int*)(o.n_rows + 1);
+    o.capacity = cap;
+    for (int k = 0; k < n_cols; k++) {
+      RW_CUDA(col[k].reserve((size_t)std::max<int64_t>(cap, 1) * type_width(sd.types[k])));
+      RW_CUDA(val[k].reserve((size_t)std::max<int64_t>(cap, 1)));
+      o.col[k] = col[k].p;
+      o.valid[k] = val[k].as<uint8_t>();
+    }
+    if (h->uni) uni_snapshot_kernel<<<jgrid((int64_t)h->uni_cap + 2, 256), 256, 0, h->stream>>>(uni_dev(h), side, n_cols, o);
+    else join_snapshot_kernel<<<jgrid((int64_t)sd.slot_cap + 2, 256), 256, 0, h->stream>>>(h->plan_dev.as<JoinPlanDev>(), side, side_dev(h, side), o);
+    RW_CUDA(cudaGetLastError());
+    h->launches++;
+    unsigned long long cnt = 0;
+    RW_CUDA(cudaMemcpyAsync(&cnt, counters.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    RW_CUDA(cudaMemcpyAsync(has_null, o.has_null, sizeof(unsigned int) * RW_MAX_COLS, cudaMemcpyDeviceToHost, h->stream));
+    RW_CUDA(cudaStreamSynchronize(h->stream));
+    n = (int64_t)cnt;
+    if (n <= cap) break;
+    cap = n;  // (the bound was too small: once more with the exact size)
+  }
+  auto ro = new rwgpu_out();
+  ro->chunk_size = h->chunk_size;
+  unsigned long long nullm = 0;
+  for (int k = 0; k < n_cols; k++) if (has_null[k]) nullm |= 1ull << k;
+  if (!ro->layout(n, sd.types, nullm, false, h->pool)) { delete ro; return fail(RW_ERR_OOM, "pinned output block"); }
+  if (n > 0) {
+    memset(ro->ops, RW_OP_INSERT, (size_t)n);
+    for (int k = 0; k < n_cols; k++) {
+      cudaMemcpyAsync(ro->data[k], col[k].p, (size_t)n * type_width(sd.types[k]), cudaMemcpyDeviceToHost, h->stream);
+      if (ro->valid_bytes[k]) cudaMemcpyAsync(ro->valid_bytes[k], val[k].p, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { delete ro; return fail(RW_ERR_CUDA, cudaGetErrorString(e)); }
+  }
+  ro->finalize();
+  *out = ro;
+  return RW_OK;
+}
+
+int32_t rwgpu_join_restore(rwgpu_join* h, int32_t side, const rw_chunk* rows) {
+  if (!h || !rows) return fail(RW_ERR_INVALID, "null");
+  if (side != 0 && side != 1) return fail(RW_ERR_INVALID, "side");
+  if (rows->n_cols != h->side[side].n_cols) return fail(RW_ERR_INVALID, "chunk schema mismatch");
+  if (h->n_pending) return fail(RW_ERR_INVALID, "collect the outstanding asynchronous pushes first");
+  if (rows->n_rows == 0) return RW_OK;
+  // replay as inserts, a slice at a time, output discarded
+  const int64_t slice = 1 << 20;
+  for (int64_t lo = 0; lo < rows->n_rows; lo += slice) {
+    const int64_t m = std::min<int64_t>(slice, rows->n_rows - lo);
+    std::vector<rw_column> cols(rows->n_cols);
+    std::vector<std::vector<uint64_t>> vbits(rows->n_cols);
+    for (int k = 0; k < rows->n_cols; k++) {
+      cols[k] = rows->columns[k];
+      cols[k].data = (const uint8_t*)rows->columns[k].data + (size_t)lo * type_width(rows->columns[k].type);
+      if (rows->columns[k].validity) {
+        if (lo % 64) return fail(RW_ERR_INVALID, "internal: restore slice alignment");
+        cols[k].validity = rows->columns[k].validity + lo / 64;
+      }
+    }
+    rw_chunk part = *rows;
+    part.n_rows = m;
+    part.ops = rows->ops + lo;
+    part.visibility = rows->visibility ? rows->visibility + lo / 64 : nullptr;
+    part.columns = cols.data();
+    DevBuf buf;
+    DevChunk ch;
+    int rc = upload_chunk(&part, buf, &ch, h->stream);
+    if (rc != RW_OK) return rc;
+    rc = join_begin_call(h, h->stream);
+    if (rc != RW_OK) return rc;
+    int64_t n_out = 0;
+    unsigned long long nullm = 0;
+    rc = join_push_dev(h, side, ch, h->stream, 0, &n_out, &nullm);
+    if (rc != RW_OK) return rc;
+    RW_CUDA(cudaStreamSynchronize(h->stream));
+  }
   return RW_OK;
 }
 

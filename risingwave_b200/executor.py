@@ -287,6 +287,25 @@ class HashAggExecutor:
         self.backend.check(self.backend._agg_flush(self._h, epoch, C.byref(out)))
         return self.backend.take_out(out)
 
+    # state persistence (rwgpu.h rwgpu_agg_snapshot / rwgpu_agg_restore; CUDA backend only)
+    def snapshot(self) -> Tuple[List[StreamChunk], List[StreamChunk]]:
+        """-> (intermediate-state rows, materialized-input rows of retractable min / max) as chunks"""
+        fn = self.backend.lib.rwgpu_agg_snapshot
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        a, b = C.c_void_p(), C.c_void_p()
+        self.backend.check(fn(self._h, C.byref(a), C.byref(b)))
+        return self.backend.take_out(a), self.backend.take_out(b)
+
+    def restore(self, states: Optional[StreamChunk], minput: Optional[StreamChunk] = None):
+        fn = self.backend.lib.rwgpu_agg_restore
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.POINTER(abi.RwChunk), C.POINTER(abi.RwChunk)]
+        sa, k1 = states.to_abi()
+        if minput is not None:
+            ma, k2 = minput.to_abi()
+            self.backend.check(fn(self._h, C.byref(sa), C.byref(ma)))
+        else:
+            self.backend.check(fn(self._h, C.byref(sa), None))
+
     def execute(self) -> MessageStream:
         return MessageStream(self._run())
 
@@ -404,6 +423,20 @@ class HashJoinExecutor:
 
     def flush_data(self, epoch: int):
         self.backend.check(self.backend._join_barrier(self._h, epoch))
+
+    # state persistence (rwgpu.h rwgpu_join_snapshot / rwgpu_join_restore; CUDA backend only)
+    def snapshot(self, side: int) -> List[StreamChunk]:
+        fn = self.backend.lib.rwgpu_join_snapshot
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+        out = C.c_void_p()
+        self.backend.check(fn(self._h, side, C.byref(out)))
+        return self.backend.take_out(out)
+
+    def restore(self, side: int, rows: StreamChunk):
+        fn = self.backend.lib.rwgpu_join_restore
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(abi.RwChunk)]
+        ch, keep = rows.to_abi()
+        self.backend.check(fn(self._h, side, C.byref(ch)))
 
     def execute(self) -> MessageStream:
         return MessageStream(self._run())
