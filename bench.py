@@ -525,7 +525,7 @@ def run_ours(args):
 
             trace = os.environ.get("BENCH_TRACE") is not None  # per-phase wall clock (adds syncs: never for a reported number)
 
-            counted = world > 1 and isinstance(ex_plan, exchange.P2PShufflePlan) and not trace
+            counted = world > 1 and isinstance(ex_plan, exchange.P2PShufflePlan)
             recv_chunks = [device.DeviceChunk(*ex_plan.output(b), T4) for b in range(2)] if counted else None
             t_ex = t_join = 0.0
             pending = {}
@@ -572,16 +572,22 @@ def run_ours(args):
                 keep.pop(s, None)
                 return out
 
+            tl = []  # BENCH_TRACE: host timeline (never for a reported number)
+
             def run_steps(lo, hi, each=None):
                 """steps lo..hi-1, push s+1 launched before push s is collected (two output sets)"""
                 tot = 0
                 for s in range(lo, hi):
+                    t_a = time.perf_counter()
                     launch(s)
+                    t_b = time.perf_counter()
                     if s > lo:
                         o = collect(s - 1)
                         tot += o.n_rows
                         if each:
                             each(o)
+                    if trace:
+                        tl.append((s, 1e3 * (t_b - t_a), 1e3 * (time.perf_counter() - t_b)))
                 o = collect(hi - 1)
                 tot += o.n_rows
                 if each:
@@ -606,6 +612,8 @@ def run_ours(args):
             if world > 1:
                 dist.barrier()
             ms = e0.elapsed_time(e1)
+            if trace:
+                print("[trace] step: launch ms, collect(prev) ms\n" + "\n".join(f"  {a}: {b:.3f} {c:.3f}" for a, b, c in tl[-K:]), file=sys.stderr)
             clocks = sampler.stop() if rank == 0 else None
             kern_ms, kern_n = device.profile(join, "join", False)
             launches = device.launches(join, "join") - l0

@@ -116,6 +116,7 @@ struct JoinStatus {
   unsigned long long n_in;       // rows of the input chunk as the kernel saw them (device-resident row count)
   unsigned long long log_next[2];  // unified table: log ids handed out per side (copied from the device counters)
   unsigned long long n_dead[2];    // unified table: dead log records per side
+  unsigned long long n_defer;      // unified table: != 0 when the hot kernel deferred rows to uni_deferred_kernel
 };
 
 struct JoinOutDev {
@@ -1340,7 +1341,7 @@ __device__ __forceinline__ void join_status_publish(JoinStatus* st, JoinStatus* 
   *host = s;
   *(unsigned long long*)(host + 1) = tag;
   __threadfence_system();
-  if (reset & 1) { st->n_store = 0ull; st->n_del = 0ull; st->null_mask = 0ull; }
+  if (reset & 1) { st->n_store = 0ull; st->n_del = 0ull; st->null_mask = 0ull; st->n_defer = 0ull; }
   if (reset & 2) { st->out_rows = 0ull; st->pad = 0u; st->n_in = 0ull; }
 }
 
@@ -1590,9 +1591,36 @@ __global__ void __launch_bounds__(256) join_snapshot_kernel(const JoinPlanDev* _
 // =============================================================================== host handle
 using namespace rw;
 
+// unified table: a side's log as a list of 2^22-record segments behind a device table of pointers (join_uni.cuh)
+struct SegLog {
+  std::vector<DevBuf> segs;
+  DevBuf table;  // U_MAX_SEGS device pointers
+  uint64_t cap() const { return (uint64_t)segs.size() << U_SEG_SHIFT; }
+  // make room for `rows` records: new segments are allocated and their pointers appended ON `st` (stream order puts
+  // the table update before every kernel launched afterwards; existing entries never change)
+  int ensure(uint64_t rows, cudaStream_t st) {
+    if (!table.p) {
+      RW_CUDA(table.reserve(U_MAX_SEGS * sizeof(void*)));
+      RW_CUDA(cudaMemsetAsync(table.p, 0, U_MAX_SEGS * sizeof(void*), st));
+    }
+    while (cap() < rows) {
+      if (segs.size() >= U_MAX_SEGS) return fail(RW_ERR_OOM, "join side exceeds 2^31 log rows");
+      DevBuf sg;
+      cudaError_t e = sg.reserve((size_t)U_SEG_RECS * 48);
+      if (e != cudaSuccess) { cudaGetLastError(); return fail(RW_ERR_OOM, std::string("join log segment: ") + cudaGetErrorString(e)); }
+      void* ptr = sg.p;
+      // (the pointer is copied from a pageable temporary: cudaMemcpyAsync stages it before returning)
+      RW_CUDA(cudaMemcpyAsync(table.as<uint8_t>() + segs.size() * sizeof(void*), &ptr, sizeof(void*), cudaMemcpyHostToDevice, st));
+      segs.push_back(std::move(sg));
+    }
+    return RW_OK;
+  }
+};
+
 struct JoinSideHost {
   int n_cols = 0;
   std::vector<int> types;
+  SegLog log;          // unified table: the side's row log
   GrowBuf recs;        // overflow record store (grows in place)
   DevBuf slots;        // bucket array
   DevBuf pools;        // per-warp row-id pools of join_inner_q4_kernel
@@ -1637,6 +1665,8 @@ struct rwgpu_join {
   uint64_t uni_cap = 0, uni_keys = 0;
   uint64_t uni_dead[2] = {0, 0};
   uint64_t compactions = 0;
+  DevBuf uni_wk_entry, uni_wk_mask;  // worklist of the rows the hot kernel defers (join_uni.cuh UniWork)
+  int64_t uni_wk_cap = 0;
   // launch / collect split (rwgpu_join_push_device_async / rwgpu_join_collect): pushes enqueued but not collected
   JoinPending pending[2];
   int n_pending = 0;
@@ -1714,6 +1744,13 @@ static int join_alloc_slots(rwgpu_join* h, int S, DevBuf& buf, uint64_t cap) {
 // grow the record store of side S to hold at least `rows` records (contents preserved, in place)
 static int join_grow_store(rwgpu_join* h, int S, uint64_t rows) {
   JoinSideHost& s = h->side[S];
+  if (h->uni) {
+    if (rows >= 0x7ffffff0ull) return fail(RW_ERR_OOM, "join side exceeds 2^31 rows");
+    if (rows <= s.log.cap()) return RW_OK;
+    int rc = s.log.ensure(rows, h->last_st ? h->last_st : h->stream);
+    s.row_cap = s.log.cap();
+    return rc;
+  }
   if (rows <= s.row_cap) return RW_OK;
   if (rows >= 0x7ffffff0ull) return fail(RW_ERR_OOM, "join side exceeds 2^31 rows");
   // address space for the whole row-id range, capped at the device's memory size
@@ -1861,8 +1898,8 @@ static UniDev uni_dev(rwgpu_join* h) {
   t.cap = h->uni_cap;
   unsigned long long* ctr = h->uni_counters.as<unsigned long long>();
   for (int s = 0; s < 2; s++) {
-    t.log[s] = h->side[s].recs.as<uint8_t>();
-    t.log_cap[s] = h->side[s].row_cap;
+    t.log[s] = h->side[s].log.table.as<uint8_t*>();
+    t.log_cap[s] = h->side[s].log.cap();
     t.pools[s] = h->side[s].pools.as<uint2>();
     t.log_next[s] = ctr + s;
     t.n_dead[s] = ctr + 2 + s;
@@ -1901,22 +1938,26 @@ static int uni_grow_table(rwgpu_join* h, uint64_t need_keys) {
 static int uni_compact(rwgpu_join* h, int s) {
   JoinSideHost& sd = h->side[s];
   RW_CUDA(cudaDeviceSynchronize());
-  GrowBuf fresh;
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
-  const size_t va_limit = std::min<size_t>((size_t)0x7ffffff0ull * 48, std::max<size_t>(total_b, (size_t)1 << 30));
-  cudaError_t e = fresh.ensure((size_t)sd.row_cap * 48, 0, va_limit, h->stream);
-  if (e != cudaSuccess) { cudaGetLastError(); return RW_OK; }  // no room for a second log right now: keep the old one
+  SegLog fresh;
+  // the live records are at most the ids handed out minus the dead ones; the pools restart empty, so leave them room
+  const uint64_t live_upper = sd.n_rows > h->uni_dead[s] ? sd.n_rows - h->uni_dead[s] : 0;
+  int rc = fresh.ensure(std::max<uint64_t>(live_upper, 1), h->stream);
+  if (rc != RW_OK) { set_error(""); return RW_OK; }  // no room for a second log right now: keep the old one
   unsigned long long* ctr = h->uni_counters.as<unsigned long long>();
   RW_CUDA(cudaMemsetAsync(ctr + 4, 0, 8, h->stream));
-  uni_compact_kernel<<<jgrid((int64_t)h->uni_cap + 2, 256), 256, 0, h->stream>>>(uni_dev(h), s, fresh.as<uint8_t>(), ctr + 4);
+  uni_compact_kernel<<<jgrid((int64_t)h->uni_cap + 2, 256), 256, 0, h->stream>>>(uni_dev(h), s, fresh.table.as<uint8_t*>(), ctr + 4);
   RW_CUDA(cudaGetLastError());
   h->launches++;
   unsigned long long live = 0;
   RW_CUDA(cudaMemcpyAsync(&live, ctr + 4, 8, cudaMemcpyDeviceToHost, h->stream));
   RW_CUDA(cudaStreamSynchronize(h->stream));
-  sd.recs.swap(fresh);
-  sd.row_cap = std::min<uint64_t>(sd.recs.bytes() / 48, 0x7ffffff0ull);
+  std::swap(sd.log.segs, fresh.segs);
+  {
+    DevBuf t2 = std::move(sd.log.table);
+    sd.log.table = std::move(fresh.table);
+    fresh.table = std::move(t2);
+  }
+  sd.row_cap = sd.log.cap();
   sd.n_rows = live;
   h->uni_dead[s] = 0;
   const unsigned long long zero = 0;
@@ -1947,13 +1988,50 @@ static void uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_onl
   const int S = pd.S;
   const bool is_row = S == h->uni_is;
   if (pd.plain) {
-    if (probe_only) {
-      if (is_row) uni_quad_kernel<true, true><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base, pd.pool_chunk);
-      else uni_quad_kernel<true, false><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base, pd.pool_chunk);
-    } else {
-      if (is_row) uni_quad_kernel<false, true><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base, pd.pool_chunk);
-      else uni_quad_kernel<false, false><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base, pd.pool_chunk);
+    const W8Plan& w = h->w8[S];
+    PlainChunk pc;
+    pc.ops = pd.ch.ops;
+    for (int c = 0; c < 4; c++) pc.c[c] = c < w.n_u ? (const unsigned long long*)pd.ch.cols[c].data : nullptr;
+    pc.key = (const unsigned long long*)pd.ch.cols[w.key_col].data;
+    pc.n = pd.ch.n;
+    pc.n_dev = pd.ch.n_dev;
+    UniOwn own;
+    own.log = t.log[S];
+    own.log_cap = t.log_cap[S];
+    own.pools = t.pools[S];
+    own.log_next = t.log_next[S];
+    const JoinOutDev od = out_dev(h);
+    PlainOut po;
+    po.ops = od.ops;
+    po.vis = od.vis;
+    for (int c = 0; c < 4; c++) {
+      po.ucol[c] = (c < w.n_u && w.u_out[c] >= 0) ? (unsigned long long*)od.col[w.u_out[c]] : nullptr;
+      po.mcol[c] = (c < w.n_m && w.m_out[c] >= 0) ? (unsigned long long*)od.col[w.m_out[c]] : nullptr;
     }
+    po.capacity = od.capacity;
+    UniWork wk;
+    wk.entry = h->uni_wk_entry.as<UniDefer>();
+    wk.mask = h->uni_wk_mask.as<uint8_t>();
+    // resident blocks per SM (registers per thread): 4 (64) by default; RWGPU_UNI_MINB=3 / 5 / 6 for tuning runs
+    static const int minb = getenv("RWGPU_UNI_MINB") ? atoi(getenv("RWGPU_UNI_MINB")) : 4;
+#define UNI_LAUNCH(PO, IS, MB) uni_hot_kernel<PO, IS, MB><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pc, t.buckets, t.cap, own, po, wk, ds, pd.seq_base, pd.out_base, pd.pool_chunk)
+    if (probe_only) {
+      if (is_row) UNI_LAUNCH(true, true, 4); else UNI_LAUNCH(true, false, 4);
+    } else if (is_row) {
+      UNI_LAUNCH(false, true, 4);
+    } else {
+      switch (minb) {
+        case 3: UNI_LAUNCH(false, false, 3); break;
+        case 5: UNI_LAUNCH(false, false, 5); break;
+        case 6: UNI_LAUNCH(false, false, 6); break;
+        default: UNI_LAUNCH(false, false, 4); break;
+      }
+    }
+#undef UNI_LAUNCH
+    // the rows the hot kernel deferred (exits at once when it deferred none)
+    if (probe_only) uni_deferred_kernel<true><<<jgrid(pd.ch.n, 256), 256, 0, pd.st>>>(pdev, w, S, pd.ch, t, od, wk, ds, pd.seq_base, pd.out_base);
+    else uni_deferred_kernel<false><<<jgrid(pd.ch.n, 256), 256, 0, pd.st>>>(pdev, w, S, pd.ch, t, od, wk, ds, pd.seq_base, pd.out_base);
+    h->launches++;
   } else {
     if (probe_only) uni_slow_kernel<true><<<jgrid(pd.ch.n, 256), 256, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base);
     else uni_slow_kernel<false><<<jgrid(pd.ch.n, 256), 256, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base);
@@ -1991,6 +2069,13 @@ static int uni_enqueue(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream_t
   if (rc != RW_OK) return rc;
   rc = join_ensure_out(h, out_base + n + std::max<int64_t>(n / 2, 4096), st, out_base);
   if (rc != RW_OK) return rc;
+  if (plain_cols && n > h->uni_wk_cap) {
+    RW_CUDA(cudaDeviceSynchronize());  // (growth only) an outstanding push may still read the old worklist
+    const int64_t cap = n + n / 4 + 64;
+    RW_CUDA(h->uni_wk_entry.reserve((size_t)cap * sizeof(UniDefer)));
+    RW_CUDA(h->uni_wk_mask.reserve((size_t)(cap + 7) / 8 + 16));
+    h->uni_wk_cap = cap;
+  }
   rc = join_order(h, st);
   if (rc != RW_OK) return rc;
   pd->S = S;
@@ -2454,7 +2539,7 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
   p.single_key = (p.n_keys == 1);
   p.KW = p.single_key ? 1 : 1 + p.n_keys;
   p.SW = p.KW + 1;
-  p.bhdr = (p.KW + 1) * 8;
+  p.bhdr = ((p.KW + 1) * 8 + 15) / 16 * 16;  // the inline record starts 16-byte aligned (its header is written with one 16-byte store)
   for (int s2 = 0; s2 < 2; s2++) {
     p.bstride[s2] = (p.bhdr + p.stride[s2] + 15) / 16 * 16;
     h->side[s2].bstride = p.bstride[s2];
@@ -2509,6 +2594,7 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
     RW_CUDA(cudaMemsetAsync(h->uni_counters.p, 0, 8 * sizeof(unsigned long long), h->stream));
     for (int s = 0; s < 2; s++) {
       h->side[s].stride = 48;
+      h->last_st = h->stream;
       // chained side: every row lives in its log; inline side: only the 2nd, 3rd ... row of a key
       const uint64_t rows = s == h->uni_is ? std::max<uint64_t>(4096, sd[s]->row_capacity_hint / 4) : std::max<uint64_t>(4096, 2 * sd[s]->row_capacity_hint);
       rc = join_grow_store(h, s, std::min<uint64_t>(rows, 0x40000000ull));

@@ -31,10 +31,17 @@ namespace rw {
 #define U_NIL 0x7fffffffu
 #define U_XCHUNK 64  // extra-match output rows a warp reserves at a time
 
+// A side's log is a list of fixed-size SEGMENTS (2^22 records = 192 MiB each) reached through a small device table of
+// segment pointers: growing the log allocates one more segment and appends its pointer -- no copy of the existing
+// hundreds of megabytes in the middle of the stream (round 1: allocate + copy + free, 0.3-0.7 ms per event), no
+// contiguous virtual range.  Record id -> segment id >> 22, offset (id & 2^22-1) * 48.
+#define U_SEG_SHIFT 22
+#define U_SEG_RECS (1u << U_SEG_SHIFT)
+#define U_MAX_SEGS 512
 struct UniDev {
   uint8_t* buckets;   // (cap + 2) x 64 B; slot cap = NULL key (null-safe equality), cap + 1 = the key equal to J_EMPTY
   uint64_t cap;       // power of two
-  uint8_t* log[2];
+  uint8_t* const* log[2];  // segment tables
   uint64_t log_cap[2];
   uint2* pools[2];                  // per-warp id pools {next, end}, persistent across launches
   unsigned long long* log_next[2];  // ids handed out per side (device counters, absolute)
@@ -55,7 +62,11 @@ __device__ __forceinline__ unsigned long long* ub_IH(const UniDev& t, int64_t b)
 __device__ __forceinline__ uint32_t* ub_chead(const UniDev& t, int64_t b) { return (uint32_t*)(ub(t, b) + 24); }
 __device__ __forceinline__ uint32_t* ub_ccount(const UniDev& t, int64_t b) { return (uint32_t*)(ub(t, b) + 28); }
 __device__ __forceinline__ uint64_t* ub_cols(const UniDev& t, int64_t b) { return (uint64_t*)(ub(t, b) + 32); }
-__device__ __forceinline__ UniRec* urec(const UniDev& t, int side, uint32_t id) { return (UniRec*)(t.log[side] + (uint64_t)id * 48); }
+__device__ __forceinline__ uint8_t* useg_rec(uint8_t* const* segs, uint32_t id) {
+  const unsigned long long base = __ldg((const unsigned long long*)segs + (id >> U_SEG_SHIFT));
+  return (uint8_t*)(base + (unsigned long long)(id & (U_SEG_RECS - 1u)) * 48ull);
+}
+__device__ __forceinline__ UniRec* urec(const UniDev& t, int side, uint32_t id) { return (UniRec*)useg_rec(t.log[side], id); }
 __device__ __forceinline__ uint64_t uhome(uint64_t key, uint64_t mask) { return mix64(key) & mask; }
 
 __global__ void uni_init_kernel(uint8_t* buckets, uint64_t from, uint64_t to) {
@@ -275,68 +286,103 @@ __device__ __forceinline__ ulonglong2 ld128_cg(const void* ptr) { return __ldcg(
 // change on the same line, lanes 1..3 write the record (header, columns) with one 16-byte store each.
 // Output is positional (output row r = first match of input row r, extra matches behind the n positional rows);
 // the extra rows come from a per-warp reservation of U_XCHUNK rows (reserved-but-unused rows are invisible).
-template <bool PROBE_ONLY, bool IS_ROW>
-__global__ void __launch_bounds__(JF_BLOCK, 4) uni_quad_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch, UniDev t,
-                                                                JoinOutDev o, JoinStatus* st, uint64_t seq_base, int64_t out_base,
-                                                                uint32_t pool_chunk) {
-  const int64_t n_rows = chunk_rows(ch, st, blockIdx.x == 0 && threadIdx.x == 0);
+//
+// The kernel body holds ONLY the common case.  Rows it cannot finish with the quad -- several matches, a match
+// that is not the bucket's inline record, NULLs in the matched record, the key equal to the EMPTY sentinel, every
+// row of the inline side (its matches live in a chain) -- are DEFERRED: the quad records (bucket, match count,
+// reserved extra rows) in the row's worklist entry and sets the row's bit; uni_deferred_kernel, launched right
+// behind, finishes them one thread per row.  (With those paths inlined the hot loop spilled ~350 bytes.)
+struct PlainChunk {      // a chunk without bitmaps, 8-byte columns
+  const uint8_t* ops;
+  const unsigned long long* c[4];
+  const unsigned long long* key;  // the key column (one of c[])
+  int64_t n;
+  const int64_t* n_dev;  // or nullptr
+};
+struct UniOwn {          // the pushing side's log, resolved on the host (a side index into UniDev's arrays would make
+  uint8_t* const* log;   // the compiler copy the parameter struct to local memory)
+  uint64_t log_cap;
+  uint2* pools;
+  unsigned long long* log_next;
+};
+struct PlainOut {
+  uint8_t* ops;
+  uint8_t* vis;
+  unsigned long long* ucol[4];  // output column fed by update column c (nullptr = not projected)
+  unsigned long long* mcol[4];  // output column fed by matched column c
+  int64_t capacity;
+};
+struct UniDefer {
+  int64_t b;       // the key's bucket (-1: look the key up -- sentinel key)
+  int64_t xpos;    // first reserved extra-match row
+  uint32_t cnt;    // matches to emit (0: whole row through uni_row_generic)
+  uint32_t pad;
+};
+struct UniWork {
+  UniDefer* entry;   // [n], written for deferred rows only
+  uint8_t* mask;     // [(n + 7) / 8], one bit per input row, every byte written by the hot kernel
+};
+
+template <bool PROBE_ONLY, bool IS_ROW, int MINB>
+__global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, uint8_t* buckets, uint64_t cap, UniOwn own, PlainOut o, UniWork wk,
+                                                                  JoinStatus* st, uint64_t seq_base, int64_t out_base, uint32_t pool_chunk) {
+  int64_t n_rows = ch.n;
+  if (ch.n_dev) {
+    const int64_t nd = *ch.n_dev;
+    if (nd < 0 || nd > ch.n) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&st->err, JERR_BAD_COUNT);
+      n_rows = 0;
+    } else {
+      n_rows = nd;
+      if (blockIdx.x == 0 && threadIdx.x == 0) st->n_in = (unsigned long long)nd;
+    }
+  }
   const int lane = lane_id(), q = lane & 3, qlead = lane & ~3;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   uint32_t pool_next = 0, pool_end = 0;
   if (!PROBE_ONLY) {
-    const uint2 pl = t.pools[S][warp_global];
+    const uint2 pl = own.pools[warp_global];
     pool_next = pl.x;
     pool_end = pl.y;
   }
   const uint32_t pool_next0 = pool_next, pool_end0 = pool_end;
   int64_t xnext = 0, xend = 0;  // this warp's reservation in the extra-match area (offsets from xarea)
   const int64_t xarea = out_base + n_rows;
-  const uint64_t mask = t.cap - 1;
+  const uint64_t mask = cap - 1;
   unsigned int new_keys = 0, n_del = 0;
-  bool any_match = false, any_hole = false;
-  const int ca = 2 * (q & 1), cb = ca + 1;
-  const unsigned long long* pa = ca < w.n_u ? (const unsigned long long*)ch.cols[ca].data : nullptr;
-  const unsigned long long* pb = cb < w.n_u ? (const unsigned long long*)ch.cols[cb].data : nullptr;
-  const unsigned long long* pk = (const unsigned long long*)ch.cols[w.key_col].data;
-  int oc0, oc1;
-  if (q < 2) {
-    oc0 = ca < w.n_u ? w.u_out[ca] : -1;
-    oc1 = cb < w.n_u ? w.u_out[cb] : -1;
-  } else {
-    oc0 = ca < w.n_m ? w.m_out[ca] : -1;
-    oc1 = cb < w.n_m ? w.m_out[cb] : -1;
-  }
-  uint64_t* po0 = oc0 >= 0 ? (uint64_t*)o.col[oc0] : nullptr;
-  uint64_t* po1 = oc1 >= 0 ? (uint64_t*)o.col[oc1] : nullptr;
+  bool any_match = false, any_hole = false, any_defer = false;
+  // (selected with ?: -- an index computed from the lane would put the parameter arrays in local memory)
+  const unsigned long long* pa = (q & 1) ? ch.c[2] : ch.c[0];
+  const unsigned long long* pb = (q & 1) ? ch.c[3] : ch.c[1];
+  const unsigned long long* pk = ch.key;
+  unsigned long long* po0 = q == 0 ? o.ucol[0] : (q == 1 ? o.ucol[2] : (q == 2 ? o.mcol[0] : o.mcol[2]));
+  unsigned long long* po1 = q == 0 ? o.ucol[1] : (q == 1 ? o.ucol[3] : (q == 2 ? o.mcol[1] : o.mcol[3]));
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t groups = (n_rows + 7) >> 3;
   const unsigned long long init_W = IS_ROW ? ((W_EMPTY | W_IL_LIVE) + W_COUNT_ONE) : W_EMPTY;
   // software pipeline: the sequential column loads of the warp's next group are issued right after the random
   // access of the current one
   uint8_t n_op = 0;
-  uint64_t n_key = J_EMPTY, n_va = 0ull, n_vb = 0ull;
-  auto fetch = [&](int64_t g2) {
-    const int64_t r2 = g2 * 8 + (lane >> 2);
-    n_op = 0;
-    if (g2 < groups && r2 < n_rows) {
-      n_op = ch.ops[r2];
-      n_key = __ldg(pk + r2);
-      if (pa) n_va = __ldg(pa + r2);
-      if (pb) n_vb = __ldg(pb + r2);
-    }
-  };
-  fetch(warp_global);
+  unsigned long long n_key = J_EMPTY, n_va = 0ull, n_vb = 0ull;
+#define UNI_FETCH(G2)                                         \
+  do {                                                        \
+    const int64_t g2_ = (G2), r2_ = g2_ * 8 + (lane >> 2);    \
+    n_op = 0;                                                 \
+    if (g2_ < groups && r2_ < n_rows) {                       \
+      n_op = ch.ops[r2_];                                     \
+      n_key = __ldg(pk + r2_);                                \
+      if (pa) n_va = __ldg(pa + r2_);                         \
+      if (pb) n_vb = __ldg(pb + r2_);                         \
+    }                                                         \
+  } while (0)
+  UNI_FETCH(warp_global);
   for (int64_t g = warp_global; g < groups; g += nwarps) {
     const int64_t r = g * 8 + (lane >> 2);
     const bool in = r < n_rows;
     const uint8_t op = n_op;
-    const uint64_t key = n_key, va = n_va, vb = n_vb;
+    const unsigned long long key = n_key, va = n_va, vb = n_vb;
     const int64_t pos = out_base + r;
     const bool act = op != 0;
-    if (in && !act) {  // invisible input row
-      if (q == 0) o.vis[pos] = 0;
-      any_hole = true;
-    }
     const bool ins = act && (op == RW_OP_INSERT || op == RW_OP_UPDATE_INSERT);
     if (act && !ins && q == 0) n_del++;
     const bool keyok = act && key != J_EMPTY;
@@ -347,9 +393,9 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) uni_quad_kernel(const JoinPlanDev
     ulonglong2 pv = make_ulonglong2(0ull, 0ull);
     bool first_iter = true;
     while (__any_sync(0xffffffffu, need)) {
-      if (need) pv = ld128_cg(t.buckets + idx * 64 + 16 * q);
-      if (first_iter) { fetch(g + nwarps); first_iter = false; }
-      const uint64_t bkey = shfl64m(0xffffffffu, pv.x, qlead);
+      if (need) pv = ld128_cg(buckets + idx * 64 + 16 * q);
+      if (first_iter) { UNI_FETCH(g + nwarps); first_iter = false; }
+      const unsigned long long bkey = shfl64m(0xffffffffu, pv.x, qlead);
       const bool empty = need && bkey == J_EMPTY;
       if (need && !empty) {
         if (bkey == key) { found = true; need = false; }
@@ -361,9 +407,9 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) uni_quad_kernel(const JoinPlanDev
           ulonglong2 e, d;
           e.x = J_EMPTY; e.y = W_EMPTY;
           d.x = key; d.y = init_W;
-          cas128(t.buckets + idx * 64, e, d, &cf);
+          cas128(buckets + idx * 64, e, d, &cf);
         }
-        const uint64_t cfx = shfl64m(0xffffffffu, cf.x, qlead), cfy = shfl64m(0xffffffffu, cf.y, qlead);
+        const unsigned long long cfx = shfl64m(0xffffffffu, cf.x, qlead), cfy = shfl64m(0xffffffffu, cf.y, qlead);
         if (empty) {
           if (!do_ins) {
             need = false;  // the key is absent
@@ -380,10 +426,10 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) uni_quad_kernel(const JoinPlanDev
         }
       }
     }
-    if (first_iter) fetch(g + nwarps);
+    if (first_iter) UNI_FETCH(g + nwarps);
     if (created && q == 0) new_keys++;
     // ---- what does the other side hold for the key ?
-    const uint64_t WI = shfl64m(0xffffffffu, pv.y, qlead);
+    const unsigned long long WI = shfl64m(0xffffffffu, pv.y, qlead);
     uint32_t cnt;
     bool fast = false;
     if (!IS_ROW) {
@@ -401,18 +447,17 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) uni_quad_kernel(const JoinPlanDev
       if (q == 1) o.vis[pos] = 1;
       if (po0) po0[pos] = q < 2 ? va : pv.x;
       if (po1) po1[pos] = q < 2 ? vb : pv.y;
+    } else if (in && q == 0) {
+      // deferred rows get their visibility from uni_deferred_kernel; the others are holes
+      if (!(act && (!keyok || cnt > 0u))) { o.vis[pos] = 0; any_hole = true; }
     }
-    const bool slow = keyok && !fast && cnt > 0u;
-    if (keyok && cnt == 0u) {
-      if (q == 0) o.vis[pos] = 0;
-      any_hole = true;
-    }
+    const bool defer = act && !fast && (!keyok || cnt > 0u);
     // extra-match rows: one reservation per warp and U_XCHUNK rows (an atomic per row on the shared counter
     // serialises in one L2 slice)
     int64_t xoff = 0;
     bool xbad = false;
     {
-      const uint32_t xneed = (slow && q == 0 && cnt > 1u) ? cnt - 1u : 0u;
+      const uint32_t xneed = (defer && keyok && q == 0 && cnt > 1u) ? cnt - 1u : 0u;
       if (__any_sync(0xffffffffu, xneed != 0u)) {
         uint32_t incl = xneed;
         for (int d = 1; d < 32; d <<= 1) {
@@ -442,20 +487,30 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) uni_quad_kernel(const JoinPlanDev
         if (!xbad) xnext += total;
       }
     }
-    if (q == 0 && act) {
-      if (slow) {
-        any_match = true;
-        o.vis[pos] = 1;
-        uni_emit_matches(t, w, S, ch, r, ins ? RW_OP_INSERT : RW_OP_DELETE, (int64_t)idx, xbad ? 1u : cnt, o, st, pos, xarea + xoff);
-      } else if (!keyok) {  // the key equal to the EMPTY sentinel lives in a side slot: whole row by this lane
-        uni_row_generic<PROBE_ONLY>(p, w, S, ch, r, op, t, o, st, seq_base + (uint64_t)r, pos, xarea, new_keys, any_match, any_hole);
+    // ---- worklist: one mask byte per group of 8 rows (always written), an entry per deferred row
+    {
+      const unsigned dbal = __ballot_sync(0xffffffffu, defer && q == 0);
+      if (dbal) any_defer = true;
+      if (lane == 0 && g * 8 < n_rows) {
+        unsigned m8 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) m8 |= ((dbal >> (4 * k)) & 1u) << k;
+        wk.mask[g] = (uint8_t)m8;
+      }
+      if (defer && q == 0) {
+        UniDefer e;
+        e.b = keyok ? (int64_t)idx : -1;
+        e.xpos = xarea + xoff;
+        e.cnt = keyok ? (xbad ? 1u : cnt) : 0u;
+        e.pad = 0;
+        wk.entry[r] = e;
       }
     }
     // ---- append to the own side (same bucket)
     if (!PROBE_ONLY) {
       bool need_id = false, inline_won = false;
       unsigned long long Wcur = WI;
-      unsigned long long* Wp = (unsigned long long*)(t.buckets + idx * 64 + 8);
+      unsigned long long* Wp = (unsigned long long*)(buckets + idx * 64 + 8);
       const bool mine = do_ins && keyok && q == 0;
       if (IS_ROW) {
         if (mine) {
@@ -480,8 +535,8 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) uni_quad_kernel(const JoinPlanDev
         uint32_t nb = 0;
         if (left < k) {
           if (lane == 0) {
-            const unsigned long long got = atomicAdd(t.log_next[S], (unsigned long long)pool_chunk);
-            if (got + pool_chunk > t.log_cap[S]) { atomicOr(&st->err, JERR_STORE_CAPACITY); nb = 0xffffffffu; }
+            const unsigned long long got = atomicAdd(own.log_next, (unsigned long long)pool_chunk);
+            if (got + pool_chunk > own.log_cap) { atomicOr(&st->err, JERR_STORE_CAPACITY); nb = 0xffffffffu; }
             else nb = (uint32_t)got;
           }
           nb = __shfl_sync(0xffffffffu, nb, 0);
@@ -497,9 +552,9 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) uni_quad_kernel(const JoinPlanDev
         }
       }
       uint32_t link = 0u;
-      uint64_t recp = 0;  // 0 = nothing to write; bit 0 set = the bucket's inline record
+      unsigned long long recp = 0;  // 0 = nothing to write; bit 0 set = the bucket's inline record
       if (IS_ROW) {
-        if (inline_won) recp = (uint64_t)(t.buckets + idx * 64) | 1ull;
+        if (inline_won) recp = (unsigned long long)(buckets + idx * 64) | 1ull;
         else if (row != U_NIL) {
           while (true) {  // one CAS pushes the row on the key's overflow chain
             const unsigned long long nw = ((Wcur & ~0x7fffffffull) | (unsigned long long)row) + W_COUNT_ONE;
@@ -508,17 +563,17 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) uni_quad_kernel(const JoinPlanDev
             Wcur = old;
           }
           link = W_head(Wcur);
-          recp = (uint64_t)urec(t, S, row);
+          recp = (unsigned long long)useg_rec(own.log, row);
         }
       } else if (row != U_NIL) {
-        link = atomicExch((uint32_t*)(t.buckets + idx * 64 + 24), row);
-        atomicAdd((uint32_t*)(t.buckets + idx * 64 + 28), 1u);
-        recp = (uint64_t)urec(t, S, row);
+        link = atomicExch((uint32_t*)(buckets + idx * 64 + 24), row);
+        atomicAdd((uint32_t*)(buckets + idx * 64 + 28), 1u);
+        recp = (unsigned long long)useg_rec(own.log, row);
       }
       recp = shfl64m(0xffffffffu, recp, qlead);
       link = __shfl_sync(0xffffffffu, link, qlead);
       if (recp && q != 0) {
-        const uint64_t seq = seq_base + (uint64_t)r;
+        const unsigned long long seq = seq_base + (unsigned long long)r;
         if (recp & 1ull) {  // inline: IH (8 bytes: WC sits next to it) + the columns
           uint8_t* bp = (uint8_t*)(recp & ~1ull);
           if (q == 1) *(unsigned long long*)(bp + 16) = seq << 8;
@@ -532,12 +587,14 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) uni_quad_kernel(const JoinPlanDev
       }
     }
   }
+#undef UNI_FETCH
   // leftover of the extra-row reservation
   for (int64_t f = xnext + lane; f < xend; f += 32) { o.ops[xarea + f] = RW_OP_INSERT; o.vis[xarea + f] = 0; }
   if (xend > xnext) any_hole = true;
-  if (!PROBE_ONLY && lane == 0 && (pool_next != pool_next0 || pool_end != pool_end0)) t.pools[S][warp_global] = make_uint2(pool_next, pool_end);
+  if (!PROBE_ONLY && lane == 0 && (pool_next != pool_next0 || pool_end != pool_end0)) own.pools[warp_global] = make_uint2(pool_next, pool_end);
   unsigned long long flags = (any_hole ? (1ull << 63) : 0ull);
   const bool warp_match = __any_sync(0xffffffffu, any_match);
+  const bool warp_defer = __any_sync(0xffffffffu, any_defer);
   for (int d = 16; d > 0; d >>= 1) {
     flags |= __shfl_xor_sync(0xffffffffu, flags, d);
     new_keys += __shfl_xor_sync(0xffffffffu, new_keys, d);
@@ -546,9 +603,37 @@ __global__ void __launch_bounds__(JF_BLOCK, 4) uni_quad_kernel(const JoinPlanDev
   if (lane == 0) {
     if (flags && (__ldcg(&st->null_mask) & flags) != flags) atomicOr(&st->null_mask, flags);
     if (warp_match && __ldcg(&st->pad) == 0u) st->pad = 1u;
+    if (warp_defer && __ldcg(&st->n_defer) == 0ull) st->n_defer = 1ull;  // (plain store: all writers store 1)
     if (!PROBE_ONLY && new_keys) atomicAdd(&st->n_keys[0], (unsigned long long)new_keys);
     if (!PROBE_ONLY && n_del) atomicAdd(&st->n_del, (unsigned long long)n_del);
   }
+}
+
+// the rows uni_hot_kernel deferred, one thread per input row (exits at once when there are none)
+template <bool PROBE_ONLY>
+__global__ void __launch_bounds__(256) uni_deferred_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch, UniDev t, JoinOutDev o,
+                                                           UniWork wk, JoinStatus* st, uint64_t seq_base, int64_t out_base) {
+  if (*(volatile unsigned long long*)&st->n_defer == 0ull) return;
+  const int64_t n_rows = chunk_rows(ch, st, false);
+  unsigned new_keys = 0;
+  bool any_match = false, any_hole = false;
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+    if (!((wk.mask[r >> 3] >> (r & 7)) & 1u)) continue;
+    const UniDefer e = wk.entry[r];
+    const uint8_t op = ch.ops[r];
+    const int64_t pos = out_base + r;
+    if (e.cnt == 0u) {  // whole row (the key equal to the EMPTY sentinel)
+      uni_row_generic<PROBE_ONLY>(p, w, S, ch, r, op, t, o, st, seq_base + (uint64_t)r, pos, out_base + n_rows, new_keys, any_match, any_hole);
+    } else {
+      any_match = true;
+      o.vis[pos] = 1;
+      const bool ins = (op == RW_OP_INSERT || op == RW_OP_UPDATE_INSERT);
+      uni_emit_matches(t, w, S, ch, r, ins ? RW_OP_INSERT : RW_OP_DELETE, e.b, e.cnt, o, st, pos, e.xpos);
+    }
+  }
+  if (any_hole) atomicOr(&st->null_mask, 1ull << 63);
+  if (any_match) st->pad = 1u;
+  if (!PROBE_ONLY && new_keys) atomicAdd(&st->n_keys[0], (unsigned long long)new_keys);
 }
 
 // pk equality of a stored row (columns c[], null mask) with chunk row r
@@ -686,7 +771,7 @@ __global__ void uni_rehash_kernel(const uint8_t* ob, uint64_t ocap, uint8_t* nb,
 // compaction of a side's log (barrier time, when dead records dominate): every chain is copied, live records only
 // and in chain order, into a fresh log -- ids change, links and heads are rewritten, dead rows disappear.
 // One thread per bucket; nothing else runs on the table meanwhile.
-__global__ void uni_compact_kernel(UniDev t, int side, uint8_t* new_log, unsigned long long* new_next) {
+__global__ void uni_compact_kernel(UniDev t, int side, uint8_t* const* new_log, unsigned long long* new_next) {
   const int lane = lane_id();
   for (uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) & ~31ull; i0 < t.cap + 2; i0 += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t i = i0 + lane;
@@ -722,7 +807,7 @@ __global__ void uni_compact_kernel(UniDev t, int side, uint8_t* new_log, unsigne
       const UniRec* rec = urec(t, side, m);
       const uint32_t lk = rec->link;
       if (!(lk & J_DEAD)) {
-        UniRec* d = (UniRec*)(new_log + (uint64_t)nid * 48);
+        UniRec* d = (UniRec*)useg_rec(new_log, nid);
         *d = *rec;
         d->link = U_NIL;
         if (prev) prev->link = nid; else new_head = nid;

@@ -36,6 +36,9 @@ class DeviceChunk:
         return self.ops.numel()
 
     def to_abi(self):
+        cached = getattr(self, "_abi", None)
+        if cached is not None:  # (tensors of a DeviceChunk are never re-bound)
+            return cached
         cols = (abi.RwColumn * max(1, len(self.cols)))()
         for k, (c, t) in enumerate(zip(self.cols, self.types)):
             cols[k].type = t
@@ -47,6 +50,7 @@ class DeviceChunk:
         ch.ops = self.ops.data_ptr() if self.ops.numel() else None
         ch.visibility = self.visibility.data_ptr() if self.visibility is not None else None
         ch.columns = cols
+        self._abi = (ch, cols)
         return ch, cols
 
 

@@ -79,12 +79,27 @@ static void test_hash_agg_count_sum() {
   next_barrier(hash_agg);
   expect_same(next_chunk(hash_agg), " I I I I\n + 3 1 3 3\n - 1 1 1 1\n U- 2 2 4 4\n U+ 2 1 2 2");
   next_barrier(hash_agg);
-  // retractable min is a MaterializedInput state: create must refuse so the shim falls back
+  // a plan the device path does not take: create must refuse so the shim falls back to the CPU executor
   try {
-    HashAggExecutor bad(tx, false, {{RW_AGG_COUNT, -1, RW_T_INT64}, {RW_AGG_MIN, 1, RW_T_INT64}}, 0, {0});
-    EXPECT(false, "retractable min must be unsupported");
+    HashAggExecutor bad(tx, false, {{RW_AGG_COUNT, -1, RW_T_INT64}, {RW_AGG_SUM, 1, RW_T_DECIMAL}}, 0, {0, 1, 2, 0, 1});  // 5 group key columns
+    EXPECT(false, "more than 4 group key columns must be unsupported");
   } catch (const StreamExecutorError& e) {
     EXPECT(e.code == RW_ERR_UNSUPPORTED, "error code");
+  }
+  // retractable min = MaterializedInput state (hash_agg.rs test_hash_agg_min, tests/integration_tests/hash_agg.rs:97-170)
+  {
+    auto tm = std::make_shared<MockSource>(std::vector<int32_t>{RW_T_INT64, RW_T_INT64, RW_T_INT64}, std::vector<int32_t>{});
+    HashAggExecutor agg_min(tm, false, {{RW_AGG_COUNT, -1, RW_T_INT64}, {RW_AGG_MIN, 1, RW_T_INT64}}, 0, {0});
+    tm->push_barrier(1);
+    tm->push_chunk(StreamChunk::from_pretty(" I I I\n + 1 233 1001\n + 1 23333 1002\n + 2 2333 1003"));
+    tm->push_barrier(2);
+    tm->push_chunk(StreamChunk::from_pretty(" I I I\n - 1 233 1001\n - 1 23333 1002 D\n - 2 2333 1003"));
+    tm->push_barrier(3);
+    next_barrier(agg_min);
+    expect_same(next_chunk(agg_min), " I I I\n + 1 2 233\n + 2 1 2333");
+    next_barrier(agg_min);
+    expect_same(next_chunk(agg_min), " I I I\n - 2 1 2333\n U- 1 2 233\n U+ 1 1 23333");
+    next_barrier(agg_min);
   }
 }
 
