@@ -44,8 +44,11 @@ extern "C" {
 #define RW_OP_UPDATE_INSERT 3
 #define RW_OP_UPDATE_DELETE 4
 
-/* ---------------------------------------------------------------- column types (fixed width only;
- * varlen keys are `KeySerialized` in the reference and stay on the CPU executor) */
+/* ---------------------------------------------------------------- column types.  Fixed-width types everywhere; the
+ * two VARLEN types (BytesArray{offset, bitmap, data}, src/common/src/array/bytes_array.rs:30-34) cross the ABI as
+ * PAYLOAD: a join carries them from input to output (stored in a per-side byte heap in HBM), HashAgg / Filter /
+ * Project ignore columns they do not reference.  A varlen column cannot be a join key, a pk column, a group key, an
+ * aggregate argument or a predicate operand here (`KeySerialized` keys stay on the CPU executor).   */
 #define RW_T_BOOL 1        /* 1 byte / row (BoolArray bit-unpacked by the shim)         */
 #define RW_T_INT16 2
 #define RW_T_INT32 3
@@ -59,8 +62,10 @@ extern "C" {
 #define RW_T_SERIAL 11     /* int64 row id                                             */
 #define RW_T_DECIMAL 12    /* 16 bytes: little-endian two's-complement i128 mantissa,
                               scale fixed per column by agreement          */
+#define RW_T_VARCHAR 13    /* varlen: offsets[n_rows + 1] (uint32) into `data` bytes   */
+#define RW_T_BYTEA 14      /* varlen, same layout                                      */
 
-/* width in bytes of one value of `type`, 0 if unknown */
+/* width in bytes of one value of a fixed-width `type`; 0 if unknown or varlen */
 int32_t rwgpu_type_width(int32_t type);
 
 /* ---------------------------------------------------------------- StreamChunk view
@@ -69,8 +74,10 @@ int32_t rwgpu_type_width(int32_t type);
 typedef struct rw_column {
   int32_t type;              /* RW_T_*                                                  */
   int32_t reserved;
-  const void* data;          /* n_rows * width bytes; NULL slots hold any value         */
+  const void* data;          /* n_rows * width bytes; NULL slots hold any value.  Varlen: the bytes */
   const uint64_t* validity;  /* 1 = non-NULL; NULL pointer = no NULLs                   */
+  const uint32_t* offsets;   /* varlen types only: value i = data[offsets[i] .. offsets[i+1]); else NULL.
+                                offsets[0] need not be 0 (chunk views cut from one buffer share `data`) */
 } rw_column;
 
 typedef struct rw_chunk {

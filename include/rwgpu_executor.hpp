@@ -129,7 +129,7 @@ class StreamChunk {
   };
   View view() const {
     View v;
-    for (auto& c : columns) v.cols.push_back(rw_column{c.type, 0, c.data.data(), c.validity.empty() ? nullptr : c.validity.data()});
+    for (auto& c : columns) v.cols.push_back(rw_column{c.type, 0, c.data.data(), c.validity.empty() ? nullptr : c.validity.data(), nullptr});
     v.raw = rw_chunk{capacity(), (int32_t)columns.size(), 0, ops.data(), visibility.empty() ? nullptr : visibility.data(), v.cols.data()};
     return v;
   }

@@ -44,11 +44,13 @@ typedef __int128 i128;
 // ------------------------------------------------------------------ Datum
 struct Datum {
   bool null = true;
-  i128 i = 0;    // all integer-like types, sign-extended; decimal mantissa
-  double f = 0;  // float32 / float64 (float32 kept exactly representable)
+  i128 i = 0;     // all integer-like types, sign-extended; decimal mantissa
+  double f = 0;   // float32 / float64 (float32 kept exactly representable)
+  std::string s;  // varchar / bytea (BytesArray, bytes_array.rs:30-34): payload only
 };
 
 bool is_float(int t) { return t == RW_T_FLOAT32 || t == RW_T_FLOAT64; }
+bool is_varlen(int t) { return t == RW_T_VARCHAR || t == RW_T_BYTEA; }
 
 int type_width(int t) {
   switch (t) {
@@ -69,6 +71,10 @@ Datum read_datum(const rw_column& c, int64_t r) {
   if (!bit_get(c.validity, r)) return d;
   d.null = false;
   const uint8_t* p = (const uint8_t*)c.data;
+  if (is_varlen(c.type)) {
+    d.s.assign((const char*)p + c.offsets[r], (size_t)(c.offsets[r + 1] - c.offsets[r]));
+    return d;
+  }
   switch (c.type) {
     case RW_T_BOOL: d.i = p[r] ? 1 : 0; break;
     case RW_T_INT16: { int16_t v; memcpy(&v, p + r * 2, 2); d.i = v; break; }
@@ -84,6 +90,7 @@ Datum read_datum(const rw_column& c, int64_t r) {
 // OrderedFloat equality: NaN == NaN, -0 == +0 (src/common/src/types/ordered_float.rs)
 bool datum_eq(const Datum& a, const Datum& b, int type) {
   if (a.null || b.null) return a.null && b.null;
+  if (is_varlen(type)) return a.s == b.s;
   if (is_float(type)) {
     if (std::isnan(a.f) || std::isnan(b.f)) return std::isnan(a.f) && std::isnan(b.f);
     return a.f == b.f;
@@ -136,6 +143,7 @@ struct OutCol {
   int type = 0;
   std::vector<uint8_t> data;
   std::vector<uint64_t> valid;
+  std::vector<uint32_t> offsets;  // varlen columns: n + 1 entries
   bool has_null = false;
 };
 struct OutChunk {
@@ -162,6 +170,15 @@ void bit_push(std::vector<uint64_t>& w, int64_t i, bool v) {
 }
 
 void write_datum(OutCol& c, const Datum& d) {
+  if (is_varlen(c.type)) {
+    if (c.offsets.empty()) c.offsets.push_back(0);
+    const int64_t r = (int64_t)c.offsets.size() - 1;
+    bit_push(c.valid, r, !d.null);
+    if (d.null) c.has_null = true;
+    else c.data.insert(c.data.end(), d.s.begin(), d.s.end());
+    c.offsets.push_back((uint32_t)c.data.size());
+    return;
+  }
   int w = type_width(c.type);
   size_t off = c.data.size();
   c.data.resize(off + w, 0);
@@ -251,6 +268,14 @@ void finalize_views(rwgpu_out* o) {
       c.views[i].reserved = 0;
       c.views[i].data = c.cols[i].data.data();
       c.views[i].validity = c.cols[i].has_null ? c.cols[i].valid.data() : nullptr;
+      if (is_varlen(c.cols[i].type)) {
+        if (c.cols[i].offsets.empty()) c.cols[i].offsets.push_back(0);
+        if (c.cols[i].data.empty()) c.cols[i].data.push_back(0);  // a non-NULL data pointer even for zero bytes
+        c.views[i].data = c.cols[i].data.data();
+        c.views[i].offsets = c.cols[i].offsets.data();
+      } else {
+        c.views[i].offsets = nullptr;
+      }
     }
   }
 }
@@ -666,6 +691,9 @@ int32_t rwo_join_create(const rw_join_desc* d, rwo_join** out) {
     x.pk_idx.assign(sd[s]->pk_indices, sd[s]->pk_indices + sd[s]->n_pk);
     x.stream_key.assign(sd[s]->stream_key, sd[s]->stream_key + sd[s]->n_stream_key);
     x.pk_in_jk = is_subset(x.stream_key, x.key_idx);  // :377-378
+    // varlen columns are payload only at this boundary (rwgpu.h): a varlen join key would be `KeySerialized`
+    for (int k : x.key_idx) if (is_varlen(x.types[k])) { delete h; return fail(RW_ERR_UNSUPPORTED, "varlen join key"); }
+    for (int k : x.pk_idx) if (is_varlen(x.types[k])) { delete h; return fail(RW_ERR_UNSUPPORTED, "varlen pk column"); }
   }
   j.side[0].start_pos = 0;
   j.side[1].start_pos = j.side[0].n_cols;

@@ -24,6 +24,8 @@ OP_INSERT, OP_DELETE, OP_UPDATE_INSERT, OP_UPDATE_DELETE = 1, 2, 3, 4
 # ---- types
 T_BOOL, T_INT16, T_INT32, T_INT64, T_FLOAT32, T_FLOAT64 = 1, 2, 3, 4, 5, 6
 T_DATE, T_TIME, T_TIMESTAMP, T_TIMESTAMPTZ, T_SERIAL, T_DECIMAL = 7, 8, 9, 10, 11, 12
+T_VARCHAR, T_BYTEA = 13, 14  # varlen payload: offsets[n + 1] + bytes
+VARLEN_TYPES = (T_VARCHAR, T_BYTEA)
 
 TYPE_WIDTH = {T_BOOL: 1, T_INT16: 2, T_INT32: 4, T_INT64: 8, T_FLOAT32: 4, T_FLOAT64: 8, T_DATE: 4,
               T_TIME: 8, T_TIMESTAMP: 8, T_TIMESTAMPTZ: 8, T_SERIAL: 8, T_DECIMAL: 16}
@@ -38,7 +40,7 @@ CMP_NONE, CMP_LT, CMP_LE, CMP_GT, CMP_GE, CMP_EQ, CMP_NE = range(7)
 
 class RwColumn(C.Structure):
     _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("data", C.c_void_p),
-                ("validity", C.c_void_p)]
+                ("validity", C.c_void_p), ("offsets", C.c_void_p)]
 
 
 class RwChunk(C.Structure):

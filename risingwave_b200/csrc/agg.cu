@@ -1405,6 +1405,7 @@ int32_t rwgpu_agg_create(const rw_agg_desc* d, rwgpu_agg** out) {
     int c = d->group_key_indices[k];
     if (c < 0 || c >= d->n_input_cols) return fail(RW_ERR_INVALID, "group key index");
     if (h->in_types[c] == RW_T_DECIMAL) return fail(RW_ERR_UNSUPPORTED, "decimal group key");
+    if (type_is_varlen(h->in_types[c])) return fail(RW_ERR_UNSUPPORTED, "varlen group key (KeySerialized) stays on the CPU executor");
     p.key_col[k] = c;
     p.key_type[k] = h->in_types[c];
     used[c] = true;
@@ -1430,6 +1431,7 @@ int32_t rwgpu_agg_create(const rw_agg_desc* d, rwgpu_agg** out) {
       used[call.arg_col] = true;
     }
     p.arg_type[c] = at;
+    if (type_is_varlen(at)) return fail(RW_ERR_UNSUPPORTED, "aggregates over varlen arguments stay on the CPU executor");
     switch (call.kind) {
       case RW_AGG_COUNT:
         if (call.ret_type != RW_T_INT64) return fail(RW_ERR_INVALID, "count returns int8");

@@ -48,10 +48,14 @@ int type_width(int t) {
     case RW_T_INT64: case RW_T_FLOAT64: case RW_T_TIME: case RW_T_TIMESTAMP:
     case RW_T_TIMESTAMPTZ: case RW_T_SERIAL: return 8;
     case RW_T_DECIMAL: return 16;
+    // varlen payload: inside the library a value is an 8-byte HANDLE (heap offset | length | heap id) into a byte heap
+    // in HBM; the bytes themselves only move when a chunk enters (interned) or leaves (materialised)
+    case RW_T_VARCHAR: case RW_T_BYTEA: return 8;
     default: return 0;
   }
 }
 bool type_is_float(int t) { return t == RW_T_FLOAT32 || t == RW_T_FLOAT64; }
+bool type_is_varlen(int t) { return t == RW_T_VARCHAR || t == RW_T_BYTEA; }
 bool type_supported(int t) { return type_width(t) != 0; }
 
 int devchunk_from_abi(const rw_chunk* c, DevChunk* out) {
@@ -84,9 +88,13 @@ bool rwgpu_out::layout(int64_t rows, const std::vector<int>& col_types, unsigned
   data.assign(types.size(), nullptr);
   valid_bytes.assign(types.size(), nullptr);
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  offsets.assign(types.size(), nullptr);
+  auto col_bytes = [&](size_t k) {  // a varlen column's block share is its offsets array; the bytes come later (set_var_bytes)
+    return rw::type_is_varlen(types[k]) ? (size_t)(rows + 1) * 4 : (size_t)rows * rw::type_width(types[k]);
+  };
   size_t total = up((size_t)rows) * (1 + (with_vis ? 1 : 0));
   for (size_t k = 0; k < types.size(); k++) {
-    total += up((size_t)rows * rw::type_width(types[k]));
+    total += up(col_bytes(k));
     if ((null_mask >> k) & 1) total += up((size_t)rows);
   }
   if (rows == 0) return true;
@@ -96,10 +104,20 @@ bool rwgpu_out::layout(int64_t rows, const std::vector<int>& col_types, unsigned
   ops = block.p + off; off += up((size_t)rows);
   if (with_vis) { vis_bytes = block.p + off; off += up((size_t)rows); }
   for (size_t k = 0; k < types.size(); k++) {
-    data[k] = block.p + off; off += up((size_t)rows * rw::type_width(types[k]));
+    if (rw::type_is_varlen(types[k])) offsets[k] = (uint32_t*)(block.p + off);
+    else data[k] = block.p + off;
+    off += up(col_bytes(k));
     if ((null_mask >> k) & 1) { valid_bytes[k] = block.p + off; off += up((size_t)rows); }
   }
   return true;
+}
+
+// pinned bytes of varlen column k (owned by the output object)
+uint8_t* rwgpu_out::var_bytes(size_t k, size_t bytes) {
+  var_store.emplace_back(new rw::PinnedBuf());
+  if (var_store.back()->reserve(std::max<size_t>(bytes, 16)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  data[k] = var_store.back()->as<uint8_t>();
+  return data[k];
 }
 
 // Cut the super-chunk into StreamChunks of <= chunk_size rows; a U- is never the last row of a
@@ -138,7 +156,13 @@ void rwgpu_out::finalize() {
       rw_column& c = chunk_cols[i][k];
       c.type = types[k];
       c.reserved = 0;
-      c.data = data[k] + (size_t)lo * wd;
+      c.offsets = nullptr;
+      if (rw::type_is_varlen(types[k])) {  // chunk views share the column's bytes; their offsets are a slice
+        c.data = data[k];
+        c.offsets = offsets[k] + lo;
+      } else {
+        c.data = data[k] + (size_t)lo * wd;
+      }
       c.validity = nullptr;
       if (valid_bytes[k]) {
         bool all = true;
@@ -157,7 +181,7 @@ void rwgpu_out::finalize() {
 
 extern "C" {
 
-int32_t rwgpu_type_width(int32_t type) { return rw::type_width(type); }
+int32_t rwgpu_type_width(int32_t type) { return rw::type_is_varlen(type) ? 0 : rw::type_width(type); }
 const char* rwgpu_last_error(void) { return rw::last_error_cstr(); }
 const char* rwgpu_version(void) { return "rwgpu 0.1.0 sm_100a"; }
 

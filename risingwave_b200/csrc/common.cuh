@@ -29,6 +29,7 @@ const char* last_error_cstr();
 
 int type_width(int t);
 bool type_is_float(int t);
+bool type_is_varlen(int t);
 bool type_supported(int t);
 
 // ------------------------------------------------------------------ device buffer (RAII)
@@ -317,7 +318,10 @@ struct rwgpu_out {
   std::vector<int> types;
   uint8_t* ops = nullptr;
   uint8_t* vis_bytes = nullptr;            // nullptr = all visible
-  std::vector<uint8_t*> data;              // per column, native width
+  std::vector<uint8_t*> data;              // per column, native width (varlen: the bytes, see var_bytes)
+  std::vector<uint32_t*> offsets;          // per column: varlen offsets[n_rows + 1], nullptr for fixed-width columns
+  std::vector<std::unique_ptr<rw::PinnedBuf>> var_store;
+  uint8_t* var_bytes(size_t k, size_t bytes);
   std::vector<uint8_t*> valid_bytes;       // per column, nullptr = no NULLs
   PinnedBlock block;
   std::shared_ptr<PinnedPool> pool;

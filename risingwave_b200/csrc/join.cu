@@ -125,6 +125,7 @@ struct JoinOutDev {
   void* col[J_MAX_OUT];
   uint8_t* valid[J_MAX_OUT];    // kept at 1; only NULLs are written (0)
   int64_t capacity;
+  const uint8_t* heap[2];       // varlen payload: the sides' byte heaps (handles in varlen output columns point here)
 };
 
 // join/mod.rs:103-169
@@ -1438,6 +1439,15 @@ static inline size_t align_up_j(size_t x, size_t a) { return (x + a - 1) / a * a
 
 #include "join_uni.cuh"
 
+namespace rw {
+// varlen payload handles (see "varlen payload columns" below)
+#define VH_LEN_MAX ((1u << 22) - 1u)
+__device__ __host__ __forceinline__ uint64_t vh_make(int heap, uint32_t len, uint64_t off) { return ((uint64_t)heap << 62) | ((uint64_t)len << 40) | off; }
+__device__ __host__ __forceinline__ uint64_t vh_off(uint64_t h) { return h & ((1ull << 40) - 1); }
+__device__ __host__ __forceinline__ uint32_t vh_len(uint64_t h) { return (uint32_t)((h >> 40) & VH_LEN_MAX); }
+__device__ __host__ __forceinline__ int vh_heap(uint64_t h) { return (int)(h >> 62); }
+}  // namespace rw
+
 // =============================================================================== eliminate_adjacent_noop_update
 // StreamChunk::eliminate_adjacent_noop_update (src/common/src/array/stream_chunk.rs:331-392), applied by
 // JoinChunkBuilder::post_process to every chunk the join yields: walking the visible rows of a chunk, a Delete-then-
@@ -1460,6 +1470,16 @@ __device__ __forceinline__ bool out_rows_equal(const JoinOutDev& o, const JoinPl
     const int w = p->out_width[k];
     const uint8_t* x = (const uint8_t*)o.col[k] + a * w;
     const uint8_t* y = (const uint8_t*)o.col[k] + b * w;
+    if (p->out_type[k] == RW_T_VARCHAR || p->out_type[k] == RW_T_BYTEA) {  // handles: compare the bytes they name
+      const uint64_t hx = *(const uint64_t*)x, hy = *(const uint64_t*)y;
+      if (hx == hy) continue;
+      const uint32_t len = vh_len(hx);
+      if (len != vh_len(hy)) return false;
+      const uint8_t* bx = o.heap[vh_heap(hx) - 1] + vh_off(hx);
+      const uint8_t* by = o.heap[vh_heap(hy) - 1] + vh_off(hy);
+      for (uint32_t i = 0; i < len; i++) if (bx[i] != by[i]) return false;
+      continue;
+    }
     switch (w) {
       case 1: if (*x != *y) return false; break;
       case 2: if (*(const uint16_t*)x != *(const uint16_t*)y) return false; break;
@@ -1516,6 +1536,73 @@ __global__ void noop_normalize_kernel(JoinOutDev o, int64_t n, int chunk_size) {
       if (dv && !iv) o.ops[i] = RW_OP_DELETE;
       else if (!dv && iv) o.ops[i + 1] = RW_OP_INSERT;
     }
+  }
+}
+}  // namespace rw
+
+// =============================================================================== varlen payload columns
+// A varchar / bytea column (BytesArray{offset, bitmap, data}, src/common/src/array/bytes_array.rs:30-34) travels through
+// the join as PAYLOAD.  When a chunk enters, the bytes of its visible rows are INTERNED into the side's byte heap in
+// HBM and the column becomes a column of 8-byte handles
+//     bits 0..39 heap offset | bits 40..61 length (< 4 MiB) | bits 62..63 heap id (1 = left, 2 = right)
+// which every join kernel treats like any other 8-byte column (stored in buckets / logs, gathered into the output).
+// When a result leaves, the handles of a varlen output column are turned back into offsets[n + 1] + bytes: lengths ->
+// exclusive scan -> gather.  The heap is append-only (a deleted row's bytes stay until the operator is rebuilt).
+namespace rw {
+
+// bytes: base pointer such that value r is bytes[offs[r] .. offs[r+1])
+__global__ void __launch_bounds__(256) varlen_intern_kernel(const uint8_t* bytes, const uint32_t* offs, const uint8_t* ops, const uint64_t* vis_bits,
+                                                            const uint64_t* valid_bits, int64_t n, uint8_t* heap, unsigned long long* heap_next,
+                                                            uint64_t heap_cap, int heap_id, uint64_t* handles, unsigned int* err) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) & ~31ll; r0 < n; r0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = r0 + lane;
+    uint32_t len = 0, o0 = 0;
+    bool live = false;
+    if (r < n) {
+      live = ops[r] != 0 && bit_get(vis_bits, r) && bit_get(valid_bits, r);
+      if (live) { o0 = offs[r]; len = offs[r + 1] - o0; }
+    }
+    if (len > VH_LEN_MAX) { atomicOr(err, 1u); len = 0; live = false; }
+    const uint32_t need = (len + 7u) & ~7u;
+    uint32_t incl = need;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && total) base = atomicAdd(heap_next, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (r >= n) continue;
+    uint64_t hd = 0;
+    if (live) {
+      const unsigned long long at = base + (incl - need);
+      if (at + need > heap_cap) { atomicOr(err, 2u); }
+      else {
+        for (uint32_t i = 0; i < len; i++) heap[at + i] = bytes[o0 + i];
+        hd = vh_make(heap_id, len, at);
+      }
+    }
+    handles[r] = hd;
+  }
+}
+
+__global__ void varlen_lens_kernel(const uint64_t* handles, const uint8_t* vis, const uint8_t* valid, int64_t n, uint32_t* lens) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const bool live = (!vis || vis[r]) && (!valid || valid[r]);
+    lens[r] = live ? vh_len(handles[r]) : 0u;
+  }
+}
+__global__ void varlen_total_kernel(const uint32_t* lens, uint32_t* offs, int64_t n) { offs[n] = n ? offs[n - 1] + lens[n - 1] : 0u; }
+__global__ void varlen_gather_kernel(const uint64_t* handles, const uint32_t* offs, int64_t n, const uint8_t* heap_l, const uint8_t* heap_r, uint8_t* out) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t len = offs[r + 1] - offs[r];
+    if (!len) continue;
+    const uint64_t hd = handles[r];
+    const uint8_t* src = (vh_heap(hd) == 1 ? heap_l : heap_r) + vh_off(hd);
+    uint8_t* dst = out + offs[r];
+    for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
   }
 }
 }  // namespace rw
@@ -1700,6 +1787,13 @@ struct rwgpu_join {
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
   std::vector<rw_column> dev_view_cols[2];  // per output set
   DevBuf noop_nxt, noop_prv, noop_elig, noop_flag;  // eliminate_adjacent_noop_update scratch
+  // varlen payload (see varlen_intern_kernel): per-side byte heaps, per input column handle staging, per output column bytes
+  std::vector<int> var_in[2];        // varlen columns of each side
+  std::vector<int> var_out;          // varlen output columns
+  DevBuf var_heap[2], var_ctr;       // var_ctr: heap_next[2] (u64), err (u32)
+  uint64_t var_cap[2] = {0, 0}, var_upper[2] = {0, 0};
+  DevBuf var_handles[RW_MAX_COLS], var_stage_off[RW_MAX_COLS], var_stage_bytes[RW_MAX_COLS];  // device staging of an input chunk
+  struct VarOut { DevBuf lens, offs, bytes, tmp; size_t tmp_bytes = 0; int64_t cap = 0; uint32_t total = 0; } vout[2][J_MAX_OUT];
   int64_t noop_cap = 0;
   bool call_had_deletes = false;            // some push of the current API call saw visible Delete / UpdateDelete rows
   bool call_vis_stale = false;              // the scan-based kernel compacts its output and never writes vis bytes
@@ -1852,6 +1946,8 @@ static JoinOutDev out_dev(rwgpu_join* h) {
   o.vis = h->os().out_vis.as<uint8_t>();
   for (size_t k = 0; k < h->out_types.size(); k++) { o.col[k] = h->os().out_col[k].p; o.valid[k] = h->os().out_valid[k].as<uint8_t>(); }
   o.capacity = h->os().out_cap;
+  o.heap[0] = h->var_heap[0].as<uint8_t>();
+  o.heap[1] = h->var_heap[1].as<uint8_t>();
   return o;
 }
 
@@ -2473,15 +2569,19 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
     }
     p.stride[s] = (off + 15) / 16 * 16;
     hs.stride = p.stride[s];
+    for (int c = 0; c < sd[s]->n_cols; c++)
+      if (type_is_varlen(sd[s]->types[c])) h->var_in[s].push_back(c);
     for (int k = 0; k < d->n_keys; k++) {
       int c = sd[s]->key_indices[k];
       if (c < 0 || c >= sd[s]->n_cols) return fail(RW_ERR_INVALID, "join key index");
       if (sd[s]->types[c] == RW_T_DECIMAL) return fail(RW_ERR_UNSUPPORTED, "decimal join key");
+      if (type_is_varlen(sd[s]->types[c])) return fail(RW_ERR_UNSUPPORTED, "varlen join key (KeySerialized) stays on the CPU executor");
       p.key_col[s][k] = c;
     }
     p.n_pk[s] = sd[s]->n_pk;
     for (int i = 0; i < sd[s]->n_pk; i++) {
       if (sd[s]->pk_indices[i] < 0 || sd[s]->pk_indices[i] >= sd[s]->n_cols) return fail(RW_ERR_INVALID, "pk index");
+      if (type_is_varlen(sd[s]->types[sd[s]->pk_indices[i]])) return fail(RW_ERR_UNSUPPORTED, "varlen pk column");
       p.pk_col[s][i] = sd[s]->pk_indices[i];
     }
     // pk_contained_in_jk (hash_join.rs:377-378)
@@ -2518,6 +2618,7 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
     p.out_type[oi] = nat[idx];
     p.out_width[oi] = type_width(nat[idx]);
     h->out_types.push_back(nat[idx]);
+    if (type_is_varlen(nat[idx])) h->var_out.push_back(oi);
     int s = idx < left_len ? 0 : 1;
     int local = idx < left_len ? idx : idx - left_len;
     p.map_in[s][p.n_map[s]] = local;
@@ -2533,7 +2634,7 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
       return fail(RW_ERR_INVALID, "join condition");
     for (int idx : {p.cond_lhs, p.cond_rhs}) {
       int t = idx < d->left.n_cols ? d->left.types[idx] : d->right.types[idx - d->left.n_cols];
-      if (type_is_float(t) || t == RW_T_DECIMAL) return fail(RW_ERR_UNSUPPORTED, "non-integer join condition stays on the CPU executor");
+      if (type_is_float(t) || t == RW_T_DECIMAL || type_is_varlen(t)) return fail(RW_ERR_UNSUPPORTED, "non-integer join condition stays on the CPU executor");
     }
   }
   p.single_key = (p.n_keys == 1);
@@ -2578,6 +2679,8 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
   h->uni_is = pk_in_jk[1] ? 1 : (pk_in_jk[0] ? 0 : 1);
 
   RW_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  RW_CUDA(h->var_ctr.reserve(32));
+  RW_CUDA(cudaMemsetAsync(h->var_ctr.p, 0, 32, h->stream));
   RW_CUDA(h->plan_dev.reserve(sizeof(JoinPlanDev)));
   RW_CUDA(cudaMemcpyAsync(h->plan_dev.p, &p, sizeof(p), cudaMemcpyHostToDevice, h->stream));
   RW_CUDA(h->status.reserve(sizeof(JoinStatus)));
@@ -2633,6 +2736,106 @@ int32_t rwgpu_join_push_device(rwgpu_join* h, int32_t side, const rw_chunk* c, r
   return rwgpu_join_push_device_counted(h, side, c, nullptr, view, cuda_stream);
 }
 
+// ---- varlen payload: heaps, interning, materialisation (see varlen_intern_kernel)
+static int var_ensure_heap(rwgpu_join* h, int S, uint64_t bytes) {
+  if (h->var_upper[S] + bytes <= h->var_cap[S]) return RW_OK;
+  RW_CUDA(cudaDeviceSynchronize());
+  unsigned long long used = 0;
+  RW_CUDA(cudaMemcpy(&used, h->var_ctr.as<unsigned long long>() + S, 8, cudaMemcpyDeviceToHost));
+  h->var_upper[S] = used;
+  if (used + bytes <= h->var_cap[S]) return RW_OK;
+  const uint64_t ncap = std::max<uint64_t>(std::max<uint64_t>(h->var_cap[S] * 2, (used + bytes) + (used + bytes) / 2), 1 << 20);
+  if (ncap >= (1ull << 40)) return fail(RW_ERR_OOM, "varlen heap exceeds 1 TiB");
+  DevBuf nb;
+  RW_CUDA(nb.reserve((size_t)ncap));
+  if (used) RW_CUDA(cudaMemcpy(nb.p, h->var_heap[S].p, (size_t)used, cudaMemcpyDeviceToDevice));
+  h->var_heap[S] = std::move(nb);
+  h->var_cap[S] = ncap;
+  return RW_OK;
+}
+
+// intern rows [0, m) of one varlen column (device pointers; value r = bytes_base[offs[r] .. offs[r+1])) -> handles[m]
+static int var_intern(rwgpu_join* h, int S, const uint8_t* bytes_base, const uint32_t* offs, const uint8_t* ops, const uint64_t* vis_bits,
+                      const uint64_t* valid_bits, int64_t m, uint64_t* handles, cudaStream_t st) {
+  if (m <= 0) return RW_OK;
+  varlen_intern_kernel<<<jgrid(m, 256), 256, 0, st>>>(bytes_base, offs, ops, vis_bits, valid_bits, m, h->var_heap[S].as<uint8_t>(),
+                                                       h->var_ctr.as<unsigned long long>() + S, h->var_cap[S], S + 1, handles,
+                                                       (unsigned int*)(h->var_ctr.as<unsigned long long>() + 2));
+  RW_CUDA(cudaGetLastError());
+  h->launches++;
+  return RW_OK;
+}
+
+static int var_check_err(rwgpu_join* h, cudaStream_t st) {
+  unsigned int e = 0;
+  RW_CUDA(cudaMemcpyAsync(&e, h->var_ctr.as<unsigned long long>() + 2, 4, cudaMemcpyDeviceToHost, st));
+  RW_CUDA(cudaStreamSynchronize(st));
+  if (!e) return RW_OK;
+  RW_CUDA(cudaMemsetAsync(h->var_ctr.as<unsigned long long>() + 2, 0, 4, st));
+  if (e & 1u) return fail(RW_ERR_UNSUPPORTED, "a varlen value of 4 MiB or more");
+  return fail(RW_ERR_CUDA, "internal: varlen heap capacity");
+}
+
+// handles[n] (device) -> vo.offs[n + 1] + vo.bytes on the device; vo.total = bytes.  vis / valid: byte arrays or nullptr.
+static int var_materialize(rwgpu_join* h, rwgpu_join::VarOut& vo, const uint64_t* handles, const uint8_t* vis, const uint8_t* valid, int64_t n,
+                           cudaStream_t st) {
+  if (n + 1 > vo.cap) {
+    RW_CUDA(cudaStreamSynchronize(st));
+    const int64_t cap = n + n / 4 + 64;
+    RW_CUDA(vo.lens.reserve((size_t)cap * 4));
+    RW_CUDA(vo.offs.reserve((size_t)cap * 4));
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)cap);
+    RW_CUDA(vo.tmp.reserve(tb + 256));
+    vo.tmp_bytes = tb + 256;
+    vo.cap = cap;
+  }
+  vo.total = 0;
+  if (n == 0) { RW_CUDA(cudaMemsetAsync(vo.offs.p, 0, 4, st)); return RW_OK; }
+  varlen_lens_kernel<<<jgrid(n, 256), 256, 0, st>>>(handles, vis, valid, n, vo.lens.as<uint32_t>());
+  size_t tb = vo.tmp_bytes;
+  cub::DeviceScan::ExclusiveSum(vo.tmp.p, tb, vo.lens.as<uint32_t>(), vo.offs.as<uint32_t>(), (int)n, st);
+  varlen_total_kernel<<<1, 1, 0, st>>>(vo.lens.as<uint32_t>(), vo.offs.as<uint32_t>(), n);
+  RW_CUDA(cudaGetLastError());
+  uint32_t total = 0;
+  RW_CUDA(cudaMemcpyAsync(&total, vo.offs.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, st));
+  RW_CUDA(cudaStreamSynchronize(st));
+  vo.total = total;
+  RW_CUDA(vo.bytes.reserve((size_t)total + 16));
+  if (total) {
+    varlen_gather_kernel<<<jgrid(n, 256), 256, 0, st>>>(handles, vo.offs.as<uint32_t>(), n, h->var_heap[0].as<uint8_t>(), h->var_heap[1].as<uint8_t>(),
+                                                         vo.bytes.as<uint8_t>());
+    RW_CUDA(cudaGetLastError());
+  }
+  h->launches += 4;
+  return RW_OK;
+}
+
+// device chunk with varlen columns (rw_chunk pointers are DEVICE pointers): intern them, point the DevChunk at the handles
+static int var_intern_device_chunk(rwgpu_join* h, int side, const rw_chunk* c, DevChunk* ch, cudaStream_t st) {
+  if (h->var_in[side].empty()) return RW_OK;
+  if (ch->n_dev) return fail(RW_ERR_UNSUPPORTED, "a device-resident row count with varlen columns");
+  const int64_t n = c->n_rows;
+  for (int k : h->var_in[side]) {
+    if (n && !c->columns[k].offsets) return fail(RW_ERR_INVALID, "varlen column without offsets");
+    uint32_t o0 = 0, o1 = 0;
+    if (n) {
+      RW_CUDA(cudaMemcpyAsync(&o0, c->columns[k].offsets, 4, cudaMemcpyDeviceToHost, st));
+      RW_CUDA(cudaMemcpyAsync(&o1, c->columns[k].offsets + n, 4, cudaMemcpyDeviceToHost, st));
+      RW_CUDA(cudaStreamSynchronize(st));
+    }
+    int rc = var_ensure_heap(h, side, (uint64_t)(o1 - o0) + 8ull * (uint64_t)n);
+    if (rc != RW_OK) return rc;
+    h->var_upper[side] += (uint64_t)(o1 - o0) + 8ull * (uint64_t)n;
+    RW_CUDA(h->var_handles[k].reserve((size_t)std::max<int64_t>(n, 1) * 8));
+    rc = var_intern(h, side, (const uint8_t*)c->columns[k].data, c->columns[k].offsets, c->ops, c->visibility, c->columns[k].validity, n,
+                    h->var_handles[k].as<uint64_t>(), st);
+    if (rc != RW_OK) return rc;
+    ch->cols[k].data = h->var_handles[k].p;
+  }
+  return var_check_err(h, st);
+}
+
 // JoinChunkBuilder::post_process (join/builder.rs:166-168): eliminate_adjacent_noop_update on what the call emitted.
 // Only a call that saw Delete rows can have emitted a Delete / Insert pair.
 static int join_post_process(rwgpu_join* h, int64_t n, unsigned long long* nullm, cudaStream_t st) {
@@ -2654,6 +2857,15 @@ static int join_fill_view(rwgpu_join* h, int64_t n, unsigned long long nullm, rw
     col.reserved = 0;
     col.data = h->os().out_col[k].p;
     col.validity = nullptr;
+    col.offsets = nullptr;
+    if (type_is_varlen(h->out_types[k])) {  // handles -> offsets + bytes (device)
+      rwgpu_join::VarOut& vo = h->vout[h->cur][k];
+      int rc = var_materialize(h, vo, h->os().out_col[k].as<uint64_t>(), (nullm >> 63) ? h->os().out_vis.as<uint8_t>() : nullptr,
+                               ((nullm >> k) & 1) ? h->os().out_valid[k].as<uint8_t>() : nullptr, n, st);
+      if (rc != RW_OK) return rc;
+      col.data = vo.bytes.p;
+      col.offsets = vo.offs.as<uint32_t>();
+    }
     if (((nullm >> k) & 1) && n > 0) {
       pack_bytes_to_bits_kernel<<<jgrid((n + 63) / 64, 256), 256, 0, st>>>(h->os().out_valid[k].as<uint8_t>(), h->os().out_bits[k].as<uint64_t>(), n);
       RW_CUDA(cudaGetLastError());
@@ -2689,6 +2901,8 @@ int32_t rwgpu_join_push_device_counted(rwgpu_join* h, int32_t side, const rw_chu
   unsigned long long nullm = 0;
   rc = join_begin_call(h, st);
   if (rc != RW_OK) return rc;
+  rc = var_intern_device_chunk(h, side, c, &ch, st);
+  if (rc != RW_OK) return rc;
   rc = join_push_dev(h, side, ch, st, 0, &n, &nullm);
   if (rc != RW_OK) return rc;
   rc = join_post_process(h, n, &nullm, st);
@@ -2714,7 +2928,9 @@ int32_t rwgpu_join_push_device_async(rwgpu_join* h, int32_t side, const rw_chunk
   rc = join_begin_call(h, st);
   if (rc != RW_OK) return rc;
   JoinPending pd;
-  if (h->uni && ch.n > 0 && ch.n < (1ll << 31)) {
+  rc = var_intern_device_chunk(h, side, c, &ch, st);
+  if (rc != RW_OK) return rc;
+  if (h->uni && ch.n > 0 && ch.n < (1ll << 31) && h->var_in[side].empty()) {
     rc = uni_enqueue(h, side, ch, st, 0, &pd);
     if (rc != RW_OK) return rc;
   } else {
@@ -2786,10 +3002,24 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
   size_t off = 0;
   auto region = [&](size_t bytes) { size_t o = align_up_j(off, 256); off = o + bytes; return o; };
   const size_t o_ops = region((size_t)n), o_vis = region(nw);
-  size_t o_data[RW_MAX_COLS], o_valid[RW_MAX_COLS];
+  size_t o_data[RW_MAX_COLS], o_valid[RW_MAX_COLS], o_voff[RW_MAX_COLS], o_vbytes[RW_MAX_COLS];
+  uint64_t var_bytes_in = 0;  // bytes of the chunk's varlen columns (interned into the side's heap below)
   for (int k = 0; k < c->n_cols; k++) {
-    o_data[k] = region((size_t)n * type_width(c->columns[k].type));
+    o_data[k] = region((size_t)n * type_width(c->columns[k].type));  // (varlen: the 8-byte handles)
     o_valid[k] = region(nw);
+    o_voff[k] = o_vbytes[k] = 0;
+    if (type_is_varlen(c->columns[k].type)) {
+      if (n && !c->columns[k].offsets) return fail(RW_ERR_INVALID, "varlen column without offsets");
+      const size_t vb = n ? (size_t)(c->columns[k].offsets[n] - c->columns[k].offsets[0]) : 0;
+      o_voff[k] = region((size_t)(n + 1) * 4);
+      o_vbytes[k] = region(vb + 16);
+      var_bytes_in += vb + 8ull * (uint64_t)n;
+    }
+  }
+  if (var_bytes_in) {
+    int rcv = var_ensure_heap(h, side, var_bytes_in);
+    if (rcv != RW_OK) return rcv;
+    h->var_upper[side] += var_bytes_in;
   }
   RW_CUDA(h->up.reserve(off + 256));
   RW_CUDA(h->up_host.reserve(off + 256));
@@ -2819,7 +3049,13 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
     if (c->visibility) h2d(o_vis + wlo, (const uint8_t*)c->visibility + wlo, wn, false);
     for (int k = 0; k < c->n_cols; k++) {
       const int w = type_width(c->columns[k].type);
-      h2d(o_data[k] + (size_t)lo * w, (const uint8_t*)c->columns[k].data + (size_t)lo * w, (size_t)m * w, pin_col[k]);
+      if (type_is_varlen(c->columns[k].type)) {  // offsets lo .. lo+m and the bytes they span
+        const uint32_t* of = c->columns[k].offsets;
+        h2d(o_voff[k] + (size_t)lo * 4, of + lo, (size_t)(m + 1) * 4, false);
+        h2d(o_vbytes[k] + (size_t)(of[lo] - of[0]), (const uint8_t*)c->columns[k].data + of[lo], (size_t)(of[lo + m] - of[lo]), pin_col[k]);
+      } else {
+        h2d(o_data[k] + (size_t)lo * w, (const uint8_t*)c->columns[k].data + (size_t)lo * w, (size_t)m * w, pin_col[k]);
+      }
       if (c->columns[k].validity) h2d(o_valid[k] + wlo, (const uint8_t*)c->columns[k].validity + wlo, wn, false);
     }
     RW_CUDA(cudaEventRecord(h->ev_h2d[n_sub], h->s_h2d));
@@ -2843,7 +3079,7 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
   std::vector<int> alias_src(h->out_types.size(), -1);
   if (alias_ok)
     for (int k = 0; k < c->n_cols; k++)
-      if (h->w8[side].u_out[k] >= 0) alias_src[(size_t)h->w8[side].u_out[k]] = k;
+      if (h->w8[side].u_out[k] >= 0 && !type_is_varlen(c->columns[k].type)) alias_src[(size_t)h->w8[side].u_out[k]] = k;
   bool aligned = true;  // every sub-batch produced exactly its positional rows (no extras, no empty result)
   int64_t total = 0;
   unsigned long long nullm = 0;
@@ -2867,6 +3103,11 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
     double ta = 0, tb = 0;
     if (trace) { ta = now(); cudaEventSynchronize(h->ev_h2d[js]); tb = now(); }
     RW_CUDA(cudaStreamWaitEvent(h->stream, h->ev_h2d[js], 0));
+    for (int k : h->var_in[side]) {  // bytes -> the side's heap, the column becomes a column of handles
+      rc = var_intern(h, side, dp + o_vbytes[k] - c->columns[k].offsets[0], (const uint32_t*)(dp + o_voff[k]) + lo, ch.ops, ch.vis_bits,
+                      ch.cols[k].valid_bits, m, (uint64_t*)(dp + o_data[k]) + lo, h->stream);
+      if (rc != RW_OK) { cudaStreamSynchronize(h->s_d2h); return rc; }
+    }
     int64_t rows = 0;
     rc = join_push_dev(h, side, ch, h->stream, total, &rows, &nullm);
     if (trace) fprintf(stderr, "   sub %d: wait-h2d %.3f  push_dev %.3f ms\n", js, tb - ta, now() - tb);
@@ -2880,7 +3121,8 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
       if (!o2->layout(ncap, h->out_types, ~0ull >> 1, true, h->pool)) { delete o2; return fail(RW_ERR_OOM, "pinned output block"); }
       if (total > 0) {
         memcpy(o2->ops, o->ops, (size_t)total);
-        for (size_t k = 0; k < h->out_types.size(); k++) memcpy(o2->data[k], o->data[k], (size_t)total * type_width(h->out_types[k]));
+        for (size_t k = 0; k < h->out_types.size(); k++)
+          if (!type_is_varlen(h->out_types[k])) memcpy(o2->data[k], o->data[k], (size_t)total * type_width(h->out_types[k]));
       }
       guard.reset(o2);
       o = o2;
@@ -2892,6 +3134,7 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
       cudaMemcpyAsync(o->ops + total, h->os().out_ops.as<uint8_t>() + total, (size_t)rows, cudaMemcpyDeviceToHost, h->s_d2h);
       for (size_t k = 0; k < h->out_types.size(); k++) {
         if (alias_src[k] >= 0) continue;  // decided after the last sub-batch
+        if (type_is_varlen(h->out_types[k])) continue;  // materialised after the last sub-batch
         const size_t w = type_width(h->out_types[k]);
         cudaMemcpyAsync(o->data[k] + (size_t)total * w, h->os().out_col[k].as<uint8_t>() + (size_t)total * w, (size_t)rows * w,
                         cudaMemcpyDeviceToHost, h->s_d2h);
@@ -2901,6 +3144,20 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
   }
   rc = join_post_process(h, total, &nullm, h->stream);
   if (rc != RW_OK) { cudaStreamSynchronize(h->s_d2h); return rc; }
+  if (!h->var_in[side].empty()) {
+    rc = var_check_err(h, h->stream);
+    if (rc != RW_OK) { cudaStreamSynchronize(h->s_d2h); return rc; }
+  }
+  for (int k : h->var_out) {  // handles -> offsets + bytes, then to the host
+    rwgpu_join::VarOut& vo = h->vout[h->cur][k];
+    rc = var_materialize(h, vo, h->os().out_col[k].as<uint64_t>(), (nullm >> 63) ? h->os().out_vis.as<uint8_t>() : nullptr,
+                         ((nullm >> k) & 1) ? h->os().out_valid[k].as<uint8_t>() : nullptr, total, h->stream);
+    if (rc != RW_OK) { cudaStreamSynchronize(h->s_d2h); return rc; }
+    uint8_t* hb = o->var_bytes((size_t)k, vo.total);
+    if (!hb) { cudaStreamSynchronize(h->s_d2h); return fail(RW_ERR_OOM, "pinned varlen output"); }
+    RW_CUDA(cudaMemcpyAsync(o->offsets[k], vo.offs.p, (size_t)(total + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (vo.total) RW_CUDA(cudaMemcpyAsync(hb, vo.bytes.p, vo.total, cudaMemcpyDeviceToHost, h->stream));
+  }
   for (size_t k = 0; k < h->out_types.size(); k++) {
     if (alias_src[k] < 0) continue;
     if (aligned && total == n) {
@@ -2999,7 +3256,18 @@ int32_t rwgpu_join_snapshot(rwgpu_join* h, int32_t side, rwgpu_out** out) {
   if (n > 0) {
     memset(ro->ops, RW_OP_INSERT, (size_t)n);
     for (int k = 0; k < n_cols; k++) {
-      cudaMemcpyAsync(ro->data[k], col[k].p, (size_t)n * type_width(sd.types[k]), cudaMemcpyDeviceToHost, h->stream);
+      if (type_is_varlen(sd.types[k])) {  // handles -> offsets + bytes
+        rwgpu_join::VarOut vo;
+        int rcv = var_materialize(h, vo, col[k].as<uint64_t>(), nullptr, has_null[k] ? val[k].as<uint8_t>() : nullptr, n, h->stream);
+        if (rcv != RW_OK) { delete ro; return rcv; }
+        uint8_t* hb = ro->var_bytes((size_t)k, vo.total);
+        if (!hb) { delete ro; return fail(RW_ERR_OOM, "pinned varlen output"); }
+        cudaMemcpyAsync(ro->offsets[k], vo.offs.p, (size_t)(n + 1) * 4, cudaMemcpyDeviceToHost, h->stream);
+        if (vo.total) cudaMemcpyAsync(hb, vo.bytes.p, vo.total, cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);  // (vo's device buffers die at the end of this iteration)
+      } else {
+        cudaMemcpyAsync(ro->data[k], col[k].p, (size_t)n * type_width(sd.types[k]), cudaMemcpyDeviceToHost, h->stream);
+      }
       if (ro->valid_bytes[k]) cudaMemcpyAsync(ro->valid_bytes[k], val[k].p, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
     }
     cudaError_t e = cudaStreamSynchronize(h->stream);
@@ -3010,42 +3278,37 @@ int32_t rwgpu_join_snapshot(rwgpu_join* h, int32_t side, rwgpu_out** out) {
   return RW_OK;
 }
 
+int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_out** out);
+
 int32_t rwgpu_join_restore(rwgpu_join* h, int32_t side, const rw_chunk* rows) {
   if (!h || !rows) return fail(RW_ERR_INVALID, "null");
   if (side != 0 && side != 1) return fail(RW_ERR_INVALID, "side");
   if (rows->n_cols != h->side[side].n_cols) return fail(RW_ERR_INVALID, "chunk schema mismatch");
   if (h->n_pending) return fail(RW_ERR_INVALID, "collect the outstanding asynchronous pushes first");
-  if (rows->n_rows == 0) return RW_OK;
-  // replay as inserts, a slice at a time, output discarded
+  // replay as inserts through the ordinary push, a slice (a multiple of 64 rows: bitmap words split cleanly) at a time;
+  // the output is discarded
   const int64_t slice = 1 << 20;
   for (int64_t lo = 0; lo < rows->n_rows; lo += slice) {
     const int64_t m = std::min<int64_t>(slice, rows->n_rows - lo);
     std::vector<rw_column> cols(rows->n_cols);
-    std::vector<std::vector<uint64_t>> vbits(rows->n_cols);
     for (int k = 0; k < rows->n_cols; k++) {
       cols[k] = rows->columns[k];
-      cols[k].data = (const uint8_t*)rows->columns[k].data + (size_t)lo * type_width(rows->columns[k].type);
-      if (rows->columns[k].validity) {
-        if (lo % 64) return fail(RW_ERR_INVALID, "internal: restore slice alignment");
-        cols[k].validity = rows->columns[k].validity + lo / 64;
+      if (type_is_varlen(rows->columns[k].type)) {
+        cols[k].offsets = rows->columns[k].offsets + lo;  // (offsets[0] need not be 0: `data` stays the column's base)
+      } else {
+        cols[k].data = (const uint8_t*)rows->columns[k].data + (size_t)lo * type_width(rows->columns[k].type);
       }
+      if (rows->columns[k].validity) cols[k].validity = rows->columns[k].validity + lo / 64;
     }
     rw_chunk part = *rows;
     part.n_rows = m;
     part.ops = rows->ops + lo;
     part.visibility = rows->visibility ? rows->visibility + lo / 64 : nullptr;
     part.columns = cols.data();
-    DevBuf buf;
-    DevChunk ch;
-    int rc = upload_chunk(&part, buf, &ch, h->stream);
+    rwgpu_out* out = nullptr;
+    int rc = rwgpu_join_push(h, side, &part, &out);
     if (rc != RW_OK) return rc;
-    rc = join_begin_call(h, h->stream);
-    if (rc != RW_OK) return rc;
-    int64_t n_out = 0;
-    unsigned long long nullm = 0;
-    rc = join_push_dev(h, side, ch, h->stream, 0, &n_out, &nullm);
-    if (rc != RW_OK) return rc;
-    RW_CUDA(cudaStreamSynchronize(h->stream));
+    rwgpu_out_release(out);
   }
   return RW_OK;
 }

@@ -438,6 +438,8 @@ static int make_vnode_plan(const rw_chunk* c, const int32_t* keys, int n_keys, i
   if (n_keys < 1 || n_keys > RW_MAX_KEYS * 2) return fail(RW_ERR_UNSUPPORTED, "1..8 distribution key columns");
   if (vnode_count < 1 || vnode_count > 32768) return fail(RW_ERR_INVALID, "vnode_count (vnode.rs:79 MAX_COUNT = 2^15)");
   p->n_keys = n_keys;
+  for (int k = 0; k < c->n_cols; k++)
+    if (type_is_varlen(c->columns[k].type)) return fail(RW_ERR_UNSUPPORTED, "the hash shuffle does not carry varlen columns");
   for (int k = 0; k < n_keys; k++) {
     if (keys[k] < 0 || keys[k] >= c->n_cols) return fail(RW_ERR_INVALID, "key index");
     p->key_col[k] = keys[k];
@@ -482,7 +484,8 @@ int upload_chunk(const rw_chunk* c, DevBuf& buf, DevChunk* out, cudaStream_t st)
     int w = type_width(c->columns[k].type);
     out->cols[k].type = c->columns[k].type;
     out->cols[k].width = w;
-    out->cols[k].data = put(c->columns[k].data, (size_t)n * w);
+    // (a varlen payload column is not uploaded: no kernel behind this helper touches columns it does not reference)
+    out->cols[k].data = type_is_varlen(c->columns[k].type) ? nullptr : put(c->columns[k].data, (size_t)n * w);
     out->cols[k].valid_bits = (const uint64_t*)put(c->columns[k].validity, nw);
   }
   RW_CUDA(cudaGetLastError());

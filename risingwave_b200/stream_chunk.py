@@ -31,7 +31,10 @@ NP_DTYPE = {
 # from_pretty type tokens (data_chunk.rs:726-741); "s" (int16) is our extension
 PRETTY_TYPES = {"B": abi.T_BOOL, "s": abi.T_INT16, "i": abi.T_INT32, "I": abi.T_INT64,
                 "f": abi.T_FLOAT32, "F": abi.T_FLOAT64, "D": abi.T_DATE, "TS": abi.T_TIMESTAMP,
-                "TZ": abi.T_TIMESTAMPTZ, "SRL": abi.T_SERIAL, "DEC": abi.T_DECIMAL}
+                "TZ": abi.T_TIMESTAMPTZ, "SRL": abi.T_SERIAL, "DEC": abi.T_DECIMAL, "T": abi.T_VARCHAR}
+# varlen columns (BytesArray, bytes_array.rs:30-34) hold Python `bytes` in an object array on the host
+for _t in abi.VARLEN_TYPES:
+    NP_DTYPE[_t] = np.dtype(object)
 PRETTY_TOKENS = {v: k for k, v in PRETTY_TYPES.items()}
 OP_TOKENS = {"+": abi.OP_INSERT, "-": abi.OP_DELETE, "U+": abi.OP_UPDATE_INSERT, "U-": abi.OP_UPDATE_DELETE}
 OP_STR = {v: k for k, v in OP_TOKENS.items()}
@@ -72,6 +75,8 @@ class Column:
         if self.valid is not None and not self.valid[i]:
             return None
         v = self.data[i]
+        if self.type in abi.VARLEN_TYPES:
+            return bytes(v)
         if self.type == abi.T_DECIMAL:
             return decimal_to_int(v)
         if self.type in (abi.T_FLOAT32, abi.T_FLOAT64):
@@ -189,10 +194,19 @@ class StreamChunk:
         n = len(self.ops)
         cols = (abi.RwColumn * max(1, len(self.columns)))()
         for k, c in enumerate(self.columns):
-            data = np.ascontiguousarray(c.data, dtype=NP_DTYPE[c.type])
-            keep.append(data)
             cols[k].type = c.type
-            cols[k].data = data.ctypes.data if n else None
+            if c.type in abi.VARLEN_TYPES:
+                vals = [b"" if (c.valid is not None and not c.valid[i]) else bytes(c.data[i]) for i in range(n)]
+                offs = np.zeros(n + 1, dtype=np.uint32)
+                np.cumsum([len(v) for v in vals], out=offs[1:])
+                blob = np.frombuffer(b"".join(vals) + b"\0", dtype=np.uint8).copy()
+                keep += [offs, blob]
+                cols[k].data = blob.ctypes.data
+                cols[k].offsets = offs.ctypes.data
+            else:
+                data = np.ascontiguousarray(c.data, dtype=NP_DTYPE[c.type])
+                keep.append(data)
+                cols[k].data = data.ctypes.data if n else None
             if c.valid is not None and not bool(np.all(c.valid)):
                 w = pack_bits(c.valid)
                 keep.append(w)
@@ -229,7 +243,15 @@ class StreamChunk:
         for k in range(view.n_cols):
             c = view.columns[k]
             dt = NP_DTYPE[c.type]
-            if n:
+            if c.type in abi.VARLEN_TYPES:
+                data = np.empty(n, dtype=object)
+                if n:
+                    offs = np.ctypeslib.as_array(C.cast(c.offsets, C.POINTER(C.c_uint32)), shape=(n + 1,)).copy()
+                    total = int(offs[n])
+                    blob = bytes(np.ctypeslib.as_array(C.cast(c.data, C.POINTER(C.c_uint8)), shape=(max(total, 1),))[:total])
+                    for i in range(n):
+                        data[i] = blob[int(offs[i]):int(offs[i + 1])]
+            elif n:
                 raw = np.ctypeslib.as_array(C.cast(c.data, C.POINTER(C.c_uint8)), shape=(n * dt.itemsize,)).copy()
                 data = raw.view(dt)
             else:
@@ -250,6 +272,8 @@ def _parse_value(tok: str, t: int):
         return float(tok)
     if t == abi.T_BOOL:
         return tok in ("t", "true", "1", "T")
+    if t in abi.VARLEN_TYPES:
+        return b"" if tok == "(empty)" else tok.encode()
     return int(tok)
 
 
@@ -258,6 +282,8 @@ def _fmt(v) -> str:
         return "t" if v else "f"
     if isinstance(v, float):
         return repr(v)
+    if isinstance(v, bytes):
+        return v.decode(errors="replace") if v else "(empty)"
     return str(v)
 
 
@@ -281,6 +307,10 @@ def column_from_values(t: int, vals: Sequence) -> Column:
     for i, v in enumerate(vals):
         if v is None:
             valid[i] = False
+            if t in abi.VARLEN_TYPES:
+                data[i] = b""
+        elif t in abi.VARLEN_TYPES:
+            data[i] = v.encode() if isinstance(v, str) else bytes(v)
         elif t == abi.T_DECIMAL:
             data[i] = int_to_decimal(int(v))
         else:

@@ -35,7 +35,7 @@ def test_type_width_and_version():
 
 def test_struct_sizes_match_header():
     # x86-64 SysV layout of the structs in include/rwgpu.h
-    assert ctypes.sizeof(abi.RwColumn) == 24
+    assert ctypes.sizeof(abi.RwColumn) == 32
     assert ctypes.sizeof(abi.RwChunk) == 40
     assert ctypes.sizeof(abi.RwAggCall) == 16
     assert ctypes.sizeof(abi.RwAggDesc) == 72

@@ -518,3 +518,86 @@ def test_noop_update_pairs_are_hidden_like_the_reference(cuda, oracle, shape):
         assert emitted_multiset(g) == emitted_multiset(o), f"push {i}: emitted rows differ"
         hidden += sum(int((~c.vis).sum()) for c in g if c.vis is not None)
     assert hidden > 0
+
+
+# ------------------------------------------------------------------------------------------ varlen payload columns (round 2)
+@pytest.mark.parametrize("name", ["Inner", "LeftOuter", "RightSemi"])
+def test_varlen_payload_columns_travel_through_the_join(cuda, oracle, name):
+    """varchar columns (BytesArray{offset, bitmap, data}, bytes_array.rs:30-34) as PAYLOAD: interned into the side's byte
+    heap on the way in, gathered back into offsets + bytes on the way out; NULL and empty strings, deletes, updates that
+    change only the string, snapshot / restore -- vs the oracle."""
+    jt = JOIN_TYPES[name]
+    tl = [abi.T_INT64, abi.T_INT64, abi.T_VARCHAR, abi.T_INT64]      # bid-like: auction, row id, url, price
+    tr = [abi.T_INT64, abi.T_VARCHAR, abi.T_VARCHAR]                 # auction-like: id, item name, description
+    rng = np.random.default_rng(23)
+    words = [b"", b"a", b"url-" + bytes(range(65, 91)), b"\xf0\x9f\x9a\x80 unicode", b"x" * 300, None]
+
+    def mk(be):
+        _, sl = MockSource.channel()
+        _, sr = MockSource.channel()
+        return HashJoinExecutor(be, jt, sl.into_executor(tl, [1]), sr.into_executor(tr, [0]), JoinParams([0], [1]), JoinParams([0], [0]), [False])
+
+    g, o = mk(cuda), mk(oracle)
+    live = [dict(), dict()]
+    next_pk = [0]
+
+    def w():
+        return words[int(rng.integers(len(words)))]
+
+    def chunk(side, n):
+        rows = []
+        while len(rows) < n:
+            x = rng.random()
+            lv = live[side]
+            if lv and x < 0.2:
+                k = list(lv)[int(rng.integers(len(lv)))]
+                rows.append((abi.OP_DELETE, lv.pop(k)))
+            elif lv and x < 0.35 and len(rows) + 2 <= n:
+                k = list(lv)[int(rng.integers(len(lv)))]
+                old = lv[k]
+                new = (old[:2] + (w(),) + old[3:]) if side == 0 else (old[:1] + (w(),) + old[2:])
+                rows += [(abi.OP_UPDATE_DELETE, old), (abi.OP_UPDATE_INSERT, new)]
+                lv[k] = new
+            elif side == 0:
+                next_pk[0] += 1
+                row = (int(rng.integers(0, 60)), next_pk[0], w(), int(rng.integers(0, 1000)))
+                rows.append((abi.OP_INSERT, row))
+                lv[row[1]] = row
+            else:
+                k = int(rng.integers(0, 60))
+                if k in lv:
+                    continue
+                row = (k, w(), w())
+                rows.append((abi.OP_INSERT, row))
+                lv[k] = row
+        return StreamChunk.from_rows(tl if side == 0 else tr, rows)
+
+    for i in range(14):
+        side = int(rng.integers(2))
+        ch = chunk(side, int(rng.integers(20, 400)))
+        assert net_multiset(g.eq_join_oneside(side, ch)) == net_multiset(o.eq_join_oneside(side, ch)), f"push {i}"
+    # state persistence with varlen columns
+    snaps = [g.snapshot(s) for s in (0, 1)]
+    for s in (0, 1):
+        assert sorted((r for c in snaps[s] for _, r in c.rows()), key=repr) == sorted(live[s].values(), key=repr)
+    g2 = mk(cuda)
+    for s in (0, 1):
+        if snaps[s]:
+            from risingwave_b200.stream_chunk import concat_chunks
+            g2.restore(s, concat_chunks(snaps[s]))
+    for i in range(6):
+        side = int(rng.integers(2))
+        ch = chunk(side, int(rng.integers(20, 300)))
+        want = net_multiset(o.eq_join_oneside(side, ch))
+        assert net_multiset(g.eq_join_oneside(side, ch)) == want, f"after snapshot, push {i}"
+        assert net_multiset(g2.eq_join_oneside(side, ch)) == want, f"restored operator, push {i}"
+
+
+def test_varlen_key_or_pk_is_refused(cuda):
+    for types, keys, pk in (([abi.T_VARCHAR, abi.T_INT64], [0], [1]), ([abi.T_INT64, abi.T_VARCHAR], [0], [1])):
+        _, sl = MockSource.channel()
+        _, sr = MockSource.channel()
+        with pytest.raises(abi.RwError) as e:
+            HashJoinExecutor(cuda, abi.JOIN_INNER, sl.into_executor(types, [1]), sr.into_executor(types, [1]), JoinParams(keys, pk), JoinParams(keys, pk),
+                             [False])
+        assert e.value.code == abi.RW_ERR_UNSUPPORTED
