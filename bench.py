@@ -774,66 +774,30 @@ def run_ours(args):
             del jh, hdev
             torch.cuda.empty_cache()
 
-        # ================================================================ leg: e2e (host buffers, C ABI)
+        # ================================================================ leg: e2e (host buffers, C ABI, COMPILED caller)
         def e2e_leg():
-            # N>1: the host input is already partitioned (every rank pushes the bids of its OWN auctions through
-            # its C-ABI handle, as N independent shim instances would); no exchange on this path
-            e2e_batches = batches_host if world == 1 else \
-                [gen_bids(BATCH, (rank * (K + W) + s) * BATCH, SEED, N_BUILD, id_base) for s in range(K + W)]
-            join2 = new_join()
-            build(join2, shuffle=False)
-            FFI_ROWS = BATCH  # the same 1024 coalesced 1024-row chunks per C-ABI call as the device-resident leg
-            ones_pinned = torch.ones(FFI_ROWS, dtype=torch.uint8).pin_memory().numpy()
-            chunks_host = []
-            for s in range(W + K):
-                for i in range(0, BATCH, FFI_ROWS):
-                    # the shim's StreamChunk arrays live in pinned host memory (cudaHostAlloc'd arena)
-                    cols = [torch.from_numpy(c[i:i + FFI_ROWS].copy()).pin_memory().numpy() for c in e2e_batches[s]]
-                    ch = StreamChunk(ones_pinned, [Column(abi.T_INT64, c) for c in cols])
-                    chunks_host.append(ch.to_abi())  # (rw_chunk with HOST pointers, keepalive)
-            per_step = BATCH // FFI_ROWS
-
-            aliased = [0]
-
-            def host_step(s):
-                """the calls a Rust shim makes: rwgpu_join_push(host chunk) -> out (pinned host memory); take the
-                chunk views; release.  The first and last 1024-row views are fetched and read here -- walking all
-                1024 of them through ctypes costs ~1 ms of pure Python per step, which a compiled caller does not pay."""
-                tot = 0
-                view = abi.RwChunk()
-                for j in range(per_step):
-                    out = C.c_void_p()
-                    be.check(be._join_push(join2._h, abi.SIDE_LEFT, C.byref(chunks_host[s * per_step + j][0]), C.byref(out)))
-                    nch = be._out_num_chunks(out)
-                    for i in ((0, nch - 1) if nch > 1 else range(nch)):
-                        be._out_chunk(out, i, C.byref(view))
-                        if i == 0 and view.n_rows:
-                            # output columns that alias the input chunk's host buffers were not copied back
-                            inp = chunks_host[s * per_step + j][0]
-                            lo = [int(inp.columns[k].data or 0) for k in range(inp.n_cols)]
-                            aliased[0] = sum(any(a <= int(view.columns[k].data or 0) < a + 8 * FFI_ROWS for a in lo if a)
-                                             for k in range(view.n_cols))
-                        if view.n_rows:
-                            last = C.cast(view.columns[view.n_cols - 1].data, C.POINTER(C.c_int64))[view.n_rows - 1]
-                            tot += 0 * int(last)  # a host read of the result
-                    tot += int(be._out_num_rows(out))
-                    be._out_release(out)
-                return tot
-
-            for s in range(W):
-                host_step(s)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()  # (no barrier here: a rank that failed above must not leave the others waiting)
-            tot = 0
-            for s in range(W, W + K):
-                tot += host_step(s)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-            return {"value": K * BATCH / dt, "unit": "rows/s", "h2d_bytes_per_step": BATCH * (4 * 8 + 1),
-                           "d2h_bytes_per_step": tot * (8 * (8 - aliased[0]) + 1) // K, "ffi_batch_rows": FFI_ROWS, "ms_per_step": dt / K * 1e3,
-                           "output_columns_aliasing_input": aliased[0],
-                           "note": "pinned host StreamChunk buffers -> rwgpu_join_push -> host output chunk views (C ABI via ctypes); "
-                                   "the bid-side output columns alias the caller's input buffers (rwgpu.h), the rest is read back"}
+            """the same steps through the host-buffer entry point, driven by a compiled caller of the C ABI
+            (tools/e2e_caller.cc, built by __graft_entry__.build()): pinned host StreamChunk buffers -> rwgpu_join_push ->
+            EVERY output chunk view fetched and read -> release -- what the Rust shim does per message.  N>1: every rank
+            runs its own caller on its own GPU and partition (as N independent shim instances would), started together."""
+            exe = os.path.join(ROOT, "build", "e2e_caller")
+            if not os.path.exists(exe):
+                raise RuntimeError("build/e2e_caller missing: run __graft_entry__.build()")
+            env = dict(os.environ)
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            env["CUDA_VISIBLE_DEVICES"] = (vis.split(",")[local_rank] if vis else str(local_rank))
+            torch.cuda.empty_cache()
+            r = subprocess.run([exe, str(N_BUILD), str(BATCH), str(K), str(W)], capture_output=True, text=True, env=env, timeout=900)
+            if r.returncode != 0:
+                raise RuntimeError(f"e2e_caller failed: {r.stderr[-500:]}")
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            al = int(j["output_columns_aliasing_input"])
+            return {"value": j["value"], "unit": "rows/s", "h2d_bytes_per_step": BATCH * (4 * 8 + 1),
+                    "d2h_bytes_per_step": int(j["out_rows"]) * (8 * (8 - al) + 1) // K, "ffi_batch_rows": BATCH, "ms_per_step": j["ms_per_step"],
+                    "output_columns_aliasing_input": al, "chunk_views_read_per_step": j["chunk_views_read_per_step"],
+                    "note": "compiled caller (tools/e2e_caller.cc): pinned host StreamChunk buffers -> rwgpu_join_push -> every one of the "
+                            "output chunk views fetched and read -> rwgpu_out_release; the bid-side output columns alias the caller's input "
+                            "buffers (rwgpu.h), the rest is read back over PCIe"}
 
         if "e2e" in legs:
             res, ok = None, 1.0

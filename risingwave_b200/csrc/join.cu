@@ -1749,7 +1749,7 @@ struct rwgpu_join {
   bool uni = false;
   int uni_is = 1;                  // inline side
   DevBuf uni_buckets, uni_counters;  // counters: log_next[2], n_dead[2], scratch
-  uint64_t uni_cap = 0, uni_keys = 0;
+  uint64_t uni_cap = 0, uni_keys = 0, uni_keys_exact = 0;  // uni_keys: upper bound while pushes are outstanding
   uint64_t uni_dead[2] = {0, 0};
   uint64_t compactions = 0;
   DevBuf uni_wk_entry, uni_wk_mask;  // worklist of the rows the hot kernel defers (join_uni.cuh UniWork)
@@ -2015,6 +2015,11 @@ static int uni_alloc_buckets(rwgpu_join* h, DevBuf& buf, uint64_t cap) {
 // keep the load of the bucket array <= 0.5 (every extra probe is one more random 64-byte transaction)
 static int uni_grow_table(rwgpu_join* h, uint64_t need_keys) {
   if (need_keys * 2 <= h->uni_cap) return RW_OK;
+  // `need_keys` is an upper bound: every row of every outstanding push counted as a new key, and a push whose row count
+  // lives on the device counted at its buffer CAPACITY (N>1: world x the rows it will really hold).  As long as the
+  // keys KNOWN to exist keep the load under 0.5 and even the bound leaves a tenth of the buckets free, probing
+  // terminates and nothing has to stop; the exact count arrives with the next collect.
+  if (h->uni_keys_exact * 2 <= h->uni_cap && need_keys * 10 <= h->uni_cap * 9) return RW_OK;
   uint64_t ncap = h->uni_cap;
   while (ncap < need_keys * 4) ncap <<= 1;
   RW_CUDA(cudaDeviceSynchronize());  // every push in flight on any stream has finished with the old array
@@ -2250,6 +2255,7 @@ static int uni_finish(rwgpu_join* h, const JoinPending& pd, int64_t* out_rows, u
     const uint64_t n = (uint64_t)pd.ch.n, slack = (uint64_t)pd.grid * 8 * pd.pool_chunk;
     own.n_rows = hs.log_next[pd.S] + (own.n_rows - (pd.ids_before + n + slack));
     h->uni_keys = hs.n_keys[0] + (h->uni_keys - (pd.keys_before + n));
+    h->uni_keys_exact = hs.n_keys[0];
   }
   hs.err = err;
   rc = join_check_err(h, hs, st);
