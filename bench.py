@@ -787,6 +787,8 @@ def run_ours(args):
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             env["CUDA_VISIBLE_DEVICES"] = (vis.split(",")[local_rank] if vis else str(local_rank))
             torch.cuda.empty_cache()
+            if world > 1:
+                dist.barrier()  # the callers of all ranks start together
             r = subprocess.run([exe, str(N_BUILD), str(BATCH), str(K), str(W)], capture_output=True, text=True, env=env, timeout=900)
             if r.returncode != 0:
                 raise RuntimeError(f"e2e_caller failed: {r.stderr[-500:]}")

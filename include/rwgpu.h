@@ -281,6 +281,13 @@ int32_t rwgpu_join_collect(rwgpu_join* h, rw_chunk* view, void* cuda_stream);
 int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t epoch);
 int32_t rwgpu_join_stats(rwgpu_join* h, uint64_t* left_rows, uint64_t* right_rows,
                          uint64_t* kernel_launches);
+/* Watermark-driven state cleaning (HashJoinExecutor::handle_watermark, hash_join.rs:791-891 -> JoinHashMap::
+ * update_watermark): the host keeps the BufferedWatermarks logic (take the smaller of the two sides' watermarks,
+ * derive the output watermarks) and tells the operator which side's state may drop every row whose join key column
+ * `key_pos` is below `value` (integer-typed key columns).  Like the reference's state table the rows leave at the next
+ * rwgpu_join_barrier.  By the watermark contract no later row can match them, so results are unchanged; the
+ * state stops growing.                                                                                     */
+int32_t rwgpu_join_update_watermark(rwgpu_join* h, int32_t side, int32_t key_pos, int64_t value);
 /* ---- state persistence (checkpoint / recovery).  A side's persistent state is the set of its stored input rows: the
  * reference writes every stored row to the side's StateTable (JoinHashMap::insert, join/hash_join.rs:591-625; table
  * pk = join key | deduped input pk, stream_plan.proto:628-637), so on the write path the shim passes the INPUT chunks

@@ -1673,6 +1673,25 @@ __global__ void __launch_bounds__(256) join_snapshot_kernel(const JoinPlanDev* _
     });
   }
 }
+// two-table layout: rows of side S whose key column `key_pos` is below the watermark leave the state
+__global__ void __launch_bounds__(256) join_clean_kernel(const JoinPlanDev* __restrict__ p, JoinSideDev s, int key_pos, long long wm) {
+  for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < s.cap + 2; b += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t* w = (const uint64_t*)bkt(s, (int64_t)b);
+    long long kv;
+    if (p->single_key) {
+      if (b == s.cap) continue;  // NULL key
+      if (b < s.cap && w[0] == J_EMPTY) continue;
+      kv = b == s.cap + 1 ? (long long)J_EMPTY : (long long)w[0];
+    } else {
+      if (b >= s.cap || w[0] == 0ull) continue;
+      if ((w[0] >> (8 + key_pos)) & 1ull) continue;  // NULL in this key column
+      kv = (long long)w[1 + key_pos];
+    }
+    if (kv >= wm) continue;
+    unsigned long long* Wp = bkt_W(s, p, (int64_t)b);
+    *Wp = W_EMPTY | (W_istate(*Wp) ? W_IL_DEAD : 0ull);
+  }
+}
 }  // namespace rw
 
 // =============================================================================== host handle
@@ -1760,6 +1779,11 @@ struct rwgpu_join {
   cudaEvent_t pend_ev[2] = {nullptr, nullptr};
   cudaStream_t last_st = nullptr;
   cudaEvent_t order_ev = nullptr;
+  // watermark-driven state cleaning, applied at the next barrier
+  bool wm_pending[2] = {false, false};
+  int wm_key_pos[2] = {0, 0};
+  int64_t wm_value[2] = {0, 0};
+  uint64_t wm_cleanings = 0;
   uint64_t launches = 0;
   uint64_t seq = 0;
   unsigned long long status_tag = 0;
@@ -3202,6 +3226,25 @@ int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t /*epoch*/) {
   // state lives in HBM (StateStore stubbed to memory, north_star): a barrier is an ordering point
   RW_CUDA(cudaStreamSynchronize(h->stream));
   if (h->last_st && h->last_st != h->stream) RW_CUDA(cudaStreamSynchronize(h->last_st));
+  // watermark-driven state cleaning (hash_join.rs:791-891 -> JoinHashMap::update_watermark; the state table drops the
+  // range below the watermark when the epoch commits)
+  for (int s = 0; s < 2; s++) {
+    if (!h->wm_pending[s]) continue;
+    h->wm_pending[s] = false;
+    if (h->uni) uni_clean_kernel<<<jgrid((int64_t)h->uni_cap + 2, 256), 256, 0, h->stream>>>(uni_dev(h), s, (long long)h->wm_value[s]);
+    else join_clean_kernel<<<jgrid((int64_t)h->side[s].slot_cap + 2, 256), 256, 0, h->stream>>>(h->plan_dev.as<JoinPlanDev>(), side_dev(h, s),
+                                                                                                   h->wm_key_pos[s], (long long)h->wm_value[s]);
+    RW_CUDA(cudaGetLastError());
+    h->launches++;
+    h->wm_cleanings++;
+    if (h->uni) {  // the dead count decides about compaction below
+      unsigned long long nd = 0;
+      RW_CUDA(cudaMemcpyAsync(&nd, h->uni_counters.as<unsigned long long>() + 2 + s, 8, cudaMemcpyDeviceToHost, h->stream));
+      RW_CUDA(cudaStreamSynchronize(h->stream));
+      h->uni_dead[s] = nd;
+    }
+  }
+  RW_CUDA(cudaStreamSynchronize(h->stream));
   // ... and the point where deleted rows are reclaimed (the reference's delete frees the entry at once,
   // join/hash_join.rs:659-681): a log that is more than half dead is rebuilt from its live records
   if (h->uni)
@@ -3210,6 +3253,22 @@ int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t /*epoch*/) {
         int rc = uni_compact(h, s);
         if (rc != RW_OK) return rc;
       }
+  return RW_OK;
+}
+
+int32_t rwgpu_join_update_watermark(rwgpu_join* h, int32_t side, int32_t key_pos, int64_t value) {
+  if (!h) return fail(RW_ERR_INVALID, "null");
+  if (side != 0 && side != 1) return fail(RW_ERR_INVALID, "side");
+  if (key_pos < 0 || key_pos >= h->plan.n_keys) return fail(RW_ERR_INVALID, "join key position");
+  const int t = h->plan.col_type[side][h->plan.key_col[side][key_pos]];
+  if (type_is_float(t) || t == RW_T_BOOL) return fail(RW_ERR_UNSUPPORTED, "watermarks on this key type keep the state (CPU semantics unchanged)");
+  if (h->uni && key_pos != 0) return fail(RW_ERR_INVALID, "join key position");
+  // a later watermark on the same side only moves up
+  if (!h->wm_pending[side] || value > h->wm_value[side] || key_pos != h->wm_key_pos[side]) {
+    h->wm_pending[side] = true;
+    h->wm_key_pos[side] = key_pos;
+    h->wm_value[side] = value;
+  }
   return RW_OK;
 }
 

@@ -738,6 +738,34 @@ __global__ void __launch_bounds__(256) uni_delete_kernel(const JoinPlanDev* __re
   if (dead_log) atomicAdd(t.n_dead[S], (unsigned long long)dead_log);
 }
 
+// watermark-driven state cleaning (JoinHashMap::update_watermark, join/hash_join.rs; applied at the barrier like the
+// state table's commit-time range delete): every row of `side` whose join key is below the watermark leaves the state.
+// The whole key dies on that side, so the side's part of the bucket is simply reset; its log records become
+// unreachable and are counted as dead for the compaction trigger.
+__global__ void __launch_bounds__(256) uni_clean_kernel(UniDev t, int side, long long wm) {
+  unsigned int dead = 0;
+  for (uint64_t b = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; b < t.cap + 2; b += (uint64_t)gridDim.x * blockDim.x) {
+    if (b == t.cap) continue;  // NULL keys sort last: never below a watermark
+    const unsigned long long key = *(const unsigned long long*)ub(t, (int64_t)b);
+    if (b < t.cap && key == J_EMPTY) continue;
+    const long long kv = b == t.cap + 1 ? (long long)J_EMPTY : (long long)key;
+    if (kv >= wm) continue;
+    if (side == t.is) {
+      unsigned long long* Wp = ub_WI(t, (int64_t)b);
+      const unsigned long long W = *Wp;
+      const uint32_t cnt = W_count(W);
+      if (cnt) dead += cnt - (W_istate(W) == 1u ? 1u : 0u);
+      *Wp = W_EMPTY | (W_istate(W) ? W_IL_DEAD : 0ull);
+    } else {
+      dead += *ub_ccount(t, (int64_t)b);
+      *ub_chead(t, (int64_t)b) = U_NIL;
+      *ub_ccount(t, (int64_t)b) = 0u;
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) dead += __shfl_xor_sync(0xffffffffu, dead, d);
+  if (lane_id() == 0 && dead) atomicAdd(t.n_dead[side], (unsigned long long)dead);
+}
+
 // status publication after a delete kernel that had real work
 __global__ void uni_status_kernel(UniDev t, JoinStatus* st, JoinStatus* status_host, unsigned long long tag, int reset) {
   st->log_next[0] = *t.log_next[0]; st->log_next[1] = *t.log_next[1];

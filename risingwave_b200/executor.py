@@ -424,6 +424,12 @@ class HashJoinExecutor:
     def flush_data(self, epoch: int):
         self.backend.check(self.backend._join_barrier(self._h, epoch))
 
+    def update_watermark(self, side: int, key_pos: int, value: int):
+        """JoinHashMap::update_watermark: rows of `side` with join key column `key_pos` < value leave at the next barrier"""
+        fn = self.backend.lib.rwgpu_join_update_watermark
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64]
+        self.backend.check(fn(self._h, side, key_pos, value))
+
     # state persistence (rwgpu.h rwgpu_join_snapshot / rwgpu_join_restore; CUDA backend only)
     def snapshot(self, side: int) -> List[StreamChunk]:
         fn = self.backend.lib.rwgpu_join_snapshot

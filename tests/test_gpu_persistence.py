@@ -103,3 +103,52 @@ def test_agg_snapshot_restore_round_trip(cuda, oracle):
             ga, gb, go = a.flush_data(epoch + 1), b.flush_data(epoch + 1), o.flush_data(epoch + 1)
             assert net_multiset(ga) == net_multiset(go), f"cfg {ci} epoch {epoch}: original vs oracle"
             assert net_multiset(gb) == net_multiset(go), f"cfg {ci} epoch {epoch}: restored vs oracle"
+
+
+@pytest.mark.parametrize("shape", ["unified", "two_keys"])
+def test_watermark_state_cleaning(cuda, oracle, shape):
+    """HashJoinExecutor::handle_watermark -> JoinHashMap::update_watermark (hash_join.rs:791-891): after a join-key
+    watermark both sides drop every row below it at the next barrier.  The state shrinks (snapshot), and -- the
+    watermark contract: no later row is below it -- every later result is still exactly the oracle's (which never cleans)."""
+    if shape == "unified":
+        types, keys, pk = [abi.T_INT64] * 3, [0], [1]
+    else:
+        types, keys, pk = [abi.T_INT64, abi.T_INT32, abi.T_INT64], [0, 1], [2]
+    rng = np.random.default_rng(17)
+
+    def mk(be):
+        _, sl = MockSource.channel()
+        _, sr = MockSource.channel()
+        return HashJoinExecutor(be, abi.JOIN_INNER, sl.into_executor(types, pk), sr.into_executor(types, pk), JoinParams(keys, pk), JoinParams(keys, pk),
+                                [False] * len(keys))
+
+    g, o = mk(cuda), mk(oracle)
+    next_pk = [0]
+
+    def chunk(lo, hi, n):
+        rows = []
+        for _ in range(n):
+            next_pk[0] += 1
+            if shape == "unified":
+                rows.append((abi.OP_INSERT, (int(rng.integers(lo, hi)), next_pk[0], int(rng.integers(0, 100)))))
+            else:
+                rows.append((abi.OP_INSERT, (int(rng.integers(lo, hi)), int(rng.integers(0, 3)), next_pk[0])))
+        return StreamChunk.from_rows(types, rows)
+
+    for i in range(6):  # event-time keys 0 .. 1000
+        side = i % 2
+        ch = chunk(0, 1000, 800)
+        assert net_multiset(g.eq_join_oneside(side, ch)) == net_multiset(o.eq_join_oneside(side, ch))
+    before = [sum(c.cardinality() for c in g.snapshot(s)) for s in (0, 1)]
+    for s in (0, 1):
+        g.update_watermark(s, 0, 600)
+    g.flush_data(1)
+    snaps = [g.snapshot(s) for s in (0, 1)]
+    for s in (0, 1):
+        rows = [r for c in snaps[s] for _, r in c.rows()]
+        assert rows and all(r[0] >= 600 for r in rows)
+        assert len(rows) < before[s] * 0.6
+    for i in range(6):  # later rows respect the watermark
+        side = i % 2
+        ch = chunk(600, 1400, 700)
+        assert net_multiset(g.eq_join_oneside(side, ch)) == net_multiset(o.eq_join_oneside(side, ch)), f"push {i} after cleaning"
