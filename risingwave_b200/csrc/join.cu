@@ -2165,7 +2165,11 @@ static void uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_onl
 
 // LAUNCH half of a push: main kernel + delete kernel (which publishes the status block into the output set's pinned
 // slot) are enqueued on `st`; nothing is waited for.  The output goes to the CURRENT output set (h->cur).
+static double uni_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static const bool uni_trace = getenv("RWGPU_TRACE") != nullptr;  // host-side timeline on stderr (debugging only)
+
 static int uni_enqueue(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream_t st, int64_t out_base, JoinPending* pd) {
+  const double tr0 = uni_trace ? uni_now_ms() : 0.0;
   DevChunk ch = ch_in;
   bool plain_cols = ch.vis_bits == nullptr;
   for (int c = 0; c < ch.n_cols && plain_cols; c++)
@@ -2203,6 +2207,7 @@ static int uni_enqueue(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream_t
   }
   rc = join_order(h, st);
   if (rc != RW_OK) return rc;
+  const double tr1 = uni_trace ? uni_now_ms() : 0.0;
   pd->S = S;
   pd->ch = ch;
   pd->st = st;
@@ -2230,6 +2235,10 @@ static int uni_enqueue(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream_t
   h->launches += 2;
   if (!h->pend_ev[pd->set]) RW_CUDA(cudaEventCreateWithFlags(&h->pend_ev[pd->set], cudaEventDisableTiming));
   RW_CUDA(cudaEventRecord(h->pend_ev[pd->set], st));
+  if (uni_trace)
+    fprintf(stderr, "  [uni_enqueue S=%d n=%lld set=%d] grow/ensure %.3f ms, launch %.3f ms (log segs %zu/%zu, cap %llu keys<=%llu)\n", S, (long long)n,
+            pd->set, tr1 - tr0, uni_now_ms() - tr1, h->side[0].log.segs.size(), h->side[1].log.segs.size(), (unsigned long long)h->uni_cap,
+            (unsigned long long)h->uni_keys);
   return RW_OK;
 }
 
@@ -2248,14 +2257,17 @@ static int uni_finish(rwgpu_join* h, const JoinPending& pd, int64_t* out_rows, u
     memcpy(&hs, slot, sizeof(JoinStatus));
     return RW_OK;
   };
+  const double tr0 = uni_trace ? uni_now_ms() : 0.0;
   RW_CUDA(cudaEventSynchronize(h->pend_ev[pd.set]));
+  const double tr1 = uni_trace ? uni_now_ms() : 0.0;
   int rc;
   if (*(volatile unsigned long long*)(slot + 1) == pd.tag) memcpy(&hs, slot, sizeof(JoinStatus));
   else { rc = read_status(3); if (rc != RW_OK) return rc; }  // the delete kernel had real work: it did not publish
   unsigned int err = hs.err;
   const unsigned long long first_null = hs.null_mask;
   const bool first_match = hs.pad != 0;
-  if (hs.err & JERR_OUT_CAPACITY) {
+  const bool redone = (hs.err & JERR_OUT_CAPACITY) != 0;
+  if (redone) {
     // the extra-match area overflowed: redo the probe + emit with room for every reservation.  The probe reads the
     // OTHER side's state only, which no later push of the same side has touched (pushes of different sides are never
     // outstanding together), so the redo is exact.
@@ -2290,6 +2302,10 @@ static int uni_finish(rwgpu_join* h, const JoinPending& pd, int64_t* out_rows, u
   *null_mask = h->call_null_mask;
   h->os().valid_dirty |= hs.null_mask & ((1ull << 63) - 1);
   if (hs.n_del) h->call_had_deletes = true;
+  if (uni_trace)
+    fprintf(stderr, "  [uni_finish S=%d set=%d] wait %.3f ms, rest %.3f ms (redo %d, extras %llu, n_del %llu, out %lld)\n", pd.S, pd.set, tr1 - tr0,
+            uni_now_ms() - tr1, (int)redone, (unsigned long long)hs.out_rows,
+            (unsigned long long)hs.n_del, (long long)*out_rows);
   return RW_OK;
 }
 

@@ -57,7 +57,10 @@ class DeviceChunk:
 class DeviceView:
     """Device pointers returned by a `*_device` call (valid until the next call on that handle)."""
 
-    def __init__(self, view: abi.RwChunk):
+    def __init__(self, view: abi.RwChunk, stream: Optional[torch.cuda.Stream] = None):
+        # the library may still be packing bitmaps on `stream` when the call returns: readers below wait for it
+        self._stream = stream
+        self._synced = False
         self.n_rows = int(view.n_rows)
         self.n_cols = int(view.n_cols)
         self.ops_ptr = view.ops
@@ -66,8 +69,17 @@ class DeviceView:
         self.col_types = [int(view.columns[k].type) for k in range(self.n_cols)]
         self.valid_ptrs = [view.columns[k].validity for k in range(self.n_cols)]
 
+    def _wait(self):
+        if not self._synced:
+            if self._stream is not None:
+                self._stream.synchronize()
+            else:  # the library's own stream
+                torch.cuda.synchronize()
+            self._synced = True
+
     def column(self, k: int) -> torch.Tensor:
         """copy column k out of the library-owned buffer into a fresh tensor (D2D)."""
+        self._wait()
         t = self.col_types[k]
         out = torch.empty(self.n_rows, dtype=TORCH_DTYPE[t], device="cuda")
         if self.n_rows:
@@ -76,6 +88,7 @@ class DeviceView:
         return out
 
     def ops(self) -> torch.Tensor:
+        self._wait()
         out = torch.empty(self.n_rows, dtype=torch.uint8, device="cuda")
         if self.n_rows:
             cudart().cudaMemcpy(C.c_void_p(out.data_ptr()), C.c_void_p(self.ops_ptr), C.c_size_t(self.n_rows), 3)
@@ -85,6 +98,7 @@ class DeviceView:
         """bool[n_rows] from the packed visibility words, or None when every row is visible."""
         if not self.vis_ptr or not self.n_rows:
             return None
+        self._wait()
         nw = (self.n_rows + 63) // 64
         words = torch.empty(nw, dtype=torch.int64, device="cuda")
         cudart().cudaMemcpy(C.c_void_p(words.data_ptr()), C.c_void_p(self.vis_ptr), C.c_size_t(nw * 8), 3)
@@ -194,7 +208,7 @@ def agg_push_device(executor, chunk: DeviceChunk, stream: Optional[torch.cuda.St
 def agg_flush_device(executor, epoch: int, stream: Optional[torch.cuda.Stream] = None) -> DeviceView:
     view = abi.RwChunk()
     _check(_lib().rwgpu_agg_flush_device(executor._h, epoch, C.byref(view), _stream_ptr(stream)))
-    return DeviceView(view)
+    return DeviceView(view, stream)
 
 
 def agg_flush_device_async(executor, epoch: int, stream: Optional[torch.cuda.Stream] = None):
@@ -206,7 +220,7 @@ def agg_flush_collect(executor, stream: Optional[torch.cuda.Stream] = None) -> D
     """wait for the oldest outstanding barrier; -> its delta (device pointers)"""
     view = abi.RwChunk()
     _check(_lib().rwgpu_agg_flush_collect(executor._h, C.byref(view), _stream_ptr(stream)))
-    return DeviceView(view)
+    return DeviceView(view, stream)
 
 
 def join_push_device(executor, side: int, chunk: DeviceChunk, stream: Optional[torch.cuda.Stream] = None,
@@ -220,7 +234,7 @@ def join_push_device(executor, side: int, chunk: DeviceChunk, stream: Optional[t
     else:
         _check(_lib().rwgpu_join_push_device_counted(executor._h, side, C.byref(ch), C.c_void_p(n_rows_dev), C.byref(view),
                                                      _stream_ptr(stream)))
-    return DeviceView(view)
+    return DeviceView(view, stream)
 
 
 def join_push_device_async(executor, side: int, chunk: DeviceChunk, stream: Optional[torch.cuda.Stream] = None,
@@ -235,7 +249,7 @@ def join_collect(executor, stream: Optional[torch.cuda.Stream] = None) -> Device
     """COLLECT half: wait for the oldest outstanding push; -> its output (device pointers)"""
     view = abi.RwChunk()
     _check(_lib().rwgpu_join_collect(executor._h, C.byref(view), _stream_ptr(stream)))
-    return DeviceView(view)
+    return DeviceView(view, stream)
 
 
 def profile(executor, kind: str, enable: bool):
