@@ -241,11 +241,13 @@ def pin_to_gpu_numa_node(gpu_index):
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r1_traffic.json), or None"""
-    try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kernel]["bytes_per_launch"])
-    except Exception:
-        return None
+    """DRAM bytes per launch of `kernel` from the committed ncu captures (profiles/r2_traffic.json, r1_traffic.json), or None"""
+    for f in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            return float(json.load(open(os.path.join(ROOT, "profiles", f)))[kernel]["bytes_per_launch"])
+        except Exception:
+            continue
+    return None
 
 
 def bench_config(world):
@@ -637,9 +639,9 @@ def run_ours(args):
                                   "exchange": None if world == 1 else ex_name},
                 "host_ms_per_step": {"enqueue_exchange": 1e3 * t_ex / K, "join_launch_and_collect": 1e3 * t_join / K},
                 "build_rows_per_s": N_BUILD * world / build_s, "out_rows": out_rows, "gpu_launches": int(launches), "clocks": clocks,
-                "roofline": {"bound": "hbm", "kernel": "join_inner_q4_kernel<false> (probe + emit + own-side append, 4 lanes per row)",
+                "roofline": {"bound": "hbm", "kernel": "uni_hot_kernel<false,false,4> (unified bucket: probe + emit + own-side append, 4 lanes per row)",
                              "achieved": fused_gbs, "peak": peak, "unit": "GB/s", "frac": fused_gbs / peak if fused_gbs else None,
-                             "traffic": ncu_traffic("join_inner_q4_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                             "traffic": ncu_traffic("uni_hot_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write)",
                              "algorithmic_bytes_per_launch": JOIN_BYTES_PER_ROW_STEP * BATCH,
                              "peak_source": which, "algorithmic_bytes_per_row": JOIN_BYTES_PER_ROW_STEP,
                              "rows_per_launch": BATCH, "kernel_ms_avg": kern_ms / max(kern_n, 1),
@@ -715,7 +717,7 @@ def run_ours(args):
                                 f"({(W + K + V) * BATCH} bids stored), 2^19 pairs = 2^20 rows per step",
                     "metric": "input rows/s", "value": KR * 2 * RP / (rms / 1e3), "steps": KR, "ms_per_step": rms / KR,
                     "out_rows_per_input_row": m_avg,
-                    "roofline": {"bound": "hbm", "kernel": "uni_quad_kernel<false,true> (inline-side rows: chain walk + emit + inline claim) + uni_delete_kernel",
+                    "roofline": {"bound": "hbm", "kernel": "uni_hot_kernel<false,true,4> (inline-side rows: bucket + inline claim; chain walk + emit deferred to uni_tail_kernel)",
                                  "achieved": bpr * 2 * RP * rk_n / (rk_ms / 1e3) / 1e9 if rk_ms else None, "peak": peak, "unit": "GB/s",
                                  "frac": (bpr * 2 * RP * rk_n / (rk_ms / 1e3) / 1e9 / peak) if rk_ms else None,
                                  "algorithmic_bytes_per_row": bpr, "kernel_ms_avg": rk_ms / max(rk_n, 1), "traffic": None}}
@@ -768,7 +770,7 @@ def run_ours(args):
             hg = JOIN_BYTES_PER_ROW_STEP * BATCH * hk_n / (hk_ms / 1e3) / 1e9 if hk_ms else None
             line["hot"] = {"workload": "cfg3 hot variant: half of the bids go to 100 hot auctions (same-bucket atomics, long chains)",
                            "metric": "input rows/s", "value": KH * BATCH / (hms / 1e3), "steps": KH, "ms_per_step": hms / KH,
-                           "roofline": {"bound": "hbm", "kernel": "uni_quad_kernel<false,false>", "achieved": hg, "peak": peak, "unit": "GB/s",
+                           "roofline": {"bound": "hbm", "kernel": "uni_hot_kernel<false,false,4>", "achieved": hg, "peak": peak, "unit": "GB/s",
                                         "frac": hg / peak if hg else None, "algorithmic_bytes_per_row": JOIN_BYTES_PER_ROW_STEP,
                                         "kernel_ms_avg": hk_ms / max(hk_n, 1), "traffic": None}}
             del jh, hdev

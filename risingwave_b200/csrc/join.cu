@@ -2106,14 +2106,37 @@ static int join_order(rwgpu_join* h, cudaStream_t st) {
   return RW_OK;
 }
 
-static void uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_only) {
-  const UniDev t = uni_dev(h);
+// grid of the cooperative tail kernel: every block resident at once (cooperative launch), no more than the rows need
+static int uni_tail_grid(int64_t n) {
+  static int max_blocks = 0;
+  if (!max_blocks) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int a = 0, b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, uni_tail_kernel<false>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, uni_tail_kernel<true>, 256, 0);
+    per_sm = std::max(1, std::min(std::min(a, b), 4));
+    max_blocks = std::max(1, sms * per_sm);
+  }
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, max_blocks));
+}
+
+// main kernel (timed by the profiler) + the cooperative tail kernel, which ends by publishing the status block
+// (tagged `tag`) into the pinned slot of the push's output set
+static int uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_only, unsigned long long tag) {
+  UniDev t = uni_dev(h);
   const JoinPlanDev* pdev = h->plan_dev.as<JoinPlanDev>();
   JoinStatus* ds = h->status.as<JoinStatus>();
-  const int S = pd.S;
+  int S = pd.S;
   const bool is_row = S == h->uni_is;
+  JoinOutDev od = out_dev(h);
+  UniWork wk;
+  wk.entry = h->uni_wk_entry.as<UniDefer>();
+  wk.mask = h->uni_wk_mask.as<uint8_t>();
+  W8Plan w = h->w8[S];
+  h->prof.begin(pd.st);
   if (pd.plain) {
-    const W8Plan& w = h->w8[S];
     PlainChunk pc;
     pc.ops = pd.ch.ops;
     for (int c = 0; c < 4; c++) pc.c[c] = c < w.n_u ? (const unsigned long long*)pd.ch.cols[c].data : nullptr;
@@ -2125,7 +2148,6 @@ static void uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_onl
     own.log_cap = t.log_cap[S];
     own.pools = t.pools[S];
     own.log_next = t.log_next[S];
-    const JoinOutDev od = out_dev(h);
     PlainOut po;
     po.ops = od.ops;
     po.vis = od.vis;
@@ -2134,12 +2156,10 @@ static void uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_onl
       po.mcol[c] = (c < w.n_m && w.m_out[c] >= 0) ? (unsigned long long*)od.col[w.m_out[c]] : nullptr;
     }
     po.capacity = od.capacity;
-    UniWork wk;
-    wk.entry = h->uni_wk_entry.as<UniDefer>();
-    wk.mask = h->uni_wk_mask.as<uint8_t>();
     // resident blocks per SM (registers per thread): 4 (64) by default; RWGPU_UNI_MINB=3 / 5 / 6 for tuning runs
     static const int minb = getenv("RWGPU_UNI_MINB") ? atoi(getenv("RWGPU_UNI_MINB")) : 4;
-#define UNI_LAUNCH(PO, IS, MB) uni_hot_kernel<PO, IS, MB><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pc, t.buckets, t.cap, own, po, wk, ds, pd.seq_base, pd.out_base, pd.pool_chunk)
+    static const uint32_t kflags = getenv("RWGPU_UNI_FLAGS") ? (uint32_t)atoi(getenv("RWGPU_UNI_FLAGS")) : 1u;  // bit 0: L2 prefetch of the next bucket
+#define UNI_LAUNCH(PO, IS, MB) uni_hot_kernel<PO, IS, MB><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pc, t.buckets, t.cap, own, po, wk, ds, pd.seq_base, pd.out_base, pd.pool_chunk, kflags)
     if (probe_only) {
       if (is_row) UNI_LAUNCH(true, true, 4); else UNI_LAUNCH(true, false, 4);
     } else if (is_row) {
@@ -2153,14 +2173,25 @@ static void uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_onl
       }
     }
 #undef UNI_LAUNCH
-    // the rows the hot kernel deferred (exits at once when it deferred none)
-    if (probe_only) uni_deferred_kernel<true><<<jgrid(pd.ch.n, 256), 256, 0, pd.st>>>(pdev, w, S, pd.ch, t, od, wk, ds, pd.seq_base, pd.out_base);
-    else uni_deferred_kernel<false><<<jgrid(pd.ch.n, 256), 256, 0, pd.st>>>(pdev, w, S, pd.ch, t, od, wk, ds, pd.seq_base, pd.out_base);
-    h->launches++;
   } else {
-    if (probe_only) uni_slow_kernel<true><<<jgrid(pd.ch.n, 256), 256, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base);
-    else uni_slow_kernel<false><<<jgrid(pd.ch.n, 256), 256, 0, pd.st>>>(pdev, h->w8[S], S, pd.ch, t, out_dev(h), ds, pd.seq_base, pd.out_base);
+    if (probe_only) uni_slow_kernel<true><<<jgrid(pd.ch.n, 256), 256, 0, pd.st>>>(pdev, w, S, pd.ch, t, od, ds, pd.seq_base, pd.out_base);
+    else uni_slow_kernel<false><<<jgrid(pd.ch.n, 256), 256, 0, pd.st>>>(pdev, w, S, pd.ch, t, od, ds, pd.seq_base, pd.out_base);
   }
+  h->prof.end(pd.st);
+  RW_CUDA(cudaGetLastError());
+  // tail: deferred rows, own-side deletes, status publication
+  DevChunk chv = pd.ch;
+  uint64_t seq_base = pd.seq_base;
+  int64_t out_base = pd.out_base;
+  JoinStatus* slot = (JoinStatus*)(h->status_host.as<uint8_t>() + 512 * pd.set);
+  int reset = 3;
+  unsigned int* done = (unsigned int*)(h->uni_counters.as<unsigned long long>() + 6);
+  void* args[] = {(void*)&pdev, (void*)&w, (void*)&S, (void*)&chv, (void*)&t, (void*)&od, (void*)&wk, (void*)&ds, (void*)&seq_base, (void*)&out_base,
+                  (void*)&slot, (void*)&tag, (void*)&reset, (void*)&done};
+  const void* fn = probe_only ? (const void*)uni_tail_kernel<true> : (const void*)uni_tail_kernel<false>;
+  RW_CUDA(cudaLaunchCooperativeKernel(fn, dim3(uni_tail_grid(pd.ch.n)), dim3(256), args, 0, pd.st));
+  h->launches += 2;
+  return RW_OK;
 }
 
 // LAUNCH half of a push: main kernel + delete kernel (which publishes the status block into the output set's pinned
@@ -2225,14 +2256,8 @@ static int uni_enqueue(rwgpu_join* h, int S, const DevChunk& ch_in, cudaStream_t
   own.n_rows += (uint64_t)n + id_slack;  // upper bounds until the status comes back
   h->uni_keys += (uint64_t)n;
   static const bool dbg_probe_only = getenv("RWGPU_DBG_PROBE_ONLY") != nullptr;  // timing experiments only (state is not updated)
-  h->prof.begin(st);
-  uni_launch_main(h, *pd, dbg_probe_only && S == 0);
-  h->prof.end(st);
-  JoinStatus* slot = (JoinStatus*)(h->status_host.as<uint8_t>() + 512 * pd->set);
-  uni_delete_kernel<<<jgrid(n, 256), 256, 0, st>>>(h->plan_dev.as<JoinPlanDev>(), S, ch, uni_dev(h), h->status.as<JoinStatus>(), pd->seq_base, slot,
-                                                     pd->tag, 3);
-  RW_CUDA(cudaGetLastError());
-  h->launches += 2;
+  rc = uni_launch_main(h, *pd, dbg_probe_only && S == 0, pd->tag);
+  if (rc != RW_OK) return rc;
   if (!h->pend_ev[pd->set]) RW_CUDA(cudaEventCreateWithFlags(&h->pend_ev[pd->set], cudaEventDisableTiming));
   RW_CUDA(cudaEventRecord(h->pend_ev[pd->set], st));
   if (uni_trace)
@@ -2249,23 +2274,16 @@ static int uni_finish(rwgpu_join* h, const JoinPending& pd, int64_t* out_rows, u
   JoinStatus* ds = h->status.as<JoinStatus>();
   JoinStatus* slot = (JoinStatus*)(h->status_host.as<uint8_t>() + 512 * pd.set);
   JoinStatus hs;
-  auto read_status = [&](int reset) -> int {  // one-thread kernel: counters -> status block -> pinned host memory
-    uni_status_kernel<<<1, 1, 0, st>>>(uni_dev(h), ds, slot, 0ull, reset);
-    RW_CUDA(cudaGetLastError());
-    h->launches++;
-    RW_CUDA(cudaStreamSynchronize(st));
-    memcpy(&hs, slot, sizeof(JoinStatus));
-    return RW_OK;
-  };
   const double tr0 = uni_trace ? uni_now_ms() : 0.0;
   RW_CUDA(cudaEventSynchronize(h->pend_ev[pd.set]));
   const double tr1 = uni_trace ? uni_now_ms() : 0.0;
   int rc;
-  if (*(volatile unsigned long long*)(slot + 1) == pd.tag) memcpy(&hs, slot, sizeof(JoinStatus));
-  else { rc = read_status(3); if (rc != RW_OK) return rc; }  // the delete kernel had real work: it did not publish
+  if (*(volatile unsigned long long*)(slot + 1) != pd.tag) return fail(RW_ERR_CUDA, "join status block was not published");
+  memcpy(&hs, slot, sizeof(JoinStatus));
   unsigned int err = hs.err;
   const unsigned long long first_null = hs.null_mask;
   const bool first_match = hs.pad != 0;
+  const unsigned long long first_del = hs.n_del;
   const bool redone = (hs.err & JERR_OUT_CAPACITY) != 0;
   if (redone) {
     // the extra-match area overflowed: redo the probe + emit with room for every reservation.  The probe reads the
@@ -2275,14 +2293,16 @@ static int uni_finish(rwgpu_join* h, const JoinPending& pd, int64_t* out_rows, u
     RW_CUDA(cudaMemsetAsync(&ds->err, 0, 4, st));
     rc = join_ensure_out(h, pd.out_base + n + extras + (int64_t)pd.grid * 8 * U_XCHUNK, st, pd.out_base);
     if (rc != RW_OK) return rc;
-    uni_launch_main(h, pd, true);
-    RW_CUDA(cudaGetLastError());
-    h->launches++;
-    rc = read_status(3);
+    const unsigned long long tag2 = ++h->status_tag;
+    rc = uni_launch_main(h, pd, true, tag2);
     if (rc != RW_OK) return rc;
+    RW_CUDA(cudaStreamSynchronize(st));
+    if (*(volatile unsigned long long*)(slot + 1) != tag2) return fail(RW_ERR_CUDA, "join status block was not published");
+    memcpy(&hs, slot, sizeof(JoinStatus));
     err = (err & ~JERR_OUT_CAPACITY) | hs.err;
     hs.null_mask |= first_null & ~(1ull << 63);
     hs.pad = hs.pad || first_match;
+    hs.n_del = first_del;  // (the redo is probe-only: it counts no deletes)
   }
   // bookkeeping: what the device really used, plus the upper bounds of the pushes enqueued after this one
   for (int s = 0; s < 2; s++) h->uni_dead[s] = hs.n_dead[s];

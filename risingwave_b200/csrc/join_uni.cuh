@@ -25,6 +25,7 @@
 // that line (one 32/64 B write-back), 48 B appended to the log, 33 B read and 65 B written sequentially.
 // An IS row (auction) reads its bucket, walks the CS chain for matches, and claims the inline record.
 #pragma once
+#include <cooperative_groups.h>
 
 namespace rw {
 
@@ -325,7 +326,8 @@ struct UniWork {
 
 template <bool PROBE_ONLY, bool IS_ROW, int MINB>
 __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, uint8_t* buckets, uint64_t cap, UniOwn own, PlainOut o, UniWork wk,
-                                                                  JoinStatus* st, uint64_t seq_base, int64_t out_base, uint32_t pool_chunk) {
+                                                                  JoinStatus* st, uint64_t seq_base, int64_t out_base, uint32_t pool_chunk,
+                                                                  uint32_t kflags) {
   int64_t n_rows = ch.n;
   if (ch.n_dev) {
     const int64_t nd = *ch.n_dev;
@@ -427,6 +429,12 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
       }
     }
     if (first_iter) UNI_FETCH(g + nwarps);
+    // the NEXT group's bucket line is pulled into L2 while this group's atomics and stores are in flight (its
+    // key arrived with the column loads issued above): the next iteration's probe then waits for L2, not DRAM
+    if ((kflags & 1u) && n_op != 0 && !(q & 1)) {
+      const uint8_t* nb_ = buckets + uhome(n_key, mask) * 64 + 16 * q;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nb_));
+    }
     if (created && q == 0) new_keys++;
     // ---- what does the other side hold for the key ?
     const unsigned long long WI = shfl64m(0xffffffffu, pv.y, qlead);
@@ -609,11 +617,10 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
   }
 }
 
-// the rows uni_hot_kernel deferred, one thread per input row (exits at once when there are none)
+// the rows uni_hot_kernel deferred, one thread per input row (phase 1 of uni_tail_kernel)
 template <bool PROBE_ONLY>
-__global__ void __launch_bounds__(256) uni_deferred_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch, UniDev t, JoinOutDev o,
-                                                           UniWork wk, JoinStatus* st, uint64_t seq_base, int64_t out_base) {
-  if (*(volatile unsigned long long*)&st->n_defer == 0ull) return;
+__device__ __forceinline__ void uni_deferred_body(const JoinPlanDev* __restrict__ p, const W8Plan& w, int S, const DevChunk& ch, const UniDev& t,
+                                                  const JoinOutDev& o, const UniWork& wk, JoinStatus* st, uint64_t seq_base, int64_t out_base) {
   const int64_t n_rows = chunk_rows(ch, st, false);
   unsigned new_keys = 0;
   bool any_match = false, any_hole = false;
@@ -652,17 +659,9 @@ __device__ __forceinline__ bool uni_pk_equal(const JoinPlanDev* p, int S, const 
 // status block).  Sequential rule: the delete at chunk position r removes the live row with equal pk that
 // arrived most recently BEFORE r: rows this very chunk inserted at positions >= r are excluded by their 64-bit
 // arrival number (seq_base .. seq_base + n), every other live pk-equal row is older; the newest wins.
-__global__ void __launch_bounds__(256) uni_delete_kernel(const JoinPlanDev* __restrict__ p, int S, DevChunk ch, UniDev t, JoinStatus* st,
-                                                          uint64_t seq_base, JoinStatus* status_host, unsigned long long tag, int reset) {
+__device__ __forceinline__ void uni_delete_body(const JoinPlanDev* __restrict__ p, int S, const DevChunk& ch, const UniDev& t, JoinStatus* st,
+                                                uint64_t seq_base) {
   const int64_t n_rows = chunk_rows(ch, st, false);
-  if (*(volatile unsigned long long*)&st->n_del == 0ull) {
-    if (status_host && blockIdx.x == 0 && threadIdx.x == 0) {
-      st->log_next[0] = *t.log_next[0]; st->log_next[1] = *t.log_next[1];
-      st->n_dead[0] = *t.n_dead[0]; st->n_dead[1] = *t.n_dead[1];
-      join_status_publish(st, status_host, tag, reset);
-    }
-    return;
-  }
   const uint64_t SEQ56 = (1ull << 56) - 1;
   unsigned int dead_log = 0;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
@@ -736,6 +735,37 @@ __global__ void __launch_bounds__(256) uni_delete_kernel(const JoinPlanDev* __re
     if (!found && p->strict) atomicOr(&st->err, JERR_DOUBLE_DELETE);
   }
   if (dead_log) atomicAdd(t.n_dead[S], (unsigned long long)dead_log);
+}
+
+// Everything behind the hot kernel in ONE cooperative launch: (1) the deferred rows, (2) the own-side deletes, (3) the
+// status block published to pinned host memory by the block that finishes last.  Phases 1 and 2 exit at once when
+// the hot kernel flagged no such rows (st->n_defer / st->n_del: final when this kernel starts, so every block takes
+// the same path); only a batch with BOTH needs the grid-wide barrier between them (a delete must see the rows the
+// deferred phase appended).  `plain` = the chunk went through uni_hot_kernel (else uni_slow_kernel: nothing deferred).
+template <bool PROBE_ONLY>
+__global__ void __launch_bounds__(256) uni_tail_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch, UniDev t, JoinOutDev o, UniWork wk,
+                                                       JoinStatus* st, uint64_t seq_base, int64_t out_base, JoinStatus* status_host,
+                                                       unsigned long long tag, int reset, unsigned int* done) {
+  const bool has_defer = *(volatile unsigned long long*)&st->n_defer != 0ull;
+  const bool has_del = !PROBE_ONLY && *(volatile unsigned long long*)&st->n_del != 0ull;
+  if (has_defer) uni_deferred_body<PROBE_ONLY>(p, w, S, ch, t, o, wk, st, seq_base, out_base);
+  if (has_del) {
+    if (has_defer) cooperative_groups::this_grid().sync();
+    uni_delete_body(p, S, ch, t, st, seq_base);
+  }
+  // last block out publishes (every block's work is fenced before its ticket)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int ticket = atomicAdd(done, 1u);
+    if (ticket == gridDim.x - 1) {
+      *done = 0u;
+      __threadfence();
+      st->log_next[0] = *(volatile unsigned long long*)t.log_next[0]; st->log_next[1] = *(volatile unsigned long long*)t.log_next[1];
+      st->n_dead[0] = *(volatile unsigned long long*)t.n_dead[0]; st->n_dead[1] = *(volatile unsigned long long*)t.n_dead[1];
+      join_status_publish(st, status_host, tag, reset);
+    }
+  }
 }
 
 // watermark-driven state cleaning (JoinHashMap::update_watermark, join/hash_join.rs; applied at the barrier like the
