@@ -298,3 +298,137 @@ def run_nexmark_q8(backend):
     assert all(v in (0, 1) for v in mv.values())
     got = sorted([k[0], name[k[0]], k[1]] for k, v in mv.items() if v)
     assert got == sorted(fx["expected_q8"])
+
+
+def run_tpch_q3(backend, n_cust=300, n_orders=1500, n_items=6000, seed=0x7C43, epochs=6):
+    """SURVEY 8(d) cfg5, the TPC-H q3 streaming plan (src/frontend/planner_test/tests/testdata/output/tpch.yaml,
+    `tpch_q3` stream_plan) at test size, incrementally through the operators of `backend`:
+        customer [c_mktsegment filter upstream] JOIN orders ON c_custkey = o_custkey  [o_orderdate < D1]
+          -> Project(o_orderkey, o_orderdate, o_shippriority)
+          JOIN lineitem ON l_orderkey = o_orderkey                                    [l_shipdate > D1]
+          -> Project(l_orderkey, o_orderdate, o_shippriority, l_extendedprice * (100 - l_discount))
+          -> HashAgg(sum, count GROUP BY l_orderkey, o_orderdate, o_shippriority)      (Key128-class key: i64, date, i32)
+    Money is scale-2 fixed point in int64 (revenue = scale 4), the sum accumulates in 128 bits and leaves as a decimal.
+    The streams carry retractions (orders are deleted again, line items updated), so both joins emit Delete rows and
+    the aggregation retracts.  Returns (materialized view {key: (count, revenue)}, per-barrier delta multisets); the view
+    is checked here against a direct evaluation of the SQL over the rows that are live at the end."""
+    from collections import Counter
+    from risingwave_b200.executor import AggCall, FilterExecutor, HashAggExecutor, HashJoinExecutor, JoinParams, MockSource, ProjectExecutor
+    from risingwave_b200.stream_chunk import Column, StreamChunk
+    I, D, I4 = abi.T_INT64, abi.T_DATE, abi.T_INT32
+    NPT = {I: np.int64, D: np.int32, I4: np.int32}
+    rng = np.random.default_rng(seed)
+    D1 = 9204  # 1995-03-15 as days since 1970-01-01
+    # ---- tables (customer: only the rows that pass the segment filter reach the join)
+    cust = [(int(k),) for k in rng.permutation(n_cust * 5)[:n_cust]]
+    cust_keys = np.array([c[0] for c in cust] + list(range(n_cust * 5, n_cust * 5 + 40)))  # some orders of filtered-out customers
+    orders = [(int(ok), int(rng.choice(cust_keys)), int(D1 + rng.integers(-60, 20)), int(rng.integers(0, 3)))
+              for ok in rng.permutation(n_orders * 4)[:n_orders]]
+    okeys = np.array([o[0] for o in orders])
+    items = []
+    seen = Counter()
+    for _ in range(n_items):
+        ok = int(rng.choice(okeys))
+        seen[ok] += 1
+        items.append((ok, int(rng.integers(100, 10_000_000)), int(rng.integers(0, 11)), int(D1 + rng.integers(-20, 60)), seen[ok]))
+    T_ORD, T_ITEM = [I, I, D, I4], [I, I, I, D, I]
+
+    def chunk(rows, types, ops=None):
+        cols = list(zip(*rows))
+        return StreamChunk(np.full(len(rows), abi.OP_INSERT, np.uint8) if ops is None else np.asarray(ops, np.uint8),
+                           [Column(t, np.array(c, dtype=NPT[t])) for t, c in zip(types, cols)])
+
+    def src(types, pk):
+        _, s = MockSource.channel()
+        return s.into_executor(types, pk)
+
+    f_ord = FilterExecutor(backend, src(T_ORD, [0]), f"(less_than:boolean $2:date {D1}:date)")
+    f_item = FilterExecutor(backend, src(T_ITEM, [0, 4]), f"(greater_than:boolean $3:date {D1}:date)")
+    # join 1: customer (key 0) x orders (key col 1 = o_custkey, stream key o_orderkey)
+    j1 = HashJoinExecutor(backend, abi.JOIN_INNER, src([I], [0]), src(T_ORD, [0]), JoinParams([0], [0]), JoinParams([1], [0]), [False])
+    p1 = ProjectExecutor(backend, src([I] + T_ORD, []), ["$1:int8", "$3:date", "$4:int4"])
+    # join 2: (o_orderkey, o_orderdate, o_shippriority) x lineitem (key col 0, stream key (l_orderkey, l_linenumber))
+    j2 = HashJoinExecutor(backend, abi.JOIN_INNER, src([I, D, I4], [0]), src(T_ITEM, [0, 4]), JoinParams([0], [0]), JoinParams([0], [0, 4]), [False])
+    p2 = ProjectExecutor(backend, src([I, D, I4] + T_ITEM, []),
+                         ["$3:int8", "$1:date", "$2:int4", "(multiply:int8 $4:int8 (subtract:int8 100:int8 $5:int8))"])
+    agg = HashAggExecutor(backend, src([I, D, I4, I], []), False,
+                          [AggCall.from_pretty(c) for c in ("(count:int8)", "(sum:decimal $3:int8)")], 0, [0, 1, 2])
+    mv, deltas = {}, []
+
+    def to_agg(chunks):
+        for ch in chunks:
+            if ch.cardinality():
+                agg.apply_chunk(p2.apply_project_exprs(ch))
+
+    def push_orders(rows, ops=None):
+        f = f_ord.filter(chunk(rows, T_ORD, ops))
+        if f is None:
+            return
+        for ch in j1.eq_join_oneside(1, f):
+            if ch.cardinality():
+                to_agg(j2.eq_join_oneside(0, p1.apply_project_exprs(ch)))
+
+    def push_items(rows, ops=None):
+        f = f_item.filter(chunk(rows, T_ITEM, ops))
+        if f is not None:
+            to_agg(j2.eq_join_oneside(1, f))
+
+    def push_customers(rows):
+        for ch in j1.eq_join_oneside(0, chunk(rows, [I])):
+            if ch.cardinality():
+                to_agg(j2.eq_join_oneside(0, p1.apply_project_exprs(ch)))
+
+    def barrier(epoch):
+        d = Counter()
+        for ch in agg.flush_data(epoch):
+            for op, row in ch.rows():
+                key, val = tuple(row[:3]), (row[3], row[4])
+                d[(op, key, val)] += 1
+                if op in (abi.OP_INSERT, abi.OP_UPDATE_INSERT):
+                    mv[key] = val
+                else:
+                    assert mv.get(key) == val, (key, val, mv.get(key))
+                    del mv[key]
+        deltas.append(d)
+
+    live_orders, live_items = {}, {}
+    co = len(cust) // epochs + 1
+    oo = len(orders) // epochs + 1
+    io = len(items) // epochs + 1
+    for e in range(epochs):
+        push_customers(cust[e * co:(e + 1) * co])
+        new_o = orders[e * oo:(e + 1) * oo]
+        if new_o:
+            push_orders(new_o)
+            live_orders.update({o[0]: o for o in new_o})
+        new_i = items[e * io:(e + 1) * io]
+        if new_i:
+            push_items(new_i)
+            live_items.update({(i[0], i[4]): i for i in new_i})
+        # retractions: a few orders disappear, a few line items change their discount (U- / U+)
+        gone = [live_orders.pop(k) for k in list(live_orders)[:: 17][:20]]
+        if gone:
+            push_orders(gone, [abi.OP_DELETE] * len(gone))
+        upd = [live_items[k] for k in list(live_items)[:: 23][:30]]
+        if upd:
+            rows, ops = [], []
+            for it in upd:
+                new = (it[0], it[1], (it[2] + 3) % 11, it[3], it[4])
+                rows += [it, new]
+                ops += [abi.OP_UPDATE_DELETE, abi.OP_UPDATE_INSERT]
+                live_items[(it[0], it[4])] = new
+            push_items(rows, ops)
+        barrier(e + 1)
+    # ---- the SQL, evaluated directly over the live rows
+    custset = {c[0] for c in cust}
+    want = {}
+    for it in live_items.values():
+        o = live_orders.get(it[0])
+        if o is None or it[3] <= D1 or o[2] >= D1 or o[1] not in custset:
+            continue
+        key = (o[0], o[2], o[3])
+        n, s = want.get(key, (0, 0))
+        want[key] = (n + 1, s + it[1] * (100 - it[2]))
+    got = {k: (v[0], int(v[1])) for k, v in mv.items()}
+    assert got == want, (len(got), len(want))
+    return got, deltas

@@ -186,3 +186,19 @@ def test_project_expressions_match_oracle(cuda, oracle):
         ch = StreamChunk(rng.integers(1, 5, n).astype(np.uint8), cols, rng.random(n) > 0.05)
         g, o = (pe.apply_project_exprs(ch) for pe in pes)
         assert g == o, f"n={n}"
+
+
+def test_tpch_q3_pipeline(cuda, oracle):
+    """SURVEY 8(d) cfg5 (TPC-H q3 streaming plan: customer x orders x lineitem -> sum / count by (orderkey, orderdate,
+    shippriority)) through the CUDA operators: the view equals the SQL evaluated directly (checked inside run_tpch_q3) and
+    every barrier's delta multiset equals the oracle's.  Mixed-width payload (int64 / date / int32) keeps both joins on
+    the general inner-join kernels, the aggregation on the multi-column-key path with a 128-bit sum."""
+    from helpers import run_tpch_q3
+    got, deltas = run_tpch_q3(cuda)
+    want, want_deltas = run_tpch_q3(oracle)
+    assert got == want
+    assert deltas == want_deltas
+    # a second size: larger chunks, more retractions in flight per epoch
+    got, deltas = run_tpch_q3(cuda, n_cust=2000, n_orders=20000, n_items=80000, seed=5, epochs=4)
+    want, want_deltas = run_tpch_q3(oracle, n_cust=2000, n_orders=20000, n_items=80000, seed=5, epochs=4)
+    assert got == want and deltas == want_deltas

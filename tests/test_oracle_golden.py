@@ -259,3 +259,11 @@ def test_project_arithmetic_is_non_strict_and_tumble_follows_the_reference_formu
                 d = x - v
                 want[4] = d if -(1 << 31) <= d < (1 << 31) else None
         assert list(g) == want, (v, w, x, g, want)
+
+
+def test_tpch_q3_pipeline_oracle(oracle):
+    """the TPC-H q3 streaming plan (two inner joins, two projects, a three-column-key aggregation with a
+    128-bit sum) through the oracle's operators, with retractions; the view must equal the SQL evaluated directly."""
+    from helpers import run_tpch_q3
+    got, deltas = run_tpch_q3(oracle)
+    assert len(got) > 50 and any(op == abi.OP_UPDATE_DELETE for d in deltas for (op, _, _) in d)
