@@ -487,12 +487,17 @@ def run_ours(args):
 
     if world > 1:
         from risingwave_b200 import exchange
-        if os.environ.get("RWGPU_EXCHANGE", "p2p") == "nccl":
+        ex_kind = os.environ.get("RWGPU_EXCHANGE", "flat")
+        if ex_kind == "nccl":
             ex_plan = exchange.ShufflePlan(world, rank, key_indices=[0], types=T4)
             ex_name = "crc32 vnode partition kernel + NCCL all_to_all_single per column"
-        else:
+        elif ex_kind == "p2p":
             ex_plan = exchange.P2PShufflePlan(world, rank, key_indices=[0], types=T4, batch_rows=BATCH)
             ex_name = "crc32 vnode partition kernel storing straight into the peers' receive regions over NVLink (symmetric memory), device barrier, unpack kernel"
+        else:
+            ex_plan = exchange.FlatShufflePlan(world, rank, key_indices=[0], types=T4, batch_rows=BATCH)
+            ex_name = ("one cooperative kernel per batch: crc32 vnode histograms, scan, count exchange + cross-rank barrier, scatter over NVLink "
+                       "(symmetric memory) into the rows' final place in the destination's receive buffer, barrier; the join reads the buffer in place")
 
     def shuffled(cols_dev):
         if world == 1:
@@ -527,7 +532,7 @@ def run_ours(args):
 
             trace = os.environ.get("BENCH_TRACE") is not None  # per-phase wall clock (adds syncs: never for a reported number)
 
-            counted = world > 1 and isinstance(ex_plan, exchange.P2PShufflePlan)
+            counted = world > 1 and isinstance(ex_plan, (exchange.P2PShufflePlan, exchange.FlatShufflePlan))
             recv_chunks = [device.DeviceChunk(*ex_plan.output(b), T4) for b in range(2)] if counted else None
             t_ex = t_join = 0.0
             pending = {}

@@ -374,6 +374,32 @@ int32_t rwgpu_shuffle_exchange_p2p_device(const rw_chunk* chunk, const int32_t* 
                                           uint8_t* out_ops, void* const* out_cols, int64_t* counts,
                                           int32_t* overflow, int64_t* total_host, void* cuda_stream);
 
+/* ---- the exchange as ONE cooperative kernel, rows stored straight into their final place ------------------
+ * Flat receive buffer (symmetric, peer-mapped, two alternate): [header: int64 M[64][64], M[s][d] = rows source s sends
+ * to destination d][ops: cap_rows bytes][column k: cap_rows * width_k], parts 256-B aligned (rwgpu_shuffle_flat_layout
+ * returns the offsets).  One launch per batch: per-block histograms -> scan -> every source writes its count row into
+ * every rank's header -> cross-rank barrier -> every source scatters its rows over NVLink to
+ *     first row of (s -> d) = sum of M[s'][d] over s' < s        (source-rank order, row order kept inside a source)
+ * -> cross-rank barrier -> the received row count is stored to *total_dev (DEVICE int64, feed it to
+ * rwgpu_join_push_device_counted / _async) and, if given, *total_host (pinned).  Nothing is unpacked: the consumer
+ * reads ops / columns of the buffer in place.  Size cap_rows = n_dest x (rows per batch): no batch can overflow.
+ *   peer_bases : HOST array of n_dest peer-mapped pointers to THIS batch's receive buffer of every rank
+ *   peer_flags : as for rwgpu_shuffle_exchange_p2p_device; batch `epoch` (1, 2, ...) uses the values 2*epoch-1, 2*epoch
+ *   err        : DEVICE int32, bit 0 = a destination buffer was too small, bit 1 = a peer did not reach the barrier
+ *                within ~10 s (the count then reads -1)
+ *   max_blocks : 0 = as many blocks as are co-resident; > 0 caps the grid (several ranks sharing one device in tests)
+ * Caller contract: batch e is launched after this rank's consumer of batch e - 2 (same buffer) has finished; that is
+ * all the cross-rank ordering needed -- a peer writes into the buffer only after barrier 1 of batch e, which this
+ * rank enters inside its own launch.  Replaces dispatch.rs:961-1053 + the exchange channel + merge for N GPUs.     */
+int32_t rwgpu_shuffle_flat_layout(const int32_t* types, int32_t n_cols, int64_t cap_rows, int64_t* total_bytes,
+                                  int64_t* ops_off, int64_t* col_off /* [n_cols] */);
+int32_t rwgpu_shuffle_exchange_flat_device(const rw_chunk* chunk, const int32_t* key_indices, int32_t n_keys,
+                                           int32_t vnode_count, const int32_t* vnode_to_dest, int32_t n_dest,
+                                           int32_t my_rank, void* const* peer_bases, void* const* peer_flags,
+                                           uint64_t epoch, int64_t cap_rows, int64_t* counts, int32_t* err,
+                                           int64_t* total_dev, int64_t* total_host, int32_t max_blocks,
+                                           void* cuda_stream);
+
 /* ================================================================ Filter (operator chaining on the device)
  * Replaces FilterExecutorInner::filter           src/stream/src/executor/filter.rs:58-150
  * for predicates that are a CONJUNCTION of integer comparisons `col cmp col` / `col cmp constant`

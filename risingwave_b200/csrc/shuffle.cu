@@ -7,6 +7,8 @@
 // The reference builds one visibility bitmap per downstream actor over shared column buffers;
 // here rows are STABLY partitioned by destination GPU into contiguous regions (the send buffers
 // of an NCCL all-to-all-v), preserving per-key row order.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -434,6 +436,201 @@ __global__ void p2p_total_to_host_kernel(const int64_t* total, int64_t* total_ho
   __threadfence_system();
 }
 
+// ------------------------------------------------------------------ fused exchange: ONE cooperative kernel per batch
+// Flat receive buffer of a rank (symmetric on every rank, two of them alternate):
+//   [ header: int64 M[PART_MAX_DEST][PART_MAX_DEST], M[s][d] = rows source s sends to destination d in this batch ]
+//   [ ops: cap bytes ][ column k: cap * width_k bytes ]                      (each part 256-byte aligned)
+// Every source publishes its count row M[me][*] into EVERY rank's header, a cross-rank barrier makes the matrix
+// complete, and each source then knows where its rows belong inside every destination's buffer:
+//   first row of (s -> d) = sum over s' < s of M[s'][d]
+// so the scatter stores the rows over NVLink straight into their FINAL, contiguous place (source-rank order, row order
+// kept inside a source): nothing is unpacked on the receiving side, the consumer reads the buffer as it is.  A second
+// barrier tells every rank that its buffer is complete.  hist -> scan -> publish -> barrier -> scatter -> barrier are the
+// phases of one cooperative launch (grid-wide syncs in between), replacing six launches and the unpack copy.
+struct FlatLayout {
+  int64_t cap;  // rows a buffer can hold (the caller sizes it for world x batch rows: every batch fits)
+  int64_t ops_off;
+  int64_t col_off[RW_MAX_COLS];
+  int64_t total_bytes;
+  int n_cols;
+  int col_width[RW_MAX_COLS];
+};
+#define FLAT_HEADER_BYTES ((int64_t)PART_MAX_DEST * PART_MAX_DEST * 8)
+
+static int flat_layout(const int32_t* types, int n_cols, int64_t cap_rows, FlatLayout* L) {
+  if (n_cols < 0 || n_cols > RW_MAX_COLS || cap_rows <= 0) return fail(RW_ERR_INVALID, "flat layout");
+  auto up = [](int64_t x) { return (x + 255) / 256 * 256; };
+  int64_t off = FLAT_HEADER_BYTES;
+  L->cap = cap_rows;
+  L->n_cols = n_cols;
+  L->ops_off = off;
+  off = up(off + cap_rows);
+  for (int k = 0; k < n_cols; k++) {
+    int w = type_width(types[k]);
+    if (!w || type_is_varlen(types[k])) return fail(RW_ERR_UNSUPPORTED, "column type");
+    L->col_width[k] = w;
+    L->col_off[k] = off;
+    off = up(off + cap_rows * w);
+  }
+  L->total_bytes = off;
+  return RW_OK;
+}
+
+// signal every rank, wait for every rank (thread t <-> rank t); bounded: a peer that never arrives (a rank that died,
+// kernels that cannot run side by side) raises bit 1 of *err instead of hanging the GPU
+__device__ __forceinline__ void flat_barrier(const PeerBases& flags, int n, int my_rank, unsigned long long value, int* err) {
+  const int t = threadIdx.x;
+  if (t < n) {
+    __threadfence_system();
+    unsigned long long* remote = (unsigned long long*)flags.base[t] + my_rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(value) : "memory");
+    const unsigned long long* mine = (const unsigned long long*)flags.base[my_rank] + t;
+    unsigned long long v;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v < value && clock64() - t0 > 20000000000ll) { atomicOr(err, 2); break; }  // ~10 s
+    } while (v < value);
+  }
+}
+
+__global__ void __launch_bounds__(PART_BLOCK) flat_exchange_kernel(DevChunk ch, VnodePlan p, const int32_t* vnode_to_dest, int n_dest, int my_rank,
+                                                                    FlatLayout L, PeerBases peers, PeerBases flags, unsigned long long epoch,
+                                                                    uint8_t* dest, uint32_t* block_hist, int n_vblocks, int64_t* counts,
+                                                                    int64_t* total_dev, int64_t* total_host, int* err) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t tab[256];
+  __shared__ uint32_t hist[PART_MAX_DEST];
+  __shared__ uint32_t run[PART_MAX_DEST];
+  __shared__ uint32_t warp_cnt[PART_BLOCK / 32][PART_MAX_DEST];
+  __shared__ int64_t s_first[PART_MAX_DEST];  // first row of (me -> d) inside d's buffer
+  const int lane = lane_id(), wid = threadIdx.x >> 5;
+  tab[threadIdx.x] = crc_table_entry(threadIdx.x);
+  // ---- phase A: destination per row + per-block histograms
+  for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {
+    if (threadIdx.x < PART_MAX_DEST) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)vb * PART_ROWS_PER_BLOCK;
+    for (int i = threadIdx.x; i < PART_ROWS_PER_BLOCK; i += PART_BLOCK) {
+      const int64_t r = base + i;
+      if (r >= ch.n) break;
+      const uint8_t op = ch.ops[r];
+      uint8_t d = 255;
+      if (row_visible(ch, r, op)) {
+        d = (uint8_t)vnode_to_dest[row_vnode(tab, p, ch, r, true)];
+        atomicAdd(&hist[d], 1u);
+      }
+      dest[r] = d;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_dest) block_hist[(size_t)vb * n_dest + threadIdx.x] = hist[threadIdx.x];
+    __syncthreads();
+  }
+  grid.sync();
+  // ---- phase B (block 0): exclusive scan over the blocks per destination, count row to every rank, barrier 1
+  if (blockIdx.x == 0) {
+    for (int d = wid; d < n_dest; d += PART_BLOCK / 32) {
+      uint32_t acc = 0;
+      for (int b0 = 0; b0 < n_vblocks; b0 += 32) {
+        const int b = b0 + lane;
+        const uint32_t v = b < n_vblocks ? block_hist[(size_t)b * n_dest + d] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
+        }
+        if (b < n_vblocks) block_hist[(size_t)b * n_dest + d] = acc + inc - v;
+        acc += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) counts[d] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_dest * n_dest; i += PART_BLOCK) {  // M[me][d] into rank q's header
+      const int q = i / n_dest, d = i % n_dest;
+      int64_t* M = (int64_t*)peers.base[q];
+      M[(size_t)my_rank * PART_MAX_DEST + d] = counts[d];
+    }
+    __syncthreads();
+    flat_barrier(flags, n_dest, my_rank, 2ull * epoch - 1ull, err);
+  }
+  grid.sync();
+  // ---- phase C: stable scatter into the final place
+  {
+    const volatile int64_t* M = (const volatile int64_t*)peers.base[my_rank];
+    if (threadIdx.x < n_dest) {
+      int64_t first = 0;
+      for (int s2 = 0; s2 < my_rank; s2++) first += M[(size_t)s2 * PART_MAX_DEST + threadIdx.x];
+      s_first[threadIdx.x] = first;
+    }
+    __syncthreads();
+  }
+  for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {
+    if (threadIdx.x < PART_MAX_DEST) run[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)vb * PART_ROWS_PER_BLOCK;
+    for (int it = 0; it < PART_ROWS_PER_BLOCK / PART_BLOCK; it++) {
+      const int64_t r = base + it * PART_BLOCK + threadIdx.x;
+      const uint8_t d = (r < ch.n) ? dest[r] : 255;
+      const unsigned peers_m = __match_any_sync(0xffffffffu, (unsigned)d);
+      const unsigned rank_in_warp = __popc(peers_m & ((1u << lane) - 1));
+      for (int k = lane; k < n_dest; k += 32) warp_cnt[wid][k] = 0;
+      __syncwarp();
+      if (rank_in_warp == 0 && d != 255) warp_cnt[wid][d] = __popc(peers_m);
+      __syncthreads();
+      uint32_t pos = 0;
+      if (d != 255) {
+        uint32_t before = 0;
+        for (int w = 0; w < wid; w++) before += warp_cnt[w][d];
+        pos = run[d] + before + rank_in_warp;
+      }
+      __syncthreads();
+      if (threadIdx.x < n_dest) {
+        uint32_t tot = 0;
+        for (int w = 0; w < PART_BLOCK / 32; w++) tot += warp_cnt[w][threadIdx.x];
+        run[threadIdx.x] += tot;
+      }
+      if (d != 255) {
+        const int64_t dst = s_first[d] + (int64_t)block_hist[(size_t)vb * n_dest + d] + pos;
+        if (dst >= L.cap) {
+          atomicOr(err, 1);
+        } else {
+          uint8_t* buf = peers.base[d];
+          buf[L.ops_off + dst] = ch.ops[r];
+          for (int k = 0; k < ch.n_cols; k++) {
+            const ColRef& c = ch.cols[k];
+            uint8_t* col = buf + L.col_off[k];
+            switch (c.width) {
+              case 1: ((uint8_t*)col)[dst] = ((const uint8_t*)c.data)[r]; break;
+              case 2: ((uint16_t*)col)[dst] = ((const uint16_t*)c.data)[r]; break;
+              case 4: ((uint32_t*)col)[dst] = ((const uint32_t*)c.data)[r]; break;
+              case 8: ((uint64_t*)col)[dst] = ((const uint64_t*)c.data)[r]; break;
+              default: ((ulonglong2*)col)[dst] = ((const ulonglong2*)c.data)[r]; break;
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __threadfence_system();
+  grid.sync();
+  // ---- phase D (block 0): barrier 2, then the received row count for the consumer
+  if (blockIdx.x == 0) {
+    flat_barrier(flags, n_dest, my_rank, 2ull * epoch, err);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const volatile int64_t* M = (const volatile int64_t*)peers.base[my_rank];
+      int64_t total = 0;
+      for (int s2 = 0; s2 < n_dest; s2++) total += M[(size_t)s2 * PART_MAX_DEST + my_rank];
+      if (*(volatile int*)err) total = -1;
+      *total_dev = total;
+      if (total_host) { *total_host = total; __threadfence_system(); }
+    }
+  }
+}
+
 static int make_vnode_plan(const rw_chunk* c, const int32_t* keys, int n_keys, int vnode_count, VnodePlan* p) {
   if (n_keys < 1 || n_keys > RW_MAX_KEYS * 2) return fail(RW_ERR_UNSUPPORTED, "1..8 distribution key columns");
   if (vnode_count < 1 || vnode_count > 32768) return fail(RW_ERR_INVALID, "vnode_count (vnode.rs:79 MAX_COUNT = 2^15)");
@@ -694,6 +891,69 @@ int32_t rwgpu_shuffle_unpack_device(const void* recv_base, int32_t n_src, const 
   for (int k = 0; k < n_cols; k++) o.col[k] = out_cols[k];
   p2p_unpack_kernel<<<148 * 4, 256, 0, (cudaStream_t)cuda_stream>>>((const uint8_t*)recv_base, n_src, L, out_ops, o, total);
   RW_CUDA(cudaGetLastError());
+  return RW_OK;
+}
+
+int32_t rwgpu_shuffle_flat_layout(const int32_t* types, int32_t n_cols, int64_t cap_rows, int64_t* total_bytes, int64_t* ops_off,
+                                  int64_t* col_off) {
+  if (!types || !total_bytes || !ops_off || !col_off) return fail(RW_ERR_INVALID, "null");
+  FlatLayout L;
+  int rc = flat_layout(types, n_cols, cap_rows, &L);
+  if (rc != RW_OK) return rc;
+  *total_bytes = L.total_bytes;
+  *ops_off = L.ops_off;
+  for (int k = 0; k < n_cols; k++) col_off[k] = L.col_off[k];
+  return RW_OK;
+}
+
+int32_t rwgpu_shuffle_exchange_flat_device(const rw_chunk* c, const int32_t* keys, int32_t n_keys, int32_t vnode_count,
+                                           const int32_t* vnode_to_dest, int32_t n_dest, int32_t my_rank, void* const* peer_bases,
+                                           void* const* peer_flags, uint64_t epoch, int64_t cap_rows, int64_t* counts, int32_t* err,
+                                           int64_t* total_dev, int64_t* total_host, int32_t max_blocks, void* cuda_stream) {
+  if (!c || !keys || !vnode_to_dest || !peer_bases || !peer_flags || !counts || !err || !total_dev) return fail(RW_ERR_INVALID, "null");
+  if (n_dest < 1 || n_dest > PART_MAX_DEST || my_rank < 0 || my_rank >= n_dest) return fail(RW_ERR_INVALID, "ranks");
+  if (epoch == 0) return fail(RW_ERR_INVALID, "epochs start at 1");
+  for (int k = 0; k < c->n_cols; k++)
+    if (c->columns[k].validity) return fail(RW_ERR_UNSUPPORTED, "the peer-memory exchange does not carry validity bitmaps");
+  VnodePlan p;
+  int rc = make_vnode_plan(c, keys, n_keys, vnode_count, &p);
+  if (rc != RW_OK) return rc;
+  DevChunk ch;
+  rc = devchunk_from_abi(c, &ch);
+  if (rc != RW_OK) return rc;
+  std::vector<int32_t> types(c->n_cols);
+  for (int k = 0; k < c->n_cols; k++) types[k] = c->columns[k].type;
+  FlatLayout L;
+  rc = flat_layout(types.data(), c->n_cols, cap_rows, &L);
+  if (rc != RW_OK) return rc;
+  PeerBases pb, pf;
+  memset(&pb, 0, sizeof(pb));
+  memset(&pf, 0, sizeof(pf));
+  for (int d = 0; d < n_dest; d++) { pb.base[d] = (uint8_t*)peer_bases[d]; pf.base[d] = (uint8_t*)peer_flags[d]; }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int n_vblocks = (int)std::max<int64_t>(1, (c->n_rows + PART_ROWS_PER_BLOCK - 1) / PART_ROWS_PER_BLOCK);
+  static int coresident = 0;
+  if (!coresident) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_exchange_kernel, PART_BLOCK, 0);
+    coresident = std::max(1, sms * std::max(1, std::min(per_sm, 4)));
+  }
+  int grid = std::min(n_vblocks, coresident);
+  if (max_blocks > 0) grid = std::min(grid, (int)max_blocks);
+  uint8_t* scratch = nullptr;
+  size_t dest_bytes = ((size_t)c->n_rows + 255) / 256 * 256;
+  size_t hist_bytes = (size_t)n_vblocks * n_dest * 4;
+  RW_CUDA(cudaMallocAsync((void**)&scratch, dest_bytes + hist_bytes + 256, st));
+  uint8_t* dest = scratch;
+  uint32_t* hist = (uint32_t*)(scratch + dest_bytes);
+  unsigned long long ep = epoch;
+  int* errp = (int*)err;
+  void* args[] = {(void*)&ch, (void*)&p, (void*)&vnode_to_dest, (void*)&n_dest, (void*)&my_rank, (void*)&L, (void*)&pb, (void*)&pf, (void*)&ep,
+                  (void*)&dest, (void*)&hist, (void*)&n_vblocks, (void*)&counts, (void*)&total_dev, (void*)&total_host, (void*)&errp};
+  RW_CUDA(cudaLaunchCooperativeKernel((const void*)flat_exchange_kernel, dim3(grid), dim3(PART_BLOCK), args, 0, st));
+  RW_CUDA(cudaFreeAsync(scratch, st));
   return RW_OK;
 }
 

@@ -341,6 +341,49 @@ class P2PExchangeCall:
                                                         _stream_ptr(stream)))
 
 
+def flat_layout(types: Sequence[int], cap_rows: int):
+    """rwgpu_shuffle_flat_layout -> (total bytes, ops offset, [column offsets]) of a flat receive buffer"""
+    t = (C.c_int32 * len(types))(*types)
+    total, ops_off = C.c_int64(), C.c_int64()
+    col_off = (C.c_int64 * max(1, len(types)))()
+    _check(_lib().rwgpu_shuffle_flat_layout(t, len(types), C.c_int64(cap_rows), C.byref(total), C.byref(ops_off), col_off))
+    return total.value, ops_off.value, [col_off[k] for k in range(len(types))]
+
+
+class FlatExchangeCall:
+    """Pre-built argument block of rwgpu_shuffle_exchange_flat_device for one receive-buffer parity (one ctypes call per
+    batch: partition, peer stores, both barriers and the row count are one cooperative kernel)."""
+
+    def __init__(self, key_indices, vnode_to_dest, n_dest, my_rank, peer_ptrs, flag_ptrs, cap_rows, counts, err, total_dev_ptr,
+                 total_host, vnode_count=256, max_blocks=0):
+        self.keys = (C.c_int32 * len(key_indices))(*key_indices)
+        self.n_keys = len(key_indices)
+        self.peers = (C.c_void_p * n_dest)(*peer_ptrs)
+        self.flags = (C.c_void_p * n_dest)(*flag_ptrs)
+        self.args = (vnode_count, C.c_void_p(vnode_to_dest.data_ptr()), n_dest, my_rank)
+        self.cap_rows = cap_rows
+        self.counts, self.err = C.c_void_p(counts.data_ptr()), C.c_void_p(err.data_ptr())
+        self.total_dev = C.c_void_p(total_dev_ptr)
+        self.total_host = C.c_void_p(total_host.data_ptr()) if total_host is not None else None
+        self.max_blocks = max_blocks
+        self.keep = (vnode_to_dest, counts, err, total_host)
+        lib = _lib()
+        if not getattr(lib, "_flat_sig", False):
+            lib.rwgpu_shuffle_exchange_flat_device.restype = C.c_int32
+            lib.rwgpu_shuffle_exchange_flat_device.argtypes = [
+                C.POINTER(abi.RwChunk), C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                C.c_int32, C.c_void_p]
+            lib._flat_sig = True
+
+    def __call__(self, chunk: DeviceChunk, epoch: int, stream):
+        ch, keep = chunk.to_abi()
+        vc, v2d, n_dest, my_rank = self.args
+        _check(_lib().rwgpu_shuffle_exchange_flat_device(C.byref(ch), self.keys, self.n_keys, vc, v2d, n_dest, my_rank, self.peers, self.flags,
+                                                         C.c_uint64(epoch), C.c_int64(self.cap_rows), self.counts, self.err, self.total_dev,
+                                                         self.total_host, self.max_blocks, _stream_ptr(stream)))
+
+
 def project_device(chunk: DeviceChunk, exprs, ret_types: Sequence[int], stream: Optional[torch.cuda.Stream] = None):
     """rwgpu_project_device: `exprs` = (abi.RwProjectExpr * m) postfix programs over the chunk's columns.
     -> (columns, valid bytes, has_null uint32[m]) as CUDA tensors (ops / visibility of the chunk pass through)."""

@@ -182,3 +182,88 @@ class P2PShufflePlan:
 
     def exchange(self, chunk, stream=None):
         return self.finish(self.start(chunk, stream))
+
+
+class FlatShufflePlan:
+    """The N-GPU hash shuffle as ONE cooperative kernel per batch (rwgpu_shuffle_exchange_flat_device): histograms,
+    scan, count exchange, cross-rank barrier, scatter over NVLink straight into the rows' FINAL place in the
+    destination's receive buffer, second barrier, row count -- no NCCL call, no unpack copy; the consumer (the join's
+    counted push) reads the receive buffer in place and the row count on the device.
+
+    Two symmetric receive buffers alternate.  Caller contract (rwgpu.h): `start` of batch e is enqueued after the local
+    consumer of batch e - 2 has finished (e.g. `stream.wait_event(join_done[e - 2])`).  A buffer holds world x batch_rows
+    rows, so no distribution of keys can overflow it.  Columns with validity bitmaps are not carried (ValueError)."""
+
+    def __init__(self, world: int, rank: int, key_indices: Sequence[int], types: Sequence[int], batch_rows: int,
+                 group=None, vnode_count: int = 256, max_blocks: int = 0):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import abi, device
+        self.world, self.rank = world, rank
+        self.keys, self.types, self.vnode_count = list(key_indices), list(types), vnode_count
+        self.v2d = vnode_to_dest_table(world, vnode_count).cuda()
+        self.batch_rows = int(batch_rows)
+        self.max_rows = world * self.batch_rows
+        total, ops_off, col_off = device.flat_layout(self.types, self.max_rows)
+        group = group if group is not None else dist.group.WORLD
+        self.bufs, self.hdls, self.out = [], [], []
+        self.flags = symm_mem.empty(1024, dtype=torch.uint8, device="cuda")
+        self.flags.zero_()
+        self.flags_hdl = symm_mem.rendezvous(self.flags, group)
+        flag_ptrs = [int(self.flags_hdl.buffer_ptrs[r]) for r in range(world)]
+        self.counts = torch.zeros(world, dtype=torch.int64, device="cuda")
+        self.err = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self.totals_dev = torch.zeros(2, dtype=torch.int64, device="cuda")
+        self.totals_host, self.events, self.calls = [], [], []
+        for b in range(2):
+            buf = symm_mem.empty(total, dtype=torch.uint8, device="cuda")
+            buf.zero_()
+            h = symm_mem.rendezvous(buf, group)
+            self.bufs.append(buf)
+            self.hdls.append(h)
+            peers = [int(h.buffer_ptrs[r]) for r in range(world)]
+            ops = buf[ops_off:ops_off + self.max_rows]
+            cols = [buf[o:o + self.max_rows * abi.TYPE_WIDTH[t]].view(device.TORCH_DTYPE[t]) for o, t in zip(col_off, self.types)]
+            self.out.append((ops, cols))
+            self.totals_host.append(torch.zeros(1, dtype=torch.int64).pin_memory())
+            self.events.append(torch.cuda.Event())
+            self.calls.append(device.FlatExchangeCall(self.keys, self.v2d, world, rank, peers, flag_ptrs, self.max_rows, self.counts, self.err,
+                                                      self.totals_dev.data_ptr() + 8 * b, self.totals_host[b], vnode_count, max_blocks))
+        self.step = 0
+        torch.cuda.synchronize()
+        self.flags_hdl.barrier(channel=0)  # every rank's flags and headers are zero before anybody signals
+        torch.cuda.synchronize()
+
+    def start(self, chunk, stream=None):
+        """enqueue one batch on `stream` (one launch); -> token"""
+        if chunk.n_rows() > self.batch_rows:
+            raise ValueError(f"batch of {chunk.n_rows()} rows exceeds the plan's batch_rows {self.batch_rows}")
+        if chunk.visibility is not None or any(v is not None for v in chunk.validity):
+            raise ValueError("the exchange does not carry validity / visibility bitmaps (fold visibility into ops; NULLs are unsupported)")
+        b = self.step & 1
+        self.step += 1
+        stream = stream if stream is not None else torch.cuda.current_stream()
+        self.calls[b](chunk, self.step, stream)
+        self.events[b].record(stream)
+        return b
+
+    def count_ptr(self, b) -> int:
+        """device address of the int64 row count of token `b`"""
+        return self.totals_dev.data_ptr() + 8 * b
+
+    def output(self, b):
+        """(ops, cols) views of the WHOLE receive buffer of token `b` (capacity world x batch_rows); the first
+        `count` rows are the batch"""
+        return self.out[b]
+
+    def finish(self, b):
+        """wait for token `b`; -> (ops, cols) views of the received rows (valid until the second `start` after it)"""
+        self.events[b].synchronize()
+        n = int(self.totals_host[b][0])
+        if n < 0:
+            raise RuntimeError(f"flat shuffle failed on the device (err bits {int(self.err.item())}: 1 = receive buffer too small, "
+                               "2 = a peer did not reach the barrier)")
+        ops, cols = self.out[b]
+        return ops[:n], [c[:n] for c in cols]
+
+    def exchange(self, chunk, stream=None):
+        return self.finish(self.start(chunk, stream))

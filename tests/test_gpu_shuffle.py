@@ -247,8 +247,9 @@ def _two_gpu_worker(rank, world, port, q):
         n = 50000
         rng = np.random.default_rng(100 + rank)
         res = {}
-        for name in ("p2p", "nccl"):
-            plan = exchange.P2PShufflePlan(world, rank, [0], types, batch_rows=n) if name == "p2p" else exchange.ShufflePlan(world, rank, [0], types)
+        for name in ("flat", "p2p", "nccl"):
+            plan = (exchange.FlatShufflePlan(world, rank, [0], types, batch_rows=n) if name == "flat" else
+                    exchange.P2PShufflePlan(world, rank, [0], types, batch_rows=n) if name == "p2p" else exchange.ShufflePlan(world, rank, [0], types))
             out = []
             for step in range(3):
                 key = rng.integers(0, 1 << 40, n).astype(np.int64)
@@ -267,7 +268,8 @@ def _two_gpu_worker(rank, world, port, q):
 
 
 def test_p2p_exchange_two_gpus_matches_numpy_and_nccl(cuda, oracle):
-    """two real ranks: the peer-memory exchange (P2PShufflePlan) and the NCCL all-to-all-v path (ShufflePlan) both deliver
+    """two real ranks: the one-kernel exchange (FlatShufflePlan, bench.py's default at N>1), the region exchange
+    (P2PShufflePlan) and the NCCL all-to-all-v path (ShufflePlan) all deliver
     exactly the rows numpy's stable partition assigns to each rank, sources in rank order -- including a batch whose
     rows ALL go to one destination (regions are sized for that)."""
     import torch
@@ -283,7 +285,7 @@ def test_p2p_exchange_two_gpus_matches_numpy_and_nccl(cuda, oracle):
     got = dict(q.get(timeout=300) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
-    for name in ("p2p", "nccl"):
+    for name in ("flat", "p2p", "nccl"):
         for step in range(3):
             for d in range(world):
                 w_pay = []
@@ -294,3 +296,130 @@ def test_p2p_exchange_two_gpus_matches_numpy_and_nccl(cuda, oracle):
                 w_pay = np.concatenate(w_pay)
                 _, _, ops, cols = got[d][name][step]
                 assert len(ops) == len(w_pay) and np.array_equal(cols[1], w_pay), (name, step, d)
+
+
+def _flat_setup(world, types, cap):
+    import torch
+    from risingwave_b200 import device
+    total, ops_off, col_off = device.flat_layout(types, cap)
+    bufs = [torch.zeros(total, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    flags = [torch.zeros(1024, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    views = []
+    for b in bufs:
+        ops = b[ops_off:ops_off + cap]
+        cols = [b[o:o + cap * abi.TYPE_WIDTH[t]].view(device.TORCH_DTYPE[t]) for o, t in zip(col_off, types)]
+        views.append((ops, cols))
+    return bufs, flags, views
+
+
+def test_flat_exchange_self_peer_feeds_counted_join(cuda, oracle):
+    """world = 1 through the ONE-KERNEL exchange (rwgpu_shuffle_exchange_flat_device) into the counted join push, row count
+    read on the device, the join reading the receive buffer IN PLACE -- the chain bench.py times at N>1 -- vs the oracle."""
+    import torch
+    from collections import Counter
+    from risingwave_b200 import device, exchange
+    from risingwave_b200.executor import HashJoinExecutor, JoinParams, MockSource
+    from risingwave_b200.stream_chunk import net_multiset
+    rng = np.random.default_rng(12)
+    types = [abi.T_INT64] * 4
+    nb, n, cap = 3000, 20000, 20000
+    exs = []
+    for be in (cuda, oracle):
+        _, sl = MockSource.channel()
+        _, sr = MockSource.channel()
+        exs.append(HashJoinExecutor(be, abi.JOIN_INNER, sl.into_executor(types, [1]), sr.into_executor(types, [0]),
+                                    JoinParams([0], [1]), JoinParams([0], []), [False], capacity_hint=nb))
+    auct = [np.arange(nb, dtype=np.int64)] + [rng.integers(0, 1000, nb).astype(np.int64) for _ in range(3)]
+    a_ops = np.full(nb, abi.OP_INSERT, np.uint8)
+    for ex in exs:
+        assert ex.eq_join_oneside(1, StreamChunk(a_ops, [Column(abi.T_INT64, c) for c in auct])) == []
+    bufs, flags, views = _flat_setup(1, types, cap)
+    counts = torch.zeros(1, dtype=torch.int64, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    total_dev = torch.zeros(1, dtype=torch.int64, device="cuda")
+    total_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+    call = device.FlatExchangeCall([0], exchange.vnode_to_dest_table(1).cuda(), 1, 0, [bufs[0].data_ptr()], [flags[0].data_ptr()], cap,
+                                   counts, err, total_dev.data_ptr(), total_host)
+    stream = torch.cuda.Stream()
+    for epoch in (1, 2, 3):
+        m = n - 1000 * epoch
+        bid = [rng.integers(0, nb + 200, m).astype(np.int64), (np.arange(m) + 10 ** 6 * epoch).astype(np.int64),
+               rng.integers(0, 1 << 30, m).astype(np.int64), rng.integers(0, 1 << 30, m).astype(np.int64)]
+        ops = np.full(m, abi.OP_INSERT, np.uint8)
+        ops[rng.integers(0, m, 40)] = 0
+        chunk = device.DeviceChunk(torch.from_numpy(ops).cuda(), [torch.from_numpy(c).cuda() for c in bid], types)
+        with torch.cuda.stream(stream):
+            call(chunk, epoch, stream)
+            view = device.join_push_device(exs[0], abi.SIDE_LEFT, device.DeviceChunk(views[0][0], views[0][1], types), stream,
+                                           n_rows_dev=total_dev.data_ptr())
+            stream.synchronize()
+        keep = ops != 0
+        assert int(err.item()) == 0 and int(total_host.item()) == int(keep.sum()) == int(total_dev.item())
+        # the receive buffer holds the visible rows in input order
+        assert np.array_equal(views[0][1][1][:int(keep.sum())].cpu().numpy(), bid[1][keep])
+        vis = view.visible()
+        go, gc = view.ops().cpu().numpy(), [view.column(k).cpu().numpy() for k in range(view.n_cols)]
+        if vis is not None:
+            v = vis.cpu().numpy()
+            go, gc = go[v], [c[v] for c in gc]
+        got = Counter()
+        for i in range(len(go)):
+            got[tuple(int(c[i]) for c in gc)] += 1 if go[i] in (abi.OP_INSERT, abi.OP_UPDATE_INSERT) else -1
+        want = net_multiset(exs[1].eq_join_oneside(0, StreamChunk(ops[keep], [Column(abi.T_INT64, c[keep]) for c in bid])))
+        assert {k: v for k, v in got.items() if v} == dict(want), f"epoch {epoch}"
+
+
+def test_flat_exchange_virtual_ranks(cuda, oracle):
+    """flat_exchange_kernel with W virtual ranks on ONE device, one stream per rank, the W cooperative kernels running side
+    by side (grids capped so they are co-resident) and meeting in the kernel's own cross-rank barriers: every receive buffer
+    must hold the numpy stable partition, sources concatenated in rank order, with no gaps.  Two batches, so the second
+    one reuses the flags with larger barrier values."""
+    import torch
+    from risingwave_b200 import device, exchange
+    rng = np.random.default_rng(21)
+    types = [abi.T_INT64, abi.T_INT64, abi.T_INT32]
+    for world, n in ((2, 70001), (4, 9000)):
+        cap = world * n
+        bufs, flags, views = _flat_setup(world, types, cap)
+        v2d = exchange.vnode_to_dest_table(world).cuda()
+        peers, flag_ptrs = [b.data_ptr() for b in bufs], [f.data_ptr() for f in flags]
+        streams = [torch.cuda.Stream() for _ in range(world)]
+        state = [dict(counts=torch.zeros(world, dtype=torch.int64, device="cuda"), err=torch.zeros(1, dtype=torch.int32, device="cuda"),
+                      total=torch.zeros(1, dtype=torch.int64, device="cuda")) for _ in range(world)]
+        calls = [device.FlatExchangeCall([0], v2d, world, r, peers, flag_ptrs, cap, state[r]["counts"], state[r]["err"],
+                                         state[r]["total"].data_ptr(), None, max_blocks=24) for r in range(world)]
+        for epoch in (1, 2):
+            src, chunks = [], []
+            for r in range(world):
+                key = rng.integers(0, 100000, n).astype(np.int64)
+                if epoch == 2 and r == 0:
+                    key[:] = 5  # one source sends everything to one destination
+                pay = np.arange(n, dtype=np.int64) + r * 10 ** 9 + epoch * 10 ** 7
+                small = rng.integers(0, 100, n).astype(np.int32)
+                ops = rng.integers(1, 5, n).astype(np.uint8)
+                ops[rng.random(n) < 0.05] = 0
+                src.append((ops, [key, pay, small]))
+                chunks.append(device.DeviceChunk(torch.from_numpy(ops).cuda(), [torch.from_numpy(c).cuda() for c in (key, pay, small)], types))
+            torch.cuda.synchronize()
+            for r in range(world):
+                calls[r](chunks[r], epoch, streams[r])
+            torch.cuda.synchronize()
+            errs = [int(state[r]["err"].item()) for r in range(world)]
+            if any(e & 2 for e in errs):
+                pytest.skip("this device did not run the ranks' cooperative kernels side by side (barrier timed out)")
+            assert errs == [0] * world
+            for d in range(world):
+                w_ops, w_cols = [], [[] for _ in types]
+                for r in range(world):
+                    ops, cols = src[r]
+                    ix = _expected_partition(oracle, ops, [cols[0]], world)[d]
+                    assert int(state[r]["counts"][d].item()) == len(ix)
+                    w_ops.append(ops[ix])
+                    for k in range(len(types)):
+                        w_cols[k].append(cols[k][ix])
+                w_ops = np.concatenate(w_ops)
+                m = int(state[d]["total"].item())
+                assert m == len(w_ops)
+                assert np.array_equal(views[d][0][:m].cpu().numpy(), w_ops)
+                for k in range(len(types)):
+                    assert np.array_equal(views[d][1][k][:m].cpu().numpy(), np.concatenate(w_cols[k]))
