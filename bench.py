@@ -510,14 +510,25 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         auct_dev = to_dev(auct)
 
+        build_first_ms = [0.0]
+
         def build(join, shuffle=True):
+            """-> seconds per build row, measured over the pushes AFTER the first one (the first push allocates the handle's
+            output set and scratch -- tens of milliseconds of cudaMalloc, reported separately)"""
             torch.cuda.synchronize()
             t0 = time.perf_counter()
+            t1, rows_timed = t0, 0
             for i in range(0, N_BUILD, BATCH):
                 part = [c[i:i + BATCH] for c in auct_dev]
                 device.join_push_device(join, abi.SIDE_RIGHT, shuffled(part) if shuffle else dchunk(part), stream)
+                if i == 0:
+                    torch.cuda.synchronize()
+                    t1 = time.perf_counter()
+                    build_first_ms[0] = 1e3 * (t1 - t0)
+                else:
+                    rows_timed += part[0].numel()
             torch.cuda.synchronize()
-            return time.perf_counter() - t0
+            return (time.perf_counter() - t1) / max(rows_timed, 1)
 
         # ================================================================ leg: value (device-resident)
         if "value" in legs:
@@ -643,7 +654,7 @@ def run_ours(args):
                                   "l2": "inputs_larger_than_l2 (fresh 32 MiB batch per step; >1.3 GB of join state)",
                                   "exchange": None if world == 1 else ex_name},
                 "host_ms_per_step": {"enqueue_exchange": 1e3 * t_ex / K, "join_launch_and_collect": 1e3 * t_join / K},
-                "build_rows_per_s": N_BUILD * world / build_s, "out_rows": out_rows, "gpu_launches": int(launches), "clocks": clocks,
+                "build_rows_per_s": world / build_s, "build_first_push_ms": build_first_ms[0], "out_rows": out_rows, "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": {"bound": "hbm", "kernel": "uni_hot_kernel<false,false,4> (unified bucket: probe + emit + own-side append, 4 lanes per row)",
                              "achieved": fused_gbs, "peak": peak, "unit": "GB/s", "frac": fused_gbs / peak if fused_gbs else None,
                              "traffic": ncu_traffic("uni_hot_kernel"), "traffic_unit": "bytes per launch (ncu dram read+write)",
@@ -796,17 +807,29 @@ def run_ours(args):
             torch.cuda.empty_cache()
             if world > 1:
                 dist.barrier()  # the callers of all ranks start together
-            r = subprocess.run([exe, str(N_BUILD), str(BATCH), str(K), str(W)], capture_output=True, text=True, env=env, timeout=900)
-            if r.returncode != 0:
-                raise RuntimeError(f"e2e_caller failed: {r.stderr[-500:]}")
-            j = json.loads(r.stdout.strip().splitlines()[-1])
+            def run_caller(mode):
+                r = subprocess.run([exe, str(N_BUILD), str(BATCH), str(K), str(W), mode], capture_output=True, text=True, env=env, timeout=900)
+                if r.returncode != 0:
+                    raise RuntimeError(f"e2e_caller ({mode}) failed: {r.stderr[-500:]}")
+                return json.loads(r.stdout.strip().splitlines()[-1])
+
+            j = run_caller("async")
+            js = run_caller("sync") if world == 1 else None
             al = int(j["output_columns_aliasing_input"])
-            return {"value": j["value"], "unit": "rows/s", "h2d_bytes_per_step": BATCH * (4 * 8 + 1),
-                    "d2h_bytes_per_step": int(j["out_rows"]) * (8 * (8 - al) + 1) // K, "ffi_batch_rows": BATCH, "ms_per_step": j["ms_per_step"],
-                    "output_columns_aliasing_input": al, "chunk_views_read_per_step": j["chunk_views_read_per_step"],
-                    "note": "compiled caller (tools/e2e_caller.cc): pinned host StreamChunk buffers -> rwgpu_join_push -> every one of the "
-                            "output chunk views fetched and read -> rwgpu_out_release; the bid-side output columns alias the caller's input "
-                            "buffers (rwgpu.h), the rest is read back over PCIe"}
+            res = {"value": j["value"], "unit": "rows/s", "h2d_bytes_per_step": BATCH * (4 * 8 + 1),
+                   "d2h_bytes_per_step": int(j["out_rows"]) * (8 * (8 - al) + 1) // K, "ffi_batch_rows": BATCH, "ms_per_step": j["ms_per_step"],
+                   "output_columns_aliasing_input": al, "chunk_views_read_per_step": j["chunk_views_read_per_step"],
+                   "verified": bool(j.get("verified")), "verification": {"rows": j.get("verify_rows"), "checksum": j.get("verify_checksum"),
+                                                                          "how": "one more step after the timed ones, every output row read by the "
+                                                                                 "caller and compared with the join evaluated on the host"},
+                   "note": "compiled caller (tools/e2e_caller.cc) = what the executor shim does per message: pinned host StreamChunk buffers -> "
+                           "rwgpu_join_push_async (step s+1 launched before step s is collected) -> rwgpu_join_collect_out -> every one of the "
+                           "output chunk views fetched and read -> rwgpu_out_release; the bid-side output columns alias the caller's input "
+                           "buffers (rwgpu.h), the rest is read back over PCIe"}
+            if js is not None:
+                res["one_call_at_a_time"] = {"value": js["value"], "ms_per_step": js["ms_per_step"], "verified": bool(js.get("verified")),
+                                             "note": "the same caller through the synchronous rwgpu_join_push (H2D / kernels / D2H overlap inside a call only)"}
+            return res
 
         if "e2e" in legs:
             res, ok = None, 1.0

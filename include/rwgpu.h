@@ -278,6 +278,19 @@ int32_t rwgpu_join_push_device_counted(rwgpu_join* h, int32_t side, const rw_chu
 int32_t rwgpu_join_push_device_async(rwgpu_join* h, int32_t side, const rw_chunk* chunk, const int64_t* n_rows_dev,
                                      void* cuda_stream);
 int32_t rwgpu_join_collect(rwgpu_join* h, rw_chunk* view, void* cuda_stream);
+/* The same split for HOST chunks -- what the executor shim uses per message: the launch
+ * enqueues the input's H2D copy, the push, and the D2H copy of the positional output rows (one per input row: the
+ * common case) on three streams and returns; while the caller launches the NEXT chunk (its input travels host -> device)
+ * this chunk's output travels device -> host, so both PCIe directions stay busy across calls (rwgpu_join_push overlaps
+ * them only inside one call).  `rwgpu_join_collect_out` waits for the OLDEST outstanding push, copies what the status
+ * block says is still missing (extra matches, NULL / visibility bytes) and returns the rwgpu_out (release it as usual).
+ * Rules as above (two outstanding, one side, errors at collect), and
+ *  - the chunk's HOST buffers stay valid and unmodified until the push is collected -- and, when output columns alias
+ *    them (see rwgpu_join_push), until the rwgpu_out is released;
+ *  - device-chunk and host-chunk pushes each have their own collect call; collect them in launch order.
+ * Plan shapes without an asynchronous kernel path (and chunks with varlen payload) complete inside the launch.  */
+int32_t rwgpu_join_push_async(rwgpu_join* h, int32_t side, const rw_chunk* chunk);
+int32_t rwgpu_join_collect_out(rwgpu_join* h, rwgpu_out** out);
 int32_t rwgpu_join_barrier(rwgpu_join* h, uint64_t epoch);
 int32_t rwgpu_join_stats(rwgpu_join* h, uint64_t* left_rows, uint64_t* right_rows,
                          uint64_t* kernel_launches);

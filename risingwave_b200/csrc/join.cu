@@ -1808,6 +1808,20 @@ struct rwgpu_join {
   // host staging
   DevBuf up;
   PinnedBuf up_host;
+  // launch / collect split for HOST chunks (rwgpu_join_push_async / rwgpu_join_collect_out): per output set, the device
+  // staging of the input, the pinned output block and what collect still has to copy
+  struct HostPending {
+    bool active = false, sync_done = false;
+    rwgpu_out* out = nullptr;      // sync_done: the finished result; else the block the copies land in
+    rw_chunk in;                   // the caller's chunk (its buffers stay valid until collect: rwgpu.h)
+    std::vector<rw_column> in_cols;
+    std::vector<int> alias_src;
+    int64_t n = 0, host_cap = 0;
+    bool alias_ok = false;
+  } hpend[2];
+  DevBuf up2[2];
+  PinnedBuf up2_host[2];
+  cudaEvent_t ev_up2[2] = {nullptr, nullptr};
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
   std::vector<rw_column> dev_view_cols[2];  // per output set
   DevBuf noop_nxt, noop_prv, noop_elig, noop_flag;  // eliminate_adjacent_noop_update scratch
@@ -2794,7 +2808,8 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
 
 void rwgpu_join_destroy(rwgpu_join* h) {
   if (!h) return;
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaDeviceSynchronize();  // pushes may be outstanding on the handle's or a caller's stream
+  for (int i = 0; i < 2; i++) delete h->hpend[i].out;
   delete h;
 }
 
@@ -3017,6 +3032,7 @@ int32_t rwgpu_join_collect(rwgpu_join* h, rw_chunk* view, void* cuda_stream) {
   if (!h || !view) return fail(RW_ERR_INVALID, "null");
   if (h->n_pending == 0) return fail(RW_ERR_INVALID, "no push outstanding");
   const JoinPending pd = h->pending[0];
+  if (h->hpend[pd.set].active) return fail(RW_ERR_INVALID, "the oldest outstanding push was launched with a host chunk: use rwgpu_join_collect_out");
   h->pending[0] = h->pending[1];
   h->n_pending--;
   h->cur = pd.set;
@@ -3252,6 +3268,210 @@ int32_t rwgpu_join_push(rwgpu_join* h, int32_t side, const rw_chunk* c, rwgpu_ou
   if (trace)
     fprintf(stderr, "[rwgpu_join_push] n=%lld out=%lld J=%d  h2d-enqueue %.3f  layout %.3f  sub-batches %.3f  drain %.3f  finalize %.3f  total %.3f ms\n",
             (long long)n, (long long)total, n_sub, t1 - t0, t2 - t1, t3 - t2, t4 - t3, now() - t4, now() - t0);
+  *out = guard.release();
+  return RW_OK;
+}
+
+// ---- launch / collect split for HOST chunks.  rwgpu_join_push handles one chunk per call and returns when its output
+// sits in host memory: H2D, kernels and D2H of ONE call overlap (sub-batches), consecutive calls do not.  Here the call
+// only ENQUEUES: input H2D on the copy-in stream, the push on the main stream, and -- the common case being one output
+// row per input row -- the D2H of the positional rows on the copy-out stream.  While the caller launches chunk s+1
+// (its H2D uses the other PCIe direction), chunk s's output streams back; collect waits, copies what the status block
+// says is still missing (extra matches, NULL / visibility bytes) and cuts the chunk views.
+int32_t rwgpu_join_push_async(rwgpu_join* h, int32_t side, const rw_chunk* c) {
+  if (!h || !c) return fail(RW_ERR_INVALID, "null");
+  if (side != 0 && side != 1) return fail(RW_ERR_INVALID, "side");
+  if (c->n_cols != h->side[side].n_cols) return fail(RW_ERR_INVALID, "chunk schema mismatch");
+  for (int k = 0; k < c->n_cols; k++)
+    if (c->columns[k].type != h->side[side].types[k]) return fail(RW_ERR_INVALID, "chunk column type mismatch");
+  if (h->n_pending >= 2) return fail(RW_ERR_INVALID, "two pushes are already outstanding: collect one first");
+  if (h->n_pending && h->pending[0].S != side)
+    return fail(RW_ERR_INVALID, "pushes of different sides cannot be outstanding together: collect first");
+  const int64_t n = c->n_rows;
+  const int set = h->n_pending ? 1 - h->pending[h->n_pending - 1].set : h->cur;
+  rwgpu_join::HostPending& hp = h->hpend[set];
+  if (hp.active) return fail(RW_ERR_INVALID, "output set still holds an uncollected host push");
+  hp = rwgpu_join::HostPending();
+  hp.active = true;
+  hp.n = n;
+  hp.in = *c;
+  hp.in_cols.assign(c->columns, c->columns + c->n_cols);
+  hp.in.columns = hp.in_cols.data();
+  JoinPending pd;
+  pd.S = side;
+  pd.set = set;
+  pd.st = h->stream;
+  bool simple = h->uni && n > 0 && n < (1ll << 31) && h->var_in[side].empty() && h->var_out.empty();
+  if (!simple) {
+    // other plan shapes / varlen payload / empty chunks: run the synchronous call now, hand the result over at collect
+    if (h->n_pending) return fail(RW_ERR_INVALID, "this join shape runs its pushes synchronously: collect the outstanding push first");
+    hp.active = false;
+    rwgpu_out* o = nullptr;
+    int rc = rwgpu_join_push(h, side, c, &o);
+    if (rc != RW_OK) return rc;
+    hp.active = true;
+    hp.sync_done = true;
+    hp.out = o;
+    pd.sync_done = true;  // (nothing is outstanding: `set` is the current set)
+    h->pending[h->n_pending++] = pd;
+    return RW_OK;
+  }
+  if (!h->s_h2d) {
+    RW_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    RW_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) {
+      RW_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+      RW_CUDA(cudaEventCreateWithFlags(&h->ev_main[i], cudaEventDisableTiming));
+    }
+  }
+  if (!h->ev_up2[set]) RW_CUDA(cudaEventCreateWithFlags(&h->ev_up2[set], cudaEventDisableTiming));
+  // ---- input: device staging of this set
+  const size_t nw = (size_t)((n + 63) / 64) * 8;
+  size_t off = 0;
+  auto region = [&](size_t bytes) { size_t o = align_up_j(off, 256); off = o + bytes; return o; };
+  const size_t o_ops = region((size_t)n), o_vis = region(nw);
+  size_t o_data[RW_MAX_COLS], o_valid[RW_MAX_COLS];
+  for (int k = 0; k < c->n_cols; k++) {
+    o_data[k] = region((size_t)n * type_width(c->columns[k].type));
+    o_valid[k] = region(nw);
+  }
+  if (off + 256 > h->up2[set].bytes) {
+    RW_CUDA(cudaDeviceSynchronize());  // (growth only)
+    RW_CUDA(h->up2[set].reserve(off + off / 4 + 256));
+    RW_CUDA(h->up2_host[set].reserve(off + off / 4 + 256));
+  }
+  uint8_t* hs = h->up2_host[set].as<uint8_t>();
+  uint8_t* dp = h->up2[set].as<uint8_t>();
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  // (the copy-in stream is ordered behind the kernels that read this staging two pushes ago: that push was collected)
+  auto h2d = [&](size_t dst_off, const void* src, size_t bytes, bool pinned) {
+    if (!bytes) return;
+    if (pinned || bytes >= (1u << 20)) cudaMemcpyAsync(dp + dst_off, src, bytes, cudaMemcpyHostToDevice, h->s_h2d);
+    else { memcpy(hs + dst_off, src, bytes); cudaMemcpyAsync(dp + dst_off, hs + dst_off, bytes, cudaMemcpyHostToDevice, h->s_h2d); }
+  };
+  h2d(o_ops, c->ops, (size_t)n, is_pinned(c->ops));
+  if (c->visibility) h2d(o_vis, c->visibility, nw, false);
+  for (int k = 0; k < c->n_cols; k++) {
+    h2d(o_data[k], c->columns[k].data, (size_t)n * type_width(c->columns[k].type), is_pinned(c->columns[k].data));
+    if (c->columns[k].validity) h2d(o_valid[k], c->columns[k].validity, nw, false);
+  }
+  RW_CUDA(cudaEventRecord(h->ev_up2[set], h->s_h2d));
+  RW_CUDA(cudaGetLastError());
+  DevChunk ch;
+  memset(&ch, 0, sizeof(ch));
+  ch.n = n;
+  ch.n_cols = c->n_cols;
+  ch.ops = dp + o_ops;
+  ch.vis_bits = c->visibility ? (const uint64_t*)(dp + o_vis) : nullptr;
+  for (int k = 0; k < c->n_cols; k++) {
+    ch.cols[k].type = c->columns[k].type;
+    ch.cols[k].width = type_width(c->columns[k].type);
+    ch.cols[k].data = dp + o_data[k];
+    ch.cols[k].valid_bits = c->columns[k].validity ? (const uint64_t*)(dp + o_valid[k]) : nullptr;
+  }
+  // ---- the push
+  h->cur = set;
+  int rc = join_begin_call(h, h->stream);
+  if (rc != RW_OK) { hp.active = false; return rc; }
+  RW_CUDA(cudaStreamWaitEvent(h->stream, h->ev_up2[set], 0));
+  rc = uni_enqueue(h, side, ch, h->stream, 0, &pd);
+  if (rc != RW_OK) { hp.active = false; return rc; }
+  // ---- output block + the copy-out of the positional rows
+  auto o = new rwgpu_out();
+  o->chunk_size = h->chunk_size;
+  hp.host_cap = std::max<int64_t>(2 * n, 1024);
+  if (!o->layout(hp.host_cap, h->out_types, ~0ull >> 1, true, h->pool)) { delete o; hp.active = false; return fail(RW_ERR_OOM, "pinned output block"); }
+  hp.out = o;
+  static const bool no_alias = getenv("RWGPU_NO_ALIAS") != nullptr;
+  hp.alias_ok = !no_alias && h->w8_ok[side] && !c->visibility;
+  for (int k = 0; k < c->n_cols && hp.alias_ok; k++) hp.alias_ok = c->columns[k].validity == nullptr;
+  hp.alias_src.assign(h->out_types.size(), -1);
+  if (hp.alias_ok)
+    for (int k = 0; k < c->n_cols; k++)
+      if (h->w8[side].u_out[k] >= 0) hp.alias_src[(size_t)h->w8[side].u_out[k]] = k;
+  RW_CUDA(cudaStreamWaitEvent(h->s_d2h, h->pend_ev[set], 0));
+  cudaMemcpyAsync(o->ops, h->os().out_ops.p, (size_t)n, cudaMemcpyDeviceToHost, h->s_d2h);
+  for (size_t k = 0; k < h->out_types.size(); k++) {
+    if (hp.alias_src[k] >= 0) continue;
+    const size_t w = type_width(h->out_types[k]);
+    cudaMemcpyAsync(o->data[k], h->os().out_col[k].p, (size_t)n * w, cudaMemcpyDeviceToHost, h->s_d2h);
+  }
+  RW_CUDA(cudaGetLastError());
+  h->pending[h->n_pending++] = pd;
+  return RW_OK;
+}
+
+int32_t rwgpu_join_collect_out(rwgpu_join* h, rwgpu_out** out) {
+  if (!h || !out) return fail(RW_ERR_INVALID, "null");
+  if (h->n_pending == 0) return fail(RW_ERR_INVALID, "no push outstanding");
+  const JoinPending pd = h->pending[0];
+  rwgpu_join::HostPending& hp = h->hpend[pd.set];
+  if (!hp.active) return fail(RW_ERR_INVALID, "the oldest outstanding push was launched with a device chunk: use rwgpu_join_collect");
+  h->pending[0] = h->pending[1];
+  h->n_pending--;
+  hp.active = false;
+  if (hp.sync_done) {
+    *out = hp.out;
+    hp.out = nullptr;
+    return RW_OK;
+  }
+  std::unique_ptr<rwgpu_out> guard(hp.out);
+  hp.out = nullptr;
+  rwgpu_out* o = guard.get();
+  h->cur = pd.set;
+  h->call_null_mask = 0;
+  h->call_had_deletes = false;
+  int64_t total = 0;
+  unsigned long long nullm = 0;
+  const uint8_t* ops_before = h->os().out_ops.as<uint8_t>();
+  auto bail = [&](int rc) { cudaStreamSynchronize(h->s_d2h); if (h->n_pending) h->cur = h->pending[h->n_pending - 1].set; return rc; };
+  int rc = uni_finish(h, pd, &total, &nullm);
+  if (rc != RW_OK) return bail(rc);
+  rc = join_post_process(h, total, &nullm, pd.st);
+  if (rc != RW_OK) return bail(rc);
+  const int64_t n = hp.n;
+  // what the launch already copied is good unless the emission was redone into re-allocated buffers
+  bool pre_ok = h->os().out_ops.as<uint8_t>() == ops_before && total >= n;
+  if (total > hp.host_cap) {  // rare: amplification above 2x -- a larger host block, everything is copied again
+    RW_CUDA(cudaStreamSynchronize(h->s_d2h));
+    auto o2 = new rwgpu_out();
+    o2->chunk_size = h->chunk_size;
+    if (!o2->layout(total + total / 4, h->out_types, ~0ull >> 1, true, h->pool)) { delete o2; return bail(fail(RW_ERR_OOM, "pinned output block")); }
+    guard.reset(o2);
+    o = o2;
+    pre_ok = false;
+  }
+  const bool aligned = total == n;  // exactly the positional rows: the update side's columns ARE the caller's input columns
+  if (total > 0) {
+    const int64_t from = pre_ok ? n : 0;  // rows [0, n) of the non-aliased columns are already on their way
+    const int64_t ops_from = h->call_had_deletes ? 0 : from;  // (the no-op elimination pass may have rewritten ops)
+    if (total > ops_from)
+      cudaMemcpyAsync(o->ops + ops_from, h->os().out_ops.as<uint8_t>() + ops_from, (size_t)(total - ops_from), cudaMemcpyDeviceToHost, h->s_d2h);
+    for (size_t k = 0; k < h->out_types.size(); k++) {
+      const size_t w = type_width(h->out_types[k]);
+      if (hp.alias_src[k] >= 0) {
+        if (aligned) o->data[k] = (uint8_t*)const_cast<void*>(hp.in_cols[(size_t)hp.alias_src[k]].data);  // zero-copy
+        else cudaMemcpyAsync(o->data[k], h->os().out_col[k].p, (size_t)total * w, cudaMemcpyDeviceToHost, h->s_d2h);
+      } else if (total > from) {
+        cudaMemcpyAsync(o->data[k] + (size_t)from * w, h->os().out_col[k].as<uint8_t>() + (size_t)from * w, (size_t)(total - from) * w,
+                        cudaMemcpyDeviceToHost, h->s_d2h);
+      }
+    }
+    if (nullm >> 63) cudaMemcpyAsync(o->vis_bytes, h->os().out_vis.p, (size_t)total, cudaMemcpyDeviceToHost, h->s_d2h);
+    for (size_t k = 0; k < h->out_types.size(); k++)
+      if ((nullm >> k) & 1) cudaMemcpyAsync(o->valid_bytes[k], h->os().out_valid[k].p, (size_t)total, cudaMemcpyDeviceToHost, h->s_d2h);
+  }
+  RW_CUDA(cudaStreamSynchronize(h->s_d2h));
+  o->n_rows = total;
+  if (!(nullm >> 63)) o->vis_bytes = nullptr;
+  for (size_t k = 0; k < h->out_types.size(); k++)
+    if (!((nullm >> k) & 1)) o->valid_bytes[k] = nullptr;
+  o->finalize();
+  if (h->n_pending) h->cur = h->pending[h->n_pending - 1].set;
   *out = guard.release();
   return RW_OK;
 }

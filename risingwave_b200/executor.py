@@ -421,6 +421,27 @@ class HashJoinExecutor:
         self.backend.check(self.backend._join_push(self._h, side, C.byref(ch), C.byref(out)))
         return self.backend.take_out(out)
 
+    # launch / collect split for host chunks (rwgpu.h rwgpu_join_push_async / rwgpu_join_collect_out; CUDA backend only)
+    def eq_join_oneside_launch(self, side: int, chunk: StreamChunk):
+        """enqueue the push of `chunk`; its buffers are kept alive here until `eq_join_oneside_collect` returns the output"""
+        fn = self.backend.lib.rwgpu_join_push_async
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(abi.RwChunk)]
+        ch, keep = chunk.to_abi()
+        self.backend.check(fn(self._h, side, C.byref(ch)))
+        if not hasattr(self, "_inflight"):
+            self._inflight = []
+        self._inflight.append((chunk, ch, keep))
+
+    def eq_join_oneside_collect(self) -> List[StreamChunk]:
+        """output of the OLDEST outstanding launch"""
+        fn = self.backend.lib.rwgpu_join_collect_out
+        fn.restype, fn.argtypes = C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)]
+        out = C.c_void_p()
+        self.backend.check(fn(self._h, C.byref(out)))
+        res = self.backend.take_out(out)  # (copies out of the rwgpu_out, which may alias the input buffers, then releases it)
+        self._inflight.pop(0)
+        return res
+
     def flush_data(self, epoch: int):
         self.backend.check(self.backend._join_barrier(self._h, epoch))
 

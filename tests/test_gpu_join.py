@@ -604,3 +604,91 @@ def test_varlen_key_or_pk_is_refused(cuda):
             HashJoinExecutor(cuda, abi.JOIN_INNER, sl.into_executor(types, [1]), sr.into_executor(types, [1]), JoinParams(keys, pk), JoinParams(keys, pk),
                              [False])
         assert e.value.code == abi.RW_ERR_UNSUPPORTED
+
+
+def test_host_async_pushes_match_synchronous(cuda, oracle):
+    """rwgpu_join_push_async / rwgpu_join_collect_out (host chunks, two outstanding): every collected output equals the
+    synchronous rwgpu_join_push on an identical handle and the oracle's net result -- inserts with 0 / 1 / many matches
+    (extra rows copied at collect), deletes (ops re-copied after the no-op pass), NULL payload (validity bytes), invisible
+    input rows, and an amplification above the 2x host block (re-laid at collect)."""
+    rng = np.random.default_rng(77)
+    types = [abi.T_INT64] * 4
+    nb = 5000
+
+    def make(be):
+        _, sl = MockSource.channel()
+        _, sr = MockSource.channel()
+        return HashJoinExecutor(be, abi.JOIN_INNER, sl.into_executor(types, [1]), sr.into_executor(types, [0]),
+                                JoinParams([0], [1]), JoinParams([0], []), [False], capacity_hint=1000)
+
+    a, b, o = make(cuda), make(cuda), make(oracle)
+    auct_cols = [np.arange(nb, dtype=np.int64)] + [rng.integers(0, 1000, nb).astype(np.int64) for _ in range(3)]
+    valid3 = rng.random(nb) > 0.1
+    auct = StreamChunk(np.full(nb, abi.OP_INSERT, np.uint8), [Column(abi.T_INT64, c) for c in auct_cols[:3]] + [Column(abi.T_INT64, auct_cols[3], valid3)])
+    for ex in (a, b, o):
+        assert ex.eq_join_oneside(1, auct) == []
+    pushes = []
+    stored = []
+    for s in range(7):
+        n = 20000 + 3000 * s
+        key = rng.integers(0, nb + 500, n).astype(np.int64)  # some bids match nothing
+        pk = (np.arange(n) + 10 ** 6 * s).astype(np.int64)
+        cols = [key, pk, rng.integers(0, 1 << 30, n).astype(np.int64), rng.integers(0, 1 << 30, n).astype(np.int64)]
+        ops = np.full(n, abi.OP_INSERT, np.uint8)
+        vis = None
+        if s == 3:  # retract rows of an earlier push
+            k0, p0, c2, c3 = stored[0]
+            cols = [k0[:5000], p0[:5000], c2[:5000], c3[:5000]]
+            ops = np.full(5000, abi.OP_DELETE, np.uint8)
+        elif s == 4:
+            vis = rng.random(n) > 0.2
+        else:
+            stored.append(cols)
+        pushes.append((0, StreamChunk(ops, [Column(abi.T_INT64, c) for c in cols], vis)))
+    # auction updates: every bid of the auction is emitted twice (extra-match rows; > 2x the input for the hot ones)
+    hot = np.repeat(np.arange(40, dtype=np.int64), 2)
+    upd_ops = np.tile(np.array([abi.OP_UPDATE_DELETE, abi.OP_UPDATE_INSERT], np.uint8), 40)
+    upd_cols = [hot] + [np.repeat(c[:40], 2) for c in auct_cols[1:]]
+    upd_cols[3] = upd_cols[3] + np.tile(np.array([0, 1], np.int64), 40)
+    hot_bids = StreamChunk(np.full(4000, abi.OP_INSERT, np.uint8),
+                           [Column(abi.T_INT64, rng.integers(0, 40, 4000).astype(np.int64)), Column(abi.T_INT64, np.arange(4000, dtype=np.int64) + 10 ** 9),
+                            Column(abi.T_INT64, np.zeros(4000, np.int64)), Column(abi.T_INT64, np.ones(4000, np.int64))])
+    pushes.append((0, hot_bids))
+    pushes.append((1, StreamChunk(upd_ops, [Column(abi.T_INT64, c) for c in upd_cols[:3]] + [Column(abi.T_INT64, upd_cols[3], np.repeat(valid3[:40], 2))])))
+
+    def rows_of(chunks):
+        return sorted((int(op), tuple(None if v is None else int(v) for v in row)) for ch in chunks for op, row in ch.rows())
+
+    want = [rows_of(a.eq_join_oneside(side, ch)) for side, ch in pushes]
+    want_net = [net_multiset(o.eq_join_oneside(side, ch)) for side, ch in pushes]
+    got = []
+    outstanding = []
+    for side, ch in pushes:
+        if outstanding and outstanding[-1] != side:  # pushes of different sides are never outstanding together
+            while outstanding:
+                got.append(rows_of(b.eq_join_oneside_collect()))
+                outstanding.pop(0)
+        b.eq_join_oneside_launch(side, ch)
+        outstanding.append(side)
+        if len(outstanding) == 2:
+            got.append(rows_of(b.eq_join_oneside_collect()))
+            outstanding.pop(0)
+    while outstanding:
+        got.append(rows_of(b.eq_join_oneside_collect()))
+        outstanding.pop(0)
+    assert len(got) == len(want)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert g == w, f"push {i}"
+    from collections import Counter
+    for i, g in enumerate(got):
+        net = Counter()
+        for op, row in g:
+            net[row] += 1 if op in (abi.OP_INSERT, abi.OP_UPDATE_INSERT) else -1
+        assert {k: v for k, v in net.items() if v} == {k: v for k, v in dict(want_net[i]).items() if v}, f"push {i} vs oracle"
+    # a third launch without a collect is refused; so is a device collect of a host launch
+    b.eq_join_oneside_launch(0, pushes[0][1])
+    b.eq_join_oneside_launch(0, pushes[1][1])
+    with pytest.raises(abi.RwError):
+        b.eq_join_oneside_launch(0, pushes[2][1])
+    b.eq_join_oneside_collect()
+    b.eq_join_oneside_collect()

@@ -17,7 +17,7 @@ N_BATCH = int(os.environ.get("DBG_NBATCH", 20))
 RP = int(os.environ.get("DBG_PAIRS", 1 << 17))
 STEPS = int(os.environ.get("DBG_STEPS", 3))
 T4 = [abi.T_INT64] * 4
-be = Backend.gpu()
+be = Backend.cuda()
 stream = torch.cuda.Stream()
 
 
