@@ -990,6 +990,73 @@ def run_ours(args):
                           "roofline": {"bound": "hbm", "kernel": "project_kernel", "achieved": pgbs, "peak": peak, "unit": "GB/s", "frac": pgbs / peak,
                                        "algorithmic_bytes_per_row": 17.0, "kernel_ms_avg": dev_ms, "traffic": None}}
 
+        # ================================================================ leg: generic (the path of the 7 non-inner join types)
+        if "generic" in legs and world == 1:
+            # LEFT OUTER bid x auction on the generic path (join_prepare_kernel -> cub scan + radix sort by (key group, row) ->
+            # join_serial_kernel: one thread per join key runs hash_join_utils' match loop literally, degrees included).
+            # 2^20 auctions resident; a step = 2^18 bids, 1/8 of them without a partner (NULL-padded output rows); then 2^18
+            # auction inserts, half of which find waiting bids (each flips its NULL row: U-/U+ ... here Delete + Insert pairs).
+            NG, BG, KG, WG = 1 << 20, 1 << 18, min(K, 8), 2
+            _, gl = MockSource.channel()
+            _, gr = MockSource.channel()
+            jg = HashJoinExecutor(be, abi.JOIN_LEFT_OUTER, gl.into_executor(T4, [1]), gr.into_executor(T4, [0]),
+                                  JoinParams([0], [1]), JoinParams([0], []), [False], capacity_hint=(NG, NG))
+            ag = gen_auctions(NG, SEED + 77)
+            device.join_push_device(jg, abi.SIDE_RIGHT, dchunk(to_dev(ag)), stream)
+            gb = [gen_bids(BG, s * BG, SEED + 5, NG + NG // 8) for s in range(WG + KG)]  # ids >= NG have no auction yet
+            gdev = [dchunk(to_dev(b)) for b in gb]
+            torch.cuda.synchronize()
+            for s in range(WG):
+                device.join_push_device(jg, abi.SIDE_LEFT, gdev[s], stream)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0g = device.launches(jg, "join")
+            g0.record(stream)
+            g_rows = g_null = 0
+            for s in range(WG, WG + KG):
+                v = device.join_push_device(jg, abi.SIDE_LEFT, gdev[s], stream)
+                g_rows += v.n_rows
+            g1.record(stream)
+            torch.cuda.synchronize()
+            gms = g0.elapsed_time(g1)
+            lg = device.launches(jg, "join") - l0g
+            # verification of the last step on the host: every bid emits exactly one row; unmatched ones are NULL-padded
+            vv = device.join_push_device(jg, abi.SIDE_LEFT, dchunk(to_dev(gen_bids(BG, (WG + KG) * BG, SEED + 5, NG + NG // 8))), stream)
+            vb = gen_bids(BG, (WG + KG) * BG, SEED + 5, NG + NG // 8)
+            pos_of = np.empty(NG, np.int64)
+            pos_of[ag[0]] = np.arange(NG)
+            matched = vb[0] < NG
+            ok = vv.n_rows == BG
+            if ok:
+                got = [vv.column(k).cpu().numpy() for k in range(8)]
+                order_g = np.argsort(got[1], kind="stable")  # date_time is unique: aligns output rows with input rows
+                order_w = np.argsort(vb[1], kind="stable")
+                for k in range(4):
+                    ok = ok and bool(np.array_equal(got[k][order_g], vb[k][order_w]))
+                m_w = matched[order_w]
+                for k in range(4):
+                    want_k = ag[k][pos_of[np.where(m_w, vb[0][order_w], 0)]]
+                    ok = ok and bool(np.array_equal(got[4 + k][order_g][m_w], want_k[m_w]))
+                ok = ok and bool(vv.valid_ptrs[4])  # the unmatched rows carry NULLs on the auction side
+            # the other direction: new auctions, half of which find waiting (NULL-padded) bids
+            new_ids = NG + np.arange(0, NG // 8, dtype=np.int64)
+            upd = [new_ids, new_ids % 1000, 10 + new_ids % 5, new_ids * 3]
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record(stream)
+            vu = device.join_push_device(jg, abi.SIDE_RIGHT, dchunk(to_dev(upd)), stream)
+            h1.record(stream)
+            torch.cuda.synchronize()
+            ums = h0.elapsed_time(h1)
+            line["generic_join"] = {
+                "workload": f"LEFT OUTER bid x auction, {NG} auctions resident, {BG} bids per step (1/9 without a partner: NULL-padded rows); "
+                            f"then {NG // 8} new auctions whose waiting bids flip from NULL-padded to matched",
+                "metric": "input rows/s", "value": KG * BG / (gms / 1e3), "steps": KG, "ms_per_step": gms / KG, "out_rows_per_step": g_rows / KG,
+                "launches_per_step": lg / KG, "verified": bool(ok),
+                "degree_flip_step": {"input_rows": int(NG // 8), "out_rows": int(vu.n_rows), "ms": ums, "rows_per_s": (NG // 8) / (ums / 1e3)},
+                "note": "the generic path runs hash_join_utils' per-key match loop on ONE thread per join key (exact degree semantics); "
+                        "its cost is the sort by key group, not HBM bandwidth: no roofline is claimed for it"}
+            del jg, gdev
+            torch.cuda.empty_cache()
+
         # ================================================================ leg: chain (join -> filter -> project -> agg in HBM)
         if "chain" in legs and world == 1:
             from risingwave_b200.executor import parse_filter_expr
@@ -1164,8 +1231,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--legs", default="value,retract,hot,e2e,agg,q1,chain,cpu",
-                    help="comma list of: value,retract,hot,e2e,agg,q1,chain,cpu (subset for ncu runs; retract needs value)")
+    ap.add_argument("--legs", default="value,retract,hot,e2e,agg,q1,chain,generic,cpu",
+                    help="comma list of: value,retract,hot,e2e,agg,q1,chain,generic,cpu (subset for ncu runs; retract needs value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

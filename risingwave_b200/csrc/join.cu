@@ -2172,7 +2172,7 @@ static int uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_only
     po.capacity = od.capacity;
     // resident blocks per SM (registers per thread): 4 (64) by default; RWGPU_UNI_MINB=3 / 5 / 6 for tuning runs
     static const int minb = getenv("RWGPU_UNI_MINB") ? atoi(getenv("RWGPU_UNI_MINB")) : 4;
-    static const uint32_t kflags = getenv("RWGPU_UNI_FLAGS") ? (uint32_t)atoi(getenv("RWGPU_UNI_FLAGS")) : 1u;  // bit 0: L2 prefetch of the next bucket
+    static const uint32_t kflags = getenv("RWGPU_UNI_FLAGS") ? (uint32_t)atoi(getenv("RWGPU_UNI_FLAGS")) : 1u;  // bit 0: L2 prefetch of the next bucket, bit 1: deferred link store
 #define UNI_LAUNCH(PO, IS, MB) uni_hot_kernel<PO, IS, MB><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pc, t.buckets, t.cap, own, po, wk, ds, pd.seq_base, pd.out_base, pd.pool_chunk, kflags)
     if (probe_only) {
       if (is_row) UNI_LAUNCH(true, true, 4); else UNI_LAUNCH(true, false, 4);
@@ -2183,7 +2183,11 @@ static int uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_only
         case 3: UNI_LAUNCH(false, false, 3); break;
         case 5: UNI_LAUNCH(false, false, 5); break;
         case 6: UNI_LAUNCH(false, false, 6); break;
-        default: UNI_LAUNCH(false, false, 4); break;
+        default:
+          if (kflags & 2u) uni_hot_kernel<false, false, 4, true><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pc, t.buckets, t.cap, own, po, wk, ds, pd.seq_base, pd.out_base,
+                                                                                                pd.pool_chunk, kflags);
+          else UNI_LAUNCH(false, false, 4);
+          break;
       }
     }
 #undef UNI_LAUNCH
@@ -3043,8 +3047,10 @@ int32_t rwgpu_join_collect(rwgpu_join* h, rw_chunk* view, void* cuda_stream) {
     h->call_had_deletes = false;
     int rc = uni_finish(h, pd, &n, &nullm);
     if (rc != RW_OK) return rc;
+    const double tp0 = uni_trace ? uni_now_ms() : 0.0;
     rc = join_post_process(h, n, &nullm, pd.st);
     if (rc != RW_OK) return rc;
+    if (uni_trace) fprintf(stderr, "  [collect] post-process (no-op elimination: %d) %.3f ms\n", (int)h->call_had_deletes, uni_now_ms() - tp0);
   }
   int rc = join_fill_view(h, n, nullm, view, cuda_stream ? (cudaStream_t)cuda_stream : pd.st);
   // the next synchronous push must not land in the set a still-outstanding push writes to

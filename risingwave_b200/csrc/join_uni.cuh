@@ -324,7 +324,10 @@ struct UniWork {
   uint8_t* mask;     // [(n + 7) / 8], one bit per input row, every byte written by the hot kernel
 };
 
-template <bool PROBE_ONLY, bool IS_ROW, int MINB>
+// DL ("deferred link", chained-side rows only): the record's link word -- the old chain head the exchange returns -- is
+// stored by the exchanging lane at the top of the NEXT iteration, after that iteration's bucket load has been issued, so
+// the exchange's round trip overlaps the next bucket's instead of ending the iteration.
+template <bool PROBE_ONLY, bool IS_ROW, int MINB, bool DL = false>
 __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, uint8_t* buckets, uint64_t cap, UniOwn own, PlainOut o, UniWork wk,
                                                                   JoinStatus* st, uint64_t seq_base, int64_t out_base, uint32_t pool_chunk,
                                                                   uint32_t kflags) {
@@ -378,6 +381,8 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
     }                                                         \
   } while (0)
   UNI_FETCH(warp_global);
+  unsigned long long pend_rec = 0ull;  // DL: record whose link word is still to be written (lane 0 of a quad)
+  uint32_t pend_link = 0u;
   for (int64_t g = warp_global; g < groups; g += nwarps) {
     const int64_t r = g * 8 + (lane >> 2);
     const bool in = r < n_rows;
@@ -396,7 +401,11 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
     bool first_iter = true;
     while (__any_sync(0xffffffffu, need)) {
       if (need) pv = ld128_cg(buckets + idx * 64 + 16 * q);
-      if (first_iter) { UNI_FETCH(g + nwarps); first_iter = false; }
+      if (first_iter) {
+        UNI_FETCH(g + nwarps);
+        first_iter = false;
+        if (DL && pend_rec) { *(unsigned long long*)pend_rec = (unsigned long long)pend_link; pend_rec = 0ull; }
+      }
       const unsigned long long bkey = shfl64m(0xffffffffu, pv.x, qlead);
       const bool empty = need && bkey == J_EMPTY;
       if (need && !empty) {
@@ -429,6 +438,7 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
       }
     }
     if (first_iter) UNI_FETCH(g + nwarps);
+    if (DL && pend_rec) { *(unsigned long long*)pend_rec = (unsigned long long)pend_link; pend_rec = 0ull; }
     // the NEXT group's bucket line is pulled into L2 while this group's atomics and stores are in flight (its
     // key arrived with the column loads issued above): the next iteration's probe then waits for L2, not DRAM
     if ((kflags & 1u) && n_op != 0 && !(q & 1)) {
@@ -578,6 +588,14 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
         atomicAdd((uint32_t*)(buckets + idx * 64 + 28), 1u);
         recp = (unsigned long long)useg_rec(own.log, row);
       }
+      if (DL && !IS_ROW) {
+        if (q == 0 && recp) { pend_rec = recp; pend_link = link; }  // (the link is still in flight: not touched here)
+        recp = shfl64m(0xffffffffu, recp, qlead);
+        if (recp && q != 0) {
+          if (q == 1) *(unsigned long long*)(recp + 8) = seq_base + (unsigned long long)r;  // the link word follows later
+          else *(ulonglong2*)(recp + 16 * (q - 1)) = make_ulonglong2(va, vb);
+        }
+      } else {
       recp = shfl64m(0xffffffffu, recp, qlead);
       link = __shfl_sync(0xffffffffu, link, qlead);
       if (recp && q != 0) {
@@ -593,9 +611,11 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
           *(ulonglong2*)(recp + 16 * (q - 1)) = v;
         }
       }
+      }
     }
   }
 #undef UNI_FETCH
+  if (DL && pend_rec) *(unsigned long long*)pend_rec = (unsigned long long)pend_link;
   // leftover of the extra-row reservation
   for (int64_t f = xnext + lane; f < xend; f += 32) { o.ops[xarea + f] = RW_OP_INSERT; o.vis[xarea + f] = 0; }
   if (xend > xnext) any_hole = true;
