@@ -228,6 +228,8 @@ typedef struct rw_join_side_desc {
   const int32_t* stream_key;        /* input.stream_key(): decides pk_contained_in_jk
                                        (hash_join.rs:377-381)                               */
   uint64_t row_capacity_hint;       /* expected distinct join keys of this side (index grows on demand) */
+  uint64_t stored_rows_hint;        /* expected rows STORED on this side (0 = two per expected key); the row store
+                                       grows on demand, one 200 MB segment at a time                          */
 } rw_join_side_desc;
 
 typedef struct rw_join_desc {

@@ -87,7 +87,7 @@ class RwJoinSideDesc(C.Structure):
                 ("key_indices", C.POINTER(C.c_int32)),
                 ("n_pk", C.c_int32), ("pk_indices", C.POINTER(C.c_int32)),
                 ("n_stream_key", C.c_int32), ("stream_key", C.POINTER(C.c_int32)),
-                ("row_capacity_hint", C.c_uint64)]
+                ("row_capacity_hint", C.c_uint64), ("stored_rows_hint", C.c_uint64)]
 
 
 class RwJoinDesc(C.Structure):

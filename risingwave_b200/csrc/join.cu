@@ -34,6 +34,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <mutex>
+#include <thread>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -1701,7 +1703,35 @@ using namespace rw;
 struct SegLog {
   std::vector<DevBuf> segs;
   DevBuf table;  // U_MAX_SEGS device pointers
+  // ONE segment is allocated ahead of need by a helper thread (a 200 MB cudaMalloc takes 1.5-2 ms on the GPU boxes:
+  // on the push path the GPU would idle for ten steps' worth of time)
+  std::thread worker;
+  std::mutex mu;
+  DevBuf spare;
+  bool spare_ready = false, worker_running = false;
+  uint64_t stalls = 0, prefetched = 0;  // segments allocated on the push path / taken from the helper
+  SegLog() = default;
+  SegLog(const SegLog&) = delete;
+  ~SegLog() { if (worker.joinable()) worker.join(); }
   uint64_t cap() const { return (uint64_t)segs.size() << U_SEG_SHIFT; }
+  void prefetch() {
+    {
+      std::lock_guard<std::mutex> g(mu);
+      if (worker_running || spare_ready || segs.size() >= U_MAX_SEGS) return;
+      worker_running = true;
+    }
+    if (worker.joinable()) worker.join();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    worker = std::thread([this, dev]() {
+      cudaSetDevice(dev);
+      DevBuf b;
+      const cudaError_t e = b.reserve((size_t)U_SEG_RECS * 48);
+      std::lock_guard<std::mutex> g(mu);
+      if (e == cudaSuccess) { spare = std::move(b); spare_ready = true; } else { cudaGetLastError(); }
+      worker_running = false;
+    });
+  }
   // make room for `rows` records: new segments are allocated and their pointers appended ON `st` (stream order puts
   // the table update before every kernel launched afterwards; existing entries never change)
   int ensure(uint64_t rows, cudaStream_t st) {
@@ -1712,8 +1742,16 @@ struct SegLog {
     while (cap() < rows) {
       if (segs.size() >= U_MAX_SEGS) return fail(RW_ERR_OOM, "join side exceeds 2^31 log rows");
       DevBuf sg;
-      cudaError_t e = sg.reserve((size_t)U_SEG_RECS * 48);
-      if (e != cudaSuccess) { cudaGetLastError(); return fail(RW_ERR_OOM, std::string("join log segment: ") + cudaGetErrorString(e)); }
+      if (worker.joinable()) worker.join();  // (a running helper finishes sooner than a second allocation would)
+      {
+        std::lock_guard<std::mutex> g(mu);
+        if (spare_ready) { sg = std::move(spare); spare_ready = false; prefetched++; }
+      }
+      if (!sg.p) {
+        cudaError_t e = sg.reserve((size_t)U_SEG_RECS * 48);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(RW_ERR_OOM, std::string("join log segment: ") + cudaGetErrorString(e)); }
+        stalls++;
+      }
       void* ptr = sg.p;
       // (the pointer is copied from a pageable temporary: cudaMemcpyAsync stages it before returning)
       RW_CUDA(cudaMemcpyAsync(table.as<uint8_t>() + segs.size() * sizeof(void*), &ptr, sizeof(void*), cudaMemcpyHostToDevice, st));
@@ -1878,9 +1916,13 @@ static int join_grow_store(rwgpu_join* h, int S, uint64_t rows) {
   JoinSideHost& s = h->side[S];
   if (h->uni) {
     if (rows >= 0x7ffffff0ull) return fail(RW_ERR_OOM, "join side exceeds 2^31 rows");
-    if (rows <= s.log.cap()) return RW_OK;
-    int rc = s.log.ensure(rows, h->last_st ? h->last_st : h->stream);
-    s.row_cap = s.log.cap();
+    int rc = RW_OK;
+    if (rows > s.log.cap()) {
+      rc = s.log.ensure(rows, h->last_st ? h->last_st : h->stream);
+      s.row_cap = s.log.cap();
+    }
+    // less than one segment of headroom left: have the next one allocated in the background
+    if (rc == RW_OK && !s.log.segs.empty() && rows + U_SEG_RECS > s.log.cap()) s.log.prefetch();
     return rc;
   }
   if (rows <= s.row_cap) return RW_OK;
@@ -2120,7 +2162,7 @@ static int join_order(rwgpu_join* h, cudaStream_t st) {
   return RW_OK;
 }
 
-// grid of the cooperative tail kernel: every block resident at once (cooperative launch), no more than the rows need
+// grid of the tail kernel: every block resident at once (its rare grid-wide barrier relies on it), no more than the rows need
 static int uni_tail_grid(int64_t n) {
   static int max_blocks = 0;
   if (!max_blocks) {
@@ -2136,7 +2178,7 @@ static int uni_tail_grid(int64_t n) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, max_blocks));
 }
 
-// main kernel (timed by the profiler) + the cooperative tail kernel, which ends by publishing the status block
+// main kernel (timed by the profiler) + the tail kernel, which ends by publishing the status block
 // (tagged `tag`) into the pinned slot of the push's output set
 static int uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_only, unsigned long long tag) {
   UniDev t = uni_dev(h);
@@ -2172,7 +2214,7 @@ static int uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_only
     po.capacity = od.capacity;
     // resident blocks per SM (registers per thread): 4 (64) by default; RWGPU_UNI_MINB=3 / 5 / 6 for tuning runs
     static const int minb = getenv("RWGPU_UNI_MINB") ? atoi(getenv("RWGPU_UNI_MINB")) : 4;
-    static const uint32_t kflags = getenv("RWGPU_UNI_FLAGS") ? (uint32_t)atoi(getenv("RWGPU_UNI_FLAGS")) : 1u;  // bit 0: L2 prefetch of the next bucket, bit 1: deferred link store
+    static const uint32_t kflags = getenv("RWGPU_UNI_FLAGS") ? (uint32_t)atoi(getenv("RWGPU_UNI_FLAGS")) : 0u;  // bit 0: L2 prefetch of the next bucket (key column two groups ahead), bit 1: deferred link store
 #define UNI_LAUNCH(PO, IS, MB) uni_hot_kernel<PO, IS, MB><<<pd.grid, JF_BLOCK, 0, pd.st>>>(pc, t.buckets, t.cap, own, po, wk, ds, pd.seq_base, pd.out_base, pd.pool_chunk, kflags)
     if (probe_only) {
       if (is_row) UNI_LAUNCH(true, true, 4); else UNI_LAUNCH(true, false, 4);
@@ -2204,10 +2246,10 @@ static int uni_launch_main(rwgpu_join* h, const JoinPending& pd, bool probe_only
   JoinStatus* slot = (JoinStatus*)(h->status_host.as<uint8_t>() + 512 * pd.set);
   int reset = 3;
   unsigned int* done = (unsigned int*)(h->uni_counters.as<unsigned long long>() + 6);
-  void* args[] = {(void*)&pdev, (void*)&w, (void*)&S, (void*)&chv, (void*)&t, (void*)&od, (void*)&wk, (void*)&ds, (void*)&seq_base, (void*)&out_base,
-                  (void*)&slot, (void*)&tag, (void*)&reset, (void*)&done};
-  const void* fn = probe_only ? (const void*)uni_tail_kernel<true> : (const void*)uni_tail_kernel<false>;
-  RW_CUDA(cudaLaunchCooperativeKernel(fn, dim3(uni_tail_grid(pd.ch.n)), dim3(256), args, 0, pd.st));
+  const int tg = uni_tail_grid(pd.ch.n);
+  if (probe_only) uni_tail_kernel<true><<<tg, 256, 0, pd.st>>>(pdev, w, S, chv, t, od, wk, ds, seq_base, out_base, slot, tag, reset, done);
+  else uni_tail_kernel<false><<<tg, 256, 0, pd.st>>>(pdev, w, S, chv, t, od, wk, ds, seq_base, out_base, slot, tag, reset, done);
+  RW_CUDA(cudaGetLastError());
   h->launches += 2;
   return RW_OK;
 }
@@ -2783,7 +2825,8 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
       h->side[s].stride = 48;
       h->last_st = h->stream;
       // chained side: every row lives in its log; inline side: only the 2nd, 3rd ... row of a key
-      const uint64_t rows = s == h->uni_is ? std::max<uint64_t>(4096, sd[s]->row_capacity_hint / 4) : std::max<uint64_t>(4096, 2 * sd[s]->row_capacity_hint);
+      uint64_t rows = s == h->uni_is ? std::max<uint64_t>(4096, sd[s]->row_capacity_hint / 4) : std::max<uint64_t>(4096, 2 * sd[s]->row_capacity_hint);
+      if (sd[s]->stored_rows_hint && s != h->uni_is) rows = std::max<uint64_t>(4096, sd[s]->stored_rows_hint);
       rc = join_grow_store(h, s, std::min<uint64_t>(rows, 0x40000000ull));
       if (rc != RW_OK) return rc;
       RW_CUDA(h->side[s].pools.reserve((size_t)Q4_MAX_GRID * (JF_BLOCK / 32) * sizeof(uint2)));

@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
   const int64_t xarea = out_base + n_rows;
   const uint64_t mask = cap - 1;
   unsigned int new_keys = 0, n_del = 0;
-  bool any_match = false, any_hole = false, any_defer = false;
+  bool any_match = false, any_hole = false, any_defer = false, any_sentinel = false;
   // (selected with ?: -- an index computed from the lane would put the parameter arrays in local memory)
   const unsigned long long* pa = (q & 1) ? ch.c[2] : ch.c[0];
   const unsigned long long* pb = (q & 1) ? ch.c[3] : ch.c[1];
@@ -367,19 +367,35 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
   const unsigned long long init_W = IS_ROW ? ((W_EMPTY | W_IL_LIVE) + W_COUNT_ONE) : W_EMPTY;
   // software pipeline: the sequential column loads of the warp's next group are issued right after the random
   // access of the current one
+  // (kflags bit 0) the KEY column runs two groups ahead: when group g's bucket load has been issued, the key of group
+  // g + 1 is already in a register (it was loaded during group g - 1), so its bucket line can be pulled into L2 at once
+  // -- a whole iteration before it is needed -- without waiting for anything.
   uint8_t n_op = 0;
-  unsigned long long n_key = J_EMPTY, n_va = 0ull, n_vb = 0ull;
-#define UNI_FETCH(G2)                                         \
-  do {                                                        \
-    const int64_t g2_ = (G2), r2_ = g2_ * 8 + (lane >> 2);    \
-    n_op = 0;                                                 \
-    if (g2_ < groups && r2_ < n_rows) {                       \
-      n_op = ch.ops[r2_];                                     \
-      n_key = __ldg(pk + r2_);                                \
-      if (pa) n_va = __ldg(pa + r2_);                         \
-      if (pb) n_vb = __ldg(pb + r2_);                         \
-    }                                                         \
+  unsigned long long n_key = J_EMPTY, n_va = 0ull, n_vb = 0ull, nn_key = J_EMPTY;
+  const bool pf = (kflags & 1u) != 0u;
+#define UNI_FETCH(G2)                                                             \
+  do {                                                                            \
+    const int64_t g2_ = (G2), r2_ = g2_ * 8 + (lane >> 2);                        \
+    n_op = 0;                                                                     \
+    if (g2_ < groups && r2_ < n_rows) {                                           \
+      n_op = ch.ops[r2_];                                                         \
+      n_key = pf ? nn_key : __ldg(pk + r2_);                                      \
+      if (pa) n_va = __ldg(pa + r2_);                                             \
+      if (pb) n_vb = __ldg(pb + r2_);                                             \
+      if (pf) {                                                                   \
+        if (!(q & 1)) {                                                           \
+          const uint8_t* nb_ = buckets + uhome(n_key, mask) * 64 + 16 * q;        \
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nb_));                    \
+        }                                                                         \
+        const int64_t r3_ = r2_ + nwarps * 8;                                     \
+        nn_key = (g2_ + nwarps < groups && r3_ < n_rows) ? __ldg(pk + r3_) : J_EMPTY; \
+      }                                                                           \
+    }                                                                             \
   } while (0)
+  if (pf) {
+    const int64_t r0_ = warp_global * 8 + (lane >> 2);
+    if (warp_global < groups && r0_ < n_rows) nn_key = __ldg(pk + r0_);
+  }
   UNI_FETCH(warp_global);
   unsigned long long pend_rec = 0ull;  // DL: record whose link word is still to be written (lane 0 of a quad)
   uint32_t pend_link = 0u;
@@ -439,12 +455,6 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
     }
     if (first_iter) UNI_FETCH(g + nwarps);
     if (DL && pend_rec) { *(unsigned long long*)pend_rec = (unsigned long long)pend_link; pend_rec = 0ull; }
-    // the NEXT group's bucket line is pulled into L2 while this group's atomics and stores are in flight (its
-    // key arrived with the column loads issued above): the next iteration's probe then waits for L2, not DRAM
-    if ((kflags & 1u) && n_op != 0 && !(q & 1)) {
-      const uint8_t* nb_ = buckets + uhome(n_key, mask) * 64 + 16 * q;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nb_));
-    }
     if (created && q == 0) new_keys++;
     // ---- what does the other side hold for the key ?
     const unsigned long long WI = shfl64m(0xffffffffu, pv.y, qlead);
@@ -509,6 +519,7 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
     {
       const unsigned dbal = __ballot_sync(0xffffffffu, defer && q == 0);
       if (dbal) any_defer = true;
+      if (__any_sync(0xffffffffu, defer && !keyok)) any_sentinel = true;  // whole rows (insert included) go to the tail kernel
       if (lane == 0 && g * 8 < n_rows) {
         unsigned m8 = 0;
 #pragma unroll
@@ -623,6 +634,7 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
   unsigned long long flags = (any_hole ? (1ull << 63) : 0ull);
   const bool warp_match = __any_sync(0xffffffffu, any_match);
   const bool warp_defer = __any_sync(0xffffffffu, any_defer);
+  const bool warp_sentinel = __any_sync(0xffffffffu, any_sentinel);
   for (int d = 16; d > 0; d >>= 1) {
     flags |= __shfl_xor_sync(0xffffffffu, flags, d);
     new_keys += __shfl_xor_sync(0xffffffffu, new_keys, d);
@@ -631,7 +643,10 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
   if (lane == 0) {
     if (flags && (__ldcg(&st->null_mask) & flags) != flags) atomicOr(&st->null_mask, flags);
     if (warp_match && __ldcg(&st->pad) == 0u) st->pad = 1u;
-    if (warp_defer && __ldcg(&st->n_defer) == 0ull) st->n_defer = 1ull;  // (plain store: all writers store 1)
+    {  // bit 0: rows deferred; bit 1: some of them are whole rows whose own-side insert happens in the tail kernel
+      const unsigned long long want = (warp_defer ? 1ull : 0ull) | (warp_sentinel ? 2ull : 0ull);
+      if (want && (__ldcg(&st->n_defer) & want) != want) atomicOr(&st->n_defer, want);
+    }
     if (!PROBE_ONLY && new_keys) atomicAdd(&st->n_keys[0], (unsigned long long)new_keys);
     if (!PROBE_ONLY && n_del) atomicAdd(&st->n_del, (unsigned long long)n_del);
   }
@@ -757,20 +772,32 @@ __device__ __forceinline__ void uni_delete_body(const JoinPlanDev* __restrict__ 
   if (dead_log) atomicAdd(t.n_dead[S], (unsigned long long)dead_log);
 }
 
-// Everything behind the hot kernel in ONE cooperative launch: (1) the deferred rows, (2) the own-side deletes, (3) the
-// status block published to pinned host memory by the block that finishes last.  Phases 1 and 2 exit at once when
-// the hot kernel flagged no such rows (st->n_defer / st->n_del: final when this kernel starts, so every block takes
-// the same path); only a batch with BOTH needs the grid-wide barrier between them (a delete must see the rows the
-// deferred phase appended).  `plain` = the chunk went through uni_hot_kernel (else uni_slow_kernel: nothing deferred).
+// Everything behind the hot kernel in ONE launch: (1) the deferred rows, (2) the own-side deletes, (3) the status block
+// published to pinned host memory by the block that finishes last.  Phases 1 and 2 exit at once when the hot kernel
+// flagged no such rows (st->n_defer / st->n_del are final when this kernel starts: every block takes the same path).
+// The two phases are independent -- deferred emission reads the OTHER side's records, deletes change the OWN side's --
+// except for deferred WHOLE rows (the key equal to the EMPTY sentinel: their insert happens in phase 1 and a delete
+// later in the chunk may target it).  Only then (n_defer bit 1 and deletes in one batch) the blocks meet in a grid-wide
+// barrier between the phases; the host sizes the grid so that every block is resident (uni_tail_grid).
+// (r2c/r2d: as a cooperative launch this kernel cost ~35 us per step, two plain launches ~19 us.)
 template <bool PROBE_ONLY>
 __global__ void __launch_bounds__(256) uni_tail_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch, UniDev t, JoinOutDev o, UniWork wk,
                                                        JoinStatus* st, uint64_t seq_base, int64_t out_base, JoinStatus* status_host,
                                                        unsigned long long tag, int reset, unsigned int* done) {
-  const bool has_defer = *(volatile unsigned long long*)&st->n_defer != 0ull;
+  const unsigned long long defer_flags = *(volatile unsigned long long*)&st->n_defer;
   const bool has_del = !PROBE_ONLY && *(volatile unsigned long long*)&st->n_del != 0ull;
-  if (has_defer) uni_deferred_body<PROBE_ONLY>(p, w, S, ch, t, o, wk, st, seq_base, out_base);
+  if (defer_flags) uni_deferred_body<PROBE_ONLY>(p, w, S, ch, t, o, wk, st, seq_base, out_base);
   if (has_del) {
-    if (has_defer) cooperative_groups::this_grid().sync();
+    if (defer_flags & 2ull) {  // software grid barrier (done[1]); reset by the publishing block below
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(done + 1, 1u);
+        while (*(volatile unsigned int*)(done + 1) < gridDim.x) __nanosleep(64);
+        __threadfence();
+      }
+      __syncthreads();
+    }
     uni_delete_body(p, S, ch, t, st, seq_base);
   }
   // last block out publishes (every block's work is fenced before its ticket)
@@ -779,7 +806,8 @@ __global__ void __launch_bounds__(256) uni_tail_kernel(const JoinPlanDev* __rest
     __threadfence();
     const unsigned int ticket = atomicAdd(done, 1u);
     if (ticket == gridDim.x - 1) {
-      *done = 0u;
+      done[0] = 0u;
+      done[1] = 0u;
       __threadfence();
       st->log_next[0] = *(volatile unsigned long long*)t.log_next[0]; st->log_next[1] = *(volatile unsigned long long*)t.log_next[1];
       st->n_dead[0] = *(volatile unsigned long long*)t.n_dead[0]; st->n_dead[1] = *(volatile unsigned long long*)t.n_dead[1];

@@ -361,7 +361,9 @@ class HashJoinExecutor:
                  params_l: JoinParams, params_r: JoinParams, null_safe: Sequence[bool],
                  output_indices: Optional[Sequence[int]] = None, cond: Optional[str] = None,
                  is_append_only: bool = False, chunk_size: int = 1024, strict_consistency: bool = True,
-                 capacity_hint=0):
+                 capacity_hint=0, stored_rows_hint=0):
+        """capacity_hint: expected distinct join keys (one number or (left, right)); stored_rows_hint: expected rows stored
+        per side (same shapes; 0 = two per expected key)"""
         self.backend = backend
         self.input_l, self.input_r = input_l, input_r
         self._keep = []
@@ -369,7 +371,8 @@ class HashJoinExecutor:
         d.join_type = join_type
         d.n_keys = len(params_l.join_key_indices)
         hints = capacity_hint if isinstance(capacity_hint, (tuple, list)) else (capacity_hint, capacity_hint)
-        for side, inp, p, hint in ((d.left, input_l, params_l, hints[0]), (d.right, input_r, params_r, hints[1])):
+        shints = stored_rows_hint if isinstance(stored_rows_hint, (tuple, list)) else (stored_rows_hint, stored_rows_hint)
+        for side, inp, p, hint, shint in ((d.left, input_l, params_l, hints[0], shints[0]), (d.right, input_r, params_r, hints[1], shints[1])):
             types = (C.c_int32 * max(1, len(inp.schema)))(*inp.schema)
             keys = (C.c_int32 * max(1, len(p.join_key_indices)))(*p.join_key_indices)
             pk = (C.c_int32 * max(1, len(p.deduped_pk_indices)))(*p.deduped_pk_indices)
@@ -383,6 +386,7 @@ class HashJoinExecutor:
             side.n_stream_key = len(inp.stream_key)
             side.stream_key = sk
             side.row_capacity_hint = int(hint)  # expected distinct join keys of the side
+            side.stored_rows_hint = int(shint)
         ns = (C.c_uint8 * max(1, len(null_safe)))(*[int(b) for b in null_safe])
         d.null_safe = ns
         if join_type in (abi.JOIN_LEFT_SEMI, abi.JOIN_LEFT_ANTI):

@@ -39,8 +39,8 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(abi.RwChunk) == 40
     assert ctypes.sizeof(abi.RwAggCall) == 16
     assert ctypes.sizeof(abi.RwAggDesc) == 72
-    assert ctypes.sizeof(abi.RwJoinSideDesc) == 64
-    assert ctypes.sizeof(abi.RwJoinDesc) == 192
+    assert ctypes.sizeof(abi.RwJoinSideDesc) == 72
+    assert ctypes.sizeof(abi.RwJoinDesc) == 208
     assert ctypes.sizeof(abi.RwFilterTerm) == 24
 
 

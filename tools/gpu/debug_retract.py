@@ -34,28 +34,64 @@ with torch.cuda.stream(stream):
     ad = to_dev(auct)
     device.join_push_device(join, abi.SIDE_RIGHT, device.DeviceChunk(torch.ones(N_BUILD, dtype=torch.uint8, device="cuda"), ad, T4), stream)
     bids = [bench.gen_bids(BATCH, s * BATCH, bench.SEED, N_BUILD) for s in range(N_BATCH)]
-    for b in bids:
-        o = device.join_push_device(join, abi.SIDE_LEFT, device.DeviceChunk(torch.ones(BATCH, dtype=torch.uint8, device="cuda"), to_dev(b), T4), stream)
-        assert o.n_rows == BATCH, o.n_rows
+    PIPE = int(os.environ.get("DBG_PIPE", 0))  # 1: two pushes outstanding, as bench.py drives the handle
+    if PIPE:
+        bdev = [device.DeviceChunk(torch.ones(BATCH, dtype=torch.uint8, device="cuda"), to_dev(b), T4) for b in bids]
+        for i, ch in enumerate(bdev):
+            device.join_push_device_async(join, abi.SIDE_LEFT, ch, stream)
+            if i:
+                assert device.join_collect(join, stream).n_rows == BATCH
+        assert device.join_collect(join, stream).n_rows == BATCH
+    else:
+        for b in bids:
+            o = device.join_push_device(join, abi.SIDE_LEFT, device.DeviceChunk(torch.ones(BATCH, dtype=torch.uint8, device="cuda"), to_dev(b), T4), stream)
+            assert o.n_rows == BATCH, o.n_rows
     allb = [np.concatenate([b[k] for b in bids]) for k in range(4)]
     order = np.argsort(allb[0], kind="stable")
     sk = allb[0][order]
     bad = 0
+    ups = [bench.gen_auction_updates(auct, s * RP, RP) for s in range(STEPS)]
+    udev = [device.DeviceChunk(torch.from_numpy(o_).cuda(), to_dev(c_), T4) for o_, c_ in ups]
+    outs = {}
+    cks = []
+    if PIPE:  # every step but the last with two outstanding; outputs snapshotted at collect
+        def snap(o):
+            torch.cuda.synchronize()
+            vis = o.visible()
+            cks.append(o.checksum(bench.CHECKSUM_WEIGHTS))
+            return (o.n_rows, o.ops().cpu().numpy(), np.stack([o.column(k).cpu().numpy() for k in range(8)], 1), None if vis is None else vis.cpu().numpy())
+        for s in range(STEPS - 1):
+            device.join_push_device_async(join, abi.SIDE_RIGHT, udev[s], stream)
+            if s:
+                outs[s - 1] = snap(device.join_collect(join, stream))
+        if STEPS > 1:
+            outs[STEPS - 2] = snap(device.join_collect(join, stream))
+        device.join_push_device_async(join, abi.SIDE_RIGHT, udev[STEPS - 1], stream)
+        outs[STEPS - 1] = snap(device.join_collect(join, stream))
     for s in range(STEPS):
-        ops, cols = bench.gen_auction_updates(auct, s * RP, RP)
-        ch = device.DeviceChunk(torch.from_numpy(ops).cuda(), to_dev(cols), T4)
-        if s % 2 == 0:
-            o = device.join_push_device(join, abi.SIDE_RIGHT, ch, stream)
+        ops, cols = ups[s]
+        if PIPE:
+            n_out, got_ops, got, v = outs[s]
+            if v is not None:
+                got_ops, got = got_ops[v], got[v]
+
+            class _O:
+                n_rows = n_out
+            o = _O()
         else:
-            device.join_push_device_async(join, abi.SIDE_RIGHT, ch, stream)
-            o = device.join_collect(join, stream)
-        torch.cuda.synchronize()
-        vis = o.visible()
-        got_ops = o.ops().cpu().numpy()
-        got = np.stack([o.column(k).cpu().numpy() for k in range(8)], 1)
-        if vis is not None:
-            v = vis.cpu().numpy()
-            got_ops, got = got_ops[v], got[v]
+            ch = udev[s]
+            if s % 2 == 0:
+                o = device.join_push_device(join, abi.SIDE_RIGHT, ch, stream)
+            else:
+                device.join_push_device_async(join, abi.SIDE_RIGHT, ch, stream)
+                o = device.join_collect(join, stream)
+            torch.cuda.synchronize()
+            vis = o.visible()
+            got_ops = o.ops().cpu().numpy()
+            got = np.stack([o.column(k).cpu().numpy() for k in range(8)], 1)
+            if vis is not None:
+                v = vis.cpu().numpy()
+                got_ops, got = got_ops[v], got[v]
         # expectation
         lo = np.searchsorted(sk, cols[0], "left")
         hi = np.searchsorted(sk, cols[0], "right")
@@ -70,7 +106,9 @@ with torch.cuda.stream(stream):
         gs = g[np.lexsort(g.T[::-1])]
         ws = w[np.lexsort(w.T[::-1])]
         same = gs.shape == ws.shape and bool((gs == ws).all())
-        print(f"step {s}: out {o.n_rows} visible {len(g)} expected {len(w)} equal {same}", flush=True)
+        wsum = int((np.where(w[:, 0] == 1, 1, -1).astype(np.int64)[:, None] * w[:, 1:] * np.array(bench.CHECKSUM_WEIGHTS, np.int64)[None, :]).sum()) & ((1 << 64) - 1)
+        print(f"step {s}: out {o.n_rows} visible {len(g)} expected {len(w)} equal {same}  expected checksum {wsum:016x}"
+              + (f"  DeviceView.checksum {cks[s][0]} {cks[s][1]:016x}" if PIPE else ""), flush=True)
         if not same:
             bad += 1
             if gs.shape == ws.shape:
