@@ -1860,6 +1860,8 @@ struct rwgpu_join {
   DevBuf up2[2];
   PinnedBuf up2_host[2];
   cudaEvent_t ev_up2[2] = {nullptr, nullptr};
+  cudaStream_t s_out[2] = {nullptr, nullptr};  // one copy-out stream per output set: collecting push s must not wait for
+                                               // the copies of push s+1, which are already queued when s is collected
   std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
   std::vector<rw_column> dev_view_cols[2];  // per output set
   DevBuf noop_nxt, noop_prv, noop_elig, noop_flag;  // eliminate_adjacent_noop_update scratch
@@ -2856,7 +2858,10 @@ int32_t rwgpu_join_create(const rw_join_desc* d, rwgpu_join** out) {
 void rwgpu_join_destroy(rwgpu_join* h) {
   if (!h) return;
   cudaDeviceSynchronize();  // pushes may be outstanding on the handle's or a caller's stream
-  for (int i = 0; i < 2; i++) delete h->hpend[i].out;
+  for (int i = 0; i < 2; i++) {
+    delete h->hpend[i].out;
+    if (h->s_out[i]) cudaStreamDestroy(h->s_out[i]);
+  }
   delete h;
 }
 
@@ -3374,6 +3379,8 @@ int32_t rwgpu_join_push_async(rwgpu_join* h, int32_t side, const rw_chunk* c) {
     }
   }
   if (!h->ev_up2[set]) RW_CUDA(cudaEventCreateWithFlags(&h->ev_up2[set], cudaEventDisableTiming));
+  if (!h->s_out[set]) RW_CUDA(cudaStreamCreateWithFlags(&h->s_out[set], cudaStreamNonBlocking));
+  cudaStream_t sd = h->s_out[set];
   // ---- input: device staging of this set
   const size_t nw = (size_t)((n + 63) / 64) * 8;
   size_t off = 0;
@@ -3442,12 +3449,12 @@ int32_t rwgpu_join_push_async(rwgpu_join* h, int32_t side, const rw_chunk* c) {
   if (hp.alias_ok)
     for (int k = 0; k < c->n_cols; k++)
       if (h->w8[side].u_out[k] >= 0) hp.alias_src[(size_t)h->w8[side].u_out[k]] = k;
-  RW_CUDA(cudaStreamWaitEvent(h->s_d2h, h->pend_ev[set], 0));
-  cudaMemcpyAsync(o->ops, h->os().out_ops.p, (size_t)n, cudaMemcpyDeviceToHost, h->s_d2h);
+  RW_CUDA(cudaStreamWaitEvent(sd, h->pend_ev[set], 0));
+  cudaMemcpyAsync(o->ops, h->os().out_ops.p, (size_t)n, cudaMemcpyDeviceToHost, sd);
   for (size_t k = 0; k < h->out_types.size(); k++) {
     if (hp.alias_src[k] >= 0) continue;
     const size_t w = type_width(h->out_types[k]);
-    cudaMemcpyAsync(o->data[k], h->os().out_col[k].p, (size_t)n * w, cudaMemcpyDeviceToHost, h->s_d2h);
+    cudaMemcpyAsync(o->data[k], h->os().out_col[k].p, (size_t)n * w, cudaMemcpyDeviceToHost, sd);
   }
   RW_CUDA(cudaGetLastError());
   h->pending[h->n_pending++] = pd;
@@ -3471,13 +3478,14 @@ int32_t rwgpu_join_collect_out(rwgpu_join* h, rwgpu_out** out) {
   std::unique_ptr<rwgpu_out> guard(hp.out);
   hp.out = nullptr;
   rwgpu_out* o = guard.get();
+  cudaStream_t sd = h->s_out[pd.set];
   h->cur = pd.set;
   h->call_null_mask = 0;
   h->call_had_deletes = false;
   int64_t total = 0;
   unsigned long long nullm = 0;
   const uint8_t* ops_before = h->os().out_ops.as<uint8_t>();
-  auto bail = [&](int rc) { cudaStreamSynchronize(h->s_d2h); if (h->n_pending) h->cur = h->pending[h->n_pending - 1].set; return rc; };
+  auto bail = [&](int rc) { cudaStreamSynchronize(sd); if (h->n_pending) h->cur = h->pending[h->n_pending - 1].set; return rc; };
   int rc = uni_finish(h, pd, &total, &nullm);
   if (rc != RW_OK) return bail(rc);
   rc = join_post_process(h, total, &nullm, pd.st);
@@ -3486,7 +3494,7 @@ int32_t rwgpu_join_collect_out(rwgpu_join* h, rwgpu_out** out) {
   // what the launch already copied is good unless the emission was redone into re-allocated buffers
   bool pre_ok = h->os().out_ops.as<uint8_t>() == ops_before && total >= n;
   if (total > hp.host_cap) {  // rare: amplification above 2x -- a larger host block, everything is copied again
-    RW_CUDA(cudaStreamSynchronize(h->s_d2h));
+    RW_CUDA(cudaStreamSynchronize(sd));
     auto o2 = new rwgpu_out();
     o2->chunk_size = h->chunk_size;
     if (!o2->layout(total + total / 4, h->out_types, ~0ull >> 1, true, h->pool)) { delete o2; return bail(fail(RW_ERR_OOM, "pinned output block")); }
@@ -3499,22 +3507,22 @@ int32_t rwgpu_join_collect_out(rwgpu_join* h, rwgpu_out** out) {
     const int64_t from = pre_ok ? n : 0;  // rows [0, n) of the non-aliased columns are already on their way
     const int64_t ops_from = h->call_had_deletes ? 0 : from;  // (the no-op elimination pass may have rewritten ops)
     if (total > ops_from)
-      cudaMemcpyAsync(o->ops + ops_from, h->os().out_ops.as<uint8_t>() + ops_from, (size_t)(total - ops_from), cudaMemcpyDeviceToHost, h->s_d2h);
+      cudaMemcpyAsync(o->ops + ops_from, h->os().out_ops.as<uint8_t>() + ops_from, (size_t)(total - ops_from), cudaMemcpyDeviceToHost, sd);
     for (size_t k = 0; k < h->out_types.size(); k++) {
       const size_t w = type_width(h->out_types[k]);
       if (hp.alias_src[k] >= 0) {
         if (aligned) o->data[k] = (uint8_t*)const_cast<void*>(hp.in_cols[(size_t)hp.alias_src[k]].data);  // zero-copy
-        else cudaMemcpyAsync(o->data[k], h->os().out_col[k].p, (size_t)total * w, cudaMemcpyDeviceToHost, h->s_d2h);
+        else cudaMemcpyAsync(o->data[k], h->os().out_col[k].p, (size_t)total * w, cudaMemcpyDeviceToHost, sd);
       } else if (total > from) {
         cudaMemcpyAsync(o->data[k] + (size_t)from * w, h->os().out_col[k].as<uint8_t>() + (size_t)from * w, (size_t)(total - from) * w,
-                        cudaMemcpyDeviceToHost, h->s_d2h);
+                        cudaMemcpyDeviceToHost, sd);
       }
     }
-    if (nullm >> 63) cudaMemcpyAsync(o->vis_bytes, h->os().out_vis.p, (size_t)total, cudaMemcpyDeviceToHost, h->s_d2h);
+    if (nullm >> 63) cudaMemcpyAsync(o->vis_bytes, h->os().out_vis.p, (size_t)total, cudaMemcpyDeviceToHost, sd);
     for (size_t k = 0; k < h->out_types.size(); k++)
-      if ((nullm >> k) & 1) cudaMemcpyAsync(o->valid_bytes[k], h->os().out_valid[k].p, (size_t)total, cudaMemcpyDeviceToHost, h->s_d2h);
+      if ((nullm >> k) & 1) cudaMemcpyAsync(o->valid_bytes[k], h->os().out_valid[k].p, (size_t)total, cudaMemcpyDeviceToHost, sd);
   }
-  RW_CUDA(cudaStreamSynchronize(h->s_d2h));
+  RW_CUDA(cudaStreamSynchronize(sd));
   o->n_rows = total;
   if (!(nullm >> 63)) o->vis_bytes = nullptr;
   for (size_t k = 0; k < h->out_types.size(); k++)
