@@ -1464,11 +1464,15 @@ struct NoopScratch {
   uint8_t* elig;  // the edge (row, nxt[row]) is an eliminable pair
 };
 
-__device__ __forceinline__ bool out_rows_equal(const JoinOutDev& o, const JoinPlanDev* p, int64_t a, int64_t b) {
-  for (int k = 0; k < p->n_out; k++) {
-    const bool na = o.valid[k][a] == 0, nb = o.valid[k][b] == 0;
-    if (na != nb) return false;
-    if (na) continue;
+// (null_cols: bit k = output column k holds NULLs in this call -- the validity bytes of the others are all 1 and are not
+// read; columns are compared from the last one: in a retraction pair the update side's payload differs first)
+__device__ __forceinline__ bool out_rows_equal(const JoinOutDev& o, const JoinPlanDev* p, int64_t a, int64_t b, unsigned long long null_cols) {
+  for (int k = p->n_out - 1; k >= 0; k--) {
+    if ((null_cols >> k) & 1ull) {
+      const bool na = o.valid[k][a] == 0, nb = o.valid[k][b] == 0;
+      if (na != nb) return false;
+      if (na) continue;
+    }
     const int w = p->out_width[k];
     const uint8_t* x = (const uint8_t*)o.col[k] + a * w;
     const uint8_t* y = (const uint8_t*)o.col[k] + b * w;
@@ -1493,10 +1497,14 @@ __device__ __forceinline__ bool out_rows_equal(const JoinOutDev& o, const JoinPl
   return true;
 }
 
-__global__ void noop_edges_kernel(JoinOutDev o, const JoinPlanDev* __restrict__ p, int64_t n, int chunk_size, NoopScratch sc) {
+// flag[0] = something was hidden, flag[1] = some edge is eligible (the two passes behind this one exit at once otherwise)
+__global__ void noop_edges_kernel(JoinOutDev o, const JoinPlanDev* __restrict__ p, int64_t n, int chunk_size, NoopScratch sc, unsigned long long null_cols,
+                                  unsigned int* flag) {
+  bool any = false;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     sc.elig[i] = 0;
     sc.nxt[i] = -1;
+    sc.prv[i] = -1;
     if (!o.vis[i]) continue;
     int64_t end = (i / chunk_size + 1) * (int64_t)chunk_size;
     if (end > n) end = n;
@@ -1506,17 +1514,19 @@ __global__ void noop_edges_kernel(JoinOutDev o, const JoinPlanDev* __restrict__ 
     sc.nxt[i] = (int32_t)j;
     const uint8_t a = o.ops[i], b = o.ops[j];
     const bool a_del = a == RW_OP_DELETE || a == RW_OP_UPDATE_DELETE, b_del = b == RW_OP_DELETE || b == RW_OP_UPDATE_DELETE;
-    if (a_del != b_del && out_rows_equal(o, p, i, j)) sc.elig[i] = 1;
+    if (a_del != b_del && out_rows_equal(o, p, i, j, null_cols)) { sc.elig[i] = 1; any = true; }
   }
+  if (any) flag[1] = 1u;
 }
-__global__ void noop_prev_kernel(int64_t n, int chunk_size, NoopScratch sc) {
+__global__ void noop_prev_kernel(int64_t n, int chunk_size, NoopScratch sc, const unsigned int* flag) {
+  if (*(volatile const unsigned int*)(flag + 1) == 0u) return;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    if (i % chunk_size == 0 || sc.nxt[i] < 0) { /* filled below by the predecessor, or none */ }
     const int32_t j = sc.nxt[i];
     if (j >= 0) sc.prv[j] = (int32_t)i;
   }
 }
 __global__ void noop_take_kernel(JoinOutDev o, int64_t n, NoopScratch sc, unsigned int* hid) {
+  if (*(volatile unsigned int*)(hid + 1) == 0u) return;
   bool any = false;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     if (!sc.elig[i]) continue;
@@ -1530,7 +1540,8 @@ __global__ void noop_take_kernel(JoinOutDev o, int64_t n, NoopScratch sc, unsign
   if (any) *hid = 1u;
 }
 // "Normalize update pairs that became partially invisible" (stream_chunk.rs:377-389)
-__global__ void noop_normalize_kernel(JoinOutDev o, int64_t n, int chunk_size) {
+__global__ void noop_normalize_kernel(JoinOutDev o, int64_t n, int chunk_size, const unsigned int* hid) {
+  if (*(volatile const unsigned int*)hid == 0u) return;  // nothing was hidden: no pair lost a half
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i + 1 < n; i += (int64_t)gridDim.x * blockDim.x) {
     if ((i + 1) % chunk_size == 0) continue;  // the pair would straddle two chunks
     if (o.ops[i] == RW_OP_UPDATE_DELETE && o.ops[i + 1] == RW_OP_UPDATE_INSERT) {
@@ -2629,18 +2640,19 @@ static int join_eliminate_noop(rwgpu_join* h, int64_t n, bool vis_valid, cudaStr
     RW_CUDA(h->noop_flag.reserve(8));
     h->noop_cap = cap;
   }
-  RW_CUDA(cudaMemsetAsync(h->noop_flag.p, 0, 4, st));
+  RW_CUDA(cudaMemsetAsync(h->noop_flag.p, 0, 8, st));
   if (!vis_valid) RW_CUDA(cudaMemsetAsync(h->os().out_vis.p, 1, (size_t)n, st));
   NoopScratch sc;
   sc.nxt = h->noop_nxt.as<int32_t>();
   sc.prv = h->noop_prv.as<int32_t>();
   sc.elig = h->noop_elig.as<uint8_t>();
-  RW_CUDA(cudaMemsetAsync(sc.prv, 0xff, (size_t)n * 4, st));
   const int g = jgrid(n, 256);
-  noop_edges_kernel<<<g, 256, 0, st>>>(out_dev(h), h->plan_dev.as<JoinPlanDev>(), n, h->chunk_size, sc);
-  noop_prev_kernel<<<g, 256, 0, st>>>(n, h->chunk_size, sc);
-  noop_take_kernel<<<g, 256, 0, st>>>(out_dev(h), n, sc, h->noop_flag.as<unsigned int>());
-  noop_normalize_kernel<<<g, 256, 0, st>>>(out_dev(h), n, h->chunk_size);
+  unsigned int* flag = h->noop_flag.as<unsigned int>();
+  const unsigned long long null_cols = h->call_null_mask & ((1ull << 63) - 1);
+  noop_edges_kernel<<<g, 256, 0, st>>>(out_dev(h), h->plan_dev.as<JoinPlanDev>(), n, h->chunk_size, sc, null_cols, flag);
+  noop_prev_kernel<<<g, 256, 0, st>>>(n, h->chunk_size, sc, flag);
+  noop_take_kernel<<<g, 256, 0, st>>>(out_dev(h), n, sc, flag);
+  noop_normalize_kernel<<<g, 256, 0, st>>>(out_dev(h), n, h->chunk_size, flag);
   RW_CUDA(cudaGetLastError());
   h->launches += 4;
   unsigned int hid = 0;  // did the pass hide anything ?

@@ -297,7 +297,7 @@ def test_join_push_device_counted_matches_exact_chunk(cuda):
         if view.vis_ptr is None:
             return np.ones(got[0], bool)
         words = torch.empty((got[0] + 63) // 64, dtype=torch.int64, device="cuda")
-        device.cudart().cudaMemcpy(C.c_void_p(words.data_ptr()), C.c_void_p(view.vis_ptr), C.c_size_t(words.numel() * 8), 3)
+        device._d2d(words.data_ptr(), view.vis_ptr, words.numel() * 8)
         bits = np.unpackbits(words.cpu().numpy().view(np.uint8), bitorder="little")[:got[0]]
         return bits.astype(bool)
     ma, mb = visible(va, got_a), visible(vb, got_b)
