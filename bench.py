@@ -470,7 +470,8 @@ def run_ours(args):
         return HashJoinExecutor(be, abi.JOIN_INNER, sl.into_executor(T4, [1]), sr.into_executor(T4, [0]),
                                 JoinParams([0], [1]), JoinParams([0], []), [False],
                                 capacity_hint=(N_BUILD, N_BUILD),  # distinct auction ids per GPU, both sides
-                                stored_rows_hint=(int((K + W + V + 4) * BATCH * 1.12), 0))  # bids this GPU will store (its share: ~BATCH per step)
+                                stored_rows_hint=(int((K + W + V + 4) * BATCH * 1.12) + 6 * world * BATCH, 0))  # bids this GPU will store (its share:
+        # ~BATCH per step) + the upper bounds of the pushes in flight (a counted push reserves for its buffer's capacity)
         # (the bid side is sized for the run: at 6 G rows/s it grows by ~290 GB/s, three times faster than cudaMalloc hands
         #  out memory -- 200 MB in 1.5-2 ms; a helper thread keeps one 200 MB segment ahead for streams that grow at a
         #  realistic rate)
