@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) agg_mm_delete_kernel(AggTable t, AggPlanD
 // serialised in one L2 slice -- ~8 K same-address atomics per 2^18-row epoch at one per ~7 cycles were the
 // kernel's whole duration.
 template <int NCALLS>
-__global__ void __launch_bounds__(256, 4) agg_apply_fast_kernel(AggTable t, AggPlanDev p, DevChunk ch) {  // (4: a 2^18-row epoch is ONE wave)
+__global__ void __launch_bounds__(256) agg_apply_fast_kernel(AggTable t, AggPlanDev p, DevChunk ch) {
   __shared__ unsigned int s_warp[8];
   __shared__ unsigned int s_base;
   unsigned int created_local = 0;
@@ -368,56 +368,19 @@ __global__ void __launch_bounds__(256, 4) agg_apply_fast_kernel(AggTable t, AggP
         for (int c = 0; c < NCALLS; c++)
           if (p.arg_col[c] >= 0) { a[c][0] = ((const long long*)ch.cols[p.arg_col[c]].data)[r0]; a[c][1] = 0; }
       }
-      // The two rows of a thread advance TOGETHER: both home-slot loads are in flight before either is looked at, then
-      // both dirty words, then both first-touch atomics, then all state atomics (only the sums' return values are
-      // waited for, after every atomic has been issued).  Row after row, the chain of dependent L2 round trips was
-      // twice as long -- and this single-wave kernel's duration IS that chain (r2b ncu: 21 us at 10 % SM, 42 % occupancy).
-      const uint64_t tmask = t.cap - 1;
-      uint64_t idx[2];
-      unsigned long long cur[2] = {0ull, 0ull};
-      bool live[2], special[2];
 #pragma unroll
       for (int j = 0; j < 2; j++) {
-        live[j] = op[j] != 0;
-        special[j] = (uint64_t)k[j] == AGG_EMPTY;
-        idx[j] = mix64((uint64_t)k[j]) & tmask;
-        if (live[j] && !special[j]) cur[j] = __ldcg((const unsigned long long*)(t.hot + idx[j] * p.HW));
-      }
-#pragma unroll
-      for (int j = 0; j < 2; j++) {
-        if (!live[j]) continue;
-        if (special[j]) { slot[j] = t.cap + 1; continue; }
+        if (op[j] == 0) continue;
         bool created = false;
-        while (true) {  // (the first probe's value is already here)
-          unsigned long long* hp = (unsigned long long*)(t.hot + idx[j] * p.HW);
-          if (cur[j] == (unsigned long long)k[j]) break;
-          if (cur[j] == AGG_EMPTY) {
-            const unsigned long long old = atomicCAS(hp, (unsigned long long)AGG_EMPTY, (unsigned long long)k[j]);
-            if (old == AGG_EMPTY) { created = true; break; }
-            if (old == (unsigned long long)k[j]) break;
-          }
-          idx[j] = (idx[j] + 1) & tmask;
-          cur[j] = __ldcg((const unsigned long long*)(t.hot + idx[j] * p.HW));
-        }
+        const uint64_t sl = ((uint64_t)k[j] == AGG_EMPTY) ? t.cap + 1 : find_or_insert_single(t, p.HW, (uint64_t)k[j], &created);
         if (created) created_local++;
-        slot[j] = idx[j];
-      }
-      // first touch of the group in this epoch ?
-      uint32_t dwv[2] = {0xffffffffu, 0xffffffffu}, bit[2] = {0u, 0u};
-#pragma unroll
-      for (int j = 0; j < 2; j++)
-        if (live[j]) { bit[j] = 1u << (slot[j] & 31); dwv[j] = __ldcg(t.dirty + (slot[j] >> 5)); }
-      uint32_t oldw[2] = {0xffffffffu, 0xffffffffu};
-#pragma unroll
-      for (int j = 0; j < 2; j++)
-        if (live[j] && !(dwv[j] & bit[j])) oldw[j] = atomicOr(t.dirty + (slot[j] >> 5), bit[j]);
-      // state atomics of both rows; the sums' old values are consumed after everything has been issued
-      unsigned long long sum_old[NCALLS][2], sum_add[NCALLS][2];
-      bool sum_neg[NCALLS][2];
-#pragma unroll
-      for (int j = 0; j < 2; j++) {
-        if (!live[j]) continue;
-        unsigned long long* sp = (unsigned long long*)(t.hot + slot[j] * p.HW + 1);
+        slot[j] = sl;
+        {  // first touch of the group in this epoch ?
+          const uint32_t bit = 1u << (sl & 31);
+          uint32_t* dw = t.dirty + (sl >> 5);
+          if (!(__ldcg(dw) & bit)) first[j] = !(atomicOr(dw, bit) & bit);
+        }
+        unsigned long long* sp = (unsigned long long*)(t.hot + sl * p.HW + 1);
         const bool retract = (op[j] == RW_OP_DELETE || op[j] == RW_OP_UPDATE_DELETE);
 #pragma unroll
         for (int c = 0; c < NCALLS; c++) {
@@ -425,27 +388,16 @@ __global__ void __launch_bounds__(256, 4) agg_apply_fast_kernel(AggTable t, AggP
           if (kind == RW_AGG_COUNT) {
             atomicAdd(sp + c, retract ? ~0ull : 1ull);
           } else if (kind == RW_AGG_SUM || kind == RW_AGG_SUM0) {
-            const long long x = a[c][j];
-            sum_add[c][j] = retract ? (0ull - (unsigned long long)x) : (unsigned long long)x;
-            sum_neg[c][j] = retract ? (x > 0) : (x < 0);
-            sum_old[c][j] = atomicAdd(sp + c, sum_add[c][j]);
+            long long x = a[c][j];
+            unsigned long long add = retract ? (0ull - (unsigned long long)x) : (unsigned long long)x;
+            bool neg = retract ? (x > 0) : (x < 0);
+            unsigned long long old = atomicAdd(sp + c, add);
+            unsigned long long nw = old + add;
+            long long hd = (neg ? -1ll : 0ll) + ((nw < old) ? 1ll : 0ll);
+            if (hd != 0) atomicAdd((unsigned long long*)(t.cold + sl * p.CW + p.hi_off[c]), (unsigned long long)hd);
           } else {
             if (op[j] != RW_OP_INSERT) { atomicOr(&t.status->err, AGG_ERR_RETRACT_APPEND_ONLY); continue; }
             if (kind == RW_AGG_MIN) atomicMin((long long*)(sp + c), a[c][j]); else atomicMax((long long*)(sp + c), a[c][j]);
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 2; j++) {
-        if (!live[j]) continue;
-        first[j] = (oldw[j] & bit[j]) == 0u;
-#pragma unroll
-        for (int c = 0; c < NCALLS; c++) {
-          const int kind = p.kind[c];
-          if (kind == RW_AGG_SUM || kind == RW_AGG_SUM0) {  // carry / borrow into the high word (exact 128-bit sums)
-            const unsigned long long nw = sum_old[c][j] + sum_add[c][j];
-            const long long hd = (sum_neg[c][j] ? -1ll : 0ll) + ((nw < sum_old[c][j]) ? 1ll : 0ll);
-            if (hd != 0) atomicAdd((unsigned long long*)(t.cold + slot[j] * p.CW + p.hi_off[c]), (unsigned long long)hd);
           }
         }
       }
