@@ -693,7 +693,7 @@ def run_ours(args):
             # `expires`) probe the bid side -- every matched bid is emitted twice (- then +), the first time multi-match
             # emission, the own-side delete kernel and re-insertion are timed.  Step = 2^19 pairs = 2^20 rows.
             if "retract" in legs and world == 1:
-                RP, KR, WR = 1 << 19, 4, 1
+                RP, KR, WR = 1 << 19, 8, 2  # (2 warm-up steps: each output set grows once to hold ~3 output rows per input row)
                 ups = [gen_auction_updates(auct, s * RP, RP) for s in range(WR + KR + 1)]  # (+1: verification step)
                 ups_dev = [device.DeviceChunk(torch.from_numpy(o).cuda(), to_dev(c), T4) for o, c in ups]
                 torch.cuda.synchronize()
