@@ -27,6 +27,8 @@ RWGPU_EXCHANGE=nccl selects partition + NCCL all-to-all-v instead.
 single-threaded actor per host core, inputs pre-partitioned by vnode) on a bounded sample.
 """
 import argparse
+import contextlib
+import io
 import ctypes as C
 import json
 import os
@@ -1240,10 +1242,29 @@ def main():
                     help="comma list of: value,retract,hot,e2e,agg,q1,chain,generic,cpu (subset for ncu runs; retract needs value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE line (the JSON): everything a library prints there on its own (NCCL's "NCCL version ..."
+    # banner at communicator creation, for one) is sent to stderr for the duration of the run
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(out):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    lines = [ln for ln in out.getvalue().splitlines() if ln.strip()]
+    json_lines = [ln for ln in lines if ln.lstrip().startswith("{")]
+    for ln in lines:
+        if ln not in json_lines:
+            print(ln, file=sys.stderr)
+    if json_lines:
+        print(json_lines[-1], flush=True)
 
 
 if __name__ == "__main__":
