@@ -389,7 +389,7 @@ int32_t rwgpu_shuffle_exchange_p2p_device(const rw_chunk* chunk, const int32_t* 
                                           uint8_t* out_ops, void* const* out_cols, int64_t* counts,
                                           int32_t* overflow, int64_t* total_host, void* cuda_stream);
 
-/* ---- the exchange as ONE cooperative kernel, rows stored straight into their final place ------------------
+/* ---- the exchange as ONE kernel, rows stored straight into their final place ------------------
  * Flat receive buffer (symmetric, peer-mapped, two alternate): [header: int64 M[64][64], M[s][d] = rows source s sends
  * to destination d][ops: cap_rows bytes][column k: cap_rows * width_k], parts 256-B aligned (rwgpu_shuffle_flat_layout
  * returns the offsets).  One launch per batch: per-block histograms -> scan -> every source writes its count row into

@@ -2185,7 +2185,7 @@ static int uni_tail_grid(int64_t n) {
     int a = 0, b = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, uni_tail_kernel<false>, 256, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, uni_tail_kernel<true>, 256, 0);
-    per_sm = std::max(1, std::min(std::min(a, b), 4));
+    per_sm = std::max(1, std::min(std::min(a, b), 2));  // (two per SM: fits next to the exchange kernel, shuffle.cu)
     max_blocks = std::max(1, sms * per_sm);
   }
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, max_blocks));

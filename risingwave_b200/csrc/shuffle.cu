@@ -436,7 +436,7 @@ __global__ void p2p_total_to_host_kernel(const int64_t* total, int64_t* total_ho
   __threadfence_system();
 }
 
-// ------------------------------------------------------------------ fused exchange: ONE cooperative kernel per batch
+// ------------------------------------------------------------------ fused exchange: ONE kernel per batch
 // Flat receive buffer of a rank (symmetric on every rank, two of them alternate):
 //   [ header: int64 M[PART_MAX_DEST][PART_MAX_DEST], M[s][d] = rows source s sends to destination d in this batch ]
 //   [ ops: cap bytes ][ column k: cap * width_k bytes ]                      (each part 256-byte aligned)
@@ -446,7 +446,7 @@ __global__ void p2p_total_to_host_kernel(const int64_t* total, int64_t* total_ho
 // so the scatter stores the rows over NVLink straight into their FINAL, contiguous place (source-rank order, row order
 // kept inside a source): nothing is unpacked on the receiving side, the consumer reads the buffer as it is.  A second
 // barrier tells every rank that its buffer is complete.  hist -> scan -> publish -> barrier -> scatter -> barrier are the
-// phases of one cooperative launch (grid-wide syncs in between), replacing six launches and the unpack copy.
+// phases of one launch (grid-wide barriers in between, see soft_grid_sync), replacing six launches and the unpack copy.
 struct FlatLayout {
   int64_t cap;  // rows a buffer can hold (the caller sizes it for world x batch rows: every batch fits)
   int64_t ops_off;
@@ -494,12 +494,26 @@ __device__ __forceinline__ void flat_barrier(const PeerBases& flags, int n, int 
   }
 }
 
+// grid-wide barrier of a PLAIN launch whose grid is sized to be resident (flat_exchange_kernel): `bar` counts arrivals
+// and is never reset inside a launch -- barrier number k (1, 2, ...) waits for k * gridDim.x.  A cooperative launch
+// (grid.sync()) cost ~20 us more per launch on the join's tail kernel and cannot start before EVERY block fits; this
+// one starts with the blocks that fit and the rest follow as a neighbour kernel drains.
+__device__ __forceinline__ void soft_grid_sync(unsigned int* bar, unsigned int k) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned int target = k * gridDim.x;
+    while (*(volatile unsigned int*)bar < target) __nanosleep(32);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(PART_BLOCK) flat_exchange_kernel(DevChunk ch, VnodePlan p, const int32_t* vnode_to_dest, int n_dest, int my_rank,
                                                                     FlatLayout L, PeerBases peers, PeerBases flags, unsigned long long epoch,
                                                                     uint8_t* dest, uint32_t* block_hist, int n_vblocks, int64_t* counts,
-                                                                    int64_t* total_dev, int64_t* total_host, int* err) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+                                                                    int64_t* total_dev, int64_t* total_host, int* err, unsigned int* bar) {
   __shared__ uint32_t tab[256];
   __shared__ uint32_t hist[PART_MAX_DEST];
   __shared__ uint32_t run[PART_MAX_DEST];
@@ -527,7 +541,7 @@ __global__ void __launch_bounds__(PART_BLOCK) flat_exchange_kernel(DevChunk ch, 
     if (threadIdx.x < n_dest) block_hist[(size_t)vb * n_dest + threadIdx.x] = hist[threadIdx.x];
     __syncthreads();
   }
-  grid.sync();
+  soft_grid_sync(bar, 1u);
   // ---- phase B (block 0): exclusive scan over the blocks per destination, count row to every rank, barrier 1
   if (blockIdx.x == 0) {
     for (int d = wid; d < n_dest; d += PART_BLOCK / 32) {
@@ -555,7 +569,7 @@ __global__ void __launch_bounds__(PART_BLOCK) flat_exchange_kernel(DevChunk ch, 
     __syncthreads();
     flat_barrier(flags, n_dest, my_rank, 2ull * epoch - 1ull, err);
   }
-  grid.sync();
+  soft_grid_sync(bar, 2u);
   // ---- phase C: stable scatter into the final place
   {
     const volatile int64_t* M = (const volatile int64_t*)peers.base[my_rank];
@@ -615,7 +629,7 @@ __global__ void __launch_bounds__(PART_BLOCK) flat_exchange_kernel(DevChunk ch, 
     }
   }
   __threadfence_system();
-  grid.sync();
+  soft_grid_sync(bar, 3u);
   // ---- phase D (block 0): barrier 2, then the received row count for the consumer
   if (blockIdx.x == 0) {
     flat_barrier(flags, n_dest, my_rank, 2ull * epoch, err);
@@ -938,21 +952,23 @@ int32_t rwgpu_shuffle_exchange_flat_device(const rw_chunk* c, const int32_t* key
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_exchange_kernel, PART_BLOCK, 0);
-    coresident = std::max(1, sms * std::max(1, std::min(per_sm, 4)));
+    // two blocks per SM: this kernel and the join's tail kernel (the other one that may spin in a grid-wide barrier) always
+    // fit on the device TOGETHER, so neither can hold SMs the other one is waiting for
+    coresident = std::max(1, sms * std::max(1, std::min(per_sm, 2)));
   }
   int grid = std::min(n_vblocks, coresident);
   if (max_blocks > 0) grid = std::min(grid, (int)max_blocks);
   uint8_t* scratch = nullptr;
   size_t dest_bytes = ((size_t)c->n_rows + 255) / 256 * 256;
   size_t hist_bytes = (size_t)n_vblocks * n_dest * 4;
-  RW_CUDA(cudaMallocAsync((void**)&scratch, dest_bytes + hist_bytes + 256, st));
+  RW_CUDA(cudaMallocAsync((void**)&scratch, dest_bytes + hist_bytes + 512, st));
   uint8_t* dest = scratch;
   uint32_t* hist = (uint32_t*)(scratch + dest_bytes);
-  unsigned long long ep = epoch;
-  int* errp = (int*)err;
-  void* args[] = {(void*)&ch, (void*)&p, (void*)&vnode_to_dest, (void*)&n_dest, (void*)&my_rank, (void*)&L, (void*)&pb, (void*)&pf, (void*)&ep,
-                  (void*)&dest, (void*)&hist, (void*)&n_vblocks, (void*)&counts, (void*)&total_dev, (void*)&total_host, (void*)&errp};
-  RW_CUDA(cudaLaunchCooperativeKernel((const void*)flat_exchange_kernel, dim3(grid), dim3(PART_BLOCK), args, 0, st));
+  unsigned int* bar = (unsigned int*)(scratch + dest_bytes + (hist_bytes + 255) / 256 * 256);
+  RW_CUDA(cudaMemsetAsync(bar, 0, 4, st));
+  flat_exchange_kernel<<<grid, PART_BLOCK, 0, st>>>(ch, p, vnode_to_dest, n_dest, my_rank, L, pb, pf, (unsigned long long)epoch, dest, hist, n_vblocks,
+                                                    counts, total_dev, total_host, (int*)err, bar);
+  RW_CUDA(cudaGetLastError());
   RW_CUDA(cudaFreeAsync(scratch, st));
   return RW_OK;
 }
