@@ -503,7 +503,7 @@ def run_ours(args):
             ex_name = "crc32 vnode partition kernel storing straight into the peers' receive regions over NVLink (symmetric memory), device barrier, unpack kernel"
         else:
             ex_plan = exchange.FlatShufflePlan(world, rank, key_indices=[0], types=T4, batch_rows=BATCH)
-            ex_name = ("one cooperative kernel per batch: crc32 vnode histograms, scan, count exchange + cross-rank barrier, scatter over NVLink "
+            ex_name = ("one kernel per batch: crc32 vnode histograms, scan, count exchange + cross-rank barrier, scatter over NVLink "
                        "(symmetric memory) into the rows' final place in the destination's receive buffer, barrier; the join reads the buffer in place")
 
     def shuffled(cols_dev):

@@ -361,7 +361,7 @@ def flat_layout(types: Sequence[int], cap_rows: int):
 
 class FlatExchangeCall:
     """Pre-built argument block of rwgpu_shuffle_exchange_flat_device for one receive-buffer parity (one ctypes call per
-    batch: partition, peer stores, both barriers and the row count are one cooperative kernel)."""
+    batch: partition, peer stores, both barriers and the row count are one kernel)."""
 
     def __init__(self, key_indices, vnode_to_dest, n_dest, my_rank, peer_ptrs, flag_ptrs, cap_rows, counts, err, total_dev_ptr,
                  total_host, vnode_count=256, max_blocks=0):

@@ -185,7 +185,7 @@ class P2PShufflePlan:
 
 
 class FlatShufflePlan:
-    """The N-GPU hash shuffle as ONE cooperative kernel per batch (rwgpu_shuffle_exchange_flat_device): histograms,
+    """The N-GPU hash shuffle as ONE kernel per batch (rwgpu_shuffle_exchange_flat_device): histograms,
     scan, count exchange, cross-rank barrier, scatter over NVLink straight into the rows' FINAL place in the
     destination's receive buffer, second barrier, row count -- no NCCL call, no unpack copy; the consumer (the join's
     counted push) reads the receive buffer in place and the row count on the device.

@@ -370,7 +370,7 @@ def test_flat_exchange_self_peer_feeds_counted_join(cuda, oracle):
 
 
 def test_flat_exchange_virtual_ranks(cuda, oracle):
-    """flat_exchange_kernel with W virtual ranks on ONE device, one stream per rank, the W cooperative kernels running side
+    """flat_exchange_kernel with W virtual ranks on ONE device, one stream per rank, the W kernels running side
     by side (grids capped so they are co-resident) and meeting in the kernel's own cross-rank barriers: every receive buffer
     must hold the numpy stable partition, sources concatenated in rank order, with no gaps.  Two batches, so the second
     one reuses the flags with larger barrier values."""
@@ -406,7 +406,7 @@ def test_flat_exchange_virtual_ranks(cuda, oracle):
             torch.cuda.synchronize()
             errs = [int(state[r]["err"].item()) for r in range(world)]
             if any(e & 2 for e in errs):
-                pytest.skip("this device did not run the ranks' cooperative kernels side by side (barrier timed out)")
+                pytest.skip("this device did not run the ranks' kernels side by side (barrier timed out)")
             assert errs == [0] * world
             for d in range(world):
                 w_ops, w_cols = [], [[] for _ in types]
