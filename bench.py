@@ -1256,6 +1256,10 @@ def main():
                 run_ours(args)
     finally:
         sys.stdout.flush()
+        try:
+            C.CDLL(None).fflush(None)  # C stdio buffers too (NCCL printf()s its banner: it would surface at exit)
+        except Exception:
+            pass
         os.dup2(real_stdout, 1)
         os.close(real_stdout)
     lines = [ln for ln in out.getvalue().splitlines() if ln.strip()]
