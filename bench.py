@@ -1032,9 +1032,13 @@ def run_ours(args):
             pos_of = np.empty(NG, np.int64)
             pos_of[ag[0]] = np.arange(NG)
             matched = vb[0] < NG
-            ok = vv.n_rows == BG
+            vis_v = vv.visible()  # (the generic path's output has invisible rows: it is not compacted)
+            keep_v = None if vis_v is None else vis_v.cpu().numpy()
+            got = [vv.column(k).cpu().numpy() for k in range(8)]
+            if keep_v is not None:
+                got = [g[keep_v] for g in got]
+            ok = len(got[0]) == BG
             if ok:
-                got = [vv.column(k).cpu().numpy() for k in range(8)]
                 order_g = np.argsort(got[1], kind="stable")  # date_time is unique: aligns output rows with input rows
                 order_w = np.argsort(vb[1], kind="stable")
                 for k in range(4):

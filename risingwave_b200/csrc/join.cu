@@ -2175,7 +2175,7 @@ static int join_order(rwgpu_join* h, cudaStream_t st) {
   return RW_OK;
 }
 
-// grid of the tail kernel: every block resident at once (its rare grid-wide barrier relies on it), no more than the rows need
+// grid of the tail kernel: about one wave, no more than the rows need
 static int uni_tail_grid(int64_t n) {
   static int max_blocks = 0;
   if (!max_blocks) {
@@ -2185,7 +2185,7 @@ static int uni_tail_grid(int64_t n) {
     int a = 0, b = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, uni_tail_kernel<false>, 256, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, uni_tail_kernel<true>, 256, 0);
-    per_sm = std::max(1, std::min(std::min(a, b), 2));  // (two per SM: fits next to the exchange kernel, shuffle.cu)
+    per_sm = std::max(1, std::min(std::min(a, b), 3));
     max_blocks = std::max(1, sms * per_sm);
   }
   return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, max_blocks));

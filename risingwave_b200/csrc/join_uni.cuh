@@ -694,18 +694,22 @@ __device__ __forceinline__ bool uni_pk_equal(const JoinPlanDev* p, int S, const 
 // status block).  Sequential rule: the delete at chunk position r removes the live row with equal pk that
 // arrived most recently BEFORE r: rows this very chunk inserted at positions >= r are excluded by their 64-bit
 // arrival number (seq_base .. seq_base + n), every other live pk-equal row is older; the newest wins.
+// sentinel_mode: 0 = every delete row; 1 = all but the rows whose key is the EMPTY sentinel; 2 = only those, by ONE block
 __device__ __forceinline__ void uni_delete_body(const JoinPlanDev* __restrict__ p, int S, const DevChunk& ch, const UniDev& t, JoinStatus* st,
-                                                uint64_t seq_base) {
+                                                uint64_t seq_base, int sentinel_mode) {
   const int64_t n_rows = chunk_rows(ch, st, false);
   const uint64_t SEQ56 = (1ull << 56) - 1;
   unsigned int dead_log = 0;
-  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n_rows; r += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t r_first = sentinel_mode == 2 ? (int64_t)threadIdx.x : blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t r_step = sentinel_mode == 2 ? (int64_t)blockDim.x : (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r = r_first; r < n_rows; r += r_step) {
     const uint8_t op = ch.ops[r];
     if (!row_visible(ch, r, op) || !(op == RW_OP_DELETE || op == RW_OP_UPDATE_DELETE)) continue;
     const ColRef& kc = ch.cols[p->key_col[S][0]];
     const bool knull = col_is_null(kc, r);
     if (knull && !p->null_safe[0]) continue;  // never-match rows were never stored
     const uint64_t key = knull ? 0ull : ((const uint64_t*)kc.data)[r];
+    if (sentinel_mode && ((!knull && key == J_EMPTY) != (sentinel_mode == 2))) continue;
     const int64_t b = uni_find(t, key, knull);
     bool found = false;
     while (b >= 0 && !found) {
@@ -777,42 +781,39 @@ __device__ __forceinline__ void uni_delete_body(const JoinPlanDev* __restrict__ 
 // flagged no such rows (st->n_defer / st->n_del are final when this kernel starts: every block takes the same path).
 // The two phases are independent -- deferred emission reads the OTHER side's records, deletes change the OWN side's --
 // except for deferred WHOLE rows (the key equal to the EMPTY sentinel: their insert happens in phase 1 and a delete
-// later in the chunk may target it).  Only then (n_defer bit 1 and deletes in one batch) the blocks meet in a grid-wide
-// barrier between the phases; the host sizes the grid so that every block is resident (uni_tail_grid).
-// (r2c/r2d: as a cooperative launch this kernel cost ~35 us per step, two plain launches ~19 us.)
+// later in the chunk may target it).  When a batch has both (n_defer bit 1 and deletes), the deletes of sentinel-key
+// rows are left to the LAST block, which runs them after every other block has finished: no block ever waits for
+// another one, so the kernel needs no co-residency and no cooperative launch.
+// (r2b: separate deferred and delete launches ~9 us each; r2d: as a cooperative launch 37 us per step; plain: 15 us.)
 template <bool PROBE_ONLY>
 __global__ void __launch_bounds__(256) uni_tail_kernel(const JoinPlanDev* __restrict__ p, W8Plan w, int S, DevChunk ch, UniDev t, JoinOutDev o, UniWork wk,
                                                        JoinStatus* st, uint64_t seq_base, int64_t out_base, JoinStatus* status_host,
                                                        unsigned long long tag, int reset, unsigned int* done) {
+  __shared__ bool s_last;
   const unsigned long long defer_flags = *(volatile unsigned long long*)&st->n_defer;
   const bool has_del = !PROBE_ONLY && *(volatile unsigned long long*)&st->n_del != 0ull;
+  const bool split = has_del && (defer_flags & 2ull) != 0ull;
   if (defer_flags) uni_deferred_body<PROBE_ONLY>(p, w, S, ch, t, o, wk, st, seq_base, out_base);
-  if (has_del) {
-    if (defer_flags & 2ull) {  // software grid barrier (done[1]); reset by the publishing block below
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(done + 1, 1u);
-        while (*(volatile unsigned int*)(done + 1) < gridDim.x) __nanosleep(64);
-        __threadfence();
-      }
-      __syncthreads();
-    }
-    uni_delete_body(p, S, ch, t, st, seq_base);
-  }
-  // last block out publishes (every block's work is fenced before its ticket)
+  if (has_del) uni_delete_body(p, S, ch, t, st, seq_base, split ? 1 : 0);
+  // last block out: the sentinel-key deletes (if any were left), then the status block
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned int ticket = atomicAdd(done, 1u);
-    if (ticket == gridDim.x - 1) {
-      done[0] = 0u;
-      done[1] = 0u;
-      __threadfence();
-      st->log_next[0] = *(volatile unsigned long long*)t.log_next[0]; st->log_next[1] = *(volatile unsigned long long*)t.log_next[1];
-      st->n_dead[0] = *(volatile unsigned long long*)t.n_dead[0]; st->n_dead[1] = *(volatile unsigned long long*)t.n_dead[1];
-      join_status_publish(st, status_host, tag, reset);
-    }
+    s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (split) {
+    uni_delete_body(p, S, ch, t, st, seq_base, 2);
+    __threadfence();
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    done[0] = 0u;
+    st->log_next[0] = *(volatile unsigned long long*)t.log_next[0]; st->log_next[1] = *(volatile unsigned long long*)t.log_next[1];
+    st->n_dead[0] = *(volatile unsigned long long*)t.n_dead[0]; st->n_dead[1] = *(volatile unsigned long long*)t.n_dead[1];
+    join_status_publish(st, status_host, tag, reset);
   }
 }
 

@@ -510,39 +510,59 @@ __device__ __forceinline__ void soft_grid_sync(unsigned int* bar, unsigned int k
   __syncthreads();
 }
 
+// STAGED (every column 8 bytes wide): a tile's rows are first partitioned into SHARED MEMORY (stable, destination by
+// destination) and then written out with consecutive threads storing consecutive rows of a destination's segment -- a
+// warp's store instruction covers 256 contiguous bytes of ONE peer instead of 8-byte pieces scattered over all of them
+// (r2 4-GPU run: the per-row peer stores sustained ~80 GB/s of NVLink's 900).  Otherwise rows go out one by one.
+#define FLAT_TILE 1024
+template <bool STAGED>
 __global__ void __launch_bounds__(PART_BLOCK) flat_exchange_kernel(DevChunk ch, VnodePlan p, const int32_t* vnode_to_dest, int n_dest, int my_rank,
                                                                     FlatLayout L, PeerBases peers, PeerBases flags, unsigned long long epoch,
-                                                                    uint8_t* dest, uint32_t* block_hist, int n_vblocks, int64_t* counts,
-                                                                    int64_t* total_dev, int64_t* total_host, int* err, unsigned int* bar) {
+                                                                    uint8_t* dest, uint32_t* block_hist, uint32_t* tile_cnt, int n_vblocks,
+                                                                    int64_t* counts, int64_t* total_dev, int64_t* total_host, int* err,
+                                                                    unsigned int* bar) {
+  extern __shared__ __align__(16) uint8_t s_stage[];  // STAGED: ops[FLAT_TILE] | col k: u64[FLAT_TILE]
   __shared__ uint32_t tab[256];
   __shared__ uint32_t hist[PART_MAX_DEST];
   __shared__ uint32_t run[PART_MAX_DEST];
   __shared__ uint32_t warp_cnt[PART_BLOCK / 32][PART_MAX_DEST];
-  __shared__ int64_t s_first[PART_MAX_DEST];  // first row of (me -> d) inside d's buffer
+  __shared__ uint32_t s_seg[PART_MAX_DEST + 1];  // STAGED: first staged row of destination d in this tile
+  __shared__ int64_t s_first[PART_MAX_DEST];     // first row of (me -> d) inside d's buffer
   const int lane = lane_id(), wid = threadIdx.x >> 5;
+  constexpr int ITERS = FLAT_TILE / PART_BLOCK;
   tab[threadIdx.x] = crc_table_entry(threadIdx.x);
-  // ---- phase A: destination per row + per-block histograms
+  // ---- phase A: destination per row + per-tile histograms
   for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {
     if (threadIdx.x < PART_MAX_DEST) hist[threadIdx.x] = 0;
     __syncthreads();
-    const int64_t base = (int64_t)vb * PART_ROWS_PER_BLOCK;
-    for (int i = threadIdx.x; i < PART_ROWS_PER_BLOCK; i += PART_BLOCK) {
-      const int64_t r = base + i;
-      if (r >= ch.n) break;
-      const uint8_t op = ch.ops[r];
-      uint8_t d = 255;
-      if (row_visible(ch, r, op)) {
-        d = (uint8_t)vnode_to_dest[row_vnode(tab, p, ch, r, true)];
-        atomicAdd(&hist[d], 1u);
+    const int64_t base = (int64_t)vb * FLAT_TILE;
+    uint8_t dv[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {  // (the tile's loads are independent: issued together)
+      const int64_t r = base + it * PART_BLOCK + threadIdx.x;
+      dv[it] = 255;
+      if (r < ch.n) {
+        const uint8_t op = ch.ops[r];
+        if (row_visible(ch, r, op)) dv[it] = (uint8_t)vnode_to_dest[row_vnode(tab, p, ch, r, true)];
       }
-      dest[r] = d;
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+      const int64_t r = base + it * PART_BLOCK + threadIdx.x;
+      if (r < ch.n) {
+        dest[r] = dv[it];
+        if (dv[it] != 255) atomicAdd(&hist[dv[it]], 1u);
+      }
     }
     __syncthreads();
-    if (threadIdx.x < n_dest) block_hist[(size_t)vb * n_dest + threadIdx.x] = hist[threadIdx.x];
+    if (threadIdx.x < n_dest) {
+      block_hist[(size_t)vb * n_dest + threadIdx.x] = hist[threadIdx.x];
+      tile_cnt[(size_t)vb * n_dest + threadIdx.x] = hist[threadIdx.x];
+    }
     __syncthreads();
   }
   soft_grid_sync(bar, 1u);
-  // ---- phase B (block 0): exclusive scan over the blocks per destination, count row to every rank, barrier 1
+  // ---- phase B (block 0): exclusive scan over the tiles per destination, count row to every rank, barrier 1
   if (blockIdx.x == 0) {
     for (int d = wid; d < n_dest; d += PART_BLOCK / 32) {
       uint32_t acc = 0;
@@ -580,11 +600,18 @@ __global__ void __launch_bounds__(PART_BLOCK) flat_exchange_kernel(DevChunk ch, 
     }
     __syncthreads();
   }
+  uint8_t* s_ops = s_stage;
+  unsigned long long* s_col = (unsigned long long*)(s_stage + FLAT_TILE);
   for (int vb = blockIdx.x; vb < n_vblocks; vb += gridDim.x) {
     if (threadIdx.x < PART_MAX_DEST) run[threadIdx.x] = 0;
+    if (STAGED && threadIdx.x == 0) {
+      uint32_t acc = 0;
+      for (int d = 0; d < n_dest; d++) { s_seg[d] = acc; acc += tile_cnt[(size_t)vb * n_dest + d]; }
+      s_seg[n_dest] = acc;
+    }
     __syncthreads();
-    const int64_t base = (int64_t)vb * PART_ROWS_PER_BLOCK;
-    for (int it = 0; it < PART_ROWS_PER_BLOCK / PART_BLOCK; it++) {
+    const int64_t base = (int64_t)vb * FLAT_TILE;
+    for (int it = 0; it < ITERS; it++) {
       const int64_t r = base + it * PART_BLOCK + threadIdx.x;
       const uint8_t d = (r < ch.n) ? dest[r] : 255;
       const unsigned peers_m = __match_any_sync(0xffffffffu, (unsigned)d);
@@ -606,26 +633,45 @@ __global__ void __launch_bounds__(PART_BLOCK) flat_exchange_kernel(DevChunk ch, 
         run[threadIdx.x] += tot;
       }
       if (d != 255) {
-        const int64_t dst = s_first[d] + (int64_t)block_hist[(size_t)vb * n_dest + d] + pos;
-        if (dst >= L.cap) {
-          atomicOr(err, 1);
+        if (STAGED) {
+          const uint32_t at = s_seg[d] + pos;
+          s_ops[at] = ch.ops[r];
+          for (int k = 0; k < ch.n_cols; k++) s_col[(size_t)k * FLAT_TILE + at] = ((const unsigned long long*)ch.cols[k].data)[r];
         } else {
-          uint8_t* buf = peers.base[d];
-          buf[L.ops_off + dst] = ch.ops[r];
-          for (int k = 0; k < ch.n_cols; k++) {
-            const ColRef& c = ch.cols[k];
-            uint8_t* col = buf + L.col_off[k];
-            switch (c.width) {
-              case 1: ((uint8_t*)col)[dst] = ((const uint8_t*)c.data)[r]; break;
-              case 2: ((uint16_t*)col)[dst] = ((const uint16_t*)c.data)[r]; break;
-              case 4: ((uint32_t*)col)[dst] = ((const uint32_t*)c.data)[r]; break;
-              case 8: ((uint64_t*)col)[dst] = ((const uint64_t*)c.data)[r]; break;
-              default: ((ulonglong2*)col)[dst] = ((const ulonglong2*)c.data)[r]; break;
+          const int64_t dst = s_first[d] + (int64_t)block_hist[(size_t)vb * n_dest + d] + pos;
+          if (dst >= L.cap) {
+            atomicOr(err, 1);
+          } else {
+            uint8_t* buf = peers.base[d];
+            buf[L.ops_off + dst] = ch.ops[r];
+            for (int k = 0; k < ch.n_cols; k++) {
+              const ColRef& c = ch.cols[k];
+              uint8_t* col = buf + L.col_off[k];
+              switch (c.width) {
+                case 1: ((uint8_t*)col)[dst] = ((const uint8_t*)c.data)[r]; break;
+                case 2: ((uint16_t*)col)[dst] = ((const uint16_t*)c.data)[r]; break;
+                case 4: ((uint32_t*)col)[dst] = ((const uint32_t*)c.data)[r]; break;
+                case 8: ((uint64_t*)col)[dst] = ((const uint64_t*)c.data)[r]; break;
+                default: ((ulonglong2*)col)[dst] = ((const ulonglong2*)c.data)[r]; break;
+              }
             }
           }
         }
       }
       __syncthreads();
+    }
+    if (STAGED) {  // write the staged tile out: consecutive threads, consecutive rows of a destination's segment
+      const uint32_t staged = s_seg[n_dest];
+      for (uint32_t i = threadIdx.x; i < staged; i += PART_BLOCK) {
+        int d = 0;
+        while (d + 1 < n_dest && i >= s_seg[d + 1]) d++;
+        const int64_t dst = s_first[d] + (int64_t)block_hist[(size_t)vb * n_dest + d] + (int64_t)(i - s_seg[d]);
+        if (dst >= L.cap) { atomicOr(err, 1); continue; }
+        uint8_t* buf = peers.base[d];
+        buf[L.ops_off + dst] = s_ops[i];
+        for (int k = 0; k < ch.n_cols; k++) ((unsigned long long*)(buf + L.col_off[k]))[dst] = s_col[(size_t)k * FLAT_TILE + i];
+      }
+      __syncthreads();  // the staging area is refilled by the next tile
     }
   }
   __threadfence_system();
@@ -945,29 +991,42 @@ int32_t rwgpu_shuffle_exchange_flat_device(const rw_chunk* c, const int32_t* key
   memset(&pf, 0, sizeof(pf));
   for (int d = 0; d < n_dest; d++) { pb.base[d] = (uint8_t*)peer_bases[d]; pf.base[d] = (uint8_t*)peer_flags[d]; }
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  int n_vblocks = (int)std::max<int64_t>(1, (c->n_rows + PART_ROWS_PER_BLOCK - 1) / PART_ROWS_PER_BLOCK);
-  static int coresident = 0;
-  if (!coresident) {
+  const int n_vblocks = (int)std::max<int64_t>(1, (c->n_rows + FLAT_TILE - 1) / FLAT_TILE);
+  bool staged = c->n_cols <= 12;
+  for (int k = 0; k < c->n_cols; k++) staged = staged && type_width(c->columns[k].type) == 8;
+  const size_t smem = staged ? (size_t)FLAT_TILE * (1 + 8 * (size_t)c->n_cols) : 0;
+  // every block resident at once (the grid-wide barriers rely on it): occupancy x SMs, at most 6 blocks per SM
+  static int coresident[2][13] = {{0}};
+  int& cores = coresident[staged ? 1 : 0][staged ? c->n_cols : 0];
+  if (!cores) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_exchange_kernel, PART_BLOCK, 0);
-    // two blocks per SM: this kernel and the join's tail kernel (the other one that may spin in a grid-wide barrier) always
-    // fit on the device TOGETHER, so neither can hold SMs the other one is waiting for
-    coresident = std::max(1, sms * std::max(1, std::min(per_sm, 2)));
+    if (staged) {
+      if (smem > 48 * 1024) RW_CUDA(cudaFuncSetAttribute(flat_exchange_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(FLAT_TILE * (1 + 8 * 12))));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_exchange_kernel<true>, PART_BLOCK, smem);
+    } else {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_exchange_kernel<false>, PART_BLOCK, 0);
+    }
+    cores = std::max(1, sms * std::max(1, std::min(per_sm, 6)));
   }
-  int grid = std::min(n_vblocks, coresident);
+  int grid = std::min(n_vblocks, cores);
   if (max_blocks > 0) grid = std::min(grid, (int)max_blocks);
   uint8_t* scratch = nullptr;
   size_t dest_bytes = ((size_t)c->n_rows + 255) / 256 * 256;
-  size_t hist_bytes = (size_t)n_vblocks * n_dest * 4;
-  RW_CUDA(cudaMallocAsync((void**)&scratch, dest_bytes + hist_bytes + 512, st));
+  size_t hist_bytes = ((size_t)n_vblocks * n_dest * 4 + 255) / 256 * 256;
+  RW_CUDA(cudaMallocAsync((void**)&scratch, dest_bytes + 2 * hist_bytes + 512, st));
   uint8_t* dest = scratch;
   uint32_t* hist = (uint32_t*)(scratch + dest_bytes);
-  unsigned int* bar = (unsigned int*)(scratch + dest_bytes + (hist_bytes + 255) / 256 * 256);
+  uint32_t* tcnt = (uint32_t*)(scratch + dest_bytes + hist_bytes);
+  unsigned int* bar = (unsigned int*)(scratch + dest_bytes + 2 * hist_bytes);
   RW_CUDA(cudaMemsetAsync(bar, 0, 4, st));
-  flat_exchange_kernel<<<grid, PART_BLOCK, 0, st>>>(ch, p, vnode_to_dest, n_dest, my_rank, L, pb, pf, (unsigned long long)epoch, dest, hist, n_vblocks,
-                                                    counts, total_dev, total_host, (int*)err, bar);
+  if (staged)
+    flat_exchange_kernel<true><<<grid, PART_BLOCK, smem, st>>>(ch, p, vnode_to_dest, n_dest, my_rank, L, pb, pf, (unsigned long long)epoch, dest, hist, tcnt,
+                                                               n_vblocks, counts, total_dev, total_host, (int*)err, bar);
+  else
+    flat_exchange_kernel<false><<<grid, PART_BLOCK, 0, st>>>(ch, p, vnode_to_dest, n_dest, my_rank, L, pb, pf, (unsigned long long)epoch, dest, hist, tcnt,
+                                                             n_vblocks, counts, total_dev, total_host, (int*)err, bar);
   RW_CUDA(cudaGetLastError());
   RW_CUDA(cudaFreeAsync(scratch, st));
   return RW_OK;

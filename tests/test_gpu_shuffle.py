@@ -377,8 +377,9 @@ def test_flat_exchange_virtual_ranks(cuda, oracle):
     import torch
     from risingwave_b200 import device, exchange
     rng = np.random.default_rng(21)
-    types = [abi.T_INT64, abi.T_INT64, abi.T_INT32]
-    for world, n in ((2, 70001), (4, 9000)):
+    # (int64 x3: the staged path -- tiles partitioned in shared memory, coalesced stores; with an int32 column: row by row)
+    for types, world, n in (([abi.T_INT64, abi.T_INT64, abi.T_INT32], 2, 70001), ([abi.T_INT64] * 3, 2, 70001), ([abi.T_INT64] * 3, 4, 9000),
+                            ([abi.T_INT64, abi.T_INT64, abi.T_INT32], 4, 9000)):
         cap = world * n
         bufs, flags, views = _flat_setup(world, types, cap)
         v2d = exchange.vnode_to_dest_table(world).cuda()
@@ -395,7 +396,7 @@ def test_flat_exchange_virtual_ranks(cuda, oracle):
                 if epoch == 2 and r == 0:
                     key[:] = 5  # one source sends everything to one destination
                 pay = np.arange(n, dtype=np.int64) + r * 10 ** 9 + epoch * 10 ** 7
-                small = rng.integers(0, 100, n).astype(np.int32)
+                small = rng.integers(0, 100, n).astype(np.int32 if types[2] == abi.T_INT32 else np.int64)
                 ops = rng.integers(1, 5, n).astype(np.uint8)
                 ops[rng.random(n) < 0.05] = 0
                 src.append((ops, [key, pay, small]))
