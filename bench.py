@@ -502,7 +502,8 @@ def run_ours(args):
             ex_plan = exchange.P2PShufflePlan(world, rank, key_indices=[0], types=T4, batch_rows=BATCH)
             ex_name = "crc32 vnode partition kernel storing straight into the peers' receive regions over NVLink (symmetric memory), device barrier, unpack kernel"
         else:
-            ex_plan = exchange.FlatShufflePlan(world, rank, key_indices=[0], types=T4, batch_rows=BATCH)
+            ex_plan = exchange.FlatShufflePlan(world, rank, key_indices=[0], types=T4, batch_rows=BATCH,
+                                               max_blocks=int(os.environ.get("RWGPU_EXCHANGE_BLOCKS", "0")))
             ex_name = ("one kernel per batch: crc32 vnode histograms, scan, count exchange + cross-rank barrier, scatter over NVLink "
                        "(symmetric memory) into the rows' final place in the destination's receive buffer, barrier; the join reads the buffer in place")
 
