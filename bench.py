@@ -556,7 +556,8 @@ def run_ours(args):
             t_ex = t_join = 0.0
             pending = {}
             lookahead = True
-            ex_stream = torch.cuda.Stream() if counted else None
+            # (BENCH_EX_PRIO=1: the exchange on a high-priority stream -- its blocks get the SM slots the join's kernel frees)
+            ex_stream = (torch.cuda.Stream(priority=-1) if os.environ.get("BENCH_EX_PRIO") else torch.cuda.Stream()) if counted else None
 
             join_done = {}
             keep = {}
