@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(PART_BLOCK) flat_exchange_kernel(DevChunk ch, 
                                                                     FlatLayout L, PeerBases peers, PeerBases flags, unsigned long long epoch,
                                                                     uint8_t* dest, uint32_t* block_hist, uint32_t* tile_cnt, int n_vblocks,
                                                                     int64_t* counts, int64_t* total_dev, int64_t* total_host, int* err,
-                                                                    unsigned int* bar) {
+                                                                    unsigned int* bar, int coop) {
   extern __shared__ __align__(16) uint8_t s_stage[];  // STAGED: ops[FLAT_TILE] | col k: u64[FLAT_TILE]
   __shared__ uint32_t tab[256];
   __shared__ uint32_t hist[PART_MAX_DEST];
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(PART_BLOCK) flat_exchange_kernel(DevChunk ch, 
     }
     __syncthreads();
   }
-  soft_grid_sync(bar, 1u);
+  if (coop) cooperative_groups::this_grid().sync(); else soft_grid_sync(bar, 1u);
   // ---- phase B (block 0): exclusive scan over the tiles per destination, count row to every rank, barrier 1
   if (blockIdx.x == 0) {
     for (int d = wid; d < n_dest; d += PART_BLOCK / 32) {
@@ -589,7 +589,7 @@ __global__ void __launch_bounds__(PART_BLOCK) flat_exchange_kernel(DevChunk ch, 
     __syncthreads();
     flat_barrier(flags, n_dest, my_rank, 2ull * epoch - 1ull, err);
   }
-  soft_grid_sync(bar, 2u);
+  if (coop) cooperative_groups::this_grid().sync(); else soft_grid_sync(bar, 2u);
   // ---- phase C: stable scatter into the final place
   {
     const volatile int64_t* M = (const volatile int64_t*)peers.base[my_rank];
@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(PART_BLOCK) flat_exchange_kernel(DevChunk ch, 
     }
   }
   __threadfence_system();
-  soft_grid_sync(bar, 3u);
+  if (coop) cooperative_groups::this_grid().sync(); else soft_grid_sync(bar, 3u);
   // ---- phase D (block 0): barrier 2, then the received row count for the consumer
   if (blockIdx.x == 0) {
     flat_barrier(flags, n_dest, my_rank, 2ull * epoch, err);
@@ -1021,12 +1021,19 @@ int32_t rwgpu_shuffle_exchange_flat_device(const rw_chunk* c, const int32_t* key
   uint32_t* tcnt = (uint32_t*)(scratch + dest_bytes + hist_bytes);
   unsigned int* bar = (unsigned int*)(scratch + dest_bytes + 2 * hist_bytes);
   RW_CUDA(cudaMemsetAsync(bar, 0, 4, st));
-  if (staged)
-    flat_exchange_kernel<true><<<grid, PART_BLOCK, smem, st>>>(ch, p, vnode_to_dest, n_dest, my_rank, L, pb, pf, (unsigned long long)epoch, dest, hist, tcnt,
-                                                               n_vblocks, counts, total_dev, total_host, (int*)err, bar);
-  else
-    flat_exchange_kernel<false><<<grid, PART_BLOCK, 0, st>>>(ch, p, vnode_to_dest, n_dest, my_rank, L, pb, pf, (unsigned long long)epoch, dest, hist, tcnt,
-                                                             n_vblocks, counts, total_dev, total_host, (int*)err, bar);
+  // RWGPU_EXCHANGE_COOP=1: cooperative launch (grid.sync()) instead of the software barriers -- the whole grid starts at
+  // once, which on the 2-GPU runs let the join's kernel fill in around it (profiles/README.md, multi-GPU table)
+  static const int coop = getenv("RWGPU_EXCHANGE_COOP") ? atoi(getenv("RWGPU_EXCHANGE_COOP")) : 0;
+  int coop_arg = coop;
+  unsigned long long ep = epoch;
+  int* errp = (int*)err;
+  int nvb = n_vblocks;
+  void* args[] = {(void*)&ch, (void*)&p, (void*)&vnode_to_dest, (void*)&n_dest, (void*)&my_rank, (void*)&L, (void*)&pb, (void*)&pf, (void*)&ep,
+                  (void*)&dest, (void*)&hist, (void*)&tcnt, (void*)&nvb, (void*)&counts, (void*)&total_dev, (void*)&total_host, (void*)&errp,
+                  (void*)&bar, (void*)&coop_arg};
+  const void* fn = staged ? (const void*)flat_exchange_kernel<true> : (const void*)flat_exchange_kernel<false>;
+  if (coop) RW_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(PART_BLOCK), args, smem, st));
+  else RW_CUDA(cudaLaunchKernel(fn, dim3(grid), dim3(PART_BLOCK), args, smem, st));
   RW_CUDA(cudaGetLastError());
   RW_CUDA(cudaFreeAsync(scratch, st));
   return RW_OK;
