@@ -995,7 +995,7 @@ int32_t rwgpu_shuffle_exchange_flat_device(const rw_chunk* c, const int32_t* key
   bool staged = c->n_cols <= 12;
   for (int k = 0; k < c->n_cols; k++) staged = staged && type_width(c->columns[k].type) == 8;
   const size_t smem = staged ? (size_t)FLAT_TILE * (1 + 8 * (size_t)c->n_cols) : 0;
-  // every block resident at once (the grid-wide barriers rely on it): occupancy x SMs, at most 6 blocks per SM
+  // every block resident at once (the grid-wide barriers rely on it): occupancy x SMs, at most 3 blocks per SM
   static int coresident[2][13] = {{0}};
   int& cores = coresident[staged ? 1 : 0][staged ? c->n_cols : 0];
   if (!cores) {
@@ -1008,7 +1008,8 @@ int32_t rwgpu_shuffle_exchange_flat_device(const rw_chunk* c, const int32_t* key
     } else {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flat_exchange_kernel<false>, PART_BLOCK, 0);
     }
-    cores = std::max(1, sms * std::max(1, std::min(per_sm, 6)));
+    // three blocks per SM: measured best next to the join's kernel at N=2 (profiles/README.md: 296 / 444 / 888 blocks)
+    cores = std::max(1, sms * std::max(1, std::min(per_sm, 3)));
   }
   int grid = std::min(n_vblocks, cores);
   if (max_blocks > 0) grid = std::min(grid, (int)max_blocks);
