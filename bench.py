@@ -808,6 +808,13 @@ def run_ours(args):
             EVERY output chunk view fetched and read -> release -- what the Rust shim does per message.  N>1: every rank
             runs its own caller on its own GPU and partition (as N independent shim instances would), started together."""
             exe = os.path.join(ROOT, "build", "e2e_caller")
+            if not os.path.exists(exe):  # (a snapshot without build/: the caller only needs g++ and the library)
+                if rank == 0:
+                    sys.path.insert(0, ROOT)
+                    import __graft_entry__
+                    __graft_entry__.build_e2e_caller()
+                if world > 1:
+                    dist.barrier()
             if not os.path.exists(exe):
                 raise RuntimeError("build/e2e_caller missing: run __graft_entry__.build()")
             env = dict(os.environ)
