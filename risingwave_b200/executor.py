@@ -17,6 +17,7 @@ INTEGRATION.md which forwards to the same C ABI (include/rwgpu.h).  All compute 
 from __future__ import annotations
 
 import ctypes as C
+import heapq
 import re
 from collections import deque
 from dataclasses import dataclass, field
@@ -354,6 +355,43 @@ def parse_cond(text: Optional[str]) -> Tuple[int, int, int]:
     return (_CMP[m.group(1)], int(m.group(2)), int(m.group(3)))
 
 
+class BufferedWatermarks:
+    """BufferedWatermarks<Id> (src/stream/src/executor/watermark/mod.rs:38-115): per upstream id the smallest buffered
+    watermark sits in a heap, the later ones are staged behind it; a watermark is emitted when EVERY upstream has one in
+    the heap (the smallest wins), and equal ones that follow are swallowed.  Watermarks order by value (mod.rs:1219-1222)
+    and compare equal on (col_idx, value)."""
+    MAX_STAGED = 1024
+
+    def __init__(self, ids: Sequence[int]):
+        self.first: List[Tuple[int, int, Watermark]] = []  # heap of (value, id, watermark)
+        self.staged = {i: [False, deque()] for i in sorted(ids)}  # id -> [in_heap, staged watermarks]
+
+    def handle_watermark(self, buffer_id: int, wm: Watermark) -> Optional[Watermark]:
+        st = self.staged[buffer_id]
+        if st[0]:
+            if len(st[1]) >= self.MAX_STAGED:
+                st[1].popleft()
+            st[1].append(wm)
+            return None
+        st[0] = True
+        heapq.heappush(self.first, (wm.val, buffer_id, wm))
+        return self.check_watermark_heap()
+
+    def check_watermark_heap(self) -> Optional[Watermark]:
+        n, emit = len(self.staged), None
+        while self.first and (len(self.first) == n or (emit is not None and (emit.col_idx, emit.val) ==
+                                                       (self.first[0][2].col_idx, self.first[0][2].val))):
+            _, i, wm = heapq.heappop(self.first)
+            emit = wm
+            st = self.staged[i]
+            if st[1]:
+                nxt = st[1].popleft()
+                heapq.heappush(self.first, (nxt.val, i, nxt))
+            else:
+                st[0] = False
+        return emit
+
+
 class HashJoinExecutor:
     """Mirror of HashJoinExecutor<K,S,T,E>::new (hash_join.rs:255-301)."""
 
@@ -361,9 +399,10 @@ class HashJoinExecutor:
                  params_l: JoinParams, params_r: JoinParams, null_safe: Sequence[bool],
                  output_indices: Optional[Sequence[int]] = None, cond: Optional[str] = None,
                  is_append_only: bool = False, chunk_size: int = 1024, strict_consistency: bool = True,
-                 capacity_hint=0, stored_rows_hint=0):
+                 capacity_hint=0, stored_rows_hint=0, watermark_indices_in_jk: Sequence[Tuple[int, bool]] = ()):
         """capacity_hint: expected distinct join keys (one number or (left, right)); stored_rows_hint: expected rows stored
-        per side (same shapes; 0 = two per expected key)"""
+        per side (same shapes; 0 = two per expected key); watermark_indices_in_jk: (join key position, clean state?) pairs
+        as in HashJoinExecutor::new (hash_join.rs:255-301)"""
         self.backend = backend
         self.input_l, self.input_r = input_l, input_r
         self._keep = []
@@ -411,12 +450,48 @@ class HashJoinExecutor:
         backend.check(backend._join_create(C.byref(d), C.byref(h)))
         self._h = h
         self.schema = [nat[i] for i in output_indices]
+        # watermark handling (hash_join.rs:791-891): i2o_mapping_indexed per side (input column -> output positions)
+        n_l = len(input_l.schema)
+        semi_l = join_type in (abi.JOIN_LEFT_SEMI, abi.JOIN_LEFT_ANTI)
+        semi_r = join_type in (abi.JOIN_RIGHT_SEMI, abi.JOIN_RIGHT_ANTI)
+        self._i2o = ({}, {})
+        for o, i in enumerate(output_indices):
+            if semi_l or (not semi_r and i < n_l):
+                self._i2o[0].setdefault(i, []).append(o)
+            else:
+                self._i2o[1].setdefault(i if semi_r else i - n_l, []).append(o)
+        self._jk = (list(params_l.join_key_indices), list(params_r.join_key_indices))
+        self._wm_in_jk = list(watermark_indices_in_jk)
+        self._wm_buffers = {}
 
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
             self.backend._join_destroy(h)
             self._h = None
+
+    def handle_watermark(self, side: int, wm: Watermark) -> List[Watermark]:
+        """HashJoinExecutor::handle_watermark, the join-key part (hash_join.rs:791-842): a watermark on a join key column
+        is buffered per join key position; what BOTH sides have passed is emitted for every output column fed by that
+        key on either side (the update side's first), and -- where the plan asks for it -- both sides' state is cleaned
+        below it (JoinHashMap::update_watermark = rwgpu_join_update_watermark, applied at the next barrier).  Inequality
+        pairs (:844-889) stay with the CPU executor: their `cond` is not offloaded either."""
+        out: List[Watermark] = []
+        upd, mat = side, 1 - side
+        for idx, col in enumerate(self._jk[upd]):
+            if col != wm.col_idx:
+                continue
+            buf = self._wm_buffers.setdefault(idx, BufferedWatermarks([abi.SIDE_LEFT, abi.SIDE_RIGHT]))
+            sel = buf.handle_watermark(side, wm)
+            if sel is None:
+                continue
+            if any(p == idx and clean for p, clean in self._wm_in_jk) and hasattr(self.backend.lib, "rwgpu_join_update_watermark") \
+                    and self.backend.prefix == "rwgpu_":
+                self.update_watermark(mat, idx, sel.val)
+                self.update_watermark(upd, idx, sel.val)
+            for o in self._i2o[upd].get(self._jk[upd][idx], []) + self._i2o[mat].get(self._jk[mat][idx], []):
+                out.append(Watermark(o, sel.data_type, sel.val))
+        return out
 
     # direct operator calls (what the Rust shim would issue)
     def eq_join_oneside(self, side: int, chunk: StreamChunk) -> List[StreamChunk]:
@@ -498,8 +573,9 @@ class HashJoinExecutor:
                         blocked = [None, None]
                         self.flush_data(b.epoch)
                         yield Message(barrier=b)
-                else:
-                    pass  # watermark state cleaning stays on the CPU executor (hash_join.rs:791-891)
+                else:  # AlignedMessage::WatermarkLeft / WatermarkRight (hash_join.rs:711-722)
+                    for w in self.handle_watermark(s, m.watermark):
+                        yield Message(watermark=w)
                 break
             if not progressed:
                 yield PENDING

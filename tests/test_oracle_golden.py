@@ -267,3 +267,38 @@ def test_tpch_q3_pipeline_oracle(oracle):
     from helpers import run_tpch_q3
     got, deltas = run_tpch_q3(oracle)
     assert len(got) > 50 and any(op == abi.OP_UPDATE_DELETE for d in deltas for (op, _, _) in d)
+
+
+def test_streaming_hash_join_watermark(oracle):
+    """hash_join.rs:3648-3715 `test_streaming_hash_join_watermark`, transcribed: watermarks on the join key are buffered per
+    side (BufferedWatermarks, watermark/mod.rs:38-115); what both sides have passed is emitted for the output columns of
+    the key, the update side's first.  (create_classical_executor: two int64 columns per side, key = column 0.)"""
+    from risingwave_b200.executor import BufferedWatermarks, HashJoinExecutor, JoinParams, MockSource, Watermark
+    I = abi.T_INT64
+    tx_l, sl = MockSource.channel()
+    tx_r, sr = MockSource.channel()
+    ex = HashJoinExecutor(oracle, abi.JOIN_INNER, sl.into_executor([I, I], [1]), sr.into_executor([I, I], [1]),
+                          JoinParams([0], [1]), JoinParams([0], [1]), [False], watermark_indices_in_jk=[(0, True)])
+    st = ex.execute()
+    tx_l.push_barrier(1, False)
+    tx_r.push_barrier(1, False)
+    st.next_unwrap_ready_barrier()
+    tx_l.push_watermark(0, I, 100)
+    tx_l.push_watermark(0, I, 200)
+    tx_l.push_barrier(2, False)
+    tx_r.push_barrier(2, False)
+    got = st.drain_until_pending()
+    assert [m.barrier.epoch for m in got if m.barrier] == [2] and not any(m.watermark for m in got)
+    tx_r.push_watermark(0, I, 50)
+    w1, w2 = st.next_unwrap_ready_watermark(), st.next_unwrap_ready_watermark()
+    tx_r.push_watermark(0, I, 100)
+    w3, w4 = st.next_unwrap_ready_watermark(), st.next_unwrap_ready_watermark()
+    assert (w1, w2, w3, w4) == (Watermark(2, I, 50), Watermark(0, I, 50), Watermark(2, I, 100), Watermark(0, I, 100))
+    st.next_unwrap_pending()
+    # BufferedWatermarks on its own: three upstreams, the smallest of the heads wins, equal followers are swallowed
+    b = BufferedWatermarks([0, 1, 2])
+    assert b.handle_watermark(0, Watermark(0, I, 7)) is None
+    assert b.handle_watermark(1, Watermark(0, I, 5)) is None
+    assert b.handle_watermark(1, Watermark(0, I, 9)) is None
+    assert b.handle_watermark(2, Watermark(0, I, 5)) == Watermark(0, I, 5)   # 5 (id 1), then the equal 5 of id 2
+    assert b.handle_watermark(2, Watermark(0, I, 8)) == Watermark(0, I, 7)   # heads now 7, 9, 8
