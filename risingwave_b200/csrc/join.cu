@@ -118,7 +118,7 @@ struct JoinStatus {
   unsigned long long n_in;       // rows of the input chunk as the kernel saw them (device-resident row count)
   unsigned long long log_next[2];  // unified table: log ids handed out per side (copied from the device counters)
   unsigned long long n_dead[2];    // unified table: dead log records per side
-  unsigned long long n_defer;      // unified table: != 0 when the hot kernel deferred rows to uni_deferred_kernel
+  unsigned long long n_defer;      // unified table: bit 0 = the hot kernel deferred rows to the tail kernel, bit 1 = some are whole (sentinel-key) rows
 };
 
 struct JoinOutDev {

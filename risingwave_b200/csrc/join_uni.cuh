@@ -291,7 +291,7 @@ __device__ __forceinline__ ulonglong2 ld128_cg(const void* ptr) { return __ldcg(
 // The kernel body holds ONLY the common case.  Rows it cannot finish with the quad -- several matches, a match
 // that is not the bucket's inline record, NULLs in the matched record, the key equal to the EMPTY sentinel, every
 // row of the inline side (its matches live in a chain) -- are DEFERRED: the quad records (bucket, match count,
-// reserved extra rows) in the row's worklist entry and sets the row's bit; uni_deferred_kernel, launched right
+// reserved extra rows) in the row's worklist entry and sets the row's bit; phase 1 of uni_tail_kernel, launched right
 // behind, finishes them one thread per row.  (With those paths inlined the hot loop spilled ~350 bytes.)
 struct PlainChunk {      // a chunk without bitmaps, 8-byte columns
   const uint8_t* ops;
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(JF_BLOCK, MINB) uni_hot_kernel(PlainChunk ch, 
       if (po0) po0[pos] = q < 2 ? va : pv.x;
       if (po1) po1[pos] = q < 2 ? vb : pv.y;
     } else if (in && q == 0) {
-      // deferred rows get their visibility from uni_deferred_kernel; the others are holes
+      // deferred rows get their visibility from uni_tail_kernel's deferred phase; the others are holes
       if (!(act && (!keyok || cnt > 0u))) { o.vis[pos] = 0; any_hole = true; }
     }
     const bool defer = act && !fast && (!keyok || cnt > 0u);
