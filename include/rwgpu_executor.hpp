@@ -12,6 +12,7 @@
 // Errors: a non-zero ABI status becomes a StreamExecutorError exception (the Rust shim maps it to
 // `StreamExecutorResult::Err`, which terminates the actor; src/stream/src/executor/error.rs).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <deque>
@@ -337,6 +338,49 @@ class FilterExecutor : public Execute {
   bool upsert_;
 };
 
+// ------------------------------------------------------------------------------------ watermarks
+// BufferedWatermarks<Id> (src/stream/src/executor/watermark/mod.rs:38-115): per upstream id the smallest buffered
+// watermark sits in a heap, later ones are staged behind it; a watermark is emitted when EVERY upstream has one in the
+// heap (the smallest wins) and equal ones that follow are swallowed.  Order by value (mod.rs:1219-1222), equality on
+// (col_idx, value).
+class BufferedWatermarks {
+ public:
+  explicit BufferedWatermarks(std::vector<int> ids) { for (int i : ids) staged_[i]; }
+  std::optional<Watermark> handle_watermark(int id, const Watermark& wm) {
+    Staged& st = staged_.at(id);
+    if (st.in_heap) {
+      if (st.q.size() >= 1024) st.q.pop_front();
+      st.q.push_back(wm);
+      return std::nullopt;
+    }
+    st.in_heap = true;
+    push(wm, id);
+    return check_watermark_heap();
+  }
+  std::optional<Watermark> check_watermark_heap() {
+    std::optional<Watermark> emit;
+    while (!heap_.empty() && (heap_.size() == staged_.size() ||
+                              (emit && emit->col_idx == heap_.front().wm.col_idx && emit->val == heap_.front().wm.val))) {
+      std::pop_heap(heap_.begin(), heap_.end(), later);
+      Entry e = heap_.back();
+      heap_.pop_back();
+      emit = e.wm;
+      Staged& st = staged_.at(e.id);
+      if (!st.q.empty()) { push(st.q.front(), e.id); st.q.pop_front(); }
+      else st.in_heap = false;
+    }
+    return emit;
+  }
+
+ private:
+  struct Entry { Watermark wm; int id; };
+  struct Staged { bool in_heap = false; std::deque<Watermark> q; };
+  static bool later(const Entry& a, const Entry& b) { return a.wm.val != b.wm.val ? a.wm.val > b.wm.val : a.id > b.id; }  // min-heap
+  void push(const Watermark& wm, int id) { heap_.push_back(Entry{wm, id}); std::push_heap(heap_.begin(), heap_.end(), later); }
+  std::vector<Entry> heap_;
+  std::map<int, Staged> staged_;
+};
+
 // ------------------------------------------------------------------------------------ HashJoin
 struct JoinParams { std::vector<int32_t> join_key_indices, deduped_pk_indices; };
 
@@ -344,8 +388,9 @@ class HashJoinExecutor : public Execute {
  public:
   HashJoinExecutor(int32_t join_type, std::shared_ptr<Execute> input_l, std::shared_ptr<Execute> input_r, JoinParams params_l,
                    JoinParams params_r, std::vector<uint8_t> null_safe, std::vector<int32_t> output_indices = {},
-                   rw_join_cond cond = rw_join_cond{RW_CMP_NONE, 0, 0, 0}, bool is_append_only = false, int32_t chunk_size = 1024)
-      : in_{std::move(input_l), std::move(input_r)} {
+                   rw_join_cond cond = rw_join_cond{RW_CMP_NONE, 0, 0, 0}, bool is_append_only = false, int32_t chunk_size = 1024,
+                   std::vector<std::pair<int, bool>> watermark_indices_in_jk = {})
+      : in_{std::move(input_l), std::move(input_r)}, wm_in_jk_(std::move(watermark_indices_in_jk)) {
     std::vector<int32_t> nat;
     if (join_type == RW_JOIN_LEFT_SEMI || join_type == RW_JOIN_LEFT_ANTI) nat = in_[0]->schema();
     else if (join_type == RW_JOIN_RIGHT_SEMI || join_type == RW_JOIN_RIGHT_ANTI) nat = in_[1]->schema();
@@ -374,6 +419,41 @@ class HashJoinExecutor : public Execute {
     d.strict_consistency = 1;
     check(rwgpu_join_create(&d, &h_));
     for (int32_t i : output_indices) schema_.push_back(nat[i]);
+    // i2o_mapping_indexed per side (input column -> output positions), for the watermarks
+    const int32_t n_l = (int32_t)in_[0]->schema().size();
+    const bool semi_l = join_type == RW_JOIN_LEFT_SEMI || join_type == RW_JOIN_LEFT_ANTI;
+    const bool semi_r = join_type == RW_JOIN_RIGHT_SEMI || join_type == RW_JOIN_RIGHT_ANTI;
+    for (size_t o = 0; o < output_indices.size(); o++) {
+      const int32_t i = output_indices[o];
+      if (semi_l || (!semi_r && i < n_l)) i2o_[0][i].push_back((int32_t)o);
+      else i2o_[1][semi_r ? i : i - n_l].push_back((int32_t)o);
+    }
+    jk_[0] = params_l.join_key_indices;
+    jk_[1] = params_r.join_key_indices;
+  }
+  // HashJoinExecutor::handle_watermark, the join-key part (hash_join.rs:791-842); inequality pairs stay on the CPU executor
+  std::vector<Watermark> handle_watermark(int side, const Watermark& wm) {
+    std::vector<Watermark> out;
+    const int upd = side, mat = 1 - side;
+    for (size_t idx = 0; idx < jk_[upd].size(); idx++) {
+      if (jk_[upd][idx] != wm.col_idx) continue;
+      auto it = wm_buffers_.find((int)idx);
+      if (it == wm_buffers_.end()) it = wm_buffers_.emplace((int)idx, BufferedWatermarks({RW_SIDE_LEFT, RW_SIDE_RIGHT})).first;
+      auto sel = it->second.handle_watermark(side, wm);
+      if (!sel) continue;
+      for (auto& pc : wm_in_jk_)
+        if (pc.first == (int)idx && pc.second) {  // JoinHashMap::update_watermark on both sides, applied at the next barrier
+          check(rwgpu_join_update_watermark(h_, mat, (int32_t)idx, sel->val));
+          check(rwgpu_join_update_watermark(h_, upd, (int32_t)idx, sel->val));
+          break;
+        }
+      for (int s2 : {upd, mat}) {
+        auto f = i2o_[s2].find(jk_[s2][idx]);
+        if (f == i2o_[s2].end()) continue;
+        for (int32_t o : f->second) out.push_back(Watermark{o, sel->data_type, sel->val});
+      }
+    }
+    return out;
   }
   ~HashJoinExecutor() override { rwgpu_join_destroy(h_); }
   // into_stream over barrier_align: a side that delivered its barrier is blocked until the other
@@ -401,7 +481,9 @@ class HashJoinExecutor : public Execute {
             check(rwgpu_join_barrier(h_, bar.epoch));
             pending_.emplace_back(bar);
           }
-        }  // watermark state cleaning stays on the CPU executor (hash_join.rs:791-891)
+        } else if (auto* w = std::get_if<Watermark>(&*m)) {  // AlignedMessage::WatermarkLeft / Right (hash_join.rs:711-722)
+          for (auto& o : handle_watermark(s, *w)) pending_.emplace_back(o);
+        }
       }
       if (!progressed && pending_.empty()) return std::nullopt;
     }
@@ -415,6 +497,10 @@ class HashJoinExecutor : public Execute {
   std::optional<Barrier> blocked_[2];
   std::deque<Message> pending_;
   std::vector<int32_t> schema_, key_;
+  std::vector<std::pair<int, bool>> wm_in_jk_;
+  std::map<int32_t, std::vector<int32_t>> i2o_[2];
+  std::vector<int32_t> jk_[2];
+  std::map<int, BufferedWatermarks> wm_buffers_;
 };
 
 }  // namespace rwgpu

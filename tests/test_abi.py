@@ -52,3 +52,15 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "liboracle" not in txt and "rwo_" not in txt and "oracle/" not in txt, f
+
+
+def test_cpp_host_mirror_watermark_buffers():
+    """include/rwgpu_executor.hpp BufferedWatermarks (CPU-only binary built by __graft_entry__.build()): the traces of the
+    reference's test_streaming_hash_join_watermark and a three-upstream case"""
+    import subprocess
+    exe = os.path.join(ROOT, "build", "test_watermarks")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "watermarks: ok" in r.stdout, r.stdout + r.stderr
