@@ -64,3 +64,27 @@ def test_cpp_host_mirror_watermark_buffers():
         __graft_entry__.build()
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "watermarks: ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_flat_exchange_layout_host_side():
+    """rwgpu_shuffle_flat_layout (host arithmetic only): header of 64 x 64 int64 counts, then ops and the columns, every part
+    256-byte aligned and large enough for cap rows; varlen columns are refused"""
+    lib = abi.load_library()
+    lib.rwgpu_shuffle_flat_layout.restype = ctypes.c_int32
+    lib.rwgpu_shuffle_flat_layout.argtypes = [ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_int64, ctypes.POINTER(ctypes.c_int64),
+                                              ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
+    for types, cap in (([abi.T_INT64] * 4, 1 << 20), ([abi.T_INT64, abi.T_INT32, abi.T_INT16, abi.T_DECIMAL], 1000), ([abi.T_BOOL], 7)):
+        t = (ctypes.c_int32 * len(types))(*types)
+        total, ops_off = ctypes.c_int64(), ctypes.c_int64()
+        col_off = (ctypes.c_int64 * len(types))()
+        assert lib.rwgpu_shuffle_flat_layout(t, len(types), cap, ctypes.byref(total), ctypes.byref(ops_off), col_off) == abi.RW_OK
+        assert ops_off.value == 64 * 64 * 8
+        prev_end = ops_off.value + cap
+        for k, ty in enumerate(types):
+            assert col_off[k] % 256 == 0 and col_off[k] >= prev_end
+            prev_end = col_off[k] + cap * abi.TYPE_WIDTH[ty]
+        assert total.value >= prev_end and total.value % 256 == 0
+    t = (ctypes.c_int32 * 1)(abi.T_VARCHAR)
+    total, ops_off = ctypes.c_int64(), ctypes.c_int64()
+    col_off = (ctypes.c_int64 * 1)()
+    assert lib.rwgpu_shuffle_flat_layout(t, 1, 10, ctypes.byref(total), ctypes.byref(ops_off), col_off) != abi.RW_OK
