@@ -1934,8 +1934,9 @@ static int join_grow_store(rwgpu_join* h, int S, uint64_t rows) {
       rc = s.log.ensure(rows, h->last_st ? h->last_st : h->stream);
       s.row_cap = s.log.cap();
     }
-    // less than one segment of headroom left: have the next one allocated in the background
-    if (rc == RW_OK && !s.log.segs.empty() && rows + U_SEG_RECS > s.log.cap()) s.log.prefetch();
+    // less than one segment of headroom left in a log that is at least half full: have the next segment allocated in the
+    // background (a fresh single-segment log of a small operator never asks for a spare)
+    if (rc == RW_OK && !s.log.segs.empty() && rows + U_SEG_RECS > s.log.cap() && rows * 2 > s.log.cap()) s.log.prefetch();
     return rc;
   }
   if (rows <= s.row_cap) return RW_OK;
