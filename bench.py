@@ -552,7 +552,15 @@ def run_ours(args):
             trace = os.environ.get("BENCH_TRACE") is not None  # per-phase wall clock (adds syncs: never for a reported number)
 
             counted = world > 1 and isinstance(ex_plan, (exchange.P2PShufflePlan, exchange.FlatShufflePlan))
-            recv_chunks = [device.DeviceChunk(*ex_plan.output(b), T4) for b in range(2)] if counted else None
+            # the join sizes its bookkeeping (row-id and key upper bounds, output area) for the CAPACITY of a counted push; a
+            # rank receives ~BATCH rows per step, so the view handed to the join covers min(world, 4) x BATCH rows of the
+            # world x BATCH receive buffer (a step with more rows than that fails loudly: JERR_BAD_COUNT)
+            def recv_view(b):
+                ops_b, cols_b = ex_plan.output(b)
+                m = min(ops_b.numel(), min(world, 4) * BATCH)
+                return device.DeviceChunk(ops_b[:m], [c[:m] for c in cols_b], T4)
+
+            recv_chunks = [recv_view(b) for b in range(2)] if counted else None
             t_ex = t_join = 0.0
             pending = {}
             lookahead = True
