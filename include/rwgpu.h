@@ -403,6 +403,9 @@ int32_t rwgpu_shuffle_exchange_p2p_device(const rw_chunk* chunk, const int32_t* 
  *   err        : DEVICE int32, bit 0 = a destination buffer was too small, bit 1 = a peer did not reach the barrier
  *                within ~10 s (the count then reads -1)
  *   max_blocks : 0 = as many blocks as are co-resident; > 0 caps the grid (several ranks sharing one device in tests)
+ * The kernel meets in grid-wide barriers of its own (plain launch, grid sized to be resident: at most three blocks per SM),
+ * so at most TWO exchange launches may be in flight on one device at a time (different plans on different streams); a third
+ * could keep the others' remaining blocks off the SMs.
  * Caller contract: batch e is launched after this rank's consumer of batch e - 2 (same buffer) has finished; that is
  * all the cross-rank ordering needed -- a peer writes into the buffer only after barrier 1 of batch e, which this
  * rank enters inside its own launch.  Replaces dispatch.rs:961-1053 + the exchange channel + merge for N GPUs.     */
